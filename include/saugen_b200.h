@@ -1,0 +1,117 @@
+/* include/saugen_b200.h -- C ABI of the B200-native saugns generator back end.
+ *
+ * Plain pointers and sizes only; no torch / C++ types.  The three core entry
+ * points replace, one for one, the reference generator interface
+ *   sau_create_Generator   sau/generator.h:20-21   (sau/generator.c:200-217)
+ *   sauGenerator_run       sau/generator.h:24-26   (sau/generator.c:905-973)
+ *   sau_destroy_Generator  sau/generator.h:22      (sau/generator.c:222-228)
+ * and saugns_b200/csrc/dropin.c re-exports them under the reference's own
+ * symbol names so that the unmodified CLI (saugns.c:575-623) links against
+ * this library instead of generator.o.
+ *
+ * All rendering happens in hand-written sm_100a CUDA kernels.  There is no
+ * CPU fallback: every entry point fails (NULL / negative return) when no CUDA
+ * device is usable.
+ */
+#ifndef SAUGEN_B200_H
+#define SAUGEN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+#include "sau_program_abi.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct saugen_Generator saugen_Generator;
+
+/* The 12 pre-integrated wave tables + per-wave coefficients, as built on the
+ * host by the front-end library (sau/wave.c:49-66,105-221; sau/wave.h:33-70).
+ * The drop-in passes libsau's own arrays; NULL selects the built-in tables
+ * (saugns_b200/csrc/wavetab.cpp). */
+typedef struct saugen_WaveTables {
+	const float *pilut[SAUABI_WAVE_NAMED];   /* 2048 floats each */
+	float amp_scale[SAUABI_WAVE_NAMED];
+	float amp_dc[SAUABI_WAVE_NAMED];
+	int32_t phase_adj[SAUABI_WAVE_NAMED];
+} saugen_WaveTables;
+
+const saugen_WaveTables *saugen_builtin_wave_tables(void);
+
+/* Creation options (zero-initialise for defaults). */
+typedef struct saugen_Options {
+	int device;              /* CUDA device ordinal */
+	void *stream;            /* cudaStream_t to launch on; NULL = own stream */
+	uint32_t voice_begin;    /* render only voices [voice_begin, voice_end) ... */
+	uint32_t voice_end;      /* ... 0,0 = all (multi-GPU voice sharding) */
+	uint32_t max_call_len;   /* largest buf_len that will be passed; 0 = 256 ms */
+} saugen_Options;
+
+/* == sau_create_Generator(prg, srate).  Borrows `prg` until destroy. */
+saugen_Generator *saugen_create(const sauabi_Program *prg, uint32_t srate,
+		const saugen_WaveTables *tables, const saugen_Options *opt);
+
+/* == sau_destroy_Generator(o); NULL-safe. */
+void saugen_destroy(saugen_Generator *o);
+
+/* == sauGenerator_run(o, buf, buf_len, stereo, out_len) with HOST buffers:
+ * launches the kernels, copies the PCM back, returns 1 while more signal
+ * follows, 0 on the final call, <0 on CUDA error (out_len = 0). */
+int saugen_run(saugen_Generator *o, int16_t *buf, size_t buf_len, int stereo,
+		size_t *out_len);
+
+/* Same call with the PCM left in device memory (*dev_pcm, valid until the
+ * next call on this generator).  Only a 32-byte status record crosses PCIe. */
+int saugen_run_device(saugen_Generator *o, size_t buf_len, int stereo,
+		int16_t **dev_pcm, size_t *out_len);
+
+/* Batched form (SURVEY.md section 8b "batch gap"): advance n independent
+ * generators by one call each with ONE pair of kernel launches.  bufs[i] may
+ * be NULL (device-resident).  more[i] receives each generator's return. */
+int saugen_run_many(saugen_Generator *const *gens, size_t n, int16_t *const *bufs,
+		size_t buf_len, int stereo, size_t *out_lens, int *more);
+
+/* Voice-sharded rendering across GPUs: produce this rank's partial float mix
+ * (2 x buf_len floats, L then R planes) in device memory; the caller reduces
+ * the planes over ranks (NCCL sum) and converts on the root. */
+int saugen_run_mix(saugen_Generator *o, size_t buf_len, float **dev_mix,
+		size_t *out_len);
+int saugen_mix_to_pcm(saugen_Generator *o, const float *dev_mix, size_t buf_len,
+		int stereo, int16_t *host_buf);
+
+/* ---- introspection for parity tests ------------------------------------ */
+
+typedef struct saugen_LineView {
+	float v0, vt;
+	uint32_t pos, end;
+	uint32_t type, flags;
+} saugen_LineView;
+
+/* Same field meaning as oracle/ref_harness.c:RefOpState. */
+typedef struct saugen_OpView {
+	uint32_t inited, type, flags, time;
+	saugen_LineView amp, amp2, pan, freq, freq2, pm_a;
+	uint32_t i0, i1;
+	uint32_t mode, oscflags;
+	double prev_Is;
+	float prev_s, fb_s;
+	uint32_t alpha, rate2x;
+} saugen_OpView;
+
+int saugen_read_op(saugen_Generator *o, uint32_t op_id, saugen_OpView *out);
+int saugen_read_voice(saugen_Generator *o, uint32_t vo_id, uint32_t out[4]);
+/* Float carrier rows (s = carrier*amp_scale, r = s*pan) written by the last
+ * call for one voice: n = frames of that call. */
+int saugen_read_voice_rows(saugen_Generator *o, uint32_t vo_id, float *s, float *r,
+		size_t n);
+/* Counters: [0] render launches, [1] mix launches, [2] voice-chunks rendered */
+int saugen_counters(saugen_Generator *o, uint64_t out[4]);
+float saugen_amp_scale(saugen_Generator *o);
+const char *saugen_last_error(void);
+int saugen_device_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,169 @@
+/* device_types.h -- data layout in HBM shared by the host runtime and the
+ * sm_100a kernels.  Everything the generator needs at run time lives in
+ * device memory: per-operator state (mirrors OperatorNode, reference
+ * sau/generator.c:45-88), per-voice state (VoiceNode, :97-102), the flattened
+ * event / op-data records (sau/program.h:212-241) and the per-voice bytecode
+ * the host compiles from the modulator lists.
+ */
+#pragma once
+#include <stdint.h>
+
+namespace saugen {
+
+constexpr int CHUNK = 128;            // samples per interpreter pass (4 per lane)
+constexpr int SPL = CHUNK / 32;       // consecutive samples owned by one lane
+constexpr int REF_BLOCK = 1024;       // BUF_LEN, sau/generator.c:28
+constexpr int WAVE_LEN = 2048;        // sau/wave.h:18-19
+constexpr int NUM_WAVES = 12;
+constexpr int MAX_NEST = 24;          // len-stack depth per warp
+constexpr uint32_t NO_BUF = 0xFF;
+
+/* sauLine run-time state (sau/line.h:115-121 minus time_ms). */
+struct LineState {
+	float v0, vt;
+	uint32_t pos, end;
+	uint8_t type, flags;
+	uint16_t _pad;
+};
+
+enum { LINE_AMP = 0, LINE_AMP2, LINE_PAN, LINE_FREQ, LINE_FREQ2, LINE_PMA, LINE_COUNT };
+
+/* Operator node flags (sau/generator.c:39-43) + ours. */
+enum {
+	ON_INIT      = 1 << 0,
+	ON_TIME_INF  = 1 << 2,
+	ON_PMA_RUN   = 1 << 4,   // pm_a line is being run for the current REF_BLOCK
+};
+enum { OSC_RESET_DIFF = 1 << 0 };   // sau/generator/wosc.h:37-38
+
+struct OpState {
+	uint32_t time;
+	uint8_t type;          // SAUABI_POPT_*
+	uint8_t flags;         // ON_*
+	uint8_t mode;          // W: wave, N: noise type, R: line type
+	uint8_t oscflags;      // W: OSC_RESET_DIFF, R: bit0 = rate2x
+	LineState line[LINE_COUNT];
+	/* W: phasor.phase / prev_phase; N: n / prev; R: cycle_phase lo / hi */
+	uint32_t i0, i1;
+	double prev_Is;
+	float prev_s, fb_s;
+	/* R options (sau/program.h:126-132) */
+	uint16_t ras_flags;
+	uint8_t ras_func, ras_level;
+	uint32_t ras_alpha;
+};
+
+enum { VN_INIT = 1 << 0 };
+struct VoiceState {
+	uint32_t duration;
+	uint32_t carr_op;
+	uint32_t flags;
+	uint32_t ev_cursor;    // next entry of this voice's event list
+	uint32_t code_off;     // current program (offset into GenDesc::code)
+	uint32_t code_len;
+};
+
+/* Flattened sauLine delta carried by an event (NULL pointer => present = 0). */
+struct LineDelta {
+	float v0, vt;
+	uint32_t end_samples;  // sau_ms_in_samples(time_ms, srate, NULL)
+	uint8_t type, flags, present, _pad;
+};
+
+struct OpDataRec {
+	uint32_t id;
+	uint32_t params;
+	uint32_t time_samples;
+	uint8_t time_flags;
+	uint8_t type;
+	uint8_t use_type;
+	uint8_t mode_main;
+	LineDelta line[LINE_COUNT];
+	uint32_t phase, seed;
+	uint16_t ras_flags;
+	uint8_t ras_func, ras_level;
+	uint32_t ras_alpha;
+};
+
+struct EventRec {
+	uint32_t vo_id;
+	uint32_t carr_op_id;
+	uint32_t opdata_off, opdata_count;
+	uint32_t code_off, code_len;    // voice program after this event
+};
+
+/* Bytecode: the reference's recursive run_block walk (sau/generator.c:448-729)
+ * flattened per voice.  a..e are work-buffer slots (gen_bufs indices). */
+enum Opcode : uint8_t {
+	I_ENTER = 1,   // op; a=out; flags: layer bits
+	I_LEAVE,       // op; a=out
+	I_ZERO,        // a=out (circular reference guard, generator.c:685-689)
+	I_LINE,        // op; a=dst; b=mulbuf|NO_BUF; c=which line; d=1 run / 0 skip
+	I_RANGE,       // a=par; b=r_par; c=mod   (generator.c:465-467)
+	I_PHASOR,      // op; a=phase dst; b=freq; c=pm|NO_BUF; d=fpm|NO_BUF
+	I_PMA,         // op; a=dst  (generator.c:485-490)
+	I_WOSC,        // op; a=dst; b=phase; c=pm_a buf; flags HAS_APMODS
+	I_CYCLOR,      // op; a=cycle dst; b=phase(float) dst; c=freq; d=pm; e=fpm
+	I_RASG,        // op; a=in/out; b=cycle; c=pm_a buf; d,e=tmp; flags HAS_APMODS
+	I_NOISE,       // op; a=dst
+	I_MIX,         // a=out; b=in|NO_BUF(=1.0); c=amp; flags WAVEENV
+	I_VPAN,        // op=carrier; a=pan dst; d=1 run (camods) / 0 decide at run time
+	I_VOUT,        // op=carrier; a=carrier out; b=pan buf
+	I_END
+};
+enum {
+	F_LAYER       = 1 << 0,   // accumulate into out
+	F_LAYER_PMA   = 1 << 1,   // layer = "pm_a buffer already filled" (run time)
+	F_WAVEENV     = 1 << 2,
+	F_HAS_APMODS  = 1 << 3,
+	F_HAS_CAMODS  = 1 << 4,
+};
+struct Instr {
+	uint8_t opcode, a, b, c, d, e;
+	uint16_t flags;
+	uint32_t op;
+};
+
+/* One generator's device-resident description. */
+struct GenDesc {
+	OpState *ops;
+	VoiceState *voices;
+	const EventRec *events;
+	const OpDataRec *opdata;
+	const Instr *code;
+	const uint32_t *vev_off;      // [vo_count+1] CSR into vev_idx
+	const uint32_t *vev_idx;      // global event indices per voice, in order
+	float *rows_s, *rows_r;       // [n_local_voices][row_len] carrier rows of a call
+	uint32_t *vlen;               // [max_segs][n_local_voices] frames run per segment
+	uint32_t *status;             // [0]=any voice still alive, [1..]=per-segment max len
+	float *mix;                   // [2][row_len] float mix planes (L, R)
+	int16_t *pcm;                 // [row_len*2]
+	uint32_t vo_count, op_count;
+	uint32_t voice_begin, voice_end;
+	uint32_t row_len;             // frames per row (max call length)
+	uint32_t nbufs;               // work buffers per voice warp
+	uint32_t srate;
+	float coeff;                  // (float)(2^32 / srate), wosc.h:30, rasg.h:27
+	float amp_scale;
+	uint32_t wave_mask;           // waves referenced by any op-data
+	uint8_t wave_slot[NUM_WAVES]; // wave -> shared-memory table slot
+};
+
+constexpr int MAX_SEGS = 64;          // segments per call handled in one launch
+struct CallDesc {
+	uint32_t gen;                 // index into the GenDesc array
+	uint32_t call_len;
+	uint32_t nseg;
+	uint32_t stereo;
+	uint32_t seg_start[MAX_SEGS]; // frame offset inside the call
+	uint32_t seg_len[MAX_SEGS];
+	uint32_t seg_ev_end[MAX_SEGS];// events with index < this are due at seg start
+};
+
+/* A render task = one voice of one call. */
+struct Task {
+	uint32_t call;
+	uint32_t voice;
+};
+
+} // namespace saugen

@@ -1,0 +1,145 @@
+"""Script corpora shared by the CPU (oracle) and GPU (parity) tests.
+
+FEATURE_SCRIPTS are short single-feature SAU scripts that together touch every
+arithmetic path of the generator back end: the 12 wave
+types, 7 noise types, 6 R functions x flags, 13 line shapes as parameter
+sweeps and as R segment shapes, PM / fPM / FM / range-FM / AM / range-AM,
+self-PM for W and R, panning (constant, swept, modulated), the A operator,
+finite-time modulators, event sequencing and voice reuse.
+"""
+import random
+
+WAVES = ["sin", "tri", "srs", "sqr", "ean", "cat", "eto", "par", "mto", "saw", "hsi", "spa"]
+LINES = ["cos", "lin", "sah", "exp", "log", "xpe", "lge", "sqe", "cub", "smo", "ncl", "nhl", "uwh"]
+NOISES = ["wh", "gw", "bw", "tw", "re", "vi", "bv"]
+
+
+def feature_scripts():
+    s = {}
+    for w in WAVES:
+        s[f"wave_{w}"] = f"W{w} f220 t0.25"
+        s[f"wave_{w}_pm"] = f"W{w} f330 t0.2 p[Wsin f440 a0.7]"
+    for n in NOISES:
+        s[f"noise_{n}"] = f"N{n} t0.2 a0.5"
+    for l in LINES:
+        s[f"sweep_f_{l}"] = f"Wsin f200[g900 l{l} t0.21] t0.3"
+        s[f"sweep_a_{l}"] = f"Wtri f300 a1[g0.1 l{l} t0.2] t0.3"
+        s[f"R_{l}"] = f"R{l} f300 t0.2"
+        s[f"R_{l}_perlin"] = f"R{l} mp f300 t0.2"
+        s[f"R_{l}_self"] = f"R{l} f250 p.a0.6 t0.2"
+    for m in ["u", "g", "b", "b3", "t", "t4", "f", "f2", "f5", "a", "uv", "bv", "b2v", "fv", "f3v",
+              "uh", "gz", "us", "uhp", "b4hz", "t2ps", "f1vs", "gp", "ahz", "up", "uvp", "uzp"]:
+        s[f"Rmode_{m}"] = f"Rlin m{m} f260 t0.15"
+        s[f"Rmode_{m}_self"] = f"Rsqe m{m} f260 p.a0.5 t0.15"
+    s["Rmode_a_alpha"] = "Rlin ma.a0.7548776662 f300 t0.2"
+    s["pm_chain"] = "Wsin f200 t0.3 p[Wtri r2 a0.8[g0.1 llin] p[Wsin r3.5 a0.5]]"
+    s["pm_two"] = "Wsin f200 t0.3 p[Wsin f300 a0.5 Wsaw f120 a0.2]"
+    s["fpm"] = "Wsin f300 t0.3 p.f[Wsin f100 a0.9]"
+    s["pm_fpm"] = "Wsin f300 t0.3 p[Wsin f150 a0.4] p.f[Wtri f90 a0.5]"
+    s["fm_add"] = "Wsin f300[Wsin f5 a40] t0.3"
+    s["fm_range"] = "Wsin f300.r600[Wsin f7] t0.3"
+    s["fm_range2"] = "Wsin f300.r600[Wsin f7 Wtri f3 a-0.8] t0.3"
+    s["fm_both"] = "Wsin f300.r500[Wsin f4][Wsin f11 a25] t0.3"
+    s["am_add"] = "Wsin f300 a0.5[Wsin f6 a0.4] t0.3"
+    s["am_range"] = "Wsin f300 a1.r0[Wsin f6] t0.3"
+    s["rm"] = "Wsin f300 a0[Wsin f80] t0.3"
+    s["am_range_sweep"] = "Wsin f300 a1.r0.2[g0.9 lsqe t0.2][Wsin f6] t0.3"
+    s["ratio_sweep"] = "Wsin f200 t0.3 p[Wsin r2[g3 lexp t0.25] a0.6]"
+    s["ratio_fm"] = "Wsin f200 t0.3 f[Wsin r0.5 a30]"
+    s["self_w"] = "Wsin f220 p.a0.8 t0.3"
+    s["self_w_sweep"] = "Wsin f220 p.a0[g1.2 t0.2] t0.3"
+    s["self_w_mod"] = "Wcat f220 t0.5 p.a0.5[Wsin f1 a0.4]"
+    s["self_w_off"] = "Wsin f220 p.a0.7[g0 t0.05] t0.3"
+    s["self_r"] = "Rlin f220 p.a0.7 t0.3"
+    s["self_r_pm"] = "Rcos mg f220 p.a0.7 p[Wsin f100 a0.3] t0.3"
+    s["r_pm_fm"] = "Rsmo f200.r400[Wsin f3] p[Wsin f300 a0.5] t0.3"
+    s["r_fpm"] = "Rlin mh f200 p.f[Wsin f50 a0.7] t0.3"
+    s["pan_const"] = "Wsin f300 c-0.5 t0.2"
+    s["pan_sweep"] = "Wsin f300 c-1[g1 t0.15] t0.3"
+    s["pan_mod"] = "Wsin f300 c0[Wsin f5 a0.8] t0.3"
+    s["pan_mod_ratio"] = "Wsin f300 c0.1[Wsin r0.01 a0.8] t0.3"
+    s["amp_op"] = "A0[Wsin f300 a0.5 Wtri f100 a0.3] t0.3"
+    s["amp_op_range"] = "A0.8.r0.1[Wsin f8] t0.2"
+    s["noise_am"] = "Nwh a0.5.r0[Wsin f9] t0.3"
+    s["noise_as_pm"] = "Wsin f300 p[Nre a0.2] t0.3"
+    s["mod_finite"] = "Wsin f200 t0.5 p[Wsin f300 t0.1 a0.8]"
+    s["mod_finite_fm"] = "Wsin f200[Wsin f9 a50 t0.2] t0.5"
+    s["voices3"] = "Wsin f200 c-0.3 t0.3 Wtri f301 c0.4 t0.2 Nwh a0.2 t0.25"
+    s["seq_update"] = "Wsin f200 t0.3; f300 t0.2; f150[g400] t0.25"
+    s["seq_bar"] = "Wsin f200 t0.2 | Wtri f300 t0.15 | Nvi t0.1"
+    s["seq_delay"] = "Wsin f200 t0.2 /0.3 Wsaw f100 t0.2"
+    s["seq_overlap"] = "Wsin f200 t0.4 /0.1 Wsin f250 t0.4 /0.1 Wsin f300 t0.4"
+    s["regoal"] = "Wsin f200[g800 t0.4] t0.2; f[g100 t0.1] t0.2"
+    s["wave_change"] = "Wsin f200 t0.2; wsaw t0.2; wtri p0.25 t0.1"
+    s["pm_addrem"] = "Wsin f200 t0.2 p[Wsin f300]; p-[] t0.1; p[Wtri f100 a0.5] t0.2"
+    s["ampmult"] = "S a0.3 Wsin f200 t0.2 Wsin f300 t0.2"
+    s["zero_freq"] = "Wsin f0 t0.1 p[Wsin f200 a0.5]"
+    s["neg_freq"] = "Wsaw f-200 t0.2"
+    s["high_freq"] = "Wsqr f30000 t0.1"
+    s["deep"] = "Wsin f200 t0.3 p[Wsin r2 p[Wsin r2 p[Wsin r2 p[Wsin r0.5 a0.3]]]]"
+    s["silence_mid"] = "Wsin f200 t0.1 /0.6 Wsin f300 t0.1"
+    return s
+
+
+def synth_c3(n_voices=4096, secs=60, seed=1, fm=False):
+    """BASELINE config 3: n voices of 3-operator PM (or FM) chains with ramps."""
+    rnd = random.Random(seed)
+    lines = [f"S a{1.0 / n_voices:.9f}"]
+    for _ in range(n_voices):
+        f = 110.0 * 2 ** rnd.uniform(0, 4)
+        c = rnd.uniform(-1, 1)
+        r1 = rnd.choice([0.5, 1, 1.5, 2, 3])
+        r2 = rnd.choice([1, 2, 3.5, 7])
+        if fm:
+            lines.append(
+                f"Wsin f{f:.3f}.r{2 * f:.3f}[Wtri r{r1} a0.8[g0.1 llin]] t{secs} "
+                f"a1[g0.2 lxpe] c{c:.3f} p[Wsin r{r2} a0.5]")
+        else:
+            lines.append(
+                f"Wsin f{f:.3f} t{secs} a1[g0.2 lxpe] c{c:.3f} "
+                f"p[Wtri r{r1} a0.8[g0.1 llin] p[Wsin r{r2} a0.5]]")
+    return "\n".join(lines) + "\n"
+
+
+def synth_c4(n_voices=1024, secs=60, seed=2):
+    """BASELINE config 4: self-feedback PM carriers with range-AM / ring-mod."""
+    rnd = random.Random(seed)
+    lines = [f"S a{1.0 / n_voices:.9f}"]
+    for i in range(n_voices):
+        f = 110.0 * 2 ** rnd.uniform(0, 4)
+        c = rnd.uniform(-1, 1)
+        pa = rnd.uniform(0.3, 1.0)
+        fm = rnd.uniform(0.5, 8)
+        k = i % 3
+        if k == 0:
+            lines.append(f"Wsin f{f:.3f} t{secs} p.a{pa:.3f} a0.5.r1[Wsin f{fm:.3f}] c{c:.3f}")
+        elif k == 1:
+            lines.append(f"Rlin f{f:.3f} t{secs} p.a{pa:.3f} a0.5.r1[Wsin f{fm:.3f}] c{c:.3f}")
+        else:
+            lines.append(f"Wtri f{f:.3f} t{secs} p.a{pa:.3f} a0[Wsin f{fm * 20:.3f} a0.8] c{c:.3f}")
+    return "\n".join(lines) + "\n"
+
+
+def synth_c5_script(index):
+    """BASELINE config 5: one of the independent mixed scripts (seed 1000+index)."""
+    rnd = random.Random(1000 + index)
+    nv = rnd.randint(4, 16)
+    lines = [f"S a{1.0 / nv:.6f}"]
+    for _ in range(nv):
+        t = rnd.uniform(1, 10)
+        f = 110.0 * 2 ** rnd.uniform(0, 4)
+        c = rnd.uniform(-1, 1)
+        kind = rnd.randrange(4)
+        if kind == 0:
+            w, w2 = rnd.choice(WAVES), rnd.choice(WAVES)
+            lines.append(f"W{w} f{f:.3f} t{t:.3f} c{c:.3f} p[W{w2} r{rnd.choice([0.5, 1, 2, 3])} "
+                         f"a{rnd.uniform(0.1, 1):.3f}]")
+        elif kind == 1:
+            lines.append(f"N{rnd.choice(NOISES)} t{t:.3f} c{c:.3f} a{rnd.uniform(0.1, 0.8):.3f}")
+        elif kind == 2:
+            mode = rnd.choice("ugbtfa") + rnd.choice(["", "h", "p", "s", "v", "z"])
+            lines.append(f"R{rnd.choice(LINES)} m{mode} f{f:.3f} t{t:.3f} c{c:.3f}")
+        else:
+            lines.append(f"W{rnd.choice(WAVES)} f{f:.3f}[g{f * rnd.uniform(0.5, 2):.3f} "
+                         f"l{rnd.choice(LINES)}] t{t:.3f} c{c:.3f} a1.r0[Wsin f{rnd.uniform(0.5, 9):.3f}]")
+    return "\n".join(lines) + "\n"
