@@ -122,6 +122,7 @@ struct Instr {
 	uint8_t opcode, a, b, c, d, e;
 	uint16_t flags;
 	uint32_t op;
+	uint32_t aux;          // I_ENTER: index of the matching I_LEAVE
 };
 
 /* One generator's device-resident description. */
@@ -134,8 +135,9 @@ struct GenDesc {
 	const uint32_t *vev_off;      // [vo_count+1] CSR into vev_idx
 	const uint32_t *vev_idx;      // global event indices per voice, in order
 	float *rows_s, *rows_r;       // [n_local_voices][row_len] carrier rows of a call
-	uint32_t *vlen;               // [max_segs][n_local_voices] frames run per segment
-	uint32_t *status;             // [0]=any voice still alive, [1..]=per-segment max len
+	uint32_t *vlen;               // [seg][n_local_voices] frames run per segment of a call
+	uint32_t *status;             // [0]=any voice still alive, [1+seg]=per-segment max len
+	uint32_t vlen_cap;            // segments the vlen/status arrays can hold
 	float *mix;                   // [2][row_len] float mix planes (L, R)
 	int16_t *pcm;                 // [row_len*2]
 	uint32_t vo_count, op_count;
@@ -146,24 +148,34 @@ struct GenDesc {
 	float coeff;                  // (float)(2^32 / srate), wosc.h:30, rasg.h:27
 	float amp_scale;
 	uint32_t wave_mask;           // waves referenced by any op-data
-	uint8_t wave_slot[NUM_WAVES]; // wave -> shared-memory table slot
+	const float *tables;          // 12 x 2048 floats, then a WaveCoeffs
 };
 
-constexpr int MAX_SEGS = 64;          // segments per call handled in one launch
+/* Per-wave constants derived from sauWave_picoeffs (sau/wave.h:33-70,144-149),
+ * stored after the 12 tables in the device table block. */
+struct WaveCoeffs {
+	float diff_scale[NUM_WAVES];   // amp_scale * 0.125f * 2^32
+	float diff_offset[NUM_WAVES];  // amp_dc
+	float amp256[NUM_WAVES];       // amp_scale * 256 (reset path, wosc.h:224)
+	int32_t phase_adj[NUM_WAVES];
+};
+
+/* One inter-event stretch of a call (sau/generator.c:915-949). */
+struct SegDesc {
+	uint32_t start;    // frame offset inside the call
+	uint32_t len;
+	uint32_t ev_end;   // events with index < ev_end are due at the segment start
+};
+
+/* One sauGenerator_run call of one generator. */
 struct CallDesc {
-	uint32_t gen;                 // index into the GenDesc array
+	const GenDesc *gen;
 	uint32_t call_len;
 	uint32_t nseg;
+	uint32_t seg_off;      // first SegDesc of this call
+	uint32_t task_base;    // index of this call's first voice task in the launch
 	uint32_t stereo;
-	uint32_t seg_start[MAX_SEGS]; // frame offset inside the call
-	uint32_t seg_len[MAX_SEGS];
-	uint32_t seg_ev_end[MAX_SEGS];// events with index < this are due at seg start
-};
-
-/* A render task = one voice of one call. */
-struct Task {
-	uint32_t call;
-	uint32_t voice;
+	uint32_t _pad;
 };
 
 } // namespace saugen

@@ -1,0 +1,1060 @@
+/* kernels.cu -- sm_100a kernels of the saugns generator back end.
+ *
+ *   render_kernel : one warp per (call, voice).  The warp owns its voice's
+ *     timeline for the call: it applies the voice's due events
+ *     (handle_event, sau/generator.c:348-377), then renders every inter-event
+ *     segment in 128-sample chunks by interpreting the voice's bytecode (the
+ *     flattened run_block recursion, generator.c:448-729).  Each lane owns 4
+ *     consecutive samples of a chunk; integer phase accumulation is a warp
+ *     shuffle scan over the rounded increments (bit-exact with
+ *     sauPhasor_fill / sauCyclor_fill), self-PM operators run as a serial
+ *     loop on one lane with their state in registers.  Wave tables are
+ *     staged into shared memory with TMA bulk copies (cp.async.bulk +
+ *     mbarrier).  The carrier block, scaled and panned, goes to HBM rows
+ *     (128-bit stores when aligned).
+ *   mix_kernel : fused epilogue.  One thread per output frame sums the voice
+ *     rows in voice order (same float summation order as mix_add,
+ *     generator.c:749-788), clamps and rounds to int16
+ *     (mix_write_stereo/mono, generator.c:795-825).
+ *
+ * Compiled with -fmad=false: every float/double operation is a separately
+ * rounded IEEE operation, in the order sau_arith.h states.
+ */
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "device_types.h"
+#include "sau_arith.h"
+#include "../../include/sau_program_abi.h"
+
+namespace saugen {
+
+#define FULL 0xffffffffu
+
+/* ---- TMA 1-D bulk copy + mbarrier (PTX) --------------------------------- */
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+	return (uint32_t) __cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+			:: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes,
+		uint64_t *bar) {
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes"
+			" [%0], [%1], %2, [%3];"
+			:: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase) {
+	asm volatile(
+		"{\n"
+		".reg .pred p;\n"
+		"WAIT_LOOP:\n"
+		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+		"@p bra WAIT_DONE;\n"
+		"bra WAIT_LOOP;\n"
+		"WAIT_DONE:\n"
+		"}\n" :: "r"(smem_u32(bar)), "r"(phase) : "memory");
+}
+
+/* ---- per-warp interpreter context --------------------------------------- */
+
+struct Ctx {
+	float *bufs;               // shared: nbufs x CHUNK floats of this warp
+	uint32_t *stk_len;         // shared: MAX_NEST entries each
+	uint32_t *stk_rem;
+	uint32_t *stk_layer;
+	const float *tab;          // shared: staged wave tables
+	const WaveCoeffs *wc;      // global
+	const GenDesc *g;          // global
+	OpState *ops;
+	uint32_t wave_mask;        // tables staged by this launch
+	uint32_t oc;               // chunk offset inside the reference's 1024-block
+	int lane;
+	int sp;
+	bool pma_flag, pan_dyn;
+	uint32_t last_len, last_rem;
+};
+
+__device__ __forceinline__ float4 *B4(const Ctx &c, uint32_t i) {
+	return reinterpret_cast<float4*>(c.bufs + i * CHUNK) + c.lane;
+}
+__device__ __forceinline__ uint4 *U4(const Ctx &c, uint32_t i) {
+	return reinterpret_cast<uint4*>(c.bufs + i * CHUNK) + c.lane;
+}
+__device__ __forceinline__ const float *wave_lut(const Ctx &c, uint32_t wave) {
+	uint32_t slot = __popc(c.wave_mask & ((1u << wave) - 1u));
+	return c.tab + slot * WAVE_LEN;
+}
+__device__ __forceinline__ uint32_t scan_incl_u32(uint32_t v, int lane) {
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+		uint32_t y = __shfl_up_sync(FULL, v, d);
+		if (lane >= d) v += y;
+	}
+	return v;
+}
+__device__ __forceinline__ uint64_t scan_incl_u64(uint64_t v, int lane) {
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+		uint64_t y = __shfl_up_sync(FULL, v, d);
+		if (lane >= d) v += y;
+	}
+	return v;
+}
+
+/* ---- sauLine state machine (sau/line.c:349-473) on a chunk -------------- */
+
+__device__ __forceinline__ void line_advance(uint32_t &pos, uint32_t end, uint32_t &flags,
+		uint32_t n, bool &expired) {                             /* line.c:385-398 */
+	if (pos < end) {
+		uint32_t l = end - pos;
+		if (l > n) l = n;
+		pos += l;
+	}
+	expired = false;
+	if (pos >= end) {
+		pos = 0;
+		flags &= ~SAUABI_LINEP_TIME;
+		expired = true;
+	}
+}
+
+/* sauLine_run(line, bufs[dst], len, mulbuf) -- line.c:417-445 */
+__device__ void line_run(Ctx &c, LineState *ls, uint32_t dst, uint32_t mul, uint32_t n) {
+	float v0 = ls->v0, vt = ls->vt;
+	uint32_t pos = ls->pos, end = ls->end, type = ls->type, flags = ls->flags;
+	const bool has_mul = (mul != NO_BUF);
+	float m[SPL] = {1.f, 1.f, 1.f, 1.f};
+	if (has_mul) { float4 t = *B4(c, mul); m[0] = t.x; m[1] = t.y; m[2] = t.z; m[3] = t.w; }
+	float out[SPL];
+	const uint32_t i0 = c.lane * SPL;
+	if (!(flags & SAUABI_LINEP_GOAL)) {
+		bool ex;
+		line_advance(pos, end, flags, n, ex);
+		const bool um = has_mul && (flags & SAUABI_LINEP_STATE_RATIO);
+#pragma unroll
+		for (int k = 0; k < SPL; ++k) out[k] = um ? v0 * m[k] : v0;
+	} else {
+		bool fillmul = has_mul;                                   /* sauLine_get, line.c:349-378 */
+		if (flags & SAUABI_LINEP_GOAL_RATIO) {
+			if (!(flags & SAUABI_LINEP_STATE_RATIO)) {
+				if (has_mul) v0 = v0 / c.bufs[mul * CHUNK];
+				flags |= SAUABI_LINEP_STATE_RATIO;
+			}
+		} else {
+			if (flags & SAUABI_LINEP_STATE_RATIO) {
+				if (has_mul) v0 = v0 * c.bufs[mul * CHUNK];
+				flags &= ~SAUABI_LINEP_STATE_RATIO;
+			}
+			fillmul = false;
+		}
+		uint32_t flen = 0;
+		if (pos < end) { flen = end - pos; if (flen > n) flen = n; }
+		if (flen > 0) {
+			sau::LineFill f = sau::line_fill_setup((int) type, v0, vt, pos, end);
+			/* gcc's scalar tail of sauLine_fill_cub: the last element of an
+			 * odd-length fill call, counted in the reference's 1024-block. */
+			uint32_t tail_idx = 0xffffffffu;
+			if (f.type == sau::L_cub) {
+				uint32_t F = end - pos, rem = c.stk_rem[c.sp];
+				if (F > rem) F = rem;
+				if (F <= (uint32_t) CHUNK && ((c.oc + F) & 1u)) tail_idx = F - 1;
+			}
+#pragma unroll
+			for (int k = 0; k < SPL; ++k) {
+				uint32_t idx = i0 + k;
+				float v = sau::line_fill_at(f, idx, idx == tail_idx);
+				out[k] = fillmul ? v * m[k] : v;
+			}
+		}
+		pos += flen;
+		if (pos >= end) {
+			v0 = vt;
+			pos = 0;
+			flags &= ~(SAUABI_LINEP_GOAL | SAUABI_LINEP_GOAL_RATIO | SAUABI_LINEP_TIME);
+			const bool um = has_mul && (flags & SAUABI_LINEP_STATE_RATIO);
+#pragma unroll
+			for (int k = 0; k < SPL; ++k)
+				if (i0 + k >= flen) out[k] = um ? v0 * m[k] : v0;
+		}
+	}
+	*B4(c, dst) = make_float4(out[0], out[1], out[2], out[3]);
+	__syncwarp();   /* every lane has read the state before lane 0 rewrites it */
+	if (c.lane == 0) {
+		ls->v0 = v0; ls->pos = pos; ls->flags = (uint8_t) flags;
+	}
+}
+
+/* sauLine_skip -- line.c:456-473 */
+__device__ void line_skip(Ctx &c, LineState *ls, uint32_t n) {
+	if (c.lane != 0) return;
+	uint32_t pos = ls->pos, end = ls->end, flags = ls->flags;
+	bool ex;
+	line_advance(pos, end, flags, n, ex);
+	if (ex && (flags & SAUABI_LINEP_GOAL)) {
+		ls->v0 = ls->vt;
+		if (flags & SAUABI_LINEP_GOAL_RATIO) flags |= SAUABI_LINEP_STATE_RATIO;
+		else flags &= ~SAUABI_LINEP_STATE_RATIO;
+		flags &= ~(SAUABI_LINEP_GOAL | SAUABI_LINEP_GOAL_RATIO);
+	}
+	ls->pos = pos; ls->flags = (uint8_t) flags;
+}
+
+/* ---- sauPhasor_fill (wosc.h:135-169): scan over rounded increments ------ */
+
+__device__ void phasor_fill(Ctx &c, const Instr &in, uint32_t n) {
+	OpState *o = &c.ops[in.op];
+	const float coeff = c.g->coeff;
+	const uint32_t phase0 = o->i0;
+	const float4 f4 = *B4(c, in.b);
+	const float f[SPL] = {f4.x, f4.y, f4.z, f4.w};
+	float pm[SPL] = {0, 0, 0, 0}, fpm[SPL] = {0, 0, 0, 0};
+	const bool has_pm = in.c != NO_BUF, has_fpm = in.d != NO_BUF;
+	if (has_pm) { float4 t = *B4(c, in.c); pm[0] = t.x; pm[1] = t.y; pm[2] = t.z; pm[3] = t.w; }
+	if (has_fpm) { float4 t = *B4(c, in.d); fpm[0] = t.x; fpm[1] = t.y; fpm[2] = t.z; fpm[3] = t.w; }
+	const uint32_t i0 = c.lane * SPL;
+	uint32_t p[SPL], ofs[SPL];
+	uint32_t run = 0;
+#pragma unroll
+	for (int k = 0; k < SPL; ++k) {
+		uint32_t inc = (i0 + k < n) ? (uint32_t) sau::ftoi64(coeff * f[k]) : 0u;
+		run += inc;
+		p[k] = run;
+		int64_t of = 0;
+		if (has_pm && has_fpm) of = sau::pofs_pm_fpm(pm[k], fpm[k], f[k], 2147483648.f);
+		else if (has_pm) of = sau::pofs_pm(pm[k], 2147483648.f);
+		else if (has_fpm) of = sau::pofs_fpm(fpm[k], f[k], 2147483648.f);
+		ofs[k] = (uint32_t) of;
+	}
+	const uint32_t incl = scan_incl_u32(run, c.lane);
+	const uint32_t base = phase0 + (incl - run);
+	*U4(c, in.a) = make_uint4(base + p[0] + ofs[0], base + p[1] + ofs[1],
+			base + p[2] + ofs[2], base + p[3] + ofs[3]);
+	const uint32_t total = __shfl_sync(FULL, incl, 31);
+	if (c.lane == 0) o->i0 = phase0 + total;
+}
+
+/* ---- sauWOsc_run / sauWOsc_run_selfmod (wosc.h:215-310) ----------------- */
+
+__device__ void wosc_run(Ctx &c, const Instr &in, uint32_t n) {
+	OpState *o = &c.ops[in.op];
+	const uint32_t wave = o->mode;
+	const float *lut = wave_lut(c, wave);
+	const float ds = c.wc->diff_scale[wave], doff = c.wc->diff_offset[wave];
+	uint32_t prev_phase = o->i1;
+	double prev_Is = o->prev_Is;
+	float prev_s = o->prev_s;
+	uint32_t oscflags = o->oscflags;
+	const uint32_t *phase_buf = reinterpret_cast<const uint32_t*>(c.bufs + in.b * CHUNK);
+	const bool selfmod = (in.flags & F_HAS_APMODS) || c.pma_flag;
+	if (oscflags & OSC_RESET_DIFF) {                              /* wosc.h:215-230 */
+		const uint32_t ph = phase_buf[0];
+		double poly, c0;
+		sau::herp(lut, ph - sau::WAVE_SLEN, &poly, &c0);
+		const double Is = sau::herp(lut, ph, (double*) 0, (double*) 0);
+		prev_s = (float) (((Is - poly) - c0) * (double) c.wc->amp256[wave] + (double) doff);
+		prev_Is = Is;
+		prev_phase = ph;
+		oscflags &= ~OSC_RESET_DIFF;
+	}
+	__syncwarp();
+	if (selfmod) {
+		/* truly serial (non-linear recurrence through fb_s): one lane, state in registers */
+		if (c.lane == 0) {
+			float fb_s = o->fb_s;
+			const float *pma = c.bufs + in.c * CHUNK;
+			float *dst = c.bufs + in.a * CHUNK;
+			for (uint32_t i = 0; i < n; ++i) {
+				float s;
+				const uint32_t phase = phase_buf[i] +
+					(uint32_t) sau::ftoi64(fb_s * pma[i] * 2147483648.f);
+				const int32_t d = (int32_t) (phase - prev_phase);
+				if (d == 0) {
+					s = prev_s;
+				} else {
+					const double Is = sau::herp(lut, phase, (double*) 0, (double*) 0);
+					s = sau::wosc_diff(Is, prev_Is, d, ds, doff);
+					prev_Is = Is; prev_s = s; prev_phase = phase;
+				}
+				dst[i] = s;
+				fb_s = (fb_s + s) * 0.5f;
+			}
+			o->fb_s = fb_s;
+			o->i1 = prev_phase; o->prev_Is = prev_Is; o->prev_s = prev_s;
+			o->oscflags = (uint8_t) oscflags;
+		}
+		return;
+	}
+	const uint4 ph4 = *U4(c, in.b);
+	const uint32_t ph[SPL] = {ph4.x, ph4.y, ph4.z, ph4.w};
+	const uint32_t i0 = c.lane * SPL;
+	double Is[SPL];
+#pragma unroll
+	for (int k = 0; k < SPL; ++k) Is[k] = sau::herp(lut, ph[k], (double*) 0, (double*) 0);
+	/* sample before this lane's first: previous lane's last, or carried state */
+	uint32_t pph = __shfl_up_sync(FULL, ph[SPL - 1], 1);
+	double pIs = __shfl_up_sync(FULL, Is[SPL - 1], 1);
+	if (c.lane == 0) { pph = prev_phase; pIs = prev_Is; }
+	float s[SPL];
+	bool zd[SPL];               // valid sample with zero phase difference
+	bool lead_zero = false;     // has zero-difference samples before its first computed one
+	bool has_nz = false;
+	float s_run = 0.f;
+#pragma unroll
+	for (int k = 0; k < SPL; ++k) {
+		const bool valid = (i0 + k) < n;
+		const int32_t d = (int32_t) (ph[k] - pph);
+		zd[k] = valid && d == 0;
+		if (valid && d != 0) {
+			s_run = sau::wosc_diff(Is[k], pIs, d, ds, doff);
+			has_nz = true;
+		}
+		if (zd[k] && !has_nz) lead_zero = true;
+		s[k] = s_run;
+		pph = ph[k]; pIs = Is[k];
+	}
+	/* zero-difference samples repeat the last computed output (wosc.h:251-252):
+	 * fetch it from the nearest lower lane that computed one, else carried state */
+	const uint32_t any_lead = __ballot_sync(FULL, lead_zero);
+	if (any_lead) {
+		const uint32_t nzmask = __ballot_sync(FULL, has_nz);
+		const uint32_t lower = nzmask & ((1u << c.lane) - 1u);
+		const int src = lower ? (31 - __clz(lower)) : 0;
+		float inc = __shfl_sync(FULL, s_run, src);
+		if (!lower) inc = prev_s;
+		bool seen = false;
+#pragma unroll
+		for (int k = 0; k < SPL; ++k) {
+			if (!zd[k] && (i0 + k) < n) seen = true;
+			if (!seen) s[k] = inc;
+		}
+		if (!has_nz) s_run = inc;
+	}
+	*B4(c, in.a) = make_float4(s[0], s[1], s[2], s[3]);
+	/* carried state = last valid sample (n >= 1 here) */
+	const uint32_t li = n - 1;
+	const int src_lane = (int) (li / SPL), src_k = (int) (li % SPL);
+	uint32_t e_ph = ph[0]; double e_Is = Is[0]; float e_s = s[0];
+#pragma unroll
+	for (int k = 1; k < SPL; ++k) if (src_k == k) { e_ph = ph[k]; e_Is = Is[k]; e_s = s[k]; }
+	e_ph = __shfl_sync(FULL, e_ph, src_lane);
+	e_Is = __shfl_sync(FULL, e_Is, src_lane);
+	e_s = __shfl_sync(FULL, e_s, src_lane);
+	if (c.lane == 0) {
+		o->i1 = e_ph; o->prev_Is = e_Is; o->prev_s = e_s;
+		o->oscflags = (uint8_t) oscflags;
+	}
+}
+
+/* ---- sauCyclor_fill (rasg.h:165-222) ------------------------------------ */
+
+__device__ void cyclor_fill(Ctx &c, const Instr &in, uint32_t n) {
+	OpState *o = &c.ops[in.op];
+	float coeff = c.g->coeff, ps = 2147483648.f;
+	if (o->oscflags & 1) { coeff *= 2; ps *= 2; }
+	const uint64_t cp0 = ((uint64_t) o->i1 << 32) | o->i0;
+	const float4 f4 = *B4(c, in.c);
+	const float f[SPL] = {f4.x, f4.y, f4.z, f4.w};
+	float pm[SPL] = {0, 0, 0, 0}, fpm[SPL] = {0, 0, 0, 0};
+	const bool has_pm = in.d != NO_BUF, has_fpm = in.e != NO_BUF;
+	if (has_pm) { float4 t = *B4(c, in.d); pm[0] = t.x; pm[1] = t.y; pm[2] = t.z; pm[3] = t.w; }
+	if (has_fpm) { float4 t = *B4(c, in.e); fpm[0] = t.x; fpm[1] = t.y; fpm[2] = t.z; fpm[3] = t.w; }
+	const uint32_t i0 = c.lane * SPL;
+	uint64_t pre[SPL], ofs[SPL];
+	uint64_t run = 0;
+#pragma unroll
+	for (int k = 0; k < SPL; ++k) {
+		pre[k] = run;                                              /* post-increment */
+		uint64_t inc = (i0 + k < n) ? (uint64_t) sau::ftoi64(coeff * f[k]) : 0ull;
+		run += inc;
+		int64_t of = 0;
+		if (has_pm && has_fpm) of = sau::pofs_pm_fpm(pm[k], fpm[k], f[k], ps);
+		else if (has_pm) of = sau::pofs_pm(pm[k], ps);
+		else if (has_fpm) of = sau::pofs_fpm(fpm[k], f[k], ps);
+		ofs[k] = (uint64_t) of;
+	}
+	const uint64_t incl = scan_incl_u64(run, c.lane);
+	const uint64_t base = cp0 + (incl - run);
+	uint32_t cyc[SPL]; float phf[SPL];
+#pragma unroll
+	for (int k = 0; k < SPL; ++k) {
+		const uint64_t cp = base + pre[k] + ofs[k];
+		cyc[k] = (uint32_t) (cp >> 32);
+		const uint32_t phase = ((uint32_t) cp) >> 1;
+		phf[k] = sau::i2f((int32_t) phase) * (1.f / 2147483648.f);
+	}
+	*U4(c, in.a) = make_uint4(cyc[0], cyc[1], cyc[2], cyc[3]);
+	*B4(c, in.b) = make_float4(phf[0], phf[1], phf[2], phf[3]);
+	const uint64_t total = __shfl_sync(FULL, incl, 31);
+	if (c.lane == 0) {
+		const uint64_t cp = cp0 + total;
+		o->i0 = (uint32_t) cp; o->i1 = (uint32_t) (cp >> 32);
+	}
+}
+
+/* ---- sauRasG_run / sauRasG_run_selfmod (rasg.h:692-772) ----------------- */
+
+__device__ void rasg_run(Ctx &c, const Instr &in, uint32_t n) {
+	OpState *o = &c.ops[in.op];
+	const unsigned flags = o->ras_flags, func = o->ras_func;
+	const int sr = o->ras_level, line = o->mode;
+	const uint32_t alpha = o->ras_alpha;
+	const bool selfmod = (in.flags & F_HAS_APMODS) || c.pma_flag;
+	if (selfmod) {
+		if (c.lane == 0) {                                         /* rasg.h:242-280 */
+			float fb_s = o->fb_s, prev_s = o->prev_s;
+			float *main_buf = c.bufs + in.a * CHUNK;
+			const uint32_t *cycle_buf = reinterpret_cast<const uint32_t*>(c.bufs + in.b * CHUNK);
+			const float *pma = c.bufs + in.c * CHUNK;
+			for (uint32_t i = 0; i < n; ++i) {
+				const float pm_a = fb_s * pma[i] * 0.5f;
+				float phase = main_buf[i] + pm_a;
+				const int32_t cycle_adj = (int32_t) floorf(phase);
+				const uint32_t cycle = cycle_buf[i] + (uint32_t) cycle_adj;
+				phase -= (float) cycle_adj;
+				const float s = sau::rasg_sample(func, flags, sr, alpha, line, cycle, phase,
+						true, false);
+				main_buf[i] = s;
+				fb_s = ((fb_s + prev_s) + s) * 0.5f;
+				prev_s = s;
+			}
+			o->fb_s = fb_s; o->prev_s = prev_s;
+		}
+		return;
+	}
+	const uint4 cy4 = *U4(c, in.b);
+	const uint32_t cy[SPL] = {cy4.x, cy4.y, cy4.z, cy4.w};
+	const float4 p4 = *B4(c, in.a);
+	const float ph[SPL] = {p4.x, p4.y, p4.z, p4.w};
+	/* sauLine_map_cub: 4-wide body + scalar tail, counted in the 1024-block */
+	const uint32_t blk_len = c.oc + c.stk_rem[c.sp];
+	const uint32_t tail_from = blk_len & ~3u;
+	float out[SPL];
+#pragma unroll
+	for (int k = 0; k < SPL; ++k) {
+		const uint32_t idx = c.lane * SPL + k;
+		out[k] = sau::rasg_sample(func, flags, sr, alpha, line, cy[k], ph[k], false,
+				(c.oc + idx) >= tail_from);
+	}
+	*B4(c, in.a) = make_float4(out[0], out[1], out[2], out[3]);
+}
+
+/* ---- sauNoiseG_run_* (noise.h:41-185) ----------------------------------- */
+
+__device__ __forceinline__ int32_t noise_tern(uint32_t n) {       /* bv's s1, noise.h:165-167 */
+	int32_t s1 = sau::sar32((int32_t) sau::ranfast32(n), 31);
+	return (n & 1) ? (s1 * 2 + 1) : 0;
+}
+__device__ void noise_run(Ctx &c, const Instr &in, uint32_t n) {
+	OpState *o = &c.ops[in.op];
+	const uint32_t n0 = o->i0, prev = o->i1, type = o->mode;
+	const float scale = 1.f / 2147483648.f;
+	const uint32_t i0 = c.lane * SPL;
+	float out[SPL];
+	uint32_t new_prev = prev;
+	switch (type) {
+	default:
+	case SAUABI_NOISE_wh:
+#pragma unroll
+		for (int k = 0; k < SPL; ++k) out[k] = sau::fscalei(sau::ranfast32(n0 + i0 + k), scale);
+		break;
+	case SAUABI_NOISE_gw:
+#pragma unroll
+		for (int k = 0; k < SPL; ++k) out[k] = sau::franssgauss32(n0 + i0 + k);
+		break;
+	case SAUABI_NOISE_bw:
+#pragma unroll
+		for (int k = 0; k < SPL; ++k)
+			out[k] = (float) (sau::sar32((int32_t) sau::ranfast32(n0 + i0 + k), 31) * 2 + 1);
+		break;
+	case SAUABI_NOISE_tw:
+#pragma unroll
+		for (int k = 0; k < SPL; ++k) {
+			const uint32_t nn = n0 + i0 + k;
+			const int32_t s = sau::sar32((int32_t) sau::ranfast32(nn), 31) * 2 + 1;
+			out[k] = (nn & 1) ? (float) s : 0.f;
+		}
+		break;
+	case SAUABI_NOISE_re: {                                        /* integer prefix sum */
+		uint32_t p[SPL], run = 0;
+#pragma unroll
+		for (int k = 0; k < SPL; ++k) {
+			const int32_t s = (int32_t) sau::ranfast32(n0 + i0 + k);
+			run += (i0 + k < n) ? (uint32_t) (s >> 6) : 0u;
+			p[k] = run;
+		}
+		const uint32_t incl = scan_incl_u32(run, c.lane);
+		const uint32_t base = prev + (incl - run);
+#pragma unroll
+		for (int k = 0; k < SPL; ++k)
+			out[k] = sau::fscalei((uint32_t) sau::foldhd32((int32_t) (base + p[k])), scale);
+		new_prev = prev + __shfl_sync(FULL, incl, 31);
+		break; }
+	case SAUABI_NOISE_vi:                                          /* 1-sample shift */
+#pragma unroll
+		for (int k = 0; k < SPL; ++k) {
+			const uint32_t idx = i0 + k;
+			const uint32_t s1 = sau::ranfast32(n0 + idx);
+			const uint32_t s0 = idx ? sau::ranfast32(n0 + idx - 1) : prev;
+			out[k] = sau::fscalei((s1 / 2) - (s0 / 2), scale);
+		}
+		if (n) new_prev = sau::ranfast32(n0 + n - 1);
+		break;
+	case SAUABI_NOISE_bv:
+#pragma unroll
+		for (int k = 0; k < SPL; ++k) {
+			const uint32_t idx = i0 + k;
+			const int32_t s1 = noise_tern(n0 + idx);
+			const int32_t s0 = idx ? noise_tern(n0 + idx - 1) : (int32_t) prev;
+			out[k] = (float) (s1 - s0);
+		}
+		if (n) new_prev = (uint32_t) noise_tern(n0 + n - 1);
+		break;
+	}
+	*B4(c, in.a) = make_float4(out[0], out[1], out[2], out[3]);
+	__syncwarp();
+	if (c.lane == 0) { o->i0 = n0 + n; o->i1 = new_prev; }
+}
+
+/* ---- event application (generator.c:233-377, line.c:287-332) ------------ */
+
+__device__ void dev_line_copy(LineState *o, const LineDelta *src) {
+	if (!src->present) return;
+	uint32_t mask = 0, flags = o->flags;
+	const uint32_t sf = src->flags;
+	if (sf & SAUABI_LINEP_STATE) {
+		o->v0 = src->v0;
+		mask |= SAUABI_LINEP_STATE | SAUABI_LINEP_STATE_RATIO;
+	} else if (flags & SAUABI_LINEP_GOAL) {
+		if (sf & SAUABI_LINEP_GOAL) {
+			/* sauLine_get(o, &f, 1, NULL): one value on the old trajectory */
+			if (flags & SAUABI_LINEP_GOAL_RATIO) flags |= SAUABI_LINEP_STATE_RATIO;
+			else flags &= ~SAUABI_LINEP_STATE_RATIO;
+			if (o->pos < o->end) {
+				sau::LineFill f = sau::line_fill_setup(o->type, o->v0, o->vt, o->pos, o->end);
+				o->v0 = sau::line_fill_at(f, 0, true);   /* 1-element fill = gcc's tail */
+			}
+		}
+	}
+	if (sf & SAUABI_LINEP_GOAL) {
+		o->vt = src->vt;
+		if (sf & SAUABI_LINEP_TIME_IF_NEW) o->end -= o->pos;
+		o->pos = 0;
+		mask |= SAUABI_LINEP_GOAL | SAUABI_LINEP_GOAL_RATIO;
+	}
+	if (sf & SAUABI_LINEP_TYPE) {
+		o->type = src->type;
+		mask |= SAUABI_LINEP_TYPE;
+	}
+	if (!(flags & SAUABI_LINEP_TIME) || !(sf & SAUABI_LINEP_TIME_IF_NEW)) {
+		if (sf & SAUABI_LINEP_TIME) {
+			o->end = src->end_samples;
+			mask |= SAUABI_LINEP_TIME;
+		}
+	}
+	flags &= ~mask;
+	flags |= (sf & mask);
+	o->flags = (uint8_t) flags;
+}
+
+/* R oscillator setters, rasg.h:59-119 */
+__device__ __forceinline__ uint64_t ras_cp(const OpState *o) { return ((uint64_t) o->i1 << 32) | o->i0; }
+__device__ __forceinline__ void ras_store(OpState *o, uint64_t cp) { o->i0 = (uint32_t) cp; o->i1 = (uint32_t) (cp >> 32); }
+__device__ __forceinline__ uint32_t ras_get_cycle(const OpState *o) { return o->i1 & ~1u; }
+__device__ __forceinline__ uint32_t ras_get_phase(const OpState *o) {
+	return (o->oscflags & 1) ? (uint32_t) (ras_cp(o) >> 1) : o->i0;
+}
+__device__ void ras_set_cycle(OpState *o, uint32_t cycle) {
+	const uint32_t phase = ras_get_phase(o);
+	const uint64_t p64 = (o->oscflags & 1) ? ((uint64_t) phase) << 1 : phase;
+	ras_store(o, ((uint64_t) (cycle & ~1u)) << 32 | p64);
+}
+__device__ void ras_set_phase(OpState *o, uint32_t phase) {
+	const uint32_t cycle = ras_get_cycle(o);
+	const uint64_t p64 = (o->oscflags & 1) ? ((uint64_t) phase) << 1 : phase;
+	ras_store(o, ((uint64_t) cycle) << 32 | p64);
+}
+
+__device__ void apply_event(const GenDesc *g, const WaveCoeffs *wc, const EventRec *ev,
+		VoiceState *vs) {
+	for (uint32_t i = 0; i < ev->opdata_count; ++i) {
+		const OpDataRec *od = &g->opdata[ev->opdata_off + i];
+		OpState *n = &g->ops[od->id];
+		if (!(n->flags & ON_INIT)) {                               /* prepare_op, :245-278 */
+			OpState z;
+			memset(&z, 0, sizeof(z));
+			z.type = od->type;
+			z.flags = ON_INIT;
+			if (od->type == SAUABI_POPT_wave) {                    /* wosc.h:55-71 */
+				z.i0 = (uint32_t) wc->phase_adj[SAUABI_WAVE_sin];
+				z.mode = SAUABI_WAVE_sin;
+				z.oscflags = OSC_RESET_DIFF;
+			} else if (od->type == SAUABI_POPT_raseg) {            /* rasg.h:44-57 */
+				z.oscflags = 1;   /* rate2x */
+				z.mode = SAUABI_LINE_lin;
+				z.ras_func = SAUABI_RAS_F_URAND;
+				z.ras_level = 27;
+				z.ras_alpha = 0x9e3779b9u;
+			}
+			*n = z;
+		}
+		const uint32_t params = od->params;                        /* update_op, :283-343 */
+		bool osc = false;
+		switch (od->type) {
+		case SAUABI_POPT_noise:
+			if (params & SAUABI_POPP_MODE) { n->mode = od->mode_main; n->i1 = 0; }
+			if (params & SAUABI_POPP_SEED) n->i0 = od->seed;
+			break;
+		case SAUABI_POPT_wave:
+			if (params & SAUABI_POPP_MODE) {                       /* wosc.h:81-87 */
+				const uint32_t wave = od->mode_main;
+				n->i0 += (uint32_t) wc->phase_adj[wave] - (uint32_t) wc->phase_adj[n->mode];
+				n->mode = (uint8_t) wave;
+				n->oscflags |= OSC_RESET_DIFF;
+			}
+			if (params & SAUABI_POPP_PHASE)
+				n->i0 = od->phase + (uint32_t) wc->phase_adj[n->mode];
+			osc = true;
+			break;
+		case SAUABI_POPT_raseg:
+			if (params & SAUABI_POPP_MODE) {                       /* rasg.h:97-119 */
+				unsigned flags = od->ras_flags;
+				if (flags & SAUABI_RAS_O_LINE_SET) n->mode = od->mode_main;
+				if (flags & SAUABI_RAS_O_FUNC_SET) n->ras_func = od->ras_func;
+				else flags |= n->ras_flags;
+				if (od->ras_flags & SAUABI_RAS_O_LEVEL_SET) n->ras_level = od->ras_level;
+				if (od->ras_flags & SAUABI_RAS_O_ASUBVAL_SET) n->ras_alpha = od->ras_alpha;
+				n->ras_flags = (uint16_t) (flags & 0x3ff);
+				const bool rate2x = !(flags & SAUABI_RAS_O_HALFSHAPE);
+				if (rate2x != (bool) (n->oscflags & 1)) {
+					const uint32_t cycle = ras_get_cycle(n);
+					const uint32_t phase = ras_get_phase(n);
+					n->oscflags = rate2x ? 1 : 0;
+					ras_set_cycle(n, cycle);
+					ras_set_phase(n, phase);
+				}
+			}
+			if (params & SAUABI_POPP_PHASE) ras_set_phase(n, od->phase);
+			if (params & SAUABI_POPP_SEED) ras_set_cycle(n, od->seed);
+			osc = true;
+			break;
+		}
+		if (osc) {
+			dev_line_copy(&n->line[LINE_FREQ], &od->line[LINE_FREQ]);
+			dev_line_copy(&n->line[LINE_FREQ2], &od->line[LINE_FREQ2]);
+			dev_line_copy(&n->line[LINE_PMA], &od->line[LINE_PMA]);
+		}
+		if (params & SAUABI_POPP_TIME) {
+			if (od->time_flags & SAUABI_TIMEP_IMPLICIT) {
+				n->time = 0;
+				n->flags |= ON_TIME_INF;
+			} else {
+				n->time = od->time_samples;
+				n->flags &= ~ON_TIME_INF;
+			}
+		}
+		dev_line_copy(&n->line[LINE_AMP], &od->line[LINE_AMP]);
+		dev_line_copy(&n->line[LINE_AMP2], &od->line[LINE_AMP2]);
+		dev_line_copy(&n->line[LINE_PAN], &od->line[LINE_PAN]);
+	}
+	vs->carr_op = ev->carr_op_id;
+	vs->flags |= VN_INIT;
+	vs->code_off = ev->code_off;
+	vs->code_len = ev->code_len;
+	vs->duration = g->ops[vs->carr_op].time;                       /* set_voice_duration */
+}
+
+/* ---- bytecode interpreter: one chunk of one voice ----------------------- */
+
+__device__ uint32_t run_chunk(Ctx &c, const Instr *code, uint32_t code_len, uint32_t time,
+		uint32_t rem0, float *row_s, float *row_r) {
+	c.sp = 0;
+	if (c.lane == 0) { c.stk_len[0] = time; c.stk_rem[0] = rem0; c.stk_layer[0] = 0; }
+	__syncwarp();
+	c.pma_flag = false; c.pan_dyn = false;
+	c.last_len = 0; c.last_rem = 0;
+	uint32_t pc = 0;
+	while (pc < code_len) {
+		const uint4 raw = __ldg(reinterpret_cast<const uint4*>(code + pc));
+		Instr in;
+		memcpy(&in, &raw, sizeof(in));
+		++pc;
+		const uint32_t n = c.stk_len[c.sp];
+		const uint32_t i0 = c.lane * SPL;
+		switch (in.opcode) {
+		case I_ENTER: {                                            /* generator.c:675-698 */
+			const OpState *o = &c.ops[in.op];
+			const uint32_t flags = o->flags, t = o->time;
+			uint32_t rem = c.stk_rem[c.sp];
+			if (!(flags & ON_TIME_INF) && t < rem) rem = t;
+			const uint32_t len = rem < n ? rem : n;
+			const uint32_t layer = (in.flags & F_LAYER) ? 1u :
+				((in.flags & F_LAYER_PMA) ? (c.pma_flag ? 1u : 0u) : 0u);
+			++c.sp;
+			if (c.lane == 0) { c.stk_len[c.sp] = len; c.stk_rem[c.sp] = rem; c.stk_layer[c.sp] = layer; }
+			__syncwarp();
+			if (len == 0) pc = in.aux;     /* nothing to render: go to the LEAVE */
+			break; }
+		case I_LEAVE: {                                            /* generator.c:716-728 */
+			OpState *o = &c.ops[in.op];
+			const uint32_t len = n, layer = c.stk_layer[c.sp];
+			c.last_len = len; c.last_rem = c.stk_rem[c.sp];
+			--c.sp;
+			const uint32_t plen = c.stk_len[c.sp];
+			if (!(o->flags & ON_TIME_INF)) {
+				if (!layer && len < plen) {
+					float4 v = *B4(c, in.a);
+					if (i0 + 0 >= len) v.x = 0.f;
+					if (i0 + 1 >= len) v.y = 0.f;
+					if (i0 + 2 >= len) v.z = 0.f;
+					if (i0 + 3 >= len) v.w = 0.f;
+					*B4(c, in.a) = v;
+				}
+				if (c.lane == 0) o->time -= len;
+			}
+			__syncwarp();
+			break; }
+		case I_ZERO:
+			*B4(c, in.a) = make_float4(0.f, 0.f, 0.f, 0.f);
+			__syncwarp();
+			break;
+		case I_LINE: {
+			LineState *ls = &c.ops[in.op].line[in.c];
+			if (in.d) line_run(c, ls, in.a, in.b, n);
+			else line_skip(c, ls, n);
+			__syncwarp();
+			break; }
+		case I_RANGE: {                                            /* generator.c:465-467 */
+			float4 p = *B4(c, in.a);
+			const float4 r = *B4(c, in.b), m = *B4(c, in.c);
+			if (i0 + 0 < n) p.x += (r.x - p.x) * m.x;
+			if (i0 + 1 < n) p.y += (r.y - p.y) * m.y;
+			if (i0 + 2 < n) p.z += (r.z - p.z) * m.z;
+			if (i0 + 3 < n) p.w += (r.w - p.w) * m.w;
+			*B4(c, in.a) = p;
+			__syncwarp();
+			break; }
+		case I_PHASOR:
+			phasor_fill(c, in, n);
+			__syncwarp();
+			break;
+		case I_PMA: {                                              /* generator.c:485-490 */
+			OpState *o = &c.ops[in.op];
+			LineState *ls = &o->line[LINE_PMA];
+			uint32_t of = o->flags;
+			bool run;
+			if (c.oc == 0) {
+				/* decided once per reference block (the reference tests it per 1024-block) */
+				run = (ls->v0 != 0.f) || (ls->flags & SAUABI_LINEP_GOAL);
+				of = run ? (of | ON_PMA_RUN) : (of & ~ON_PMA_RUN);
+			} else {
+				run = (of & ON_PMA_RUN) != 0;
+			}
+			__syncwarp();
+			if (c.lane == 0) o->flags = (uint8_t) of;
+			if (run) line_run(c, ls, in.a, NO_BUF, n);
+			else line_skip(c, ls, n);
+			c.pma_flag = run;
+			__syncwarp();
+			break; }
+		case I_WOSC:
+			if (n) wosc_run(c, in, n);
+			__syncwarp();
+			break;
+		case I_CYCLOR:
+			cyclor_fill(c, in, n);
+			__syncwarp();
+			break;
+		case I_RASG:
+			if (n) rasg_run(c, in, n);
+			__syncwarp();
+			break;
+		case I_NOISE:
+			noise_run(c, in, n);
+			__syncwarp();
+			break;
+		case I_MIX: {                                              /* generator.c:384-440 */
+			const uint32_t layer = c.stk_layer[c.sp];
+			float4 iv = make_float4(1.f, 1.f, 1.f, 1.f);
+			if (in.b != NO_BUF) iv = *B4(c, in.b);
+			const float4 av = *B4(c, in.c);
+			float4 ov = *B4(c, in.a);
+			const float x[SPL] = {iv.x, iv.y, iv.z, iv.w};
+			const float a[SPL] = {av.x, av.y, av.z, av.w};
+			float o[SPL] = {ov.x, ov.y, ov.z, ov.w};
+#pragma unroll
+			for (int k = 0; k < SPL; ++k) {
+				if (i0 + k >= n) continue;
+				if (in.flags & F_WAVEENV) {
+					const float s_amp = a[k] * 0.5f;
+					const float s = (x[k] * s_amp) + fabsf(s_amp);
+					o[k] = layer ? o[k] * s : s;
+				} else {
+					const float v = x[k] * a[k];
+					o[k] = layer ? o[k] + v : v;
+				}
+			}
+			*B4(c, in.a) = make_float4(o[0], o[1], o[2], o[3]);
+			__syncwarp();
+			break; }
+		case I_VPAN: {                                             /* generator.c:756-762 */
+			/* the voice-level part runs over the carrier's out_len */
+			if (c.lane == 0) { c.stk_len[0] = c.last_len; c.stk_rem[0] = c.last_rem; }
+			__syncwarp();
+			if (c.last_len == 0) return 0;
+			LineState *ls = &c.ops[in.op].line[LINE_PAN];
+			const bool run = in.d || (ls->flags & SAUABI_LINEP_GOAL);
+			__syncwarp();
+			if (run) line_run(c, ls, in.a, NO_BUF, c.last_len);
+			else line_skip(c, ls, c.last_len);
+			c.pan_dyn = run;
+			__syncwarp();
+			break; }
+		case I_VOUT: {                                             /* generator.c:772-786 */
+			const uint32_t vn = c.stk_len[0];
+			const float amp_scale = c.g->amp_scale;
+			const float4 sv = *B4(c, in.a);
+			float4 pv;
+			if (c.pan_dyn) pv = *B4(c, in.b);
+			else { const float p = c.ops[in.op].line[LINE_PAN].v0; pv = make_float4(p, p, p, p); }
+			float4 s, r;
+			s.x = sv.x * amp_scale; r.x = s.x * pv.x;
+			s.y = sv.y * amp_scale; r.y = s.y * pv.y;
+			s.z = sv.z * amp_scale; r.z = s.z * pv.z;
+			s.w = sv.w * amp_scale; r.w = s.w * pv.w;
+			if (i0 + 3 < vn && ((reinterpret_cast<uintptr_t>(row_s + i0) & 15) == 0)) {
+				*reinterpret_cast<float4*>(row_s + i0) = s;       /* coalesced 128-bit stores */
+				*reinterpret_cast<float4*>(row_r + i0) = r;
+			} else {
+				if (i0 + 0 < vn) { row_s[i0 + 0] = s.x; row_r[i0 + 0] = r.x; }
+				if (i0 + 1 < vn) { row_s[i0 + 1] = s.y; row_r[i0 + 1] = r.y; }
+				if (i0 + 2 < vn) { row_s[i0 + 2] = s.z; row_r[i0 + 2] = r.z; }
+				if (i0 + 3 < vn) { row_s[i0 + 3] = s.w; row_r[i0 + 3] = r.w; }
+			}
+			return vn; }
+		case I_END:
+		default:
+			return c.stk_len[0];
+		}
+	}
+	return 0;
+}
+
+/* ---- render kernel ------------------------------------------------------ */
+
+__global__ void __launch_bounds__(256)
+render_kernel(const CallDesc *calls, uint32_t ncalls, const SegDesc *segs, uint32_t ntasks,
+		const float *tables, uint32_t wave_mask, uint32_t nbufs, uint32_t warps_per_cta) {
+	extern __shared__ __align__(128) unsigned char smem[];
+	uint64_t *bar = reinterpret_cast<uint64_t*>(smem);
+	float *tab = reinterpret_cast<float*>(smem + 128);
+	const uint32_t nslots = __popc(wave_mask);
+	unsigned char *warp_area = smem + 128 + nslots * WAVE_LEN * sizeof(float);
+	const uint32_t per_warp = nbufs * CHUNK * sizeof(float) + 3 * MAX_NEST * sizeof(uint32_t);
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+	/* stage the wave tables this launch needs: TMA bulk copies, one mbarrier */
+	if (threadIdx.x == 0) {
+		mbar_init(bar, 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	__syncthreads();
+	if (threadIdx.x == 0 && nslots) {
+		mbar_expect_tx(bar, nslots * WAVE_LEN * (uint32_t) sizeof(float));
+		uint32_t slot = 0;
+		for (uint32_t w = 0; w < NUM_WAVES; ++w) {
+			if (!(wave_mask & (1u << w))) continue;
+			tma_bulk_g2s(tab + slot * WAVE_LEN, tables + w * WAVE_LEN,
+					WAVE_LEN * sizeof(float), bar);
+			++slot;
+		}
+	}
+	if (nslots) mbar_wait(bar, 0);
+
+	const uint32_t task = blockIdx.x * warps_per_cta + warp;
+	if (task >= ntasks) return;
+	/* task -> (call, voice): binary search on task_base */
+	uint32_t ci = 0, hi = ncalls;
+	while (hi - ci > 1) {
+		const uint32_t mid = (ci + hi) >> 1;
+		if (calls[mid].task_base <= task) ci = mid; else hi = mid;
+	}
+	const CallDesc *cd = &calls[ci];
+	const GenDesc *g = cd->gen;
+	const uint32_t lv = task - cd->task_base;           // local voice index
+	const uint32_t v = g->voice_begin + lv;
+	const uint32_t nlv = g->voice_end - g->voice_begin;
+
+	Ctx c;
+	c.bufs = reinterpret_cast<float*>(warp_area + warp * per_warp);
+	c.stk_len = reinterpret_cast<uint32_t*>(c.bufs + nbufs * CHUNK);
+	c.stk_rem = c.stk_len + MAX_NEST;
+	c.stk_layer = c.stk_rem + MAX_NEST;
+	c.tab = tab;
+	c.wc = reinterpret_cast<const WaveCoeffs*>(tables + NUM_WAVES * WAVE_LEN);
+	c.g = g;
+	c.ops = g->ops;
+	c.wave_mask = wave_mask;
+	c.lane = lane;
+
+	VoiceState *vsp = &g->voices[v];
+	VoiceState vs = *vsp;
+	const uint32_t ev_lo = g->vev_off[v], ev_n = g->vev_off[v + 1] - ev_lo;
+	float *row_s = g->rows_s + (size_t) lv * g->row_len;
+	float *row_r = g->rows_r + (size_t) lv * g->row_len;
+
+	for (uint32_t si = 0; si < cd->nseg; ++si) {
+		const SegDesc sd = segs[cd->seg_off + si];
+		/* this voice's events due at the segment start, in order */
+		while (vs.ev_cursor < ev_n && g->vev_idx[ev_lo + vs.ev_cursor] < sd.ev_end) {
+			if (lane == 0) {
+				apply_event(g, c.wc, &g->events[g->vev_idx[ev_lo + vs.ev_cursor]], &vs);
+				vs.ev_cursor++;
+				*vsp = vs;
+			}
+			__syncwarp();
+			vs = *vsp;
+		}
+		uint32_t run_total = 0;
+		for (uint32_t off = 0; off < sd.len && vs.duration != 0; off += CHUNK) {
+			uint32_t clen = sd.len - off;
+			if (clen > (uint32_t) CHUNK) clen = CHUNK;
+			const uint32_t time = vs.duration < clen ? vs.duration : clen;
+			c.oc = off % REF_BLOCK;
+			uint32_t rem0 = vs.duration;
+			if (sd.len - off < rem0) rem0 = sd.len - off;
+			if (REF_BLOCK - c.oc < rem0) rem0 = REF_BLOCK - c.oc;
+			uint32_t out_len = 0;
+			if (c.ops[vs.carr_op].time > 0)                        /* run_voice, :833-846 */
+				out_len = run_chunk(c, g->code + vs.code_off, vs.code_len, time, rem0,
+						row_s + sd.start + off, row_r + sd.start + off);
+			__syncwarp();
+			vs.duration -= time;
+			run_total += out_len;
+		}
+		if (lane == 0) {
+			g->vlen[(size_t) si * nlv + lv] = run_total;
+			if (run_total) atomicMax(&g->status[1 + si], run_total);
+		}
+	}
+	if (lane == 0) {
+		*vsp = vs;
+		if (vs.duration != 0) atomicOr(&g->status[0], 1u);
+	}
+}
+
+/* ---- mix + clip epilogue ------------------------------------------------- */
+
+__global__ void __launch_bounds__(256)
+mix_kernel(const CallDesc *calls, const SegDesc *segs, uint32_t mode /*0 pcm, 1 float planes*/) {
+	const CallDesc *cd = &calls[blockIdx.y];
+	const GenDesc *g = cd->gen;
+	const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+	if (f >= cd->call_len) return;
+	const uint32_t nlv = g->voice_end - g->voice_begin;
+	/* locate the segment holding frame f */
+	uint32_t si = 0;
+	for (; si < cd->nseg; ++si) {
+		const SegDesc sd = segs[cd->seg_off + si];
+		if (f >= sd.start && f < sd.start + sd.len) break;
+	}
+	float L = 0.f, R = 0.f;
+	if (si < cd->nseg) {
+		const uint32_t fi = f - segs[cd->seg_off + si].start;
+		const uint32_t *vl = g->vlen + (size_t) si * nlv;
+		const float *ps = g->rows_s + f, *pr = g->rows_r + f;
+		const size_t stride = g->row_len;
+		if (fi < g->status[1 + si]) {
+			for (uint32_t lv = 0; lv < nlv; ++lv) {
+				if (fi < vl[lv]) {
+					const float s = ps[(size_t) lv * stride];
+					const float r = pr[(size_t) lv * stride];
+					L = (L + s) - r;                               /* as compiled, Appendix B.3 */
+					R = (R + s) + r;
+				}
+			}
+		}
+	}
+	if (mode == 1) {
+		g->mix[f] = L;
+		g->mix[g->row_len + f] = R;
+		return;
+	}
+	if (cd->stereo) {
+		L = sau::fclampf(L, -1.f, 1.f);
+		R = sau::fclampf(R, -1.f, 1.f);
+		short2 o;
+		o.x = (short) __float2int_rn(L * 32767.f);
+		o.y = (short) __float2int_rn(R * 32767.f);
+		reinterpret_cast<short2*>(g->pcm)[f] = o;
+	} else {
+		float m = (L + R) * 0.5f;
+		m = sau::fclampf(m, -1.f, 1.f);
+		g->pcm[f] = (short) __float2int_rn(m * 32767.f);
+	}
+}
+
+/* float planes (already reduced over ranks) -> int16, for voice-sharded runs */
+__global__ void planes_to_pcm_kernel(const float *mix, uint32_t plane_stride, uint32_t n,
+		uint32_t stereo, int16_t *pcm) {
+	const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+	if (f >= n) return;
+	float L = mix[f], R = mix[plane_stride + f];
+	if (stereo) {
+		L = sau::fclampf(L, -1.f, 1.f);
+		R = sau::fclampf(R, -1.f, 1.f);
+		pcm[2 * f] = (short) __float2int_rn(L * 32767.f);
+		pcm[2 * f + 1] = (short) __float2int_rn(R * 32767.f);
+	} else {
+		float m = sau::fclampf((L + R) * 0.5f, -1.f, 1.f);
+		pcm[f] = (short) __float2int_rn(m * 32767.f);
+	}
+}
+
+/* ---- host-callable launchers -------------------------------------------- */
+
+size_t render_smem_bytes(uint32_t wave_mask, uint32_t nbufs, uint32_t warps) {
+	uint32_t nslots = 0;
+	for (uint32_t w = 0; w < NUM_WAVES; ++w) if (wave_mask & (1u << w)) ++nslots;
+	return 128 + (size_t) nslots * WAVE_LEN * sizeof(float) +
+		(size_t) warps * (nbufs * CHUNK * sizeof(float) + 3 * MAX_NEST * sizeof(uint32_t));
+}
+
+cudaError_t launch_render(const CallDesc *d_calls, uint32_t ncalls, const SegDesc *d_segs,
+		uint32_t ntasks, const float *d_tables, uint32_t wave_mask, uint32_t nbufs,
+		uint32_t warps, cudaStream_t stream) {
+	if (ntasks == 0) return cudaSuccess;
+	const size_t smem = render_smem_bytes(wave_mask, nbufs, warps);
+	static size_t configured = 0;
+	if (smem > configured) {
+		cudaError_t e = cudaFuncSetAttribute(render_kernel,
+				cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+		if (e != cudaSuccess) return e;
+		configured = smem;
+	}
+	const uint32_t grid = (ntasks + warps - 1) / warps;
+	render_kernel<<<grid, warps * 32, smem, stream>>>(d_calls, ncalls, d_segs, ntasks,
+			d_tables, wave_mask, nbufs, warps);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_mix(const CallDesc *d_calls, uint32_t ncalls, const SegDesc *d_segs,
+		uint32_t max_call_len, uint32_t mode, cudaStream_t stream) {
+	if (ncalls == 0 || max_call_len == 0) return cudaSuccess;
+	dim3 grid((max_call_len + 255) / 256, ncalls);
+	mix_kernel<<<grid, 256, 0, stream>>>(d_calls, d_segs, mode);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_planes_to_pcm(const float *d_mix, uint32_t plane_stride, uint32_t n,
+		uint32_t stereo, int16_t *d_pcm, cudaStream_t stream) {
+	if (!n) return cudaSuccess;
+	planes_to_pcm_kernel<<<(n + 255) / 256, 256, 0, stream>>>(d_mix, plane_stride, n, stereo, d_pcm);
+	return cudaGetLastError();
+}
+
+} // namespace saugen

@@ -1,0 +1,848 @@
+/* runtime.cpp -- host side of the B200 generator back end and its C ABI
+ * (include/saugen_b200.h).
+ *
+ * create : flattens the pointer-rich sauProgram (sau/program.h:212-265) into
+ *          index-based records, walks the event list once to mirror the
+ *          modulator-graph topology (the mod-list pointer updates of
+ *          update_op, sau/generator.c:316-339) and compiles, per event, the
+ *          voice's operator walk (run_voice/run_block/mix_add,
+ *          generator.c:448-788) into bytecode; uploads everything.
+ * run    : replays sauGenerator_run's event/time interleaving
+ *          (generator.c:915-949) as a list of segments for this call, then
+ *          launches render_kernel + mix_kernel once.  All sample-rate work and
+ *          all generator state stay on the device; the host never computes
+ *          audio.  There is no CPU fallback.
+ */
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include <map>
+#include <mutex>
+
+#include "../../include/saugen_b200.h"
+#include "device_types.h"
+
+namespace saugen {
+size_t render_smem_bytes(uint32_t wave_mask, uint32_t nbufs, uint32_t warps);
+cudaError_t launch_render(const CallDesc *d_calls, uint32_t ncalls, const SegDesc *d_segs,
+		uint32_t ntasks, const float *d_tables, uint32_t wave_mask, uint32_t nbufs,
+		uint32_t warps, cudaStream_t stream);
+cudaError_t launch_mix(const CallDesc *d_calls, uint32_t ncalls, const SegDesc *d_segs,
+		uint32_t max_call_len, uint32_t mode, cudaStream_t stream);
+cudaError_t launch_planes_to_pcm(const float *d_mix, uint32_t plane_stride, uint32_t n,
+		uint32_t stereo, int16_t *d_pcm, cudaStream_t stream);
+const saugen_WaveTables *builtin_wave_tables();
+}
+
+using namespace saugen;
+
+static thread_local std::string g_err;
+static void set_err(const char *what, cudaError_t e) {
+	char b[256];
+	snprintf(b, sizeof b, "%s: %s", what, e == cudaSuccess ? "failed" : cudaGetErrorString(e));
+	g_err = b;
+	fprintf(stderr, "saugen_b200: error: %s\n", b);
+}
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { set_err(#call, e_); goto fail; } } while (0)
+
+static uint32_t ms_in_samples(uint64_t ms, uint64_t srate, int *carry) {   /* sau/math.h:35-46 */
+	uint64_t t = ms * srate;
+	if (carry) { t += *carry; *carry = (int) (t % 1000); }
+	return (uint32_t) (t / 1000);
+}
+
+/* ---- device wave-table blocks, shared by content ------------------------ */
+
+struct TableBlock { float *d; };
+static std::mutex g_tab_mu;
+static std::map<std::pair<int, uint64_t>, TableBlock> g_tabs;
+
+static float *get_device_tables(int device, const saugen_WaveTables *t) {
+	std::vector<float> host((size_t) NUM_WAVES * WAVE_LEN + sizeof(WaveCoeffs) / sizeof(float));
+	for (int w = 0; w < NUM_WAVES; ++w)
+		memcpy(&host[(size_t) w * WAVE_LEN], t->pilut[w], sizeof(float) * WAVE_LEN);
+	WaveCoeffs wc;
+	for (int w = 0; w < NUM_WAVES; ++w) {
+		wc.diff_scale[w] = t->amp_scale[w] * 0.125f * 4294967296.f;   /* wave.h:144-145 */
+		wc.diff_offset[w] = t->amp_dc[w];
+		wc.amp256[w] = t->amp_scale[w] * 256.f;
+		wc.phase_adj[w] = t->phase_adj[w];
+	}
+	memcpy(&host[(size_t) NUM_WAVES * WAVE_LEN], &wc, sizeof(wc));
+	uint64_t h = 1469598103934665603ull;
+	const unsigned char *b = (const unsigned char*) host.data();
+	for (size_t i = 0; i < host.size() * sizeof(float); ++i) { h ^= b[i]; h *= 1099511628211ull; }
+	std::lock_guard<std::mutex> lk(g_tab_mu);
+	auto key = std::make_pair(device, h);
+	auto it = g_tabs.find(key);
+	if (it != g_tabs.end()) return it->second.d;
+	float *d = nullptr;
+	if (cudaMalloc(&d, host.size() * sizeof(float)) != cudaSuccess) return nullptr;
+	if (cudaMemcpy(d, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
+		cudaFree(d);
+		return nullptr;
+	}
+	g_tabs[key] = TableBlock{d};
+	return d;
+}
+
+/* ---- generator object ---------------------------------------------------- */
+
+struct HostOp {
+	bool inited = false;
+	uint8_t type = 0;
+	const sauabi_ProgramIDArr *mods[SAUABI_POP_NAMED] = {0};   /* index = use type */
+};
+
+struct saugen_Generator {
+	const sauabi_Program *prg = nullptr;
+	uint32_t srate = 0;
+	int device = 0;
+	cudaStream_t stream = nullptr;
+	bool own_stream = false;
+	uint32_t vo_count = 0, op_count = 0, nlv = 0;
+	uint32_t voice_begin = 0, voice_end = 0;
+	uint32_t row_len = 0, nbufs = 1, wave_mask = 0, seg_cap = 0;
+	float amp_scale = 0.f;
+	/* timeline (host-only integer bookkeeping) */
+	std::vector<uint64_t> ev_time;     // absolute sample time of each event
+	size_t next_event = 0;
+	uint64_t cur_time = 0;
+	bool ended = false;
+	/* device */
+	GenDesc h_desc;
+	GenDesc *d_desc = nullptr;
+	float *d_tables = nullptr;
+	void *d_ops = nullptr, *d_voices = nullptr, *d_events = nullptr, *d_opdata = nullptr,
+	     *d_code = nullptr, *d_vev_off = nullptr, *d_vev_idx = nullptr;
+	float *d_rows_s = nullptr, *d_rows_r = nullptr, *d_mix = nullptr;
+	uint32_t *d_vlen = nullptr, *d_status = nullptr;
+	int16_t *d_pcm = nullptr;
+	CallDesc *d_call = nullptr;
+	SegDesc *d_segs = nullptr;
+	/* pinned host staging */
+	uint32_t *h_status = nullptr;
+	int16_t *h_pcm = nullptr;
+	CallDesc *h_call = nullptr;
+	SegDesc *h_segs = nullptr;
+	uint64_t counters[4] = {0, 0, 0, 0};
+	std::vector<SegDesc> segs_tmp;
+};
+
+/* ---- bytecode compiler --------------------------------------------------- */
+
+struct Compiler {
+	const std::vector<HostOp> &ops;
+	std::vector<Instr> out;
+	std::vector<char> onstack;
+	uint32_t max_buf = 0;
+	bool too_deep = false;
+	int depth = 0;
+	Compiler(const std::vector<HostOp> &o) : ops(o), onstack(o.size(), 0) {}
+
+	void emit(uint8_t opc, uint32_t op, uint32_t a, uint32_t b = NO_BUF, uint32_t c = NO_BUF,
+			uint32_t d = NO_BUF, uint32_t e = NO_BUF, uint16_t flags = 0) {
+		Instr i;
+		i.opcode = opc; i.a = (uint8_t) a; i.b = (uint8_t) b; i.c = (uint8_t) c;
+		i.d = (uint8_t) d; i.e = (uint8_t) e; i.flags = flags; i.op = op; i.aux = 0;
+		const uint32_t bs[5] = {a, b, c, d, e};
+		for (uint32_t x : bs) if (x != NO_BUF && opc != I_LINE && x + 1 > max_buf) max_buf = x + 1;
+		if (opc == I_LINE) { if (a + 1 > max_buf) max_buf = a + 1; if (b != NO_BUF && b + 1 > max_buf) max_buf = b + 1; }
+		if (max_buf >= 250) too_deep = true;
+		out.push_back(i);
+	}
+	static uint32_t cnt(const sauabi_ProgramIDArr *a) { return a ? a->count : 0; }
+
+	/* run_param_with_rangemod, generator.c:448-477 */
+	void param(uint32_t op, uint32_t B, int par, int rpar, int mods_use, int rmods_use,
+			uint32_t mulbuf, uint32_t reused_freq, bool is_freq) {
+		const HostOp &n = ops[op];
+		const uint32_t freq = reused_freq != NO_BUF ? reused_freq : (is_freq ? B : NO_BUF);
+		emit(I_LINE, op, B, mulbuf, par, 1);
+		const sauabi_ProgramIDArr *rm = n.mods[rmods_use], *m = n.mods[mods_use];
+		if (cnt(rm) > 0) {
+			emit(I_LINE, op, B + 1, mulbuf, rpar, 1);
+			for (uint32_t i = 0; i < rm->count; ++i)
+				visit(rm->ids[i], B + 2, freq, true, i > 0 ? F_LAYER : 0);
+			emit(I_RANGE, 0, B, B + 1, B + 2);
+		} else {
+			emit(I_LINE, op, 0, NO_BUF, rpar, 0);
+		}
+		for (uint32_t i = 0; i < cnt(m); ++i)
+			visit(m->ids[i], B, freq, false, F_LAYER);
+	}
+
+	/* run_block + run_block_{amp,noiseg,wosc,rasg}, generator.c:505-729 */
+	void visit(uint32_t op, uint32_t base, uint32_t parent_freq, bool wave_env, uint16_t layer_flags) {
+		if (op >= ops.size() || !ops[op].inited) {     /* never prepared: renders nothing */
+			if (!(layer_flags & (F_LAYER | F_LAYER_PMA))) emit(I_ZERO, 0, base);
+			return;
+		}
+		if (onstack[op]) { emit(I_ZERO, 0, base); return; }   /* generator.c:685-689 */
+		if (++depth >= MAX_NEST - 1) { too_deep = true; --depth; return; }
+		onstack[op] = 1;
+		const HostOp &n = ops[op];
+		const size_t enter_at = out.size();
+		emit(I_ENTER, op, base, NO_BUF, NO_BUF, NO_BUF, NO_BUF, layer_flags);
+		const uint16_t mixf = wave_env ? F_WAVEENV : 0;
+		switch (n.type) {
+		case SAUABI_POPT_amp:
+		case SAUABI_POPT_noise: {
+			param(op, base + 1, LINE_AMP, LINE_AMP2, SAUABI_POP_amod, SAUABI_POP_ramod,
+					NO_BUF, NO_BUF, false);
+			if (n.type == SAUABI_POPT_noise) {
+				emit(I_NOISE, op, base + 2);
+				emit(I_MIX, 0, base, base + 2, base + 1, NO_BUF, NO_BUF, mixf);
+			} else {
+				emit(I_MIX, 0, base, NO_BUF, base + 1, NO_BUF, NO_BUF, mixf);
+			}
+			break; }
+		case SAUABI_POPT_wave: {
+			const uint32_t phase = base + 1, freq = base + 2;
+			param(op, freq, LINE_FREQ, LINE_FREQ2, SAUABI_POP_fmod, SAUABI_POP_rfmod,
+					parent_freq, NO_BUF, true);
+			uint32_t pm = NO_BUF, fpm = NO_BUF;
+			const sauabi_ProgramIDArr *pl = n.mods[SAUABI_POP_pmod], *fl = n.mods[SAUABI_POP_fpmod],
+				*al = n.mods[SAUABI_POP_apmod];
+			for (uint32_t i = 0; i < cnt(pl); ++i) visit(pl->ids[i], base + 3, freq, false, i > 0 ? F_LAYER : 0);
+			if (cnt(pl)) pm = base + 3;
+			for (uint32_t i = 0; i < cnt(fl); ++i) visit(fl->ids[i], base + 4, freq, false, i > 0 ? F_LAYER : 0);
+			if (cnt(fl)) fpm = base + 4;
+			emit(I_PHASOR, op, phase, freq, pm, fpm);
+			param(op, base + 3, LINE_AMP, LINE_AMP2, SAUABI_POP_amod, SAUABI_POP_ramod,
+					NO_BUF, freq, false);
+			emit(I_PMA, op, base + 5);
+			for (uint32_t i = 0; i < cnt(al); ++i)
+				visit(al->ids[i], base + 5, freq, false, i > 0 ? F_LAYER : F_LAYER_PMA);
+			emit(I_WOSC, op, base + 4, phase, base + 5, NO_BUF, NO_BUF, cnt(al) ? F_HAS_APMODS : 0);
+			emit(I_MIX, 0, base, base + 4, base + 3, NO_BUF, NO_BUF, mixf);
+			break; }
+		case SAUABI_POPT_raseg: {
+			const uint32_t cycle = base + 1, rasg = base + 2, freq = base + 3;
+			param(op, freq, LINE_FREQ, LINE_FREQ2, SAUABI_POP_fmod, SAUABI_POP_rfmod,
+					parent_freq, NO_BUF, true);
+			uint32_t pm = NO_BUF, fpm = NO_BUF;
+			const sauabi_ProgramIDArr *pl = n.mods[SAUABI_POP_pmod], *fl = n.mods[SAUABI_POP_fpmod],
+				*al = n.mods[SAUABI_POP_apmod];
+			for (uint32_t i = 0; i < cnt(pl); ++i) visit(pl->ids[i], base + 4, freq, false, i > 0 ? F_LAYER : 0);
+			if (cnt(pl)) pm = base + 4;
+			for (uint32_t i = 0; i < cnt(fl); ++i) visit(fl->ids[i], base + 5, freq, false, i > 0 ? F_LAYER : 0);
+			if (cnt(fl)) fpm = base + 5;
+			emit(I_CYCLOR, op, cycle, rasg, freq, pm, fpm);
+			param(op, base + 4, LINE_AMP, LINE_AMP2, SAUABI_POP_amod, SAUABI_POP_ramod,
+					NO_BUF, freq, false);
+			emit(I_PMA, op, base + 5);
+			for (uint32_t i = 0; i < cnt(al); ++i)
+				visit(al->ids[i], base + 5, freq, false, i > 0 ? F_LAYER : F_LAYER_PMA);
+			emit(I_RASG, op, rasg, cycle, base + 5, NO_BUF, NO_BUF, cnt(al) ? F_HAS_APMODS : 0);
+			emit(I_MIX, 0, base, rasg, base + 4, NO_BUF, NO_BUF, mixf);
+			break; }
+		}
+		out[enter_at].aux = (uint32_t) out.size();   /* index of the LEAVE */
+		emit(I_LEAVE, op, base, NO_BUF, NO_BUF, NO_BUF, NO_BUF, layer_flags);
+		onstack[op] = 0;
+		--depth;
+	}
+
+	/* run_voice + mix_add, generator.c:749-788,833-846 */
+	void voice(uint32_t carr) {
+		out.clear();
+		if (carr >= ops.size() || !ops[carr].inited) { emit(I_END, 0, 0); return; }
+		visit(carr, 0, NO_BUF, false, 0);
+		const HostOp &n = ops[carr];
+		const uint32_t fb = n.type == SAUABI_POPT_wave ? 2 : n.type == SAUABI_POPT_raseg ? 3 : 0;
+		const sauabi_ProgramIDArr *cl = n.mods[SAUABI_POP_camod];
+		emit(I_VPAN, carr, 1 + fb, NO_BUF, NO_BUF, cnt(cl) ? 1 : 0);
+		for (uint32_t i = 0; i < cnt(cl); ++i)
+			visit(cl->ids[i], 1 + fb, fb ? fb : NO_BUF, false, F_LAYER);
+		emit(I_VOUT, carr, 0, 1 + fb);
+		emit(I_END, 0, 0);
+	}
+};
+
+static void flatten_line(LineDelta *d, const sauabi_Line *s, uint32_t srate) {
+	memset(d, 0, sizeof(*d));
+	if (!s) return;
+	d->present = 1;
+	d->v0 = s->v0; d->vt = s->vt;
+	d->end_samples = ms_in_samples(s->time_ms, srate, NULL);   /* line.c:325 */
+	d->type = s->type; d->flags = s->flags;
+}
+
+template <typename T>
+static cudaError_t upload(void **dptr, const std::vector<T> &v) {
+	size_t bytes = v.size() * sizeof(T);
+	if (bytes == 0) bytes = sizeof(T);
+	cudaError_t e = cudaMalloc(dptr, bytes);
+	if (e != cudaSuccess) return e;
+	if (!v.empty()) e = cudaMemcpy(*dptr, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+	return e;
+}
+
+extern "C" void saugen_destroy(saugen_Generator *o);
+
+extern "C" saugen_Generator *saugen_create(const sauabi_Program *prg, uint32_t srate,
+		const saugen_WaveTables *tables, const saugen_Options *opt) {
+	saugen_Options defopt;
+	memset(&defopt, 0, sizeof defopt);
+	if (!opt) opt = &defopt;
+	if (!prg || !srate) { g_err = "saugen_create: NULL program or zero sample rate"; return nullptr; }
+	int ndev = 0;
+	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || opt->device >= ndev) {
+		set_err("saugen_create: no usable CUDA device (this back end has no CPU path)", cudaGetLastError());
+		return nullptr;
+	}
+	saugen_Generator *o = new saugen_Generator();
+	std::vector<HostOp> hops(prg->op_count);
+	std::vector<EventRec> events(prg->ev_count);
+	std::vector<OpDataRec> opdata;
+	std::vector<Instr> code;
+	std::vector<std::vector<uint32_t>> vev(prg->vo_count);
+	std::vector<uint32_t> vev_off, vev_idx;
+	std::vector<uint32_t> vcarr(prg->vo_count, 0xffffffffu);
+	std::vector<std::pair<uint32_t, uint32_t>> vprog(prg->vo_count, {0u, 0u});
+	if (!tables) tables = saugen::builtin_wave_tables();
+
+	o->prg = prg; o->srate = srate; o->device = opt->device;
+	o->vo_count = prg->vo_count; o->op_count = prg->op_count;
+	o->voice_begin = 0; o->voice_end = prg->vo_count;
+	if (opt->voice_end > opt->voice_begin) {
+		o->voice_begin = opt->voice_begin < prg->vo_count ? opt->voice_begin : prg->vo_count;
+		o->voice_end = opt->voice_end < prg->vo_count ? opt->voice_end : prg->vo_count;
+	}
+	o->nlv = o->voice_end - o->voice_begin;
+	o->row_len = opt->max_call_len ? opt->max_call_len : ms_in_samples(256, srate, NULL);  /* saugns.c:471 */
+	o->row_len = (o->row_len + 3u) & ~3u;
+	if (o->row_len < 4) o->row_len = 4;
+	o->amp_scale = 0.5f * prg->ampmult;                           /* generator.c:183-185 */
+	if (prg->mode & SAUABI_PMODE_AMP_DIV_VOICES) o->amp_scale /= (float) prg->vo_count;
+
+	/* event timeline with carry (generator.c:181-192) */
+	{
+		int carry = 0;
+		uint64_t t = 0;
+		o->ev_time.resize(prg->ev_count);
+		for (size_t i = 0; i < prg->ev_count; ++i) {
+			t += ms_in_samples(prg->events[i].wait_ms, srate, &carry);
+			o->ev_time[i] = t;
+		}
+	}
+	/* flatten events + mirror the graph + compile voice programs */
+	{
+		Compiler comp(hops);
+		for (size_t ei = 0; ei < prg->ev_count; ++ei) {
+			const sauabi_ProgramEvent *pe = &prg->events[ei];
+			EventRec &er = events[ei];
+			er.vo_id = pe->vo_id;
+			er.carr_op_id = pe->carr_op_id;
+			er.opdata_off = (uint32_t) opdata.size();
+			er.opdata_count = pe->op_data_count;
+			for (uint32_t k = 0; k < pe->op_data_count; ++k) {
+				const sauabi_ProgramOpData *od = &pe->op_data[k];
+				OpDataRec r;
+				memset(&r, 0, sizeof r);
+				r.id = od->id; r.params = od->params;
+				r.time_samples = ms_in_samples(od->time.v_ms, srate, NULL);  /* generator.c:332 */
+				r.time_flags = od->time.flags;
+				r.type = od->type; r.use_type = od->use_type;
+				r.mode_main = od->mode.main;
+				flatten_line(&r.line[LINE_AMP], od->amp, srate);
+				flatten_line(&r.line[LINE_AMP2], od->amp2, srate);
+				flatten_line(&r.line[LINE_PAN], od->pan, srate);
+				flatten_line(&r.line[LINE_FREQ], od->freq, srate);
+				flatten_line(&r.line[LINE_FREQ2], od->freq2, srate);
+				flatten_line(&r.line[LINE_PMA], od->pm_a, srate);
+				r.phase = od->phase; r.seed = od->seed;
+				if (od->type == SAUABI_POPT_raseg) {
+					r.ras_flags = od->mode.ras.flags; r.ras_func = od->mode.ras.func;
+					r.ras_level = od->mode.ras.level; r.ras_alpha = od->mode.ras.alpha;
+				}
+				if (od->type == SAUABI_POPT_wave) {
+					if (od->params & SAUABI_POPP_MODE) o->wave_mask |= 1u << (od->mode.main % NUM_WAVES);
+					o->wave_mask |= 1u << SAUABI_WAVE_sin;   /* sau_init_WOsc default */
+				}
+				opdata.push_back(r);
+				if (od->id < hops.size()) {
+					HostOp &h = hops[od->id];
+					if (!h.inited) { h.inited = true; h.type = od->type; }
+					if (od->type >= SAUABI_POPT_wave) {            /* generator.c:316-320 */
+						if (od->fmods) h.mods[SAUABI_POP_fmod] = od->fmods;
+						if (od->rfmods) h.mods[SAUABI_POP_rfmod] = od->rfmods;
+						if (od->pmods) h.mods[SAUABI_POP_pmod] = od->pmods;
+						if (od->apmods) h.mods[SAUABI_POP_apmod] = od->apmods;
+						if (od->fpmods) h.mods[SAUABI_POP_fpmod] = od->fpmods;
+					}
+					if (od->camods) h.mods[SAUABI_POP_camod] = od->camods;  /* :337-339 */
+					if (od->amods) h.mods[SAUABI_POP_amod] = od->amods;
+					if (od->ramods) h.mods[SAUABI_POP_ramod] = od->ramods;
+				}
+			}
+			er.code_off = 0; er.code_len = 0;
+			if (pe->vo_id != SAUABI_PVO_NO_ID && pe->vo_id < prg->vo_count) {
+				vcarr[pe->vo_id] = pe->carr_op_id;
+				comp.voice(pe->carr_op_id);
+				/* reuse the voice's previous program when the walk is unchanged */
+				auto &pv = vprog[pe->vo_id];
+				bool same = pv.second == comp.out.size() && pv.second > 0 &&
+					memcmp(&code[pv.first], comp.out.data(), pv.second * sizeof(Instr)) == 0;
+				if (!same) {
+					pv.first = (uint32_t) code.size();
+					pv.second = (uint32_t) comp.out.size();
+					code.insert(code.end(), comp.out.begin(), comp.out.end());
+				}
+				er.code_off = pv.first; er.code_len = pv.second;
+				vev[pe->vo_id].push_back((uint32_t) ei);
+			}
+		}
+		if (comp.too_deep) {
+			g_err = "saugen_create: operator nesting too deep for the device interpreter";
+			fprintf(stderr, "saugen_b200: error: %s\n", g_err.c_str());
+			delete o;
+			return nullptr;
+		}
+		o->nbufs = comp.max_buf ? comp.max_buf : 1;
+	}
+	vev_off.resize(prg->vo_count + 1);
+	for (uint32_t v = 0; v < prg->vo_count; ++v) {
+		vev_off[v] = (uint32_t) vev_idx.size();
+		vev_idx.insert(vev_idx.end(), vev[v].begin(), vev[v].end());
+	}
+	vev_off[prg->vo_count] = (uint32_t) vev_idx.size();
+
+	/* ---- device allocation ---- */
+	CK(cudaSetDevice(o->device));
+	if (opt->stream) o->stream = (cudaStream_t) opt->stream;
+	else { CK(cudaStreamCreateWithFlags(&o->stream, cudaStreamNonBlocking)); o->own_stream = true; }
+	o->d_tables = get_device_tables(o->device, tables);
+	if (!o->d_tables) { set_err("wave table upload", cudaGetLastError()); goto fail; }
+	{
+		size_t nops = prg->op_count ? prg->op_count : 1, nvo = prg->vo_count ? prg->vo_count : 1;
+		CK(cudaMalloc(&o->d_ops, nops * sizeof(OpState)));
+		CK(cudaMemset(o->d_ops, 0, nops * sizeof(OpState)));
+		CK(cudaMalloc(&o->d_voices, nvo * sizeof(VoiceState)));
+		CK(cudaMemset(o->d_voices, 0, nvo * sizeof(VoiceState)));
+	}
+	CK(upload(&o->d_events, events));
+	CK(upload(&o->d_opdata, opdata));
+	CK(upload(&o->d_code, code));
+	CK(upload(&o->d_vev_off, vev_off));
+	CK(upload(&o->d_vev_idx, vev_idx));
+	{
+		size_t nl = o->nlv ? o->nlv : 1;
+		o->seg_cap = 64;
+		CK(cudaMalloc(&o->d_rows_s, nl * o->row_len * sizeof(float)));
+		CK(cudaMalloc(&o->d_rows_r, nl * o->row_len * sizeof(float)));
+		CK(cudaMalloc(&o->d_vlen, (size_t) o->seg_cap * nl * sizeof(uint32_t)));
+		CK(cudaMalloc(&o->d_status, (1 + o->seg_cap) * sizeof(uint32_t)));
+		CK(cudaMalloc(&o->d_mix, 2 * (size_t) o->row_len * sizeof(float)));
+		CK(cudaMalloc(&o->d_pcm, 2 * (size_t) o->row_len * sizeof(int16_t)));
+		CK(cudaMalloc(&o->d_call, sizeof(CallDesc)));
+		CK(cudaMalloc(&o->d_segs, o->seg_cap * sizeof(SegDesc)));
+		CK(cudaMallocHost(&o->h_status, (1 + o->seg_cap) * sizeof(uint32_t)));
+		CK(cudaMallocHost(&o->h_pcm, 2 * (size_t) o->row_len * sizeof(int16_t)));
+		CK(cudaMallocHost(&o->h_call, sizeof(CallDesc)));
+		CK(cudaMallocHost(&o->h_segs, o->seg_cap * sizeof(SegDesc)));
+	}
+	{
+		GenDesc &d = o->h_desc;
+		memset(&d, 0, sizeof d);
+		d.ops = (OpState*) o->d_ops; d.voices = (VoiceState*) o->d_voices;
+		d.events = (const EventRec*) o->d_events; d.opdata = (const OpDataRec*) o->d_opdata;
+		d.code = (const Instr*) o->d_code;
+		d.vev_off = (const uint32_t*) o->d_vev_off; d.vev_idx = (const uint32_t*) o->d_vev_idx;
+		d.rows_s = o->d_rows_s; d.rows_r = o->d_rows_r;
+		d.vlen = o->d_vlen; d.status = o->d_status; d.vlen_cap = o->seg_cap;
+		d.mix = o->d_mix; d.pcm = o->d_pcm;
+		d.vo_count = o->vo_count; d.op_count = o->op_count;
+		d.voice_begin = o->voice_begin; d.voice_end = o->voice_end;
+		d.row_len = o->row_len; d.nbufs = o->nbufs; d.srate = srate;
+		d.coeff = (float) (4294967296.0 / srate);                 /* wosc.h:30, math.h:386 */
+		d.amp_scale = o->amp_scale;
+		d.wave_mask = o->wave_mask; d.tables = o->d_tables;
+		CK(cudaMalloc(&o->d_desc, sizeof(GenDesc)));
+		CK(cudaMemcpy(o->d_desc, &d, sizeof d, cudaMemcpyHostToDevice));
+	}
+	return o;
+fail:
+	saugen_destroy(o);
+	return nullptr;
+}
+
+extern "C" void saugen_destroy(saugen_Generator *o) {
+	if (!o) return;
+	cudaSetDevice(o->device);
+	if (o->stream) cudaStreamSynchronize(o->stream);
+	void *dev[] = {o->d_ops, o->d_voices, o->d_events, o->d_opdata, o->d_code, o->d_vev_off,
+		o->d_vev_idx, o->d_rows_s, o->d_rows_r, o->d_vlen, o->d_status, o->d_mix, o->d_pcm,
+		o->d_call, o->d_segs, o->d_desc};
+	for (void *p : dev) if (p) cudaFree(p);
+	void *host[] = {o->h_status, o->h_pcm, o->h_call, o->h_segs};
+	for (void *p : host) if (p) cudaFreeHost(p);
+	if (o->own_stream && o->stream) cudaStreamDestroy(o->stream);
+	delete o;
+}
+
+/* Replay of the PROCESS loop of sauGenerator_run (generator.c:915-949): cut the
+ * call into inter-event segments; ev_end says which events are due by then. */
+static void plan_call(saugen_Generator *o, uint32_t buf_len, std::vector<SegDesc> &segs) {
+	segs.clear();
+	uint64_t t = o->cur_time;
+	const uint64_t t_end = t + buf_len;
+	size_t ev = o->next_event;
+	const size_t nev = o->ev_time.size();
+	while (t < t_end) {
+		while (ev < nev && o->ev_time[ev] <= t) ++ev;
+		uint64_t stop = t_end;
+		if (ev < nev && o->ev_time[ev] < stop) stop = o->ev_time[ev];
+		SegDesc s;
+		s.start = (uint32_t) (t - o->cur_time);
+		s.len = (uint32_t) (stop - t);
+		s.ev_end = (uint32_t) ev;
+		segs.push_back(s);
+		t = stop;
+	}
+	if (buf_len == 0) {                  /* events due now are still handled */
+		while (ev < nev && o->ev_time[ev] <= t) ++ev;
+		SegDesc s; s.start = 0; s.len = 0; s.ev_end = (uint32_t) ev;
+		segs.push_back(s);
+	}
+	o->next_event = ev;
+	o->cur_time = t_end;
+}
+
+static uint32_t pick_warps(uint32_t ntasks, uint32_t wave_mask, uint32_t nbufs) {
+	uint32_t warps = 8;
+	while (warps > 1 && (ntasks + warps - 1) / warps < 148) warps >>= 1;   /* fill the 148 SMs */
+	while (warps > 1 && render_smem_bytes(wave_mask, nbufs, warps) > 200 * 1024) warps >>= 1;
+	return warps;
+}
+
+/* mode: 0 = PCM in device memory, 1 = float planes */
+static int run_common(saugen_Generator *o, size_t buf_len, int stereo, uint32_t mode,
+		size_t *out_len, int *more_out) {
+	if (!o) return -1;
+	if (buf_len > o->row_len) { g_err = "saugen_run: buf_len exceeds max_call_len"; return -1; }
+	cudaSetDevice(o->device);
+	if (o->ended) {
+		cudaMemsetAsync(o->d_pcm, 0, 2 * (size_t) o->row_len * sizeof(int16_t), o->stream);
+		if (out_len) *out_len = 0;
+		*more_out = 0;
+		return 0;
+	}
+	std::vector<SegDesc> &segs = o->segs_tmp;
+	plan_call(o, (uint32_t) buf_len, segs);
+	if (segs.size() > o->seg_cap) {
+		/* grow the per-segment arrays (rare: > 64 events inside one call) */
+		uint32_t cap = o->seg_cap;
+		while (cap < segs.size()) cap *= 2;
+		size_t nl = o->nlv ? o->nlv : 1;
+		cudaStreamSynchronize(o->stream);
+		cudaFree(o->d_vlen); cudaFree(o->d_status); cudaFree(o->d_segs);
+		cudaFreeHost(o->h_status); cudaFreeHost(o->h_segs);
+		if (cudaMalloc(&o->d_vlen, (size_t) cap * nl * sizeof(uint32_t)) != cudaSuccess ||
+		    cudaMalloc(&o->d_status, (1 + cap) * sizeof(uint32_t)) != cudaSuccess ||
+		    cudaMalloc(&o->d_segs, cap * sizeof(SegDesc)) != cudaSuccess ||
+		    cudaMallocHost(&o->h_status, (1 + cap) * sizeof(uint32_t)) != cudaSuccess ||
+		    cudaMallocHost(&o->h_segs, cap * sizeof(SegDesc)) != cudaSuccess) {
+			set_err("saugen_run: segment table growth", cudaGetLastError());
+			return -1;
+		}
+		o->seg_cap = cap;
+		o->h_desc.vlen = o->d_vlen; o->h_desc.status = o->d_status; o->h_desc.vlen_cap = cap;
+		cudaMemcpy(o->d_desc, &o->h_desc, sizeof(GenDesc), cudaMemcpyHostToDevice);
+	}
+	const uint32_t nseg = (uint32_t) segs.size();
+	memcpy(o->h_segs, segs.data(), nseg * sizeof(SegDesc));
+	CallDesc &cd = *o->h_call;
+	cd.gen = o->d_desc; cd.call_len = (uint32_t) buf_len; cd.nseg = nseg; cd.seg_off = 0;
+	cd.task_base = 0; cd.stereo = stereo ? 1 : 0; cd._pad = 0;
+	cudaError_t e;
+	e = cudaMemcpyAsync(o->d_segs, o->h_segs, nseg * sizeof(SegDesc), cudaMemcpyHostToDevice, o->stream);
+	if (e == cudaSuccess) e = cudaMemcpyAsync(o->d_call, o->h_call, sizeof(CallDesc), cudaMemcpyHostToDevice, o->stream);
+	if (e == cudaSuccess) e = cudaMemsetAsync(o->d_status, 0, (1 + nseg) * sizeof(uint32_t), o->stream);
+	if (e == cudaSuccess) {
+		const uint32_t warps = pick_warps(o->nlv, o->wave_mask, o->nbufs);
+		e = launch_render(o->d_call, 1, o->d_segs, o->nlv, o->d_tables, o->wave_mask, o->nbufs,
+				warps, o->stream);
+		o->counters[0]++;
+	}
+	if (e == cudaSuccess) {
+		e = launch_mix(o->d_call, 1, o->d_segs, (uint32_t) buf_len, mode, o->stream);
+		o->counters[1]++;
+	}
+	if (e == cudaSuccess) e = cudaMemcpyAsync(o->h_status, o->d_status, (1 + nseg) * sizeof(uint32_t),
+			cudaMemcpyDeviceToHost, o->stream);
+	if (e != cudaSuccess) { set_err("saugen_run: launch", e); if (out_len) *out_len = 0; return -1; }
+	(void) more_out;
+	return 1;   /* caller finishes after its own D2H + sync via finish_call */
+}
+
+/* After the stream is synchronised: out_len / return value (generator.c:938-972). */
+static int finish_call(saugen_Generator *o, size_t buf_len, size_t *out_len) {
+	const uint32_t nseg = (uint32_t) o->segs_tmp.size();
+	size_t gen_len = 0;
+	for (uint32_t s = 0; s + 1 < nseg; ++s) gen_len += o->segs_tmp[s].len;
+	if (nseg) gen_len += o->h_status[1 + (nseg - 1)];
+	const bool alive = o->h_status[0] != 0;
+	const bool more = alive || o->next_event < o->ev_time.size();
+	if (!more) {
+		o->ended = true;
+		if (out_len) *out_len = gen_len;
+		return 0;
+	}
+	if (out_len) *out_len = buf_len;
+	return 1;
+}
+
+extern "C" int saugen_run(saugen_Generator *o, int16_t *buf, size_t buf_len, int stereo,
+		size_t *out_len) {
+	int more = 0;
+	int r = run_common(o, buf_len, stereo, 0, out_len, &more);
+	if (r < 0) return r;
+	const size_t bytes = buf_len * (stereo ? 2 : 1) * sizeof(int16_t);
+	if (r == 0) { if (buf) memset(buf, 0, bytes); return 0; }
+	cudaError_t e = cudaMemcpyAsync(o->h_pcm, o->d_pcm, bytes, cudaMemcpyDeviceToHost, o->stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(o->stream);
+	if (e != cudaSuccess) { set_err("saugen_run", e); if (out_len) *out_len = 0; return -1; }
+	if (buf) memcpy(buf, o->h_pcm, bytes);
+	return finish_call(o, buf_len, out_len);
+}
+
+extern "C" int saugen_run_device(saugen_Generator *o, size_t buf_len, int stereo,
+		int16_t **dev_pcm, size_t *out_len) {
+	int more = 0;
+	int r = run_common(o, buf_len, stereo, 0, out_len, &more);
+	if (r < 0) return r;
+	if (dev_pcm) *dev_pcm = o->d_pcm;
+	if (r == 0) return 0;
+	cudaError_t e = cudaStreamSynchronize(o->stream);
+	if (e != cudaSuccess) { set_err("saugen_run_device", e); if (out_len) *out_len = 0; return -1; }
+	return finish_call(o, buf_len, out_len);
+}
+
+extern "C" int saugen_run_mix(saugen_Generator *o, size_t buf_len, float **dev_mix, size_t *out_len) {
+	int more = 0;
+	int r = run_common(o, buf_len, 1, 1, out_len, &more);
+	if (r < 0) return r;
+	if (dev_mix) *dev_mix = o->d_mix;
+	if (r == 0) { cudaMemsetAsync(o->d_mix, 0, 2 * (size_t) o->row_len * sizeof(float), o->stream); cudaStreamSynchronize(o->stream); return 0; }
+	cudaError_t e = cudaStreamSynchronize(o->stream);
+	if (e != cudaSuccess) { set_err("saugen_run_mix", e); if (out_len) *out_len = 0; return -1; }
+	return finish_call(o, buf_len, out_len);
+}
+
+extern "C" int saugen_mix_to_pcm(saugen_Generator *o, const float *dev_mix, size_t buf_len,
+		int stereo, int16_t *host_buf) {
+	if (!o || buf_len > o->row_len) return -1;
+	cudaSetDevice(o->device);
+	cudaError_t e = launch_planes_to_pcm(dev_mix, o->row_len, (uint32_t) buf_len, stereo ? 1 : 0,
+			o->d_pcm, o->stream);
+	const size_t bytes = buf_len * (stereo ? 2 : 1) * sizeof(int16_t);
+	if (e == cudaSuccess && host_buf)
+		e = cudaMemcpyAsync(o->h_pcm, o->d_pcm, bytes, cudaMemcpyDeviceToHost, o->stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(o->stream);
+	if (e != cudaSuccess) { set_err("saugen_mix_to_pcm", e); return -1; }
+	if (host_buf) memcpy(host_buf, o->h_pcm, bytes);
+	return 0;
+}
+
+/* Batched: one render + one mix launch for n generators (same device, stream
+ * and wave tables; the first generator's stream is used). */
+extern "C" int saugen_run_many(saugen_Generator *const *gens, size_t n, int16_t *const *bufs,
+		size_t buf_len, int stereo, size_t *out_lens, int *more) {
+	if (!gens || n == 0) return 0;
+	saugen_Generator *g0 = gens[0];
+	cudaSetDevice(g0->device);
+	static thread_local std::vector<CallDesc> calls;
+	static thread_local std::vector<SegDesc> segs;
+	static thread_local std::vector<size_t> call_of;     // generator index per call
+	static thread_local CallDesc *d_calls = nullptr; static thread_local size_t d_calls_cap = 0;
+	static thread_local SegDesc *d_segs = nullptr; static thread_local size_t d_segs_cap = 0;
+	calls.clear(); segs.clear(); call_of.clear();
+	uint32_t ntasks = 0, wave_mask = 0, nbufs = 1;
+	for (size_t i = 0; i < n; ++i) {
+		saugen_Generator *o = gens[i];
+		if (out_lens) out_lens[i] = 0;
+		if (more) more[i] = 0;
+		if (!o || o->ended) continue;
+		if (buf_len > o->row_len || o->d_tables != g0->d_tables) {
+			g_err = "saugen_run_many: generators must share tables and fit buf_len";
+			return -1;
+		}
+		plan_call(o, (uint32_t) buf_len, o->segs_tmp);
+		if (o->segs_tmp.size() > o->seg_cap) {
+			g_err = "saugen_run_many: too many events inside one call (use saugen_run)";
+			return -1;
+		}
+		CallDesc cd;
+		cd.gen = o->d_desc; cd.call_len = (uint32_t) buf_len; cd.nseg = (uint32_t) o->segs_tmp.size();
+		cd.seg_off = (uint32_t) segs.size(); cd.task_base = ntasks; cd.stereo = stereo ? 1 : 0; cd._pad = 0;
+		segs.insert(segs.end(), o->segs_tmp.begin(), o->segs_tmp.end());
+		calls.push_back(cd);
+		call_of.push_back(i);
+		ntasks += o->nlv;
+		wave_mask |= o->wave_mask;
+		if (o->nbufs > nbufs) nbufs = o->nbufs;
+		cudaMemsetAsync(o->d_status, 0, (1 + cd.nseg) * sizeof(uint32_t), g0->stream);
+	}
+	if (calls.empty()) return 0;
+	cudaError_t e = cudaSuccess;
+	if (calls.size() > d_calls_cap) {
+		if (d_calls) cudaFree(d_calls);
+		d_calls_cap = calls.size() * 2;
+		e = cudaMalloc(&d_calls, d_calls_cap * sizeof(CallDesc));
+	}
+	if (e == cudaSuccess && segs.size() > d_segs_cap) {
+		if (d_segs) cudaFree(d_segs);
+		d_segs_cap = segs.size() * 2;
+		e = cudaMalloc(&d_segs, d_segs_cap * sizeof(SegDesc));
+	}
+	if (e == cudaSuccess) e = cudaMemcpyAsync(d_calls, calls.data(), calls.size() * sizeof(CallDesc), cudaMemcpyHostToDevice, g0->stream);
+	if (e == cudaSuccess) e = cudaMemcpyAsync(d_segs, segs.data(), segs.size() * sizeof(SegDesc), cudaMemcpyHostToDevice, g0->stream);
+	if (e == cudaSuccess) {
+		const uint32_t warps = pick_warps(ntasks, wave_mask, nbufs);
+		e = launch_render(d_calls, (uint32_t) calls.size(), d_segs, ntasks, g0->d_tables, wave_mask,
+				nbufs, warps, g0->stream);
+		g0->counters[0]++;
+	}
+	if (e == cudaSuccess) {
+		e = launch_mix(d_calls, (uint32_t) calls.size(), d_segs, (uint32_t) buf_len, 0, g0->stream);
+		g0->counters[1]++;
+	}
+	const size_t bytes = buf_len * (stereo ? 2 : 1) * sizeof(int16_t);
+	for (size_t c = 0; c < calls.size() && e == cudaSuccess; ++c) {
+		saugen_Generator *o = gens[call_of[c]];
+		e = cudaMemcpyAsync(o->h_status, o->d_status, (1 + calls[c].nseg) * sizeof(uint32_t),
+				cudaMemcpyDeviceToHost, g0->stream);
+		if (e == cudaSuccess && bufs && bufs[call_of[c]])
+			e = cudaMemcpyAsync(o->h_pcm, o->d_pcm, bytes, cudaMemcpyDeviceToHost, g0->stream);
+	}
+	if (e == cudaSuccess) e = cudaStreamSynchronize(g0->stream);
+	if (e != cudaSuccess) { set_err("saugen_run_many", e); return -1; }
+	int any = 0;
+	for (size_t c = 0; c < calls.size(); ++c) {
+		const size_t i = call_of[c];
+		saugen_Generator *o = gens[i];
+		if (bufs && bufs[i]) memcpy(bufs[i], o->h_pcm, bytes);
+		size_t ol = 0;
+		int m = finish_call(o, buf_len, &ol);
+		if (out_lens) out_lens[i] = ol;
+		if (more) more[i] = m;
+		any |= m;
+	}
+	return any;
+}
+
+/* ---- introspection ------------------------------------------------------- */
+
+static void view_line(saugen_LineView *d, const LineState *s) {
+	d->v0 = s->v0; d->vt = s->vt; d->pos = s->pos; d->end = s->end;
+	d->type = s->type; d->flags = s->flags;
+}
+
+extern "C" int saugen_read_op(saugen_Generator *o, uint32_t op_id, saugen_OpView *out) {
+	if (!o || op_id >= o->op_count) return -1;
+	cudaSetDevice(o->device);
+	OpState s;
+	cudaStreamSynchronize(o->stream);
+	if (cudaMemcpy(&s, (OpState*) o->d_ops + op_id, sizeof s, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+	memset(out, 0, sizeof *out);
+	out->inited = (s.flags & ON_INIT) != 0;
+	if (!out->inited) return 0;
+	out->type = s.type;
+	out->flags = s.flags & (ON_INIT | ON_TIME_INF);   /* reference bits only */
+	out->time = s.time;
+	view_line(&out->amp, &s.line[LINE_AMP]); view_line(&out->amp2, &s.line[LINE_AMP2]);
+	view_line(&out->pan, &s.line[LINE_PAN]);
+	if (s.type >= SAUABI_POPT_wave) {
+		view_line(&out->freq, &s.line[LINE_FREQ]); view_line(&out->freq2, &s.line[LINE_FREQ2]);
+		view_line(&out->pm_a, &s.line[LINE_PMA]);
+	}
+	out->i0 = s.i0; out->i1 = s.i1; out->mode = s.mode;
+	switch (s.type) {
+	case SAUABI_POPT_wave:
+		out->oscflags = s.oscflags; out->prev_Is = s.prev_Is;
+		out->prev_s = s.prev_s; out->fb_s = s.fb_s; break;
+	case SAUABI_POPT_raseg:
+		out->oscflags = s.ras_flags | (s.ras_func << 16) | (s.ras_level << 24);
+		out->prev_s = s.prev_s; out->fb_s = s.fb_s;
+		out->alpha = s.ras_alpha; out->rate2x = s.oscflags & 1; break;
+	}
+	return 0;
+}
+
+extern "C" int saugen_read_voice(saugen_Generator *o, uint32_t vo_id, uint32_t out[4]) {
+	if (!o || vo_id >= o->vo_count) return -1;
+	cudaSetDevice(o->device);
+	VoiceState s;
+	cudaStreamSynchronize(o->stream);
+	if (cudaMemcpy(&s, (VoiceState*) o->d_voices + vo_id, sizeof s, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+	out[0] = s.duration; out[1] = s.flags; out[2] = s.carr_op; out[3] = 0;
+	return 0;
+}
+
+extern "C" int saugen_read_voice_rows(saugen_Generator *o, uint32_t vo_id, float *s, float *r, size_t n) {
+	if (!o || vo_id < o->voice_begin || vo_id >= o->voice_end || n > o->row_len) return -1;
+	cudaSetDevice(o->device);
+	cudaStreamSynchronize(o->stream);
+	const size_t lv = vo_id - o->voice_begin;
+	if (s && cudaMemcpy(s, o->d_rows_s + lv * o->row_len, n * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+	if (r && cudaMemcpy(r, o->d_rows_r + lv * o->row_len, n * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+	return 0;
+}
+
+extern "C" int saugen_counters(saugen_Generator *o, uint64_t out[4]) {
+	if (!o) return -1;
+	for (int i = 0; i < 4; ++i) out[i] = o->counters[i];
+	out[2] = o->nbufs; out[3] = o->wave_mask;
+	return 0;
+}
+extern "C" float saugen_amp_scale(saugen_Generator *o) { return o ? o->amp_scale : 0.f; }
+extern "C" const char *saugen_last_error(void) { return g_err.c_str(); }
+extern "C" int saugen_device_count(void) {
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+	return n;
+}
+extern "C" const saugen_WaveTables *saugen_builtin_wave_tables(void) { return saugen::builtin_wave_tables(); }
+
+extern "C" size_t saugen_abi_layout(uint32_t *out, size_t cap) {
+	const uint32_t v[] = {
+		sizeof(sauabi_Line), offsetof(sauabi_Line, v0), offsetof(sauabi_Line, vt),
+		offsetof(sauabi_Line, pos), offsetof(sauabi_Line, end),
+		offsetof(sauabi_Line, time_ms), offsetof(sauabi_Line, type), offsetof(sauabi_Line, flags),
+		sizeof(sauabi_Time), offsetof(sauabi_Time, v_ms), offsetof(sauabi_Time, flags),
+		sizeof(sauabi_RasOpt), offsetof(sauabi_RasOpt, line), offsetof(sauabi_RasOpt, alpha),
+		sizeof(sauabi_ProgramIDArr), offsetof(sauabi_ProgramIDArr, ids),
+		sizeof(sauabi_ProgramOpData),
+		offsetof(sauabi_ProgramOpData, id), offsetof(sauabi_ProgramOpData, params),
+		offsetof(sauabi_ProgramOpData, time), offsetof(sauabi_ProgramOpData, pan),
+		offsetof(sauabi_ProgramOpData, amp), offsetof(sauabi_ProgramOpData, amp2),
+		offsetof(sauabi_ProgramOpData, freq), offsetof(sauabi_ProgramOpData, freq2),
+		offsetof(sauabi_ProgramOpData, pm_a), offsetof(sauabi_ProgramOpData, phase),
+		offsetof(sauabi_ProgramOpData, seed), offsetof(sauabi_ProgramOpData, use_type),
+		offsetof(sauabi_ProgramOpData, type), offsetof(sauabi_ProgramOpData, mode),
+		offsetof(sauabi_ProgramOpData, camods), offsetof(sauabi_ProgramOpData, amods),
+		offsetof(sauabi_ProgramOpData, ramods), offsetof(sauabi_ProgramOpData, fmods),
+		offsetof(sauabi_ProgramOpData, rfmods), offsetof(sauabi_ProgramOpData, pmods),
+		offsetof(sauabi_ProgramOpData, apmods), offsetof(sauabi_ProgramOpData, fpmods),
+		sizeof(sauabi_ProgramEvent),
+		offsetof(sauabi_ProgramEvent, wait_ms), offsetof(sauabi_ProgramEvent, vo_id),
+		offsetof(sauabi_ProgramEvent, carr_op_id), offsetof(sauabi_ProgramEvent, op_count),
+		offsetof(sauabi_ProgramEvent, op_data_count), offsetof(sauabi_ProgramEvent, op_list),
+		offsetof(sauabi_ProgramEvent, op_data),
+		sizeof(sauabi_Program),
+		offsetof(sauabi_Program, events), offsetof(sauabi_Program, ev_count),
+		offsetof(sauabi_Program, mode), offsetof(sauabi_Program, vo_count),
+		offsetof(sauabi_Program, op_count), offsetof(sauabi_Program, op_nest_depth),
+		offsetof(sauabi_Program, duration_ms), offsetof(sauabi_Program, ampmult),
+		offsetof(sauabi_Program, name),
+		SAUABI_WAVE_NAMED, SAUABI_LINE_NAMED, SAUABI_NOISE_NAMED, SAUABI_RAS_FUNCTIONS,
+	};
+	const size_t n = sizeof(v) / sizeof(v[0]);
+	for (size_t i = 0; i < n && i < cap; ++i) out[i] = v[i];
+	return n;
+}

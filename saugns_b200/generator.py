@@ -1,0 +1,240 @@
+"""ctypes binding of libsaugen_b200.so and the Generator class.
+
+`Generator(prg, srate)` / `.run(buf_len, stereo)` / `.close()` mirror
+sau_create_Generator / sauGenerator_run / sau_destroy_Generator
+(reference sau/generator.c:200-228,905-973): same argument meaning, same
+return convention (`more`, PCM, `out_len`), NULL -> exception on failure.
+`prg` is anything with a `.ptr` attribute holding the address of a sauProgram
+laid out per include/sau_program_abi.h (the reference front end's output, or
+saugns_b200.program.ProgramBuilder).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsaugen_b200.so")
+
+
+class WaveTables(C.Structure):
+    """saugen_WaveTables (include/saugen_b200.h)."""
+    _fields_ = [("pilut", C.c_void_p * 12), ("amp_scale", C.c_float * 12),
+                ("amp_dc", C.c_float * 12), ("phase_adj", C.c_int32 * 12)]
+
+
+class Options(C.Structure):
+    _fields_ = [("device", C.c_int), ("stream", C.c_void_p), ("voice_begin", C.c_uint32),
+                ("voice_end", C.c_uint32), ("max_call_len", C.c_uint32)]
+
+
+class LineView(C.Structure):
+    _fields_ = [("v0", C.c_float), ("vt", C.c_float), ("pos", C.c_uint32),
+                ("end", C.c_uint32), ("type", C.c_uint32), ("flags", C.c_uint32)]
+
+
+class OpView(C.Structure):
+    """saugen_OpView; same layout as oracle/ref_harness.c:RefOpState."""
+    _fields_ = [("inited", C.c_uint32), ("type", C.c_uint32), ("flags", C.c_uint32),
+                ("time", C.c_uint32),
+                ("amp", LineView), ("amp2", LineView), ("pan", LineView),
+                ("freq", LineView), ("freq2", LineView), ("pm_a", LineView),
+                ("i0", C.c_uint32), ("i1", C.c_uint32), ("mode", C.c_uint32),
+                ("oscflags", C.c_uint32), ("prev_Is", C.c_double),
+                ("prev_s", C.c_float), ("fb_s", C.c_float),
+                ("alpha", C.c_uint32), ("rate2x", C.c_uint32)]
+
+
+_lib = None
+
+
+def lib():
+    """Load the CUDA extension; fail loudly when it is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; "
+                "g.build()'` (nvcc, sm_100a). saugns_b200 has no CPU fallback.")
+        L = C.CDLL(LIB_PATH, mode=os.RTLD_LOCAL)
+        L.saugen_create.restype = C.c_void_p
+        L.saugen_create.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+        L.saugen_destroy.argtypes = [C.c_void_p]
+        L.saugen_run.restype = C.c_int
+        L.saugen_run.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int,
+                                 C.POINTER(C.c_size_t)]
+        L.saugen_run_device.restype = C.c_int
+        L.saugen_run_device.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.POINTER(C.c_void_p),
+                                        C.POINTER(C.c_size_t)]
+        L.saugen_run_many.restype = C.c_int
+        L.saugen_run_many.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int,
+                                      C.c_void_p, C.c_void_p]
+        L.saugen_run_mix.restype = C.c_int
+        L.saugen_run_mix.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p),
+                                     C.POINTER(C.c_size_t)]
+        L.saugen_mix_to_pcm.restype = C.c_int
+        L.saugen_mix_to_pcm.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]
+        L.saugen_read_op.restype = C.c_int
+        L.saugen_read_op.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(OpView)]
+        L.saugen_read_voice.restype = C.c_int
+        L.saugen_read_voice.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]
+        L.saugen_read_voice_rows.restype = C.c_int
+        L.saugen_read_voice_rows.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p,
+                                             C.c_size_t]
+        L.saugen_counters.restype = C.c_int
+        L.saugen_counters.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+        L.saugen_amp_scale.restype = C.c_float
+        L.saugen_amp_scale.argtypes = [C.c_void_p]
+        L.saugen_last_error.restype = C.c_char_p
+        L.saugen_device_count.restype = C.c_int
+        L.saugen_builtin_wave_tables.restype = C.POINTER(WaveTables)
+        L.saugen_abi_layout.restype = C.c_size_t
+        L.saugen_abi_layout.argtypes = [C.POINTER(C.c_uint32), C.c_size_t]
+        _lib = L
+    return _lib
+
+
+def last_error():
+    return lib().saugen_last_error().decode()
+
+
+def device_count():
+    return lib().saugen_device_count()
+
+
+def builtin_tables():
+    """(piluts[12,2048] float32, [(amp_scale, amp_dc, phase_adj)]*12) built by wavetab.cpp."""
+    t = lib().saugen_builtin_wave_tables().contents
+    tabs = np.zeros((12, 2048), np.float32)
+    for w in range(12):
+        tabs[w] = np.ctypeslib.as_array(C.cast(t.pilut[w], C.POINTER(C.c_float)), shape=(2048,))
+    return tabs, [(t.amp_scale[w], t.amp_dc[w], t.phase_adj[w]) for w in range(12)]
+
+
+def abi_layout():
+    buf = (C.c_uint32 * 128)()
+    n = lib().saugen_abi_layout(buf, 128)
+    return list(buf[:n])
+
+
+class Generator:
+    """One sauGenerator instance living on a B200."""
+
+    def __init__(self, prg, srate=96000, tables=None, device=0, stream=None,
+                 voice_range=None, max_call_len=0):
+        self._prg = prg            # borrowed for the generator's life (generator.c:191)
+        self._tables = tables
+        opt = Options(device=device, stream=stream or 0,
+                      voice_begin=voice_range[0] if voice_range else 0,
+                      voice_end=voice_range[1] if voice_range else 0,
+                      max_call_len=max_call_len)
+        tptr = C.addressof(tables) if tables is not None else None
+        self.ptr = lib().saugen_create(prg.ptr, srate, tptr, C.byref(opt))
+        if not self.ptr:
+            raise RuntimeError("saugen_create failed: " + last_error())
+        self.srate = srate
+
+    def run(self, buf_len, stereo=True):
+        """-> (more, int16 array of buf_len*channels, out_len)."""
+        ch = 2 if stereo else 1
+        buf = np.zeros(buf_len * ch, dtype=np.int16)
+        n = C.c_size_t(0)
+        r = lib().saugen_run(self.ptr, buf.ctypes.data, buf_len, int(stereo), C.byref(n))
+        if r < 0:
+            raise RuntimeError("saugen_run failed: " + last_error())
+        return bool(r), buf, n.value
+
+    def run_device(self, buf_len, stereo=True):
+        """Render one call leaving the PCM in HBM -> (more, device pointer, out_len)."""
+        n = C.c_size_t(0)
+        p = C.c_void_p(0)
+        r = lib().saugen_run_device(self.ptr, buf_len, int(stereo), C.byref(p), C.byref(n))
+        if r < 0:
+            raise RuntimeError("saugen_run_device failed: " + last_error())
+        return bool(r), p.value, n.value
+
+    def run_mix(self, buf_len):
+        """Partial float mix planes in HBM (voice-sharded multi-GPU) -> (more, dev ptr, out_len)."""
+        n = C.c_size_t(0)
+        p = C.c_void_p(0)
+        r = lib().saugen_run_mix(self.ptr, buf_len, C.byref(p), C.byref(n))
+        if r < 0:
+            raise RuntimeError("saugen_run_mix failed: " + last_error())
+        return bool(r), p.value, n.value
+
+    def mix_to_pcm(self, dev_mix_ptr, buf_len, stereo=True):
+        ch = 2 if stereo else 1
+        buf = np.zeros(buf_len * ch, dtype=np.int16)
+        if lib().saugen_mix_to_pcm(self.ptr, dev_mix_ptr, buf_len, int(stereo), buf.ctypes.data) < 0:
+            raise RuntimeError("saugen_mix_to_pcm failed: " + last_error())
+        return buf
+
+    def op_state(self, op_id):
+        v = OpView()
+        if lib().saugen_read_op(self.ptr, op_id, C.byref(v)) != 0:
+            raise IndexError(op_id)
+        return v
+
+    def voice_state(self, vo_id):
+        out = (C.c_uint32 * 4)()
+        lib().saugen_read_voice(self.ptr, vo_id, out)
+        return list(out)
+
+    def voice_rows(self, vo_id, n):
+        s = np.zeros(n, np.float32)
+        r = np.zeros(n, np.float32)
+        if lib().saugen_read_voice_rows(self.ptr, vo_id, s.ctypes.data, r.ctypes.data, n) != 0:
+            raise IndexError(vo_id)
+        return s, r
+
+    def counters(self):
+        out = (C.c_uint64 * 4)()
+        lib().saugen_counters(self.ptr, out)
+        return list(out)
+
+    @property
+    def amp_scale(self):
+        return lib().saugen_amp_scale(self.ptr)
+
+    def close(self):
+        if getattr(self, "ptr", None):
+            lib().saugen_destroy(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def render(prg, srate=96000, stereo=True, call_len=None, tables=None, device=0, max_frames=None):
+    """Render a whole program the way Player_run does (saugns.c:575-623)."""
+    if call_len is None:
+        call_len = srate * 256 // 1000
+    g = Generator(prg, srate, tables=tables, device=device, max_call_len=call_len)
+    ch = 2 if stereo else 1
+    chunks, total, more = [], 0, True
+    while more:
+        more, buf, n = g.run(call_len, stereo)
+        chunks.append(buf[:n * ch])
+        total += n
+        if max_frames and total >= max_frames:
+            break
+    g.close()
+    return np.concatenate(chunks).reshape(-1, ch) if chunks else np.zeros((0, ch), np.int16)
+
+
+def run_many(gens, buf_len, stereo=True, want_pcm=True):
+    """One call on each generator with a single pair of kernel launches."""
+    n = len(gens)
+    ch = 2 if stereo else 1
+    ptrs = (C.c_void_p * n)(*[g.ptr for g in gens])
+    outs = np.zeros((n, buf_len * ch), np.int16) if want_pcm else None
+    bufs = (C.c_void_p * n)(*[outs[i].ctypes.data for i in range(n)]) if want_pcm else None
+    lens = (C.c_size_t * n)()
+    more = (C.c_int * n)()
+    r = lib().saugen_run_many(ptrs, n, bufs, buf_len, int(stereo), lens, more)
+    if r < 0:
+        raise RuntimeError("saugen_run_many failed: " + last_error())
+    return list(more), outs, list(lens)
