@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""bench.py -- voice-samples/s and realtime factor of the generator back end.
+
+Workload (BASELINE.json configs[2], "C3"): 4096 concurrent voices of 3-operator
+PM/FM chains with envelope ramps at 96 kHz stereo.  A step is ONE generator
+call (sauGenerator_run) of 24576 frames = 256 ms of audio for all voices, i.e.
+4096 x 24576 voice-samples (the reference player's own call size,
+saugns.c:471,526).  At N GPUs every rank renders an independent 4096-voice
+script (weak scaling, no data-path collective).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]        GPU arm
+    python bench.py --impl reference ...                         reference CPU arm
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SRATE = 96000
+FRAMES = 24576          # 256 ms at 96 kHz, saugns.c:471
+VOICES = 4096
+SECS = 60
+METRIC = "voice-samples/sec"
+WORKLOAD = ("C3: 4096 concurrent voices x 3-operator PM/FM chains (alternating PM chain / "
+            "range-FM+PM) with xpe/lin amp ramps, 60 s script at 96 kHz stereo; "
+            "step = one 24576-frame generator call")
+
+
+def env_rank():
+    return (int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")),
+            int(os.environ.get("WORLD_SIZE", "1")))
+
+
+# ---------------------------------------------------------------------------
+# clocks sampling (B200_PROFILING.md "clocks DURING the timed region")
+# ---------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1]))
+                mx.append(float(p[2]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if p[5 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------
+# reference CPU arm / cpu_baseline
+# ---------------------------------------------------------------------------
+def _ref_worker(args):
+    text, frames = args
+    from oracle import pyref
+    prg = pyref.Program(text)
+    t0 = time.perf_counter()
+    n = pyref.lib().refwb_render_null(prg.ptr, SRATE, 1, FRAMES, frames)
+    dt = time.perf_counter() - t0
+    return n, prg.vo_count, dt
+
+
+def reference_render(voices, frames, procs, seed=1):
+    """Unmodified reference generator (oracle/_ref) on `procs` host processes,
+    each rendering a disjoint slice of the C3 voices for `frames` frames.
+    Returns (voice_samples, wall_seconds, kind)."""
+    import multiprocessing as mp
+    from saugns_b200 import workloads
+    from oracle import pyref
+    if not pyref.available():
+        raise RuntimeError("oracle/_ref/libsauref.so missing")
+    # one script per process: same voices as the GPU workload, split by voice index
+    full = workloads.synth_c3(voices, SECS, seed=seed, fm="mix").splitlines()
+    head, body = full[0], full[1:]
+    per = (len(body) + procs - 1) // procs
+    jobs = []
+    for p in range(procs):
+        part = body[p * per:(p + 1) * per]
+        if part:
+            jobs.append(("\n".join([head] + part) + "\n", frames))
+    ctx = mp.get_context("fork")
+    with ctx.Pool(len(jobs)) as pool:
+        res = pool.map(_ref_worker, jobs)
+    # all processes run concurrently; the job takes as long as the slowest one's
+    # create+render (script parsing is not the generator's work and is excluded)
+    wall = max(dt for _, _, dt in res)
+    vs = sum(n * v for n, v, _ in res)
+    return vs, wall, len(jobs)
+
+
+def run_reference_arm(args):
+    rank, _, world = env_rank()
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    procs = max(1, min(cores, 64))
+    # one step = the same 24576-frame call over all 4096 voices, on all host cores
+    for _ in range(args.warmup):
+        reference_render(VOICES, FRAMES, procs)
+    t_tot, vs_tot = 0.0, 0
+    for _ in range(args.steps):
+        vs, wall, used = reference_render(VOICES, FRAMES, procs)
+        t_tot += wall
+        vs_tot += vs
+    value = vs_tot / t_tot
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "voice-samples/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1000.0 * t_tot / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "voices": VOICES, "frames_per_step": FRAMES,
+                   "srate": SRATE},
+        "realtime_factor": (FRAMES * args.steps / SRATE) / t_tot,
+        "cpu_baseline": {"value": value, "unit": "voice-samples/s", "cores": procs,
+                         "kind": "reference",
+                         "sample": f"unmodified reference generator (oracle/_ref, -O3 -ffast-math), "
+                                   f"{VOICES} voices split over {procs} processes, "
+                                   f"{FRAMES} frames per step; create+render timed, parsing excluded"},
+        "e2e": {"value": value, "unit": "voice-samples/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ---------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------
+def run_gpu_arm(args):
+    import torch
+    import saugns_b200
+    from saugns_b200 import workloads
+
+    rank, local_rank, world = env_rank()
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if not torch.cuda.is_available() or saugns_b200.device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device; the B200 back end has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    stream = torch.cuda.Stream()
+    K, W = args.steps, args.warmup
+    if W + K > SECS * SRATE // FRAMES - 1:
+        raise SystemExit("steps+warmup exceed the 60 s workload (234 calls)")
+
+    prg = workloads.build_c3(VOICES, SECS, seed=1 + rank, fm="mix")
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident throughput: PCM stays in HBM ----
+    g = saugns_b200.Generator(prg, SRATE, device=local_rank, stream=stream.cuda_stream,
+                              max_call_len=FRAMES)
+    for _ in range(W):
+        g.run_device(FRAMES)
+    g.set_timing(True)
+    sampler = ClockSampler(local_rank)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    sampler.start()
+    c0 = g.counters()
+    with torch.cuda.stream(stream):
+        ev0.record(stream)
+        for _ in range(K):
+            more, _, n = g.run_device(FRAMES)
+            assert more and n == FRAMES
+        ev1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    ms = max_over_ranks(ev0.elapsed_time(ev1))
+    c1 = g.counters()
+    render_ms, mix_ms = g.kernel_ms()
+    launches = (c1[0] - c0[0]) + (c1[1] - c0[1])
+    g.close()
+
+    # ---- end to end through the public call with HOST buffers ----
+    g2 = saugns_b200.Generator(prg, SRATE, device=local_rank, stream=stream.cuda_stream,
+                               max_call_len=FRAMES)
+    for _ in range(W):
+        g2.run(FRAMES)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        more, pcm, n = g2.run(FRAMES)
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    assert int(abs(pcm.astype("int32")).max()) > 0, "silent output"
+    g2.close()
+    barrier()
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    vs_step = VOICES * FRAMES
+    value = world * vs_step * K / (ms / 1000.0)
+    e2e = world * vs_step * K / e2e_s
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = peaks.get("hbm_gbs", 6650.0)
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650"
+    # algorithmic bytes: 8 B per voice-sample x voice-samples per launch
+    alg_bytes = 8.0 * vs_step
+    rk_s = (render_ms / K) / 1000.0
+    achieved = alg_bytes / rk_s / 1e9
+    prof = {}
+    try:
+        prof = json.load(open(os.path.join(ROOT, "profiles", "r01_render_kernel.json")))
+    except Exception:
+        pass
+    line = {
+        "metric": METRIC, "value": value, "unit": "voice-samples/s", "n_gpus": world,
+        "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "voices": VOICES, "frames_per_step": FRAMES,
+                   "srate": SRATE, "op_samples_per_step": 3 * vs_step,
+                   "l2": "per-step voice rows 805 MB > 126 MB L2 (inputs larger than L2)",
+                   "parallelism": f"independent 4096-voice scripts x{world}"},
+        "realtime_factor": (FRAMES * K / SRATE) / (ms / 1000.0),
+        "clocks": clocks,
+        "e2e": {"value": e2e, "unit": "voice-samples/s",
+                "h2d_bytes_per_step": 40 + 12, "d2h_bytes_per_step": FRAMES * 2 * 2 + 8,
+                "realtime_factor": (FRAMES * K / SRATE) / e2e_s},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": prof.get("dram_bytes_per_launch"),
+                     "kernel": "render_kernel", "kernel_ms_per_launch": render_ms / K,
+                     "mix_kernel_ms_per_launch": mix_ms / K, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": alg_bytes,
+                     "note": "path is issue-/FP64-pipe-bound, not HBM-bound (SURVEY.md 8d); "
+                             "issue-slot figures from ncu in profiles/",
+                     "issue_slot_frac_ncu": prof.get("issue_slot_frac"),
+                     "fp64_pipe_frac_ncu": prof.get("fp64_pipe_frac")},
+    }
+    if world == 1 and not args.no_cpu:
+        try:
+            cores = min(os.cpu_count() or 1, 64)
+            sample_frames = SRATE // 2      # 0.5 s of all 4096 voices
+            vs, wall, used = reference_render(VOICES, sample_frames, cores)
+            line["cpu_baseline"] = {
+                "value": vs / wall, "unit": "voice-samples/s", "cores": used, "kind": "reference",
+                "sample": f"unmodified reference generator (oracle/_ref), same {VOICES}-voice "
+                          f"script, first {sample_frames} frames, voices split over {used} "
+                          f"processes; {wall:.2f} s create+render"}
+        except Exception as e:   # the baseline is reported, never required for the GPU number
+            line["cpu_baseline"] = {"value": None, "unit": "voice-samples/s", "cores": 0,
+                                    "kind": "reference", "sample": f"unavailable: {e}"}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

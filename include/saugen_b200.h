@@ -107,6 +107,10 @@ int saugen_read_voice_rows(saugen_Generator *o, uint32_t vo_id, float *s, float 
 		size_t n);
 /* Counters: [0] render launches, [1] mix launches, [2] voice-chunks rendered */
 int saugen_counters(saugen_Generator *o, uint64_t out[4]);
+/* Device time of render_kernel / mix_kernel accumulated since timing was
+ * switched on (CUDA events on the launch stream; for bench.py's roofline). */
+int saugen_set_timing(saugen_Generator *o, int on);
+int saugen_kernel_ms(saugen_Generator *o, double out[2]);
 float saugen_amp_scale(saugen_Generator *o);
 const char *saugen_last_error(void);
 int saugen_device_count(void);

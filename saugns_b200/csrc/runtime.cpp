@@ -130,6 +130,10 @@ struct saugen_Generator {
 	SegDesc *h_segs = nullptr;
 	uint64_t counters[4] = {0, 0, 0, 0};
 	std::vector<SegDesc> segs_tmp;
+	/* device time of the two kernels, measured with events on the launch stream */
+	cudaEvent_t ev_t[3] = {nullptr, nullptr, nullptr};
+	double render_ms = 0.0, mix_ms = 0.0;
+	bool timing = false, timed_call = false;
 };
 
 /* ---- bytecode compiler --------------------------------------------------- */
@@ -445,6 +449,7 @@ extern "C" saugen_Generator *saugen_create(const sauabi_Program *prg, uint32_t s
 		CK(cudaMallocHost(&o->h_pcm, 2 * (size_t) o->row_len * sizeof(int16_t)));
 		CK(cudaMallocHost(&o->h_call, sizeof(CallDesc)));
 		CK(cudaMallocHost(&o->h_segs, o->seg_cap * sizeof(SegDesc)));
+		for (int i = 0; i < 3; ++i) CK(cudaEventCreate(&o->ev_t[i]));
 	}
 	{
 		GenDesc &d = o->h_desc;
@@ -481,6 +486,7 @@ extern "C" void saugen_destroy(saugen_Generator *o) {
 	for (void *p : dev) if (p) cudaFree(p);
 	void *host[] = {o->h_status, o->h_pcm, o->h_call, o->h_segs};
 	for (void *p : host) if (p) cudaFreeHost(p);
+	for (int i = 0; i < 3; ++i) if (o->ev_t[i]) cudaEventDestroy(o->ev_t[i]);
 	if (o->own_stream && o->stream) cudaStreamDestroy(o->stream);
 	delete o;
 }
@@ -563,16 +569,20 @@ static int run_common(saugen_Generator *o, size_t buf_len, int stereo, uint32_t 
 	e = cudaMemcpyAsync(o->d_segs, o->h_segs, nseg * sizeof(SegDesc), cudaMemcpyHostToDevice, o->stream);
 	if (e == cudaSuccess) e = cudaMemcpyAsync(o->d_call, o->h_call, sizeof(CallDesc), cudaMemcpyHostToDevice, o->stream);
 	if (e == cudaSuccess) e = cudaMemsetAsync(o->d_status, 0, (1 + nseg) * sizeof(uint32_t), o->stream);
+	o->timed_call = o->timing;
+	if (e == cudaSuccess && o->timed_call) e = cudaEventRecord(o->ev_t[0], o->stream);
 	if (e == cudaSuccess) {
 		const uint32_t warps = pick_warps(o->nlv, o->wave_mask, o->nbufs);
 		e = launch_render(o->d_call, 1, o->d_segs, o->nlv, o->d_tables, o->wave_mask, o->nbufs,
 				warps, o->stream);
 		o->counters[0]++;
 	}
+	if (e == cudaSuccess && o->timed_call) e = cudaEventRecord(o->ev_t[1], o->stream);
 	if (e == cudaSuccess) {
 		e = launch_mix(o->d_call, 1, o->d_segs, (uint32_t) buf_len, mode, o->stream);
 		o->counters[1]++;
 	}
+	if (e == cudaSuccess && o->timed_call) e = cudaEventRecord(o->ev_t[2], o->stream);
 	if (e == cudaSuccess) e = cudaMemcpyAsync(o->h_status, o->d_status, (1 + nseg) * sizeof(uint32_t),
 			cudaMemcpyDeviceToHost, o->stream);
 	if (e != cudaSuccess) { set_err("saugen_run: launch", e); if (out_len) *out_len = 0; return -1; }
@@ -583,6 +593,12 @@ static int run_common(saugen_Generator *o, size_t buf_len, int stereo, uint32_t 
 /* After the stream is synchronised: out_len / return value (generator.c:938-972). */
 static int finish_call(saugen_Generator *o, size_t buf_len, size_t *out_len) {
 	const uint32_t nseg = (uint32_t) o->segs_tmp.size();
+	if (o->timed_call) {
+		float a = 0.f, b = 0.f;
+		if (cudaEventElapsedTime(&a, o->ev_t[0], o->ev_t[1]) == cudaSuccess) o->render_ms += a;
+		if (cudaEventElapsedTime(&b, o->ev_t[1], o->ev_t[2]) == cudaSuccess) o->mix_ms += b;
+		o->timed_call = false;
+	}
 	size_t gen_len = 0;
 	for (uint32_t s = 0; s + 1 < nseg; ++s) gen_len += o->segs_tmp[s].len;
 	if (nseg) gen_len += o->h_status[1 + (nseg - 1)];
@@ -798,6 +814,18 @@ extern "C" int saugen_counters(saugen_Generator *o, uint64_t out[4]) {
 	if (!o) return -1;
 	for (int i = 0; i < 4; ++i) out[i] = o->counters[i];
 	out[2] = o->nbufs; out[3] = o->wave_mask;
+	return 0;
+}
+/* Per-kernel device time: CUDA events on the launch stream around each kernel. */
+extern "C" int saugen_set_timing(saugen_Generator *o, int on) {
+	if (!o) return -1;
+	o->timing = on != 0;
+	o->render_ms = o->mix_ms = 0.0;
+	return 0;
+}
+extern "C" int saugen_kernel_ms(saugen_Generator *o, double out[2]) {
+	if (!o) return -1;
+	out[0] = o->render_ms; out[1] = o->mix_ms;
 	return 0;
 }
 extern "C" float saugen_amp_scale(saugen_Generator *o) { return o ? o->amp_scale : 0.f; }

@@ -83,6 +83,8 @@ def lib():
                                              C.c_size_t]
         L.saugen_counters.restype = C.c_int
         L.saugen_counters.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+        L.saugen_set_timing.argtypes = [C.c_void_p, C.c_int]
+        L.saugen_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         L.saugen_amp_scale.restype = C.c_float
         L.saugen_amp_scale.argtypes = [C.c_void_p]
         L.saugen_last_error.restype = C.c_char_p
@@ -192,6 +194,15 @@ class Generator:
         lib().saugen_counters(self.ptr, out)
         return list(out)
 
+    def set_timing(self, on=True):
+        lib().saugen_set_timing(self.ptr, int(on))
+
+    def kernel_ms(self):
+        """(render_kernel ms, mix_kernel ms) accumulated since set_timing(True)."""
+        out = (C.c_double * 2)()
+        lib().saugen_kernel_ms(self.ptr, out)
+        return out[0], out[1]
+
     @property
     def amp_scale(self):
         return lib().saugen_amp_scale(self.ptr)
@@ -206,6 +217,21 @@ class Generator:
             self.close()
         except Exception:
             pass
+
+
+class _DevArray:
+    """Raw device memory exposed through __cuda_array_interface__ (zero copy)."""
+
+    def __init__(self, ptr, numel, typestr="<f4"):
+        self.__cuda_array_interface__ = {"shape": (numel,), "typestr": typestr,
+                                         "data": (ptr, False), "version": 2}
+
+
+def planes_as_torch(ptr, numel):
+    """View `numel` floats at device pointer `ptr` as a torch CUDA tensor (for the
+    NCCL reduce of voice-sharded mixes); valid until the generator's next call."""
+    import torch
+    return torch.as_tensor(_DevArray(ptr, numel), device="cuda")
 
 
 def render(prg, srate=96000, stereo=True, call_len=None, tables=None, device=0, max_frames=None):

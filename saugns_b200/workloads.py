@@ -1,0 +1,64 @@
+"""Synthetic many-voice workloads (BASELINE.json configs[2]: "4096 concurrent
+voices of 3-operator PM/FM chains with envelope ramps, 60 s at 96 kHz").
+
+`synth_c3` writes the workload as a SAU script (for the reference front end and
+the CPU baseline); `build_c3` emits the identical sauProgram directly
+(saugns_b200.program.ProgramBuilder) so that the GPU arm of bench.py needs no
+script front end.  tests/test_program_builder.py checks the two agree field by
+field.  fm: False = PM chain, True = range-FM + PM, "mix" = alternating.
+"""
+import random
+
+
+def _is_fm(fm, i):
+    return (i % 2 == 1) if fm == "mix" else bool(fm)
+
+
+def synth_c3(n_voices=4096, secs=60, seed=1, fm=False):
+    """BASELINE config 3: n voices of 3-operator PM (or FM) chains with ramps."""
+    rnd = random.Random(seed)
+    lines = [f"S a.m{0.3 / n_voices ** 0.5:.6f}"]
+    for i in range(n_voices):
+        f = 110.0 * 2 ** rnd.uniform(0, 4)
+        c = rnd.uniform(-1, 1)
+        r1 = rnd.choice([0.5, 1, 1.5, 2, 3])
+        r2 = rnd.choice([1, 2, 3.5, 7])
+        if _is_fm(fm, i):
+            lines.append(
+                f"Wsin f{f:.3f}.r{2 * f:.3f}[Wtri r{r1} a0.8[g0.1 llin]] t{secs} "
+                f"a1[g0.2 lxpe] c{c:.3f} p[Wsin r{r2} a0.5]")
+        else:
+            lines.append(
+                f"Wsin f{f:.3f} t{secs} a1[g0.2 lxpe] c{c:.3f} "
+                f"p[Wtri r{r1} a0.8[g0.1 llin] p[Wsin r{r2} a0.5]]")
+    return "\n".join(lines) + "\n"
+
+
+
+def build_c3(n_voices=4096, secs=60, seed=1, fm=False):
+    """The same program synth_c3() describes, built without a script front end
+    (saugns_b200.program.ProgramBuilder); used by bench.py's product arm."""
+    from saugns_b200 import program as P
+    rnd = random.Random(seed)
+    pb = P.ProgramBuilder(ampmult=float(f"{0.3 / n_voices ** 0.5:.6f}"))
+    ms = int(round(secs * 1000))
+    for i in range(n_voices):
+        f_raw = 110.0 * 2 ** rnd.uniform(0, 4)
+        f = float(f"{f_raw:.3f}")
+        c = float(f"{rnd.uniform(-1, 1):.3f}")
+        r1 = rnd.choice([0.5, 1, 1.5, 2, 3])
+        r2 = rnd.choice([1, 2, 3.5, 7])
+        m2 = P.ProgramBuilder.wave("sin", freq=P.value(r2, ratio=True), amp=0.5)
+        if _is_fm(fm, i):
+            m1 = P.ProgramBuilder.wave("tri", freq=P.value(r1, ratio=True),
+                                       amp=P.value(0.8, goal=0.1, line="lin"))
+            carr = P.ProgramBuilder.wave(
+                "sin", freq=f, freq2=float(f"{2 * f_raw:.3f}"), time_ms=ms, pan=c,
+                amp=P.value(1.0, goal=0.2, line="xpe"), mods={"rfmod": [m1], "pmod": [m2]})
+        else:
+            m1 = P.ProgramBuilder.wave("tri", freq=P.value(r1, ratio=True),
+                                       amp=P.value(0.8, goal=0.1, line="lin"), mods={"pmod": [m2]})
+            carr = P.ProgramBuilder.wave("sin", freq=f, time_ms=ms, pan=c,
+                                         amp=P.value(1.0, goal=0.2, line="xpe"), mods={"pmod": [m1]})
+        pb.add_voice(carr)
+    return pb.finish()

@@ -9,6 +9,8 @@ finite-time modulators, event sequencing and voice reuse.
 """
 import random
 
+from saugns_b200.workloads import synth_c3, build_c3  # noqa: F401  (C3 lives with the product)
+
 WAVES = ["sin", "tri", "srs", "sqr", "ean", "cat", "eto", "par", "mto", "saw", "hsi", "spa"]
 LINES = ["cos", "lin", "sah", "exp", "log", "xpe", "lge", "sqe", "cub", "smo", "ncl", "nhl", "uwh"]
 NOISES = ["wh", "gw", "bw", "tw", "re", "vi", "bv"]
@@ -81,30 +83,10 @@ def feature_scripts():
     return s
 
 
-def synth_c3(n_voices=4096, secs=60, seed=1, fm=False):
-    """BASELINE config 3: n voices of 3-operator PM (or FM) chains with ramps."""
-    rnd = random.Random(seed)
-    lines = [f"S a{1.0 / n_voices:.9f}"]
-    for _ in range(n_voices):
-        f = 110.0 * 2 ** rnd.uniform(0, 4)
-        c = rnd.uniform(-1, 1)
-        r1 = rnd.choice([0.5, 1, 1.5, 2, 3])
-        r2 = rnd.choice([1, 2, 3.5, 7])
-        if fm:
-            lines.append(
-                f"Wsin f{f:.3f}.r{2 * f:.3f}[Wtri r{r1} a0.8[g0.1 llin]] t{secs} "
-                f"a1[g0.2 lxpe] c{c:.3f} p[Wsin r{r2} a0.5]")
-        else:
-            lines.append(
-                f"Wsin f{f:.3f} t{secs} a1[g0.2 lxpe] c{c:.3f} "
-                f"p[Wtri r{r1} a0.8[g0.1 llin] p[Wsin r{r2} a0.5]]")
-    return "\n".join(lines) + "\n"
-
-
 def synth_c4(n_voices=1024, secs=60, seed=2):
     """BASELINE config 4: self-feedback PM carriers with range-AM / ring-mod."""
     rnd = random.Random(seed)
-    lines = [f"S a{1.0 / n_voices:.9f}"]
+    lines = [f"S a.m{0.3 / n_voices ** 0.5:.6f}"]
     for i in range(n_voices):
         f = 110.0 * 2 ** rnd.uniform(0, 4)
         c = rnd.uniform(-1, 1)
@@ -124,7 +106,7 @@ def synth_c5_script(index):
     """BASELINE config 5: one of the independent mixed scripts (seed 1000+index)."""
     rnd = random.Random(1000 + index)
     nv = rnd.randint(4, 16)
-    lines = [f"S a{1.0 / nv:.6f}"]
+    lines = [f"S a.m{0.3 / nv ** 0.5:.6f}"]
     for _ in range(nv):
         t = rnd.uniform(1, 10)
         f = 110.0 * 2 ** rnd.uniform(0, 4)
@@ -143,3 +125,31 @@ def synth_c5_script(index):
             lines.append(f"W{rnd.choice(WAVES)} f{f:.3f}[g{f * rnd.uniform(0.5, 2):.3f} "
                          f"l{rnd.choice(LINES)}] t{t:.3f} c{c:.3f} a1.r0[Wsin f{rnd.uniform(0.5, 9):.3f}]")
     return "\n".join(lines) + "\n"
+
+
+# BASELINE config 2: the reference's examples/misc1-4fm_pm.sau (saugns v0.4.7,
+# by Joel K. Pettersson; input data for the parity test, quoted verbatim so
+# that the GPU box, which has no /root/reference, can render it).
+C2_MISC1_4FM_PM = """Wsin t15 f500.r501[Wsin f1] p[
+	Wsin f400.r800[
+		Wsqr f1.r10[Wsin f5000]
+		Wtri f0.1.r10.0[Wsin f0.2]
+	]
+] |
+
+Wsin t15 f400.r500[Wsqr f10] p[
+	Wsin r1.22/2 a.5
+	Wsin f244 a.5
+] |
+
+Wsin t15 f600.r666[Wsin f2] p[
+	Wsin f400
+	Wsin f400.r500[Wsin f.1]
+] |
+
+Wsin t15 f222.r666[Wsin f0.1] p[
+	Wsin r2/1
+	Wsin r4/3
+	Wsin r3/7
+]
+"""
