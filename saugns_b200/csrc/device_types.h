@@ -23,7 +23,8 @@ struct LineState {
 	float v0, vt;
 	uint32_t pos, end;
 	uint8_t type, flags;
-	uint16_t _pad;
+	uint8_t blk_done;   // position already wrapped inside the current REF_BLOCK (see line_run)
+	uint8_t _pad;
 };
 
 enum { LINE_AMP = 0, LINE_AMP2, LINE_PAN, LINE_FREQ, LINE_FREQ2, LINE_PMA, LINE_COUNT };

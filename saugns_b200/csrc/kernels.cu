@@ -127,14 +127,22 @@ __device__ __forceinline__ void line_advance(uint32_t &pos, uint32_t end, uint32
 __device__ void line_run(Ctx &c, LineState *ls, uint32_t dst, uint32_t mul, uint32_t n) {
 	float v0 = ls->v0, vt = ls->vt;
 	uint32_t pos = ls->pos, end = ls->end, type = ls->type, flags = ls->flags;
+	/* The reference advances a line once per 1024-block: when the position
+	 * reaches `end` (wrap, or goal reached) the rest of that block is not
+	 * counted (line.c:385-398,426-443).  blk_done carries that across our
+	 * 128-sample chunks so pos/flags stay bit-identical at any later event. */
+	uint32_t blk_done = c.oc == 0 ? 0u : ls->blk_done;
 	const bool has_mul = (mul != NO_BUF);
 	float m[SPL] = {1.f, 1.f, 1.f, 1.f};
 	if (has_mul) { float4 t = *B4(c, mul); m[0] = t.x; m[1] = t.y; m[2] = t.z; m[3] = t.w; }
 	float out[SPL];
 	const uint32_t i0 = c.lane * SPL;
 	if (!(flags & SAUABI_LINEP_GOAL)) {
-		bool ex;
-		line_advance(pos, end, flags, n, ex);
+		if (!blk_done) {
+			bool ex;
+			line_advance(pos, end, flags, n, ex);
+			if (ex) blk_done = 1;
+		}
 		const bool um = has_mul && (flags & SAUABI_LINEP_STATE_RATIO);
 #pragma unroll
 		for (int k = 0; k < SPL; ++k) out[k] = um ? v0 * m[k] : v0;
@@ -175,6 +183,7 @@ __device__ void line_run(Ctx &c, LineState *ls, uint32_t dst, uint32_t mul, uint
 		if (pos >= end) {
 			v0 = vt;
 			pos = 0;
+			blk_done = 1;
 			flags &= ~(SAUABI_LINEP_GOAL | SAUABI_LINEP_GOAL_RATIO | SAUABI_LINEP_TIME);
 			const bool um = has_mul && (flags & SAUABI_LINEP_STATE_RATIO);
 #pragma unroll
@@ -185,7 +194,7 @@ __device__ void line_run(Ctx &c, LineState *ls, uint32_t dst, uint32_t mul, uint
 	*B4(c, dst) = make_float4(out[0], out[1], out[2], out[3]);
 	__syncwarp();   /* every lane has read the state before lane 0 rewrites it */
 	if (c.lane == 0) {
-		ls->v0 = v0; ls->pos = pos; ls->flags = (uint8_t) flags;
+		ls->v0 = v0; ls->pos = pos; ls->flags = (uint8_t) flags; ls->blk_done = (uint8_t) blk_done;
 	}
 }
 
@@ -193,15 +202,21 @@ __device__ void line_run(Ctx &c, LineState *ls, uint32_t dst, uint32_t mul, uint
 __device__ void line_skip(Ctx &c, LineState *ls, uint32_t n) {
 	if (c.lane != 0) return;
 	uint32_t pos = ls->pos, end = ls->end, flags = ls->flags;
-	bool ex;
-	line_advance(pos, end, flags, n, ex);
-	if (ex && (flags & SAUABI_LINEP_GOAL)) {
-		ls->v0 = ls->vt;
-		if (flags & SAUABI_LINEP_GOAL_RATIO) flags |= SAUABI_LINEP_STATE_RATIO;
-		else flags &= ~SAUABI_LINEP_STATE_RATIO;
-		flags &= ~(SAUABI_LINEP_GOAL | SAUABI_LINEP_GOAL_RATIO);
+	uint32_t blk_done = c.oc == 0 ? 0u : ls->blk_done;
+	if (!blk_done) {
+		bool ex;
+		line_advance(pos, end, flags, n, ex);
+		if (ex) {
+			blk_done = 1;
+			if (flags & SAUABI_LINEP_GOAL) {
+				ls->v0 = ls->vt;
+				if (flags & SAUABI_LINEP_GOAL_RATIO) flags |= SAUABI_LINEP_STATE_RATIO;
+				else flags &= ~SAUABI_LINEP_STATE_RATIO;
+				flags &= ~(SAUABI_LINEP_GOAL | SAUABI_LINEP_GOAL_RATIO);
+			}
+		}
 	}
-	ls->pos = pos; ls->flags = (uint8_t) flags;
+	ls->pos = pos; ls->flags = (uint8_t) flags; ls->blk_done = (uint8_t) blk_done;
 }
 
 /* ---- sauPhasor_fill (wosc.h:135-169): scan over rounded increments ------ */
