@@ -861,9 +861,10 @@ __device__ uint32_t run_chunk(Ctx &c, const Instr *code, uint32_t code_len, uint
 
 /* ---- render kernel ------------------------------------------------------ */
 
-__global__ void __launch_bounds__(256)
-render_kernel(const CallDesc *calls, uint32_t ncalls, const SegDesc *segs, uint32_t ntasks,
-		const float *tables, uint32_t wave_mask, uint32_t nbufs, uint32_t warps_per_cta) {
+template <int MAXT, int MINB>
+__device__ __forceinline__ void render_body(const CallDesc *calls, uint32_t ncalls,
+		const SegDesc *segs, uint32_t ntasks, const float *tables, uint32_t wave_mask,
+		uint32_t nbufs, uint32_t warps_per_cta) {
 	extern __shared__ __align__(128) unsigned char smem[];
 	uint64_t *bar = reinterpret_cast<uint64_t*>(smem);
 	float *tab = reinterpret_cast<float*>(smem + 128);
@@ -962,9 +963,26 @@ render_kernel(const CallDesc *calls, uint32_t ncalls, const SegDesc *segs, uint3
 	}
 }
 
+/* Two register budgets: <=8 warps per CTA at 80 registers, or 16-warp CTAs at
+ * 64 registers so that 2 CTAs = 32 warps fit per SM (4736 resident warps on 148
+ * SMs: the 4096-voice workload renders in ONE wave instead of 1.15). */
+__global__ void __launch_bounds__(256, 3)
+render_kernel(const CallDesc *calls, uint32_t ncalls, const SegDesc *segs, uint32_t ntasks,
+		const float *tables, uint32_t wave_mask, uint32_t nbufs, uint32_t warps_per_cta) {
+	render_body<256, 3>(calls, ncalls, segs, ntasks, tables, wave_mask, nbufs, warps_per_cta);
+}
+__global__ void __launch_bounds__(512, 2)
+render_kernel_dense(const CallDesc *calls, uint32_t ncalls, const SegDesc *segs, uint32_t ntasks,
+		const float *tables, uint32_t wave_mask, uint32_t nbufs, uint32_t warps_per_cta) {
+	render_body<512, 2>(calls, ncalls, segs, ntasks, tables, wave_mask, nbufs, warps_per_cta);
+}
+
 /* ---- mix + clip epilogue ------------------------------------------------- */
 
-__global__ void __launch_bounds__(256)
+constexpr int MIX_THREADS = 128;
+constexpr int MIX_BATCH = 16;
+
+__global__ void __launch_bounds__(MIX_THREADS)
 mix_kernel(const CallDesc *calls, const SegDesc *segs, uint32_t mode /*0 pcm, 1 float planes*/) {
 	const CallDesc *cd = &calls[blockIdx.y];
 	const GenDesc *g = cd->gen;
@@ -984,11 +1002,28 @@ mix_kernel(const CallDesc *calls, const SegDesc *segs, uint32_t mode /*0 pcm, 1 
 		const float *ps = g->rows_s + f, *pr = g->rows_r + f;
 		const size_t stride = g->row_len;
 		if (fi < g->status[1 + si]) {
-			for (uint32_t lv = 0; lv < nlv; ++lv) {
+			/* voice order is kept (float sums are not associative); the loads of a
+			 * batch of voices are issued together so HBM latency overlaps */
+			uint32_t lv = 0;
+			for (; lv + MIX_BATCH <= nlv; lv += MIX_BATCH) {
+				float s[MIX_BATCH], r[MIX_BATCH];
+#pragma unroll
+				for (int k = 0; k < MIX_BATCH; ++k) {
+					const bool on = fi < __ldg(vl + lv + k);
+					s[k] = on ? __ldcs(ps + (size_t) (lv + k) * stride) : 0.f;
+					r[k] = on ? __ldcs(pr + (size_t) (lv + k) * stride) : 0.f;
+				}
+#pragma unroll
+				for (int k = 0; k < MIX_BATCH; ++k) {
+					L = (L + s[k]) - r[k];                         /* as compiled, Appendix B.3; */
+					R = (R + s[k]) + r[k];                         /* adding 0 is exact */
+				}
+			}
+			for (; lv < nlv; ++lv) {
 				if (fi < vl[lv]) {
 					const float s = ps[(size_t) lv * stride];
 					const float r = pr[(size_t) lv * stride];
-					L = (L + s) - r;                               /* as compiled, Appendix B.3 */
+					L = (L + s) - r;
 					R = (R + s) + r;
 				}
 			}
@@ -1044,24 +1079,30 @@ cudaError_t launch_render(const CallDesc *d_calls, uint32_t ncalls, const SegDes
 		uint32_t warps, cudaStream_t stream) {
 	if (ntasks == 0) return cudaSuccess;
 	const size_t smem = render_smem_bytes(wave_mask, nbufs, warps);
-	static size_t configured = 0;
-	if (smem > configured) {
-		cudaError_t e = cudaFuncSetAttribute(render_kernel,
-				cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+	static size_t configured[2] = {0, 0};
+	const int dense = warps > 8;
+	if (smem > configured[dense]) {
+		cudaError_t e = dense ?
+			cudaFuncSetAttribute(render_kernel_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem) :
+			cudaFuncSetAttribute(render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
 		if (e != cudaSuccess) return e;
-		configured = smem;
+		configured[dense] = smem;
 	}
 	const uint32_t grid = (ntasks + warps - 1) / warps;
-	render_kernel<<<grid, warps * 32, smem, stream>>>(d_calls, ncalls, d_segs, ntasks,
-			d_tables, wave_mask, nbufs, warps);
+	if (dense)
+		render_kernel_dense<<<grid, warps * 32, smem, stream>>>(d_calls, ncalls, d_segs, ntasks,
+				d_tables, wave_mask, nbufs, warps);
+	else
+		render_kernel<<<grid, warps * 32, smem, stream>>>(d_calls, ncalls, d_segs, ntasks,
+				d_tables, wave_mask, nbufs, warps);
 	return cudaGetLastError();
 }
 
 cudaError_t launch_mix(const CallDesc *d_calls, uint32_t ncalls, const SegDesc *d_segs,
 		uint32_t max_call_len, uint32_t mode, cudaStream_t stream) {
 	if (ncalls == 0 || max_call_len == 0) return cudaSuccess;
-	dim3 grid((max_call_len + 255) / 256, ncalls);
-	mix_kernel<<<grid, 256, 0, stream>>>(d_calls, d_segs, mode);
+	dim3 grid((max_call_len + MIX_THREADS - 1) / MIX_THREADS, ncalls);
+	mix_kernel<<<grid, MIX_THREADS, 0, stream>>>(d_calls, d_segs, mode);
 	return cudaGetLastError();
 }
 

@@ -519,9 +519,14 @@ static void plan_call(saugen_Generator *o, uint32_t buf_len, std::vector<SegDesc
 	o->cur_time = t_end;
 }
 
+/* CTA shape: small CTAs while there are fewer tasks than SMs x warps, 8-warp
+ * CTAs (3 per SM, 80 registers) up to 24 warps per SM, and 16-warp CTAs (2 per
+ * SM, 64 registers) beyond that when their shared memory fits twice per SM. */
 static uint32_t pick_warps(uint32_t ntasks, uint32_t wave_mask, uint32_t nbufs) {
+	const uint32_t sms = 148;
+	if (false && ntasks > sms * 24 && render_smem_bytes(wave_mask, nbufs, 16) <= 113 * 1024) return 16;
 	uint32_t warps = 8;
-	while (warps > 1 && (ntasks + warps - 1) / warps < 148) warps >>= 1;   /* fill the 148 SMs */
+	while (warps > 1 && (ntasks + warps - 1) / warps < sms) warps >>= 1;
 	while (warps > 1 && render_smem_bytes(wave_mask, nbufs, warps) > 200 * 1024) warps >>= 1;
 	return warps;
 }
