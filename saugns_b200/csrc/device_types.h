@@ -16,6 +16,7 @@ constexpr int REF_BLOCK = 1024;       // BUF_LEN, sau/generator.c:28
 constexpr int WAVE_LEN = 2048;        // sau/wave.h:18-19
 constexpr int NUM_WAVES = 12;
 constexpr int MAX_NEST = 24;          // len-stack depth per warp
+constexpr int MAX_SLOTS = 8;          // operator states cached in shared memory per voice
 constexpr uint32_t NO_BUF = 0xFF;
 
 /* sauLine run-time state (sau/line.h:115-121 minus time_ms). */
@@ -62,6 +63,9 @@ struct VoiceState {
 	uint32_t ev_cursor;    // next entry of this voice's event list
 	uint32_t code_off;     // current program (offset into GenDesc::code)
 	uint32_t code_len;
+	uint32_t ops_off;      // the program's operator list (offset into GenDesc::prog_ops)
+	uint32_t ops_cnt;
+	uint32_t carr_slot;    // carrier's slot in that list
 };
 
 /* Flattened sauLine delta carried by an event (NULL pointer => present = 0). */
@@ -91,6 +95,8 @@ struct EventRec {
 	uint32_t carr_op_id;
 	uint32_t opdata_off, opdata_count;
 	uint32_t code_off, code_len;    // voice program after this event
+	uint32_t ops_off, ops_cnt;      // its operator list (Instr::op indexes it)
+	uint32_t carr_slot;
 };
 
 /* Bytecode: the reference's recursive run_block walk (sau/generator.c:448-729)
@@ -110,7 +116,12 @@ enum Opcode : uint8_t {
 	I_MIX,         // a=out; b=in|NO_BUF(=1.0); c=amp; flags WAVEENV
 	I_VPAN,        // op=carrier; a=pan dst; d=1 run (camods) / 0 decide at run time
 	I_VOUT,        // op=carrier; a=carrier out; b=pan buf
-	I_END
+	I_END,
+	/* fused wave operator (run_block_wosc): a=out; b=freq buf (b, b+1 double as
+	 * self-PM scratch); c=pm|NO_BUF; d=fpm|NO_BUF; e=parent freq|NO_BUF (HEAD) */
+	I_WHEAD,       // ENTER + freq line -> b
+	I_WTAIL,       // phase fill + amp line + oscillator + mix + LEAVE
+	I_WLEAF,       // both, nothing leaves the registers
 };
 enum {
 	F_LAYER       = 1 << 0,   // accumulate into out
@@ -118,6 +129,9 @@ enum {
 	F_WAVEENV     = 1 << 2,
 	F_HAS_APMODS  = 1 << 3,
 	F_HAS_CAMODS  = 1 << 4,
+	F_SKIP_FREQ2  = 1 << 5,   // the freq2 / amp2 / pm_a line was set at some point:
+	F_SKIP_AMP2   = 1 << 6,   // keep its position bookkeeping (sauLine_skip)
+	F_MAY_SELFMOD = 1 << 7,
 };
 struct Instr {
 	uint8_t opcode, a, b, c, d, e;
@@ -133,6 +147,7 @@ struct GenDesc {
 	const EventRec *events;
 	const OpDataRec *opdata;
 	const Instr *code;
+	const uint32_t *prog_ops;     // operator ids of every compiled voice program
 	const uint32_t *vev_off;      // [vo_count+1] CSR into vev_idx
 	const uint32_t *vev_idx;      // global event indices per voice, in order
 	float *rows_s, *rows_r;       // [n_local_voices][row_len] carrier rows of a call

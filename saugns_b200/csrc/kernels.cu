@@ -30,6 +30,12 @@ namespace saugen {
 
 #define FULL 0xffffffffu
 
+/* per-warp shared memory: operator-state cache, work buffers, len stack */
+__host__ __device__ inline uint32_t warp_smem_bytes(uint32_t nbufs) {
+	return MAX_SLOTS * (uint32_t) sizeof(OpState) + nbufs * CHUNK * (uint32_t) sizeof(float) +
+		3 * MAX_NEST * (uint32_t) sizeof(uint32_t);
+}
+
 /* ---- TMA 1-D bulk copy + mbarrier (PTX) --------------------------------- */
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
@@ -67,10 +73,13 @@ struct Ctx {
 	uint32_t *stk_len;         // shared: MAX_NEST entries each
 	uint32_t *stk_rem;
 	uint32_t *stk_layer;
+	OpState *sops;             // shared: this voice's operator states (cache)
 	const float *tab;          // shared: staged wave tables
 	const WaveCoeffs *wc;      // global
 	const GenDesc *g;          // global
-	OpState *ops;
+	OpState *gops;             // global operator states
+	const uint32_t *prog_ops;  // global: slot -> operator id of the current program
+	uint32_t cached;           // operator states live in shared memory
 	uint32_t wave_mask;        // tables staged by this launch
 	uint32_t oc;               // chunk offset inside the reference's 1024-block
 	int lane;
@@ -79,11 +88,22 @@ struct Ctx {
 	uint32_t last_len, last_rem;
 };
 
+/* Instr::op is a slot of the voice program's operator list. */
+__device__ __forceinline__ OpState *op_ptr(const Ctx &c, uint32_t slot) {
+	return c.cached ? c.sops + slot : c.gops + c.prog_ops[slot];
+}
 __device__ __forceinline__ float4 *B4(const Ctx &c, uint32_t i) {
 	return reinterpret_cast<float4*>(c.bufs + i * CHUNK) + c.lane;
 }
 __device__ __forceinline__ uint4 *U4(const Ctx &c, uint32_t i) {
 	return reinterpret_cast<uint4*>(c.bufs + i * CHUNK) + c.lane;
+}
+__device__ __forceinline__ void ld4(const Ctx &c, uint32_t buf, float v[SPL]) {
+	const float4 t = *B4(c, buf);
+	v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+__device__ __forceinline__ void st4(const Ctx &c, uint32_t buf, const float v[SPL]) {
+	*B4(c, buf) = make_float4(v[0], v[1], v[2], v[3]);
 }
 __device__ __forceinline__ const float *wave_lut(const Ctx &c, uint32_t wave) {
 	uint32_t slot = __popc(c.wave_mask & ((1u << wave) - 1u));
@@ -123,8 +143,12 @@ __device__ __forceinline__ void line_advance(uint32_t &pos, uint32_t end, uint32
 	}
 }
 
-/* sauLine_run(line, bufs[dst], len, mulbuf) -- line.c:417-445 */
-__device__ void line_run(Ctx &c, LineState *ls, uint32_t dst, uint32_t mul, uint32_t n) {
+/* sauLine_run(line, out, n, mulbuf) -- line.c:417-445 -- into registers.
+ * mulbuf: shared-memory buffer of ratio multipliers or nullptr; rem: samples
+ * the visit still has in the reference's 1024-block (for gcc's cub tail).
+ * Ends with the state write-back by lane 0; the caller syncs the warp. */
+__device__ void line_eval(const Ctx &c, LineState *ls, const float *mulbuf, uint32_t n,
+		uint32_t rem, float out[SPL]) {
 	float v0 = ls->v0, vt = ls->vt;
 	uint32_t pos = ls->pos, end = ls->end, type = ls->type, flags = ls->flags;
 	/* The reference advances a line once per 1024-block: when the position
@@ -132,10 +156,12 @@ __device__ void line_run(Ctx &c, LineState *ls, uint32_t dst, uint32_t mul, uint
 	 * counted (line.c:385-398,426-443).  blk_done carries that across our
 	 * 128-sample chunks so pos/flags stay bit-identical at any later event. */
 	uint32_t blk_done = c.oc == 0 ? 0u : ls->blk_done;
-	const bool has_mul = (mul != NO_BUF);
+	const bool has_mul = (mulbuf != nullptr);
 	float m[SPL] = {1.f, 1.f, 1.f, 1.f};
-	if (has_mul) { float4 t = *B4(c, mul); m[0] = t.x; m[1] = t.y; m[2] = t.z; m[3] = t.w; }
-	float out[SPL];
+	if (has_mul) {
+		const float4 t = reinterpret_cast<const float4*>(mulbuf)[c.lane];
+		m[0] = t.x; m[1] = t.y; m[2] = t.z; m[3] = t.w;
+	}
 	const uint32_t i0 = c.lane * SPL;
 	if (!(flags & SAUABI_LINEP_GOAL)) {
 		if (!blk_done) {
@@ -150,12 +176,12 @@ __device__ void line_run(Ctx &c, LineState *ls, uint32_t dst, uint32_t mul, uint
 		bool fillmul = has_mul;                                   /* sauLine_get, line.c:349-378 */
 		if (flags & SAUABI_LINEP_GOAL_RATIO) {
 			if (!(flags & SAUABI_LINEP_STATE_RATIO)) {
-				if (has_mul) v0 = v0 / c.bufs[mul * CHUNK];
+				if (has_mul) v0 = v0 / mulbuf[0];
 				flags |= SAUABI_LINEP_STATE_RATIO;
 			}
 		} else {
 			if (flags & SAUABI_LINEP_STATE_RATIO) {
-				if (has_mul) v0 = v0 * c.bufs[mul * CHUNK];
+				if (has_mul) v0 = v0 * mulbuf[0];
 				flags &= ~SAUABI_LINEP_STATE_RATIO;
 			}
 			fillmul = false;
@@ -168,7 +194,7 @@ __device__ void line_run(Ctx &c, LineState *ls, uint32_t dst, uint32_t mul, uint
 			 * odd-length fill call, counted in the reference's 1024-block. */
 			uint32_t tail_idx = 0xffffffffu;
 			if (f.type == sau::L_cub) {
-				uint32_t F = end - pos, rem = c.stk_rem[c.sp];
+				uint32_t F = end - pos;
 				if (F > rem) F = rem;
 				if (F <= (uint32_t) CHUNK && ((c.oc + F) & 1u)) tail_idx = F - 1;
 			}
@@ -191,7 +217,6 @@ __device__ void line_run(Ctx &c, LineState *ls, uint32_t dst, uint32_t mul, uint
 				if (i0 + k >= flen) out[k] = um ? v0 * m[k] : v0;
 		}
 	}
-	*B4(c, dst) = make_float4(out[0], out[1], out[2], out[3]);
 	__syncwarp();   /* every lane has read the state before lane 0 rewrites it */
 	if (c.lane == 0) {
 		ls->v0 = v0; ls->pos = pos; ls->flags = (uint8_t) flags; ls->blk_done = (uint8_t) blk_done;
@@ -199,7 +224,7 @@ __device__ void line_run(Ctx &c, LineState *ls, uint32_t dst, uint32_t mul, uint
 }
 
 /* sauLine_skip -- line.c:456-473 */
-__device__ void line_skip(Ctx &c, LineState *ls, uint32_t n) {
+__device__ void line_skip(const Ctx &c, LineState *ls, uint32_t n) {
 	if (c.lane != 0) return;
 	uint32_t pos = ls->pos, end = ls->end, flags = ls->flags;
 	uint32_t blk_done = c.oc == 0 ? 0u : ls->blk_done;
@@ -221,16 +246,10 @@ __device__ void line_skip(Ctx &c, LineState *ls, uint32_t n) {
 
 /* ---- sauPhasor_fill (wosc.h:135-169): scan over rounded increments ------ */
 
-__device__ void phasor_fill(Ctx &c, const Instr &in, uint32_t n) {
-	OpState *o = &c.ops[in.op];
+__device__ void phasor_eval(const Ctx &c, OpState *o, const float f[SPL], const float *pm,
+		const float *fpm, uint32_t n, uint32_t ph[SPL]) {
 	const float coeff = c.g->coeff;
 	const uint32_t phase0 = o->i0;
-	const float4 f4 = *B4(c, in.b);
-	const float f[SPL] = {f4.x, f4.y, f4.z, f4.w};
-	float pm[SPL] = {0, 0, 0, 0}, fpm[SPL] = {0, 0, 0, 0};
-	const bool has_pm = in.c != NO_BUF, has_fpm = in.d != NO_BUF;
-	if (has_pm) { float4 t = *B4(c, in.c); pm[0] = t.x; pm[1] = t.y; pm[2] = t.z; pm[3] = t.w; }
-	if (has_fpm) { float4 t = *B4(c, in.d); fpm[0] = t.x; fpm[1] = t.y; fpm[2] = t.z; fpm[3] = t.w; }
 	const uint32_t i0 = c.lane * SPL;
 	uint32_t p[SPL], ofs[SPL];
 	uint32_t run = 0;
@@ -240,23 +259,36 @@ __device__ void phasor_fill(Ctx &c, const Instr &in, uint32_t n) {
 		run += inc;
 		p[k] = run;
 		int64_t of = 0;
-		if (has_pm && has_fpm) of = sau::pofs_pm_fpm(pm[k], fpm[k], f[k], 2147483648.f);
-		else if (has_pm) of = sau::pofs_pm(pm[k], 2147483648.f);
-		else if (has_fpm) of = sau::pofs_fpm(fpm[k], f[k], 2147483648.f);
+		if (pm && fpm) of = sau::pofs_pm_fpm(pm[k], fpm[k], f[k], 2147483648.f);
+		else if (pm) of = sau::pofs_pm(pm[k], 2147483648.f);
+		else if (fpm) of = sau::pofs_fpm(fpm[k], f[k], 2147483648.f);
 		ofs[k] = (uint32_t) of;
 	}
 	const uint32_t incl = scan_incl_u32(run, c.lane);
 	const uint32_t base = phase0 + (incl - run);
-	*U4(c, in.a) = make_uint4(base + p[0] + ofs[0], base + p[1] + ofs[1],
-			base + p[2] + ofs[2], base + p[3] + ofs[3]);
+#pragma unroll
+	for (int k = 0; k < SPL; ++k) ph[k] = base + p[k] + ofs[k];
 	const uint32_t total = __shfl_sync(FULL, incl, 31);
 	if (c.lane == 0) o->i0 = phase0 + total;
 }
 
 /* ---- sauWOsc_run / sauWOsc_run_selfmod (wosc.h:215-310) ----------------- */
 
-__device__ void wosc_run(Ctx &c, const Instr &in, uint32_t n) {
-	OpState *o = &c.ops[in.op];
+/* Differentiation (re)start, wosc.h:215-230; ph0 = phase of the chunk's sample 0. */
+__device__ __forceinline__ void wosc_reset(const Ctx &c, const float *lut, uint32_t wave,
+		uint32_t ph0, uint32_t &prev_phase, double &prev_Is, float &prev_s) {
+	double poly, c0;
+	sau::herp(lut, ph0 - sau::WAVE_SLEN, &poly, &c0);
+	const double Is = sau::herp(lut, ph0, (double*) 0, (double*) 0);
+	prev_s = (float) (((Is - poly) - c0) * (double) c.wc->amp256[wave] +
+			(double) c.wc->diff_offset[wave]);
+	prev_Is = Is;
+	prev_phase = ph0;
+}
+
+/* Parallel form: sample i needs phase[i], phase[i-1] only. */
+__device__ void wosc_eval(const Ctx &c, OpState *o, const uint32_t ph[SPL], uint32_t n,
+		float s[SPL]) {
 	const uint32_t wave = o->mode;
 	const float *lut = wave_lut(c, wave);
 	const float ds = c.wc->diff_scale[wave], doff = c.wc->diff_offset[wave];
@@ -264,48 +296,11 @@ __device__ void wosc_run(Ctx &c, const Instr &in, uint32_t n) {
 	double prev_Is = o->prev_Is;
 	float prev_s = o->prev_s;
 	uint32_t oscflags = o->oscflags;
-	const uint32_t *phase_buf = reinterpret_cast<const uint32_t*>(c.bufs + in.b * CHUNK);
-	const bool selfmod = (in.flags & F_HAS_APMODS) || c.pma_flag;
-	if (oscflags & OSC_RESET_DIFF) {                              /* wosc.h:215-230 */
-		const uint32_t ph = phase_buf[0];
-		double poly, c0;
-		sau::herp(lut, ph - sau::WAVE_SLEN, &poly, &c0);
-		const double Is = sau::herp(lut, ph, (double*) 0, (double*) 0);
-		prev_s = (float) (((Is - poly) - c0) * (double) c.wc->amp256[wave] + (double) doff);
-		prev_Is = Is;
-		prev_phase = ph;
+	if (oscflags & OSC_RESET_DIFF) {
+		const uint32_t ph0 = __shfl_sync(FULL, ph[0], 0);
+		wosc_reset(c, lut, wave, ph0, prev_phase, prev_Is, prev_s);
 		oscflags &= ~OSC_RESET_DIFF;
 	}
-	__syncwarp();
-	if (selfmod) {
-		/* truly serial (non-linear recurrence through fb_s): one lane, state in registers */
-		if (c.lane == 0) {
-			float fb_s = o->fb_s;
-			const float *pma = c.bufs + in.c * CHUNK;
-			float *dst = c.bufs + in.a * CHUNK;
-			for (uint32_t i = 0; i < n; ++i) {
-				float s;
-				const uint32_t phase = phase_buf[i] +
-					(uint32_t) sau::ftoi64(fb_s * pma[i] * 2147483648.f);
-				const int32_t d = (int32_t) (phase - prev_phase);
-				if (d == 0) {
-					s = prev_s;
-				} else {
-					const double Is = sau::herp(lut, phase, (double*) 0, (double*) 0);
-					s = sau::wosc_diff(Is, prev_Is, d, ds, doff);
-					prev_Is = Is; prev_s = s; prev_phase = phase;
-				}
-				dst[i] = s;
-				fb_s = (fb_s + s) * 0.5f;
-			}
-			o->fb_s = fb_s;
-			o->i1 = prev_phase; o->prev_Is = prev_Is; o->prev_s = prev_s;
-			o->oscflags = (uint8_t) oscflags;
-		}
-		return;
-	}
-	const uint4 ph4 = *U4(c, in.b);
-	const uint32_t ph[SPL] = {ph4.x, ph4.y, ph4.z, ph4.w};
 	const uint32_t i0 = c.lane * SPL;
 	double Is[SPL];
 #pragma unroll
@@ -314,7 +309,6 @@ __device__ void wosc_run(Ctx &c, const Instr &in, uint32_t n) {
 	uint32_t pph = __shfl_up_sync(FULL, ph[SPL - 1], 1);
 	double pIs = __shfl_up_sync(FULL, Is[SPL - 1], 1);
 	if (c.lane == 0) { pph = prev_phase; pIs = prev_Is; }
-	float s[SPL];
 	bool zd[SPL];               // valid sample with zero phase difference
 	bool lead_zero = false;     // has zero-difference samples before its first computed one
 	bool has_nz = false;
@@ -349,7 +343,6 @@ __device__ void wosc_run(Ctx &c, const Instr &in, uint32_t n) {
 		}
 		if (!has_nz) s_run = inc;
 	}
-	*B4(c, in.a) = make_float4(s[0], s[1], s[2], s[3]);
 	/* carried state = last valid sample (n >= 1 here) */
 	const uint32_t li = n - 1;
 	const int src_lane = (int) (li / SPL), src_k = (int) (li % SPL);
@@ -365,10 +358,180 @@ __device__ void wosc_run(Ctx &c, const Instr &in, uint32_t n) {
 	}
 }
 
+/* Self-PM: a non-linear recurrence through fb_s, truly serial (wosc.h:273-310).
+ * One lane runs it with the state in registers; phases and pm_a amounts come
+ * from shared memory, the output replaces the pm_a buffer in place if dst==pma. */
+__device__ void wosc_selfmod(const Ctx &c, OpState *o, const uint32_t *phase_buf,
+		const float *pma, float *dst, uint32_t n) {
+	__syncwarp();
+	if (c.lane == 0) {
+		const uint32_t wave = o->mode;
+		const float *lut = wave_lut(c, wave);
+		const float ds = c.wc->diff_scale[wave], doff = c.wc->diff_offset[wave];
+		uint32_t prev_phase = o->i1;
+		double prev_Is = o->prev_Is;
+		float prev_s = o->prev_s, fb_s = o->fb_s;
+		uint32_t oscflags = o->oscflags;
+		if (oscflags & OSC_RESET_DIFF) {
+			wosc_reset(c, lut, wave, phase_buf[0], prev_phase, prev_Is, prev_s);
+			oscflags &= ~OSC_RESET_DIFF;
+		}
+		for (uint32_t i = 0; i < n; ++i) {
+			float s;
+			const uint32_t phase = phase_buf[i] +
+				(uint32_t) sau::ftoi64(fb_s * pma[i] * 2147483648.f);
+			const int32_t d = (int32_t) (phase - prev_phase);
+			if (d == 0) {
+				s = prev_s;
+			} else {
+				const double Is = sau::herp(lut, phase, (double*) 0, (double*) 0);
+				s = sau::wosc_diff(Is, prev_Is, d, ds, doff);
+				prev_Is = Is; prev_s = s; prev_phase = phase;
+			}
+			dst[i] = s;
+			fb_s = (fb_s + s) * 0.5f;
+		}
+		o->fb_s = fb_s;
+		o->i1 = prev_phase; o->prev_Is = prev_Is; o->prev_s = prev_s;
+		o->oscflags = (uint8_t) oscflags;
+	}
+	__syncwarp();
+}
+
+/* pm_a decision, generator.c:485-490: made once per reference 1024-block */
+__device__ __forceinline__ bool pma_decide(const Ctx &c, OpState *o) {
+	const LineState *ls = &o->line[LINE_PMA];
+	uint32_t of = o->flags;
+	bool run;
+	if (c.oc == 0) {
+		run = (ls->v0 != 0.f) || (ls->flags & SAUABI_LINEP_GOAL);
+		of = run ? (of | ON_PMA_RUN) : (of & ~ON_PMA_RUN);
+	} else {
+		run = (of & ON_PMA_RUN) != 0;
+	}
+	__syncwarp();
+	if (c.lane == 0) o->flags = (uint8_t) of;
+	return run;
+}
+
+/* block_mix_add / block_mix_mul_waveenv, generator.c:384-440, on registers */
+__device__ __forceinline__ void mix_eval(const Ctx &c, uint32_t out_buf, const float x[SPL],
+		const float a[SPL], uint32_t n, uint32_t layer, bool waveenv) {
+	const uint32_t i0 = c.lane * SPL;
+	float o[SPL];
+	ld4(c, out_buf, o);
+#pragma unroll
+	for (int k = 0; k < SPL; ++k) {
+		if (i0 + k >= n) continue;
+		if (waveenv) {
+			const float s_amp = a[k] * 0.5f;
+			const float s = (x[k] * s_amp) + fabsf(s_amp);
+			o[k] = layer ? o[k] * s : s;
+		} else {
+			const float v = x[k] * a[k];
+			o[k] = layer ? o[k] + v : v;
+		}
+	}
+	st4(c, out_buf, o);
+}
+
+/* end of run_block, generator.c:716-728: zero the unfilled tail, count time */
+__device__ __forceinline__ void leave_eval(const Ctx &c, OpState *o, uint32_t out_buf,
+		uint32_t len, uint32_t plen, uint32_t layer) {
+	const uint32_t i0 = c.lane * SPL;
+	if (!(o->flags & ON_TIME_INF)) {
+		if (!layer && len < plen) {
+			float4 v = *B4(c, out_buf);
+			if (i0 + 0 >= len) v.x = 0.f;
+			if (i0 + 1 >= len) v.y = 0.f;
+			if (i0 + 2 >= len) v.z = 0.f;
+			if (i0 + 3 >= len) v.w = 0.f;
+			*B4(c, out_buf) = v;
+		}
+		__syncwarp();
+		if (c.lane == 0) o->time -= len;
+	}
+}
+
+/* ---- fused wave operator (run_block_wosc, generator.c:548-602) ---------- *
+ * HEAD = run_block entry + frequency line (no FM lists); children (PM / fPM
+ * modulators) run between HEAD and TAIL; TAIL = phase fill + amplitude line
+ * (no AM lists, no self-PM modulators) + oscillator + block_mix + run_block
+ * exit.  A leaf operator does both in one pass with everything in registers. */
+template <bool HEAD, bool TAIL>
+__device__ void wop(Ctx &c, const Instr &in, uint32_t &pc) {
+	OpState *o = op_ptr(c, in.op);
+	uint32_t len, rem, layer, plen;
+	float fr[SPL];
+	if (HEAD) {                                                    /* generator.c:675-698 */
+		plen = c.stk_len[c.sp];
+		const uint32_t flags = o->flags, t = o->time;
+		rem = c.stk_rem[c.sp];
+		if (!(flags & ON_TIME_INF) && t < rem) rem = t;
+		len = rem < plen ? rem : plen;
+		layer = (in.flags & F_LAYER) ? 1u :
+			((in.flags & F_LAYER_PMA) ? (c.pma_flag ? 1u : 0u) : 0u);
+		if (!TAIL) {
+			++c.sp;
+			if (c.lane == 0) { c.stk_len[c.sp] = len; c.stk_rem[c.sp] = rem; c.stk_layer[c.sp] = layer; }
+			__syncwarp();
+			if (len == 0) { pc = in.aux; return; }
+		}
+		if (len > 0) {
+			line_eval(c, &o->line[LINE_FREQ], in.e != NO_BUF ? c.bufs + in.e * CHUNK : nullptr,
+					len, rem, fr);
+			if (in.flags & F_SKIP_FREQ2) line_skip(c, &o->line[LINE_FREQ2], len);
+			if (!TAIL) st4(c, in.b, fr);
+			__syncwarp();
+		}
+		if (!TAIL) return;
+	} else {
+		len = c.stk_len[c.sp]; rem = c.stk_rem[c.sp]; layer = c.stk_layer[c.sp];
+		plen = c.stk_len[c.sp - 1];
+		if (len > 0) ld4(c, in.b, fr);
+	}
+	if (len > 0) {
+		float pm[SPL], fpm[SPL];
+		if (in.c != NO_BUF) ld4(c, in.c, pm);
+		if (in.d != NO_BUF) ld4(c, in.d, fpm);
+		uint32_t ph[SPL];
+		phasor_eval(c, o, fr, in.c != NO_BUF ? pm : nullptr, in.d != NO_BUF ? fpm : nullptr,
+				len, ph);
+		float am[SPL];
+		line_eval(c, &o->line[LINE_AMP], nullptr, len, rem, am);
+		if (in.flags & F_SKIP_AMP2) line_skip(c, &o->line[LINE_AMP2], len);
+		__syncwarp();
+		bool selfmod = false;
+		if (in.flags & F_MAY_SELFMOD) selfmod = pma_decide(c, o);
+		float s[SPL];
+		if (!selfmod) {
+			if (in.flags & F_MAY_SELFMOD) line_skip(c, &o->line[LINE_PMA], len);
+			wosc_eval(c, o, ph, len, s);
+		} else {
+			/* scratch: phases over the (consumed) freq buffer, pm_a amounts and
+			 * then the output over the buffer after it */
+			float pa[SPL];
+			line_eval(c, &o->line[LINE_PMA], nullptr, len, rem, pa);
+			*U4(c, in.b) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+			st4(c, in.b + 1u, pa);
+			wosc_selfmod(c, o, reinterpret_cast<const uint32_t*>(c.bufs + in.b * CHUNK),
+					c.bufs + (in.b + 1u) * CHUNK, c.bufs + (in.b + 1u) * CHUNK, len);
+			ld4(c, in.b + 1u, s);
+		}
+		c.pma_flag = selfmod;
+		__syncwarp();
+		mix_eval(c, in.a, s, am, len, layer, (in.flags & F_WAVEENV) != 0);
+	}
+	leave_eval(c, o, in.a, len, plen, layer);
+	c.last_len = len; c.last_rem = rem;
+	if (!HEAD) --c.sp;
+	__syncwarp();
+}
+
 /* ---- sauCyclor_fill (rasg.h:165-222) ------------------------------------ */
 
 __device__ void cyclor_fill(Ctx &c, const Instr &in, uint32_t n) {
-	OpState *o = &c.ops[in.op];
+	OpState *o = op_ptr(c, in.op);
 	float coeff = c.g->coeff, ps = 2147483648.f;
 	if (o->oscflags & 1) { coeff *= 2; ps *= 2; }
 	const uint64_t cp0 = ((uint64_t) o->i1 << 32) | o->i0;
@@ -376,8 +539,8 @@ __device__ void cyclor_fill(Ctx &c, const Instr &in, uint32_t n) {
 	const float f[SPL] = {f4.x, f4.y, f4.z, f4.w};
 	float pm[SPL] = {0, 0, 0, 0}, fpm[SPL] = {0, 0, 0, 0};
 	const bool has_pm = in.d != NO_BUF, has_fpm = in.e != NO_BUF;
-	if (has_pm) { float4 t = *B4(c, in.d); pm[0] = t.x; pm[1] = t.y; pm[2] = t.z; pm[3] = t.w; }
-	if (has_fpm) { float4 t = *B4(c, in.e); fpm[0] = t.x; fpm[1] = t.y; fpm[2] = t.z; fpm[3] = t.w; }
+	if (has_pm) ld4(c, in.d, pm);
+	if (has_fpm) ld4(c, in.e, fpm);
 	const uint32_t i0 = c.lane * SPL;
 	uint64_t pre[SPL], ofs[SPL];
 	uint64_t run = 0;
@@ -403,7 +566,7 @@ __device__ void cyclor_fill(Ctx &c, const Instr &in, uint32_t n) {
 		phf[k] = sau::i2f((int32_t) phase) * (1.f / 2147483648.f);
 	}
 	*U4(c, in.a) = make_uint4(cyc[0], cyc[1], cyc[2], cyc[3]);
-	*B4(c, in.b) = make_float4(phf[0], phf[1], phf[2], phf[3]);
+	st4(c, in.b, phf);
 	const uint64_t total = __shfl_sync(FULL, incl, 31);
 	if (c.lane == 0) {
 		const uint64_t cp = cp0 + total;
@@ -414,12 +577,13 @@ __device__ void cyclor_fill(Ctx &c, const Instr &in, uint32_t n) {
 /* ---- sauRasG_run / sauRasG_run_selfmod (rasg.h:692-772) ----------------- */
 
 __device__ void rasg_run(Ctx &c, const Instr &in, uint32_t n) {
-	OpState *o = &c.ops[in.op];
+	OpState *o = op_ptr(c, in.op);
 	const unsigned flags = o->ras_flags, func = o->ras_func;
 	const int sr = o->ras_level, line = o->mode;
 	const uint32_t alpha = o->ras_alpha;
 	const bool selfmod = (in.flags & F_HAS_APMODS) || c.pma_flag;
 	if (selfmod) {
+		__syncwarp();
 		if (c.lane == 0) {                                         /* rasg.h:242-280 */
 			float fb_s = o->fb_s, prev_s = o->prev_s;
 			float *main_buf = c.bufs + in.a * CHUNK;
@@ -443,8 +607,8 @@ __device__ void rasg_run(Ctx &c, const Instr &in, uint32_t n) {
 	}
 	const uint4 cy4 = *U4(c, in.b);
 	const uint32_t cy[SPL] = {cy4.x, cy4.y, cy4.z, cy4.w};
-	const float4 p4 = *B4(c, in.a);
-	const float ph[SPL] = {p4.x, p4.y, p4.z, p4.w};
+	float ph[SPL];
+	ld4(c, in.a, ph);
 	/* sauLine_map_cub: 4-wide body + scalar tail, counted in the 1024-block */
 	const uint32_t blk_len = c.oc + c.stk_rem[c.sp];
 	const uint32_t tail_from = blk_len & ~3u;
@@ -455,7 +619,7 @@ __device__ void rasg_run(Ctx &c, const Instr &in, uint32_t n) {
 		out[k] = sau::rasg_sample(func, flags, sr, alpha, line, cy[k], ph[k], false,
 				(c.oc + idx) >= tail_from);
 	}
-	*B4(c, in.a) = make_float4(out[0], out[1], out[2], out[3]);
+	st4(c, in.a, out);
 }
 
 /* ---- sauNoiseG_run_* (noise.h:41-185) ----------------------------------- */
@@ -465,7 +629,7 @@ __device__ __forceinline__ int32_t noise_tern(uint32_t n) {       /* bv's s1, no
 	return (n & 1) ? (s1 * 2 + 1) : 0;
 }
 __device__ void noise_run(Ctx &c, const Instr &in, uint32_t n) {
-	OpState *o = &c.ops[in.op];
+	OpState *o = op_ptr(c, in.op);
 	const uint32_t n0 = o->i0, prev = o->i1, type = o->mode;
 	const float scale = 1.f / 2147483648.f;
 	const uint32_t i0 = c.lane * SPL;
@@ -530,7 +694,7 @@ __device__ void noise_run(Ctx &c, const Instr &in, uint32_t n) {
 		if (n) new_prev = (uint32_t) noise_tern(n0 + n - 1);
 		break;
 	}
-	*B4(c, in.a) = make_float4(out[0], out[1], out[2], out[3]);
+	st4(c, in.a, out);
 	__syncwarp();
 	if (c.lane == 0) { o->i0 = n0 + n; o->i1 = new_prev; }
 }
@@ -680,6 +844,9 @@ __device__ void apply_event(const GenDesc *g, const WaveCoeffs *wc, const EventR
 	vs->flags |= VN_INIT;
 	vs->code_off = ev->code_off;
 	vs->code_len = ev->code_len;
+	vs->ops_off = ev->ops_off;
+	vs->ops_cnt = ev->ops_cnt;
+	vs->carr_slot = ev->carr_slot;
 	vs->duration = g->ops[vs->carr_op].time;                       /* set_voice_duration */
 }
 
@@ -701,8 +868,11 @@ __device__ uint32_t run_chunk(Ctx &c, const Instr *code, uint32_t code_len, uint
 		const uint32_t n = c.stk_len[c.sp];
 		const uint32_t i0 = c.lane * SPL;
 		switch (in.opcode) {
+		case I_WLEAF: wop<true, true>(c, in, pc); break;
+		case I_WHEAD: wop<true, false>(c, in, pc); break;
+		case I_WTAIL: wop<false, true>(c, in, pc); break;
 		case I_ENTER: {                                            /* generator.c:675-698 */
-			const OpState *o = &c.ops[in.op];
+			const OpState *o = op_ptr(c, in.op);
 			const uint32_t flags = o->flags, t = o->time;
 			uint32_t rem = c.stk_rem[c.sp];
 			if (!(flags & ON_TIME_INF) && t < rem) rem = t;
@@ -715,22 +885,11 @@ __device__ uint32_t run_chunk(Ctx &c, const Instr *code, uint32_t code_len, uint
 			if (len == 0) pc = in.aux;     /* nothing to render: go to the LEAVE */
 			break; }
 		case I_LEAVE: {                                            /* generator.c:716-728 */
-			OpState *o = &c.ops[in.op];
+			OpState *o = op_ptr(c, in.op);
 			const uint32_t len = n, layer = c.stk_layer[c.sp];
 			c.last_len = len; c.last_rem = c.stk_rem[c.sp];
 			--c.sp;
-			const uint32_t plen = c.stk_len[c.sp];
-			if (!(o->flags & ON_TIME_INF)) {
-				if (!layer && len < plen) {
-					float4 v = *B4(c, in.a);
-					if (i0 + 0 >= len) v.x = 0.f;
-					if (i0 + 1 >= len) v.y = 0.f;
-					if (i0 + 2 >= len) v.z = 0.f;
-					if (i0 + 3 >= len) v.w = 0.f;
-					*B4(c, in.a) = v;
-				}
-				if (c.lane == 0) o->time -= len;
-			}
+			leave_eval(c, o, in.a, len, c.stk_len[c.sp], layer);
 			__syncwarp();
 			break; }
 		case I_ZERO:
@@ -738,9 +897,15 @@ __device__ uint32_t run_chunk(Ctx &c, const Instr *code, uint32_t code_len, uint
 			__syncwarp();
 			break;
 		case I_LINE: {
-			LineState *ls = &c.ops[in.op].line[in.c];
-			if (in.d) line_run(c, ls, in.a, in.b, n);
-			else line_skip(c, ls, n);
+			LineState *ls = &op_ptr(c, in.op)->line[in.c];
+			if (in.d) {
+				float out[SPL];
+				line_eval(c, ls, in.b != NO_BUF ? c.bufs + in.b * CHUNK : nullptr, n,
+						c.stk_rem[c.sp], out);
+				st4(c, in.a, out);
+			} else {
+				line_skip(c, ls, n);
+			}
 			__syncwarp();
 			break; }
 		case I_RANGE: {                                            /* generator.c:465-467 */
@@ -753,31 +918,44 @@ __device__ uint32_t run_chunk(Ctx &c, const Instr *code, uint32_t code_len, uint
 			*B4(c, in.a) = p;
 			__syncwarp();
 			break; }
-		case I_PHASOR:
-			phasor_fill(c, in, n);
+		case I_PHASOR: {
+			float f[SPL], pm[SPL], fpm[SPL];
+			uint32_t ph[SPL];
+			ld4(c, in.b, f);
+			if (in.c != NO_BUF) ld4(c, in.c, pm);
+			if (in.d != NO_BUF) ld4(c, in.d, fpm);
+			phasor_eval(c, op_ptr(c, in.op), f, in.c != NO_BUF ? pm : nullptr,
+					in.d != NO_BUF ? fpm : nullptr, n, ph);
+			*U4(c, in.a) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
 			__syncwarp();
-			break;
+			break; }
 		case I_PMA: {                                              /* generator.c:485-490 */
-			OpState *o = &c.ops[in.op];
-			LineState *ls = &o->line[LINE_PMA];
-			uint32_t of = o->flags;
-			bool run;
-			if (c.oc == 0) {
-				/* decided once per reference block (the reference tests it per 1024-block) */
-				run = (ls->v0 != 0.f) || (ls->flags & SAUABI_LINEP_GOAL);
-				of = run ? (of | ON_PMA_RUN) : (of & ~ON_PMA_RUN);
+			OpState *o = op_ptr(c, in.op);
+			const bool run = pma_decide(c, o);
+			if (run) {
+				float out[SPL];
+				line_eval(c, &o->line[LINE_PMA], nullptr, n, c.stk_rem[c.sp], out);
+				st4(c, in.a, out);
 			} else {
-				run = (of & ON_PMA_RUN) != 0;
+				line_skip(c, &o->line[LINE_PMA], n);
 			}
-			__syncwarp();
-			if (c.lane == 0) o->flags = (uint8_t) of;
-			if (run) line_run(c, ls, in.a, NO_BUF, n);
-			else line_skip(c, ls, n);
 			c.pma_flag = run;
 			__syncwarp();
 			break; }
 		case I_WOSC:
-			if (n) wosc_run(c, in, n);
+			if (n) {
+				OpState *o = op_ptr(c, in.op);
+				if ((in.flags & F_HAS_APMODS) || c.pma_flag) {
+					wosc_selfmod(c, o, reinterpret_cast<const uint32_t*>(c.bufs + in.b * CHUNK),
+							c.bufs + in.c * CHUNK, c.bufs + in.a * CHUNK, n);
+				} else {
+					const uint4 p4 = *U4(c, in.b);
+					const uint32_t ph[SPL] = {p4.x, p4.y, p4.z, p4.w};
+					float sv[SPL];
+					wosc_eval(c, o, ph, n, sv);
+					st4(c, in.a, sv);
+				}
+			}
 			__syncwarp();
 			break;
 		case I_CYCLOR:
@@ -793,27 +971,10 @@ __device__ uint32_t run_chunk(Ctx &c, const Instr *code, uint32_t code_len, uint
 			__syncwarp();
 			break;
 		case I_MIX: {                                              /* generator.c:384-440 */
-			const uint32_t layer = c.stk_layer[c.sp];
-			float4 iv = make_float4(1.f, 1.f, 1.f, 1.f);
-			if (in.b != NO_BUF) iv = *B4(c, in.b);
-			const float4 av = *B4(c, in.c);
-			float4 ov = *B4(c, in.a);
-			const float x[SPL] = {iv.x, iv.y, iv.z, iv.w};
-			const float a[SPL] = {av.x, av.y, av.z, av.w};
-			float o[SPL] = {ov.x, ov.y, ov.z, ov.w};
-#pragma unroll
-			for (int k = 0; k < SPL; ++k) {
-				if (i0 + k >= n) continue;
-				if (in.flags & F_WAVEENV) {
-					const float s_amp = a[k] * 0.5f;
-					const float s = (x[k] * s_amp) + fabsf(s_amp);
-					o[k] = layer ? o[k] * s : s;
-				} else {
-					const float v = x[k] * a[k];
-					o[k] = layer ? o[k] + v : v;
-				}
-			}
-			*B4(c, in.a) = make_float4(o[0], o[1], o[2], o[3]);
+			float x[SPL] = {1.f, 1.f, 1.f, 1.f}, a[SPL];
+			if (in.b != NO_BUF) ld4(c, in.b, x);
+			ld4(c, in.c, a);
+			mix_eval(c, in.a, x, a, n, c.stk_layer[c.sp], (in.flags & F_WAVEENV) != 0);
 			__syncwarp();
 			break; }
 		case I_VPAN: {                                             /* generator.c:756-762 */
@@ -821,11 +982,16 @@ __device__ uint32_t run_chunk(Ctx &c, const Instr *code, uint32_t code_len, uint
 			if (c.lane == 0) { c.stk_len[0] = c.last_len; c.stk_rem[0] = c.last_rem; }
 			__syncwarp();
 			if (c.last_len == 0) return 0;
-			LineState *ls = &c.ops[in.op].line[LINE_PAN];
+			LineState *ls = &op_ptr(c, in.op)->line[LINE_PAN];
 			const bool run = in.d || (ls->flags & SAUABI_LINEP_GOAL);
 			__syncwarp();
-			if (run) line_run(c, ls, in.a, NO_BUF, c.last_len);
-			else line_skip(c, ls, c.last_len);
+			if (run) {
+				float out[SPL];
+				line_eval(c, ls, nullptr, c.last_len, c.last_rem, out);
+				st4(c, in.a, out);
+			} else {
+				line_skip(c, ls, c.last_len);
+			}
 			c.pan_dyn = run;
 			__syncwarp();
 			break; }
@@ -835,15 +1001,15 @@ __device__ uint32_t run_chunk(Ctx &c, const Instr *code, uint32_t code_len, uint
 			const float4 sv = *B4(c, in.a);
 			float4 pv;
 			if (c.pan_dyn) pv = *B4(c, in.b);
-			else { const float p = c.ops[in.op].line[LINE_PAN].v0; pv = make_float4(p, p, p, p); }
+			else { const float p = op_ptr(c, in.op)->line[LINE_PAN].v0; pv = make_float4(p, p, p, p); }
 			float4 s, r;
 			s.x = sv.x * amp_scale; r.x = s.x * pv.x;
 			s.y = sv.y * amp_scale; r.y = s.y * pv.y;
 			s.z = sv.z * amp_scale; r.z = s.z * pv.z;
 			s.w = sv.w * amp_scale; r.w = s.w * pv.w;
 			if (i0 + 3 < vn && ((reinterpret_cast<uintptr_t>(row_s + i0) & 15) == 0)) {
-				*reinterpret_cast<float4*>(row_s + i0) = s;       /* coalesced 128-bit stores */
-				*reinterpret_cast<float4*>(row_r + i0) = r;
+				__stcs(reinterpret_cast<float4*>(row_s + i0), s);   /* coalesced 128-bit stores */
+				__stcs(reinterpret_cast<float4*>(row_r + i0), r);
 			} else {
 				if (i0 + 0 < vn) { row_s[i0 + 0] = s.x; row_r[i0 + 0] = r.x; }
 				if (i0 + 1 < vn) { row_s[i0 + 1] = s.y; row_r[i0 + 1] = r.y; }
@@ -861,6 +1027,28 @@ __device__ uint32_t run_chunk(Ctx &c, const Instr *code, uint32_t code_len, uint
 
 /* ---- render kernel ------------------------------------------------------ */
 
+constexpr uint32_t OP_WORDS = sizeof(OpState) / 4;
+static_assert(sizeof(OpState) % 16 == 0, "OpState is copied as 32-bit words");
+
+/* operator states of the current voice program: HBM <-> shared memory */
+__device__ void ops_load(Ctx &c, uint32_t cnt) {
+	uint32_t *dst = reinterpret_cast<uint32_t*>(c.sops);
+	for (uint32_t i = c.lane; i < cnt * OP_WORDS; i += 32) {
+		const uint32_t slot = i / OP_WORDS, w = i % OP_WORDS;
+		dst[i] = reinterpret_cast<const uint32_t*>(c.gops + c.prog_ops[slot])[w];
+	}
+	__syncwarp();
+}
+__device__ void ops_store(Ctx &c, uint32_t cnt) {
+	__syncwarp();
+	const uint32_t *src = reinterpret_cast<const uint32_t*>(c.sops);
+	for (uint32_t i = c.lane; i < cnt * OP_WORDS; i += 32) {
+		const uint32_t slot = i / OP_WORDS, w = i % OP_WORDS;
+		reinterpret_cast<uint32_t*>(c.gops + c.prog_ops[slot])[w] = src[i];
+	}
+	__syncwarp();
+}
+
 template <int MAXT, int MINB>
 __device__ __forceinline__ void render_body(const CallDesc *calls, uint32_t ncalls,
 		const SegDesc *segs, uint32_t ntasks, const float *tables, uint32_t wave_mask,
@@ -870,7 +1058,7 @@ __device__ __forceinline__ void render_body(const CallDesc *calls, uint32_t ncal
 	float *tab = reinterpret_cast<float*>(smem + 128);
 	const uint32_t nslots = __popc(wave_mask);
 	unsigned char *warp_area = smem + 128 + nslots * WAVE_LEN * sizeof(float);
-	const uint32_t per_warp = nbufs * CHUNK * sizeof(float) + 3 * MAX_NEST * sizeof(uint32_t);
+	const uint32_t per_warp = warp_smem_bytes(nbufs);
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
 	/* stage the wave tables this launch needs: TMA bulk copies, one mbarrier */
@@ -906,14 +1094,17 @@ __device__ __forceinline__ void render_body(const CallDesc *calls, uint32_t ncal
 	const uint32_t nlv = g->voice_end - g->voice_begin;
 
 	Ctx c;
-	c.bufs = reinterpret_cast<float*>(warp_area + warp * per_warp);
+	c.sops = reinterpret_cast<OpState*>(warp_area + warp * per_warp);
+	c.bufs = reinterpret_cast<float*>(c.sops + MAX_SLOTS);
 	c.stk_len = reinterpret_cast<uint32_t*>(c.bufs + nbufs * CHUNK);
 	c.stk_rem = c.stk_len + MAX_NEST;
 	c.stk_layer = c.stk_rem + MAX_NEST;
 	c.tab = tab;
 	c.wc = reinterpret_cast<const WaveCoeffs*>(tables + NUM_WAVES * WAVE_LEN);
 	c.g = g;
-	c.ops = g->ops;
+	c.gops = g->ops;
+	c.prog_ops = g->prog_ops;
+	c.cached = 0;
 	c.wave_mask = wave_mask;
 	c.lane = lane;
 
@@ -922,18 +1113,32 @@ __device__ __forceinline__ void render_body(const CallDesc *calls, uint32_t ncal
 	const uint32_t ev_lo = g->vev_off[v], ev_n = g->vev_off[v + 1] - ev_lo;
 	float *row_s = g->rows_s + (size_t) lv * g->row_len;
 	float *row_r = g->rows_r + (size_t) lv * g->row_len;
+	uint32_t loaded = 0;        // operator states currently held in shared memory
 
 	for (uint32_t si = 0; si < cd->nseg; ++si) {
 		const SegDesc sd = segs[cd->seg_off + si];
 		/* this voice's events due at the segment start, in order */
-		while (vs.ev_cursor < ev_n && g->vev_idx[ev_lo + vs.ev_cursor] < sd.ev_end) {
-			if (lane == 0) {
-				apply_event(g, c.wc, &g->events[g->vev_idx[ev_lo + vs.ev_cursor]], &vs);
-				vs.ev_cursor++;
-				*vsp = vs;
+		if (vs.ev_cursor < ev_n && g->vev_idx[ev_lo + vs.ev_cursor] < sd.ev_end) {
+			if (loaded) { ops_store(c, loaded); loaded = 0; c.cached = 0; }
+			while (vs.ev_cursor < ev_n && g->vev_idx[ev_lo + vs.ev_cursor] < sd.ev_end) {
+				if (lane == 0) {
+					apply_event(g, c.wc, &g->events[g->vev_idx[ev_lo + vs.ev_cursor]], &vs);
+					vs.ev_cursor++;
+					*vsp = vs;
+				}
+				__syncwarp();
+				vs = *vsp;
 			}
-			__syncwarp();
-			vs = *vsp;
+		}
+		if (vs.duration == 0 || sd.len == 0) {
+			if (lane == 0) g->vlen[(size_t) si * nlv + lv] = 0;
+			continue;
+		}
+		c.prog_ops = g->prog_ops + vs.ops_off;
+		if (!loaded && vs.ops_cnt > 0 && vs.ops_cnt <= (uint32_t) MAX_SLOTS) {
+			ops_load(c, vs.ops_cnt);
+			loaded = vs.ops_cnt;
+			c.cached = 1;
 		}
 		uint32_t run_total = 0;
 		for (uint32_t off = 0; off < sd.len && vs.duration != 0; off += CHUNK) {
@@ -945,7 +1150,7 @@ __device__ __forceinline__ void render_body(const CallDesc *calls, uint32_t ncal
 			if (sd.len - off < rem0) rem0 = sd.len - off;
 			if (REF_BLOCK - c.oc < rem0) rem0 = REF_BLOCK - c.oc;
 			uint32_t out_len = 0;
-			if (c.ops[vs.carr_op].time > 0)                        /* run_voice, :833-846 */
+			if (vs.code_len && op_ptr(c, vs.carr_slot)->time > 0)     /* run_voice, :833-846 */
 				out_len = run_chunk(c, g->code + vs.code_off, vs.code_len, time, rem0,
 						row_s + sd.start + off, row_r + sd.start + off);
 			__syncwarp();
@@ -957,6 +1162,7 @@ __device__ __forceinline__ void render_body(const CallDesc *calls, uint32_t ncal
 			if (run_total) atomicMax(&g->status[1 + si], run_total);
 		}
 	}
+	if (loaded) ops_store(c, loaded);
 	if (lane == 0) {
 		*vsp = vs;
 		if (vs.duration != 0) atomicOr(&g->status[0], 1u);
@@ -1070,8 +1276,7 @@ __global__ void planes_to_pcm_kernel(const float *mix, uint32_t plane_stride, ui
 size_t render_smem_bytes(uint32_t wave_mask, uint32_t nbufs, uint32_t warps) {
 	uint32_t nslots = 0;
 	for (uint32_t w = 0; w < NUM_WAVES; ++w) if (wave_mask & (1u << w)) ++nslots;
-	return 128 + (size_t) nslots * WAVE_LEN * sizeof(float) +
-		(size_t) warps * (nbufs * CHUNK * sizeof(float) + 3 * MAX_NEST * sizeof(uint32_t));
+	return 128 + (size_t) nslots * WAVE_LEN * sizeof(float) + (size_t) warps * warp_smem_bytes(nbufs);
 }
 
 cudaError_t launch_render(const CallDesc *d_calls, uint32_t ncalls, const SegDesc *d_segs,

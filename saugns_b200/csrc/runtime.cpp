@@ -94,6 +94,7 @@ static float *get_device_tables(int device, const saugen_WaveTables *t) {
 struct HostOp {
 	bool inited = false;
 	uint8_t type = 0;
+	bool line_set[LINE_COUNT] = {false, false, false, false, false, false};  /* ever given by an event */
 	const sauabi_ProgramIDArr *mods[SAUABI_POP_NAMED] = {0};   /* index = use type */
 };
 
@@ -117,7 +118,7 @@ struct saugen_Generator {
 	GenDesc *d_desc = nullptr;
 	float *d_tables = nullptr;
 	void *d_ops = nullptr, *d_voices = nullptr, *d_events = nullptr, *d_opdata = nullptr,
-	     *d_code = nullptr, *d_vev_off = nullptr, *d_vev_idx = nullptr;
+	     *d_code = nullptr, *d_prog_ops = nullptr, *d_vev_off = nullptr, *d_vev_idx = nullptr;
 	float *d_rows_s = nullptr, *d_rows_r = nullptr, *d_mix = nullptr;
 	uint32_t *d_vlen = nullptr, *d_status = nullptr;
 	int16_t *d_pcm = nullptr;
@@ -141,21 +142,39 @@ struct saugen_Generator {
 struct Compiler {
 	const std::vector<HostOp> &ops;
 	std::vector<Instr> out;
+	std::vector<uint32_t> prog_ops;       // slot -> operator id of the program being built
+	std::vector<int32_t> slot_of;         // operator id -> slot, -1 if not in the program
 	std::vector<char> onstack;
 	uint32_t max_buf = 0;
 	bool too_deep = false;
 	int depth = 0;
-	Compiler(const std::vector<HostOp> &o) : ops(o), onstack(o.size(), 0) {}
+	Compiler(const std::vector<HostOp> &o) : ops(o), slot_of(o.size(), -1), onstack(o.size(), 0) {}
 
-	void emit(uint8_t opc, uint32_t op, uint32_t a, uint32_t b = NO_BUF, uint32_t c = NO_BUF,
+	uint32_t slot(uint32_t op) {
+		if (slot_of[op] < 0) { slot_of[op] = (int32_t) prog_ops.size(); prog_ops.push_back(op); }
+		return (uint32_t) slot_of[op];
+	}
+	void use_buf(uint32_t x) {
+		if (x == NO_BUF) return;
+		if (x + 1 > max_buf) max_buf = x + 1;
+		if (max_buf >= 250) too_deep = true;
+	}
+	void emit(uint8_t opc, uint32_t op_slot, uint32_t a, uint32_t b = NO_BUF, uint32_t c = NO_BUF,
 			uint32_t d = NO_BUF, uint32_t e = NO_BUF, uint16_t flags = 0) {
 		Instr i;
 		i.opcode = opc; i.a = (uint8_t) a; i.b = (uint8_t) b; i.c = (uint8_t) c;
-		i.d = (uint8_t) d; i.e = (uint8_t) e; i.flags = flags; i.op = op; i.aux = 0;
-		const uint32_t bs[5] = {a, b, c, d, e};
-		for (uint32_t x : bs) if (x != NO_BUF && opc != I_LINE && x + 1 > max_buf) max_buf = x + 1;
-		if (opc == I_LINE) { if (a + 1 > max_buf) max_buf = a + 1; if (b != NO_BUF && b + 1 > max_buf) max_buf = b + 1; }
-		if (max_buf >= 250) too_deep = true;
+		i.d = (uint8_t) d; i.e = (uint8_t) e; i.flags = flags; i.op = op_slot; i.aux = 0;
+		switch (opc) {                     /* which fields name work buffers */
+		case I_LINE: if (d) use_buf(a); use_buf(b); break;
+		case I_VPAN: use_buf(a); break;
+		case I_WLEAF: use_buf(a); use_buf(e);
+			if (flags & F_MAY_SELFMOD) { use_buf(b); use_buf(b + 1); } break;
+		case I_WHEAD: use_buf(a); use_buf(b); use_buf(e); break;
+		case I_WTAIL: use_buf(a); use_buf(b); use_buf(c); use_buf(d);
+			if (flags & F_MAY_SELFMOD) use_buf(b + 1); break;
+		case I_END: break;
+		default: use_buf(a); use_buf(b); use_buf(c); use_buf(d); use_buf(e); break;
+		}
 		out.push_back(i);
 	}
 	static uint32_t cnt(const sauabi_ProgramIDArr *a) { return a ? a->count : 0; }
@@ -165,15 +184,16 @@ struct Compiler {
 			uint32_t mulbuf, uint32_t reused_freq, bool is_freq) {
 		const HostOp &n = ops[op];
 		const uint32_t freq = reused_freq != NO_BUF ? reused_freq : (is_freq ? B : NO_BUF);
-		emit(I_LINE, op, B, mulbuf, par, 1);
+		emit(I_LINE, slot(op), B, mulbuf, par, 1);
 		const sauabi_ProgramIDArr *rm = n.mods[rmods_use], *m = n.mods[mods_use];
 		if (cnt(rm) > 0) {
-			emit(I_LINE, op, B + 1, mulbuf, rpar, 1);
+			emit(I_LINE, slot(op), B + 1, mulbuf, rpar, 1);
 			for (uint32_t i = 0; i < rm->count; ++i)
 				visit(rm->ids[i], B + 2, freq, true, i > 0 ? F_LAYER : 0);
 			emit(I_RANGE, 0, B, B + 1, B + 2);
-		} else {
-			emit(I_LINE, op, 0, NO_BUF, rpar, 0);
+		} else if (n.line_set[rpar]) {
+			/* a never-set line has no state to advance: its sauLine_skip is a no-op */
+			emit(I_LINE, slot(op), 0, NO_BUF, rpar, 0);
 		}
 		for (uint32_t i = 0; i < cnt(m); ++i)
 			visit(m->ids[i], B, freq, false, F_LAYER);
@@ -189,40 +209,70 @@ struct Compiler {
 		if (++depth >= MAX_NEST - 1) { too_deep = true; --depth; return; }
 		onstack[op] = 1;
 		const HostOp &n = ops[op];
-		const size_t enter_at = out.size();
-		emit(I_ENTER, op, base, NO_BUF, NO_BUF, NO_BUF, NO_BUF, layer_flags);
+		const uint32_t sl = slot(op);
 		const uint16_t mixf = wave_env ? F_WAVEENV : 0;
+		if (n.type == SAUABI_POPT_wave) {
+			/* fused forms of run_block_wosc where the parameter lists allow */
+			const sauabi_ProgramIDArr *pl = n.mods[SAUABI_POP_pmod], *fl = n.mods[SAUABI_POP_fpmod],
+				*al = n.mods[SAUABI_POP_apmod];
+			const bool simple_freq = !cnt(n.mods[SAUABI_POP_fmod]) && !cnt(n.mods[SAUABI_POP_rfmod]);
+			const bool simple_amp = !cnt(n.mods[SAUABI_POP_amod]) && !cnt(n.mods[SAUABI_POP_ramod]) &&
+				!cnt(al);
+			const bool kids = cnt(pl) || cnt(fl);
+			const uint32_t phase = base + 1, freq = base + 2;
+			uint16_t wf = layer_flags | mixf;
+			if (n.line_set[LINE_FREQ2]) wf |= F_SKIP_FREQ2;
+			if (n.line_set[LINE_AMP2]) wf |= F_SKIP_AMP2;
+			if (n.line_set[LINE_PMA]) wf |= F_MAY_SELFMOD;
+			if (simple_freq && simple_amp && !kids) {
+				emit(I_WLEAF, sl, base, freq, NO_BUF, NO_BUF, parent_freq, wf);
+				onstack[op] = 0; --depth;
+				return;
+			}
+			const size_t enter_at = out.size();
+			if (simple_freq) {
+				emit(I_WHEAD, sl, base, freq, NO_BUF, NO_BUF, parent_freq, wf);
+			} else {
+				emit(I_ENTER, sl, base, NO_BUF, NO_BUF, NO_BUF, NO_BUF, layer_flags);
+				param(op, freq, LINE_FREQ, LINE_FREQ2, SAUABI_POP_fmod, SAUABI_POP_rfmod,
+						parent_freq, NO_BUF, true);
+			}
+			uint32_t pm = NO_BUF, fpm = NO_BUF;
+			for (uint32_t i = 0; i < cnt(pl); ++i) visit(pl->ids[i], base + 3, freq, false, i > 0 ? F_LAYER : 0);
+			if (cnt(pl)) pm = base + 3;
+			for (uint32_t i = 0; i < cnt(fl); ++i) visit(fl->ids[i], base + 4, freq, false, i > 0 ? F_LAYER : 0);
+			if (cnt(fl)) fpm = base + 4;
+			if (simple_amp) {
+				out[enter_at].aux = (uint32_t) out.size();
+				emit(I_WTAIL, sl, base, freq, pm, fpm, NO_BUF, wf);
+			} else {
+				emit(I_PHASOR, sl, phase, freq, pm, fpm);
+				param(op, base + 3, LINE_AMP, LINE_AMP2, SAUABI_POP_amod, SAUABI_POP_ramod,
+						NO_BUF, freq, false);
+				emit(I_PMA, sl, base + 5);
+				for (uint32_t i = 0; i < cnt(al); ++i)
+					visit(al->ids[i], base + 5, freq, false, i > 0 ? F_LAYER : F_LAYER_PMA);
+				emit(I_WOSC, sl, base + 4, phase, base + 5, NO_BUF, NO_BUF, cnt(al) ? F_HAS_APMODS : 0);
+				emit(I_MIX, 0, base, base + 4, base + 3, NO_BUF, NO_BUF, mixf);
+				out[enter_at].aux = (uint32_t) out.size();
+				emit(I_LEAVE, sl, base, NO_BUF, NO_BUF, NO_BUF, NO_BUF, layer_flags);
+			}
+			onstack[op] = 0; --depth;
+			return;
+		}
+		const size_t enter_at = out.size();
+		emit(I_ENTER, sl, base, NO_BUF, NO_BUF, NO_BUF, NO_BUF, layer_flags);
 		switch (n.type) {
 		case SAUABI_POPT_amp:
 		case SAUABI_POPT_noise: {
 			param(op, base + 1, LINE_AMP, LINE_AMP2, SAUABI_POP_amod, SAUABI_POP_ramod,
 					NO_BUF, NO_BUF, false);
 			if (n.type == SAUABI_POPT_noise) {
-				emit(I_NOISE, op, base + 2);
+				emit(I_NOISE, sl, base + 2);
 				emit(I_MIX, 0, base, base + 2, base + 1, NO_BUF, NO_BUF, mixf);
 			} else {
 				emit(I_MIX, 0, base, NO_BUF, base + 1, NO_BUF, NO_BUF, mixf);
 			}
-			break; }
-		case SAUABI_POPT_wave: {
-			const uint32_t phase = base + 1, freq = base + 2;
-			param(op, freq, LINE_FREQ, LINE_FREQ2, SAUABI_POP_fmod, SAUABI_POP_rfmod,
-					parent_freq, NO_BUF, true);
-			uint32_t pm = NO_BUF, fpm = NO_BUF;
-			const sauabi_ProgramIDArr *pl = n.mods[SAUABI_POP_pmod], *fl = n.mods[SAUABI_POP_fpmod],
-				*al = n.mods[SAUABI_POP_apmod];
-			for (uint32_t i = 0; i < cnt(pl); ++i) visit(pl->ids[i], base + 3, freq, false, i > 0 ? F_LAYER : 0);
-			if (cnt(pl)) pm = base + 3;
-			for (uint32_t i = 0; i < cnt(fl); ++i) visit(fl->ids[i], base + 4, freq, false, i > 0 ? F_LAYER : 0);
-			if (cnt(fl)) fpm = base + 4;
-			emit(I_PHASOR, op, phase, freq, pm, fpm);
-			param(op, base + 3, LINE_AMP, LINE_AMP2, SAUABI_POP_amod, SAUABI_POP_ramod,
-					NO_BUF, freq, false);
-			emit(I_PMA, op, base + 5);
-			for (uint32_t i = 0; i < cnt(al); ++i)
-				visit(al->ids[i], base + 5, freq, false, i > 0 ? F_LAYER : F_LAYER_PMA);
-			emit(I_WOSC, op, base + 4, phase, base + 5, NO_BUF, NO_BUF, cnt(al) ? F_HAS_APMODS : 0);
-			emit(I_MIX, 0, base, base + 4, base + 3, NO_BUF, NO_BUF, mixf);
 			break; }
 		case SAUABI_POPT_raseg: {
 			const uint32_t cycle = base + 1, rasg = base + 2, freq = base + 3;
@@ -235,18 +285,18 @@ struct Compiler {
 			if (cnt(pl)) pm = base + 4;
 			for (uint32_t i = 0; i < cnt(fl); ++i) visit(fl->ids[i], base + 5, freq, false, i > 0 ? F_LAYER : 0);
 			if (cnt(fl)) fpm = base + 5;
-			emit(I_CYCLOR, op, cycle, rasg, freq, pm, fpm);
+			emit(I_CYCLOR, sl, cycle, rasg, freq, pm, fpm);
 			param(op, base + 4, LINE_AMP, LINE_AMP2, SAUABI_POP_amod, SAUABI_POP_ramod,
 					NO_BUF, freq, false);
-			emit(I_PMA, op, base + 5);
+			emit(I_PMA, sl, base + 5);
 			for (uint32_t i = 0; i < cnt(al); ++i)
 				visit(al->ids[i], base + 5, freq, false, i > 0 ? F_LAYER : F_LAYER_PMA);
-			emit(I_RASG, op, rasg, cycle, base + 5, NO_BUF, NO_BUF, cnt(al) ? F_HAS_APMODS : 0);
+			emit(I_RASG, sl, rasg, cycle, base + 5, NO_BUF, NO_BUF, cnt(al) ? F_HAS_APMODS : 0);
 			emit(I_MIX, 0, base, rasg, base + 4, NO_BUF, NO_BUF, mixf);
 			break; }
 		}
 		out[enter_at].aux = (uint32_t) out.size();   /* index of the LEAVE */
-		emit(I_LEAVE, op, base, NO_BUF, NO_BUF, NO_BUF, NO_BUF, layer_flags);
+		emit(I_LEAVE, sl, base, NO_BUF, NO_BUF, NO_BUF, NO_BUF, layer_flags);
 		onstack[op] = 0;
 		--depth;
 	}
@@ -254,15 +304,18 @@ struct Compiler {
 	/* run_voice + mix_add, generator.c:749-788,833-846 */
 	void voice(uint32_t carr) {
 		out.clear();
+		for (uint32_t op : prog_ops) slot_of[op] = -1;
+		prog_ops.clear();
 		if (carr >= ops.size() || !ops[carr].inited) { emit(I_END, 0, 0); return; }
+		const uint32_t cs = slot(carr);   /* carrier is slot 0 */
 		visit(carr, 0, NO_BUF, false, 0);
 		const HostOp &n = ops[carr];
 		const uint32_t fb = n.type == SAUABI_POPT_wave ? 2 : n.type == SAUABI_POPT_raseg ? 3 : 0;
 		const sauabi_ProgramIDArr *cl = n.mods[SAUABI_POP_camod];
-		emit(I_VPAN, carr, 1 + fb, NO_BUF, NO_BUF, cnt(cl) ? 1 : 0);
+		emit(I_VPAN, cs, 1 + fb, NO_BUF, NO_BUF, cnt(cl) ? 1 : 0);
 		for (uint32_t i = 0; i < cnt(cl); ++i)
 			visit(cl->ids[i], 1 + fb, fb ? fb : NO_BUF, false, F_LAYER);
-		emit(I_VOUT, carr, 0, 1 + fb);
+		emit(I_VOUT, cs, 0, 1 + fb);
 		emit(I_END, 0, 0);
 	}
 };
@@ -308,6 +361,8 @@ extern "C" saugen_Generator *saugen_create(const sauabi_Program *prg, uint32_t s
 	std::vector<uint32_t> vev_off, vev_idx;
 	std::vector<uint32_t> vcarr(prg->vo_count, 0xffffffffu);
 	std::vector<std::pair<uint32_t, uint32_t>> vprog(prg->vo_count, {0u, 0u});
+	std::vector<std::pair<uint32_t, uint32_t>> vops(prg->vo_count, {0u, 0u});
+	std::vector<uint32_t> prog_ops;
 	if (!tables) tables = saugen::builtin_wave_tables();
 
 	o->prg = prg; o->srate = srate; o->device = opt->device;
@@ -372,6 +427,12 @@ extern "C" saugen_Generator *saugen_create(const sauabi_Program *prg, uint32_t s
 				if (od->id < hops.size()) {
 					HostOp &h = hops[od->id];
 					if (!h.inited) { h.inited = true; h.type = od->type; }
+					if (od->amp) h.line_set[LINE_AMP] = true;
+					if (od->amp2) h.line_set[LINE_AMP2] = true;
+					if (od->pan) h.line_set[LINE_PAN] = true;
+					if (od->freq) h.line_set[LINE_FREQ] = true;
+					if (od->freq2) h.line_set[LINE_FREQ2] = true;
+					if (od->pm_a) h.line_set[LINE_PMA] = true;
 					if (od->type >= SAUABI_POPT_wave) {            /* generator.c:316-320 */
 						if (od->fmods) h.mods[SAUABI_POP_fmod] = od->fmods;
 						if (od->rfmods) h.mods[SAUABI_POP_rfmod] = od->rfmods;
@@ -384,20 +445,27 @@ extern "C" saugen_Generator *saugen_create(const sauabi_Program *prg, uint32_t s
 					if (od->ramods) h.mods[SAUABI_POP_ramod] = od->ramods;
 				}
 			}
-			er.code_off = 0; er.code_len = 0;
+			er.code_off = 0; er.code_len = 0; er.ops_off = 0; er.ops_cnt = 0; er.carr_slot = 0;
 			if (pe->vo_id != SAUABI_PVO_NO_ID && pe->vo_id < prg->vo_count) {
 				vcarr[pe->vo_id] = pe->carr_op_id;
 				comp.voice(pe->carr_op_id);
 				/* reuse the voice's previous program when the walk is unchanged */
 				auto &pv = vprog[pe->vo_id];
+				auto &po = vops[pe->vo_id];
 				bool same = pv.second == comp.out.size() && pv.second > 0 &&
-					memcmp(&code[pv.first], comp.out.data(), pv.second * sizeof(Instr)) == 0;
+					memcmp(&code[pv.first], comp.out.data(), pv.second * sizeof(Instr)) == 0 &&
+					po.second == comp.prog_ops.size() && (po.second == 0 ||
+					memcmp(&prog_ops[po.first], comp.prog_ops.data(), po.second * sizeof(uint32_t)) == 0);
 				if (!same) {
 					pv.first = (uint32_t) code.size();
 					pv.second = (uint32_t) comp.out.size();
 					code.insert(code.end(), comp.out.begin(), comp.out.end());
+					po.first = (uint32_t) prog_ops.size();
+					po.second = (uint32_t) comp.prog_ops.size();
+					prog_ops.insert(prog_ops.end(), comp.prog_ops.begin(), comp.prog_ops.end());
 				}
 				er.code_off = pv.first; er.code_len = pv.second;
+				er.ops_off = po.first; er.ops_cnt = po.second; er.carr_slot = 0;
 				vev[pe->vo_id].push_back((uint32_t) ei);
 			}
 		}
@@ -432,6 +500,7 @@ extern "C" saugen_Generator *saugen_create(const sauabi_Program *prg, uint32_t s
 	CK(upload(&o->d_events, events));
 	CK(upload(&o->d_opdata, opdata));
 	CK(upload(&o->d_code, code));
+	CK(upload(&o->d_prog_ops, prog_ops));
 	CK(upload(&o->d_vev_off, vev_off));
 	CK(upload(&o->d_vev_idx, vev_idx));
 	{
@@ -457,6 +526,7 @@ extern "C" saugen_Generator *saugen_create(const sauabi_Program *prg, uint32_t s
 		d.ops = (OpState*) o->d_ops; d.voices = (VoiceState*) o->d_voices;
 		d.events = (const EventRec*) o->d_events; d.opdata = (const OpDataRec*) o->d_opdata;
 		d.code = (const Instr*) o->d_code;
+		d.prog_ops = (const uint32_t*) o->d_prog_ops;
 		d.vev_off = (const uint32_t*) o->d_vev_off; d.vev_idx = (const uint32_t*) o->d_vev_idx;
 		d.rows_s = o->d_rows_s; d.rows_r = o->d_rows_r;
 		d.vlen = o->d_vlen; d.status = o->d_status; d.vlen_cap = o->seg_cap;
@@ -480,7 +550,7 @@ extern "C" void saugen_destroy(saugen_Generator *o) {
 	if (!o) return;
 	cudaSetDevice(o->device);
 	if (o->stream) cudaStreamSynchronize(o->stream);
-	void *dev[] = {o->d_ops, o->d_voices, o->d_events, o->d_opdata, o->d_code, o->d_vev_off,
+	void *dev[] = {o->d_ops, o->d_voices, o->d_events, o->d_opdata, o->d_code, o->d_prog_ops, o->d_vev_off,
 		o->d_vev_idx, o->d_rows_s, o->d_rows_r, o->d_vlen, o->d_status, o->d_mix, o->d_pcm,
 		o->d_call, o->d_segs, o->d_desc};
 	for (void *p : dev) if (p) cudaFree(p);
