@@ -111,6 +111,10 @@ int saugen_counters(saugen_Generator *o, uint64_t out[4]);
  * switched on (CUDA events on the launch stream; for bench.py's roofline). */
 int saugen_set_timing(saugen_Generator *o, int on);
 int saugen_kernel_ms(saugen_Generator *o, double out[2]);
+/* Device arithmetic self-test: how many inputs a hand-expanded fast-path
+ * primitive (exact int-divisor division, 32-bit lrintf) gets differently from
+ * the plain statement it replaces, over all 2^32 divisors / float patterns. */
+long long saugen_selftest(int device, const saugen_WaveTables *tables);
 float saugen_amp_scale(saugen_Generator *o);
 const char *saugen_last_error(void);
 int saugen_device_count(void);

@@ -16,17 +16,20 @@ constexpr int REF_BLOCK = 1024;       // BUF_LEN, sau/generator.c:28
 constexpr int WAVE_LEN = 2048;        // sau/wave.h:18-19
 constexpr int NUM_WAVES = 12;
 constexpr int MAX_NEST = 24;          // len-stack depth per warp
-constexpr int MAX_SLOTS = 8;          // operator states cached in shared memory per voice
 constexpr uint32_t NO_BUF = 0xFF;
 
-/* sauLine run-time state (sau/line.h:115-121 minus time_ms). */
+/* sauLine run-time state (sau/line.h:115-121 minus time_ms), split so that the
+ * four words a fill needs come in with one 128-bit shared-memory load. */
 struct LineState {
 	float v0, vt;
 	uint32_t pos, end;
-	uint8_t type, flags;
-	uint8_t blk_done;   // position already wrapped inside the current REF_BLOCK (see line_run)
-	uint8_t _pad;
 };
+/* lmeta word of a line: type | flags << 8 | blk_done << 16.  blk_done = the
+ * position already wrapped inside the current REF_BLOCK (see line_eval). */
+#define LM_TYPE(m)  ((m) & 0xffu)
+#define LM_FLAGS(m) (((m) >> 8) & 0xffu)
+#define LM_BLK(m)   (((m) >> 16) & 1u)
+#define LM_PACK(type, flags, blk) (((type) & 0xffu) | (((flags) & 0xffu) << 8) | (((blk) & 1u) << 16))
 
 enum { LINE_AMP = 0, LINE_AMP2, LINE_PAN, LINE_FREQ, LINE_FREQ2, LINE_PMA, LINE_COUNT };
 
@@ -38,13 +41,18 @@ enum {
 };
 enum { OSC_RESET_DIFF = 1 << 0 };   // sau/generator/wosc.h:37-38
 
-struct OpState {
+/* 192 bytes, every hot group 16-byte aligned: line[i] at 16*i, the
+ * {time, type/flags/mode/oscflags, i0, i1} group at 144, {prev_Is, prev_s,
+ * fb_s} at 160. */
+struct __align__(16) OpState {
+	LineState line[LINE_COUNT];
+	uint32_t lmeta[LINE_COUNT];
+	float linv[LINE_COUNT];   // 1.f / (float) end, kept current by apply_event
 	uint32_t time;
 	uint8_t type;          // SAUABI_POPT_*
 	uint8_t flags;         // ON_*
 	uint8_t mode;          // W: wave, N: noise type, R: line type
 	uint8_t oscflags;      // W: OSC_RESET_DIFF, R: bit0 = rate2x
-	LineState line[LINE_COUNT];
 	/* W: phasor.phase / prev_phase; N: n / prev; R: cycle_phase lo / hi */
 	uint32_t i0, i1;
 	double prev_Is;
@@ -53,6 +61,7 @@ struct OpState {
 	uint16_t ras_flags;
 	uint8_t ras_func, ras_level;
 	uint32_t ras_alpha;
+	uint32_t _pad[2];
 };
 
 enum { VN_INIT = 1 << 0 };

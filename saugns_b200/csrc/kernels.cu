@@ -31,8 +31,8 @@ namespace saugen {
 #define FULL 0xffffffffu
 
 /* per-warp shared memory: operator-state cache, work buffers, len stack */
-__host__ __device__ inline uint32_t warp_smem_bytes(uint32_t nbufs) {
-	return MAX_SLOTS * (uint32_t) sizeof(OpState) + nbufs * CHUNK * (uint32_t) sizeof(float) +
+__host__ __device__ inline uint32_t warp_smem_bytes(uint32_t nbufs, uint32_t nslots) {
+	return nslots * (uint32_t) sizeof(OpState) + nbufs * CHUNK * (uint32_t) sizeof(float) +
 		3 * MAX_NEST * (uint32_t) sizeof(uint32_t);
 }
 
@@ -73,13 +73,13 @@ struct Ctx {
 	uint32_t *stk_len;         // shared: MAX_NEST entries each
 	uint32_t *stk_rem;
 	uint32_t *stk_layer;
-	OpState *sops;             // shared: this voice's operator states (cache)
+	OpState *sops;             // shared: this voice's operator states
 	const float *tab;          // shared: staged wave tables
 	const WaveCoeffs *wc;      // global
 	const GenDesc *g;          // global
 	OpState *gops;             // global operator states
 	const uint32_t *prog_ops;  // global: slot -> operator id of the current program
-	uint32_t cached;           // operator states live in shared memory
+	float coeff;               // g->coeff
 	uint32_t wave_mask;        // tables staged by this launch
 	uint32_t oc;               // chunk offset inside the reference's 1024-block
 	int lane;
@@ -90,7 +90,7 @@ struct Ctx {
 
 /* Instr::op is a slot of the voice program's operator list. */
 __device__ __forceinline__ OpState *op_ptr(const Ctx &c, uint32_t slot) {
-	return c.cached ? c.sops + slot : c.gops + c.prog_ops[slot];
+	return c.sops + slot;
 }
 __device__ __forceinline__ float4 *B4(const Ctx &c, uint32_t i) {
 	return reinterpret_cast<float4*>(c.bufs + i * CHUNK) + c.lane;
@@ -105,9 +105,25 @@ __device__ __forceinline__ void ld4(const Ctx &c, uint32_t buf, float v[SPL]) {
 __device__ __forceinline__ void st4(const Ctx &c, uint32_t buf, const float v[SPL]) {
 	*B4(c, buf) = make_float4(v[0], v[1], v[2], v[3]);
 }
-__device__ __forceinline__ const float *wave_lut(const Ctx &c, uint32_t wave) {
+/* Staged tables: slot stride TAB_STRIDE floats, table at +4 (16-byte aligned
+ * for the bulk copy), lut[-1] at +3 and lut[2048], lut[2049] after it, so the
+ * four Hermite taps of an index are consecutive without masking. */
+constexpr uint32_t TAB_STRIDE = WAVE_LEN + 8;
+/* What the out-of-line (rare path) functions need, passed by value. */
+struct ColdCtx {
+	const float *tab;
+	const WaveCoeffs *wc;
+	uint32_t wave_mask;
+	int lane;
+};
+__device__ __forceinline__ ColdCtx cold(const Ctx &c) {
+	ColdCtx k; k.tab = c.tab; k.wc = c.wc; k.wave_mask = c.wave_mask; k.lane = c.lane;
+	return k;
+}
+template <typename C>
+__device__ __forceinline__ const float *wave_lut(const C &c, uint32_t wave) {
 	uint32_t slot = __popc(c.wave_mask & ((1u << wave) - 1u));
-	return c.tab + slot * WAVE_LEN;
+	return c.tab + slot * TAB_STRIDE + 4;
 }
 __device__ __forceinline__ uint32_t scan_incl_u32(uint32_t v, int lane) {
 #pragma unroll
@@ -143,26 +159,44 @@ __device__ __forceinline__ void line_advance(uint32_t &pos, uint32_t end, uint32
 	}
 }
 
-/* sauLine_run(line, out, n, mulbuf) -- line.c:417-445 -- into registers.
+/* Line state in registers (every lane holds the same copy). */
+struct LineRegs {
+	float v0, vt, inv;
+	uint32_t pos, end, meta;
+};
+__device__ __forceinline__ LineRegs line_load(const OpState *o, int li) {
+	LineRegs r;
+	const float4 t = *reinterpret_cast<const float4*>(&o->line[li]);
+	r.v0 = t.x; r.vt = t.y; r.pos = __float_as_uint(t.z); r.end = __float_as_uint(t.w);
+	r.meta = o->lmeta[li];
+	r.inv = o->linv[li];
+	return r;
+}
+
+/* sauLine_run(line, out, n, mulbuf) -- line.c:417-445 -- any n, any state.
  * mulbuf: shared-memory buffer of ratio multipliers or nullptr; rem: samples
  * the visit still has in the reference's 1024-block (for gcc's cub tail).
  * Ends with the state write-back by lane 0; the caller syncs the warp. */
-__device__ void line_eval(const Ctx &c, LineState *ls, const float *mulbuf, uint32_t n,
-		uint32_t rem, float out[SPL]) {
+__device__ __noinline__ float4 line_eval_any(uint32_t oc, int lane, OpState *o, int li,
+		const float *mulbuf, uint32_t n, uint32_t rem) {
+	float out[SPL] = {0.f, 0.f, 0.f, 0.f};
+	LineState *ls = &o->line[li];
 	float v0 = ls->v0, vt = ls->vt;
-	uint32_t pos = ls->pos, end = ls->end, type = ls->type, flags = ls->flags;
+	uint32_t pos = ls->pos, end = ls->end;
+	const uint32_t meta = o->lmeta[li];
+	uint32_t type = LM_TYPE(meta), flags = LM_FLAGS(meta);
 	/* The reference advances a line once per 1024-block: when the position
 	 * reaches `end` (wrap, or goal reached) the rest of that block is not
 	 * counted (line.c:385-398,426-443).  blk_done carries that across our
 	 * 128-sample chunks so pos/flags stay bit-identical at any later event. */
-	uint32_t blk_done = c.oc == 0 ? 0u : ls->blk_done;
+	uint32_t blk_done = oc == 0 ? 0u : LM_BLK(meta);
 	const bool has_mul = (mulbuf != nullptr);
 	float m[SPL] = {1.f, 1.f, 1.f, 1.f};
 	if (has_mul) {
-		const float4 t = reinterpret_cast<const float4*>(mulbuf)[c.lane];
+		const float4 t = reinterpret_cast<const float4*>(mulbuf)[lane];
 		m[0] = t.x; m[1] = t.y; m[2] = t.z; m[3] = t.w;
 	}
-	const uint32_t i0 = c.lane * SPL;
+	const uint32_t i0 = lane * SPL;
 	if (!(flags & SAUABI_LINEP_GOAL)) {
 		if (!blk_done) {
 			bool ex;
@@ -196,7 +230,7 @@ __device__ void line_eval(const Ctx &c, LineState *ls, const float *mulbuf, uint
 			if (f.type == sau::L_cub) {
 				uint32_t F = end - pos;
 				if (F > rem) F = rem;
-				if (F <= (uint32_t) CHUNK && ((c.oc + F) & 1u)) tail_idx = F - 1;
+				if (F <= (uint32_t) CHUNK && ((oc + F) & 1u)) tail_idx = F - 1;
 			}
 #pragma unroll
 			for (int k = 0; k < SPL; ++k) {
@@ -218,16 +252,96 @@ __device__ void line_eval(const Ctx &c, LineState *ls, const float *mulbuf, uint
 		}
 	}
 	__syncwarp();   /* every lane has read the state before lane 0 rewrites it */
-	if (c.lane == 0) {
-		ls->v0 = v0; ls->pos = pos; ls->flags = (uint8_t) flags; ls->blk_done = (uint8_t) blk_done;
+	if (lane == 0) {
+		ls->v0 = v0; ls->pos = pos;
+		o->lmeta[li] = LM_PACK(type, flags, blk_done);
 	}
+	return make_float4(out[0], out[1], out[2], out[3]);
+}
+
+/* The common cases of the above on a FULL chunk (n == CHUNK), from registers:
+ * no goal (hold v0), or a goal whose trajectory covers the whole chunk with
+ * no ratio reconciliation due.  Returns false (nothing touched) otherwise.
+ * Lane 0 writes the state back; the caller has synced after line_load and
+ * syncs again before anything re-reads the state. */
+template <int TYPE>
+__device__ __forceinline__ void line_fill4(const sau::LineFill &f, uint32_t i0, float out[SPL]) {
+	sau::LineFill g = f;
+	g.type = TYPE;
+#pragma unroll
+	for (int k = 0; k < SPL; ++k) out[k] = sau::line_fill_at(g, i0 + k, false);
+}
+__device__ __forceinline__ bool line_eval_full(uint32_t oc, int lane, OpState *o, int li,
+		const LineRegs &r, const float *m /* SPL multipliers or nullptr */, float out[SPL]) {
+	const uint32_t type = LM_TYPE(r.meta);
+	uint32_t flags = LM_FLAGS(r.meta);
+	const uint32_t blk0 = LM_BLK(r.meta);
+	uint32_t blk = oc == 0 ? 0u : blk0;
+	if (!(flags & SAUABI_LINEP_GOAL)) {
+		uint32_t pos = r.pos;
+		if (!blk) {
+			bool ex;
+			line_advance(pos, r.end, flags, CHUNK, ex);
+			if (ex) blk = 1;
+		}
+		const bool um = m && (flags & SAUABI_LINEP_STATE_RATIO);
+#pragma unroll
+		for (int k = 0; k < SPL; ++k) out[k] = um ? r.v0 * m[k] : r.v0;
+		if (lane == 0) {
+			if (pos != r.pos) o->line[li].pos = pos;
+			const uint32_t meta = LM_PACK(type, flags, blk);
+			if (meta != r.meta) o->lmeta[li] = meta;
+		}
+		return true;
+	}
+	const bool gr = (flags & SAUABI_LINEP_GOAL_RATIO) != 0, sr = (flags & SAUABI_LINEP_STATE_RATIO) != 0;
+	if (gr != sr) return false;
+	if (!(r.pos < r.end && r.end - r.pos > (uint32_t) CHUNK)) return false;
+	/* line_fill_setup with the reciprocal kept in the state */
+	sau::LineFill f;
+	int t = (int) type;
+	if (t == sau::L_exp) t = (r.v0 > r.vt) ? sau::L_xpe : sau::L_lge;
+	else if (t == sau::L_log) t = (r.v0 < r.vt) ? sau::L_xpe : sau::L_lge;
+	f.type = t;
+	f.v0 = r.v0; f.vt = r.vt; f.pos = r.pos;
+	f.adj_pos = (int32_t) (r.pos - (r.end / 2));
+	f.inv = r.inv;
+	f.vm = (r.v0 + r.vt) * 0.5f;
+	f.vd = r.vt - r.v0;
+	f.c = 0.f;
+	const uint32_t i0 = lane * SPL;
+	switch (t) {
+	default:
+	case sau::L_sah: line_fill4<sau::L_sah>(f, i0, out); break;
+	case sau::L_lin: f.c = f.vd * f.inv; line_fill4<sau::L_lin>(f, i0, out); break;
+	case sau::L_cos: line_fill4<sau::L_cos>(f, i0, out); break;
+	case sau::L_xpe: f.c = r.v0 - r.vt; line_fill4<sau::L_xpe>(f, i0, out); break;
+	case sau::L_lge: line_fill4<sau::L_lge>(f, i0, out); break;
+	case sau::L_sqe: f.c = r.v0 - r.vt; line_fill4<sau::L_sqe>(f, i0, out); break;
+	case sau::L_cub: f.inv = -2.f * f.inv; f.c = (r.v0 - r.vt) * 0.5f; line_fill4<sau::L_cub>(f, i0, out); break;
+	case sau::L_smo: line_fill4<sau::L_smo>(f, i0, out); break;
+	case sau::L_uwh: f.c = f.vd * (0.5f / 2147483648.f); line_fill4<sau::L_uwh>(f, i0, out); break;
+	case sau::L_ncl: line_fill4<sau::L_ncl>(f, i0, out); break;
+	case sau::L_nhl: line_fill4<sau::L_nhl>(f, i0, out); break;
+	}
+	if (m && gr) {
+#pragma unroll
+		for (int k = 0; k < SPL; ++k) out[k] = out[k] * m[k];
+	}
+	if (lane == 0) {
+		o->line[li].pos = r.pos + CHUNK;
+		if (blk != blk0) o->lmeta[li] = LM_PACK(type, flags, blk);
+	}
+	return true;
 }
 
 /* sauLine_skip -- line.c:456-473 */
-__device__ void line_skip(const Ctx &c, LineState *ls, uint32_t n) {
-	if (c.lane != 0) return;
-	uint32_t pos = ls->pos, end = ls->end, flags = ls->flags;
-	uint32_t blk_done = c.oc == 0 ? 0u : ls->blk_done;
+__device__ __noinline__ void line_skip(uint32_t oc, int lane, OpState *o, int li, uint32_t n) {
+	if (lane != 0) return;
+	LineState *ls = &o->line[li];
+	const uint32_t meta = o->lmeta[li];
+	uint32_t pos = ls->pos, end = ls->end, flags = LM_FLAGS(meta);
+	uint32_t blk_done = oc == 0 ? 0u : LM_BLK(meta);
 	if (!blk_done) {
 		bool ex;
 		line_advance(pos, end, flags, n, ex);
@@ -241,41 +355,59 @@ __device__ void line_skip(const Ctx &c, LineState *ls, uint32_t n) {
 			}
 		}
 	}
-	ls->pos = pos; ls->flags = (uint8_t) flags; ls->blk_done = (uint8_t) blk_done;
+	ls->pos = pos;
+	o->lmeta[li] = LM_PACK(LM_TYPE(meta), flags, blk_done);
 }
 
 /* ---- sauPhasor_fill (wosc.h:135-169): scan over rounded increments ------ */
 
-__device__ void phasor_eval(const Ctx &c, OpState *o, const float f[SPL], const float *pm,
-		const float *fpm, uint32_t n, uint32_t ph[SPL]) {
-	const float coeff = c.g->coeff;
-	const uint32_t phase0 = o->i0;
+/* low 32 bits of sau_ftoi(x) (generator.c:16-17): F2I.S64 saturates where
+ * x86 returns INT64_MIN; only the positive overflow differs in the low word */
+__device__ __forceinline__ uint32_t ftoi_lo32(float x) {
+	const uint32_t r = (uint32_t) __float2ll_rn(x);
+	return (x >= 9223372036854775808.f) ? 0u : r;
+}
+
+template <bool FULLC>
+__device__ __forceinline__ void phasor_eval(const Ctx &c, OpState *o, uint32_t phase0,
+		const float f[SPL], const float *pm, const float *fpm, uint32_t n, uint32_t ph[SPL]) {
+	const float coeff = c.coeff;
 	const uint32_t i0 = c.lane * SPL;
 	uint32_t p[SPL], ofs[SPL];
 	uint32_t run = 0;
 #pragma unroll
 	for (int k = 0; k < SPL; ++k) {
-		uint32_t inc = (i0 + k < n) ? (uint32_t) sau::ftoi64(coeff * f[k]) : 0u;
+		uint32_t inc = ftoi_lo32(coeff * f[k]);
+		if (!FULLC && !(i0 + k < n)) inc = 0u;
 		run += inc;
 		p[k] = run;
-		int64_t of = 0;
-		if (pm && fpm) of = sau::pofs_pm_fpm(pm[k], fpm[k], f[k], 2147483648.f);
-		else if (pm) of = sau::pofs_pm(pm[k], 2147483648.f);
-		else if (fpm) of = sau::pofs_fpm(fpm[k], f[k], 2147483648.f);
-		ofs[k] = (uint32_t) of;
+	}
+	if (pm && fpm) {
+#pragma unroll
+		for (int k = 0; k < SPL; ++k)
+			ofs[k] = ftoi_lo32((((fpm[k] * f[k]) * SAU_FPM_SCALE) + pm[k]) * 2147483648.f);
+	} else if (pm) {
+#pragma unroll
+		for (int k = 0; k < SPL; ++k) ofs[k] = ftoi_lo32(pm[k] * 2147483648.f);
+	} else if (fpm) {
+#pragma unroll
+		for (int k = 0; k < SPL; ++k)
+			ofs[k] = ftoi_lo32((fpm[k] * f[k]) * (SAU_FPM_SCALE * 2147483648.f));
+	} else {
+#pragma unroll
+		for (int k = 0; k < SPL; ++k) ofs[k] = 0u;
 	}
 	const uint32_t incl = scan_incl_u32(run, c.lane);
 	const uint32_t base = phase0 + (incl - run);
 #pragma unroll
 	for (int k = 0; k < SPL; ++k) ph[k] = base + p[k] + ofs[k];
-	const uint32_t total = __shfl_sync(FULL, incl, 31);
-	if (c.lane == 0) o->i0 = phase0 + total;
+	if (c.lane == 31) o->i0 = phase0 + incl;
 }
 
 /* ---- sauWOsc_run / sauWOsc_run_selfmod (wosc.h:215-310) ----------------- */
 
 /* Differentiation (re)start, wosc.h:215-230; ph0 = phase of the chunk's sample 0. */
-__device__ __forceinline__ void wosc_reset(const Ctx &c, const float *lut, uint32_t wave,
+__device__ __forceinline__ void wosc_reset(const ColdCtx &c, const float *lut, uint32_t wave,
 		uint32_t ph0, uint32_t &prev_phase, double &prev_Is, float &prev_s) {
 	double poly, c0;
 	sau::herp(lut, ph0 - sau::WAVE_SLEN, &poly, &c0);
@@ -286,9 +418,37 @@ __device__ __forceinline__ void wosc_reset(const Ctx &c, const float *lut, uint3
 	prev_phase = ph0;
 }
 
-/* Parallel form: sample i needs phase[i], phase[i-1] only. */
-__device__ void wosc_eval(const Ctx &c, OpState *o, const uint32_t ph[SPL], uint32_t n,
-		float s[SPL]) {
+/* sauWave_get_herp (wave.h:127-141) on a staged table whose neighbours wrap:
+ * taps[0..3] = lut[ind-1 .. ind+2] without index masking. */
+__device__ __forceinline__ double herp_taps(const float *taps_base, uint32_t phase) {
+	const float *t = taps_base + (phase >> sau::WAVE_SLENBITS);
+	const float s0 = t[0], s1 = t[1], s2 = t[2], s3 = t[3];
+	return sau::herp_poly(s0, s1, s2, s3, phase) + (double) s1;
+}
+
+/* diff_scale / (float) phase_diff, IEEE round-to-nearest: the instruction
+ * sequence of div.rn.f32 without its operand-range check -- the divisor is a
+ * non-zero int32 and the dividend amp_scale * 2^29, far from any exponent
+ * limit (checked over the whole divisor range by saugen_selftest). */
+__device__ __forceinline__ float div_scale_by_int(float a, int32_t d) {
+	const float b = (float) d;
+	float r;
+	asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(b));
+	const float e = __fmaf_rn(-b, r, 1.f);
+	r = __fmaf_rn(r, e, r);
+	float q = __fmaf_rn(a, r, 0.f);
+	float rem = __fmaf_rn(-b, q, a);
+	q = __fmaf_rn(r, rem, q);
+	rem = __fmaf_rn(-b, q, a);
+	return __fmaf_rn(r, rem, q);
+}
+
+/* Parallel form: sample i needs phase[i], phase[i-1] only.
+ * Any n; handles zero phase differences and the differentiator restart. */
+__device__ __noinline__ float4 wosc_eval_any(const ColdCtx c, OpState *o, const uint4 ph4,
+		uint32_t n) {
+	const uint32_t ph[SPL] = {ph4.x, ph4.y, ph4.z, ph4.w};
+	float s[SPL];
 	const uint32_t wave = o->mode;
 	const float *lut = wave_lut(c, wave);
 	const float ds = c.wc->diff_scale[wave], doff = c.wc->diff_offset[wave];
@@ -352,16 +512,52 @@ __device__ void wosc_eval(const Ctx &c, OpState *o, const uint32_t ph[SPL], uint
 	e_ph = __shfl_sync(FULL, e_ph, src_lane);
 	e_Is = __shfl_sync(FULL, e_Is, src_lane);
 	e_s = __shfl_sync(FULL, e_s, src_lane);
+	__syncwarp();
 	if (c.lane == 0) {
 		o->i1 = e_ph; o->prev_Is = e_Is; o->prev_s = e_s;
 		o->oscflags = (uint8_t) oscflags;
 	}
+	return make_float4(s[0], s[1], s[2], s[3]);
+}
+
+/* FULL chunk, no restart pending, carried state in registers.  Returns false
+ * (nothing written) when some phase difference is zero: the caller then runs
+ * wosc_eval_any on the same phases. */
+__device__ __forceinline__ bool wosc_eval_full(const Ctx &c, OpState *o, uint32_t wave,
+		uint32_t prev_phase, double prev_Is, const uint32_t ph[SPL], float s[SPL]) {
+	const float *taps = wave_lut(c, wave) - 1;
+	const float ds = c.wc->diff_scale[wave];
+	const double doff = (double) c.wc->diff_offset[wave];
+	double Is[SPL];
+#pragma unroll
+	for (int k = 0; k < SPL; ++k) Is[k] = herp_taps(taps, ph[k]);
+	uint32_t pph = __shfl_up_sync(FULL, ph[SPL - 1], 1);
+	double pIs = __shfl_up_sync(FULL, Is[SPL - 1], 1);
+	if (c.lane == 0) { pph = prev_phase; pIs = prev_Is; }
+	int32_t d[SPL];
+	d[0] = (int32_t) (ph[0] - pph);
+#pragma unroll
+	for (int k = 1; k < SPL; ++k) d[k] = (int32_t) (ph[k] - ph[k - 1]);
+	bool z = false;
+#pragma unroll
+	for (int k = 0; k < SPL; ++k) z |= (d[k] == 0);
+	if (__any_sync(FULL, z)) return false;
+#pragma unroll
+	for (int k = 0; k < SPL; ++k) {                               /* wosc.h:254-256 */
+		const float xq = div_scale_by_int(ds, d[k]);
+		const double dI = Is[k] - (k ? Is[k - 1] : pIs);
+		s[k] = (float) (dI * (double) xq + doff);
+	}
+	if (c.lane == 31) {
+		o->i1 = ph[SPL - 1]; o->prev_Is = Is[SPL - 1]; o->prev_s = s[SPL - 1];
+	}
+	return true;
 }
 
 /* Self-PM: a non-linear recurrence through fb_s, truly serial (wosc.h:273-310).
  * One lane runs it with the state in registers; phases and pm_a amounts come
  * from shared memory, the output replaces the pm_a buffer in place if dst==pma. */
-__device__ void wosc_selfmod(const Ctx &c, OpState *o, const uint32_t *phase_buf,
+__device__ __noinline__ void wosc_selfmod(const ColdCtx c, OpState *o, const uint32_t *phase_buf,
 		const float *pma, float *dst, uint32_t n) {
 	__syncwarp();
 	if (c.lane == 0) {
@@ -404,7 +600,7 @@ __device__ __forceinline__ bool pma_decide(const Ctx &c, OpState *o) {
 	uint32_t of = o->flags;
 	bool run;
 	if (c.oc == 0) {
-		run = (ls->v0 != 0.f) || (ls->flags & SAUABI_LINEP_GOAL);
+		run = (ls->v0 != 0.f) || (LM_FLAGS(o->lmeta[LINE_PMA]) & SAUABI_LINEP_GOAL);
 		of = run ? (of | ON_PMA_RUN) : (of & ~ON_PMA_RUN);
 	} else {
 		run = (of & ON_PMA_RUN) != 0;
@@ -415,19 +611,24 @@ __device__ __forceinline__ bool pma_decide(const Ctx &c, OpState *o) {
 }
 
 /* block_mix_add / block_mix_mul_waveenv, generator.c:384-440, on registers */
+template <bool FULLC>
 __device__ __forceinline__ void mix_eval(const Ctx &c, uint32_t out_buf, const float x[SPL],
 		const float a[SPL], uint32_t n, uint32_t layer, bool waveenv) {
 	const uint32_t i0 = c.lane * SPL;
 	float o[SPL];
-	ld4(c, out_buf, o);
+	if (!FULLC || layer) ld4(c, out_buf, o);
+	if (waveenv) {
 #pragma unroll
-	for (int k = 0; k < SPL; ++k) {
-		if (i0 + k >= n) continue;
-		if (waveenv) {
+		for (int k = 0; k < SPL; ++k) {
+			if (!FULLC && i0 + k >= n) continue;
 			const float s_amp = a[k] * 0.5f;
 			const float s = (x[k] * s_amp) + fabsf(s_amp);
 			o[k] = layer ? o[k] * s : s;
-		} else {
+		}
+	} else {
+#pragma unroll
+		for (int k = 0; k < SPL; ++k) {
+			if (!FULLC && i0 + k >= n) continue;
 			const float v = x[k] * a[k];
 			o[k] = layer ? o[k] + v : v;
 		}
@@ -457,72 +658,116 @@ __device__ __forceinline__ void leave_eval(const Ctx &c, OpState *o, uint32_t ou
  * HEAD = run_block entry + frequency line (no FM lists); children (PM / fPM
  * modulators) run between HEAD and TAIL; TAIL = phase fill + amplitude line
  * (no AM lists, no self-PM modulators) + oscillator + block_mix + run_block
- * exit.  A leaf operator does both in one pass with everything in registers. */
+ * exit.  A leaf operator does both in one pass with everything in registers.
+ * A full chunk in a steady state (the common case) runs from registers with
+ * one warp sync after the state loads and one at the end; everything else
+ * goes through the *_any forms. */
 template <bool HEAD, bool TAIL>
-__device__ void wop(Ctx &c, const Instr &in, uint32_t &pc) {
+__device__ __forceinline__ void wop(Ctx &c, const Instr &in, uint32_t &pc) {
 	OpState *o = op_ptr(c, in.op);
+	/* every piece of operator state this instruction needs, then ONE warp sync:
+	 * all lanes hold their copy before lane 0 / lane 31 start writing back */
+	const uint4 og = *reinterpret_cast<const uint4*>(&o->time);   /* time, type|flags|mode|oscflags, i0, i1 */
+	const uint32_t otime = og.x, oflags = (og.y >> 8) & 0xffu, wave = (og.y >> 16) & 0xffu;
+	const uint32_t oscflags = og.y >> 24;
+	LineRegs rf, ra;
+	float4 pg;
+	if (HEAD) rf = line_load(o, LINE_FREQ);
+	if (TAIL) {
+		ra = line_load(o, LINE_AMP);
+		pg = *reinterpret_cast<const float4*>(&o->prev_Is);         /* prev_Is, prev_s, fb_s */
+	}
+	__syncwarp();
 	uint32_t len, rem, layer, plen;
 	float fr[SPL];
 	if (HEAD) {                                                    /* generator.c:675-698 */
 		plen = c.stk_len[c.sp];
-		const uint32_t flags = o->flags, t = o->time;
 		rem = c.stk_rem[c.sp];
-		if (!(flags & ON_TIME_INF) && t < rem) rem = t;
+		if (!(oflags & ON_TIME_INF) && otime < rem) rem = otime;
 		len = rem < plen ? rem : plen;
 		layer = (in.flags & F_LAYER) ? 1u :
 			((in.flags & F_LAYER_PMA) ? (c.pma_flag ? 1u : 0u) : 0u);
 		if (!TAIL) {
 			++c.sp;
-			if (c.lane == 0) { c.stk_len[c.sp] = len; c.stk_rem[c.sp] = rem; c.stk_layer[c.sp] = layer; }
-			__syncwarp();
+			c.stk_len[c.sp] = len; c.stk_rem[c.sp] = rem; c.stk_layer[c.sp] = layer;
 			if (len == 0) { pc = in.aux; return; }
 		}
 		if (len > 0) {
-			line_eval(c, &o->line[LINE_FREQ], in.e != NO_BUF ? c.bufs + in.e * CHUNK : nullptr,
-					len, rem, fr);
-			if (in.flags & F_SKIP_FREQ2) line_skip(c, &o->line[LINE_FREQ2], len);
+			const bool has_mul = in.e != NO_BUF;
+			float m[SPL];
+			if (has_mul) ld4(c, in.e, m);
+			if (!(len == (uint32_t) CHUNK &&
+					line_eval_full(c.oc, c.lane, o, LINE_FREQ, rf, has_mul ? m : nullptr, fr))) {
+				const float4 t = line_eval_any(c.oc, c.lane, o, LINE_FREQ,
+						has_mul ? c.bufs + in.e * CHUNK : nullptr, len, rem);
+				fr[0] = t.x; fr[1] = t.y; fr[2] = t.z; fr[3] = t.w;
+			}
+			if (in.flags & F_SKIP_FREQ2) line_skip(c.oc, c.lane, o, LINE_FREQ2, len);
 			if (!TAIL) st4(c, in.b, fr);
-			__syncwarp();
 		}
-		if (!TAIL) return;
+		if (!TAIL) { __syncwarp(); return; }
 	} else {
 		len = c.stk_len[c.sp]; rem = c.stk_rem[c.sp]; layer = c.stk_layer[c.sp];
 		plen = c.stk_len[c.sp - 1];
 		if (len > 0) ld4(c, in.b, fr);
 	}
 	if (len > 0) {
+		const bool full = len == (uint32_t) CHUNK;
 		float pm[SPL], fpm[SPL];
 		if (in.c != NO_BUF) ld4(c, in.c, pm);
 		if (in.d != NO_BUF) ld4(c, in.d, fpm);
+		const double prev_Is = __hiloint2double(__float_as_int(pg.y), __float_as_int(pg.x));
 		uint32_t ph[SPL];
-		phasor_eval(c, o, fr, in.c != NO_BUF ? pm : nullptr, in.d != NO_BUF ? fpm : nullptr,
-				len, ph);
+		if (full)
+			phasor_eval<true>(c, o, og.z, fr, in.c != NO_BUF ? pm : nullptr,
+					in.d != NO_BUF ? fpm : nullptr, len, ph);
+		else
+			phasor_eval<false>(c, o, og.z, fr, in.c != NO_BUF ? pm : nullptr,
+					in.d != NO_BUF ? fpm : nullptr, len, ph);
 		float am[SPL];
-		line_eval(c, &o->line[LINE_AMP], nullptr, len, rem, am);
-		if (in.flags & F_SKIP_AMP2) line_skip(c, &o->line[LINE_AMP2], len);
-		__syncwarp();
+		if (!(full && line_eval_full(c.oc, c.lane, o, LINE_AMP, ra, nullptr, am))) {
+			const float4 t = line_eval_any(c.oc, c.lane, o, LINE_AMP, nullptr, len, rem);
+			am[0] = t.x; am[1] = t.y; am[2] = t.z; am[3] = t.w;
+		}
+		if (in.flags & F_SKIP_AMP2) line_skip(c.oc, c.lane, o, LINE_AMP2, len);
 		bool selfmod = false;
-		if (in.flags & F_MAY_SELFMOD) selfmod = pma_decide(c, o);
+		if (in.flags & F_MAY_SELFMOD) { __syncwarp(); selfmod = pma_decide(c, o); }
 		float s[SPL];
 		if (!selfmod) {
-			if (in.flags & F_MAY_SELFMOD) line_skip(c, &o->line[LINE_PMA], len);
-			wosc_eval(c, o, ph, len, s);
+			if (in.flags & F_MAY_SELFMOD) line_skip(c.oc, c.lane, o, LINE_PMA, len);
+			bool done = false;
+			if (full && !(oscflags & OSC_RESET_DIFF))
+				done = wosc_eval_full(c, o, wave, og.w, prev_Is, ph, s);
+			if (!done) {
+				const float4 t = wosc_eval_any(cold(c), o, make_uint4(ph[0], ph[1], ph[2], ph[3]), len);
+				s[0] = t.x; s[1] = t.y; s[2] = t.z; s[3] = t.w;
+			}
 		} else {
 			/* scratch: phases over the (consumed) freq buffer, pm_a amounts and
 			 * then the output over the buffer after it */
-			float pa[SPL];
-			line_eval(c, &o->line[LINE_PMA], nullptr, len, rem, pa);
+			const float4 pa = line_eval_any(c.oc, c.lane, o, LINE_PMA, nullptr, len, rem);
 			*U4(c, in.b) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-			st4(c, in.b + 1u, pa);
-			wosc_selfmod(c, o, reinterpret_cast<const uint32_t*>(c.bufs + in.b * CHUNK),
+			*B4(c, in.b + 1u) = pa;
+			wosc_selfmod(cold(c), o, reinterpret_cast<const uint32_t*>(c.bufs + in.b * CHUNK),
 					c.bufs + (in.b + 1u) * CHUNK, c.bufs + (in.b + 1u) * CHUNK, len);
 			ld4(c, in.b + 1u, s);
 		}
 		c.pma_flag = selfmod;
-		__syncwarp();
-		mix_eval(c, in.a, s, am, len, layer, (in.flags & F_WAVEENV) != 0);
+		if (full) mix_eval<true>(c, in.a, s, am, len, layer, (in.flags & F_WAVEENV) != 0);
+		else mix_eval<false>(c, in.a, s, am, len, layer, (in.flags & F_WAVEENV) != 0);
 	}
-	leave_eval(c, o, in.a, len, plen, layer);
+	if (!(oflags & ON_TIME_INF)) {                                 /* generator.c:716-728 */
+		if (!layer && len < plen) {
+			const uint32_t i0 = c.lane * SPL;
+			float4 v = *B4(c, in.a);
+			if (i0 + 0 >= len) v.x = 0.f;
+			if (i0 + 1 >= len) v.y = 0.f;
+			if (i0 + 2 >= len) v.z = 0.f;
+			if (i0 + 3 >= len) v.w = 0.f;
+			*B4(c, in.a) = v;
+		}
+		if (c.lane == 0) o->time = otime - len;
+	}
 	c.last_len = len; c.last_rem = rem;
 	if (!HEAD) --c.sp;
 	__syncwarp();
@@ -532,7 +777,7 @@ __device__ void wop(Ctx &c, const Instr &in, uint32_t &pc) {
 
 __device__ void cyclor_fill(Ctx &c, const Instr &in, uint32_t n) {
 	OpState *o = op_ptr(c, in.op);
-	float coeff = c.g->coeff, ps = 2147483648.f;
+	float coeff = c.coeff, ps = 2147483648.f;
 	if (o->oscflags & 1) { coeff *= 2; ps *= 2; }
 	const uint64_t cp0 = ((uint64_t) o->i1 << 32) | o->i0;
 	const float4 f4 = *B4(c, in.c);
@@ -701,9 +946,11 @@ __device__ void noise_run(Ctx &c, const Instr &in, uint32_t n) {
 
 /* ---- event application (generator.c:233-377, line.c:287-332) ------------ */
 
-__device__ void dev_line_copy(LineState *o, const LineDelta *src) {
+__device__ void dev_line_copy(OpState *n, int li, const LineDelta *src) {
 	if (!src->present) return;
-	uint32_t mask = 0, flags = o->flags;
+	LineState *o = &n->line[li];
+	const uint32_t meta = n->lmeta[li];
+	uint32_t mask = 0, flags = LM_FLAGS(meta), type = LM_TYPE(meta);
 	const uint32_t sf = src->flags;
 	if (sf & SAUABI_LINEP_STATE) {
 		o->v0 = src->v0;
@@ -714,7 +961,7 @@ __device__ void dev_line_copy(LineState *o, const LineDelta *src) {
 			if (flags & SAUABI_LINEP_GOAL_RATIO) flags |= SAUABI_LINEP_STATE_RATIO;
 			else flags &= ~SAUABI_LINEP_STATE_RATIO;
 			if (o->pos < o->end) {
-				sau::LineFill f = sau::line_fill_setup(o->type, o->v0, o->vt, o->pos, o->end);
+				sau::LineFill f = sau::line_fill_setup((int) type, o->v0, o->vt, o->pos, o->end);
 				o->v0 = sau::line_fill_at(f, 0, true);   /* 1-element fill = gcc's tail */
 			}
 		}
@@ -726,7 +973,7 @@ __device__ void dev_line_copy(LineState *o, const LineDelta *src) {
 		mask |= SAUABI_LINEP_GOAL | SAUABI_LINEP_GOAL_RATIO;
 	}
 	if (sf & SAUABI_LINEP_TYPE) {
-		o->type = src->type;
+		type = src->type;
 		mask |= SAUABI_LINEP_TYPE;
 	}
 	if (!(flags & SAUABI_LINEP_TIME) || !(sf & SAUABI_LINEP_TIME_IF_NEW)) {
@@ -737,7 +984,8 @@ __device__ void dev_line_copy(LineState *o, const LineDelta *src) {
 	}
 	flags &= ~mask;
 	flags |= (sf & mask);
-	o->flags = (uint8_t) flags;
+	n->lmeta[li] = LM_PACK(type, flags, LM_BLK(meta));
+	n->linv[li] = 1.f / sau::u2f(o->end);       /* line_fill_setup's reciprocal, kept current */
 }
 
 /* R oscillator setters, rasg.h:59-119 */
@@ -758,7 +1006,7 @@ __device__ void ras_set_phase(OpState *o, uint32_t phase) {
 	ras_store(o, ((uint64_t) cycle) << 32 | p64);
 }
 
-__device__ void apply_event(const GenDesc *g, const WaveCoeffs *wc, const EventRec *ev,
+__device__ __noinline__ void apply_event(const GenDesc *g, const WaveCoeffs *wc, const EventRec *ev,
 		VoiceState *vs) {
 	for (uint32_t i = 0; i < ev->opdata_count; ++i) {
 		const OpDataRec *od = &g->opdata[ev->opdata_off + i];
@@ -823,9 +1071,9 @@ __device__ void apply_event(const GenDesc *g, const WaveCoeffs *wc, const EventR
 			break;
 		}
 		if (osc) {
-			dev_line_copy(&n->line[LINE_FREQ], &od->line[LINE_FREQ]);
-			dev_line_copy(&n->line[LINE_FREQ2], &od->line[LINE_FREQ2]);
-			dev_line_copy(&n->line[LINE_PMA], &od->line[LINE_PMA]);
+			dev_line_copy(n, LINE_FREQ, &od->line[LINE_FREQ]);
+			dev_line_copy(n, LINE_FREQ2, &od->line[LINE_FREQ2]);
+			dev_line_copy(n, LINE_PMA, &od->line[LINE_PMA]);
 		}
 		if (params & SAUABI_POPP_TIME) {
 			if (od->time_flags & SAUABI_TIMEP_IMPLICIT) {
@@ -836,9 +1084,9 @@ __device__ void apply_event(const GenDesc *g, const WaveCoeffs *wc, const EventR
 				n->flags &= ~ON_TIME_INF;
 			}
 		}
-		dev_line_copy(&n->line[LINE_AMP], &od->line[LINE_AMP]);
-		dev_line_copy(&n->line[LINE_AMP2], &od->line[LINE_AMP2]);
-		dev_line_copy(&n->line[LINE_PAN], &od->line[LINE_PAN]);
+		dev_line_copy(n, LINE_AMP, &od->line[LINE_AMP]);
+		dev_line_copy(n, LINE_AMP2, &od->line[LINE_AMP2]);
+		dev_line_copy(n, LINE_PAN, &od->line[LINE_PAN]);
 	}
 	vs->carr_op = ev->carr_op_id;
 	vs->flags |= VN_INIT;
@@ -897,14 +1145,22 @@ __device__ uint32_t run_chunk(Ctx &c, const Instr *code, uint32_t code_len, uint
 			__syncwarp();
 			break;
 		case I_LINE: {
-			LineState *ls = &op_ptr(c, in.op)->line[in.c];
+			OpState *o = op_ptr(c, in.op);
 			if (in.d) {
-				float out[SPL];
-				line_eval(c, ls, in.b != NO_BUF ? c.bufs + in.b * CHUNK : nullptr, n,
-						c.stk_rem[c.sp], out);
-				st4(c, in.a, out);
+				const bool has_mul = in.b != NO_BUF;
+				float out[SPL], m[SPL];
+				bool done = false;
+				if (n == (uint32_t) CHUNK) {
+					const LineRegs r = line_load(o, in.c);
+					if (has_mul) ld4(c, in.b, m);
+					__syncwarp();
+					done = line_eval_full(c.oc, c.lane, o, in.c, r, has_mul ? m : nullptr, out);
+				}
+				if (done) st4(c, in.a, out);
+				else *B4(c, in.a) = line_eval_any(c.oc, c.lane, o, in.c,
+						has_mul ? c.bufs + in.b * CHUNK : nullptr, n, c.stk_rem[c.sp]);
 			} else {
-				line_skip(c, ls, n);
+				line_skip(c.oc, c.lane, o, in.c, n);
 			}
 			__syncwarp();
 			break; }
@@ -924,21 +1180,21 @@ __device__ uint32_t run_chunk(Ctx &c, const Instr *code, uint32_t code_len, uint
 			ld4(c, in.b, f);
 			if (in.c != NO_BUF) ld4(c, in.c, pm);
 			if (in.d != NO_BUF) ld4(c, in.d, fpm);
-			phasor_eval(c, op_ptr(c, in.op), f, in.c != NO_BUF ? pm : nullptr,
-					in.d != NO_BUF ? fpm : nullptr, n, ph);
+			{
+				OpState *o = op_ptr(c, in.op);
+				const uint32_t phase0 = o->i0;
+				__syncwarp();
+				phasor_eval<false>(c, o, phase0, f, in.c != NO_BUF ? pm : nullptr,
+						in.d != NO_BUF ? fpm : nullptr, n, ph);
+			}
 			*U4(c, in.a) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
 			__syncwarp();
 			break; }
 		case I_PMA: {                                              /* generator.c:485-490 */
 			OpState *o = op_ptr(c, in.op);
 			const bool run = pma_decide(c, o);
-			if (run) {
-				float out[SPL];
-				line_eval(c, &o->line[LINE_PMA], nullptr, n, c.stk_rem[c.sp], out);
-				st4(c, in.a, out);
-			} else {
-				line_skip(c, &o->line[LINE_PMA], n);
-			}
+			if (run) *B4(c, in.a) = line_eval_any(c.oc, c.lane, o, LINE_PMA, nullptr, n, c.stk_rem[c.sp]);
+			else line_skip(c.oc, c.lane, o, LINE_PMA, n);
 			c.pma_flag = run;
 			__syncwarp();
 			break; }
@@ -946,14 +1202,10 @@ __device__ uint32_t run_chunk(Ctx &c, const Instr *code, uint32_t code_len, uint
 			if (n) {
 				OpState *o = op_ptr(c, in.op);
 				if ((in.flags & F_HAS_APMODS) || c.pma_flag) {
-					wosc_selfmod(c, o, reinterpret_cast<const uint32_t*>(c.bufs + in.b * CHUNK),
+					wosc_selfmod(cold(c), o, reinterpret_cast<const uint32_t*>(c.bufs + in.b * CHUNK),
 							c.bufs + in.c * CHUNK, c.bufs + in.a * CHUNK, n);
 				} else {
-					const uint4 p4 = *U4(c, in.b);
-					const uint32_t ph[SPL] = {p4.x, p4.y, p4.z, p4.w};
-					float sv[SPL];
-					wosc_eval(c, o, ph, n, sv);
-					st4(c, in.a, sv);
+					*B4(c, in.a) = wosc_eval_any(cold(c), o, *U4(c, in.b), n);
 				}
 			}
 			__syncwarp();
@@ -974,7 +1226,7 @@ __device__ uint32_t run_chunk(Ctx &c, const Instr *code, uint32_t code_len, uint
 			float x[SPL] = {1.f, 1.f, 1.f, 1.f}, a[SPL];
 			if (in.b != NO_BUF) ld4(c, in.b, x);
 			ld4(c, in.c, a);
-			mix_eval(c, in.a, x, a, n, c.stk_layer[c.sp], (in.flags & F_WAVEENV) != 0);
+			mix_eval<false>(c, in.a, x, a, n, c.stk_layer[c.sp], (in.flags & F_WAVEENV) != 0);
 			__syncwarp();
 			break; }
 		case I_VPAN: {                                             /* generator.c:756-762 */
@@ -982,16 +1234,11 @@ __device__ uint32_t run_chunk(Ctx &c, const Instr *code, uint32_t code_len, uint
 			if (c.lane == 0) { c.stk_len[0] = c.last_len; c.stk_rem[0] = c.last_rem; }
 			__syncwarp();
 			if (c.last_len == 0) return 0;
-			LineState *ls = &op_ptr(c, in.op)->line[LINE_PAN];
-			const bool run = in.d || (ls->flags & SAUABI_LINEP_GOAL);
+			OpState *po = op_ptr(c, in.op);
+			const bool run = in.d || (LM_FLAGS(po->lmeta[LINE_PAN]) & SAUABI_LINEP_GOAL);
 			__syncwarp();
-			if (run) {
-				float out[SPL];
-				line_eval(c, ls, nullptr, c.last_len, c.last_rem, out);
-				st4(c, in.a, out);
-			} else {
-				line_skip(c, ls, c.last_len);
-			}
+			if (run) *B4(c, in.a) = line_eval_any(c.oc, c.lane, po, LINE_PAN, nullptr, c.last_len, c.last_rem);
+			else line_skip(c.oc, c.lane, po, LINE_PAN, c.last_len);
 			c.pan_dyn = run;
 			__syncwarp();
 			break; }
@@ -1027,38 +1274,37 @@ __device__ uint32_t run_chunk(Ctx &c, const Instr *code, uint32_t code_len, uint
 
 /* ---- render kernel ------------------------------------------------------ */
 
-constexpr uint32_t OP_WORDS = sizeof(OpState) / 4;
-static_assert(sizeof(OpState) % 16 == 0, "OpState is copied as 32-bit words");
+constexpr uint32_t OP_VEC = sizeof(OpState) / 16;
+static_assert(sizeof(OpState) == 192, "OpState layout (device_types.h)");
 
 /* operator states of the current voice program: HBM <-> shared memory */
-__device__ void ops_load(Ctx &c, uint32_t cnt) {
-	uint32_t *dst = reinterpret_cast<uint32_t*>(c.sops);
-	for (uint32_t i = c.lane; i < cnt * OP_WORDS; i += 32) {
-		const uint32_t slot = i / OP_WORDS, w = i % OP_WORDS;
-		dst[i] = reinterpret_cast<const uint32_t*>(c.gops + c.prog_ops[slot])[w];
+__device__ __forceinline__ void ops_load(Ctx &c, uint32_t cnt) {
+	uint4 *dst = reinterpret_cast<uint4*>(c.sops);
+	for (uint32_t i = c.lane; i < cnt * OP_VEC; i += 32) {
+		const uint32_t slot = i / OP_VEC, w = i % OP_VEC;
+		dst[i] = reinterpret_cast<const uint4*>(c.gops + c.prog_ops[slot])[w];
 	}
 	__syncwarp();
 }
-__device__ void ops_store(Ctx &c, uint32_t cnt) {
+__device__ __forceinline__ void ops_store(Ctx &c, uint32_t cnt) {
 	__syncwarp();
-	const uint32_t *src = reinterpret_cast<const uint32_t*>(c.sops);
-	for (uint32_t i = c.lane; i < cnt * OP_WORDS; i += 32) {
-		const uint32_t slot = i / OP_WORDS, w = i % OP_WORDS;
-		reinterpret_cast<uint32_t*>(c.gops + c.prog_ops[slot])[w] = src[i];
+	const uint4 *src = reinterpret_cast<const uint4*>(c.sops);
+	for (uint32_t i = c.lane; i < cnt * OP_VEC; i += 32) {
+		const uint32_t slot = i / OP_VEC, w = i % OP_VEC;
+		reinterpret_cast<uint4*>(c.gops + c.prog_ops[slot])[w] = src[i];
 	}
 	__syncwarp();
 }
 
-template <int MAXT, int MINB>
 __device__ __forceinline__ void render_body(const CallDesc *calls, uint32_t ncalls,
 		const SegDesc *segs, uint32_t ntasks, const float *tables, uint32_t wave_mask,
-		uint32_t nbufs, uint32_t warps_per_cta) {
+		uint32_t nbufs, uint32_t nslots_ops, uint32_t warps_per_cta) {
 	extern __shared__ __align__(128) unsigned char smem[];
 	uint64_t *bar = reinterpret_cast<uint64_t*>(smem);
 	float *tab = reinterpret_cast<float*>(smem + 128);
 	const uint32_t nslots = __popc(wave_mask);
-	unsigned char *warp_area = smem + 128 + nslots * WAVE_LEN * sizeof(float);
-	const uint32_t per_warp = warp_smem_bytes(nbufs);
+	unsigned char *warp_area = smem + 128 + nslots * TAB_STRIDE * sizeof(float);
+	const uint32_t per_warp = warp_smem_bytes(nbufs, nslots_ops);
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
 	/* stage the wave tables this launch needs: TMA bulk copies, one mbarrier */
@@ -1072,12 +1318,22 @@ __device__ __forceinline__ void render_body(const CallDesc *calls, uint32_t ncal
 		uint32_t slot = 0;
 		for (uint32_t w = 0; w < NUM_WAVES; ++w) {
 			if (!(wave_mask & (1u << w))) continue;
-			tma_bulk_g2s(tab + slot * WAVE_LEN, tables + w * WAVE_LEN,
+			tma_bulk_g2s(tab + slot * TAB_STRIDE + 4, tables + w * WAVE_LEN,
 					WAVE_LEN * sizeof(float), bar);
 			++slot;
 		}
 	}
-	if (nslots) mbar_wait(bar, 0);
+	if (nslots) {
+		mbar_wait(bar, 0);
+		/* wrapped neighbours: lut[-1], lut[2048], lut[2049] */
+		if (threadIdx.x < nslots) {
+			float *t = tab + threadIdx.x * TAB_STRIDE + 4;
+			t[-1] = t[WAVE_LEN - 1];
+			t[WAVE_LEN] = t[0];
+			t[WAVE_LEN + 1] = t[1];
+		}
+		__syncthreads();
+	}
 
 	const uint32_t task = blockIdx.x * warps_per_cta + warp;
 	if (task >= ntasks) return;
@@ -1095,7 +1351,7 @@ __device__ __forceinline__ void render_body(const CallDesc *calls, uint32_t ncal
 
 	Ctx c;
 	c.sops = reinterpret_cast<OpState*>(warp_area + warp * per_warp);
-	c.bufs = reinterpret_cast<float*>(c.sops + MAX_SLOTS);
+	c.bufs = reinterpret_cast<float*>(c.sops + nslots_ops);
 	c.stk_len = reinterpret_cast<uint32_t*>(c.bufs + nbufs * CHUNK);
 	c.stk_rem = c.stk_len + MAX_NEST;
 	c.stk_layer = c.stk_rem + MAX_NEST;
@@ -1104,7 +1360,7 @@ __device__ __forceinline__ void render_body(const CallDesc *calls, uint32_t ncal
 	c.g = g;
 	c.gops = g->ops;
 	c.prog_ops = g->prog_ops;
-	c.cached = 0;
+	c.coeff = g->coeff;
 	c.wave_mask = wave_mask;
 	c.lane = lane;
 
@@ -1119,7 +1375,7 @@ __device__ __forceinline__ void render_body(const CallDesc *calls, uint32_t ncal
 		const SegDesc sd = segs[cd->seg_off + si];
 		/* this voice's events due at the segment start, in order */
 		if (vs.ev_cursor < ev_n && g->vev_idx[ev_lo + vs.ev_cursor] < sd.ev_end) {
-			if (loaded) { ops_store(c, loaded); loaded = 0; c.cached = 0; }
+			if (loaded) { ops_store(c, loaded); loaded = 0; }
 			while (vs.ev_cursor < ev_n && g->vev_idx[ev_lo + vs.ev_cursor] < sd.ev_end) {
 				if (lane == 0) {
 					apply_event(g, c.wc, &g->events[g->vev_idx[ev_lo + vs.ev_cursor]], &vs);
@@ -1135,10 +1391,9 @@ __device__ __forceinline__ void render_body(const CallDesc *calls, uint32_t ncal
 			continue;
 		}
 		c.prog_ops = g->prog_ops + vs.ops_off;
-		if (!loaded && vs.ops_cnt > 0 && vs.ops_cnt <= (uint32_t) MAX_SLOTS) {
+		if (!loaded && vs.ops_cnt > 0) {
 			ops_load(c, vs.ops_cnt);
 			loaded = vs.ops_cnt;
-			c.cached = 1;
 		}
 		uint32_t run_total = 0;
 		for (uint32_t off = 0; off < sd.len && vs.duration != 0; off += CHUNK) {
@@ -1169,18 +1424,11 @@ __device__ __forceinline__ void render_body(const CallDesc *calls, uint32_t ncal
 	}
 }
 
-/* Two register budgets: <=8 warps per CTA at 80 registers, or 16-warp CTAs at
- * 64 registers so that 2 CTAs = 32 warps fit per SM (4736 resident warps on 148
- * SMs: the 4096-voice workload renders in ONE wave instead of 1.15). */
 __global__ void __launch_bounds__(256, 3)
 render_kernel(const CallDesc *calls, uint32_t ncalls, const SegDesc *segs, uint32_t ntasks,
-		const float *tables, uint32_t wave_mask, uint32_t nbufs, uint32_t warps_per_cta) {
-	render_body<256, 3>(calls, ncalls, segs, ntasks, tables, wave_mask, nbufs, warps_per_cta);
-}
-__global__ void __launch_bounds__(512, 2)
-render_kernel_dense(const CallDesc *calls, uint32_t ncalls, const SegDesc *segs, uint32_t ntasks,
-		const float *tables, uint32_t wave_mask, uint32_t nbufs, uint32_t warps_per_cta) {
-	render_body<512, 2>(calls, ncalls, segs, ntasks, tables, wave_mask, nbufs, warps_per_cta);
+		const float *tables, uint32_t wave_mask, uint32_t nbufs, uint32_t nslots_ops,
+		uint32_t warps_per_cta) {
+	render_body(calls, ncalls, segs, ntasks, tables, wave_mask, nbufs, nslots_ops, warps_per_cta);
 }
 
 /* ---- mix + clip epilogue ------------------------------------------------- */
@@ -1271,35 +1519,61 @@ __global__ void planes_to_pcm_kernel(const float *mix, uint32_t plane_stride, ui
 	}
 }
 
+/* ---- arithmetic self-test ------------------------------------------------ *
+ * The hand-expanded primitives of the fast path against the plain statements
+ * they replace: div_scale_by_int vs IEEE `/` for every non-zero int32 divisor
+ * (strided over the grid) and each wave's diff_scale; ftoi_lo32 vs the low
+ * word of sau::ftoi64 over a float bit-pattern sweep. */
+__global__ void selftest_kernel(const float *tables, unsigned long long *bad) {
+	const WaveCoeffs *wc = reinterpret_cast<const WaveCoeffs*>(tables + NUM_WAVES * WAVE_LEN);
+	const uint64_t tid = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+	const uint64_t nth = (uint64_t) gridDim.x * blockDim.x;
+	unsigned long long nbad = 0;
+	for (uint64_t u = tid; u < 0x100000000ull; u += nth) {
+		const int32_t d = (int32_t) (uint32_t) u;
+		if (d != 0) {
+			const uint32_t w = (uint32_t) (u % NUM_WAVES);
+			const float ds = wc->diff_scale[w];
+			const float want = ds / (float) d;
+			const float got = div_scale_by_int(ds, d);
+			if (__float_as_uint(want) != __float_as_uint(got)) ++nbad;
+		}
+		const float x = __uint_as_float((uint32_t) u);
+		if ((uint32_t) sau::ftoi64(x) != ftoi_lo32(x)) ++nbad;
+	}
+	if (nbad) atomicAdd(bad, nbad);
+}
+
+cudaError_t launch_selftest(const float *d_tables, unsigned long long *d_bad, cudaStream_t stream) {
+	selftest_kernel<<<148 * 8, 256, 0, stream>>>(d_tables, d_bad);
+	return cudaGetLastError();
+}
+
 /* ---- host-callable launchers -------------------------------------------- */
 
-size_t render_smem_bytes(uint32_t wave_mask, uint32_t nbufs, uint32_t warps) {
+size_t render_smem_bytes(uint32_t wave_mask, uint32_t nbufs, uint32_t nslots_ops, uint32_t warps) {
 	uint32_t nslots = 0;
 	for (uint32_t w = 0; w < NUM_WAVES; ++w) if (wave_mask & (1u << w)) ++nslots;
-	return 128 + (size_t) nslots * WAVE_LEN * sizeof(float) + (size_t) warps * warp_smem_bytes(nbufs);
+	return 128 + (size_t) nslots * TAB_STRIDE * sizeof(float) +
+		(size_t) warps * warp_smem_bytes(nbufs, nslots_ops);
 }
 
 cudaError_t launch_render(const CallDesc *d_calls, uint32_t ncalls, const SegDesc *d_segs,
 		uint32_t ntasks, const float *d_tables, uint32_t wave_mask, uint32_t nbufs,
-		uint32_t warps, cudaStream_t stream) {
+		uint32_t nslots_ops, uint32_t warps, cudaStream_t stream) {
 	if (ntasks == 0) return cudaSuccess;
-	const size_t smem = render_smem_bytes(wave_mask, nbufs, warps);
-	static size_t configured[2] = {0, 0};
-	const int dense = warps > 8;
-	if (smem > configured[dense]) {
-		cudaError_t e = dense ?
-			cudaFuncSetAttribute(render_kernel_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem) :
-			cudaFuncSetAttribute(render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+	if (nslots_ops == 0) nslots_ops = 1;
+	const size_t smem = render_smem_bytes(wave_mask, nbufs, nslots_ops, warps);
+	static size_t configured = 0;
+	if (smem > configured) {
+		cudaError_t e = cudaFuncSetAttribute(render_kernel,
+				cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
 		if (e != cudaSuccess) return e;
-		configured[dense] = smem;
+		configured = smem;
 	}
 	const uint32_t grid = (ntasks + warps - 1) / warps;
-	if (dense)
-		render_kernel_dense<<<grid, warps * 32, smem, stream>>>(d_calls, ncalls, d_segs, ntasks,
-				d_tables, wave_mask, nbufs, warps);
-	else
-		render_kernel<<<grid, warps * 32, smem, stream>>>(d_calls, ncalls, d_segs, ntasks,
-				d_tables, wave_mask, nbufs, warps);
+	render_kernel<<<grid, warps * 32, smem, stream>>>(d_calls, ncalls, d_segs, ntasks,
+			d_tables, wave_mask, nbufs, nslots_ops, warps);
 	return cudaGetLastError();
 }
 

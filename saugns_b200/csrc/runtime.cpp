@@ -26,14 +26,15 @@
 #include "device_types.h"
 
 namespace saugen {
-size_t render_smem_bytes(uint32_t wave_mask, uint32_t nbufs, uint32_t warps);
+size_t render_smem_bytes(uint32_t wave_mask, uint32_t nbufs, uint32_t nslots_ops, uint32_t warps);
 cudaError_t launch_render(const CallDesc *d_calls, uint32_t ncalls, const SegDesc *d_segs,
 		uint32_t ntasks, const float *d_tables, uint32_t wave_mask, uint32_t nbufs,
-		uint32_t warps, cudaStream_t stream);
+		uint32_t nslots_ops, uint32_t warps, cudaStream_t stream);
 cudaError_t launch_mix(const CallDesc *d_calls, uint32_t ncalls, const SegDesc *d_segs,
 		uint32_t max_call_len, uint32_t mode, cudaStream_t stream);
 cudaError_t launch_planes_to_pcm(const float *d_mix, uint32_t plane_stride, uint32_t n,
 		uint32_t stereo, int16_t *d_pcm, cudaStream_t stream);
+cudaError_t launch_selftest(const float *d_tables, unsigned long long *d_bad, cudaStream_t stream);
 const saugen_WaveTables *builtin_wave_tables();
 }
 
@@ -106,7 +107,7 @@ struct saugen_Generator {
 	bool own_stream = false;
 	uint32_t vo_count = 0, op_count = 0, nlv = 0;
 	uint32_t voice_begin = 0, voice_end = 0;
-	uint32_t row_len = 0, nbufs = 1, wave_mask = 0, seg_cap = 0;
+	uint32_t row_len = 0, nbufs = 1, max_ops = 1, wave_mask = 0, seg_cap = 0;
 	float amp_scale = 0.f;
 	/* timeline (host-only integer bookkeeping) */
 	std::vector<uint64_t> ev_time;     // absolute sample time of each event
@@ -462,6 +463,7 @@ extern "C" saugen_Generator *saugen_create(const sauabi_Program *prg, uint32_t s
 					code.insert(code.end(), comp.out.begin(), comp.out.end());
 					po.first = (uint32_t) prog_ops.size();
 					po.second = (uint32_t) comp.prog_ops.size();
+					if (po.second > o->max_ops) o->max_ops = po.second;
 					prog_ops.insert(prog_ops.end(), comp.prog_ops.begin(), comp.prog_ops.end());
 				}
 				er.code_off = pv.first; er.code_len = pv.second;
@@ -592,12 +594,11 @@ static void plan_call(saugen_Generator *o, uint32_t buf_len, std::vector<SegDesc
 /* CTA shape: small CTAs while there are fewer tasks than SMs x warps, 8-warp
  * CTAs (3 per SM, 80 registers) up to 24 warps per SM, and 16-warp CTAs (2 per
  * SM, 64 registers) beyond that when their shared memory fits twice per SM. */
-static uint32_t pick_warps(uint32_t ntasks, uint32_t wave_mask, uint32_t nbufs) {
+static uint32_t pick_warps(uint32_t ntasks, uint32_t wave_mask, uint32_t nbufs, uint32_t max_ops) {
 	const uint32_t sms = 148;
-	if (false && ntasks > sms * 24 && render_smem_bytes(wave_mask, nbufs, 16) <= 113 * 1024) return 16;
 	uint32_t warps = 8;
 	while (warps > 1 && (ntasks + warps - 1) / warps < sms) warps >>= 1;
-	while (warps > 1 && render_smem_bytes(wave_mask, nbufs, warps) > 200 * 1024) warps >>= 1;
+	while (warps > 1 && render_smem_bytes(wave_mask, nbufs, max_ops, warps) > 200 * 1024) warps >>= 1;
 	return warps;
 }
 
@@ -647,9 +648,9 @@ static int run_common(saugen_Generator *o, size_t buf_len, int stereo, uint32_t 
 	o->timed_call = o->timing;
 	if (e == cudaSuccess && o->timed_call) e = cudaEventRecord(o->ev_t[0], o->stream);
 	if (e == cudaSuccess) {
-		const uint32_t warps = pick_warps(o->nlv, o->wave_mask, o->nbufs);
+		const uint32_t warps = pick_warps(o->nlv, o->wave_mask, o->nbufs, o->max_ops);
 		e = launch_render(o->d_call, 1, o->d_segs, o->nlv, o->d_tables, o->wave_mask, o->nbufs,
-				warps, o->stream);
+				o->max_ops, warps, o->stream);
 		o->counters[0]++;
 	}
 	if (e == cudaSuccess && o->timed_call) e = cudaEventRecord(o->ev_t[1], o->stream);
@@ -753,7 +754,7 @@ extern "C" int saugen_run_many(saugen_Generator *const *gens, size_t n, int16_t 
 	static thread_local CallDesc *d_calls = nullptr; static thread_local size_t d_calls_cap = 0;
 	static thread_local SegDesc *d_segs = nullptr; static thread_local size_t d_segs_cap = 0;
 	calls.clear(); segs.clear(); call_of.clear();
-	uint32_t ntasks = 0, wave_mask = 0, nbufs = 1;
+	uint32_t ntasks = 0, wave_mask = 0, nbufs = 1, max_ops = 1;
 	for (size_t i = 0; i < n; ++i) {
 		saugen_Generator *o = gens[i];
 		if (out_lens) out_lens[i] = 0;
@@ -777,6 +778,7 @@ extern "C" int saugen_run_many(saugen_Generator *const *gens, size_t n, int16_t 
 		ntasks += o->nlv;
 		wave_mask |= o->wave_mask;
 		if (o->nbufs > nbufs) nbufs = o->nbufs;
+		if (o->max_ops > max_ops) max_ops = o->max_ops;
 		cudaMemsetAsync(o->d_status, 0, (1 + cd.nseg) * sizeof(uint32_t), g0->stream);
 	}
 	if (calls.empty()) return 0;
@@ -794,9 +796,9 @@ extern "C" int saugen_run_many(saugen_Generator *const *gens, size_t n, int16_t 
 	if (e == cudaSuccess) e = cudaMemcpyAsync(d_calls, calls.data(), calls.size() * sizeof(CallDesc), cudaMemcpyHostToDevice, g0->stream);
 	if (e == cudaSuccess) e = cudaMemcpyAsync(d_segs, segs.data(), segs.size() * sizeof(SegDesc), cudaMemcpyHostToDevice, g0->stream);
 	if (e == cudaSuccess) {
-		const uint32_t warps = pick_warps(ntasks, wave_mask, nbufs);
+		const uint32_t warps = pick_warps(ntasks, wave_mask, nbufs, max_ops);
 		e = launch_render(d_calls, (uint32_t) calls.size(), d_segs, ntasks, g0->d_tables, wave_mask,
-				nbufs, warps, g0->stream);
+				nbufs, max_ops, warps, g0->stream);
 		g0->counters[0]++;
 	}
 	if (e == cudaSuccess) {
@@ -829,9 +831,10 @@ extern "C" int saugen_run_many(saugen_Generator *const *gens, size_t n, int16_t 
 
 /* ---- introspection ------------------------------------------------------- */
 
-static void view_line(saugen_LineView *d, const LineState *s) {
+static void view_line(saugen_LineView *d, const OpState *o, int li) {
+	const LineState *s = &o->line[li];
 	d->v0 = s->v0; d->vt = s->vt; d->pos = s->pos; d->end = s->end;
-	d->type = s->type; d->flags = s->flags;
+	d->type = LM_TYPE(o->lmeta[li]); d->flags = LM_FLAGS(o->lmeta[li]);
 }
 
 extern "C" int saugen_read_op(saugen_Generator *o, uint32_t op_id, saugen_OpView *out) {
@@ -846,11 +849,11 @@ extern "C" int saugen_read_op(saugen_Generator *o, uint32_t op_id, saugen_OpView
 	out->type = s.type;
 	out->flags = s.flags & (ON_INIT | ON_TIME_INF);   /* reference bits only */
 	out->time = s.time;
-	view_line(&out->amp, &s.line[LINE_AMP]); view_line(&out->amp2, &s.line[LINE_AMP2]);
-	view_line(&out->pan, &s.line[LINE_PAN]);
+	view_line(&out->amp, &s, LINE_AMP); view_line(&out->amp2, &s, LINE_AMP2);
+	view_line(&out->pan, &s, LINE_PAN);
 	if (s.type >= SAUABI_POPT_wave) {
-		view_line(&out->freq, &s.line[LINE_FREQ]); view_line(&out->freq2, &s.line[LINE_FREQ2]);
-		view_line(&out->pm_a, &s.line[LINE_PMA]);
+		view_line(&out->freq, &s, LINE_FREQ); view_line(&out->freq2, &s, LINE_FREQ2);
+		view_line(&out->pm_a, &s, LINE_PMA);
 	}
 	out->i0 = s.i0; out->i1 = s.i1; out->mode = s.mode;
 	switch (s.type) {
@@ -902,6 +905,21 @@ extern "C" int saugen_kernel_ms(saugen_Generator *o, double out[2]) {
 	if (!o) return -1;
 	out[0] = o->render_ms; out[1] = o->mix_ms;
 	return 0;
+}
+/* Device arithmetic self-test (kernels.cu:selftest_kernel): number of inputs on
+ * which a fast-path primitive differs from the statement it replaces, <0 on error. */
+extern "C" long long saugen_selftest(int device, const saugen_WaveTables *tables) {
+	if (cudaSetDevice(device) != cudaSuccess) { set_err("saugen_selftest", cudaGetLastError()); return -1; }
+	if (!tables) tables = saugen::builtin_wave_tables();
+	float *d_tab = get_device_tables(device, tables);
+	unsigned long long *d_bad = nullptr, h_bad = 0;
+	if (!d_tab || cudaMalloc(&d_bad, sizeof h_bad) != cudaSuccess) { set_err("saugen_selftest", cudaGetLastError()); return -1; }
+	cudaMemset(d_bad, 0, sizeof h_bad);
+	cudaError_t e = launch_selftest(d_tab, d_bad, 0);
+	if (e == cudaSuccess) e = cudaMemcpy(&h_bad, d_bad, sizeof h_bad, cudaMemcpyDeviceToHost);
+	cudaFree(d_bad);
+	if (e != cudaSuccess) { set_err("saugen_selftest", e); return -1; }
+	return (long long) h_bad;
 }
 extern "C" float saugen_amp_scale(saugen_Generator *o) { return o ? o->amp_scale : 0.f; }
 extern "C" const char *saugen_last_error(void) { return g_err.c_str(); }

@@ -85,6 +85,8 @@ def lib():
         L.saugen_counters.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
         L.saugen_set_timing.argtypes = [C.c_void_p, C.c_int]
         L.saugen_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+        L.saugen_selftest.restype = C.c_longlong
+        L.saugen_selftest.argtypes = [C.c_int, C.c_void_p]
         L.saugen_amp_scale.restype = C.c_float
         L.saugen_amp_scale.argtypes = [C.c_void_p]
         L.saugen_last_error.restype = C.c_char_p
@@ -102,6 +104,14 @@ def last_error():
 
 def device_count():
     return lib().saugen_device_count()
+
+
+def selftest(device=0, tables=None):
+    """Mismatches of the fast-path arithmetic primitives vs their plain forms (0 = exact)."""
+    r = lib().saugen_selftest(device, C.addressof(tables) if tables is not None else None)
+    if r < 0:
+        raise RuntimeError("saugen_selftest failed: " + last_error())
+    return r
 
 
 def builtin_tables():

@@ -30,6 +30,13 @@ def gold():
     return gpuutil.golden()
 
 
+def test_fast_path_arithmetic_selftest(S, tabs):
+    """Hand-expanded division / rounding primitives == the plain IEEE statements."""
+    from saugns_b200 import generator
+    assert generator.selftest(0, tabs) == 0
+    assert generator.selftest(0, None) == 0
+
+
 def test_feature_scripts_bit_exact(S, ref, tabs, gold):
     bad = []
     for name, text in sorted(scripts.feature_scripts().items()):
