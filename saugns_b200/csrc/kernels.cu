@@ -368,8 +368,8 @@ __device__ __forceinline__ uint32_t ftoi_lo32(float x) {
 	return (x >= 9223372036854775808.f) ? 0u : r;
 }
 
-template <bool FULLC>
-__device__ __forceinline__ void phasor_eval(const Ctx &c, OpState *o, uint32_t phase0,
+template <bool FULLC, typename C>
+__device__ __forceinline__ void phasor_eval(const C &c, OpState *o, uint32_t phase0,
 		const float f[SPL], const float *pm, const float *fpm, uint32_t n, uint32_t ph[SPL]) {
 	const float coeff = c.coeff;
 	const uint32_t i0 = c.lane * SPL;
@@ -523,7 +523,8 @@ __device__ __noinline__ float4 wosc_eval_any(const ColdCtx c, OpState *o, const 
 /* FULL chunk, no restart pending, carried state in registers.  Returns false
  * (nothing written) when some phase difference is zero: the caller then runs
  * wosc_eval_any on the same phases. */
-__device__ __forceinline__ bool wosc_eval_full(const Ctx &c, OpState *o, uint32_t wave,
+template <typename C>
+__device__ __forceinline__ bool wosc_eval_full(const C &c, OpState *o, uint32_t wave,
 		uint32_t prev_phase, double prev_Is, const uint32_t ph[SPL], float s[SPL]) {
 	const float *taps = wave_lut(c, wave) - 1;
 	const float ds = c.wc->diff_scale[wave];
@@ -1100,7 +1101,7 @@ __device__ __noinline__ void apply_event(const GenDesc *g, const WaveCoeffs *wc,
 
 /* ---- bytecode interpreter: one chunk of one voice ----------------------- */
 
-__device__ uint32_t run_chunk(Ctx &c, const Instr *code, uint32_t code_len, uint32_t time,
+__device__ __noinline__ uint32_t run_chunk(Ctx &c, const Instr *code, uint32_t code_len, uint32_t time,
 		uint32_t rem0, float *row_s, float *row_r) {
 	c.sp = 0;
 	if (c.lane == 0) { c.stk_len[0] = time; c.stk_rem[0] = rem0; c.stk_layer[0] = 0; }
@@ -1272,6 +1273,303 @@ __device__ uint32_t run_chunk(Ctx &c, const Instr *code, uint32_t code_len, uint
 	return 0;
 }
 
+/* ---- steady-block fast path --------------------------------------------- *
+ * Most of a render is spent in blocks where nothing changes shape: a whole
+ * 1024-sample reference block (BUF_LEN, generator.c:28) lies inside one
+ * inter-event segment, every operator of the voice outlasts it, every line
+ * either holds its value or is on a trajectory that does not end inside the
+ * block, no differentiator restart or self-PM is pending.  For such a block
+ * the state machines of sauLine_run / run_block need no per-chunk decisions:
+ * the reference itself advances them once per block.  steady_check() proves
+ * the block is of that kind (else the general interpreter above renders it),
+ * run_chunk_fast() renders its chunks with read-only line state and only the
+ * oscillator accumulators written back, steady_update() then advances lines
+ * and operator times by one block exactly as sauLine_run / sauLine_skip /
+ * run_block do for len = 1024 (line.c:417-473, generator.c:716-728).
+ * Supported bytecode: the wave-operator forms (HEAD/TAIL/LEAF, ENTER + LINE +
+ * RANGE for FM carriers), static pan; anything else makes steady_check fail. */
+
+struct FastCtx {               /* all registers */
+	float *bufs;               // shared: work buffers of this warp
+	OpState *sops;             // shared: operator states
+	const float *tab;          // shared: staged wave tables
+	const WaveCoeffs *wc;
+	float coeff, amp_scale;
+	uint32_t wave_mask;
+	uint32_t oc;               // chunk offset inside the block
+	int lane;
+};
+__device__ __forceinline__ float4 *FB4(const FastCtx &c, uint32_t i) {
+	return reinterpret_cast<float4*>(c.bufs + i * CHUNK) + c.lane;
+}
+__device__ __forceinline__ void fld4(const FastCtx &c, uint32_t buf, float v[SPL]) {
+	const float4 t = *FB4(c, buf);
+	v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+__device__ __forceinline__ void fst4(const FastCtx &c, uint32_t buf, const float v[SPL]) {
+	*FB4(c, buf) = make_float4(v[0], v[1], v[2], v[3]);
+}
+
+/* a run line is steady over the next 1024 samples */
+__device__ __forceinline__ bool line_steady(const OpState *o, int li) {
+	const uint32_t flags = LM_FLAGS(o->lmeta[li]);
+	if (!(flags & SAUABI_LINEP_GOAL)) return true;
+	const bool gr = (flags & SAUABI_LINEP_GOAL_RATIO) != 0, sr = (flags & SAUABI_LINEP_STATE_RATIO) != 0;
+	const uint32_t pos = o->line[li].pos, end = o->line[li].end;
+	return gr == sr && pos < end && end - pos > (uint32_t) REF_BLOCK;
+}
+__device__ __forceinline__ bool op_outlasts_block(const OpState *o) {
+	return (o->flags & ON_TIME_INF) || o->time >= (uint32_t) REF_BLOCK;
+}
+
+__device__ __noinline__ bool steady_check(OpState *sops, const Instr *code, uint32_t code_len) {
+	uint32_t seen = 0;         /* operator slots already visited (< 32 of them) */
+	for (uint32_t pc = 0; pc < code_len; ++pc) {
+		const uint4 raw = __ldg(reinterpret_cast<const uint4*>(code + pc));
+		Instr in;
+		memcpy(&in, &raw, sizeof(in));
+		const OpState *o = sops + in.op;
+		bool head = false, tail = false;
+		switch (in.opcode) {
+		case I_WLEAF: head = tail = true; break;
+		case I_WHEAD: head = true; break;
+		case I_WTAIL: tail = true; break;
+		case I_ENTER:
+			if (o->type != SAUABI_POPT_wave || !op_outlasts_block(o)) return false;
+			if (in.op >= 32 || (seen & (1u << in.op))) return false;
+			seen |= 1u << in.op;
+			break;
+		case I_LINE:
+			if (in.d && !line_steady(o, in.c)) return false;
+			break;
+		case I_RANGE: case I_VOUT: case I_END:
+			break;
+		case I_VPAN:
+			if (in.d || (LM_FLAGS(o->lmeta[LINE_PAN]) & SAUABI_LINEP_GOAL)) return false;
+			break;
+		default:
+			return false;
+		}
+		if (head) {
+			if (in.op >= 32 || (seen & (1u << in.op))) return false;
+			seen |= 1u << in.op;
+			if (!op_outlasts_block(o) || !line_steady(o, LINE_FREQ)) return false;
+		}
+		if (tail) {
+			if (!op_outlasts_block(o) || !line_steady(o, LINE_AMP)) return false;
+			if (o->oscflags & OSC_RESET_DIFF) return false;
+			if (in.flags & F_MAY_SELFMOD) {                          /* generator.c:485-490 */
+				if (o->line[LINE_PMA].v0 != 0.f ||
+						(LM_FLAGS(o->lmeta[LINE_PMA]) & SAUABI_LINEP_GOAL)) return false;
+			}
+		}
+	}
+	return true;
+}
+
+/* sauLine_run's bookkeeping for one whole block of a steady run line */
+__device__ __forceinline__ void line_block_update(OpState *o, int li) {
+	const uint32_t meta = o->lmeta[li];
+	uint32_t flags = LM_FLAGS(meta), pos = o->line[li].pos;
+	if (flags & SAUABI_LINEP_GOAL) {
+		pos += REF_BLOCK;
+	} else {
+		bool ex;
+		line_advance(pos, o->line[li].end, flags, REF_BLOCK, ex);
+	}
+	o->line[li].pos = pos;
+	o->lmeta[li] = LM_PACK(LM_TYPE(meta), flags, 0u);
+}
+
+/* lane 0 only */
+__device__ __noinline__ void steady_update(OpState *sops, const Instr *code, uint32_t code_len) {
+	for (uint32_t pc = 0; pc < code_len; ++pc) {
+		const uint4 raw = __ldg(reinterpret_cast<const uint4*>(code + pc));
+		Instr in;
+		memcpy(&in, &raw, sizeof(in));
+		OpState *o = sops + in.op;
+		bool head = false, tail = false;
+		switch (in.opcode) {
+		case I_WLEAF: head = tail = true; break;
+		case I_WHEAD: head = true; break;
+		case I_WTAIL: tail = true; break;
+		case I_LINE:
+			if (in.d) line_block_update(o, in.c);
+			else line_skip(0, 0, o, in.c, REF_BLOCK);
+			break;
+		case I_VPAN:
+			line_skip(0, 0, o, LINE_PAN, REF_BLOCK);
+			break;
+		default: break;
+		}
+		if (head) {
+			line_block_update(o, LINE_FREQ);
+			if (in.flags & F_SKIP_FREQ2) line_skip(0, 0, o, LINE_FREQ2, REF_BLOCK);
+		}
+		if (tail) {
+			line_block_update(o, LINE_AMP);
+			if (in.flags & F_SKIP_AMP2) line_skip(0, 0, o, LINE_AMP2, REF_BLOCK);
+			if (in.flags & F_MAY_SELFMOD) {
+				line_skip(0, 0, o, LINE_PMA, REF_BLOCK);
+				o->flags &= ~ON_PMA_RUN;
+			}
+			if (!(o->flags & ON_TIME_INF)) o->time -= REF_BLOCK;   /* generator.c:726-727 */
+		}
+	}
+}
+
+/* value of a steady run line for this lane's samples of the chunk at c.oc */
+__device__ __forceinline__ void line_value_steady(const FastCtx &c, const OpState *o, int li,
+		const float *m /* SPL multipliers or nullptr */, float out[SPL]) {
+	const LineRegs r = line_load(o, li);
+	const uint32_t flags = LM_FLAGS(r.meta);
+	if (!(flags & SAUABI_LINEP_GOAL)) {
+		const bool um = m && (flags & SAUABI_LINEP_STATE_RATIO);
+#pragma unroll
+		for (int k = 0; k < SPL; ++k) out[k] = um ? r.v0 * m[k] : r.v0;
+		return;
+	}
+	sau::LineFill f;
+	int t = (int) LM_TYPE(r.meta);
+	if (t == sau::L_exp) t = (r.v0 > r.vt) ? sau::L_xpe : sau::L_lge;
+	else if (t == sau::L_log) t = (r.v0 < r.vt) ? sau::L_xpe : sau::L_lge;
+	f.type = t;
+	f.v0 = r.v0; f.vt = r.vt;
+	f.pos = r.pos + c.oc;
+	f.adj_pos = (int32_t) (f.pos - (r.end / 2));
+	f.inv = r.inv;
+	f.vm = (r.v0 + r.vt) * 0.5f;
+	f.vd = r.vt - r.v0;
+	f.c = 0.f;
+	const uint32_t i0 = c.lane * SPL;
+	switch (t) {
+	default:
+	case sau::L_sah: line_fill4<sau::L_sah>(f, i0, out); break;
+	case sau::L_lin: f.c = f.vd * f.inv; line_fill4<sau::L_lin>(f, i0, out); break;
+	case sau::L_cos: line_fill4<sau::L_cos>(f, i0, out); break;
+	case sau::L_xpe: f.c = r.v0 - r.vt; line_fill4<sau::L_xpe>(f, i0, out); break;
+	case sau::L_lge: line_fill4<sau::L_lge>(f, i0, out); break;
+	case sau::L_sqe: f.c = r.v0 - r.vt; line_fill4<sau::L_sqe>(f, i0, out); break;
+	case sau::L_cub: f.inv = -2.f * f.inv; f.c = (r.v0 - r.vt) * 0.5f; line_fill4<sau::L_cub>(f, i0, out); break;
+	case sau::L_smo: line_fill4<sau::L_smo>(f, i0, out); break;
+	case sau::L_uwh: f.c = f.vd * (0.5f / 2147483648.f); line_fill4<sau::L_uwh>(f, i0, out); break;
+	case sau::L_ncl: line_fill4<sau::L_ncl>(f, i0, out); break;
+	case sau::L_nhl: line_fill4<sau::L_nhl>(f, i0, out); break;
+	}
+	if (m && (flags & SAUABI_LINEP_GOAL_RATIO)) {
+#pragma unroll
+		for (int k = 0; k < SPL; ++k) out[k] = out[k] * m[k];
+	}
+}
+
+/* TAIL of a wave operator on a steady full chunk; fr = its frequency values */
+__device__ __forceinline__ void wtail_fast(const FastCtx &c, const Instr &in, OpState *o,
+		const float fr[SPL]) {
+	const uint4 og = *reinterpret_cast<const uint4*>(&o->time);
+	const float4 pg = *reinterpret_cast<const float4*>(&o->prev_Is);
+	const uint32_t wave = (og.y >> 16) & 0xffu;
+	const double prev_Is = __hiloint2double(__float_as_int(pg.y), __float_as_int(pg.x));
+	__syncwarp();              /* every lane holds the accumulators before lane 31 rewrites them */
+	float pm[SPL], fpm[SPL];
+	if (in.c != NO_BUF) fld4(c, in.c, pm);
+	if (in.d != NO_BUF) fld4(c, in.d, fpm);
+	uint32_t ph[SPL];
+	phasor_eval<true>(c, o, og.z, fr, in.c != NO_BUF ? pm : nullptr,
+			in.d != NO_BUF ? fpm : nullptr, CHUNK, ph);
+	float s[SPL];
+	if (!wosc_eval_full(c, o, wave, og.w, prev_Is, ph, s)) {
+		ColdCtx k; k.tab = c.tab; k.wc = c.wc; k.wave_mask = c.wave_mask; k.lane = c.lane;
+		const float4 t = wosc_eval_any(k, o, make_uint4(ph[0], ph[1], ph[2], ph[3]), CHUNK);
+		s[0] = t.x; s[1] = t.y; s[2] = t.z; s[3] = t.w;
+	}
+	float am[SPL];
+	line_value_steady(c, o, LINE_AMP, nullptr, am);
+	const bool layer = (in.flags & F_LAYER) != 0;      /* F_LAYER_PMA: no self-PM here */
+	float ov[SPL];
+	if (layer) fld4(c, in.a, ov);
+	if (in.flags & F_WAVEENV) {                                   /* generator.c:407-426 */
+#pragma unroll
+		for (int k = 0; k < SPL; ++k) {
+			const float s_amp = am[k] * 0.5f;
+			const float v = (s[k] * s_amp) + fabsf(s_amp);
+			ov[k] = layer ? ov[k] * v : v;
+		}
+	} else {                                                      /* generator.c:384-397 */
+#pragma unroll
+		for (int k = 0; k < SPL; ++k) {
+			const float v = s[k] * am[k];
+			ov[k] = layer ? ov[k] + v : v;
+		}
+	}
+	fst4(c, in.a, ov);
+	__syncwarp();
+}
+
+__device__ __forceinline__ void run_chunk_fast(const FastCtx &c, const Instr *code,
+		uint32_t code_len, float *row_s, float *row_r) {
+	for (uint32_t pc = 0; pc < code_len; ++pc) {
+		const uint4 raw = __ldg(reinterpret_cast<const uint4*>(code + pc));
+		Instr in;
+		memcpy(&in, &raw, sizeof(in));
+		OpState *o = c.sops + in.op;
+		switch (in.opcode) {
+		case I_WLEAF: case I_WHEAD: {
+			float fr[SPL], m[SPL];
+			const bool has_mul = in.e != NO_BUF;
+			if (has_mul) fld4(c, in.e, m);
+			line_value_steady(c, o, LINE_FREQ, has_mul ? m : nullptr, fr);
+			if (in.opcode == I_WHEAD) fst4(c, in.b, fr);
+			else wtail_fast(c, in, o, fr);
+			break; }
+		case I_WTAIL: {
+			float fr[SPL];
+			fld4(c, in.b, fr);
+			wtail_fast(c, in, o, fr);
+			break; }
+		case I_LINE:
+			if (in.d) {
+				float out[SPL], m[SPL];
+				const bool has_mul = in.b != NO_BUF;
+				if (has_mul) fld4(c, in.b, m);
+				line_value_steady(c, o, in.c, has_mul ? m : nullptr, out);
+				fst4(c, in.a, out);
+			}
+			break;
+		case I_RANGE: {                                            /* generator.c:465-467 */
+			float4 p = *FB4(c, in.a);
+			const float4 r = *FB4(c, in.b), m = *FB4(c, in.c);
+			p.x += (r.x - p.x) * m.x;
+			p.y += (r.y - p.y) * m.y;
+			p.z += (r.z - p.z) * m.z;
+			p.w += (r.w - p.w) * m.w;
+			*FB4(c, in.a) = p;
+			break; }
+		case I_VOUT: {                                             /* generator.c:772-786 */
+			const float amp_scale = c.amp_scale;
+			const float4 sv = *FB4(c, in.a);
+			const float p = o->line[LINE_PAN].v0;
+			float4 s, r;
+			s.x = sv.x * amp_scale; r.x = s.x * p;
+			s.y = sv.y * amp_scale; r.y = s.y * p;
+			s.z = sv.z * amp_scale; r.z = s.z * p;
+			s.w = sv.w * amp_scale; r.w = s.w * p;
+			const uint32_t i0 = c.lane * SPL;
+			if ((reinterpret_cast<uintptr_t>(row_s) & 15) == 0) {
+				__stcs(reinterpret_cast<float4*>(row_s + i0), s);   /* coalesced 128-bit stores */
+				__stcs(reinterpret_cast<float4*>(row_r + i0), r);
+			} else {
+				row_s[i0 + 0] = s.x; row_r[i0 + 0] = r.x;
+				row_s[i0 + 1] = s.y; row_r[i0 + 1] = r.y;
+				row_s[i0 + 2] = s.z; row_r[i0 + 2] = r.z;
+				row_s[i0 + 3] = s.w; row_r[i0 + 3] = r.w;
+			}
+			return; }
+		default:                   /* ENTER, VPAN, END: nothing to do per chunk */
+			break;
+		}
+	}
+}
+
 /* ---- render kernel ------------------------------------------------------ */
 
 constexpr uint32_t OP_VEC = sizeof(OpState) / 16;
@@ -1397,6 +1695,28 @@ __device__ __forceinline__ void render_body(const CallDesc *calls, uint32_t ncal
 		}
 		uint32_t run_total = 0;
 		for (uint32_t off = 0; off < sd.len && vs.duration != 0; off += CHUNK) {
+			/* a whole reference block in steady state: the fast path */
+			if (off % REF_BLOCK == 0 && sd.len - off >= (uint32_t) REF_BLOCK &&
+					vs.duration >= (uint32_t) REF_BLOCK && vs.code_len &&
+					op_ptr(c, vs.carr_slot)->time > 0 &&
+					steady_check(c.sops, g->code + vs.code_off, vs.code_len)) {
+				FastCtx fc;
+				fc.bufs = c.bufs; fc.sops = c.sops; fc.tab = c.tab; fc.wc = c.wc;
+				fc.coeff = c.coeff; fc.amp_scale = g->amp_scale;
+				fc.wave_mask = wave_mask; fc.lane = lane;
+				for (uint32_t oc = 0; oc < (uint32_t) REF_BLOCK; oc += CHUNK) {
+					fc.oc = oc;
+					run_chunk_fast(fc, g->code + vs.code_off, vs.code_len,
+							row_s + sd.start + off + oc, row_r + sd.start + off + oc);
+				}
+				__syncwarp();
+				if (lane == 0) steady_update(c.sops, g->code + vs.code_off, vs.code_len);
+				__syncwarp();
+				vs.duration -= REF_BLOCK;
+				run_total += REF_BLOCK;
+				off += REF_BLOCK - CHUNK;
+				continue;
+			}
 			uint32_t clen = sd.len - off;
 			if (clen > (uint32_t) CHUNK) clen = CHUNK;
 			const uint32_t time = vs.duration < clen ? vs.duration : clen;
