@@ -31,8 +31,10 @@ namespace saugen {
 #define FULL 0xffffffffu
 
 /* per-warp shared memory: operator-state cache, work buffers, len stack */
+constexpr int FAST_NS = 8;            // samples per lane in the steady-block fast path
+constexpr uint32_t BUF_FLOATS = 32 * (FAST_NS > SPL ? FAST_NS : SPL);   // per work buffer
 __host__ __device__ inline uint32_t warp_smem_bytes(uint32_t nbufs, uint32_t nslots) {
-	return nslots * (uint32_t) sizeof(OpState) + nbufs * CHUNK * (uint32_t) sizeof(float) +
+	return nslots * (uint32_t) sizeof(OpState) + nbufs * BUF_FLOATS * (uint32_t) sizeof(float) +
 		3 * MAX_NEST * (uint32_t) sizeof(uint32_t);
 }
 
@@ -1289,27 +1291,6 @@ __device__ __noinline__ uint32_t run_chunk(Ctx &c, const Instr *code, uint32_t c
  * Supported bytecode: the wave-operator forms (HEAD/TAIL/LEAF, ENTER + LINE +
  * RANGE for FM carriers), static pan; anything else makes steady_check fail. */
 
-struct FastCtx {               /* all registers */
-	float *bufs;               // shared: work buffers of this warp
-	OpState *sops;             // shared: operator states
-	const float *tab;          // shared: staged wave tables
-	const WaveCoeffs *wc;
-	float coeff, amp_scale;
-	uint32_t wave_mask;
-	uint32_t oc;               // chunk offset inside the block
-	int lane;
-};
-__device__ __forceinline__ float4 *FB4(const FastCtx &c, uint32_t i) {
-	return reinterpret_cast<float4*>(c.bufs + i * CHUNK) + c.lane;
-}
-__device__ __forceinline__ void fld4(const FastCtx &c, uint32_t buf, float v[SPL]) {
-	const float4 t = *FB4(c, buf);
-	v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-}
-__device__ __forceinline__ void fst4(const FastCtx &c, uint32_t buf, const float v[SPL]) {
-	*FB4(c, buf) = make_float4(v[0], v[1], v[2], v[3]);
-}
-
 /* a run line is steady over the next 1024 samples */
 __device__ __forceinline__ bool line_steady(const OpState *o, int li) {
 	const uint32_t flags = LM_FLAGS(o->lmeta[li]);
@@ -1418,150 +1399,366 @@ __device__ __noinline__ void steady_update(OpState *sops, const Instr *code, uin
 	}
 }
 
+/* the trajectory of a steady goal line at positions pos .. pos+3 (line.c:27-281);
+ * out of line: one copy of the 11 shapes for all call sites */
+__device__ __noinline__ float4 line_goal_fill(float v0, float vt, float inv, uint32_t pos,
+		uint32_t end, uint32_t type) {
+	sau::LineFill f;
+	int t = (int) type;
+	if (t == sau::L_exp) t = (v0 > vt) ? sau::L_xpe : sau::L_lge;
+	else if (t == sau::L_log) t = (v0 < vt) ? sau::L_xpe : sau::L_lge;
+	f.type = t;
+	f.v0 = v0; f.vt = vt;
+	f.pos = pos;
+	f.adj_pos = (int32_t) (pos - (end / 2));
+	f.inv = inv;
+	f.vm = (v0 + vt) * 0.5f;
+	f.vd = vt - v0;
+	f.c = 0.f;
+	float out[SPL];
+	switch (t) {
+	default:
+	case sau::L_sah: line_fill4<sau::L_sah>(f, 0, out); break;
+	case sau::L_lin: f.c = f.vd * f.inv; line_fill4<sau::L_lin>(f, 0, out); break;
+	case sau::L_cos: line_fill4<sau::L_cos>(f, 0, out); break;
+	case sau::L_xpe: f.c = v0 - vt; line_fill4<sau::L_xpe>(f, 0, out); break;
+	case sau::L_lge: line_fill4<sau::L_lge>(f, 0, out); break;
+	case sau::L_sqe: f.c = v0 - vt; line_fill4<sau::L_sqe>(f, 0, out); break;
+	case sau::L_cub: f.inv = -2.f * f.inv; f.c = (v0 - vt) * 0.5f; line_fill4<sau::L_cub>(f, 0, out); break;
+	case sau::L_smo: line_fill4<sau::L_smo>(f, 0, out); break;
+	case sau::L_uwh: f.c = f.vd * (0.5f / 2147483648.f); line_fill4<sau::L_uwh>(f, 0, out); break;
+	case sau::L_ncl: line_fill4<sau::L_ncl>(f, 0, out); break;
+	case sau::L_nhl: line_fill4<sau::L_nhl>(f, 0, out); break;
+	}
+	return make_float4(out[0], out[1], out[2], out[3]);
+}
+
+/* The per-chunk code addresses shared memory by 32-bit shared-window addresses
+ * through ld.shared / st.shared: one register per base, no generic loads, no
+ * re-derivation of the bases.  NS = samples per lane (chunk = 32 * NS).
+ * Work buffer i of the fast path: NS/4 planes of 32 float4 (lane-major, so
+ * 128-bit accesses are conflict-free), FBUF_BYTES apart. */
+template <int NS> struct FastCfg {
+	static constexpr uint32_t CHUNKF = 32 * NS;
+	static constexpr uint32_t FBUF_BYTES = CHUNKF * 4;
+};
+struct FastCtx {               /* all registers */
+	uint32_t sb;               // shared addr of this lane's float4 in plane 0 of buffer 0
+	uint32_t so;               // shared addr of the operator states
+	uint32_t st;               // shared addr of the staged tables
+	uint32_t wave_mask;
+	uint32_t oc;               // chunk offset inside the block
+	int lane;
+	float coeff, amp_scale;
+	const WaveCoeffs *wc;
+	const float *tab;          // generic pointer to the staged tables (rare paths)
+};
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+	float4 v;
+	asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+			: "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+	return v;
+}
+__device__ __forceinline__ uint4 lds128u(uint32_t a) {
+	uint4 v;
+	asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+			: "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+	return v;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t a) {
+	uint32_t v;
+	asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+	return v;
+}
+__device__ __forceinline__ float lds32f(uint32_t a) {
+	float v;
+	asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+	return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, float4 v) {
+	asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};"
+			:: "r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) {
+	asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory");
+}
+template <int NS>
+__device__ __forceinline__ void fld(const FastCtx &c, uint32_t buf, float v[NS]) {
+	const uint32_t a = c.sb + buf * FastCfg<NS>::FBUF_BYTES;
+#pragma unroll
+	for (int h = 0; h < NS / 4; ++h) {
+		const float4 t = lds128(a + h * 512);
+		v[4 * h] = t.x; v[4 * h + 1] = t.y; v[4 * h + 2] = t.z; v[4 * h + 3] = t.w;
+	}
+}
+template <int NS>
+__device__ __forceinline__ void fst(const FastCtx &c, uint32_t buf, const float v[NS]) {
+	const uint32_t a = c.sb + buf * FastCfg<NS>::FBUF_BYTES;
+#pragma unroll
+	for (int h = 0; h < NS / 4; ++h)
+		sts128(a + h * 512, make_float4(v[4 * h], v[4 * h + 1], v[4 * h + 2], v[4 * h + 3]));
+}
+
+/* byte offsets inside OpState (device_types.h) */
+constexpr uint32_t OS_LINE = 0, OS_LMETA = 96, OS_LINV = 120, OS_TIME = 144, OS_I0 = 152,
+	OS_I1 = 156, OS_PREV = 160;
+static_assert(offsetof(OpState, lmeta) == OS_LMETA && offsetof(OpState, linv) == OS_LINV &&
+		offsetof(OpState, time) == OS_TIME && offsetof(OpState, i0) == OS_I0 &&
+		offsetof(OpState, i1) == OS_I1 && offsetof(OpState, prev_Is) == OS_PREV, "OpState offsets");
+
 /* value of a steady run line for this lane's samples of the chunk at c.oc */
-__device__ __forceinline__ void line_value_steady(const FastCtx &c, const OpState *o, int li,
-		const float *m /* SPL multipliers or nullptr */, float out[SPL]) {
-	const LineRegs r = line_load(o, li);
-	const uint32_t flags = LM_FLAGS(r.meta);
+template <int NS>
+__device__ __forceinline__ void line_value_steady(const FastCtx &c, uint32_t op, int li,
+		const float *m /* NS multipliers or nullptr */, float out[NS]) {
+	const uint4 core = lds128u(op + OS_LINE + 16 * li);          /* v0, vt, pos, end */
+	const uint32_t meta = lds32(op + OS_LMETA + 4 * li);
+	const float v0 = __uint_as_float(core.x);
+	const uint32_t flags = LM_FLAGS(meta);
 	if (!(flags & SAUABI_LINEP_GOAL)) {
 		const bool um = m && (flags & SAUABI_LINEP_STATE_RATIO);
 #pragma unroll
-		for (int k = 0; k < SPL; ++k) out[k] = um ? r.v0 * m[k] : r.v0;
+		for (int k = 0; k < NS; ++k) out[k] = um ? v0 * m[k] : v0;
 		return;
 	}
-	sau::LineFill f;
-	int t = (int) LM_TYPE(r.meta);
-	if (t == sau::L_exp) t = (r.v0 > r.vt) ? sau::L_xpe : sau::L_lge;
-	else if (t == sau::L_log) t = (r.v0 < r.vt) ? sau::L_xpe : sau::L_lge;
-	f.type = t;
-	f.v0 = r.v0; f.vt = r.vt;
-	f.pos = r.pos + c.oc;
-	f.adj_pos = (int32_t) (f.pos - (r.end / 2));
-	f.inv = r.inv;
-	f.vm = (r.v0 + r.vt) * 0.5f;
-	f.vd = r.vt - r.v0;
-	f.c = 0.f;
-	const uint32_t i0 = c.lane * SPL;
-	switch (t) {
-	default:
-	case sau::L_sah: line_fill4<sau::L_sah>(f, i0, out); break;
-	case sau::L_lin: f.c = f.vd * f.inv; line_fill4<sau::L_lin>(f, i0, out); break;
-	case sau::L_cos: line_fill4<sau::L_cos>(f, i0, out); break;
-	case sau::L_xpe: f.c = r.v0 - r.vt; line_fill4<sau::L_xpe>(f, i0, out); break;
-	case sau::L_lge: line_fill4<sau::L_lge>(f, i0, out); break;
-	case sau::L_sqe: f.c = r.v0 - r.vt; line_fill4<sau::L_sqe>(f, i0, out); break;
-	case sau::L_cub: f.inv = -2.f * f.inv; f.c = (r.v0 - r.vt) * 0.5f; line_fill4<sau::L_cub>(f, i0, out); break;
-	case sau::L_smo: line_fill4<sau::L_smo>(f, i0, out); break;
-	case sau::L_uwh: f.c = f.vd * (0.5f / 2147483648.f); line_fill4<sau::L_uwh>(f, i0, out); break;
-	case sau::L_ncl: line_fill4<sau::L_ncl>(f, i0, out); break;
-	case sau::L_nhl: line_fill4<sau::L_nhl>(f, i0, out); break;
+	const float inv = lds32f(op + OS_LINV + 4 * li);
+#pragma unroll
+	for (int h = 0; h < NS / 4; ++h) {
+		const float4 t = line_goal_fill(v0, __uint_as_float(core.y), inv,
+				core.z + c.oc + c.lane * NS + 4 * h, core.w, LM_TYPE(meta));
+		out[4 * h] = t.x; out[4 * h + 1] = t.y; out[4 * h + 2] = t.z; out[4 * h + 3] = t.w;
 	}
 	if (m && (flags & SAUABI_LINEP_GOAL_RATIO)) {
 #pragma unroll
-		for (int k = 0; k < SPL; ++k) out[k] = out[k] * m[k];
+		for (int k = 0; k < NS; ++k) out[k] = out[k] * m[k];
 	}
 }
 
-/* TAIL of a wave operator on a steady full chunk; fr = its frequency values */
-__device__ __forceinline__ void wtail_fast(const FastCtx &c, const Instr &in, OpState *o,
-		const float fr[SPL]) {
-	const uint4 og = *reinterpret_cast<const uint4*>(&o->time);
-	const float4 pg = *reinterpret_cast<const float4*>(&o->prev_Is);
-	const uint32_t wave = (og.y >> 16) & 0xffu;
-	const double prev_Is = __hiloint2double(__float_as_int(pg.y), __float_as_int(pg.x));
-	__syncwarp();              /* every lane holds the accumulators before lane 31 rewrites them */
-	float pm[SPL], fpm[SPL];
-	if (in.c != NO_BUF) fld4(c, in.c, pm);
-	if (in.d != NO_BUF) fld4(c, in.d, fpm);
-	uint32_t ph[SPL];
-	phasor_eval<true>(c, o, og.z, fr, in.c != NO_BUF ? pm : nullptr,
-			in.d != NO_BUF ? fpm : nullptr, CHUNK, ph);
-	float s[SPL];
-	if (!wosc_eval_full(c, o, wave, og.w, prev_Is, ph, s)) {
-		ColdCtx k; k.tab = c.tab; k.wc = c.wc; k.wave_mask = c.wave_mask; k.lane = c.lane;
-		const float4 t = wosc_eval_any(k, o, make_uint4(ph[0], ph[1], ph[2], ph[3]), CHUNK);
-		s[0] = t.x; s[1] = t.y; s[2] = t.z; s[3] = t.w;
+/* sauWOsc_run over a full chunk when some phase difference is zero (the output
+ * then repeats, wosc.h:251-252): same scheme as wosc_eval_any, NS samples per
+ * lane, by value. */
+template <int NS> struct PhaseVec { uint32_t v[NS]; };
+template <int NS> struct SampVec { float v[NS]; };
+template <int NS>
+__device__ __noinline__ SampVec<NS> wosc_zero_diff(const ColdCtx c, OpState *o, const PhaseVec<NS> phv) {
+	const uint32_t *ph = phv.v;
+	SampVec<NS> sv;
+	float *s = sv.v;
+	const uint32_t wave = o->mode;
+	const float *lut = wave_lut(c, wave);
+	const float ds = c.wc->diff_scale[wave], doff = c.wc->diff_offset[wave];
+	const uint32_t prev_phase = o->i1;
+	const double prev_Is = o->prev_Is;
+	const float prev_s = o->prev_s;
+	double Is[NS];
+#pragma unroll
+	for (int k = 0; k < NS; ++k) Is[k] = sau::herp(lut, ph[k], (double*) 0, (double*) 0);
+	uint32_t pph = __shfl_up_sync(FULL, ph[NS - 1], 1);
+	double pIs = __shfl_up_sync(FULL, Is[NS - 1], 1);
+	if (c.lane == 0) { pph = prev_phase; pIs = prev_Is; }
+	bool zd[NS];
+	bool lead_zero = false, has_nz = false;
+	float s_run = 0.f;
+#pragma unroll
+	for (int k = 0; k < NS; ++k) {
+		const int32_t d = (int32_t) (ph[k] - pph);
+		zd[k] = d == 0;
+		if (d != 0) {
+			s_run = sau::wosc_diff(Is[k], pIs, d, ds, doff);
+			has_nz = true;
+		}
+		if (zd[k] && !has_nz) lead_zero = true;
+		s[k] = s_run;
+		pph = ph[k]; pIs = Is[k];
 	}
-	float am[SPL];
-	line_value_steady(c, o, LINE_AMP, nullptr, am);
+	const uint32_t any_lead = __ballot_sync(FULL, lead_zero);
+	if (any_lead) {
+		const uint32_t nzmask = __ballot_sync(FULL, has_nz);
+		const uint32_t lower = nzmask & ((1u << c.lane) - 1u);
+		const int src = lower ? (31 - __clz(lower)) : 0;
+		float inc = __shfl_sync(FULL, s_run, src);
+		if (!lower) inc = prev_s;
+		bool seen = false;
+#pragma unroll
+		for (int k = 0; k < NS; ++k) {
+			if (!zd[k]) seen = true;
+			if (!seen) s[k] = inc;
+		}
+	}
+	__syncwarp();
+	if (c.lane == 31) { o->i1 = ph[NS - 1]; o->prev_Is = Is[NS - 1]; o->prev_s = s[NS - 1]; }
+	return sv;
+}
+
+/* TAIL of a wave operator on a steady full chunk: phase fill, oscillator,
+ * amplitude line, block_mix (generator.c:584-601); fr = its frequency values */
+template <int NS>
+__device__ __forceinline__ void wtail_fast(const FastCtx &c, const Instr &in, uint32_t op,
+		const float fr[NS]) {
+	const uint4 og = lds128u(op + OS_TIME);      /* time, type|flags|mode|oscflags, i0, i1 */
+	const uint4 pg = lds128u(op + OS_PREV);      /* prev_Is lo/hi, prev_s, fb_s */
+	const uint32_t wave = (og.y >> 16) & 0xffu;
+	__syncwarp();              /* every lane holds the accumulators before lane 31 rewrites them */
+	/* sauPhasor_fill, wosc.h:135-169 */
+	uint32_t ph[NS];
+	{
+		uint32_t run = 0;
+#pragma unroll
+		for (int k = 0; k < NS; ++k) {
+			run += ftoi_lo32(c.coeff * fr[k]);
+			ph[k] = run;
+		}
+		const uint32_t incl = scan_incl_u32(run, c.lane);
+		const uint32_t base = og.z + (incl - run);
+#pragma unroll
+		for (int k = 0; k < NS; ++k) ph[k] += base;
+		if (c.lane == 31) sts32(op + OS_I0, og.z + incl);
+		const bool has_pm = in.c != NO_BUF, has_fpm = in.d != NO_BUF;
+		if (has_pm && has_fpm) {
+			float pm[NS], fpm[NS];
+			fld<NS>(c, in.c, pm); fld<NS>(c, in.d, fpm);
+#pragma unroll
+			for (int k = 0; k < NS; ++k)
+				ph[k] += ftoi_lo32((((fpm[k] * fr[k]) * SAU_FPM_SCALE) + pm[k]) * 2147483648.f);
+		} else if (has_pm) {
+			float pm[NS];
+			fld<NS>(c, in.c, pm);
+#pragma unroll
+			for (int k = 0; k < NS; ++k) ph[k] += ftoi_lo32(pm[k] * 2147483648.f);
+		} else if (has_fpm) {
+			float fpm[NS];
+			fld<NS>(c, in.d, fpm);
+#pragma unroll
+			for (int k = 0; k < NS; ++k)
+				ph[k] += ftoi_lo32((fpm[k] * fr[k]) * (SAU_FPM_SCALE * 2147483648.f));
+		}
+	}
+	/* sauWOsc_run, wosc.h:238-266 */
+	float s[NS];
+	{
+		const uint32_t slot = __popc(c.wave_mask & ((1u << wave) - 1u));
+		const uint32_t taps = c.st + slot * (TAB_STRIDE * 4) + 12;    /* &lut[-1] */
+		double Is[NS];
+#pragma unroll
+		for (int k = 0; k < NS; ++k) {
+			const uint32_t a = taps + ((ph[k] >> sau::WAVE_SLENBITS) << 2);
+			const float s0 = lds32f(a), s1 = lds32f(a + 4), s2 = lds32f(a + 8), s3 = lds32f(a + 12);
+			Is[k] = sau::herp_poly(s0, s1, s2, s3, ph[k]) + (double) s1;
+		}
+		uint32_t pph = __shfl_up_sync(FULL, ph[NS - 1], 1);
+		double pIs = __shfl_up_sync(FULL, Is[NS - 1], 1);
+		if (c.lane == 0) {
+			pph = og.w;
+			pIs = __hiloint2double((int) pg.y, (int) pg.x);
+		}
+		int32_t d[NS];
+		d[0] = (int32_t) (ph[0] - pph);
+#pragma unroll
+		for (int k = 1; k < NS; ++k) d[k] = (int32_t) (ph[k] - ph[k - 1]);
+		bool z = false;
+#pragma unroll
+		for (int k = 0; k < NS; ++k) z |= (d[k] == 0);
+		if (__any_sync(FULL, z)) {
+			ColdCtx cc; cc.tab = c.tab; cc.wc = c.wc; cc.wave_mask = c.wave_mask; cc.lane = c.lane;
+			PhaseVec<NS> pv;
+#pragma unroll
+			for (int k = 0; k < NS; ++k) pv.v[k] = ph[k];
+			OpState *o = reinterpret_cast<OpState*>(__cvta_shared_to_generic(op));
+			const SampVec<NS> sv = wosc_zero_diff<NS>(cc, o, pv);
+#pragma unroll
+			for (int k = 0; k < NS; ++k) s[k] = sv.v[k];
+		} else {
+			const float ds = c.wc->diff_scale[wave];
+			const double doff = (double) c.wc->diff_offset[wave];
+#pragma unroll
+			for (int k = 0; k < NS; ++k) {                           /* wosc.h:254-256 */
+				const float xq = div_scale_by_int(ds, d[k]);
+				const double dI = Is[k] - (k ? Is[k - 1] : pIs);
+				s[k] = (float) (dI * (double) xq + doff);
+			}
+			if (c.lane == 31) {
+				sts32(op + OS_I1, ph[NS - 1]);
+				sts128(op + OS_PREV, make_float4(__int_as_float(__double2loint(Is[NS - 1])),
+						__int_as_float(__double2hiint(Is[NS - 1])), s[NS - 1], __uint_as_float(pg.w)));
+			}
+		}
+	}
+	float am[NS];
+	line_value_steady<NS>(c, op, LINE_AMP, nullptr, am);
 	const bool layer = (in.flags & F_LAYER) != 0;      /* F_LAYER_PMA: no self-PM here */
-	float ov[SPL];
-	if (layer) fld4(c, in.a, ov);
+	float ov[NS];
+	if (layer) fld<NS>(c, in.a, ov);
 	if (in.flags & F_WAVEENV) {                                   /* generator.c:407-426 */
 #pragma unroll
-		for (int k = 0; k < SPL; ++k) {
+		for (int k = 0; k < NS; ++k) {
 			const float s_amp = am[k] * 0.5f;
 			const float v = (s[k] * s_amp) + fabsf(s_amp);
 			ov[k] = layer ? ov[k] * v : v;
 		}
 	} else {                                                      /* generator.c:384-397 */
 #pragma unroll
-		for (int k = 0; k < SPL; ++k) {
+		for (int k = 0; k < NS; ++k) {
 			const float v = s[k] * am[k];
 			ov[k] = layer ? ov[k] + v : v;
 		}
 	}
-	fst4(c, in.a, ov);
+	fst<NS>(c, in.a, ov);
 	__syncwarp();
 }
 
+template <int NS>
 __device__ __forceinline__ void run_chunk_fast(const FastCtx &c, const Instr *code,
 		uint32_t code_len, float *row_s, float *row_r) {
 	for (uint32_t pc = 0; pc < code_len; ++pc) {
 		const uint4 raw = __ldg(reinterpret_cast<const uint4*>(code + pc));
 		Instr in;
 		memcpy(&in, &raw, sizeof(in));
-		OpState *o = c.sops + in.op;
+		const uint32_t op = c.so + in.op * (uint32_t) sizeof(OpState);
 		switch (in.opcode) {
-		case I_WLEAF: case I_WHEAD: {
-			float fr[SPL], m[SPL];
-			const bool has_mul = in.e != NO_BUF;
-			if (has_mul) fld4(c, in.e, m);
-			line_value_steady(c, o, LINE_FREQ, has_mul ? m : nullptr, fr);
-			if (in.opcode == I_WHEAD) fst4(c, in.b, fr);
-			else wtail_fast(c, in, o, fr);
-			break; }
-		case I_WTAIL: {
-			float fr[SPL];
-			fld4(c, in.b, fr);
-			wtail_fast(c, in, o, fr);
-			break; }
-		case I_LINE:
-			if (in.d) {
-				float out[SPL], m[SPL];
-				const bool has_mul = in.b != NO_BUF;
-				if (has_mul) fld4(c, in.b, m);
-				line_value_steady(c, o, in.c, has_mul ? m : nullptr, out);
-				fst4(c, in.a, out);
+		case I_WLEAF: case I_WHEAD: case I_WTAIL: case I_LINE: {
+			/* one line evaluation (frequency, or the LINE's own), then the tail */
+			const bool is_line = in.opcode == I_LINE;
+			if (is_line && !in.d) break;
+			float fr[NS];
+			if (in.opcode == I_WTAIL) {
+				fld<NS>(c, in.b, fr);
+			} else {
+				float m[NS];
+				const uint32_t mb = is_line ? in.b : in.e;
+				const bool has_mul = mb != NO_BUF;
+				if (has_mul) fld<NS>(c, mb, m);
+				line_value_steady<NS>(c, op, is_line ? (int) in.c : (int) LINE_FREQ,
+						has_mul ? m : nullptr, fr);
+				if (is_line) { fst<NS>(c, in.a, fr); break; }
+				if (in.opcode == I_WHEAD) { fst<NS>(c, in.b, fr); break; }
 			}
-			break;
+			wtail_fast<NS>(c, in, op, fr);
+			break; }
 		case I_RANGE: {                                            /* generator.c:465-467 */
-			float4 p = *FB4(c, in.a);
-			const float4 r = *FB4(c, in.b), m = *FB4(c, in.c);
-			p.x += (r.x - p.x) * m.x;
-			p.y += (r.y - p.y) * m.y;
-			p.z += (r.z - p.z) * m.z;
-			p.w += (r.w - p.w) * m.w;
-			*FB4(c, in.a) = p;
+			float p[NS], r[NS], m[NS];
+			fld<NS>(c, in.a, p); fld<NS>(c, in.b, r); fld<NS>(c, in.c, m);
+#pragma unroll
+			for (int k = 0; k < NS; ++k) p[k] += (r[k] - p[k]) * m[k];
+			fst<NS>(c, in.a, p);
 			break; }
 		case I_VOUT: {                                             /* generator.c:772-786 */
-			const float amp_scale = c.amp_scale;
-			const float4 sv = *FB4(c, in.a);
-			const float p = o->line[LINE_PAN].v0;
-			float4 s, r;
-			s.x = sv.x * amp_scale; r.x = s.x * p;
-			s.y = sv.y * amp_scale; r.y = s.y * p;
-			s.z = sv.z * amp_scale; r.z = s.z * p;
-			s.w = sv.w * amp_scale; r.w = s.w * p;
-			const uint32_t i0 = c.lane * SPL;
+			float sv[NS];
+			fld<NS>(c, in.a, sv);
+			const float pan = lds32f(op + OS_LINE + 16 * LINE_PAN);
+			float s[NS], r[NS];
+#pragma unroll
+			for (int k = 0; k < NS; ++k) { s[k] = sv[k] * c.amp_scale; r[k] = s[k] * pan; }
+			const uint32_t i0 = c.lane * NS;
 			if ((reinterpret_cast<uintptr_t>(row_s) & 15) == 0) {
-				__stcs(reinterpret_cast<float4*>(row_s + i0), s);   /* coalesced 128-bit stores */
-				__stcs(reinterpret_cast<float4*>(row_r + i0), r);
+#pragma unroll
+				for (int h = 0; h < NS / 4; ++h) {                   /* 128-bit streaming stores */
+					__stcs(reinterpret_cast<float4*>(row_s + i0) + h,
+							make_float4(s[4 * h], s[4 * h + 1], s[4 * h + 2], s[4 * h + 3]));
+					__stcs(reinterpret_cast<float4*>(row_r + i0) + h,
+							make_float4(r[4 * h], r[4 * h + 1], r[4 * h + 2], r[4 * h + 3]));
+				}
 			} else {
-				row_s[i0 + 0] = s.x; row_r[i0 + 0] = r.x;
-				row_s[i0 + 1] = s.y; row_r[i0 + 1] = r.y;
-				row_s[i0 + 2] = s.z; row_r[i0 + 2] = r.z;
-				row_s[i0 + 3] = s.w; row_r[i0 + 3] = r.w;
+#pragma unroll
+				for (int k = 0; k < NS; ++k) { row_s[i0 + k] = s[k]; row_r[i0 + k] = r[k]; }
 			}
 			return; }
 		default:                   /* ENTER, VPAN, END: nothing to do per chunk */
@@ -1650,7 +1847,7 @@ __device__ __forceinline__ void render_body(const CallDesc *calls, uint32_t ncal
 	Ctx c;
 	c.sops = reinterpret_cast<OpState*>(warp_area + warp * per_warp);
 	c.bufs = reinterpret_cast<float*>(c.sops + nslots_ops);
-	c.stk_len = reinterpret_cast<uint32_t*>(c.bufs + nbufs * CHUNK);
+	c.stk_len = reinterpret_cast<uint32_t*>(c.bufs + nbufs * BUF_FLOATS);
 	c.stk_rem = c.stk_len + MAX_NEST;
 	c.stk_layer = c.stk_rem + MAX_NEST;
 	c.tab = tab;
@@ -1662,6 +1859,8 @@ __device__ __forceinline__ void render_body(const CallDesc *calls, uint32_t ncal
 	c.wave_mask = wave_mask;
 	c.lane = lane;
 
+	const WaveCoeffs *wc_g = c.wc;
+	const float coeff_g = g->coeff, amp_scale_g = g->amp_scale;
 	VoiceState *vsp = &g->voices[v];
 	VoiceState vs = *vsp;
 	const uint32_t ev_lo = g->vev_off[v], ev_n = g->vev_off[v + 1] - ev_lo;
@@ -1701,12 +1900,15 @@ __device__ __forceinline__ void render_body(const CallDesc *calls, uint32_t ncal
 					op_ptr(c, vs.carr_slot)->time > 0 &&
 					steady_check(c.sops, g->code + vs.code_off, vs.code_len)) {
 				FastCtx fc;
-				fc.bufs = c.bufs; fc.sops = c.sops; fc.tab = c.tab; fc.wc = c.wc;
-				fc.coeff = c.coeff; fc.amp_scale = g->amp_scale;
+				fc.so = smem_u32(c.sops);
+				fc.sb = smem_u32(c.bufs) + lane * 16;
+				fc.st = smem_u32(tab);
+				fc.tab = tab; fc.wc = wc_g;
+				fc.coeff = coeff_g; fc.amp_scale = amp_scale_g;
 				fc.wave_mask = wave_mask; fc.lane = lane;
-				for (uint32_t oc = 0; oc < (uint32_t) REF_BLOCK; oc += CHUNK) {
+				for (uint32_t oc = 0; oc < (uint32_t) REF_BLOCK; oc += FastCfg<FAST_NS>::CHUNKF) {
 					fc.oc = oc;
-					run_chunk_fast(fc, g->code + vs.code_off, vs.code_len,
+					run_chunk_fast<FAST_NS>(fc, g->code + vs.code_off, vs.code_len,
 							row_s + sd.start + off + oc, row_r + sd.start + off + oc);
 				}
 				__syncwarp();
@@ -1744,7 +1946,7 @@ __device__ __forceinline__ void render_body(const CallDesc *calls, uint32_t ncal
 	}
 }
 
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, 2)
 render_kernel(const CallDesc *calls, uint32_t ncalls, const SegDesc *segs, uint32_t ntasks,
 		const float *tables, uint32_t wave_mask, uint32_t nbufs, uint32_t nslots_ops,
 		uint32_t warps_per_cta) {
