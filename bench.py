@@ -204,8 +204,9 @@ def run_gpu_arm(args):
         return float(t.item())
 
     # ---- device-resident throughput: PCM stays in HBM ----
+    sched = int(os.environ.get("SAUGEN_BENCH_SCHED", "0"))   # developer knob; 0 = auto
     g = saugns_b200.Generator(prg, SRATE, device=local_rank, stream=stream.cuda_stream,
-                              max_call_len=FRAMES)
+                              max_call_len=FRAMES, sched=sched)
     for _ in range(W):
         g.run_device(FRAMES)
     g.set_timing(True)

@@ -163,6 +163,8 @@ struct GenDesc {
 	uint32_t *vlen;               // [seg][n_local_voices] frames run per segment of a call
 	uint32_t *status;             // [0]=any voice still alive, [1+seg]=per-segment max len
 	uint32_t vlen_cap;            // segments the vlen/status arrays can hold
+	uint32_t *progress;           // [n_local_voices] units done in the current call (ticketed launches)
+	uint32_t *ticket;             // next (unit, voice) ticket of the current call
 	float *mix;                   // [2][row_len] float mix planes (L, R)
 	int16_t *pcm;                 // [row_len*2]
 	uint32_t vo_count, op_count;
@@ -192,6 +194,14 @@ struct SegDesc {
 	uint32_t ev_end;   // events with index < ev_end are due at the segment start
 };
 
+/* A schedulable stretch of a segment: starts at a multiple of REF_BLOCK inside
+ * the segment. */
+struct UnitDesc {
+	uint32_t seg;      // segment index inside the call
+	uint32_t off;      // frame offset inside the segment
+	uint32_t len;
+};
+
 /* One sauGenerator_run call of one generator. */
 struct CallDesc {
 	const GenDesc *gen;
@@ -200,6 +210,8 @@ struct CallDesc {
 	uint32_t seg_off;      // first SegDesc of this call
 	uint32_t task_base;    // index of this call's first voice task in the launch
 	uint32_t stereo;
+	uint32_t unit_off;     // first UnitDesc of this call
+	uint32_t nunits;
 	uint32_t _pad;
 };
 

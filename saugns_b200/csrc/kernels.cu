@@ -1013,7 +1013,16 @@ __device__ __noinline__ void apply_event(const GenDesc *g, const WaveCoeffs *wc,
 		VoiceState *vs) {
 	for (uint32_t i = 0; i < ev->opdata_count; ++i) {
 		const OpDataRec *od = &g->opdata[ev->opdata_off + i];
-		OpState *n = &g->ops[od->id];
+		/* work on a copy read from / written to L2: under the ticketed scheduler the
+		 * operator may last have been stored by another SM */
+		OpState *gn = &g->ops[od->id];
+		OpState stv;
+		{
+			uint4 *d = reinterpret_cast<uint4*>(&stv);
+			for (uint32_t w = 0; w < sizeof(OpState) / 16; ++w)
+				d[w] = __ldcg(reinterpret_cast<const uint4*>(gn) + w);
+		}
+		OpState *n = &stv;
 		if (!(n->flags & ON_INIT)) {                               /* prepare_op, :245-278 */
 			OpState z;
 			memset(&z, 0, sizeof(z));
@@ -1090,6 +1099,11 @@ __device__ __noinline__ void apply_event(const GenDesc *g, const WaveCoeffs *wc,
 		dev_line_copy(n, LINE_AMP, &od->line[LINE_AMP]);
 		dev_line_copy(n, LINE_AMP2, &od->line[LINE_AMP2]);
 		dev_line_copy(n, LINE_PAN, &od->line[LINE_PAN]);
+		{
+			const uint4 *s = reinterpret_cast<const uint4*>(&stv);
+			for (uint32_t w = 0; w < sizeof(OpState) / 16; ++w)
+				__stcg(reinterpret_cast<uint4*>(gn) + w, s[w]);
+		}
 	}
 	vs->carr_op = ev->carr_op_id;
 	vs->flags |= VN_INIT;
@@ -1098,7 +1112,8 @@ __device__ __noinline__ void apply_event(const GenDesc *g, const WaveCoeffs *wc,
 	vs->ops_off = ev->ops_off;
 	vs->ops_cnt = ev->ops_cnt;
 	vs->carr_slot = ev->carr_slot;
-	vs->duration = g->ops[vs->carr_op].time;                       /* set_voice_duration */
+	vs->duration = __ldcg(&g->ops[vs->carr_op].time);              /* set_voice_duration */
+	__threadfence();
 }
 
 /* ---- bytecode interpreter: one chunk of one voice ----------------------- */
@@ -1767,6 +1782,16 @@ __device__ __forceinline__ void run_chunk_fast(const FastCtx &c, const Instr *co
 	}
 }
 
+/* One steady reference block: its own function, so that the hot loop gets its
+ * own register allocation whatever the general path around the call needs. */
+__device__ __noinline__ void run_block_fast(FastCtx fc, const Instr *code, uint32_t code_len,
+		float *row_s, float *row_r) {
+	for (uint32_t oc = 0; oc < (uint32_t) REF_BLOCK; oc += FastCfg<FAST_NS>::CHUNKF) {
+		fc.oc = oc;
+		run_chunk_fast<FAST_NS>(fc, code, code_len, row_s + oc, row_r + oc);
+	}
+}
+
 /* ---- render kernel ------------------------------------------------------ */
 
 constexpr uint32_t OP_VEC = sizeof(OpState) / 16;
@@ -1777,7 +1802,7 @@ __device__ __forceinline__ void ops_load(Ctx &c, uint32_t cnt) {
 	uint4 *dst = reinterpret_cast<uint4*>(c.sops);
 	for (uint32_t i = c.lane; i < cnt * OP_VEC; i += 32) {
 		const uint32_t slot = i / OP_VEC, w = i % OP_VEC;
-		dst[i] = reinterpret_cast<const uint4*>(c.gops + c.prog_ops[slot])[w];
+		dst[i] = __ldcg(reinterpret_cast<const uint4*>(c.gops + c.prog_ops[slot]) + w);
 	}
 	__syncwarp();
 }
@@ -1786,14 +1811,123 @@ __device__ __forceinline__ void ops_store(Ctx &c, uint32_t cnt) {
 	const uint4 *src = reinterpret_cast<const uint4*>(c.sops);
 	for (uint32_t i = c.lane; i < cnt * OP_VEC; i += 32) {
 		const uint32_t slot = i / OP_VEC, w = i % OP_VEC;
-		reinterpret_cast<uint4*>(c.gops + c.prog_ops[slot])[w] = src[i];
+		__stcg(reinterpret_cast<uint4*>(c.gops + c.prog_ops[slot]) + w, src[i]);
 	}
 	__syncwarp();
 }
 
+/* Units [u0, u1) of one voice of one call.  A unit is a stretch of one
+ * inter-event segment, starting at a multiple of REF_BLOCK inside it (the
+ * reference's own block grid, generator.c:854-878). */
+__device__ __forceinline__ void render_units(Ctx &c, FastCtx &fc, const CallDesc *cd,
+		const SegDesc *segs, const UnitDesc *units, uint32_t lv, uint32_t u0, uint32_t u1) {
+	const GenDesc *g = cd->gen;
+	const int lane = c.lane;
+	const uint32_t v = g->voice_begin + lv;
+	const uint32_t nlv = g->voice_end - g->voice_begin;
+	c.g = g;
+	c.gops = g->ops;
+	c.coeff = g->coeff;
+	fc.coeff = g->coeff; fc.amp_scale = g->amp_scale;
+	VoiceState *vsp = &g->voices[v];
+	VoiceState vs;
+	{
+		/* lane 0 reads (from L2: another SM may have written it), every lane gets
+		 * the same copy */
+		const uint32_t *src = reinterpret_cast<const uint32_t*>(vsp);
+		uint32_t *dst = reinterpret_cast<uint32_t*>(&vs);
+#pragma unroll
+		for (uint32_t i = 0; i < sizeof(VoiceState) / 4; ++i) {
+			uint32_t w = 0;
+			if (lane == 0) w = __ldcg(src + i);
+			dst[i] = __shfl_sync(FULL, w, 0);
+		}
+	}
+	const uint32_t ev_lo = g->vev_off[v], ev_n = g->vev_off[v + 1] - ev_lo;
+	float *row_s = g->rows_s + (size_t) lv * g->row_len;
+	float *row_r = g->rows_r + (size_t) lv * g->row_len;
+	uint32_t loaded = 0;        // operator states currently held in shared memory
+
+	for (uint32_t ui = u0; ui < u1; ++ui) {
+		const UnitDesc ud = units[cd->unit_off + ui];
+		const uint32_t si = ud.seg;
+		const SegDesc sd = segs[cd->seg_off + si];
+		/* this voice's events due at the segment start, in order */
+		if (ud.off == 0 && vs.ev_cursor < ev_n && g->vev_idx[ev_lo + vs.ev_cursor] < sd.ev_end) {
+			if (loaded) { ops_store(c, loaded); loaded = 0; }
+			while (vs.ev_cursor < ev_n && g->vev_idx[ev_lo + vs.ev_cursor] < sd.ev_end) {
+				if (lane == 0) {
+					apply_event(g, c.wc, &g->events[g->vev_idx[ev_lo + vs.ev_cursor]], &vs);
+					vs.ev_cursor++;
+				}
+				__syncwarp();
+				uint32_t *w = reinterpret_cast<uint32_t*>(&vs);
+#pragma unroll
+				for (uint32_t i = 0; i < sizeof(VoiceState) / 4; ++i) w[i] = __shfl_sync(FULL, w[i], 0);
+			}
+		}
+		if (vs.duration == 0 || ud.len == 0) continue;
+		c.prog_ops = g->prog_ops + vs.ops_off;
+		if (!loaded && vs.ops_cnt > 0) {
+			ops_load(c, vs.ops_cnt);
+			loaded = vs.ops_cnt;
+		}
+		uint32_t run_total = 0;
+		const uint32_t uend = ud.off + ud.len;
+		for (uint32_t off = ud.off; off < uend && vs.duration != 0; off += CHUNK) {
+			/* a whole reference block in steady state: the fast path */
+			if (off % REF_BLOCK == 0 && uend - off >= (uint32_t) REF_BLOCK &&
+					vs.duration >= (uint32_t) REF_BLOCK && vs.code_len &&
+					op_ptr(c, vs.carr_slot)->time > 0 &&
+					steady_check(c.sops, g->code + vs.code_off, vs.code_len)) {
+				run_block_fast(fc, g->code + vs.code_off, vs.code_len,
+						row_s + sd.start + off, row_r + sd.start + off);
+				__syncwarp();
+				if (lane == 0) steady_update(c.sops, g->code + vs.code_off, vs.code_len);
+				__syncwarp();
+				vs.duration -= REF_BLOCK;
+				run_total += REF_BLOCK;
+				off += REF_BLOCK - CHUNK;
+				continue;
+			}
+			uint32_t clen = uend - off;
+			if (clen > (uint32_t) CHUNK) clen = CHUNK;
+			const uint32_t time = vs.duration < clen ? vs.duration : clen;
+			c.oc = off % REF_BLOCK;
+			uint32_t rem0 = vs.duration;
+			if (sd.len - off < rem0) rem0 = sd.len - off;
+			if (REF_BLOCK - c.oc < rem0) rem0 = REF_BLOCK - c.oc;
+			uint32_t out_len = 0;
+			if (vs.code_len && op_ptr(c, vs.carr_slot)->time > 0)     /* run_voice, :833-846 */
+				out_len = run_chunk(c, g->code + vs.code_off, vs.code_len, time, rem0,
+						row_s + sd.start + off, row_r + sd.start + off);
+			__syncwarp();
+			vs.duration -= time;
+			run_total += out_len;
+		}
+		if (lane == 0 && run_total) {
+			/* frames this voice has run in the segment so far (units of a voice are
+			 * rendered in order, by one warp at a time) */
+			uint32_t *vl = g->vlen + (size_t) si * nlv + lv;
+			const uint32_t tot = __ldcg(vl) + run_total;
+			*vl = tot;
+			atomicMax(&g->status[1 + si], tot);
+		}
+	}
+	if (loaded) ops_store(c, loaded);
+	if (lane == 0) {
+		const uint32_t *w = reinterpret_cast<const uint32_t*>(&vs);
+#pragma unroll
+		for (uint32_t i = 0; i < sizeof(VoiceState) / 4; ++i)
+			__stcg(reinterpret_cast<uint32_t*>(vsp) + i, w[i]);
+		if (u1 == cd->nunits && vs.duration != 0) atomicOr(&g->status[0], 1u);
+	}
+}
+
 __device__ __forceinline__ void render_body(const CallDesc *calls, uint32_t ncalls,
-		const SegDesc *segs, uint32_t ntasks, const float *tables, uint32_t wave_mask,
-		uint32_t nbufs, uint32_t nslots_ops, uint32_t warps_per_cta) {
+		const SegDesc *segs, const UnitDesc *units, uint32_t ntasks, const float *tables,
+		uint32_t wave_mask, uint32_t nbufs, uint32_t nslots_ops, uint32_t warps_per_cta,
+		uint32_t ticketed) {
 	extern __shared__ __align__(128) unsigned char smem[];
 	uint64_t *bar = reinterpret_cast<uint64_t*>(smem);
 	float *tab = reinterpret_cast<float*>(smem + 128);
@@ -1830,20 +1964,6 @@ __device__ __forceinline__ void render_body(const CallDesc *calls, uint32_t ncal
 		__syncthreads();
 	}
 
-	const uint32_t task = blockIdx.x * warps_per_cta + warp;
-	if (task >= ntasks) return;
-	/* task -> (call, voice): binary search on task_base */
-	uint32_t ci = 0, hi = ncalls;
-	while (hi - ci > 1) {
-		const uint32_t mid = (ci + hi) >> 1;
-		if (calls[mid].task_base <= task) ci = mid; else hi = mid;
-	}
-	const CallDesc *cd = &calls[ci];
-	const GenDesc *g = cd->gen;
-	const uint32_t lv = task - cd->task_base;           // local voice index
-	const uint32_t v = g->voice_begin + lv;
-	const uint32_t nlv = g->voice_end - g->voice_begin;
-
 	Ctx c;
 	c.sops = reinterpret_cast<OpState*>(warp_area + warp * per_warp);
 	c.bufs = reinterpret_cast<float*>(c.sops + nslots_ops);
@@ -1852,105 +1972,63 @@ __device__ __forceinline__ void render_body(const CallDesc *calls, uint32_t ncal
 	c.stk_layer = c.stk_rem + MAX_NEST;
 	c.tab = tab;
 	c.wc = reinterpret_cast<const WaveCoeffs*>(tables + NUM_WAVES * WAVE_LEN);
-	c.g = g;
-	c.gops = g->ops;
-	c.prog_ops = g->prog_ops;
-	c.coeff = g->coeff;
 	c.wave_mask = wave_mask;
 	c.lane = lane;
+	FastCtx fc;
+	fc.so = smem_u32(c.sops);
+	fc.sb = smem_u32(c.bufs) + lane * 16;
+	fc.st = smem_u32(tab);
+	fc.tab = tab; fc.wc = c.wc;
+	fc.wave_mask = wave_mask; fc.lane = lane;
 
-	const WaveCoeffs *wc_g = c.wc;
-	const float coeff_g = g->coeff, amp_scale_g = g->amp_scale;
-	VoiceState *vsp = &g->voices[v];
-	VoiceState vs = *vsp;
-	const uint32_t ev_lo = g->vev_off[v], ev_n = g->vev_off[v + 1] - ev_lo;
-	float *row_s = g->rows_s + (size_t) lv * g->row_len;
-	float *row_r = g->rows_r + (size_t) lv * g->row_len;
-	uint32_t loaded = 0;        // operator states currently held in shared memory
-
-	for (uint32_t si = 0; si < cd->nseg; ++si) {
-		const SegDesc sd = segs[cd->seg_off + si];
-		/* this voice's events due at the segment start, in order */
-		if (vs.ev_cursor < ev_n && g->vev_idx[ev_lo + vs.ev_cursor] < sd.ev_end) {
-			if (loaded) { ops_store(c, loaded); loaded = 0; }
-			while (vs.ev_cursor < ev_n && g->vev_idx[ev_lo + vs.ev_cursor] < sd.ev_end) {
-				if (lane == 0) {
-					apply_event(g, c.wc, &g->events[g->vev_idx[ev_lo + vs.ev_cursor]], &vs);
-					vs.ev_cursor++;
-					*vsp = vs;
-				}
-				__syncwarp();
-				vs = *vsp;
-			}
+	if (!ticketed) {
+		/* one warp renders every unit of one voice; task -> (call, voice) by
+		 * binary search on task_base */
+		const uint32_t task = blockIdx.x * warps_per_cta + warp;
+		if (task >= ntasks) return;
+		uint32_t ci = 0, hi = ncalls;
+		while (hi - ci > 1) {
+			const uint32_t mid = (ci + hi) >> 1;
+			if (calls[mid].task_base <= task) ci = mid; else hi = mid;
 		}
-		if (vs.duration == 0 || sd.len == 0) {
-			if (lane == 0) g->vlen[(size_t) si * nlv + lv] = 0;
-			continue;
-		}
-		c.prog_ops = g->prog_ops + vs.ops_off;
-		if (!loaded && vs.ops_cnt > 0) {
-			ops_load(c, vs.ops_cnt);
-			loaded = vs.ops_cnt;
-		}
-		uint32_t run_total = 0;
-		for (uint32_t off = 0; off < sd.len && vs.duration != 0; off += CHUNK) {
-			/* a whole reference block in steady state: the fast path */
-			if (off % REF_BLOCK == 0 && sd.len - off >= (uint32_t) REF_BLOCK &&
-					vs.duration >= (uint32_t) REF_BLOCK && vs.code_len &&
-					op_ptr(c, vs.carr_slot)->time > 0 &&
-					steady_check(c.sops, g->code + vs.code_off, vs.code_len)) {
-				FastCtx fc;
-				fc.so = smem_u32(c.sops);
-				fc.sb = smem_u32(c.bufs) + lane * 16;
-				fc.st = smem_u32(tab);
-				fc.tab = tab; fc.wc = wc_g;
-				fc.coeff = coeff_g; fc.amp_scale = amp_scale_g;
-				fc.wave_mask = wave_mask; fc.lane = lane;
-				for (uint32_t oc = 0; oc < (uint32_t) REF_BLOCK; oc += FastCfg<FAST_NS>::CHUNKF) {
-					fc.oc = oc;
-					run_chunk_fast<FAST_NS>(fc, g->code + vs.code_off, vs.code_len,
-							row_s + sd.start + off + oc, row_r + sd.start + off + oc);
-				}
-				__syncwarp();
-				if (lane == 0) steady_update(c.sops, g->code + vs.code_off, vs.code_len);
-				__syncwarp();
-				vs.duration -= REF_BLOCK;
-				run_total += REF_BLOCK;
-				off += REF_BLOCK - CHUNK;
-				continue;
-			}
-			uint32_t clen = sd.len - off;
-			if (clen > (uint32_t) CHUNK) clen = CHUNK;
-			const uint32_t time = vs.duration < clen ? vs.duration : clen;
-			c.oc = off % REF_BLOCK;
-			uint32_t rem0 = vs.duration;
-			if (sd.len - off < rem0) rem0 = sd.len - off;
-			if (REF_BLOCK - c.oc < rem0) rem0 = REF_BLOCK - c.oc;
-			uint32_t out_len = 0;
-			if (vs.code_len && op_ptr(c, vs.carr_slot)->time > 0)     /* run_voice, :833-846 */
-				out_len = run_chunk(c, g->code + vs.code_off, vs.code_len, time, rem0,
-						row_s + sd.start + off, row_r + sd.start + off);
-			__syncwarp();
-			vs.duration -= time;
-			run_total += out_len;
-		}
-		if (lane == 0) {
-			g->vlen[(size_t) si * nlv + lv] = run_total;
-			if (run_total) atomicMax(&g->status[1 + si], run_total);
-		}
+		const CallDesc *cd = &calls[ci];
+		render_units(c, fc, cd, segs, units, task - cd->task_base, 0, cd->nunits);
+		return;
 	}
-	if (loaded) ops_store(c, loaded);
-	if (lane == 0) {
-		*vsp = vs;
-		if (vs.duration != 0) atomicOr(&g->status[0], 1u);
+	/* Ticketed: a persistent grid hands out (unit, voice) pairs in time order, so
+	 * that SMs stay evenly loaded when there are more voices than resident warps.
+	 * Unit u of a voice may start once its unit u-1 is done (progress[], release /
+	 * acquire through global memory); the holder of every earlier ticket is
+	 * already running, so the wait always ends. */
+	const CallDesc *cd = &calls[0];
+	const GenDesc *g = cd->gen;
+	const uint32_t nlv = g->voice_end - g->voice_begin;
+	const uint32_t total = nlv * cd->nunits;
+	for (;;) {
+		uint32_t t = 0;
+		if (lane == 0) t = atomicAdd(g->ticket, 1u);
+		t = __shfl_sync(FULL, t, 0);
+		if (t >= total) break;
+		const uint32_t u = t / nlv, lv = t - u * nlv;
+		if (lane == 0) {
+			volatile uint32_t *pr = g->progress + lv;
+			while (*pr != u) __nanosleep(32);
+			__threadfence();
+		}
+		__syncwarp();
+		render_units(c, fc, cd, segs, units, lv, u, u + 1);
+		__threadfence();
+		__syncwarp();
+		if (lane == 0) *(volatile uint32_t*) (g->progress + lv) = u + 1;
 	}
 }
 
 __global__ void __launch_bounds__(256, 2)
-render_kernel(const CallDesc *calls, uint32_t ncalls, const SegDesc *segs, uint32_t ntasks,
-		const float *tables, uint32_t wave_mask, uint32_t nbufs, uint32_t nslots_ops,
-		uint32_t warps_per_cta) {
-	render_body(calls, ncalls, segs, ntasks, tables, wave_mask, nbufs, nslots_ops, warps_per_cta);
+render_kernel(const CallDesc *calls, uint32_t ncalls, const SegDesc *segs, const UnitDesc *units,
+		uint32_t ntasks, const float *tables, uint32_t wave_mask, uint32_t nbufs,
+		uint32_t nslots_ops, uint32_t warps_per_cta, uint32_t ticketed) {
+	render_body(calls, ncalls, segs, units, ntasks, tables, wave_mask, nbufs, nslots_ops,
+			warps_per_cta, ticketed);
 }
 
 /* ---- mix + clip epilogue ------------------------------------------------- */
@@ -2080,22 +2158,26 @@ size_t render_smem_bytes(uint32_t wave_mask, uint32_t nbufs, uint32_t nslots_ops
 		(size_t) warps * warp_smem_bytes(nbufs, nslots_ops);
 }
 
+/* grid: one warp per voice task, or (ticketed) a persistent grid of `grid_ctas` */
 cudaError_t launch_render(const CallDesc *d_calls, uint32_t ncalls, const SegDesc *d_segs,
-		uint32_t ntasks, const float *d_tables, uint32_t wave_mask, uint32_t nbufs,
-		uint32_t nslots_ops, uint32_t warps, cudaStream_t stream) {
+		const UnitDesc *d_units, uint32_t ntasks, const float *d_tables, uint32_t wave_mask,
+		uint32_t nbufs, uint32_t nslots_ops, uint32_t warps, uint32_t ticketed_ctas,
+		cudaStream_t stream) {
 	if (ntasks == 0) return cudaSuccess;
 	if (nslots_ops == 0) nslots_ops = 1;
 	const size_t smem = render_smem_bytes(wave_mask, nbufs, nslots_ops, warps);
-	static size_t configured = 0;
-	if (smem > configured) {
+	int dev = 0;
+	cudaGetDevice(&dev);
+	static size_t configured[64] = {0};
+	if (dev >= 0 && dev < 64 && smem > configured[dev]) {
 		cudaError_t e = cudaFuncSetAttribute(render_kernel,
 				cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
 		if (e != cudaSuccess) return e;
-		configured = smem;
+		configured[dev] = smem;
 	}
-	const uint32_t grid = (ntasks + warps - 1) / warps;
-	render_kernel<<<grid, warps * 32, smem, stream>>>(d_calls, ncalls, d_segs, ntasks,
-			d_tables, wave_mask, nbufs, nslots_ops, warps);
+	const uint32_t grid = ticketed_ctas ? ticketed_ctas : (ntasks + warps - 1) / warps;
+	render_kernel<<<grid, warps * 32, smem, stream>>>(d_calls, ncalls, d_segs, d_units, ntasks,
+			d_tables, wave_mask, nbufs, nslots_ops, warps, ticketed_ctas ? 1u : 0u);
 	return cudaGetLastError();
 }
 

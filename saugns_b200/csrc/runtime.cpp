@@ -28,8 +28,9 @@
 namespace saugen {
 size_t render_smem_bytes(uint32_t wave_mask, uint32_t nbufs, uint32_t nslots_ops, uint32_t warps);
 cudaError_t launch_render(const CallDesc *d_calls, uint32_t ncalls, const SegDesc *d_segs,
-		uint32_t ntasks, const float *d_tables, uint32_t wave_mask, uint32_t nbufs,
-		uint32_t nslots_ops, uint32_t warps, cudaStream_t stream);
+		const UnitDesc *d_units, uint32_t ntasks, const float *d_tables, uint32_t wave_mask,
+		uint32_t nbufs, uint32_t nslots_ops, uint32_t warps, uint32_t ticketed_ctas,
+		cudaStream_t stream);
 cudaError_t launch_mix(const CallDesc *d_calls, uint32_t ncalls, const SegDesc *d_segs,
 		uint32_t max_call_len, uint32_t mode, cudaStream_t stream);
 cudaError_t launch_planes_to_pcm(const float *d_mix, uint32_t plane_stride, uint32_t n,
@@ -107,7 +108,7 @@ struct saugen_Generator {
 	bool own_stream = false;
 	uint32_t vo_count = 0, op_count = 0, nlv = 0;
 	uint32_t voice_begin = 0, voice_end = 0;
-	uint32_t row_len = 0, nbufs = 1, max_ops = 1, wave_mask = 0, seg_cap = 0;
+	uint32_t row_len = 0, nbufs = 1, max_ops = 1, wave_mask = 0, seg_cap = 0, sched = 0;
 	float amp_scale = 0.f;
 	/* timeline (host-only integer bookkeeping) */
 	std::vector<uint64_t> ev_time;     // absolute sample time of each event
@@ -121,7 +122,10 @@ struct saugen_Generator {
 	void *d_ops = nullptr, *d_voices = nullptr, *d_events = nullptr, *d_opdata = nullptr,
 	     *d_code = nullptr, *d_prog_ops = nullptr, *d_vev_off = nullptr, *d_vev_idx = nullptr;
 	float *d_rows_s = nullptr, *d_rows_r = nullptr, *d_mix = nullptr;
-	uint32_t *d_vlen = nullptr, *d_status = nullptr;
+	uint32_t *d_vlen = nullptr, *d_status = nullptr, *d_progress = nullptr;
+	UnitDesc *d_units = nullptr, *h_units = nullptr;
+	uint32_t unit_cap = 0;
+	std::vector<UnitDesc> units_tmp;
 	int16_t *d_pcm = nullptr;
 	CallDesc *d_call = nullptr;
 	SegDesc *d_segs = nullptr;
@@ -366,7 +370,7 @@ extern "C" saugen_Generator *saugen_create(const sauabi_Program *prg, uint32_t s
 	std::vector<uint32_t> prog_ops;
 	if (!tables) tables = saugen::builtin_wave_tables();
 
-	o->prg = prg; o->srate = srate; o->device = opt->device;
+	o->prg = prg; o->srate = srate; o->device = opt->device; o->sched = opt->sched;
 	o->vo_count = prg->vo_count; o->op_count = prg->op_count;
 	o->voice_begin = 0; o->voice_end = prg->vo_count;
 	if (opt->voice_end > opt->voice_begin) {
@@ -512,6 +516,10 @@ extern "C" saugen_Generator *saugen_create(const sauabi_Program *prg, uint32_t s
 		CK(cudaMalloc(&o->d_rows_r, nl * o->row_len * sizeof(float)));
 		CK(cudaMalloc(&o->d_vlen, (size_t) o->seg_cap * nl * sizeof(uint32_t)));
 		CK(cudaMalloc(&o->d_status, (1 + o->seg_cap) * sizeof(uint32_t)));
+		CK(cudaMalloc(&o->d_progress, (nl + 1) * sizeof(uint32_t)));   /* [nl] = ticket counter */
+		o->unit_cap = 256;
+		CK(cudaMalloc(&o->d_units, o->unit_cap * sizeof(UnitDesc)));
+		CK(cudaMallocHost(&o->h_units, o->unit_cap * sizeof(UnitDesc)));
 		CK(cudaMalloc(&o->d_mix, 2 * (size_t) o->row_len * sizeof(float)));
 		CK(cudaMalloc(&o->d_pcm, 2 * (size_t) o->row_len * sizeof(int16_t)));
 		CK(cudaMalloc(&o->d_call, sizeof(CallDesc)));
@@ -532,6 +540,7 @@ extern "C" saugen_Generator *saugen_create(const sauabi_Program *prg, uint32_t s
 		d.vev_off = (const uint32_t*) o->d_vev_off; d.vev_idx = (const uint32_t*) o->d_vev_idx;
 		d.rows_s = o->d_rows_s; d.rows_r = o->d_rows_r;
 		d.vlen = o->d_vlen; d.status = o->d_status; d.vlen_cap = o->seg_cap;
+		d.progress = o->d_progress; d.ticket = o->d_progress + (o->nlv ? o->nlv : 1);
 		d.mix = o->d_mix; d.pcm = o->d_pcm;
 		d.vo_count = o->vo_count; d.op_count = o->op_count;
 		d.voice_begin = o->voice_begin; d.voice_end = o->voice_end;
@@ -554,9 +563,9 @@ extern "C" void saugen_destroy(saugen_Generator *o) {
 	if (o->stream) cudaStreamSynchronize(o->stream);
 	void *dev[] = {o->d_ops, o->d_voices, o->d_events, o->d_opdata, o->d_code, o->d_prog_ops, o->d_vev_off,
 		o->d_vev_idx, o->d_rows_s, o->d_rows_r, o->d_vlen, o->d_status, o->d_mix, o->d_pcm,
-		o->d_call, o->d_segs, o->d_desc};
+		o->d_call, o->d_segs, o->d_desc, o->d_progress, o->d_units};
 	for (void *p : dev) if (p) cudaFree(p);
-	void *host[] = {o->h_status, o->h_pcm, o->h_call, o->h_segs};
+	void *host[] = {o->h_status, o->h_pcm, o->h_call, o->h_segs, o->h_units};
 	for (void *p : host) if (p) cudaFreeHost(p);
 	for (int i = 0; i < 3; ++i) if (o->ev_t[i]) cudaEventDestroy(o->ev_t[i]);
 	if (o->own_stream && o->stream) cudaStreamDestroy(o->stream);
@@ -589,6 +598,24 @@ static void plan_call(saugen_Generator *o, uint32_t buf_len, std::vector<SegDesc
 	}
 	o->next_event = ev;
 	o->cur_time = t_end;
+}
+
+/* Cut the segments of a call into schedulable units of at most UNIT_BLOCKS
+ * reference blocks, on the segment's own block grid. */
+static const uint32_t UNIT_BLOCKS = 4;
+static void plan_units(const std::vector<SegDesc> &segs, std::vector<UnitDesc> &units) {
+	units.clear();
+	const uint32_t ul = UNIT_BLOCKS * REF_BLOCK;
+	for (uint32_t s = 0; s < segs.size(); ++s) {
+		uint32_t off = 0;
+		do {
+			UnitDesc u;
+			u.seg = s; u.off = off;
+			u.len = segs[s].len - off < ul ? segs[s].len - off : ul;
+			units.push_back(u);
+			off += u.len;
+		} while (off < segs[s].len);
+	}
 }
 
 /* CTA shape: small CTAs while there are fewer tasks than SMs x warps, 8-warp
@@ -638,19 +665,54 @@ static int run_common(saugen_Generator *o, size_t buf_len, int stereo, uint32_t 
 	}
 	const uint32_t nseg = (uint32_t) segs.size();
 	memcpy(o->h_segs, segs.data(), nseg * sizeof(SegDesc));
+	plan_units(segs, o->units_tmp);
+	if (o->units_tmp.size() > o->unit_cap) {
+		uint32_t cap = o->unit_cap;
+		while (cap < o->units_tmp.size()) cap *= 2;
+		cudaStreamSynchronize(o->stream);
+		cudaFree(o->d_units); cudaFreeHost(o->h_units);
+		if (cudaMalloc(&o->d_units, cap * sizeof(UnitDesc)) != cudaSuccess ||
+		    cudaMallocHost(&o->h_units, cap * sizeof(UnitDesc)) != cudaSuccess) {
+			set_err("saugen_run: unit table growth", cudaGetLastError());
+			return -1;
+		}
+		o->unit_cap = cap;
+	}
+	const uint32_t nunits = (uint32_t) o->units_tmp.size();
+	memcpy(o->h_units, o->units_tmp.data(), nunits * sizeof(UnitDesc));
 	CallDesc &cd = *o->h_call;
 	cd.gen = o->d_desc; cd.call_len = (uint32_t) buf_len; cd.nseg = nseg; cd.seg_off = 0;
-	cd.task_base = 0; cd.stereo = stereo ? 1 : 0; cd._pad = 0;
+	cd.task_base = 0; cd.stereo = stereo ? 1 : 0; cd.unit_off = 0; cd.nunits = nunits; cd._pad = 0;
+	/* more voices than resident warps: persistent grid with (unit, voice) tickets */
+	const uint32_t warps = pick_warps(o->nlv, o->wave_mask, o->nbufs, o->max_ops);
+	uint32_t ticketed_ctas = 0;
+	{
+		const size_t smem = render_smem_bytes(o->wave_mask, o->nbufs, o->max_ops, warps);
+		uint32_t per_sm = (uint32_t) ((227 * 1024) / (smem + 1024));
+		const uint32_t by_threads = 512 / (warps * 32);    /* 128 registers per thread */
+		if (per_sm > by_threads) per_sm = by_threads;
+		if (per_sm < 1) per_sm = 1;
+		const uint32_t resident = 148 * per_sm * warps;
+		(void) resident;   /* auto = one warp per voice: measured faster at 4096 equal voices */
+		if (o->sched == 2) {
+			ticketed_ctas = 148 * per_sm;
+			const uint32_t need = (o->nlv + warps - 1) / warps;
+			if (ticketed_ctas > need) ticketed_ctas = need ? need : 1;
+			if (getenv("SAUGEN_ONE_CTA")) ticketed_ctas = 1;
+		}
+	}
 	cudaError_t e;
 	e = cudaMemcpyAsync(o->d_segs, o->h_segs, nseg * sizeof(SegDesc), cudaMemcpyHostToDevice, o->stream);
+	if (e == cudaSuccess) e = cudaMemcpyAsync(o->d_units, o->h_units, nunits * sizeof(UnitDesc), cudaMemcpyHostToDevice, o->stream);
+	if (e == cudaSuccess) e = cudaMemsetAsync(o->d_vlen, 0, (size_t) nseg * (o->nlv ? o->nlv : 1) * sizeof(uint32_t), o->stream);
+	if (e == cudaSuccess && ticketed_ctas) e = cudaMemsetAsync(o->d_progress, 0, ((size_t) o->nlv + 1) * sizeof(uint32_t), o->stream);
 	if (e == cudaSuccess) e = cudaMemcpyAsync(o->d_call, o->h_call, sizeof(CallDesc), cudaMemcpyHostToDevice, o->stream);
 	if (e == cudaSuccess) e = cudaMemsetAsync(o->d_status, 0, (1 + nseg) * sizeof(uint32_t), o->stream);
 	o->timed_call = o->timing;
 	if (e == cudaSuccess && o->timed_call) e = cudaEventRecord(o->ev_t[0], o->stream);
 	if (e == cudaSuccess) {
-		const uint32_t warps = pick_warps(o->nlv, o->wave_mask, o->nbufs, o->max_ops);
-		e = launch_render(o->d_call, 1, o->d_segs, o->nlv, o->d_tables, o->wave_mask, o->nbufs,
-				o->max_ops, warps, o->stream);
+		e = launch_render(o->d_call, 1, o->d_segs, o->d_units, o->nlv, o->d_tables, o->wave_mask,
+				o->nbufs, o->max_ops, warps, ticketed_ctas, o->stream);
 		o->counters[0]++;
 	}
 	if (e == cudaSuccess && o->timed_call) e = cudaEventRecord(o->ev_t[1], o->stream);
@@ -753,7 +815,9 @@ extern "C" int saugen_run_many(saugen_Generator *const *gens, size_t n, int16_t 
 	static thread_local std::vector<size_t> call_of;     // generator index per call
 	static thread_local CallDesc *d_calls = nullptr; static thread_local size_t d_calls_cap = 0;
 	static thread_local SegDesc *d_segs = nullptr; static thread_local size_t d_segs_cap = 0;
-	calls.clear(); segs.clear(); call_of.clear();
+	static thread_local std::vector<UnitDesc> units;
+	static thread_local UnitDesc *d_units = nullptr; static thread_local size_t d_units_cap = 0;
+	calls.clear(); segs.clear(); call_of.clear(); units.clear();
 	uint32_t ntasks = 0, wave_mask = 0, nbufs = 1, max_ops = 1;
 	for (size_t i = 0; i < n; ++i) {
 		saugen_Generator *o = gens[i];
@@ -772,6 +836,10 @@ extern "C" int saugen_run_many(saugen_Generator *const *gens, size_t n, int16_t 
 		CallDesc cd;
 		cd.gen = o->d_desc; cd.call_len = (uint32_t) buf_len; cd.nseg = (uint32_t) o->segs_tmp.size();
 		cd.seg_off = (uint32_t) segs.size(); cd.task_base = ntasks; cd.stereo = stereo ? 1 : 0; cd._pad = 0;
+		plan_units(o->segs_tmp, o->units_tmp);
+		cd.unit_off = (uint32_t) units.size(); cd.nunits = (uint32_t) o->units_tmp.size();
+		units.insert(units.end(), o->units_tmp.begin(), o->units_tmp.end());
+		cudaMemsetAsync(o->d_vlen, 0, (size_t) cd.nseg * (o->nlv ? o->nlv : 1) * sizeof(uint32_t), g0->stream);
 		segs.insert(segs.end(), o->segs_tmp.begin(), o->segs_tmp.end());
 		calls.push_back(cd);
 		call_of.push_back(i);
@@ -793,12 +861,18 @@ extern "C" int saugen_run_many(saugen_Generator *const *gens, size_t n, int16_t 
 		d_segs_cap = segs.size() * 2;
 		e = cudaMalloc(&d_segs, d_segs_cap * sizeof(SegDesc));
 	}
+	if (e == cudaSuccess && units.size() > d_units_cap) {
+		if (d_units) cudaFree(d_units);
+		d_units_cap = units.size() * 2;
+		e = cudaMalloc(&d_units, d_units_cap * sizeof(UnitDesc));
+	}
+	if (e == cudaSuccess) e = cudaMemcpyAsync(d_units, units.data(), units.size() * sizeof(UnitDesc), cudaMemcpyHostToDevice, g0->stream);
 	if (e == cudaSuccess) e = cudaMemcpyAsync(d_calls, calls.data(), calls.size() * sizeof(CallDesc), cudaMemcpyHostToDevice, g0->stream);
 	if (e == cudaSuccess) e = cudaMemcpyAsync(d_segs, segs.data(), segs.size() * sizeof(SegDesc), cudaMemcpyHostToDevice, g0->stream);
 	if (e == cudaSuccess) {
 		const uint32_t warps = pick_warps(ntasks, wave_mask, nbufs, max_ops);
-		e = launch_render(d_calls, (uint32_t) calls.size(), d_segs, ntasks, g0->d_tables, wave_mask,
-				nbufs, max_ops, warps, g0->stream);
+		e = launch_render(d_calls, (uint32_t) calls.size(), d_segs, d_units, ntasks, g0->d_tables,
+				wave_mask, nbufs, max_ops, warps, 0, g0->stream);
 		g0->counters[0]++;
 	}
 	if (e == cudaSuccess) {

@@ -96,6 +96,25 @@ def test_synthetic_configs(S, ref, tabs, gold, key, text):
         assert [st.inited, st.type, st.i0, st.i1, st.time] == want, (key, op)
 
 
+@pytest.mark.parametrize("sched", [1, 2])
+def test_schedulers_agree_with_reference(S, ref, tabs, gold, sched):
+    """One warp per voice (1) and the ticketed persistent grid (2, what the
+    4096-voice runs use) both reproduce the reference bit for bit."""
+    for key, text in [("config/C3_64v_1s", scripts.synth_c3(64, 1)),
+                      ("config/C3fm_64v_1s", scripts.synth_c3(64, 1, fm=True)),
+                      ("config/C4_48v_1s", scripts.synth_c4(48, 1)),
+                      ("config/C5_script3", scripts.synth_c5_script(3))]:
+        prg = ref.Program(text)
+        got = S.render(prg, srate=96000, tables=tabs, sched=sched)
+        assert got.shape[0] == gold[key]["frames"], key
+        assert gpuutil.sha(got) == gold[key]["sha256"], key
+    feats = scripts.feature_scripts()
+    for name in ["seq_update", "voices3", "regoal", "seq_overlap", "silence_mid", "pm_addrem"]:
+        prg = ref.Program(feats[name])
+        got = S.render(prg, srate=96000, tables=tabs, sched=sched, call_len=8192)
+        assert gpuutil.sha(got) == gold["feat/" + name]["sha256"], name
+
+
 @pytest.mark.parametrize("call_len", [24576, 1024, 1000, 333, 77])
 def test_state_after_every_call(S, ref, port, tabs, call_len):
     """All operator and voice state, bit for bit, after each call, any call size."""
