@@ -10,6 +10,8 @@ script (weak scaling, no data-path collective).
 
     python bench.py [--gpus N] [--steps K] [--warmup W]        GPU arm
     python bench.py --impl reference ...                         reference CPU arm
+    python bench.py --workload c4|c5 ...                         the other BASELINE configs
+                                                                 (reported in DESIGN.md, not the headline)
 """
 import argparse
 import json
@@ -95,42 +97,68 @@ class ClockSampler:
 # ---------------------------------------------------------------------------
 # reference CPU arm / cpu_baseline
 # ---------------------------------------------------------------------------
-def _ref_worker(args):
-    text, frames = args
+def _ref_worker(conn, text):
+    """One host process = one single-threaded reference generator (the reference has no
+    threading of its own) over a slice of the workload's voices, kept alive across steps."""
     from oracle import pyref
     prg = pyref.Program(text)
-    t0 = time.perf_counter()
-    n = pyref.lib().refwb_render_null(prg.ptr, SRATE, 1, FRAMES, frames)
-    dt = time.perf_counter() - t0
-    return n, prg.vo_count, dt
+    gen = None
+    while True:
+        cmd = conn.recv()
+        if cmd[0] == "stop":
+            break
+        t0 = time.perf_counter()
+        if gen is None:
+            gen = pyref.RefGenerator(prg, SRATE)          # sau_create_Generator, timed
+        frames = 0
+        for _ in range(cmd[1]):
+            more, _, n = gen.run(FRAMES)                  # sauGenerator_run, 24576 frames
+            frames += n
+        conn.send((frames, prg.vo_count, time.perf_counter() - t0))
+    conn.close()
 
 
-def reference_render(voices, frames, procs, seed=1):
-    """Unmodified reference generator (oracle/_ref) on `procs` host processes,
-    each rendering a disjoint slice of the C3 voices for `frames` frames.
-    Returns (voice_samples, wall_seconds, kind)."""
-    import multiprocessing as mp
-    from saugns_b200 import workloads
-    from oracle import pyref
-    if not pyref.available():
-        raise RuntimeError("oracle/_ref/libsauref.so missing")
-    # one script per process: same voices as the GPU workload, split by voice index
-    full = workloads.synth_c3(voices, SECS, seed=seed, fm="mix").splitlines()
-    head, body = full[0], full[1:]
-    per = (len(body) + procs - 1) // procs
-    jobs = []
-    for p in range(procs):
-        part = body[p * per:(p + 1) * per]
-        if part:
-            jobs.append(("\n".join([head] + part) + "\n", frames))
-    ctx = mp.get_context("fork")
-    with ctx.Pool(len(jobs)) as pool:
-        res = pool.map(_ref_worker, jobs)
-    # all processes run concurrently; the job takes as long as the slowest one's
-    # create+render (script parsing is not the generator's work and is excluded)
-    wall = max(dt for _, _, dt in res)
-    vs = sum(n * v for n, v, _ in res)
-    return vs, wall, len(jobs)
+class ReferencePool:
+    """The unmodified reference generator (oracle/_ref/libsauref.so) on `procs` host
+    processes, each rendering a disjoint slice of the C3 voices call by call."""
+
+    def __init__(self, voices, procs, seed=1):
+        import multiprocessing as mp
+        from saugns_b200 import workloads
+        from oracle import pyref
+        if not pyref.available():
+            raise RuntimeError("oracle/_ref/libsauref.so missing")
+        full = workloads.synth_c3(voices, SECS, seed=seed, fm="mix").splitlines()
+        head, body = full[0], full[1:]
+        per = (len(body) + procs - 1) // procs
+        ctx = mp.get_context("fork")
+        self.conns, self.procs = [], []
+        for p in range(procs):
+            part = body[p * per:(p + 1) * per]
+            if not part:
+                continue
+            a, b = ctx.Pipe()
+            pr = ctx.Process(target=_ref_worker, args=(b, "\n".join([head] + part) + "\n"),
+                             daemon=True)
+            pr.start()
+            self.conns.append(a)
+            self.procs.append(pr)
+        self.used = len(self.procs)
+
+    def step(self, calls=1):
+        """All workers render `calls` more calls concurrently -> (voice_samples, wall s)."""
+        t0 = time.perf_counter()
+        for c in self.conns:
+            c.send(("step", calls))
+        res = [c.recv() for c in self.conns]
+        wall = time.perf_counter() - t0
+        return sum(f * v for f, v, _ in res), wall
+
+    def close(self):
+        for c in self.conns:
+            c.send(("stop",))
+        for p in self.procs:
+            p.join(timeout=10)
 
 
 def run_reference_arm(args):
@@ -139,14 +167,19 @@ def run_reference_arm(args):
         return 0
     cores = os.cpu_count() or 1
     procs = max(1, min(cores, 64))
+    if args.warmup + args.steps > SECS * SRATE // FRAMES:
+        raise SystemExit("steps+warmup exceed the 60 s workload (234 calls)")
+    pool = ReferencePool(VOICES, procs)
     # one step = the same 24576-frame call over all 4096 voices, on all host cores
     for _ in range(args.warmup):
-        reference_render(VOICES, FRAMES, procs)
+        pool.step()
     t_tot, vs_tot = 0.0, 0
     for _ in range(args.steps):
-        vs, wall, used = reference_render(VOICES, FRAMES, procs)
+        vs, wall = pool.step()
         t_tot += wall
         vs_tot += vs
+    used = pool.used
+    pool.close()
     value = vs_tot / t_tot
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "voice-samples/s",
@@ -156,11 +189,12 @@ def run_reference_arm(args):
         "config": {"workload": WORKLOAD, "voices": VOICES, "frames_per_step": FRAMES,
                    "srate": SRATE},
         "realtime_factor": (FRAMES * args.steps / SRATE) / t_tot,
-        "cpu_baseline": {"value": value, "unit": "voice-samples/s", "cores": procs,
+        "cpu_baseline": {"value": value, "unit": "voice-samples/s", "cores": used,
                          "kind": "reference",
                          "sample": f"unmodified reference generator (oracle/_ref, -O3 -ffast-math), "
-                                   f"{VOICES} voices split over {procs} processes, "
-                                   f"{FRAMES} frames per step; create+render timed, parsing excluded"},
+                                   f"{VOICES} voices split over {used} single-threaded processes, "
+                                   f"{FRAMES} frames per step, wall clock around each step; "
+                                   "script parsing excluded"},
         "e2e": {"value": value, "unit": "voice-samples/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
     }
@@ -189,7 +223,10 @@ def run_gpu_arm(args):
     if W + K > SECS * SRATE // FRAMES - 1:
         raise SystemExit("steps+warmup exceed the 60 s workload (234 calls)")
 
-    prg = workloads.build_c3(VOICES, SECS, seed=1 + rank, fm="mix")
+    def build_program():
+        return workloads.build_c3(VOICES, SECS, seed=1 + rank, fm="mix")
+
+    prg = build_program()
 
     def barrier():
         if dist is not None:
@@ -230,18 +267,30 @@ def run_gpu_arm(args):
     g.close()
 
     # ---- end to end through the public call with HOST buffers ----
-    g2 = saugns_b200.Generator(prg, SRATE, device=local_rank, stream=stream.cuda_stream,
-                               max_call_len=FRAMES)
-    for _ in range(W):
-        g2.run(FRAMES)
+    # timed: sau_create_Generator (program flattening + H2D upload of events, op-data,
+    # bytecode, tables) + W+K x sauGenerator_run with a host PCM buffer (D2H every call)
+    # + destroy; the W warm-up calls are part of the same render, so they are timed and
+    # counted too (a renderer cannot skip the start of its script).
+    import ctypes
+    prg_bytes = 0
+    try:
+        from saugns_b200 import program as P
+        pp = P.Program.from_address(prg.ptr)
+        prg_bytes = (ctypes.sizeof(P.Program) + pp.ev_count * ctypes.sizeof(P.Event) +
+                     pp.op_count * (ctypes.sizeof(P.OpData) + 3 * ctypes.sizeof(P.Line)))
+    except Exception:
+        pass
     barrier()
     t0 = time.perf_counter()
-    for _ in range(K):
+    g2 = saugns_b200.Generator(prg, SRATE, device=local_rank, stream=stream.cuda_stream,
+                               max_call_len=FRAMES)
+    for _ in range(W + K):
         more, pcm, n = g2.run(FRAMES)
+    g2.close()
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_steps = W + K
     assert int(abs(pcm.astype("int32")).max()) > 0, "silent output"
-    g2.close()
     barrier()
 
     if rank != 0:
@@ -251,7 +300,7 @@ def run_gpu_arm(args):
 
     vs_step = VOICES * FRAMES
     value = world * vs_step * K / (ms / 1000.0)
-    e2e = world * vs_step * K / e2e_s
+    e2e = world * vs_step * e2e_steps / e2e_s
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -265,7 +314,10 @@ def run_gpu_arm(args):
     achieved = alg_bytes / rk_s / 1e9
     prof = {}
     try:
-        prof = json.load(open(os.path.join(ROOT, "profiles", "r01_render_kernel.json")))
+        import glob
+        latest = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_render_kernel.json")))[-1]
+        prof = json.load(open(latest))
+        prof["file"] = os.path.relpath(latest, ROOT)
     except Exception:
         pass
     line = {
@@ -279,8 +331,11 @@ def run_gpu_arm(args):
         "realtime_factor": (FRAMES * K / SRATE) / (ms / 1000.0),
         "clocks": clocks,
         "e2e": {"value": e2e, "unit": "voice-samples/s",
-                "h2d_bytes_per_step": 40 + 12, "d2h_bytes_per_step": FRAMES * 2 * 2 + 8,
-                "realtime_factor": (FRAMES * K / SRATE) / e2e_s},
+                "h2d_bytes_per_step": 40 + 12 + 6 * 12 + prg_bytes // max(e2e_steps, 1),
+                "d2h_bytes_per_step": FRAMES * 2 * 2 + 8,
+                "realtime_factor": (FRAMES * e2e_steps / SRATE) / e2e_s,
+                "timed": f"create (program flatten + upload, {prg_bytes} B) + {e2e_steps} calls "
+                         "with host PCM buffers + destroy, wall clock"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": prof.get("dram_bytes_per_launch"),
@@ -290,18 +345,24 @@ def run_gpu_arm(args):
                      "note": "path is issue-/FP64-pipe-bound, not HBM-bound (SURVEY.md 8d); "
                              "issue-slot figures from ncu in profiles/",
                      "issue_slot_frac_ncu": prof.get("issue_slot_frac"),
-                     "fp64_pipe_frac_ncu": prof.get("fp64_pipe_frac")},
+                     "fp64_pipe_frac_ncu": prof.get("fp64_pipe_frac"),
+                     "xu_pipe_frac_ncu": prof.get("xu_pipe_frac"),
+                     "ncu_profile": prof.get("file")},
     }
     if world == 1 and not args.no_cpu:
         try:
             cores = min(os.cpu_count() or 1, 64)
-            sample_frames = SRATE // 2      # 0.5 s of all 4096 voices
-            vs, wall, used = reference_render(VOICES, sample_frames, cores)
+            pool = ReferencePool(VOICES, cores)
+            pool.step(1)                    # create + first call (warm-up)
+            ncalls = 40                     # ~10 s of audio for all 4096 voices
+            vs, wall = pool.step(ncalls)
+            used = pool.used
+            pool.close()
             line["cpu_baseline"] = {
                 "value": vs / wall, "unit": "voice-samples/s", "cores": used, "kind": "reference",
                 "sample": f"unmodified reference generator (oracle/_ref), same {VOICES}-voice "
-                          f"script, first {sample_frames} frames, voices split over {used} "
-                          f"processes; {wall:.2f} s create+render"}
+                          f"script, calls 2..{ncalls + 1} of {FRAMES} frames, voices split over "
+                          f"{used} single-threaded processes; {wall:.2f} s wall"}
         except Exception as e:   # the baseline is reported, never required for the GPU number
             line["cpu_baseline"] = {"value": None, "unit": "voice-samples/s", "cores": 0,
                                     "kind": "reference", "sample": f"unavailable: {e}"}
@@ -311,18 +372,95 @@ def run_gpu_arm(args):
     return 0
 
 
+def run_gpu_config(args):
+    """The other BASELINE configs on one GPU (numbers for DESIGN.md section 8; the
+    headline line stays C3).  Scripts go through the reference's own script front end
+    on the host, exactly as in the drop-in (north star): oracle/_ref/libsauref.so is used
+    here for PARSING only; every sample is rendered by the CUDA back end."""
+    import numpy as np
+    import torch
+    import saugns_b200
+    from saugns_b200 import workloads, batch
+    from saugns_b200 import program as P
+    from oracle import pyref, pyport
+    import ctypes as C
+    rank, local_rank, world = env_rank()
+    torch.cuda.set_device(local_rank)
+    t = pyport.ref_tables()
+    tabs = saugns_b200.WaveTables.from_buffer_copy(bytes(t))
+    tabs._keep = t
+    K, W = args.steps, args.warmup
+    if args.workload == "c4":
+        nv = 1024
+        prg = pyref.Program(workloads.synth_c4(nv, SECS))
+        g = saugns_b200.Generator(prg, SRATE, tables=tabs, device=local_rank, max_call_len=FRAMES)
+        for _ in range(W):
+            g.run_device(FRAMES)
+        g.set_timing(True)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(K):
+            g.run(FRAMES)
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        rk, mk = g.kernel_ms()
+        g.close()
+        # latency model: every self-PM operator is one serial chain over the call
+        sm_mhz = 1965.0
+        line = {"metric": METRIC, "workload": "C4: 1024 voices, self-PM carriers (W and R) with "
+                "range-AM / ring-mod, 96 kHz; step = one 24576-frame call, host PCM buffers",
+                "value": nv * FRAMES * K / wall, "unit": "voice-samples/s", "steps": K,
+                "ms_per_step": 1000 * wall / K, "render_kernel_ms": rk / K, "mix_kernel_ms": mk / K,
+                "realtime_factor": (FRAMES * K / SRATE) / wall,
+                "cycles_per_feedback_iteration_at_max_clock": (rk / K) * 1e-3 * sm_mhz * 1e6 / FRAMES}
+        print(json.dumps(line))
+        return 0
+    # c5: independent scripts, this GPU's share of 10 000 (default 10000/8 = 1250)
+    n = args.scripts
+    texts = [workloads.synth_c5_script(i) for i in range(n)]
+    t0 = time.perf_counter()
+    prgs = [pyref.Program(x) for x in texts]
+    parse_s = time.perf_counter() - t0
+    vs = 0
+    for p in prgs:
+        d = P.dump(p.ptr)
+        for ev in d["events"]:
+            for od in ev["ops"]:
+                if od["id"] == ev["carr_op_id"]:
+                    vs += od["time"][0] * SRATE // 1000
+    batch.render_batch(prgs[:16], srate=SRATE, device=local_rank, tables=tabs, group_size=16)  # warm-up
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    out = batch.render_batch(prgs, srate=SRATE, device=local_rank, tables=tabs,
+                             group_size=args.group)
+    wall = time.perf_counter() - t0
+    frames = sum(o.shape[0] for o in out)
+    line = {"metric": METRIC, "workload": f"C5: {n} independent mixed scripts (4-16 voices, W/N/R, "
+            "1-10 s) on one GPU, batched saugen_run_many, PCM to host for every script",
+            "value": vs / wall, "unit": "voice-samples/s", "scripts": n, "group": args.group,
+            "wall_s": wall, "scripts_per_s": n / wall, "audio_s": frames / SRATE,
+            "realtime_factor": (frames / SRATE) / wall, "parse_s_reference_front_end": parse_s}
+    print(json.dumps(line))
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--workload", default="c3", choices=["c3", "c4", "c5"])
+    ap.add_argument("--scripts", type=int, default=1250, help="c5: scripts on this GPU")
+    ap.add_argument("--group", type=int, default=256, help="c5: generators in flight")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
     if args.impl == "reference":
         return run_reference_arm(args)
+    if args.workload != "c3":
+        return run_gpu_config(args)
     return run_gpu_arm(args)
 
 

@@ -46,9 +46,10 @@ typedef struct saugen_Options {
 	uint32_t voice_begin;    /* render only voices [voice_begin, voice_end) ... */
 	uint32_t voice_end;      /* ... 0,0 = all (multi-GPU voice sharding) */
 	uint32_t max_call_len;   /* largest buf_len that will be passed; 0 = 256 ms */
-	uint32_t sched;          /* 0 = auto; 1 = one warp per voice; 2 = persistent grid
-	                          * taking (time unit, voice) tickets (auto picks it when
-	                          * voices outnumber the resident warps) */
+	uint32_t sched;          /* 0 = auto; 1 = one warp per voice; 2 = persistent grid taking
+	                          * (time unit, voice) tickets; 3 = balanced: one contiguous
+	                          * range of (voice, block) items per resident warp (auto picks
+	                          * it when the voices need more than one wave of warps) */
 } saugen_Options;
 
 /* == sau_create_Generator(prg, srate).  Borrows `prg` until destroy. */

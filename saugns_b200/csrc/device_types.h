@@ -141,6 +141,7 @@ enum {
 	F_SKIP_FREQ2  = 1 << 5,   // the freq2 / amp2 / pm_a line was set at some point:
 	F_SKIP_AMP2   = 1 << 6,   // keep its position bookkeeping (sauLine_skip)
 	F_MAY_SELFMOD = 1 << 7,
+	F_KEEP_FREQ   = 1 << 8,   // leaf carrier with pan modulators: they read its freq buffer
 };
 struct Instr {
 	uint8_t opcode, a, b, c, d, e;

@@ -76,7 +76,7 @@ struct Ctx {
 	uint32_t *stk_rem;
 	uint32_t *stk_layer;
 	OpState *sops;             // shared: this voice's operator states
-	const float *tab;          // shared: staged wave tables
+	const float *tab;          // shared: staged wave tables (or coefficient planes, CTAB_FLAG)
 	const WaveCoeffs *wc;      // global
 	const GenDesc *g;          // global
 	OpState *gops;             // global operator states
@@ -111,6 +111,13 @@ __device__ __forceinline__ void st4(const Ctx &c, uint32_t buf, const float v[SP
  * for the bulk copy), lut[-1] at +3 and lut[2048], lut[2049] after it, so the
  * four Hermite taps of an index are consecutive without masking. */
 constexpr uint32_t TAB_STRIDE = WAVE_LEN + 8;
+/* Coefficient-table mode (flag in the top bit of the wave mask a launch carries):
+ * shared memory holds, for every wave the launch uses, the per-index cubic
+ * coefficients of sauWave_get_herp in double precision (see coef_kernel) instead
+ * of the float tables; every table evaluation, hot or rare, goes through them. */
+constexpr uint32_t CTAB_FLAG = 0x80000000u;
+constexpr uint32_t CTAB_WAVE_BYTES = WAVE_LEN * 32;       // {c3,c2} plane + {c1,c0} plane
+constexpr uint32_t CTAB_PLANE_BYTES = WAVE_LEN * 16;
 /* What the out-of-line (rare path) functions need, passed by value. */
 struct ColdCtx {
 	const float *tab;
@@ -122,10 +129,37 @@ __device__ __forceinline__ ColdCtx cold(const Ctx &c) {
 	ColdCtx k; k.tab = c.tab; k.wc = c.wc; k.wave_mask = c.wave_mask; k.lane = c.lane;
 	return k;
 }
+/* A staged wave: the float table (wrapped neighbours around it), or its
+ * coefficient planes. */
+struct WaveRef {
+	const void *p;
+	bool ct;
+};
 template <typename C>
-__device__ __forceinline__ const float *wave_lut(const C &c, uint32_t wave) {
-	uint32_t slot = __popc(c.wave_mask & ((1u << wave) - 1u));
-	return c.tab + slot * TAB_STRIDE + 4;
+__device__ __forceinline__ WaveRef wave_ref(const C &c, uint32_t wave) {
+	const uint32_t slot = __popc(c.wave_mask & ((1u << wave) - 1u));
+	WaveRef r;
+	r.ct = (c.wave_mask & CTAB_FLAG) != 0;
+	if (r.ct) r.p = reinterpret_cast<const unsigned char*>(c.tab) + (size_t) slot * CTAB_WAVE_BYTES;
+	else r.p = c.tab + slot * TAB_STRIDE + 4;
+	return r;
+}
+/* sauWave_get_herp (wave.h:127-141) on either form; poly_out / c0_out as sau::herp */
+__device__ __forceinline__ double herp_ref(const WaveRef &w, uint32_t phase, double *poly_out,
+		double *c0_out) {
+	if (w.ct) {
+		const double2 *pl = reinterpret_cast<const double2*>(w.p) + (phase >> sau::WAVE_SLENBITS);
+		const double2 hi = pl[0], lo = pl[WAVE_LEN];
+		const double p = sau::herp_horner(hi.x, hi.y, lo.x, phase);
+		if (poly_out) { *poly_out = p; *c0_out = lo.y; }
+		return p + lo.y;
+	}
+	/* staged float table: taps lut[ind-1 .. ind+2] are consecutive, no masking */
+	const float *t = reinterpret_cast<const float*>(w.p) - 1 + (phase >> sau::WAVE_SLENBITS);
+	const float s0 = t[0], s1 = t[1], s2 = t[2], s3 = t[3];
+	const double p = sau::herp_poly(s0, s1, s2, s3, phase);
+	if (poly_out) { *poly_out = p; *c0_out = (double) s1; }
+	return p + (double) s1;
 }
 __device__ __forceinline__ uint32_t scan_incl_u32(uint32_t v, int lane) {
 #pragma unroll
@@ -409,23 +443,15 @@ __device__ __forceinline__ void phasor_eval(const C &c, OpState *o, uint32_t pha
 /* ---- sauWOsc_run / sauWOsc_run_selfmod (wosc.h:215-310) ----------------- */
 
 /* Differentiation (re)start, wosc.h:215-230; ph0 = phase of the chunk's sample 0. */
-__device__ __forceinline__ void wosc_reset(const ColdCtx &c, const float *lut, uint32_t wave,
+__device__ __forceinline__ void wosc_reset(const ColdCtx &c, const WaveRef &lut, uint32_t wave,
 		uint32_t ph0, uint32_t &prev_phase, double &prev_Is, float &prev_s) {
 	double poly, c0;
-	sau::herp(lut, ph0 - sau::WAVE_SLEN, &poly, &c0);
-	const double Is = sau::herp(lut, ph0, (double*) 0, (double*) 0);
+	herp_ref(lut, ph0 - sau::WAVE_SLEN, &poly, &c0);
+	const double Is = herp_ref(lut, ph0, (double*) 0, (double*) 0);
 	prev_s = (float) (((Is - poly) - c0) * (double) c.wc->amp256[wave] +
 			(double) c.wc->diff_offset[wave]);
 	prev_Is = Is;
 	prev_phase = ph0;
-}
-
-/* sauWave_get_herp (wave.h:127-141) on a staged table whose neighbours wrap:
- * taps[0..3] = lut[ind-1 .. ind+2] without index masking. */
-__device__ __forceinline__ double herp_taps(const float *taps_base, uint32_t phase) {
-	const float *t = taps_base + (phase >> sau::WAVE_SLENBITS);
-	const float s0 = t[0], s1 = t[1], s2 = t[2], s3 = t[3];
-	return sau::herp_poly(s0, s1, s2, s3, phase) + (double) s1;
 }
 
 /* diff_scale / (float) phase_diff, IEEE round-to-nearest: the instruction
@@ -452,7 +478,7 @@ __device__ __noinline__ float4 wosc_eval_any(const ColdCtx c, OpState *o, const 
 	const uint32_t ph[SPL] = {ph4.x, ph4.y, ph4.z, ph4.w};
 	float s[SPL];
 	const uint32_t wave = o->mode;
-	const float *lut = wave_lut(c, wave);
+	const WaveRef lut = wave_ref(c, wave);
 	const float ds = c.wc->diff_scale[wave], doff = c.wc->diff_offset[wave];
 	uint32_t prev_phase = o->i1;
 	double prev_Is = o->prev_Is;
@@ -466,7 +492,7 @@ __device__ __noinline__ float4 wosc_eval_any(const ColdCtx c, OpState *o, const 
 	const uint32_t i0 = c.lane * SPL;
 	double Is[SPL];
 #pragma unroll
-	for (int k = 0; k < SPL; ++k) Is[k] = sau::herp(lut, ph[k], (double*) 0, (double*) 0);
+	for (int k = 0; k < SPL; ++k) Is[k] = herp_ref(lut, ph[k], (double*) 0, (double*) 0);
 	/* sample before this lane's first: previous lane's last, or carried state */
 	uint32_t pph = __shfl_up_sync(FULL, ph[SPL - 1], 1);
 	double pIs = __shfl_up_sync(FULL, Is[SPL - 1], 1);
@@ -528,12 +554,12 @@ __device__ __noinline__ float4 wosc_eval_any(const ColdCtx c, OpState *o, const 
 template <typename C>
 __device__ __forceinline__ bool wosc_eval_full(const C &c, OpState *o, uint32_t wave,
 		uint32_t prev_phase, double prev_Is, const uint32_t ph[SPL], float s[SPL]) {
-	const float *taps = wave_lut(c, wave) - 1;
+	const WaveRef lut = wave_ref(c, wave);
 	const float ds = c.wc->diff_scale[wave];
 	const double doff = (double) c.wc->diff_offset[wave];
 	double Is[SPL];
 #pragma unroll
-	for (int k = 0; k < SPL; ++k) Is[k] = herp_taps(taps, ph[k]);
+	for (int k = 0; k < SPL; ++k) Is[k] = herp_ref(lut, ph[k], (double*) 0, (double*) 0);
 	uint32_t pph = __shfl_up_sync(FULL, ph[SPL - 1], 1);
 	double pIs = __shfl_up_sync(FULL, Is[SPL - 1], 1);
 	if (c.lane == 0) { pph = prev_phase; pIs = prev_Is; }
@@ -565,7 +591,7 @@ __device__ __noinline__ void wosc_selfmod(const ColdCtx c, OpState *o, const uin
 	__syncwarp();
 	if (c.lane == 0) {
 		const uint32_t wave = o->mode;
-		const float *lut = wave_lut(c, wave);
+		const WaveRef lut = wave_ref(c, wave);
 		const float ds = c.wc->diff_scale[wave], doff = c.wc->diff_offset[wave];
 		uint32_t prev_phase = o->i1;
 		double prev_Is = o->prev_Is;
@@ -583,7 +609,7 @@ __device__ __noinline__ void wosc_selfmod(const ColdCtx c, OpState *o, const uin
 			if (d == 0) {
 				s = prev_s;
 			} else {
-				const double Is = sau::herp(lut, phase, (double*) 0, (double*) 0);
+				const double Is = herp_ref(lut, phase, (double*) 0, (double*) 0);
 				s = sau::wosc_diff(Is, prev_Is, d, ds, doff);
 				prev_Is = Is; prev_s = s; prev_phase = phase;
 			}
@@ -706,7 +732,7 @@ __device__ __forceinline__ void wop(Ctx &c, const Instr &in, uint32_t &pc) {
 				fr[0] = t.x; fr[1] = t.y; fr[2] = t.z; fr[3] = t.w;
 			}
 			if (in.flags & F_SKIP_FREQ2) line_skip(c.oc, c.lane, o, LINE_FREQ2, len);
-			if (!TAIL) st4(c, in.b, fr);
+			if (!TAIL || (in.flags & F_KEEP_FREQ)) st4(c, in.b, fr);
 		}
 		if (!TAIL) { __syncwarp(); return; }
 	} else {
@@ -754,6 +780,7 @@ __device__ __forceinline__ void wop(Ctx &c, const Instr &in, uint32_t &pc) {
 			wosc_selfmod(cold(c), o, reinterpret_cast<const uint32_t*>(c.bufs + in.b * CHUNK),
 					c.bufs + (in.b + 1u) * CHUNK, c.bufs + (in.b + 1u) * CHUNK, len);
 			ld4(c, in.b + 1u, s);
+			if (in.flags & F_KEEP_FREQ) { __syncwarp(); st4(c, in.b, fr); }   /* scratch over: freq back */
 		}
 		c.pma_flag = selfmod;
 		if (full) mix_eval<true>(c, in.a, s, am, len, layer, (in.flags & F_WAVEENV) != 0);
@@ -1414,9 +1441,18 @@ __device__ __noinline__ void steady_update(OpState *sops, const Instr *code, uin
 	}
 }
 
-/* the trajectory of a steady goal line at positions pos .. pos+3 (line.c:27-281);
+/* the trajectory of a steady goal line at positions pos .. pos+NS-1 (line.c:27-281);
  * out of line: one copy of the 11 shapes for all call sites */
-__device__ __noinline__ float4 line_goal_fill(float v0, float vt, float inv, uint32_t pos,
+template <int TYPE, int NS>
+__device__ __forceinline__ void line_fillN(const sau::LineFill &f, float out[NS]) {
+	sau::LineFill g = f;
+	g.type = TYPE;
+#pragma unroll
+	for (int k = 0; k < NS; ++k) out[k] = sau::line_fill_at(g, (uint32_t) k, false);
+}
+template <int NS> struct LineVec { float v[NS]; };
+template <int NS>
+__device__ __noinline__ LineVec<NS> line_goal_fill(float v0, float vt, float inv, uint32_t pos,
 		uint32_t end, uint32_t type) {
 	sau::LineFill f;
 	int t = (int) type;
@@ -1430,22 +1466,23 @@ __device__ __noinline__ float4 line_goal_fill(float v0, float vt, float inv, uin
 	f.vm = (v0 + vt) * 0.5f;
 	f.vd = vt - v0;
 	f.c = 0.f;
-	float out[SPL];
+	LineVec<NS> r;
+	float *out = r.v;
 	switch (t) {
 	default:
-	case sau::L_sah: line_fill4<sau::L_sah>(f, 0, out); break;
-	case sau::L_lin: f.c = f.vd * f.inv; line_fill4<sau::L_lin>(f, 0, out); break;
-	case sau::L_cos: line_fill4<sau::L_cos>(f, 0, out); break;
-	case sau::L_xpe: f.c = v0 - vt; line_fill4<sau::L_xpe>(f, 0, out); break;
-	case sau::L_lge: line_fill4<sau::L_lge>(f, 0, out); break;
-	case sau::L_sqe: f.c = v0 - vt; line_fill4<sau::L_sqe>(f, 0, out); break;
-	case sau::L_cub: f.inv = -2.f * f.inv; f.c = (v0 - vt) * 0.5f; line_fill4<sau::L_cub>(f, 0, out); break;
-	case sau::L_smo: line_fill4<sau::L_smo>(f, 0, out); break;
-	case sau::L_uwh: f.c = f.vd * (0.5f / 2147483648.f); line_fill4<sau::L_uwh>(f, 0, out); break;
-	case sau::L_ncl: line_fill4<sau::L_ncl>(f, 0, out); break;
-	case sau::L_nhl: line_fill4<sau::L_nhl>(f, 0, out); break;
+	case sau::L_sah: line_fillN<sau::L_sah, NS>(f, out); break;
+	case sau::L_lin: f.c = f.vd * f.inv; line_fillN<sau::L_lin, NS>(f, out); break;
+	case sau::L_cos: line_fillN<sau::L_cos, NS>(f, out); break;
+	case sau::L_xpe: f.c = v0 - vt; line_fillN<sau::L_xpe, NS>(f, out); break;
+	case sau::L_lge: line_fillN<sau::L_lge, NS>(f, out); break;
+	case sau::L_sqe: f.c = v0 - vt; line_fillN<sau::L_sqe, NS>(f, out); break;
+	case sau::L_cub: f.inv = -2.f * f.inv; f.c = (v0 - vt) * 0.5f; line_fillN<sau::L_cub, NS>(f, out); break;
+	case sau::L_smo: line_fillN<sau::L_smo, NS>(f, out); break;
+	case sau::L_uwh: f.c = f.vd * (0.5f / 2147483648.f); line_fillN<sau::L_uwh, NS>(f, out); break;
+	case sau::L_ncl: line_fillN<sau::L_ncl, NS>(f, out); break;
+	case sau::L_nhl: line_fillN<sau::L_nhl, NS>(f, out); break;
 	}
-	return make_float4(out[0], out[1], out[2], out[3]);
+	return r;
 }
 
 /* The per-chunk code addresses shared memory by 32-bit shared-window addresses
@@ -1478,6 +1515,11 @@ __device__ __forceinline__ uint4 lds128u(uint32_t a) {
 	uint4 v;
 	asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
 			: "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+	return v;
+}
+__device__ __forceinline__ double2 lds128d(uint32_t a) {
+	double2 v;
+	asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a));
 	return v;
 }
 __device__ __forceinline__ uint32_t lds32(uint32_t a) {
@@ -1530,17 +1572,21 @@ __device__ __forceinline__ void line_value_steady(const FastCtx &c, uint32_t op,
 	const float v0 = __uint_as_float(core.x);
 	const uint32_t flags = LM_FLAGS(meta);
 	if (!(flags & SAUABI_LINEP_GOAL)) {
-		const bool um = m && (flags & SAUABI_LINEP_STATE_RATIO);
+		if (m && (flags & SAUABI_LINEP_STATE_RATIO)) {
 #pragma unroll
-		for (int k = 0; k < NS; ++k) out[k] = um ? v0 * m[k] : v0;
+			for (int k = 0; k < NS; ++k) out[k] = v0 * m[k];
+		} else {
+#pragma unroll
+			for (int k = 0; k < NS; ++k) out[k] = v0;
+		}
 		return;
 	}
 	const float inv = lds32f(op + OS_LINV + 4 * li);
+	{
+		const LineVec<NS> t = line_goal_fill<NS>(v0, __uint_as_float(core.y), inv,
+				core.z + c.oc + c.lane * NS, core.w, LM_TYPE(meta));
 #pragma unroll
-	for (int h = 0; h < NS / 4; ++h) {
-		const float4 t = line_goal_fill(v0, __uint_as_float(core.y), inv,
-				core.z + c.oc + c.lane * NS + 4 * h, core.w, LM_TYPE(meta));
-		out[4 * h] = t.x; out[4 * h + 1] = t.y; out[4 * h + 2] = t.z; out[4 * h + 3] = t.w;
+		for (int k = 0; k < NS; ++k) out[k] = t.v[k];
 	}
 	if (m && (flags & SAUABI_LINEP_GOAL_RATIO)) {
 #pragma unroll
@@ -1559,14 +1605,14 @@ __device__ __noinline__ SampVec<NS> wosc_zero_diff(const ColdCtx c, OpState *o, 
 	SampVec<NS> sv;
 	float *s = sv.v;
 	const uint32_t wave = o->mode;
-	const float *lut = wave_lut(c, wave);
+	const WaveRef lut = wave_ref(c, wave);
 	const float ds = c.wc->diff_scale[wave], doff = c.wc->diff_offset[wave];
 	const uint32_t prev_phase = o->i1;
 	const double prev_Is = o->prev_Is;
 	const float prev_s = o->prev_s;
 	double Is[NS];
 #pragma unroll
-	for (int k = 0; k < NS; ++k) Is[k] = sau::herp(lut, ph[k], (double*) 0, (double*) 0);
+	for (int k = 0; k < NS; ++k) Is[k] = herp_ref(lut, ph[k], (double*) 0, (double*) 0);
 	uint32_t pph = __shfl_up_sync(FULL, ph[NS - 1], 1);
 	double pIs = __shfl_up_sync(FULL, Is[NS - 1], 1);
 	if (c.lane == 0) { pph = prev_phase; pIs = prev_Is; }
@@ -1606,7 +1652,7 @@ __device__ __noinline__ SampVec<NS> wosc_zero_diff(const ColdCtx c, OpState *o, 
 
 /* TAIL of a wave operator on a steady full chunk: phase fill, oscillator,
  * amplitude line, block_mix (generator.c:584-601); fr = its frequency values */
-template <int NS>
+template <int NS, bool CTAB>
 __device__ __forceinline__ void wtail_fast(const FastCtx &c, const Instr &in, uint32_t op,
 		const float fr[NS]) {
 	const uint4 og = lds128u(op + OS_TIME);      /* time, type|flags|mode|oscflags, i0, i1 */
@@ -1651,13 +1697,24 @@ __device__ __forceinline__ void wtail_fast(const FastCtx &c, const Instr &in, ui
 	float s[NS];
 	{
 		const uint32_t slot = __popc(c.wave_mask & ((1u << wave) - 1u));
-		const uint32_t taps = c.st + slot * (TAB_STRIDE * 4) + 12;    /* &lut[-1] */
 		double Is[NS];
+		if (CTAB) {
+			/* per-index coefficients from shared memory: two 128-bit loads, Horner */
+			const uint32_t ct = c.st + slot * CTAB_WAVE_BYTES;
 #pragma unroll
-		for (int k = 0; k < NS; ++k) {
-			const uint32_t a = taps + ((ph[k] >> sau::WAVE_SLENBITS) << 2);
-			const float s0 = lds32f(a), s1 = lds32f(a + 4), s2 = lds32f(a + 8), s3 = lds32f(a + 12);
-			Is[k] = sau::herp_poly(s0, s1, s2, s3, ph[k]) + (double) s1;
+			for (int k = 0; k < NS; ++k) {
+				const uint32_t a = ct + ((ph[k] >> sau::WAVE_SLENBITS) << 4);
+				const double2 hi = lds128d(a), lo = lds128d(a + CTAB_PLANE_BYTES);
+				Is[k] = sau::herp_horner(hi.x, hi.y, lo.x, ph[k]) + lo.y;
+			}
+		} else {
+			const uint32_t taps = c.st + slot * (TAB_STRIDE * 4) + 12;    /* &lut[-1] */
+#pragma unroll
+			for (int k = 0; k < NS; ++k) {
+				const uint32_t a = taps + ((ph[k] >> sau::WAVE_SLENBITS) << 2);
+				const float s0 = lds32f(a), s1 = lds32f(a + 4), s2 = lds32f(a + 8), s3 = lds32f(a + 12);
+				Is[k] = sau::herp_poly(s0, s1, s2, s3, ph[k]) + (double) s1;
+			}
 		}
 		uint32_t pph = __shfl_up_sync(FULL, ph[NS - 1], 1);
 		double pIs = __shfl_up_sync(FULL, Is[NS - 1], 1);
@@ -1720,7 +1777,7 @@ __device__ __forceinline__ void wtail_fast(const FastCtx &c, const Instr &in, ui
 	__syncwarp();
 }
 
-template <int NS>
+template <int NS, bool CTAB>
 __device__ __forceinline__ void run_chunk_fast(const FastCtx &c, const Instr *code,
 		uint32_t code_len, float *row_s, float *row_r) {
 	for (uint32_t pc = 0; pc < code_len; ++pc) {
@@ -1746,7 +1803,7 @@ __device__ __forceinline__ void run_chunk_fast(const FastCtx &c, const Instr *co
 				if (is_line) { fst<NS>(c, in.a, fr); break; }
 				if (in.opcode == I_WHEAD) { fst<NS>(c, in.b, fr); break; }
 			}
-			wtail_fast<NS>(c, in, op, fr);
+			wtail_fast<NS, CTAB>(c, in, op, fr);
 			break; }
 		case I_RANGE: {                                            /* generator.c:465-467 */
 			float p[NS], r[NS], m[NS];
@@ -1784,11 +1841,12 @@ __device__ __forceinline__ void run_chunk_fast(const FastCtx &c, const Instr *co
 
 /* One steady reference block: its own function, so that the hot loop gets its
  * own register allocation whatever the general path around the call needs. */
+template <bool CTAB>
 __device__ __noinline__ void run_block_fast(FastCtx fc, const Instr *code, uint32_t code_len,
 		float *row_s, float *row_r) {
 	for (uint32_t oc = 0; oc < (uint32_t) REF_BLOCK; oc += FastCfg<FAST_NS>::CHUNKF) {
 		fc.oc = oc;
-		run_chunk_fast<FAST_NS>(fc, code, code_len, row_s + oc, row_r + oc);
+		run_chunk_fast<FAST_NS, CTAB>(fc, code, code_len, row_s + oc, row_r + oc);
 	}
 }
 
@@ -1880,8 +1938,12 @@ __device__ __forceinline__ void render_units(Ctx &c, FastCtx &fc, const CallDesc
 					vs.duration >= (uint32_t) REF_BLOCK && vs.code_len &&
 					op_ptr(c, vs.carr_slot)->time > 0 &&
 					steady_check(c.sops, g->code + vs.code_off, vs.code_len)) {
-				run_block_fast(fc, g->code + vs.code_off, vs.code_len,
-						row_s + sd.start + off, row_r + sd.start + off);
+				if (fc.wave_mask & CTAB_FLAG)
+					run_block_fast<true>(fc, g->code + vs.code_off, vs.code_len,
+							row_s + sd.start + off, row_r + sd.start + off);
+				else
+					run_block_fast<false>(fc, g->code + vs.code_off, vs.code_len,
+							row_s + sd.start + off, row_r + sd.start + off);
 				__syncwarp();
 				if (lane == 0) steady_update(c.sops, g->code + vs.code_off, vs.code_len);
 				__syncwarp();
@@ -1926,36 +1988,43 @@ __device__ __forceinline__ void render_units(Ctx &c, FastCtx &fc, const CallDesc
 
 __device__ __forceinline__ void render_body(const CallDesc *calls, uint32_t ncalls,
 		const SegDesc *segs, const UnitDesc *units, uint32_t ntasks, const float *tables,
-		uint32_t wave_mask, uint32_t nbufs, uint32_t nslots_ops, uint32_t warps_per_cta,
+		const double *coefs, uint32_t wave_mask, uint32_t nbufs, uint32_t nslots_ops, uint32_t warps_per_cta,
 		uint32_t ticketed) {
 	extern __shared__ __align__(128) unsigned char smem[];
 	uint64_t *bar = reinterpret_cast<uint64_t*>(smem);
 	float *tab = reinterpret_cast<float*>(smem + 128);
-	const uint32_t nslots = __popc(wave_mask);
-	unsigned char *warp_area = smem + 128 + nslots * TAB_STRIDE * sizeof(float);
+	const bool ctab = (wave_mask & CTAB_FLAG) != 0;
+	const uint32_t nslots = __popc(wave_mask & ~CTAB_FLAG);
+	const uint32_t slot_bytes = ctab ? CTAB_WAVE_BYTES : TAB_STRIDE * (uint32_t) sizeof(float);
+	unsigned char *warp_area = smem + 128 + nslots * slot_bytes;
 	const uint32_t per_warp = warp_smem_bytes(nbufs, nslots_ops);
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-	/* stage the wave tables this launch needs: TMA bulk copies, one mbarrier */
+	/* stage the tables this launch needs: TMA bulk copies, one mbarrier */
 	if (threadIdx.x == 0) {
 		mbar_init(bar, 1);
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
 	__syncthreads();
 	if (threadIdx.x == 0 && nslots) {
-		mbar_expect_tx(bar, nslots * WAVE_LEN * (uint32_t) sizeof(float));
+		mbar_expect_tx(bar, nslots * (ctab ? CTAB_WAVE_BYTES : WAVE_LEN * (uint32_t) sizeof(float)));
 		uint32_t slot = 0;
 		for (uint32_t w = 0; w < NUM_WAVES; ++w) {
 			if (!(wave_mask & (1u << w))) continue;
-			tma_bulk_g2s(tab + slot * TAB_STRIDE + 4, tables + w * WAVE_LEN,
-					WAVE_LEN * sizeof(float), bar);
+			if (ctab)
+				tma_bulk_g2s(smem + 128 + slot * CTAB_WAVE_BYTES,
+						reinterpret_cast<const unsigned char*>(coefs) + (size_t) w * CTAB_WAVE_BYTES,
+						CTAB_WAVE_BYTES, bar);
+			else
+				tma_bulk_g2s(tab + slot * TAB_STRIDE + 4, tables + w * WAVE_LEN,
+						WAVE_LEN * sizeof(float), bar);
 			++slot;
 		}
 	}
 	if (nslots) {
 		mbar_wait(bar, 0);
 		/* wrapped neighbours: lut[-1], lut[2048], lut[2049] */
-		if (threadIdx.x < nslots) {
+		if (!ctab && threadIdx.x < nslots) {
 			float *t = tab + threadIdx.x * TAB_STRIDE + 4;
 			t[-1] = t[WAVE_LEN - 1];
 			t[WAVE_LEN] = t[0];
@@ -1970,15 +2039,15 @@ __device__ __forceinline__ void render_body(const CallDesc *calls, uint32_t ncal
 	c.stk_len = reinterpret_cast<uint32_t*>(c.bufs + nbufs * BUF_FLOATS);
 	c.stk_rem = c.stk_len + MAX_NEST;
 	c.stk_layer = c.stk_rem + MAX_NEST;
-	c.tab = tab;
+	c.tab = tab;                     /* staged float tables, or the coefficient planes */
 	c.wc = reinterpret_cast<const WaveCoeffs*>(tables + NUM_WAVES * WAVE_LEN);
 	c.wave_mask = wave_mask;
 	c.lane = lane;
 	FastCtx fc;
 	fc.so = smem_u32(c.sops);
 	fc.sb = smem_u32(c.bufs) + lane * 16;
-	fc.st = smem_u32(tab);
-	fc.tab = tab; fc.wc = c.wc;
+	fc.st = smem_u32(tab);           /* staged float tables, or the coefficient tables */
+	fc.tab = c.tab; fc.wc = c.wc;
 	fc.wave_mask = wave_mask; fc.lane = lane;
 
 	if (!ticketed) {
@@ -1995,14 +2064,68 @@ __device__ __forceinline__ void render_body(const CallDesc *calls, uint32_t ncal
 		render_units(c, fc, cd, segs, units, task - cd->task_base, 0, cd->nunits);
 		return;
 	}
+	const CallDesc *cd = &calls[0];
+	const GenDesc *g = cd->gen;
+	const uint32_t nlv = g->voice_end - g->voice_begin;
+	if (ticketed == 2) {
+		/* Balanced: more voices than resident warps, all of them alike.  The
+		 * (voice, unit) items of the call, voice-major, are cut into one contiguous
+		 * range per warp of a grid that is resident all at once, so every warp gets
+		 * the same amount of work (+-1 unit) and there is no second, partly filled
+		 * wave.  A range covers the tail of one voice, whole voices, and the head
+		 * of another.  The head comes FIRST (it depends on nothing), the tail LAST:
+		 * it continues what the previous warp rendered as its first action, handed
+		 * over through L2 (progress[], release / acquire).  Warp ranks are taken
+		 * from a counter, so the warp holding the previous rank has already started. */
+		const uint32_t U = cd->nunits;
+		const uint64_t items = (uint64_t) nlv * U;
+		const uint64_t S = (uint64_t) gridDim.x * warps_per_cta;
+		uint32_t rank = 0;
+		if (lane == 0) rank = atomicAdd(g->ticket, 1u);
+		rank = __shfl_sync(FULL, rank, 0);
+		const uint64_t begin = rank * items / S, end = (rank + 1ull) * items / S;
+		if (begin >= end) return;
+		const uint32_t vA = (uint32_t) (begin / U), uA = (uint32_t) (begin - (uint64_t) vA * U);
+		const uint32_t vB = (uint32_t) ((end - 1) / U), uB = (uint32_t) (end - (uint64_t) vB * U);
+		auto publish = [&](uint32_t lv, uint32_t u) {
+			__threadfence();
+			__syncwarp();
+			if (lane == 0) *(volatile uint32_t*) (g->progress + lv) = u;
+		};
+		auto await = [&](uint32_t lv, uint32_t u) {
+			if (lane == 0) {
+				volatile uint32_t *pr = g->progress + lv;
+				while (*pr != u) __nanosleep(64);
+				__threadfence();
+			}
+			__syncwarp();
+		};
+		if (vA == vB) {
+			if (uA) await(vA, uA);
+			render_units(c, fc, cd, segs, units, vA, uA, uB);
+			if (uB < U) publish(vA, uB);
+			return;
+		}
+		uint32_t v_hi = vB;                    /* whole voices are [v_lo, v_hi] */
+		if (uB < U) {
+			render_units(c, fc, cd, segs, units, vB, 0, uB);
+			publish(vB, uB);
+			--v_hi;
+		}
+		const uint32_t v_lo = uA ? vA + 1 : vA;
+		for (uint32_t v = v_lo; v <= v_hi; ++v)
+			render_units(c, fc, cd, segs, units, v, 0, U);
+		if (uA) {
+			await(vA, uA);
+			render_units(c, fc, cd, segs, units, vA, uA, U);
+		}
+		return;
+	}
 	/* Ticketed: a persistent grid hands out (unit, voice) pairs in time order, so
 	 * that SMs stay evenly loaded when there are more voices than resident warps.
 	 * Unit u of a voice may start once its unit u-1 is done (progress[], release /
 	 * acquire through global memory); the holder of every earlier ticket is
 	 * already running, so the wait always ends. */
-	const CallDesc *cd = &calls[0];
-	const GenDesc *g = cd->gen;
-	const uint32_t nlv = g->voice_end - g->voice_begin;
 	const uint32_t total = nlv * cd->nunits;
 	for (;;) {
 		uint32_t t = 0;
@@ -2025,9 +2148,19 @@ __device__ __forceinline__ void render_body(const CallDesc *calls, uint32_t ncal
 
 __global__ void __launch_bounds__(256, 2)
 render_kernel(const CallDesc *calls, uint32_t ncalls, const SegDesc *segs, const UnitDesc *units,
-		uint32_t ntasks, const float *tables, uint32_t wave_mask, uint32_t nbufs,
+		uint32_t ntasks, const float *tables, const double *coefs, uint32_t wave_mask, uint32_t nbufs,
 		uint32_t nslots_ops, uint32_t warps_per_cta, uint32_t ticketed) {
-	render_body(calls, ncalls, segs, units, ntasks, tables, wave_mask, nbufs, nslots_ops,
+	render_body(calls, ncalls, segs, units, ntasks, tables, coefs, wave_mask, nbufs, nslots_ops,
+			warps_per_cta, ticketed);
+}
+
+/* same body for CTAs of up to 16 warps, one per SM (coefficient-table mode: the
+ * tables take 64 KiB per wave, so one large CTA shares them among more warps) */
+__global__ void __launch_bounds__(512, 1)
+render_kernel_wide(const CallDesc *calls, uint32_t ncalls, const SegDesc *segs, const UnitDesc *units,
+		uint32_t ntasks, const float *tables, const double *coefs, uint32_t wave_mask, uint32_t nbufs,
+		uint32_t nslots_ops, uint32_t warps_per_cta, uint32_t ticketed) {
+	render_body(calls, ncalls, segs, units, ntasks, tables, coefs, wave_mask, nbufs, nslots_ops,
 			warps_per_cta, ticketed);
 }
 
@@ -2151,33 +2284,82 @@ cudaError_t launch_selftest(const float *d_tables, unsigned long long *d_bad, cu
 
 /* ---- host-callable launchers -------------------------------------------- */
 
+/* wave_mask may carry CTAB_FLAG (coefficient tables in shared memory) */
 size_t render_smem_bytes(uint32_t wave_mask, uint32_t nbufs, uint32_t nslots_ops, uint32_t warps) {
 	uint32_t nslots = 0;
 	for (uint32_t w = 0; w < NUM_WAVES; ++w) if (wave_mask & (1u << w)) ++nslots;
-	return 128 + (size_t) nslots * TAB_STRIDE * sizeof(float) +
-		(size_t) warps * warp_smem_bytes(nbufs, nslots_ops);
+	const size_t slot = (wave_mask & CTAB_FLAG) ? CTAB_WAVE_BYTES : TAB_STRIDE * sizeof(float);
+	return 128 + (size_t) nslots * slot + (size_t) warps * warp_smem_bytes(nbufs, nslots_ops);
 }
 
-/* grid: one warp per voice task, or (ticketed) a persistent grid of `grid_ctas` */
+/* ---- per-index cubic coefficients of every wave table -------------------- *
+ * sauWave_get_herp (wave.h:127-141, as compiled: sau::herp_poly) forms c1, c2,
+ * c3 from the four taps around an index before it touches the phase fraction;
+ * they depend on the index alone.  One thread per (wave, index) evaluates the
+ * SAME expressions once; the fast path then loads {c3, c2} and {c1, (double)
+ * s1} with two 128-bit shared-memory loads.  Layout per wave: 2048 x {c3, c2},
+ * then 2048 x {c1, c0}. */
+__global__ void coef_kernel(const float *tables, double *coefs) {
+	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= NUM_WAVES * WAVE_LEN) return;
+	const uint32_t w = t / WAVE_LEN, i = t % WAVE_LEN;
+	const float *lut = tables + w * WAVE_LEN;
+	const float s0 = lut[(i - 1) & sau::WAVE_LENMASK], s1 = lut[i];
+	const float s2 = lut[(i + 1) & sau::WAVE_LENMASK], s3 = lut[(i + 2) & sau::WAVE_LENMASK];
+	double c1, c2, c3;
+	sau::herp_coefs(s0, s1, s2, s3, &c1, &c2, &c3);
+	double *base = coefs + (size_t) w * (CTAB_WAVE_BYTES / 8);
+	base[2 * i] = c3; base[2 * i + 1] = c2;
+	base[2 * WAVE_LEN + 2 * i] = c1; base[2 * WAVE_LEN + 2 * i + 1] = (double) s1;
+}
+size_t coef_table_bytes() { return (size_t) NUM_WAVES * CTAB_WAVE_BYTES; }
+cudaError_t launch_coefs(const float *d_tables, double *d_coefs, cudaStream_t stream) {
+	coef_kernel<<<(NUM_WAVES * WAVE_LEN + 255) / 256, 256, 0, stream>>>(d_tables, d_coefs);
+	return cudaGetLastError();
+}
+
+/* grid: one warp per voice task, or a persistent grid of `ticketed_ctas` CTAs with
+ * sched_mode 1 = (unit, voice) tickets, 2 = balanced contiguous ranges */
+static cudaError_t ensure_smem(bool wide, size_t smem) {
+	int dev = 0;
+	cudaGetDevice(&dev);
+	static size_t configured[2][64] = {{0}, {0}};
+	if (dev >= 0 && dev < 64 && smem > configured[wide][dev]) {
+		cudaError_t e = wide ?
+			cudaFuncSetAttribute(render_kernel_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem) :
+			cudaFuncSetAttribute(render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+		if (e != cudaSuccess) return e;
+		configured[wide][dev] = smem;
+	}
+	return cudaSuccess;
+}
+int render_ctas_per_sm(size_t smem, uint32_t warps) {
+	int n = 0;
+	if (ensure_smem(warps > 8, smem) != cudaSuccess) return 0;
+	cudaError_t e = warps > 8 ?
+		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, render_kernel_wide, (int) warps * 32, smem) :
+		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, render_kernel, (int) warps * 32, smem);
+	return e == cudaSuccess ? n : 0;
+}
 cudaError_t launch_render(const CallDesc *d_calls, uint32_t ncalls, const SegDesc *d_segs,
-		const UnitDesc *d_units, uint32_t ntasks, const float *d_tables, uint32_t wave_mask,
-		uint32_t nbufs, uint32_t nslots_ops, uint32_t warps, uint32_t ticketed_ctas,
-		cudaStream_t stream) {
+		const UnitDesc *d_units, uint32_t ntasks, const float *d_tables, const double *d_coefs,
+		uint32_t wave_mask, uint32_t nbufs, uint32_t nslots_ops, uint32_t warps,
+		uint32_t ticketed_ctas, uint32_t sched_mode, cudaStream_t stream) {
 	if (ntasks == 0) return cudaSuccess;
 	if (nslots_ops == 0) nslots_ops = 1;
 	const size_t smem = render_smem_bytes(wave_mask, nbufs, nslots_ops, warps);
-	int dev = 0;
-	cudaGetDevice(&dev);
-	static size_t configured[64] = {0};
-	if (dev >= 0 && dev < 64 && smem > configured[dev]) {
-		cudaError_t e = cudaFuncSetAttribute(render_kernel,
-				cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+	const bool wide = warps > 8;
+	{
+		cudaError_t e = ensure_smem(wide, smem);
 		if (e != cudaSuccess) return e;
-		configured[dev] = smem;
 	}
 	const uint32_t grid = ticketed_ctas ? ticketed_ctas : (ntasks + warps - 1) / warps;
-	render_kernel<<<grid, warps * 32, smem, stream>>>(d_calls, ncalls, d_segs, d_units, ntasks,
-			d_tables, wave_mask, nbufs, nslots_ops, warps, ticketed_ctas ? 1u : 0u);
+	if (wide)
+		render_kernel_wide<<<grid, warps * 32, smem, stream>>>(d_calls, ncalls, d_segs, d_units, ntasks,
+				d_tables, d_coefs, wave_mask, nbufs, nslots_ops, warps, ticketed_ctas ? sched_mode : 0u);
+	else
+		render_kernel<<<grid, warps * 32, smem, stream>>>(d_calls, ncalls, d_segs, d_units, ntasks,
+				d_tables, d_coefs, wave_mask, nbufs, nslots_ops, warps, ticketed_ctas ? sched_mode : 0u);
 	return cudaGetLastError();
 }
 

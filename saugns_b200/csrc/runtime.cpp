@@ -28,9 +28,12 @@
 namespace saugen {
 size_t render_smem_bytes(uint32_t wave_mask, uint32_t nbufs, uint32_t nslots_ops, uint32_t warps);
 cudaError_t launch_render(const CallDesc *d_calls, uint32_t ncalls, const SegDesc *d_segs,
-		const UnitDesc *d_units, uint32_t ntasks, const float *d_tables, uint32_t wave_mask,
-		uint32_t nbufs, uint32_t nslots_ops, uint32_t warps, uint32_t ticketed_ctas,
-		cudaStream_t stream);
+		const UnitDesc *d_units, uint32_t ntasks, const float *d_tables, const double *d_coefs,
+		uint32_t wave_mask, uint32_t nbufs, uint32_t nslots_ops, uint32_t warps,
+		uint32_t ticketed_ctas, uint32_t sched_mode, cudaStream_t stream);
+int render_ctas_per_sm(size_t smem, uint32_t warps);
+size_t coef_table_bytes();
+cudaError_t launch_coefs(const float *d_tables, double *d_coefs, cudaStream_t stream);
 cudaError_t launch_mix(const CallDesc *d_calls, uint32_t ncalls, const SegDesc *d_segs,
 		uint32_t max_call_len, uint32_t mode, cudaStream_t stream);
 cudaError_t launch_planes_to_pcm(const float *d_mix, uint32_t plane_stride, uint32_t n,
@@ -58,11 +61,11 @@ static uint32_t ms_in_samples(uint64_t ms, uint64_t srate, int *carry) {   /* sa
 
 /* ---- device wave-table blocks, shared by content ------------------------ */
 
-struct TableBlock { float *d; };
+struct TableBlock { float *d; double *coefs; };
 static std::mutex g_tab_mu;
 static std::map<std::pair<int, uint64_t>, TableBlock> g_tabs;
 
-static float *get_device_tables(int device, const saugen_WaveTables *t) {
+static float *get_device_tables(int device, const saugen_WaveTables *t, double **coefs_out = nullptr) {
 	std::vector<float> host((size_t) NUM_WAVES * WAVE_LEN + sizeof(WaveCoeffs) / sizeof(float));
 	for (int w = 0; w < NUM_WAVES; ++w)
 		memcpy(&host[(size_t) w * WAVE_LEN], t->pilut[w], sizeof(float) * WAVE_LEN);
@@ -80,14 +83,25 @@ static float *get_device_tables(int device, const saugen_WaveTables *t) {
 	std::lock_guard<std::mutex> lk(g_tab_mu);
 	auto key = std::make_pair(device, h);
 	auto it = g_tabs.find(key);
-	if (it != g_tabs.end()) return it->second.d;
+	if (it != g_tabs.end()) {
+		if (coefs_out) *coefs_out = it->second.coefs;
+		return it->second.d;
+	}
 	float *d = nullptr;
+	double *dc = nullptr;
 	if (cudaMalloc(&d, host.size() * sizeof(float)) != cudaSuccess) return nullptr;
-	if (cudaMemcpy(d, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
+	if (cudaMemcpy(d, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess ||
+	    cudaMalloc(&dc, coef_table_bytes()) != cudaSuccess) {
 		cudaFree(d);
 		return nullptr;
 	}
-	g_tabs[key] = TableBlock{d};
+	/* per-index cubic coefficients, computed once on the device from the uploaded tables */
+	if (launch_coefs(d, dc, 0) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) {
+		cudaFree(d); cudaFree(dc);
+		return nullptr;
+	}
+	g_tabs[key] = TableBlock{d, dc};
+	if (coefs_out) *coefs_out = dc;
 	return d;
 }
 
@@ -119,6 +133,8 @@ struct saugen_Generator {
 	GenDesc h_desc;
 	GenDesc *d_desc = nullptr;
 	float *d_tables = nullptr;
+	double *d_coefs = nullptr;
+	bool ctab_ok = false;              // every voice program is fast-path material (see create)
 	void *d_ops = nullptr, *d_voices = nullptr, *d_events = nullptr, *d_opdata = nullptr,
 	     *d_code = nullptr, *d_prog_ops = nullptr, *d_vev_off = nullptr, *d_vev_idx = nullptr;
 	float *d_rows_s = nullptr, *d_rows_r = nullptr, *d_mix = nullptr;
@@ -159,28 +175,61 @@ struct Compiler {
 		if (slot_of[op] < 0) { slot_of[op] = (int32_t) prog_ops.size(); prog_ops.push_back(op); }
 		return (uint32_t) slot_of[op];
 	}
-	void use_buf(uint32_t x) {
-		if (x == NO_BUF) return;
-		if (x + 1 > max_buf) max_buf = x + 1;
-		if (max_buf >= 250) too_deep = true;
+	/* which fields of an instruction name work buffers: bit 0..4 = a..e, bit 5 =
+	 * the buffer after b too (self-PM scratch) */
+	std::vector<uint8_t> bufmask;
+	static uint8_t buf_fields(uint8_t opc, uint32_t d, uint16_t flags) {
+		enum { A = 1, B = 2, Cc = 4, D = 8, E = 16, B1 = 32 };
+		switch (opc) {
+		case I_LINE: return (uint8_t) ((d ? A : 0) | B);
+		case I_VPAN: return A;
+		case I_WLEAF: return (uint8_t) (A | E | ((flags & F_MAY_SELFMOD) ? (B | B1) : 0) |
+				((flags & F_KEEP_FREQ) ? B : 0));
+		case I_WHEAD: return A | B | E;
+		case I_WTAIL: return (uint8_t) (A | B | Cc | D | ((flags & F_MAY_SELFMOD) ? B1 : 0));
+		case I_END: return 0;
+		default: return A | B | Cc | D | E;
+		}
 	}
 	void emit(uint8_t opc, uint32_t op_slot, uint32_t a, uint32_t b = NO_BUF, uint32_t c = NO_BUF,
 			uint32_t d = NO_BUF, uint32_t e = NO_BUF, uint16_t flags = 0) {
 		Instr i;
 		i.opcode = opc; i.a = (uint8_t) a; i.b = (uint8_t) b; i.c = (uint8_t) c;
 		i.d = (uint8_t) d; i.e = (uint8_t) e; i.flags = flags; i.op = op_slot; i.aux = 0;
-		switch (opc) {                     /* which fields name work buffers */
-		case I_LINE: if (d) use_buf(a); use_buf(b); break;
-		case I_VPAN: use_buf(a); break;
-		case I_WLEAF: use_buf(a); use_buf(e);
-			if (flags & F_MAY_SELFMOD) { use_buf(b); use_buf(b + 1); } break;
-		case I_WHEAD: use_buf(a); use_buf(b); use_buf(e); break;
-		case I_WTAIL: use_buf(a); use_buf(b); use_buf(c); use_buf(d);
-			if (flags & F_MAY_SELFMOD) use_buf(b + 1); break;
-		case I_END: break;
-		default: use_buf(a); use_buf(b); use_buf(c); use_buf(d); use_buf(e); break;
-		}
+		if (a != NO_BUF && a >= 250) too_deep = true;
+		if (b != NO_BUF && b >= 249) too_deep = true;
+		if (c != NO_BUF && c >= 250) too_deep = true;
+		if (e != NO_BUF && e >= 250) too_deep = true;
 		out.push_back(i);
+		bufmask.push_back(buf_fields(opc, d, flags));
+	}
+	/* Renumber the work buffers a finished voice program really uses to 0..n-1,
+	 * keeping their order (so "b and the buffer after it" stays adjacent): the
+	 * recursive numbering (base + k per nesting level) leaves gaps, and every
+	 * buffer costs each warp 1 KiB of shared memory. */
+	void compact_buffers() {
+		bool used[256] = {false};
+		for (size_t k = 0; k < out.size(); ++k) {
+			const Instr &i = out[k];
+			const uint8_t m = bufmask[k];
+			const uint8_t f[5] = {i.a, i.b, i.c, i.d, i.e};
+			for (int q = 0; q < 5; ++q) if ((m >> q & 1) && f[q] != NO_BUF) used[f[q]] = true;
+			if ((m & 32) && i.b != NO_BUF) used[i.b + 1] = true;
+		}
+		uint8_t map[256];
+		uint32_t n = 0;
+		for (int b = 0; b < 255; ++b) map[b] = used[b] ? (uint8_t) n++ : (uint8_t) NO_BUF;
+		map[NO_BUF] = NO_BUF;
+		for (size_t k = 0; k < out.size(); ++k) {
+			Instr &i = out[k];
+			const uint8_t m = bufmask[k];
+			if (m & 1) i.a = map[i.a];
+			if (m & 2) i.b = map[i.b];
+			if (m & 4) i.c = map[i.c];
+			if (m & 8) i.d = map[i.d];
+			if (m & 16) i.e = map[i.e];
+		}
+		if (n > max_buf) max_buf = n;
 	}
 	static uint32_t cnt(const sauabi_ProgramIDArr *a) { return a ? a->count : 0; }
 
@@ -229,6 +278,9 @@ struct Compiler {
 			if (n.line_set[LINE_FREQ2]) wf |= F_SKIP_FREQ2;
 			if (n.line_set[LINE_AMP2]) wf |= F_SKIP_AMP2;
 			if (n.line_set[LINE_PMA]) wf |= F_MAY_SELFMOD;
+			/* the carrier's pan modulators take its frequency buffer as their
+			 * parent frequency (mix_add, generator.c:764-766) */
+			if (depth == 1 && cnt(n.mods[SAUABI_POP_camod])) wf |= F_KEEP_FREQ;
 			if (simple_freq && simple_amp && !kids) {
 				emit(I_WLEAF, sl, base, freq, NO_BUF, NO_BUF, parent_freq, wf);
 				onstack[op] = 0; --depth;
@@ -309,6 +361,7 @@ struct Compiler {
 	/* run_voice + mix_add, generator.c:749-788,833-846 */
 	void voice(uint32_t carr) {
 		out.clear();
+		bufmask.clear();
 		for (uint32_t op : prog_ops) slot_of[op] = -1;
 		prog_ops.clear();
 		if (carr >= ops.size() || !ops[carr].inited) { emit(I_END, 0, 0); return; }
@@ -322,6 +375,7 @@ struct Compiler {
 			visit(cl->ids[i], 1 + fb, fb ? fb : NO_BUF, false, F_LAYER);
 		emit(I_VOUT, cs, 0, 1 + fb);
 		emit(I_END, 0, 0);
+		compact_buffers();
 	}
 };
 
@@ -494,7 +548,7 @@ extern "C" saugen_Generator *saugen_create(const sauabi_Program *prg, uint32_t s
 	CK(cudaSetDevice(o->device));
 	if (opt->stream) o->stream = (cudaStream_t) opt->stream;
 	else { CK(cudaStreamCreateWithFlags(&o->stream, cudaStreamNonBlocking)); o->own_stream = true; }
-	o->d_tables = get_device_tables(o->device, tables);
+	o->d_tables = get_device_tables(o->device, tables, &o->d_coefs);
 	if (!o->d_tables) { set_err("wave table upload", cudaGetLastError()); goto fail; }
 	{
 		size_t nops = prg->op_count ? prg->op_count : 1, nvo = prg->vo_count ? prg->vo_count : 1;
@@ -602,10 +656,10 @@ static void plan_call(saugen_Generator *o, uint32_t buf_len, std::vector<SegDesc
 
 /* Cut the segments of a call into schedulable units of at most UNIT_BLOCKS
  * reference blocks, on the segment's own block grid. */
-static const uint32_t UNIT_BLOCKS = 4;
-static void plan_units(const std::vector<SegDesc> &segs, std::vector<UnitDesc> &units) {
+static void plan_units(const std::vector<SegDesc> &segs, std::vector<UnitDesc> &units,
+		uint32_t unit_blocks = 4) {
 	units.clear();
-	const uint32_t ul = UNIT_BLOCKS * REF_BLOCK;
+	const uint32_t ul = unit_blocks * REF_BLOCK;
 	for (uint32_t s = 0; s < segs.size(); ++s) {
 		uint32_t off = 0;
 		do {
@@ -618,15 +672,39 @@ static void plan_units(const std::vector<SegDesc> &segs, std::vector<UnitDesc> &
 	}
 }
 
-/* CTA shape: small CTAs while there are fewer tasks than SMs x warps, 8-warp
- * CTAs (3 per SM, 80 registers) up to 24 warps per SM, and 16-warp CTAs (2 per
- * SM, 64 registers) beyond that when their shared memory fits twice per SM. */
-static uint32_t pick_warps(uint32_t ntasks, uint32_t wave_mask, uint32_t nbufs, uint32_t max_ops) {
+/* Launch shape of render_kernel for `ntasks` voice tasks.
+ * Coefficient-table mode (kernels.cu:CTAB_FLAG) when the launch uses at most two
+ * waves: their coefficient planes (64 KiB each) go to shared memory and one wide
+ * CTA per SM shares them among up to 16 warps.  Otherwise the float tables
+ * (8 KiB per wave) are staged and 8-warp CTAs run 2 per SM (128 registers).
+ * Small CTAs while there are fewer tasks than SMs x warps. */
+static const uint32_t CTAB_FLAG = 0x80000000u;
+static const size_t SMEM_CAP = 227 * 1024;
+struct Shape { uint32_t warps; uint32_t mask; };
+static Shape pick_shape(uint32_t ntasks, uint32_t wave_mask, uint32_t nbufs, uint32_t max_ops,
+		bool have_coefs) {
 	const uint32_t sms = 148;
-	uint32_t warps = 8;
-	while (warps > 1 && (ntasks + warps - 1) / warps < sms) warps >>= 1;
-	while (warps > 1 && render_smem_bytes(wave_mask, nbufs, max_ops, warps) > 200 * 1024) warps >>= 1;
-	return warps;
+	int nw = 0;
+	for (uint32_t w = 0; w < NUM_WAVES; ++w) if (wave_mask & (1u << w)) ++nw;
+	static const char *env = getenv("SAUGEN_CTAB");       /* developer knob: 0 = off */
+	const bool want_ctab = have_coefs && nw >= 1 && nw <= 2 && !(env && env[0] == '0');
+	Shape sh;
+	if (want_ctab) {
+		sh.mask = wave_mask | CTAB_FLAG;
+		sh.warps = 16;
+		while (sh.warps > 1 && (ntasks + sh.warps - 1) / sh.warps < sms) sh.warps >>= 1;
+		if (sh.warps == 16 || (ntasks + 15) / 16 >= sms) {
+			/* all SMs busy: the largest CTA that fits */
+			sh.warps = 16;
+			while (sh.warps > 4 && render_smem_bytes(sh.mask, nbufs, max_ops, sh.warps) > SMEM_CAP) --sh.warps;
+		}
+		if (render_smem_bytes(sh.mask, nbufs, max_ops, sh.warps) <= SMEM_CAP) return sh;
+	}
+	sh.mask = wave_mask;
+	sh.warps = 8;
+	while (sh.warps > 1 && (ntasks + sh.warps - 1) / sh.warps < sms) sh.warps >>= 1;
+	while (sh.warps > 1 && render_smem_bytes(sh.mask, nbufs, max_ops, sh.warps) > 200 * 1024) sh.warps >>= 1;
+	return sh;
 }
 
 /* mode: 0 = PCM in device memory, 1 = float planes */
@@ -665,7 +743,30 @@ static int run_common(saugen_Generator *o, size_t buf_len, int stereo, uint32_t 
 	}
 	const uint32_t nseg = (uint32_t) segs.size();
 	memcpy(o->h_segs, segs.data(), nseg * sizeof(SegDesc));
-	plan_units(segs, o->units_tmp);
+	/* Launch shape and scheduling.  sched: 0 = auto, 1 = one warp per voice, 2 =
+	 * persistent grid with (unit, voice) tickets, 3 = balanced contiguous ranges.
+	 * Auto picks balanced when the voices would otherwise need a second, partly
+	 * filled wave of warps (between 1 and 4 waves), else one warp per voice. */
+	const Shape shape = pick_shape(o->nlv, o->wave_mask, o->nbufs, o->max_ops, o->d_coefs != nullptr);
+	const uint32_t warps = shape.warps;
+	uint32_t ticketed_ctas = 0, sched_mode = 0;
+	{
+		const size_t smem = render_smem_bytes(shape.mask, o->nbufs, o->max_ops, warps);
+		int per_sm = render_ctas_per_sm(smem, warps);
+		if (per_sm < 1) per_sm = 1;
+		const uint32_t resident_ctas = 148u * (uint32_t) per_sm;
+		const uint32_t need = (o->nlv + warps - 1) / warps;
+		uint32_t sched = o->sched;
+		if (sched == 0)
+			sched = (need > resident_ctas && need < 4 * resident_ctas) ? 3 : 1;
+		if (sched == 3 && need <= resident_ctas) sched = 1;   /* a single wave is balanced already */
+		if (sched == 2 || sched == 3) {
+			ticketed_ctas = resident_ctas < need ? resident_ctas : (need ? need : 1);
+			sched_mode = sched == 2 ? 1 : 2;
+			if (getenv("SAUGEN_ONE_CTA")) ticketed_ctas = 1;
+		}
+	}
+	plan_units(segs, o->units_tmp, sched_mode == 2 ? 1 : 4);
 	if (o->units_tmp.size() > o->unit_cap) {
 		uint32_t cap = o->unit_cap;
 		while (cap < o->units_tmp.size()) cap *= 2;
@@ -683,24 +784,6 @@ static int run_common(saugen_Generator *o, size_t buf_len, int stereo, uint32_t 
 	CallDesc &cd = *o->h_call;
 	cd.gen = o->d_desc; cd.call_len = (uint32_t) buf_len; cd.nseg = nseg; cd.seg_off = 0;
 	cd.task_base = 0; cd.stereo = stereo ? 1 : 0; cd.unit_off = 0; cd.nunits = nunits; cd._pad = 0;
-	/* more voices than resident warps: persistent grid with (unit, voice) tickets */
-	const uint32_t warps = pick_warps(o->nlv, o->wave_mask, o->nbufs, o->max_ops);
-	uint32_t ticketed_ctas = 0;
-	{
-		const size_t smem = render_smem_bytes(o->wave_mask, o->nbufs, o->max_ops, warps);
-		uint32_t per_sm = (uint32_t) ((227 * 1024) / (smem + 1024));
-		const uint32_t by_threads = 512 / (warps * 32);    /* 128 registers per thread */
-		if (per_sm > by_threads) per_sm = by_threads;
-		if (per_sm < 1) per_sm = 1;
-		const uint32_t resident = 148 * per_sm * warps;
-		(void) resident;   /* auto = one warp per voice: measured faster at 4096 equal voices */
-		if (o->sched == 2) {
-			ticketed_ctas = 148 * per_sm;
-			const uint32_t need = (o->nlv + warps - 1) / warps;
-			if (ticketed_ctas > need) ticketed_ctas = need ? need : 1;
-			if (getenv("SAUGEN_ONE_CTA")) ticketed_ctas = 1;
-		}
-	}
 	cudaError_t e;
 	e = cudaMemcpyAsync(o->d_segs, o->h_segs, nseg * sizeof(SegDesc), cudaMemcpyHostToDevice, o->stream);
 	if (e == cudaSuccess) e = cudaMemcpyAsync(o->d_units, o->h_units, nunits * sizeof(UnitDesc), cudaMemcpyHostToDevice, o->stream);
@@ -711,8 +794,8 @@ static int run_common(saugen_Generator *o, size_t buf_len, int stereo, uint32_t 
 	o->timed_call = o->timing;
 	if (e == cudaSuccess && o->timed_call) e = cudaEventRecord(o->ev_t[0], o->stream);
 	if (e == cudaSuccess) {
-		e = launch_render(o->d_call, 1, o->d_segs, o->d_units, o->nlv, o->d_tables, o->wave_mask,
-				o->nbufs, o->max_ops, warps, ticketed_ctas, o->stream);
+		e = launch_render(o->d_call, 1, o->d_segs, o->d_units, o->nlv, o->d_tables, o->d_coefs,
+				shape.mask, o->nbufs, o->max_ops, warps, ticketed_ctas, sched_mode, o->stream);
 		o->counters[0]++;
 	}
 	if (e == cudaSuccess && o->timed_call) e = cudaEventRecord(o->ev_t[1], o->stream);
@@ -870,9 +953,9 @@ extern "C" int saugen_run_many(saugen_Generator *const *gens, size_t n, int16_t 
 	if (e == cudaSuccess) e = cudaMemcpyAsync(d_calls, calls.data(), calls.size() * sizeof(CallDesc), cudaMemcpyHostToDevice, g0->stream);
 	if (e == cudaSuccess) e = cudaMemcpyAsync(d_segs, segs.data(), segs.size() * sizeof(SegDesc), cudaMemcpyHostToDevice, g0->stream);
 	if (e == cudaSuccess) {
-		const uint32_t warps = pick_warps(ntasks, wave_mask, nbufs, max_ops);
+		const Shape shape = pick_shape(ntasks, wave_mask, nbufs, max_ops, g0->d_coefs != nullptr);
 		e = launch_render(d_calls, (uint32_t) calls.size(), d_segs, d_units, ntasks, g0->d_tables,
-				wave_mask, nbufs, max_ops, warps, 0, g0->stream);
+				g0->d_coefs, shape.mask, nbufs, max_ops, shape.warps, 0, 0, g0->stream);
 		g0->counters[0]++;
 	}
 	if (e == cudaSuccess) {

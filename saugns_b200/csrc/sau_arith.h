@@ -249,13 +249,20 @@ constexpr uint32_t WAVE_SLEN = 1u << 21, WAVE_SLENMASK = (1u << 21) - 1;
 /* sauWave_get_herp as compiled: c2 is associated (s0-2.5*s1)+(2*s2-0.5*s3)
  * (source: left to right), the Horner steps are as written in the source.
  * Returns the polynomial part; the caller adds c0 (needed apart by reset). */
-SAU_HD double herp_poly(float s0, float s1, float s2, float s3, uint32_t phase) {
+SAU_HD void herp_coefs(float s0, float s1, float s2, float s3, double *c1, double *c2, double *c3) {
+	*c1 = 0.5 * (double) (s2 - s0);
+	*c2 = ((double) s0 - 2.5 * (double) s1) + ((double) (s2 + s2) - 0.5 * (double) s3);
+	*c3 = 0.5 * (double) (s3 - s0) + 1.5 * (double) (s1 - s2);
+}
+SAU_HD double herp_horner(double c3, double c2, double c1, uint32_t phase) {
 	float xf = u2f(phase & WAVE_SLENMASK) * (1.f / 2097152.f);
 	double x = (double) xf;
-	double c1 = 0.5 * (double) (s2 - s0);
-	double c2 = ((double) s0 - 2.5 * (double) s1) + ((double) (s2 + s2) - 0.5 * (double) s3);
-	double c3 = 0.5 * (double) (s3 - s0) + 1.5 * (double) (s1 - s2);
 	return ((c3 * x + c2) * x + c1) * x;
+}
+SAU_HD double herp_poly(float s0, float s1, float s2, float s3, uint32_t phase) {
+	double c1, c2, c3;
+	herp_coefs(s0, s1, s2, s3, &c1, &c2, &c3);
+	return herp_horner(c3, c2, c1, phase);
 }
 template <typename LutPtr>
 SAU_HD double herp(LutPtr lut, uint32_t phase, double *poly_out, double *c0_out) {

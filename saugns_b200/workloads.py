@@ -9,6 +9,10 @@ field.  fm: False = PM chain, True = range-FM + PM, "mix" = alternating.
 """
 import random
 
+WAVES = ["sin", "tri", "srs", "sqr", "ean", "cat", "eto", "par", "mto", "saw", "hsi", "spa"]
+LINES = ["cos", "lin", "sah", "exp", "log", "xpe", "lge", "sqe", "cub", "smo", "ncl", "nhl", "uwh"]
+NOISES = ["wh", "gw", "bw", "tw", "re", "vi", "bv"]
+
 
 def _is_fm(fm, i):
     return (i % 2 == 1) if fm == "mix" else bool(fm)
@@ -62,3 +66,47 @@ def build_c3(n_voices=4096, secs=60, seed=1, fm=False):
                                          amp=P.value(1.0, goal=0.2, line="xpe"), mods={"pmod": [m1]})
         pb.add_voice(carr)
     return pb.finish()
+
+
+def synth_c4(n_voices=1024, secs=60, seed=2):
+    """BASELINE config 4: self-feedback PM carriers with range-AM / ring-mod."""
+    rnd = random.Random(seed)
+    lines = [f"S a.m{0.3 / n_voices ** 0.5:.6f}"]
+    for i in range(n_voices):
+        f = 110.0 * 2 ** rnd.uniform(0, 4)
+        c = rnd.uniform(-1, 1)
+        pa = rnd.uniform(0.3, 1.0)
+        fm = rnd.uniform(0.5, 8)
+        k = i % 3
+        if k == 0:
+            lines.append(f"Wsin f{f:.3f} t{secs} p.a{pa:.3f} a0.5.r1[Wsin f{fm:.3f}] c{c:.3f}")
+        elif k == 1:
+            lines.append(f"Rlin f{f:.3f} t{secs} p.a{pa:.3f} a0.5.r1[Wsin f{fm:.3f}] c{c:.3f}")
+        else:
+            lines.append(f"Wtri f{f:.3f} t{secs} p.a{pa:.3f} a0[Wsin f{fm * 20:.3f} a0.8] c{c:.3f}")
+    return "\n".join(lines) + "\n"
+
+
+def synth_c5_script(index):
+    """BASELINE config 5: one of the independent mixed scripts (seed 1000+index)."""
+    rnd = random.Random(1000 + index)
+    nv = rnd.randint(4, 16)
+    lines = [f"S a.m{0.3 / nv ** 0.5:.6f}"]
+    for _ in range(nv):
+        t = rnd.uniform(1, 10)
+        f = 110.0 * 2 ** rnd.uniform(0, 4)
+        c = rnd.uniform(-1, 1)
+        kind = rnd.randrange(4)
+        if kind == 0:
+            w, w2 = rnd.choice(WAVES), rnd.choice(WAVES)
+            lines.append(f"W{w} f{f:.3f} t{t:.3f} c{c:.3f} p[W{w2} r{rnd.choice([0.5, 1, 2, 3])} "
+                         f"a{rnd.uniform(0.1, 1):.3f}]")
+        elif kind == 1:
+            lines.append(f"N{rnd.choice(NOISES)} t{t:.3f} c{c:.3f} a{rnd.uniform(0.1, 0.8):.3f}")
+        elif kind == 2:
+            mode = rnd.choice("ugbtfa") + rnd.choice(["", "h", "p", "s", "v", "z"])
+            lines.append(f"R{rnd.choice(LINES)} m{mode} f{f:.3f} t{t:.3f} c{c:.3f}")
+        else:
+            lines.append(f"W{rnd.choice(WAVES)} f{f:.3f}[g{f * rnd.uniform(0.5, 2):.3f} "
+                         f"l{rnd.choice(LINES)}] t{t:.3f} c{c:.3f} a1.r0[Wsin f{rnd.uniform(0.5, 9):.3f}]")
+    return "\n".join(lines) + "\n"

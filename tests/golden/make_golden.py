@@ -5,7 +5,18 @@ For every script: frame count and sha256 of the 16-bit PCM the reference
 renders at the stated rate/channels, plus the integer oscillator state
 (phase / cycle / counter words) of every operator at the end.  Run from the
 repo root in the container that has /root/reference:
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py [out.json]
+
+HOST DEPENDENCE.  The reference builds its wave tables on the host with
+`-O3 -ffast-math` (sau/wave.c:77-221), and gcc vectorises the libm calls there
+into libmvec, whose last-bit rounding depends on the CPU's ISA dispatch: the
+srs/cat/mto tables (and so every answer that uses them) differ between the
+AMD EPYC container and the Xeon GPU boxes.  Each golden file therefore carries
+the sha256 of the 12 tables it was made with (`_meta.tables`) and, per entry,
+the waves the script uses; tests/gpuutil.golden() applies an answer only when
+the tables of the host under test match.  One file per table variant:
+known_answers.epyc.json (made in the build container), known_answers.xeon.json (made on a GPU
+box: `python tests/golden/make_golden.py gpurun_out/known_answers.box.json`).
 """
 import hashlib
 import json
@@ -17,6 +28,24 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 sys.path.insert(0, os.path.dirname(HERE))
 import scripts  # noqa: E402
 from oracle import pyref  # noqa: E402
+
+
+def wave_mask(prg):
+    """Waves whose tables a program can read (sin is every W operator's initial wave)."""
+    from saugns_b200 import program as P
+    m = 0
+    for ev in P.dump(prg.ptr)["events"]:
+        for od in ev["ops"]:
+            if od["type"] == P.POPT_WAVE:
+                m |= 1
+                if od["params"] & P.POPP_MODE:
+                    m |= 1 << od["mode"][1]
+    return m
+
+
+def table_hashes():
+    t = pyref.piluts()
+    return {w: hashlib.sha256(t[i].tobytes()).hexdigest() for i, w in enumerate(pyref.WAVES)}
 
 
 def entry(text, srate=96000, stereo=True):
@@ -36,7 +65,8 @@ def entry(text, srate=96000, stereo=True):
         st = g.op_state(op)
         state.append([st.inited, st.type, st.i0, st.i1, st.time])
     return {"srate": srate, "stereo": stereo, "frames": frames, "sha256": h.hexdigest(),
-            "op_state": state, "vo_count": prg.vo_count, "op_count": prg.op_count}
+            "op_state": state, "vo_count": prg.vo_count, "op_count": prg.op_count,
+            "waves": wave_mask(prg)}
 
 
 def main():
@@ -51,9 +81,16 @@ def main():
     for i in range(8):
         out[f"config/C5_script{i}"] = entry(scripts.synth_c5_script(i))
     out["mono/voices3"] = entry(scripts.feature_scripts()["voices3"], 44100, False)
-    with open(os.path.join(HERE, "known_answers.json"), "w") as f:
+    cpu = ""
+    try:
+        cpu = [l.split(":", 1)[1].strip() for l in open("/proc/cpuinfo") if l.startswith("model name")][0]
+    except Exception:
+        pass
+    out["_meta"] = {"tables": table_hashes(), "host_cpu": cpu}
+    path = sys.argv[1] if len(sys.argv) > 1 else os.path.join(HERE, "known_answers.epyc.json")
+    with open(path, "w") as f:
         json.dump(out, f, indent=0, sort_keys=True)
-    print("wrote", len(out), "entries")
+    print("wrote", len(out) - 1, "entries to", path)
 
 
 if __name__ == "__main__":

@@ -9,11 +9,9 @@ finite-time modulators, event sequencing and voice reuse.
 """
 import random
 
-from saugns_b200.workloads import synth_c3, build_c3  # noqa: F401  (C3 lives with the product)
+from saugns_b200.workloads import (synth_c3, build_c3, synth_c4, synth_c5_script,  # noqa: F401
+                                   WAVES, LINES, NOISES)   # the BASELINE workloads live with the product
 
-WAVES = ["sin", "tri", "srs", "sqr", "ean", "cat", "eto", "par", "mto", "saw", "hsi", "spa"]
-LINES = ["cos", "lin", "sah", "exp", "log", "xpe", "lge", "sqe", "cub", "smo", "ncl", "nhl", "uwh"]
-NOISES = ["wh", "gw", "bw", "tw", "re", "vi", "bv"]
 
 
 def feature_scripts():
@@ -60,6 +58,9 @@ def feature_scripts():
     s["pan_sweep"] = "Wsin f300 c-1[g1 t0.15] t0.3"
     s["pan_mod"] = "Wsin f300 c0[Wsin f5 a0.8] t0.3"
     s["pan_mod_ratio"] = "Wsin f300 c0.1[Wsin r0.01 a0.8] t0.3"
+    s["pan_mod_ratio_self"] = "Wsin f300 p.a0.5 c0.1[Wsin r0.01 a0.8] t0.3"
+    s["pan_mod_ratio_pm"] = "Wsin f300 c0.1[Wsin r0.01 a0.8] p[Wsin f200 a0.3] t0.3"
+    s["pan_mod_ratio_fm"] = "Wsin f300.r400[Wsin f3] c0.1[Wtri r0.02 a0.6] t0.3"
     s["amp_op"] = "A0[Wsin f300 a0.5 Wtri f100 a0.3] t0.3"
     s["amp_op_range"] = "A0.8.r0.1[Wsin f8] t0.2"
     s["noise_am"] = "Nwh a0.5.r0[Wsin f9] t0.3"
@@ -81,50 +82,6 @@ def feature_scripts():
     s["deep"] = "Wsin f200 t0.3 p[Wsin r2 p[Wsin r2 p[Wsin r2 p[Wsin r0.5 a0.3]]]]"
     s["silence_mid"] = "Wsin f200 t0.1 /0.6 Wsin f300 t0.1"
     return s
-
-
-def synth_c4(n_voices=1024, secs=60, seed=2):
-    """BASELINE config 4: self-feedback PM carriers with range-AM / ring-mod."""
-    rnd = random.Random(seed)
-    lines = [f"S a.m{0.3 / n_voices ** 0.5:.6f}"]
-    for i in range(n_voices):
-        f = 110.0 * 2 ** rnd.uniform(0, 4)
-        c = rnd.uniform(-1, 1)
-        pa = rnd.uniform(0.3, 1.0)
-        fm = rnd.uniform(0.5, 8)
-        k = i % 3
-        if k == 0:
-            lines.append(f"Wsin f{f:.3f} t{secs} p.a{pa:.3f} a0.5.r1[Wsin f{fm:.3f}] c{c:.3f}")
-        elif k == 1:
-            lines.append(f"Rlin f{f:.3f} t{secs} p.a{pa:.3f} a0.5.r1[Wsin f{fm:.3f}] c{c:.3f}")
-        else:
-            lines.append(f"Wtri f{f:.3f} t{secs} p.a{pa:.3f} a0[Wsin f{fm * 20:.3f} a0.8] c{c:.3f}")
-    return "\n".join(lines) + "\n"
-
-
-def synth_c5_script(index):
-    """BASELINE config 5: one of the independent mixed scripts (seed 1000+index)."""
-    rnd = random.Random(1000 + index)
-    nv = rnd.randint(4, 16)
-    lines = [f"S a.m{0.3 / nv ** 0.5:.6f}"]
-    for _ in range(nv):
-        t = rnd.uniform(1, 10)
-        f = 110.0 * 2 ** rnd.uniform(0, 4)
-        c = rnd.uniform(-1, 1)
-        kind = rnd.randrange(4)
-        if kind == 0:
-            w, w2 = rnd.choice(WAVES), rnd.choice(WAVES)
-            lines.append(f"W{w} f{f:.3f} t{t:.3f} c{c:.3f} p[W{w2} r{rnd.choice([0.5, 1, 2, 3])} "
-                         f"a{rnd.uniform(0.1, 1):.3f}]")
-        elif kind == 1:
-            lines.append(f"N{rnd.choice(NOISES)} t{t:.3f} c{c:.3f} a{rnd.uniform(0.1, 0.8):.3f}")
-        elif kind == 2:
-            mode = rnd.choice("ugbtfa") + rnd.choice(["", "h", "p", "s", "v", "z"])
-            lines.append(f"R{rnd.choice(LINES)} m{mode} f{f:.3f} t{t:.3f} c{c:.3f}")
-        else:
-            lines.append(f"W{rnd.choice(WAVES)} f{f:.3f}[g{f * rnd.uniform(0.5, 2):.3f} "
-                         f"l{rnd.choice(LINES)}] t{t:.3f} c{c:.3f} a1.r0[Wsin f{rnd.uniform(0.5, 9):.3f}]")
-    return "\n".join(lines) + "\n"
 
 
 # BASELINE config 2: the reference's examples/misc1-4fm_pm.sau (saugns v0.4.7,

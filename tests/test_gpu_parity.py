@@ -43,12 +43,13 @@ def test_feature_scripts_bit_exact(S, ref, tabs, gold):
         prg = ref.Program(text)
         want = ref.render(prg, srate=96000)
         got = S.render(prg, srate=96000, tables=tabs)
-        g = gold["feat/" + name]
+        g = gold.get("feat/" + name)
         if got.shape != want.shape or not np.array_equal(got, want):
             bad.append(name)
-        elif got.shape[0] != g["frames"] or gpuutil.sha(got) != g["sha256"]:
+        elif g is not None and (got.shape[0] != g["frames"] or gpuutil.sha(got) != g["sha256"]):
             bad.append(name + "(golden)")
     assert not bad, bad
+    assert gold.applied >= 150      # the table-independent answers always apply
 
 
 def test_c1_known_answer(S, ref, tabs, gold):
@@ -96,10 +97,11 @@ def test_synthetic_configs(S, ref, tabs, gold, key, text):
         assert [st.inited, st.type, st.i0, st.i1, st.time] == want, (key, op)
 
 
-@pytest.mark.parametrize("sched", [1, 2])
+@pytest.mark.parametrize("sched", [1, 2, 3])
 def test_schedulers_agree_with_reference(S, ref, tabs, gold, sched):
-    """One warp per voice (1) and the ticketed persistent grid (2, what the
-    4096-voice runs use) both reproduce the reference bit for bit."""
+    """One warp per voice (1), the ticketed persistent grid (2) and the balanced
+    contiguous ranges (3, what the 4096-voice runs use) all reproduce the
+    reference bit for bit."""
     for key, text in [("config/C3_64v_1s", scripts.synth_c3(64, 1)),
                       ("config/C3fm_64v_1s", scripts.synth_c3(64, 1, fm=True)),
                       ("config/C4_48v_1s", scripts.synth_c4(48, 1)),
@@ -112,7 +114,9 @@ def test_schedulers_agree_with_reference(S, ref, tabs, gold, sched):
     for name in ["seq_update", "voices3", "regoal", "seq_overlap", "silence_mid", "pm_addrem"]:
         prg = ref.Program(feats[name])
         got = S.render(prg, srate=96000, tables=tabs, sched=sched, call_len=8192)
-        assert gpuutil.sha(got) == gold["feat/" + name]["sha256"], name
+        g = gold.get("feat/" + name)
+        assert g is None or gpuutil.sha(got) == g["sha256"], name
+        assert np.array_equal(got, ref.render(prg, srate=96000, call_len=8192)), name
 
 
 @pytest.mark.parametrize("call_len", [24576, 1024, 1000, 333, 77])
@@ -140,6 +144,26 @@ def test_state_after_every_call(S, ref, port, tabs, call_len):
             for vo in range(prg.vo_count):
                 assert gr.voice_state(vo)[:3] == gg.voice_state(vo)[:3], (name, ncall, vo)
             ncall += 1
+
+
+def test_balanced_scheduler_many_voices(S, ref, port, tabs):
+    """More voices than resident warps (the shape auto-scheduling splits into
+    balanced ranges with L2 hand-off of voice state between warps): 3000 voices
+    with different durations, events inside the call, vs the oracle port."""
+    import random
+    rnd = random.Random(7)
+    lines = ["S a.m0.004"]
+    for i in range(3000):
+        f = 110.0 * 2 ** rnd.uniform(0, 4)
+        t = rnd.choice([0.02, 0.05, 0.11, 0.15])
+        lines.append(f"Wsin f{f:.3f} t{t} a1[g0.2 lxpe] c{rnd.uniform(-1, 1):.3f} "
+                     f"p[Wtri r{rnd.choice([0.5, 1, 2])} a0.8[g0.1 llin]]")
+    prg = ref.Program("\n".join(lines) + "\n")
+    want = port.render(prg, srate=96000, tables=port.ref_tables())
+    for sched in (0, 3):
+        got = S.render(prg, srate=96000, tables=tabs, sched=sched)
+        assert got.shape == want.shape
+        assert np.array_equal(got, want), sched
 
 
 def test_mono(S, ref, tabs, gold):

@@ -155,3 +155,18 @@ def test_voice_sharded_cuda_single_process(ref, port):
     vg.close()
     assert np.array_equal(got, want)
     assert saugns_b200.device_count() >= 1
+
+
+@pytest.mark.gpu
+def test_nccl_voice_and_script_sharding_two_gpus():
+    """torchrun x2 over NCCL (tests/mgpu_voice_shard.py); skipped on 1-GPU boxes."""
+    import subprocess
+    import saugns_b200
+    if saugns_b200.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs (gpurun --gpus 2)")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+                        "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port",
+                        str(29400 + os.getpid() % 500), os.path.join(ROOT, "tests", "mgpu_voice_shard.py")],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "rank 0 OK" in r.stdout and "rank 1 OK" in r.stdout

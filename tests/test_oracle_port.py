@@ -108,3 +108,27 @@ def test_float_buffers_match(ref, port):
             gr.run(1024)
             gp.run(1024)
             assert np.array_equal(gr.gen_buf(0).view(np.uint32), gp.gen_buf(0).view(np.uint32)), name
+
+
+def test_port_reproduces_golden_answers(ref, port):
+    """The oracle port against the committed answers of the unmodified reference
+    (tests/golden/, frames + sha256 of PCM + final integer state), wherever this
+    host's wave tables are the ones the answers were made with."""
+    import gpuutil
+    gold = gpuutil.golden(ref)
+    feats = scripts.feature_scripts()
+    cases = [("feat/" + k, v) for k, v in sorted(feats.items())]
+    cases += [("config/C1_Wsin", "Wsin"), ("config/C3_64v_1s", scripts.synth_c3(64, 1)),
+              ("config/C4_48v_1s", scripts.synth_c4(48, 1))]
+    cases += [(f"config/C5_script{i}", scripts.synth_c5_script(i)) for i in range(8)]
+    checked = 0
+    for key, text in cases:
+        g = gold.get(key)
+        if g is None:
+            continue
+        prg = ref.Program(text)
+        pcm = port.render(prg, srate=g["srate"], stereo=g["stereo"])
+        assert pcm.shape[0] == g["frames"], key
+        assert gpuutil.sha(pcm) == g["sha256"], key
+        checked += 1
+    assert checked >= 150
