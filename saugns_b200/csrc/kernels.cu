@@ -1379,6 +1379,7 @@ __device__ __noinline__ bool steady_check(OpState *sops, const Instr *code, uint
 			if (!op_outlasts_block(o) || !line_steady(o, LINE_FREQ)) return false;
 		}
 		if (tail) {
+			if (in.d != NO_BUF) return false;                       /* fPM: general path */
 			if (!op_outlasts_block(o) || !line_steady(o, LINE_AMP)) return false;
 			if (o->oscflags & OSC_RESET_DIFF) return false;
 			if (in.flags & F_MAY_SELFMOD) {                          /* generator.c:485-490 */
@@ -1673,24 +1674,11 @@ __device__ __forceinline__ void wtail_fast(const FastCtx &c, const Instr &in, ui
 #pragma unroll
 		for (int k = 0; k < NS; ++k) ph[k] += base;
 		if (c.lane == 31) sts32(op + OS_I0, og.z + incl);
-		const bool has_pm = in.c != NO_BUF, has_fpm = in.d != NO_BUF;
-		if (has_pm && has_fpm) {
-			float pm[NS], fpm[NS];
-			fld<NS>(c, in.c, pm); fld<NS>(c, in.d, fpm);
-#pragma unroll
-			for (int k = 0; k < NS; ++k)
-				ph[k] += ftoi_lo32((((fpm[k] * fr[k]) * SAU_FPM_SCALE) + pm[k]) * 2147483648.f);
-		} else if (has_pm) {
+		if (in.c != NO_BUF) {              /* PM; fPM operators take the general path (steady_check) */
 			float pm[NS];
 			fld<NS>(c, in.c, pm);
 #pragma unroll
 			for (int k = 0; k < NS; ++k) ph[k] += ftoi_lo32(pm[k] * 2147483648.f);
-		} else if (has_fpm) {
-			float fpm[NS];
-			fld<NS>(c, in.d, fpm);
-#pragma unroll
-			for (int k = 0; k < NS; ++k)
-				ph[k] += ftoi_lo32((fpm[k] * fr[k]) * (SAU_FPM_SCALE * 2147483648.f));
 		}
 	}
 	/* sauWOsc_run, wosc.h:238-266 */
@@ -1777,6 +1765,17 @@ __device__ __forceinline__ void wtail_fast(const FastCtx &c, const Instr &in, ui
 	__syncwarp();
 }
 
+/* rows not 16-byte aligned: scalar stores from the (plane-major) fast buffers */
+__device__ __noinline__ void vout_unaligned(uint32_t sbuf_s, uint32_t sbuf_r, float *row_s, float *row_r,
+		int lane, int ns) {
+	for (int k = 0; k < ns; ++k) {
+		/* sample lane*ns + k sits in plane k/4, float4 slot `lane`, component k%4 */
+		const uint32_t off = (uint32_t) (k >> 2) * 512u + (uint32_t) lane * 16u + (uint32_t) (k & 3) * 4u;
+		row_s[lane * ns + k] = lds32f(sbuf_s + off);
+		row_r[lane * ns + k] = lds32f(sbuf_r + off);
+	}
+}
+
 template <int NS, bool CTAB>
 __device__ __forceinline__ void run_chunk_fast(const FastCtx &c, const Instr *code,
 		uint32_t code_len, float *row_s, float *row_r) {
@@ -1829,8 +1828,13 @@ __device__ __forceinline__ void run_chunk_fast(const FastCtx &c, const Instr *co
 							make_float4(r[4 * h], r[4 * h + 1], r[4 * h + 2], r[4 * h + 3]));
 				}
 			} else {
-#pragma unroll
-				for (int k = 0; k < NS; ++k) { row_s[i0 + k] = s[k]; row_r[i0 + k] = r[k]; }
+				/* segment starting at an odd frame: rare, out of line through the buffers */
+				fst<NS>(c, in.a, s);
+				fst<NS>(c, in.b != NO_BUF ? in.b : in.a + 1u, r);
+				__syncwarp();
+				vout_unaligned(c.sb - c.lane * 16 + in.a * FastCfg<NS>::FBUF_BYTES,
+						c.sb - c.lane * 16 + (in.b != NO_BUF ? in.b : in.a + 1u) * FastCfg<NS>::FBUF_BYTES,
+						row_s, row_r, c.lane, NS);
 			}
 			return; }
 		default:                   /* ENTER, VPAN, END: nothing to do per chunk */
@@ -1877,7 +1881,7 @@ __device__ __forceinline__ void ops_store(Ctx &c, uint32_t cnt) {
 /* Units [u0, u1) of one voice of one call.  A unit is a stretch of one
  * inter-event segment, starting at a multiple of REF_BLOCK inside it (the
  * reference's own block grid, generator.c:854-878). */
-__device__ __forceinline__ void render_units(Ctx &c, FastCtx &fc, const CallDesc *cd,
+__device__ __noinline__ void render_units(Ctx &c, FastCtx &fc, const CallDesc *cd,
 		const SegDesc *segs, const UnitDesc *units, uint32_t lv, uint32_t u0, uint32_t u1) {
 	const GenDesc *g = cd->gen;
 	const int lane = c.lane;
@@ -1972,8 +1976,9 @@ __device__ __forceinline__ void render_units(Ctx &c, FastCtx &fc, const CallDesc
 			 * rendered in order, by one warp at a time) */
 			uint32_t *vl = g->vlen + (size_t) si * nlv + lv;
 			const uint32_t tot = __ldcg(vl) + run_total;
-			*vl = tot;
-			atomicMax(&g->status[1 + si], tot);
+			__stcg(vl, tot);
+			/* the maximum only grows: skip the atomic when it is already there */
+			if (__ldcg(&g->status[1 + si]) < tot) atomicMax(&g->status[1 + si], tot);
 		}
 	}
 	if (loaded) ops_store(c, loaded);

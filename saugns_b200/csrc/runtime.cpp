@@ -105,6 +105,89 @@ static float *get_device_tables(int device, const saugen_WaveTables *t, double *
 	return d;
 }
 
+/* ---- cached device / pinned-host memory --------------------------------- *
+ * cudaFree and cudaFreeHost synchronise the whole device and take up to
+ * hundreds of milliseconds for the large carrier-row blocks; a batch render
+ * creates and destroys thousands of generators.  Blocks therefore go back to a
+ * per-device free list by size class and are handed out again (every user
+ * synchronises its stream before releasing, so a recycled block is idle). */
+namespace {
+struct MemPool {
+	static const int MAXDEV = 64;
+	std::mutex mu;
+	std::multimap<size_t, void*> free_[2][MAXDEV];     /* [0] device memory, [1] pinned host */
+	std::map<void*, size_t> live;
+	size_t cached[2][MAXDEV] = {{0}};
+	static size_t round_size(size_t n) {
+		if (n < 4096) return 4096;
+		size_t p = 4096;
+		while (p * 2 <= n) p *= 2;
+		const size_t step = p / 8;                     /* <= 12.5 % slack */
+		return (n + step - 1) / step * step;
+	}
+	void *alloc(bool host, int dev, size_t bytes) {
+		const size_t r = round_size(bytes);
+		const int d = host ? 0 : (dev < 0 || dev >= MAXDEV ? 0 : dev);
+		{
+			std::lock_guard<std::mutex> lk(mu);
+			auto it = free_[host][d].find(r);
+			if (it != free_[host][d].end()) {
+				void *p = it->second;
+				free_[host][d].erase(it);
+				cached[host][d] -= r;
+				live[p] = r;
+				return p;
+			}
+		}
+		void *p = nullptr;
+		cudaError_t e = host ? cudaHostAlloc(&p, r, cudaHostAllocPortable) : cudaMalloc(&p, r);
+		if (e != cudaSuccess) {                        /* give the cache back and retry once */
+			cudaGetLastError();
+			trim(host, d);
+			e = host ? cudaHostAlloc(&p, r, cudaHostAllocPortable) : cudaMalloc(&p, r);
+			if (e != cudaSuccess) return nullptr;
+		}
+		std::lock_guard<std::mutex> lk(mu);
+		live[p] = r;
+		return p;
+	}
+	void release(bool host, int dev, void *p) {
+		if (!p) return;
+		const int d = host ? 0 : (dev < 0 || dev >= MAXDEV ? 0 : dev);
+		const size_t limit = host ? ((size_t) 1 << 30) : ((size_t) 24 << 30);
+		size_t r = 0;
+		{
+			std::lock_guard<std::mutex> lk(mu);
+			auto it = live.find(p);
+			if (it != live.end()) { r = it->second; live.erase(it); }
+			if (r && cached[host][d] + r <= limit) {
+				free_[host][d].insert(std::make_pair(r, p));
+				cached[host][d] += r;
+				return;
+			}
+		}
+		if (host) cudaFreeHost(p); else cudaFree(p);
+	}
+	void trim(bool host, int d) {
+		std::vector<void*> v;
+		{
+			std::lock_guard<std::mutex> lk(mu);
+			for (auto &kv : free_[host][d]) v.push_back(kv.second);
+			free_[host][d].clear();
+			cached[host][d] = 0;
+		}
+		for (void *p : v) { if (host) cudaFreeHost(p); else cudaFree(p); }
+	}
+};
+MemPool g_pool;
+
+/* carve 256-byte aligned pieces out of one block */
+struct Carver {
+	size_t off = 0;
+	size_t take(size_t bytes) { size_t o = off; off = (off + (bytes ? bytes : 1) + 255) & ~(size_t) 255; return o; }
+};
+}
+
 /* ---- generator object ---------------------------------------------------- */
 
 struct HostOp {
@@ -156,6 +239,13 @@ struct saugen_Generator {
 	cudaEvent_t ev_t[3] = {nullptr, nullptr, nullptr};
 	double render_ms = 0.0, mix_ms = 0.0;
 	bool timing = false, timed_call = false;
+	/* every block this generator took from the pool: (pointer, is pinned host) */
+	std::vector<std::pair<void*, bool>> blocks;
+	void *take(bool host, size_t bytes) {
+		void *p = g_pool.alloc(host, device, bytes);
+		if (p) blocks.push_back(std::make_pair(p, host));
+		return p;
+	}
 };
 
 /* ---- bytecode compiler --------------------------------------------------- */
@@ -388,16 +478,6 @@ static void flatten_line(LineDelta *d, const sauabi_Line *s, uint32_t srate) {
 	d->type = s->type; d->flags = s->flags;
 }
 
-template <typename T>
-static cudaError_t upload(void **dptr, const std::vector<T> &v) {
-	size_t bytes = v.size() * sizeof(T);
-	if (bytes == 0) bytes = sizeof(T);
-	cudaError_t e = cudaMalloc(dptr, bytes);
-	if (e != cudaSuccess) return e;
-	if (!v.empty()) e = cudaMemcpy(*dptr, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
-	return e;
-}
-
 extern "C" void saugen_destroy(saugen_Generator *o);
 
 extern "C" saugen_Generator *saugen_create(const sauabi_Program *prg, uint32_t srate,
@@ -544,47 +624,64 @@ extern "C" saugen_Generator *saugen_create(const sauabi_Program *prg, uint32_t s
 	}
 	vev_off[prg->vo_count] = (uint32_t) vev_idx.size();
 
-	/* ---- device allocation ---- */
+	/* ---- device allocation: one state block, one row block, one pinned block ---- */
 	CK(cudaSetDevice(o->device));
 	if (opt->stream) o->stream = (cudaStream_t) opt->stream;
 	else { CK(cudaStreamCreateWithFlags(&o->stream, cudaStreamNonBlocking)); o->own_stream = true; }
 	o->d_tables = get_device_tables(o->device, tables, &o->d_coefs);
 	if (!o->d_tables) { set_err("wave table upload", cudaGetLastError()); goto fail; }
 	{
-		size_t nops = prg->op_count ? prg->op_count : 1, nvo = prg->vo_count ? prg->vo_count : 1;
-		CK(cudaMalloc(&o->d_ops, nops * sizeof(OpState)));
-		CK(cudaMemset(o->d_ops, 0, nops * sizeof(OpState)));
-		CK(cudaMalloc(&o->d_voices, nvo * sizeof(VoiceState)));
-		CK(cudaMemset(o->d_voices, 0, nvo * sizeof(VoiceState)));
-	}
-	CK(upload(&o->d_events, events));
-	CK(upload(&o->d_opdata, opdata));
-	CK(upload(&o->d_code, code));
-	CK(upload(&o->d_prog_ops, prog_ops));
-	CK(upload(&o->d_vev_off, vev_off));
-	CK(upload(&o->d_vev_idx, vev_idx));
-	{
-		size_t nl = o->nlv ? o->nlv : 1;
+		const size_t nops = prg->op_count ? prg->op_count : 1, nvo = prg->vo_count ? prg->vo_count : 1;
+		const size_t nl = o->nlv ? o->nlv : 1;
 		o->seg_cap = 64;
-		CK(cudaMalloc(&o->d_rows_s, nl * o->row_len * sizeof(float)));
-		CK(cudaMalloc(&o->d_rows_r, nl * o->row_len * sizeof(float)));
-		CK(cudaMalloc(&o->d_vlen, (size_t) o->seg_cap * nl * sizeof(uint32_t)));
-		CK(cudaMalloc(&o->d_status, (1 + o->seg_cap) * sizeof(uint32_t)));
-		CK(cudaMalloc(&o->d_progress, (nl + 1) * sizeof(uint32_t)));   /* [nl] = ticket counter */
 		o->unit_cap = 256;
-		CK(cudaMalloc(&o->d_units, o->unit_cap * sizeof(UnitDesc)));
-		CK(cudaMallocHost(&o->h_units, o->unit_cap * sizeof(UnitDesc)));
-		CK(cudaMalloc(&o->d_mix, 2 * (size_t) o->row_len * sizeof(float)));
-		CK(cudaMalloc(&o->d_pcm, 2 * (size_t) o->row_len * sizeof(int16_t)));
-		CK(cudaMalloc(&o->d_call, sizeof(CallDesc)));
-		CK(cudaMalloc(&o->d_segs, o->seg_cap * sizeof(SegDesc)));
-		CK(cudaMallocHost(&o->h_status, (1 + o->seg_cap) * sizeof(uint32_t)));
-		CK(cudaMallocHost(&o->h_pcm, 2 * (size_t) o->row_len * sizeof(int16_t)));
-		CK(cudaMallocHost(&o->h_call, sizeof(CallDesc)));
-		CK(cudaMallocHost(&o->h_segs, o->seg_cap * sizeof(SegDesc)));
+		Carver cv;
+		/* static part first: filled in a host staging image, uploaded with one copy */
+		const size_t o_events = cv.take(events.size() * sizeof(EventRec));
+		const size_t o_opdata = cv.take(opdata.size() * sizeof(OpDataRec));
+		const size_t o_code = cv.take(code.size() * sizeof(Instr));
+		const size_t o_prog_ops = cv.take(prog_ops.size() * sizeof(uint32_t));
+		const size_t o_vev_off = cv.take(vev_off.size() * sizeof(uint32_t));
+		const size_t o_vev_idx = cv.take(vev_idx.size() * sizeof(uint32_t));
+		const size_t o_desc = cv.take(sizeof(GenDesc));
+		const size_t static_bytes = cv.off;
+		const size_t o_ops = cv.take(nops * sizeof(OpState));
+		const size_t o_voices = cv.take(nvo * sizeof(VoiceState));
+		const size_t zero_bytes = cv.off - o_ops;         /* operator + voice state start zeroed */
+		const size_t o_vlen = cv.take((size_t) o->seg_cap * nl * sizeof(uint32_t));
+		const size_t o_status = cv.take((1 + o->seg_cap) * sizeof(uint32_t));
+		const size_t o_progress = cv.take((nl + 1) * sizeof(uint32_t));   /* [nl] = ticket counter */
+		const size_t o_units = cv.take(o->unit_cap * sizeof(UnitDesc));
+		const size_t o_mix = cv.take(2 * (size_t) o->row_len * sizeof(float));
+		const size_t o_pcm = cv.take(2 * (size_t) o->row_len * sizeof(int16_t));
+		const size_t o_call = cv.take(sizeof(CallDesc));
+		const size_t o_segs = cv.take(o->seg_cap * sizeof(SegDesc));
+		unsigned char *base = (unsigned char*) o->take(false, cv.off);
+		if (!base) { set_err("saugen_create: device memory", cudaGetLastError()); goto fail; }
+		o->d_events = base + o_events; o->d_opdata = base + o_opdata; o->d_code = base + o_code;
+		o->d_prog_ops = base + o_prog_ops; o->d_vev_off = base + o_vev_off; o->d_vev_idx = base + o_vev_idx;
+		o->d_desc = (GenDesc*) (base + o_desc);
+		o->d_ops = base + o_ops; o->d_voices = base + o_voices;
+		o->d_vlen = (uint32_t*) (base + o_vlen); o->d_status = (uint32_t*) (base + o_status);
+		o->d_progress = (uint32_t*) (base + o_progress); o->d_units = (UnitDesc*) (base + o_units);
+		o->d_mix = (float*) (base + o_mix); o->d_pcm = (int16_t*) (base + o_pcm);
+		o->d_call = (CallDesc*) (base + o_call); o->d_segs = (SegDesc*) (base + o_segs);
+		float *rows = (float*) o->take(false, 2 * nl * (size_t) o->row_len * sizeof(float));
+		if (!rows) { set_err("saugen_create: device memory (carrier rows)", cudaGetLastError()); goto fail; }
+		o->d_rows_s = rows; o->d_rows_r = rows + nl * (size_t) o->row_len;
+		Carver hv;
+		const size_t h_status = hv.take((1 + o->seg_cap) * sizeof(uint32_t));
+		const size_t h_pcm = hv.take(2 * (size_t) o->row_len * sizeof(int16_t));
+		const size_t h_call = hv.take(sizeof(CallDesc));
+		const size_t h_segs = hv.take(o->seg_cap * sizeof(SegDesc));
+		const size_t h_units = hv.take(o->unit_cap * sizeof(UnitDesc));
+		unsigned char *hb = (unsigned char*) o->take(true, hv.off);
+		if (!hb) { set_err("saugen_create: pinned host memory", cudaGetLastError()); goto fail; }
+		o->h_status = (uint32_t*) (hb + h_status); o->h_pcm = (int16_t*) (hb + h_pcm);
+		o->h_call = (CallDesc*) (hb + h_call); o->h_segs = (SegDesc*) (hb + h_segs);
+		o->h_units = (UnitDesc*) (hb + h_units);
 		for (int i = 0; i < 3; ++i) CK(cudaEventCreate(&o->ev_t[i]));
-	}
-	{
+
 		GenDesc &d = o->h_desc;
 		memset(&d, 0, sizeof d);
 		d.ops = (OpState*) o->d_ops; d.voices = (VoiceState*) o->d_voices;
@@ -594,7 +691,7 @@ extern "C" saugen_Generator *saugen_create(const sauabi_Program *prg, uint32_t s
 		d.vev_off = (const uint32_t*) o->d_vev_off; d.vev_idx = (const uint32_t*) o->d_vev_idx;
 		d.rows_s = o->d_rows_s; d.rows_r = o->d_rows_r;
 		d.vlen = o->d_vlen; d.status = o->d_status; d.vlen_cap = o->seg_cap;
-		d.progress = o->d_progress; d.ticket = o->d_progress + (o->nlv ? o->nlv : 1);
+		d.progress = o->d_progress; d.ticket = o->d_progress + nl;
 		d.mix = o->d_mix; d.pcm = o->d_pcm;
 		d.vo_count = o->vo_count; d.op_count = o->op_count;
 		d.voice_begin = o->voice_begin; d.voice_end = o->voice_end;
@@ -602,8 +699,21 @@ extern "C" saugen_Generator *saugen_create(const sauabi_Program *prg, uint32_t s
 		d.coeff = (float) (4294967296.0 / srate);                 /* wosc.h:30, math.h:386 */
 		d.amp_scale = o->amp_scale;
 		d.wave_mask = o->wave_mask; d.tables = o->d_tables;
-		CK(cudaMalloc(&o->d_desc, sizeof(GenDesc)));
-		CK(cudaMemcpy(o->d_desc, &d, sizeof d, cudaMemcpyHostToDevice));
+
+		/* one H2D copy of the static image, one memset of the run-time state; the
+		 * stream is synchronised before the staging image goes away */
+		std::vector<unsigned char> img(static_bytes);
+		auto put = [&](size_t off, const void *src, size_t n) { if (n) memcpy(&img[off], src, n); };
+		put(o_events, events.data(), events.size() * sizeof(EventRec));
+		put(o_opdata, opdata.data(), opdata.size() * sizeof(OpDataRec));
+		put(o_code, code.data(), code.size() * sizeof(Instr));
+		put(o_prog_ops, prog_ops.data(), prog_ops.size() * sizeof(uint32_t));
+		put(o_vev_off, vev_off.data(), vev_off.size() * sizeof(uint32_t));
+		put(o_vev_idx, vev_idx.data(), vev_idx.size() * sizeof(uint32_t));
+		put(o_desc, &d, sizeof d);
+		CK(cudaMemcpyAsync(base, img.data(), static_bytes, cudaMemcpyHostToDevice, o->stream));
+		CK(cudaMemsetAsync(base + o_ops, 0, zero_bytes, o->stream));
+		CK(cudaStreamSynchronize(o->stream));
 	}
 	return o;
 fail:
@@ -615,12 +725,7 @@ extern "C" void saugen_destroy(saugen_Generator *o) {
 	if (!o) return;
 	cudaSetDevice(o->device);
 	if (o->stream) cudaStreamSynchronize(o->stream);
-	void *dev[] = {o->d_ops, o->d_voices, o->d_events, o->d_opdata, o->d_code, o->d_prog_ops, o->d_vev_off,
-		o->d_vev_idx, o->d_rows_s, o->d_rows_r, o->d_vlen, o->d_status, o->d_mix, o->d_pcm,
-		o->d_call, o->d_segs, o->d_desc, o->d_progress, o->d_units};
-	for (void *p : dev) if (p) cudaFree(p);
-	void *host[] = {o->h_status, o->h_pcm, o->h_call, o->h_segs, o->h_units};
-	for (void *p : host) if (p) cudaFreeHost(p);
+	for (auto &b : o->blocks) g_pool.release(b.second, o->device, b.first);
 	for (int i = 0; i < 3; ++i) if (o->ev_t[i]) cudaEventDestroy(o->ev_t[i]);
 	if (o->own_stream && o->stream) cudaStreamDestroy(o->stream);
 	delete o;
@@ -727,13 +832,13 @@ static int run_common(saugen_Generator *o, size_t buf_len, int stereo, uint32_t 
 		while (cap < segs.size()) cap *= 2;
 		size_t nl = o->nlv ? o->nlv : 1;
 		cudaStreamSynchronize(o->stream);
-		cudaFree(o->d_vlen); cudaFree(o->d_status); cudaFree(o->d_segs);
-		cudaFreeHost(o->h_status); cudaFreeHost(o->h_segs);
-		if (cudaMalloc(&o->d_vlen, (size_t) cap * nl * sizeof(uint32_t)) != cudaSuccess ||
-		    cudaMalloc(&o->d_status, (1 + cap) * sizeof(uint32_t)) != cudaSuccess ||
-		    cudaMalloc(&o->d_segs, cap * sizeof(SegDesc)) != cudaSuccess ||
-		    cudaMallocHost(&o->h_status, (1 + cap) * sizeof(uint32_t)) != cudaSuccess ||
-		    cudaMallocHost(&o->h_segs, cap * sizeof(SegDesc)) != cudaSuccess) {
+		/* new, larger pieces; the old ones stay with the generator until destroy */
+		o->d_vlen = (uint32_t*) o->take(false, (size_t) cap * nl * sizeof(uint32_t));
+		o->d_status = (uint32_t*) o->take(false, (1 + cap) * sizeof(uint32_t));
+		o->d_segs = (SegDesc*) o->take(false, cap * sizeof(SegDesc));
+		o->h_status = (uint32_t*) o->take(true, (1 + cap) * sizeof(uint32_t));
+		o->h_segs = (SegDesc*) o->take(true, cap * sizeof(SegDesc));
+		if (!o->d_vlen || !o->d_status || !o->d_segs || !o->h_status || !o->h_segs) {
 			set_err("saugen_run: segment table growth", cudaGetLastError());
 			return -1;
 		}
@@ -771,9 +876,9 @@ static int run_common(saugen_Generator *o, size_t buf_len, int stereo, uint32_t 
 		uint32_t cap = o->unit_cap;
 		while (cap < o->units_tmp.size()) cap *= 2;
 		cudaStreamSynchronize(o->stream);
-		cudaFree(o->d_units); cudaFreeHost(o->h_units);
-		if (cudaMalloc(&o->d_units, cap * sizeof(UnitDesc)) != cudaSuccess ||
-		    cudaMallocHost(&o->h_units, cap * sizeof(UnitDesc)) != cudaSuccess) {
+		o->d_units = (UnitDesc*) o->take(false, cap * sizeof(UnitDesc));
+		o->h_units = (UnitDesc*) o->take(true, cap * sizeof(UnitDesc));
+		if (!o->d_units || !o->h_units) {
 			set_err("saugen_run: unit table growth", cudaGetLastError());
 			return -1;
 		}
