@@ -106,7 +106,9 @@ typedef struct saugen_OpView {
 int saugen_read_op(saugen_Generator *o, uint32_t op_id, saugen_OpView *out);
 int saugen_read_voice(saugen_Generator *o, uint32_t vo_id, uint32_t out[4]);
 /* Float carrier rows (s = carrier*amp_scale, r = s*pan) written by the last
- * call for one voice: n = frames of that call. */
+ * call for one voice: n = frames of that call.  The r row exists only where the
+ * voice's pan moves (sweep or pan modulators); a constant pan is applied in the
+ * mix kernel and leaves r untouched. */
 int saugen_read_voice_rows(saugen_Generator *o, uint32_t vo_id, float *s, float *r,
 		size_t n);
 /* Counters: [0] render launches, [1] mix launches, [2] voice-chunks rendered */

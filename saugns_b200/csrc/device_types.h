@@ -150,6 +150,20 @@ struct Instr {
 	uint32_t aux;          // I_ENTER: index of the matching I_LEAVE
 };
 
+/* What the mix kernel needs to know about one voice in one inter-event segment
+ * of a call: frames rendered, and its pan.  A pan that stands still during the
+ * segment (no sweep, no pan modulators: only an event can change that, and
+ * events start new segments) is a constant: the render kernel stores it here
+ * and skips the r = s * pan row, the mix kernel redoes that one multiply
+ * (mix_add, sau/generator.c:772-786; same operation, same bits).  A moving pan
+ * is flagged PAN_DYNAMIC and read from rows_r. */
+struct VoiceSeg {
+	uint32_t len;
+	uint32_t pan;                 // float bits, or PAN_DYNAMIC / PAN_UNSET
+};
+constexpr uint32_t PAN_UNSET = 0u - 1u;          // not decided yet (both are NaN patterns
+constexpr uint32_t PAN_DYNAMIC = 0u - 2u;        // no sauLine value can take: v0 comes from a parser)
+
 /* One generator's device-resident description. */
 struct GenDesc {
 	OpState *ops;
@@ -160,8 +174,9 @@ struct GenDesc {
 	const uint32_t *prog_ops;     // operator ids of every compiled voice program
 	const uint32_t *vev_off;      // [vo_count+1] CSR into vev_idx
 	const uint32_t *vev_idx;      // global event indices per voice, in order
-	float *rows_s, *rows_r;       // [n_local_voices][row_len] carrier rows of a call
-	uint32_t *vlen;               // [seg][n_local_voices] frames run per segment of a call
+	float *rows_s, *rows_r;       // [n_local_voices][row_len] carrier rows of a call (rows_r: only
+	                              // for voices whose pan moves in the segment, see VoiceSeg)
+	VoiceSeg *vlen;               // [seg][n_local_voices] per segment of a call
 	uint32_t *status;             // [0]=any voice still alive, [1+seg]=per-segment max len
 	uint32_t vlen_cap;            // segments the vlen/status arrays can hold
 	uint32_t *progress;           // [n_local_voices] units done in the current call (ticketed launches)
@@ -171,6 +186,7 @@ struct GenDesc {
 	uint32_t vo_count, op_count;
 	uint32_t voice_begin, voice_end;
 	uint32_t row_len;             // frames per row (max call length)
+	uint32_t row_stride;          // floats between consecutive voice rows (padded, see create)
 	uint32_t nbufs;               // work buffers per voice warp
 	uint32_t srate;
 	float coeff;                  // (float)(2^32 / srate), wosc.h:30, rasg.h:27

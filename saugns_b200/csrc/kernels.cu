@@ -56,6 +56,17 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_
 			" [%0], [%1], %2, [%3];"
 			:: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+/* 16-byte asynchronous copy global -> shared through the LSU path (L2 only), and
+ * an mbarrier arrival that fires when this thread's earlier copies have landed */
+__device__ __forceinline__ void cp_async16(void *dst, const void *src) {
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_arrive(uint64_t *bar) {
+	asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase) {
 	asm volatile(
 		"{\n"
@@ -87,6 +98,7 @@ struct Ctx {
 	int lane;
 	int sp;
 	bool pma_flag, pan_dyn;
+	bool write_r;              // the segment's pan moves: r rows are written (VoiceSeg)
 	uint32_t last_len, last_rem;
 };
 
@@ -1299,14 +1311,15 @@ __device__ __noinline__ uint32_t run_chunk(Ctx &c, const Instr *code, uint32_t c
 			s.y = sv.y * amp_scale; r.y = s.y * pv.y;
 			s.z = sv.z * amp_scale; r.z = s.z * pv.z;
 			s.w = sv.w * amp_scale; r.w = s.w * pv.w;
+			const bool wr = c.write_r || c.pan_dyn;      /* see VoiceSeg */
 			if (i0 + 3 < vn && ((reinterpret_cast<uintptr_t>(row_s + i0) & 15) == 0)) {
 				__stcs(reinterpret_cast<float4*>(row_s + i0), s);   /* coalesced 128-bit stores */
-				__stcs(reinterpret_cast<float4*>(row_r + i0), r);
+				if (wr) __stcs(reinterpret_cast<float4*>(row_r + i0), r);
 			} else {
-				if (i0 + 0 < vn) { row_s[i0 + 0] = s.x; row_r[i0 + 0] = r.x; }
-				if (i0 + 1 < vn) { row_s[i0 + 1] = s.y; row_r[i0 + 1] = r.y; }
-				if (i0 + 2 < vn) { row_s[i0 + 2] = s.z; row_r[i0 + 2] = r.z; }
-				if (i0 + 3 < vn) { row_s[i0 + 3] = s.w; row_r[i0 + 3] = r.w; }
+				if (i0 + 0 < vn) { row_s[i0 + 0] = s.x; if (wr) row_r[i0 + 0] = r.x; }
+				if (i0 + 1 < vn) { row_s[i0 + 1] = s.y; if (wr) row_r[i0 + 1] = r.y; }
+				if (i0 + 2 < vn) { row_s[i0 + 2] = s.z; if (wr) row_r[i0 + 2] = r.z; }
+				if (i0 + 3 < vn) { row_s[i0 + 3] = s.w; if (wr) row_r[i0 + 3] = r.w; }
 			}
 			return vn; }
 		case I_END:
@@ -1503,6 +1516,7 @@ struct FastCtx {               /* all registers */
 	uint32_t oc;               // chunk offset inside the block
 	int lane;
 	float coeff, amp_scale;
+	uint32_t write_r;          // as Ctx::write_r
 	const WaveCoeffs *wc;
 	const float *tab;          // generic pointer to the staged tables (rare paths)
 };
@@ -1767,12 +1781,12 @@ __device__ __forceinline__ void wtail_fast(const FastCtx &c, const Instr &in, ui
 
 /* rows not 16-byte aligned: scalar stores from the (plane-major) fast buffers */
 __device__ __noinline__ void vout_unaligned(uint32_t sbuf_s, uint32_t sbuf_r, float *row_s, float *row_r,
-		int lane, int ns) {
+		int lane, int ns, uint32_t write_r) {
 	for (int k = 0; k < ns; ++k) {
 		/* sample lane*ns + k sits in plane k/4, float4 slot `lane`, component k%4 */
 		const uint32_t off = (uint32_t) (k >> 2) * 512u + (uint32_t) lane * 16u + (uint32_t) (k & 3) * 4u;
 		row_s[lane * ns + k] = lds32f(sbuf_s + off);
-		row_r[lane * ns + k] = lds32f(sbuf_r + off);
+		if (write_r) row_r[lane * ns + k] = lds32f(sbuf_r + off);
 	}
 }
 
@@ -1821,11 +1835,14 @@ __device__ __forceinline__ void run_chunk_fast(const FastCtx &c, const Instr *co
 			const uint32_t i0 = c.lane * NS;
 			if ((reinterpret_cast<uintptr_t>(row_s) & 15) == 0) {
 #pragma unroll
-				for (int h = 0; h < NS / 4; ++h) {                   /* 128-bit streaming stores */
+				for (int h = 0; h < NS / 4; ++h)                     /* 128-bit streaming stores */
 					__stcs(reinterpret_cast<float4*>(row_s + i0) + h,
 							make_float4(s[4 * h], s[4 * h + 1], s[4 * h + 2], s[4 * h + 3]));
-					__stcs(reinterpret_cast<float4*>(row_r + i0) + h,
-							make_float4(r[4 * h], r[4 * h + 1], r[4 * h + 2], r[4 * h + 3]));
+				if (c.write_r) {
+#pragma unroll
+					for (int h = 0; h < NS / 4; ++h)
+						__stcs(reinterpret_cast<float4*>(row_r + i0) + h,
+								make_float4(r[4 * h], r[4 * h + 1], r[4 * h + 2], r[4 * h + 3]));
 				}
 			} else {
 				/* segment starting at an odd frame: rare, out of line through the buffers */
@@ -1834,7 +1851,7 @@ __device__ __forceinline__ void run_chunk_fast(const FastCtx &c, const Instr *co
 				__syncwarp();
 				vout_unaligned(c.sb - c.lane * 16 + in.a * FastCfg<NS>::FBUF_BYTES,
 						c.sb - c.lane * 16 + (in.b != NO_BUF ? in.b : in.a + 1u) * FastCfg<NS>::FBUF_BYTES,
-						row_s, row_r, c.lane, NS);
+						row_s, row_r, c.lane, NS, c.write_r);
 			}
 			return; }
 		default:                   /* ENTER, VPAN, END: nothing to do per chunk */
@@ -1906,8 +1923,8 @@ __device__ __noinline__ void render_units(Ctx &c, FastCtx &fc, const CallDesc *c
 		}
 	}
 	const uint32_t ev_lo = g->vev_off[v], ev_n = g->vev_off[v + 1] - ev_lo;
-	float *row_s = g->rows_s + (size_t) lv * g->row_len;
-	float *row_r = g->rows_r + (size_t) lv * g->row_len;
+	float *row_s = g->rows_s + (size_t) lv * g->row_stride;
+	float *row_r = g->rows_r + (size_t) lv * g->row_stride;
 	uint32_t loaded = 0;        // operator states currently held in shared memory
 
 	for (uint32_t ui = u0; ui < u1; ++ui) {
@@ -1929,6 +1946,16 @@ __device__ __noinline__ void render_units(Ctx &c, FastCtx &fc, const CallDesc *c
 			}
 		}
 		if (vs.duration == 0 || ud.len == 0) continue;
+		/* this voice's pan in this segment (VoiceSeg): undecided at the segment's
+		 * first unit, else what the unit that started the segment recorded */
+		VoiceSeg *vsg = g->vlen + (size_t) si * nlv + lv;
+		uint32_t pan_mode = PAN_UNSET;
+		if (ud.off != 0) {
+			const uint2 pv = __ldcg(reinterpret_cast<const uint2*>(vsg));
+			if (pv.x != 0) pan_mode = pv.y;
+		}
+		c.write_r = pan_mode == PAN_DYNAMIC;
+		fc.write_r = c.write_r ? 1u : 0u;
 		c.prog_ops = g->prog_ops + vs.ops_off;
 		if (!loaded && vs.ops_cnt > 0) {
 			ops_load(c, vs.ops_cnt);
@@ -1942,6 +1969,8 @@ __device__ __noinline__ void render_units(Ctx &c, FastCtx &fc, const CallDesc *c
 					vs.duration >= (uint32_t) REF_BLOCK && vs.code_len &&
 					op_ptr(c, vs.carr_slot)->time > 0 &&
 					steady_check(c.sops, g->code + vs.code_off, vs.code_len)) {
+				if (pan_mode == PAN_UNSET)       /* steady => the pan stands still */
+					pan_mode = __float_as_uint(op_ptr(c, vs.carr_slot)->line[LINE_PAN].v0);
 				if (fc.wave_mask & CTAB_FLAG)
 					run_block_fast<true>(fc, g->code + vs.code_off, vs.code_len,
 							row_s + sd.start + off, row_r + sd.start + off);
@@ -1968,15 +1997,21 @@ __device__ __noinline__ void render_units(Ctx &c, FastCtx &fc, const CallDesc *c
 				out_len = run_chunk(c, g->code + vs.code_off, vs.code_len, time, rem0,
 						row_s + sd.start + off, row_r + sd.start + off);
 			__syncwarp();
+			if (out_len && pan_mode == PAN_UNSET) {
+				/* first rendered chunk of the segment decides (run_chunk wrote r if moving) */
+				pan_mode = c.pan_dyn ? PAN_DYNAMIC :
+					__float_as_uint(op_ptr(c, vs.carr_slot)->line[LINE_PAN].v0);
+				c.write_r = c.pan_dyn;
+				fc.write_r = c.write_r ? 1u : 0u;
+			}
 			vs.duration -= time;
 			run_total += out_len;
 		}
 		if (lane == 0 && run_total) {
 			/* frames this voice has run in the segment so far (units of a voice are
 			 * rendered in order, by one warp at a time) */
-			uint32_t *vl = g->vlen + (size_t) si * nlv + lv;
-			const uint32_t tot = __ldcg(vl) + run_total;
-			__stcg(vl, tot);
+			const uint32_t tot = __ldcg(&vsg->len) + run_total;
+			__stcg(reinterpret_cast<uint2*>(vsg), make_uint2(tot, pan_mode));
 			/* the maximum only grows: skip the atomic when it is already there */
 			if (__ldcg(&g->status[1 + si]) < tot) atomicMax(&g->status[1 + si], tot);
 		}
@@ -2171,73 +2206,184 @@ render_kernel_wide(const CallDesc *calls, uint32_t ncalls, const SegDesc *segs, 
 
 /* ---- mix + clip epilogue ------------------------------------------------- */
 
-constexpr int MIX_THREADS = 128;
-constexpr int MIX_BATCH = 16;
+/* One CTA mixes MIX_FRAMES consecutive frames, one thread per frame: the sum
+ * over voices must run in voice order in ONE thread (float addition is not
+ * associative and mix_add adds voice after voice, generator.c:773-786).  The
+ * voice rows stream through a ring of shared-memory stages filled by TMA bulk
+ * copies (512 contiguous bytes of MIX_TV voice rows per stage, mbarrier
+ * completion), issued MIX_STAGES tiles ahead of the adds, so that the HBM
+ * requests are long, many and independent of the adds' dependency chain.
+ * A voice whose pan stands still contributes r = s * pan, computed here
+ * (VoiceSeg); only moving pans have an r row to fetch. */
+constexpr int MIX_FRAMES = 128;                // = consumer threads (one per frame)
+constexpr int MIX_TV = 16;                     // voices per stage
+constexpr int MIX_STAGES = 5;
+constexpr int MIX_CWARPS = MIX_FRAMES / 32;    // consumer warps; one more warp produces
+struct MixSmem {
+	float s[MIX_STAGES][MIX_TV][MIX_FRAMES];
+	float r[MIX_STAGES][MIX_TV][MIX_FRAMES];
+	uint2 vi[MIX_STAGES][MIX_TV];              // the tile's VoiceSeg records
+	uint64_t full[MIX_STAGES], empty[MIX_STAGES];
+	uint32_t ndyn[MIX_STAGES];                 // moving-pan voices in the stage's tile
+};
 
-__global__ void __launch_bounds__(MIX_THREADS)
-mix_kernel(const CallDesc *calls, const SegDesc *segs, uint32_t mode /*0 pcm, 1 float planes*/) {
-	const CallDesc *cd = &calls[blockIdx.y];
-	const GenDesc *g = cd->gen;
-	const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
-	if (f >= cd->call_len) return;
-	const uint32_t nlv = g->voice_end - g->voice_begin;
-	/* locate the segment holding frame f */
-	uint32_t si = 0;
-	for (; si < cd->nseg; ++si) {
-		const SegDesc sd = segs[cd->seg_off + si];
-		if (f >= sd.start && f < sd.start + sd.len) break;
-	}
-	float L = 0.f, R = 0.f;
-	if (si < cd->nseg) {
-		const uint32_t fi = f - segs[cd->seg_off + si].start;
-		const uint32_t *vl = g->vlen + (size_t) si * nlv;
-		const float *ps = g->rows_s + f, *pr = g->rows_r + f;
-		const size_t stride = g->row_len;
-		if (fi < g->status[1 + si]) {
-			/* voice order is kept (float sums are not associative); the loads of a
-			 * batch of voices are issued together so HBM latency overlaps */
-			uint32_t lv = 0;
-			for (; lv + MIX_BATCH <= nlv; lv += MIX_BATCH) {
-				float s[MIX_BATCH], r[MIX_BATCH];
-#pragma unroll
-				for (int k = 0; k < MIX_BATCH; ++k) {
-					const bool on = fi < __ldg(vl + lv + k);
-					s[k] = on ? __ldcs(ps + (size_t) (lv + k) * stride) : 0.f;
-					r[k] = on ? __ldcs(pr + (size_t) (lv + k) * stride) : 0.f;
-				}
-#pragma unroll
-				for (int k = 0; k < MIX_BATCH; ++k) {
-					L = (L + s[k]) - r[k];                         /* as compiled, Appendix B.3; */
-					R = (R + s[k]) + r[k];                         /* adding 0 is exact */
-				}
-			}
-			for (; lv < nlv; ++lv) {
-				if (fi < vl[lv]) {
-					const float s = ps[(size_t) lv * stride];
-					const float r = pr[(size_t) lv * stride];
-					L = (L + s) - r;
-					R = (R + s) + r;
-				}
-			}
-		}
-	}
+__device__ __forceinline__ void mix_store(const GenDesc *g, const CallDesc *cd, uint32_t mode,
+		uint32_t f, float L, float R) {
 	if (mode == 1) {
 		g->mix[f] = L;
 		g->mix[g->row_len + f] = R;
 		return;
 	}
-	if (cd->stereo) {
+	if (cd->stereo) {                                              /* generator.c:795-810 */
 		L = sau::fclampf(L, -1.f, 1.f);
 		R = sau::fclampf(R, -1.f, 1.f);
 		short2 o;
 		o.x = (short) __float2int_rn(L * 32767.f);
 		o.y = (short) __float2int_rn(R * 32767.f);
 		reinterpret_cast<short2*>(g->pcm)[f] = o;
-	} else {
+	} else {                                                       /* generator.c:812-825 */
 		float m = (L + R) * 0.5f;
 		m = sau::fclampf(m, -1.f, 1.f);
 		g->pcm[f] = (short) __float2int_rn(m * 32767.f);
 	}
+}
+
+__global__ void __launch_bounds__(MIX_FRAMES + 32)
+mix_kernel(const CallDesc *calls, const SegDesc *segs, uint32_t mode /*0 pcm, 1 float planes*/) {
+	extern __shared__ __align__(128) unsigned char mix_smem_raw[];
+	MixSmem &sm = *reinterpret_cast<MixSmem*>(mix_smem_raw);
+	const CallDesc *cd = &calls[blockIdx.y];
+	const GenDesc *g = cd->gen;
+	const uint32_t f0 = blockIdx.x * MIX_FRAMES;
+	if (f0 >= cd->call_len) return;
+	const uint32_t tid = threadIdx.x;
+	const bool producer = tid >= (uint32_t) MIX_FRAMES;          /* the last warp */
+	const uint32_t f = f0 + (producer ? 0u : tid);
+	const bool valid = !producer && f < cd->call_len;
+	const uint32_t nlv = g->voice_end - g->voice_begin;
+	const size_t stride = g->row_stride;
+	/* the segment holding each thread's frame */
+	uint32_t si = 0;
+	for (; si < cd->nseg; ++si) {
+		const SegDesc sd = segs[cd->seg_off + si];
+		if (f >= sd.start && f < sd.start + sd.len) break;
+	}
+	const bool in_seg = valid && si < cd->nseg;
+	const uint32_t fi = in_seg ? f - segs[cd->seg_off + si].start : 0u;
+	__shared__ uint32_t seg0, mixed, active;
+	if (tid == 0) { seg0 = si; mixed = 0; active = 0; }
+	__syncthreads();
+	if (valid && si != seg0) mixed = 1;
+	if (in_seg && fi < g->status[1 + si]) active = 1;
+	if (tid == 0) {
+		for (int st = 0; st < MIX_STAGES; ++st) {
+			mbar_init(&sm.full[st], 32);               /* the producer warp's lanes */
+			mbar_init(&sm.empty[st], MIX_CWARPS);
+		}
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	__syncthreads();
+	float L = 0.f, R = 0.f;
+	if (mixed || seg0 >= cd->nseg) {
+		/* an event boundary inside these frames: each thread walks its own segment's
+		 * voice list straight from global memory (rare) */
+		if (in_seg && fi < g->status[1 + si]) {
+			const uint2 *vl = reinterpret_cast<const uint2*>(g->vlen + (size_t) si * nlv);
+			for (uint32_t lv = 0; lv < nlv; ++lv) {
+				const uint2 v = vl[lv];
+				if (fi < v.x) {
+					const float s = g->rows_s[(size_t) lv * stride + f];
+					const float r = (v.y == PAN_DYNAMIC) ? g->rows_r[(size_t) lv * stride + f] :
+						s * __uint_as_float(v.y);
+					L = (L + s) - r;
+					R = (R + s) + r;
+				}
+			}
+		}
+		if (valid) mix_store(g, cd, mode, f, L, R);
+		return;
+	}
+	if (!active) {                       /* nothing was rendered for these frames */
+		if (valid) mix_store(g, cd, mode, f, 0.f, 0.f);
+		return;
+	}
+	const uint2 *vl = reinterpret_cast<const uint2*>(g->vlen + (size_t) seg0 * nlv);
+	const uint32_t ntiles = (nlv + MIX_TV - 1) / MIX_TV;
+	if (producer) {
+		/* The producer warp: per tile, the VoiceSeg records (one lane each), then every
+		 * voice row's 512-byte piece with ONE 16-bytes-per-lane asynchronous copy
+		 * (a fully coalesced request through the LSU path, which keeps far more
+		 * requests in flight than 512-byte TMA bulk copies did: 1.6 -> x TB/s);
+		 * each lane's mbarrier arrival fires when its copies have landed. */
+		const uint32_t lane = tid & 31u;
+		uint32_t piece = (uint32_t) (stride - f0) * 4u;    /* whole 16-byte units, inside the row */
+		if (piece > MIX_FRAMES * 4u) piece = MIX_FRAMES * 4u;
+		const bool lane_on = lane * 16u < piece;
+		/* the records are fetched three tiles ahead of their use (their L2 latency
+		 * would otherwise sit in this loop's critical path) */
+		auto fetch = [&](uint32_t t) {
+			const uint32_t v = t * MIX_TV + lane;
+			return (lane < (uint32_t) MIX_TV && v < nlv) ? __ldg(vl + v) : make_uint2(0u, 0u);
+		};
+		uint2 pre0 = fetch(0), pre1 = fetch(1), pre2 = fetch(2);
+		for (uint32_t t = 0; t < ntiles; ++t) {
+			const uint32_t st = t % MIX_STAGES, v0 = t * MIX_TV;
+			const uint32_t nv = nlv - v0 < (uint32_t) MIX_TV ? nlv - v0 : (uint32_t) MIX_TV;
+			const uint2 info = pre0;
+			pre0 = pre1; pre1 = pre2; pre2 = fetch(t + 3);
+			if (t >= (uint32_t) MIX_STAGES) mbar_wait(&sm.empty[st], ((t / MIX_STAGES) - 1u) & 1u);
+			const bool has = lane < nv;
+			if (has) sm.vi[st][lane] = info;
+			const uint32_t dynmask = __ballot_sync(FULL, has && info.y == PAN_DYNAMIC && info.x);
+			if (lane == 0) sm.ndyn[st] = __popc(dynmask);
+			const float *src_s = g->rows_s + (size_t) v0 * stride + f0 + lane * 4u;
+			const float *src_r = g->rows_r + (size_t) v0 * stride + f0 + lane * 4u;
+			if (lane_on) {
+#pragma unroll 4
+				for (uint32_t k = 0; k < nv; ++k)
+					cp_async16(&sm.s[st][k][lane * 4u], src_s + (size_t) k * stride);
+				for (uint32_t m = dynmask; m; m &= m - 1u) {
+					const uint32_t k = __ffs(m) - 1u;
+					cp_async16(&sm.r[st][k][lane * 4u], src_r + (size_t) k * stride);
+				}
+			}
+			cp_async_arrive(&sm.full[st]);     /* 32 arrivals per phase; also publishes vi, ndyn */
+		}
+		return;
+	}
+	const uint32_t fx = in_seg ? fi : 0xffffffffu;               /* frames outside take nothing */
+	for (uint32_t t = 0; t < ntiles; ++t) {
+		const uint32_t st = t % MIX_STAGES, v0 = t * MIX_TV;
+		const uint32_t nv = nlv - v0 < (uint32_t) MIX_TV ? nlv - v0 : (uint32_t) MIX_TV;
+		mbar_wait(&sm.full[st], (t / MIX_STAGES) & 1u);
+		const float *sp = &sm.s[st][0][tid], *rp = &sm.r[st][0][tid];
+		const uint2 *ip = &sm.vi[st][0];
+		if (nv == (uint32_t) MIX_TV && sm.ndyn[st] == 0) {
+			/* the common tile: all pans stand still */
+#pragma unroll
+			for (int k = 0; k < MIX_TV; ++k) {
+				const uint2 info = ip[k];
+				const float s = fx < info.x ? sp[k * MIX_FRAMES] : 0.f;
+				const float rr = s * __uint_as_float(info.y);
+				L = (L + s) - rr;                              /* as compiled, Appendix B.3; */
+				R = (R + s) + rr;                              /* adding 0 is exact */
+			}
+		} else {
+			for (uint32_t k = 0; k < nv; ++k) {
+				const uint2 info = ip[k];
+				const bool on = fx < info.x;
+				const float s = on ? sp[k * MIX_FRAMES] : 0.f;
+				float rr;
+				if (info.y == PAN_DYNAMIC) rr = on ? rp[k * MIX_FRAMES] : 0.f;
+				else rr = s * __uint_as_float(info.y);
+				L = (L + s) - rr;
+				R = (R + s) + rr;
+			}
+		}
+		__syncwarp();
+		if ((tid & 31u) == 0) mbar_arrive(&sm.empty[st]);        /* this warp is done with the stage */
+	}
+	if (valid) mix_store(g, cd, mode, f, L, R);
 }
 
 /* float planes (already reduced over ranks) -> int16, for voice-sharded runs */
@@ -2371,8 +2517,17 @@ cudaError_t launch_render(const CallDesc *d_calls, uint32_t ncalls, const SegDes
 cudaError_t launch_mix(const CallDesc *d_calls, uint32_t ncalls, const SegDesc *d_segs,
 		uint32_t max_call_len, uint32_t mode, cudaStream_t stream) {
 	if (ncalls == 0 || max_call_len == 0) return cudaSuccess;
-	dim3 grid((max_call_len + MIX_THREADS - 1) / MIX_THREADS, ncalls);
-	mix_kernel<<<grid, MIX_THREADS, 0, stream>>>(d_calls, d_segs, mode);
+	dim3 grid((max_call_len + MIX_FRAMES - 1) / MIX_FRAMES, ncalls);
+	static bool configured[64] = {false};
+	int dev = 0;
+	cudaGetDevice(&dev);
+	if (dev >= 0 && dev < 64 && !configured[dev]) {
+		cudaError_t e = cudaFuncSetAttribute(mix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+				(int) sizeof(MixSmem));
+		if (e != cudaSuccess) return e;
+		configured[dev] = true;
+	}
+	mix_kernel<<<grid, MIX_FRAMES + 32, sizeof(MixSmem), stream>>>(d_calls, d_segs, mode);
 	return cudaGetLastError();
 }
 

@@ -205,6 +205,7 @@ struct saugen_Generator {
 	bool own_stream = false;
 	uint32_t vo_count = 0, op_count = 0, nlv = 0;
 	uint32_t voice_begin = 0, voice_end = 0;
+	uint32_t row_stride = 0;
 	uint32_t row_len = 0, nbufs = 1, max_ops = 1, wave_mask = 0, seg_cap = 0, sched = 0;
 	float amp_scale = 0.f;
 	/* timeline (host-only integer bookkeeping) */
@@ -221,7 +222,8 @@ struct saugen_Generator {
 	void *d_ops = nullptr, *d_voices = nullptr, *d_events = nullptr, *d_opdata = nullptr,
 	     *d_code = nullptr, *d_prog_ops = nullptr, *d_vev_off = nullptr, *d_vev_idx = nullptr;
 	float *d_rows_s = nullptr, *d_rows_r = nullptr, *d_mix = nullptr;
-	uint32_t *d_vlen = nullptr, *d_status = nullptr, *d_progress = nullptr;
+	VoiceSeg *d_vlen = nullptr;
+	uint32_t *d_status = nullptr, *d_progress = nullptr;
 	UnitDesc *d_units = nullptr, *h_units = nullptr;
 	uint32_t unit_cap = 0;
 	std::vector<UnitDesc> units_tmp;
@@ -515,6 +517,11 @@ extern "C" saugen_Generator *saugen_create(const sauabi_Program *prg, uint32_t s
 	o->row_len = opt->max_call_len ? opt->max_call_len : ms_in_samples(256, srate, NULL);  /* saugns.c:471 */
 	o->row_len = (o->row_len + 3u) & ~3u;
 	if (o->row_len < 4) o->row_len = 4;
+	/* voice rows start a whole number of 128-byte lines apart, an ODD number of them:
+	 * the mix kernel walks down the rows at a fixed column, and a stride with a large
+	 * power-of-two factor (24576 frames = 96 KiB) keeps hitting the same HBM channels */
+	o->row_stride = (o->row_len + 31u) & ~31u;
+	if (((o->row_stride / 32u) & 1u) == 0) o->row_stride += 32u;
 	o->amp_scale = 0.5f * prg->ampmult;                           /* generator.c:183-185 */
 	if (prg->mode & SAUABI_PMODE_AMP_DIV_VOICES) o->amp_scale /= (float) prg->vo_count;
 
@@ -648,7 +655,7 @@ extern "C" saugen_Generator *saugen_create(const sauabi_Program *prg, uint32_t s
 		const size_t o_ops = cv.take(nops * sizeof(OpState));
 		const size_t o_voices = cv.take(nvo * sizeof(VoiceState));
 		const size_t zero_bytes = cv.off - o_ops;         /* operator + voice state start zeroed */
-		const size_t o_vlen = cv.take((size_t) o->seg_cap * nl * sizeof(uint32_t));
+		const size_t o_vlen = cv.take((size_t) o->seg_cap * nl * sizeof(VoiceSeg));
 		const size_t o_status = cv.take((1 + o->seg_cap) * sizeof(uint32_t));
 		const size_t o_progress = cv.take((nl + 1) * sizeof(uint32_t));   /* [nl] = ticket counter */
 		const size_t o_units = cv.take(o->unit_cap * sizeof(UnitDesc));
@@ -662,13 +669,13 @@ extern "C" saugen_Generator *saugen_create(const sauabi_Program *prg, uint32_t s
 		o->d_prog_ops = base + o_prog_ops; o->d_vev_off = base + o_vev_off; o->d_vev_idx = base + o_vev_idx;
 		o->d_desc = (GenDesc*) (base + o_desc);
 		o->d_ops = base + o_ops; o->d_voices = base + o_voices;
-		o->d_vlen = (uint32_t*) (base + o_vlen); o->d_status = (uint32_t*) (base + o_status);
+		o->d_vlen = (VoiceSeg*) (base + o_vlen); o->d_status = (uint32_t*) (base + o_status);
 		o->d_progress = (uint32_t*) (base + o_progress); o->d_units = (UnitDesc*) (base + o_units);
 		o->d_mix = (float*) (base + o_mix); o->d_pcm = (int16_t*) (base + o_pcm);
 		o->d_call = (CallDesc*) (base + o_call); o->d_segs = (SegDesc*) (base + o_segs);
-		float *rows = (float*) o->take(false, 2 * nl * (size_t) o->row_len * sizeof(float));
+		float *rows = (float*) o->take(false, 2 * nl * (size_t) o->row_stride * sizeof(float));
 		if (!rows) { set_err("saugen_create: device memory (carrier rows)", cudaGetLastError()); goto fail; }
-		o->d_rows_s = rows; o->d_rows_r = rows + nl * (size_t) o->row_len;
+		o->d_rows_s = rows; o->d_rows_r = rows + nl * (size_t) o->row_stride;
 		Carver hv;
 		const size_t h_status = hv.take((1 + o->seg_cap) * sizeof(uint32_t));
 		const size_t h_pcm = hv.take(2 * (size_t) o->row_len * sizeof(int16_t));
@@ -695,7 +702,7 @@ extern "C" saugen_Generator *saugen_create(const sauabi_Program *prg, uint32_t s
 		d.mix = o->d_mix; d.pcm = o->d_pcm;
 		d.vo_count = o->vo_count; d.op_count = o->op_count;
 		d.voice_begin = o->voice_begin; d.voice_end = o->voice_end;
-		d.row_len = o->row_len; d.nbufs = o->nbufs; d.srate = srate;
+		d.row_len = o->row_len; d.row_stride = o->row_stride; d.nbufs = o->nbufs; d.srate = srate;
 		d.coeff = (float) (4294967296.0 / srate);                 /* wosc.h:30, math.h:386 */
 		d.amp_scale = o->amp_scale;
 		d.wave_mask = o->wave_mask; d.tables = o->d_tables;
@@ -833,7 +840,7 @@ static int run_common(saugen_Generator *o, size_t buf_len, int stereo, uint32_t 
 		size_t nl = o->nlv ? o->nlv : 1;
 		cudaStreamSynchronize(o->stream);
 		/* new, larger pieces; the old ones stay with the generator until destroy */
-		o->d_vlen = (uint32_t*) o->take(false, (size_t) cap * nl * sizeof(uint32_t));
+		o->d_vlen = (VoiceSeg*) o->take(false, (size_t) cap * nl * sizeof(VoiceSeg));
 		o->d_status = (uint32_t*) o->take(false, (1 + cap) * sizeof(uint32_t));
 		o->d_segs = (SegDesc*) o->take(false, cap * sizeof(SegDesc));
 		o->h_status = (uint32_t*) o->take(true, (1 + cap) * sizeof(uint32_t));
@@ -892,7 +899,7 @@ static int run_common(saugen_Generator *o, size_t buf_len, int stereo, uint32_t 
 	cudaError_t e;
 	e = cudaMemcpyAsync(o->d_segs, o->h_segs, nseg * sizeof(SegDesc), cudaMemcpyHostToDevice, o->stream);
 	if (e == cudaSuccess) e = cudaMemcpyAsync(o->d_units, o->h_units, nunits * sizeof(UnitDesc), cudaMemcpyHostToDevice, o->stream);
-	if (e == cudaSuccess) e = cudaMemsetAsync(o->d_vlen, 0, (size_t) nseg * (o->nlv ? o->nlv : 1) * sizeof(uint32_t), o->stream);
+	if (e == cudaSuccess) e = cudaMemsetAsync(o->d_vlen, 0, (size_t) nseg * (o->nlv ? o->nlv : 1) * sizeof(VoiceSeg), o->stream);
 	if (e == cudaSuccess && ticketed_ctas) e = cudaMemsetAsync(o->d_progress, 0, ((size_t) o->nlv + 1) * sizeof(uint32_t), o->stream);
 	if (e == cudaSuccess) e = cudaMemcpyAsync(o->d_call, o->h_call, sizeof(CallDesc), cudaMemcpyHostToDevice, o->stream);
 	if (e == cudaSuccess) e = cudaMemsetAsync(o->d_status, 0, (1 + nseg) * sizeof(uint32_t), o->stream);
@@ -1027,7 +1034,7 @@ extern "C" int saugen_run_many(saugen_Generator *const *gens, size_t n, int16_t 
 		plan_units(o->segs_tmp, o->units_tmp);
 		cd.unit_off = (uint32_t) units.size(); cd.nunits = (uint32_t) o->units_tmp.size();
 		units.insert(units.end(), o->units_tmp.begin(), o->units_tmp.end());
-		cudaMemsetAsync(o->d_vlen, 0, (size_t) cd.nseg * (o->nlv ? o->nlv : 1) * sizeof(uint32_t), g0->stream);
+		cudaMemsetAsync(o->d_vlen, 0, (size_t) cd.nseg * (o->nlv ? o->nlv : 1) * sizeof(VoiceSeg), g0->stream);
 		segs.insert(segs.end(), o->segs_tmp.begin(), o->segs_tmp.end());
 		calls.push_back(cd);
 		call_of.push_back(i);
@@ -1145,8 +1152,8 @@ extern "C" int saugen_read_voice_rows(saugen_Generator *o, uint32_t vo_id, float
 	cudaSetDevice(o->device);
 	cudaStreamSynchronize(o->stream);
 	const size_t lv = vo_id - o->voice_begin;
-	if (s && cudaMemcpy(s, o->d_rows_s + lv * o->row_len, n * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
-	if (r && cudaMemcpy(r, o->d_rows_r + lv * o->row_len, n * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+	if (s && cudaMemcpy(s, o->d_rows_s + lv * o->row_stride, n * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+	if (r && cudaMemcpy(r, o->d_rows_r + lv * o->row_stride, n * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
 	return 0;
 }
 
