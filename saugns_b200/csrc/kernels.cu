@@ -79,6 +79,42 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase) {
 		"}\n" :: "r"(smem_u32(bar)), "r"(phase) : "memory");
 }
 
+/* ---- shared-window loads / stores by 32-bit address ------------------------ */
+
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+	float4 v;
+	asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+			: "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+	return v;
+}
+__device__ __forceinline__ uint4 lds128u(uint32_t a) {
+	uint4 v;
+	asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+			: "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+	return v;
+}
+__device__ __forceinline__ double2 lds128d(uint32_t a) {
+	double2 v;
+	asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a));
+	return v;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t a) {
+	uint32_t v;
+	asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+	return v;
+}
+__device__ __forceinline__ float lds32f(uint32_t a) {
+	float v;
+	asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+	return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, float4 v) {
+	asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};"
+			:: "r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) {
+	asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory");
+}
 /* ---- per-warp interpreter context --------------------------------------- */
 
 struct Ctx {
@@ -596,15 +632,67 @@ __device__ __forceinline__ bool wosc_eval_full(const C &c, OpState *o, uint32_t 
 }
 
 /* Self-PM: a non-linear recurrence through fb_s, truly serial (wosc.h:273-310).
- * One lane runs it with the state in registers; phases and pm_a amounts come
- * from shared memory, the output replaces the pm_a buffer in place if dst==pma. */
+ * One lane runs it with the state in registers; what matters is the length of
+ * the dependent chain per sample (fb_s -> phase -> table -> differentiate ->
+ * fb_s), so phases and pm_a amounts come in four at a time with one 128-bit
+ * shared load each, outputs leave the same way, the table step is two 128-bit
+ * loads of the coefficient planes (or four taps) and the float division is the
+ * expanded div_scale_by_int.  The output may replace the pm_a buffer in place
+ * (dst == pma): each group of four is read before it is written. */
+/* lut_s: shared-window address of the wave's coefficient planes (CT) or of tap
+ * lut[-1] of its staged float table.  No branch on a zero phase difference:
+ * the step is computed regardless and discarded by selects (wosc.h:251-252). */
+template <bool CT>
+__device__ __forceinline__ float selfmod_step(uint32_t lut_s, uint32_t phase_in, float pm_a,
+		float ds, double doff, uint32_t &prev_phase, double &prev_Is, float &prev_s, float &fb_s) {
+	const uint32_t phase = phase_in + (uint32_t) sau::ftoi64(fb_s * pm_a * 2147483648.f);
+	const int32_t d = (int32_t) (phase - prev_phase);
+	double Is;
+	if (CT) {
+		const uint32_t a = lut_s + ((phase >> sau::WAVE_SLENBITS) << 4);
+		const double2 hi = lds128d(a), lo = lds128d(a + CTAB_PLANE_BYTES);
+		Is = sau::herp_horner(hi.x, hi.y, lo.x, phase) + lo.y;
+	} else {
+		const uint32_t a = lut_s + ((phase >> sau::WAVE_SLENBITS) << 2);
+		const float s0 = lds32f(a), s1 = lds32f(a + 4), s2 = lds32f(a + 8), s3 = lds32f(a + 12);
+		Is = sau::herp_poly(s0, s1, s2, s3, phase) + (double) s1;
+	}
+	const float xq = div_scale_by_int(ds, d);                      /* wosc.h:254-256 */
+	const float s_new = (float) ((Is - prev_Is) * (double) xq + doff);
+	const bool moved = d != 0;
+	const float s = moved ? s_new : prev_s;
+	prev_Is = moved ? Is : prev_Is;
+	prev_phase = phase;                                            /* d == 0: the same value */
+	prev_s = s;
+	fb_s = (fb_s + s) * 0.5f;
+	return s;
+}
+template <bool CT>
+__device__ __forceinline__ void selfmod_loop(uint32_t lut_s, const uint32_t *phase_buf, const float *pma,
+		float *dst, uint32_t n, float ds, double doff, uint32_t &prev_phase, double &prev_Is,
+		float &prev_s, float &fb_s) {
+	uint32_t i = 0;
+	for (; i + 4 <= n; i += 4) {
+		const uint4 ph = *reinterpret_cast<const uint4*>(phase_buf + i);
+		const float4 pa = *reinterpret_cast<const float4*>(pma + i);
+		float4 out;
+		out.x = selfmod_step<CT>(lut_s, ph.x, pa.x, ds, doff, prev_phase, prev_Is, prev_s, fb_s);
+		out.y = selfmod_step<CT>(lut_s, ph.y, pa.y, ds, doff, prev_phase, prev_Is, prev_s, fb_s);
+		out.z = selfmod_step<CT>(lut_s, ph.z, pa.z, ds, doff, prev_phase, prev_Is, prev_s, fb_s);
+		out.w = selfmod_step<CT>(lut_s, ph.w, pa.w, ds, doff, prev_phase, prev_Is, prev_s, fb_s);
+		*reinterpret_cast<float4*>(dst + i) = out;
+	}
+	for (; i < n; ++i)
+		dst[i] = selfmod_step<CT>(lut_s, phase_buf[i], pma[i], ds, doff, prev_phase, prev_Is, prev_s, fb_s);
+}
 __device__ __noinline__ void wosc_selfmod(const ColdCtx c, OpState *o, const uint32_t *phase_buf,
 		const float *pma, float *dst, uint32_t n) {
 	__syncwarp();
 	if (c.lane == 0) {
 		const uint32_t wave = o->mode;
 		const WaveRef lut = wave_ref(c, wave);
-		const float ds = c.wc->diff_scale[wave], doff = c.wc->diff_offset[wave];
+		const float ds = c.wc->diff_scale[wave];
+		const double doff = (double) c.wc->diff_offset[wave];
 		uint32_t prev_phase = o->i1;
 		double prev_Is = o->prev_Is;
 		float prev_s = o->prev_s, fb_s = o->fb_s;
@@ -613,21 +701,12 @@ __device__ __noinline__ void wosc_selfmod(const ColdCtx c, OpState *o, const uin
 			wosc_reset(c, lut, wave, phase_buf[0], prev_phase, prev_Is, prev_s);
 			oscflags &= ~OSC_RESET_DIFF;
 		}
-		for (uint32_t i = 0; i < n; ++i) {
-			float s;
-			const uint32_t phase = phase_buf[i] +
-				(uint32_t) sau::ftoi64(fb_s * pma[i] * 2147483648.f);
-			const int32_t d = (int32_t) (phase - prev_phase);
-			if (d == 0) {
-				s = prev_s;
-			} else {
-				const double Is = herp_ref(lut, phase, (double*) 0, (double*) 0);
-				s = sau::wosc_diff(Is, prev_Is, d, ds, doff);
-				prev_Is = Is; prev_s = s; prev_phase = phase;
-			}
-			dst[i] = s;
-			fb_s = (fb_s + s) * 0.5f;
-		}
+		if (lut.ct)
+			selfmod_loop<true>(smem_u32(lut.p), phase_buf, pma, dst, n, ds, doff,
+					prev_phase, prev_Is, prev_s, fb_s);
+		else
+			selfmod_loop<false>(smem_u32(lut.p) - 4u, phase_buf, pma, dst, n, ds, doff,
+					prev_phase, prev_Is, prev_s, fb_s);
 		o->fb_s = fb_s;
 		o->i1 = prev_phase; o->prev_Is = prev_Is; o->prev_s = prev_s;
 		o->oscflags = (uint8_t) oscflags;
@@ -863,6 +942,44 @@ __device__ void cyclor_fill(Ctx &c, const Instr &in, uint32_t n) {
 
 /* ---- sauRasG_run / sauRasG_run_selfmod (rasg.h:692-772) ----------------- */
 
+/* one sample of sauRasG_run_selfmod's loop, rasg.h:248-280 */
+__device__ __forceinline__ float rasg_self_step(unsigned func, unsigned flags, int sr, uint32_t alpha,
+		int line, float phase_in, uint32_t cycle_in, float pma, float &fb_s, float &prev_s) {
+	const float pm_a = fb_s * pma * 0.5f;
+	float phase = phase_in + pm_a;
+	const int32_t cycle_adj = (int32_t) floorf(phase);
+	const uint32_t cycle = cycle_in + (uint32_t) cycle_adj;
+	phase -= (float) cycle_adj;
+	const float s = sau::rasg_sample(func, flags, sr, alpha, line, cycle, phase, true, false);
+	fb_s = ((fb_s + prev_s) + s) * 0.5f;
+	prev_s = s;
+	return s;
+}
+/* FUNC folded in (0xff: taken from func_dyn), no option flags; inputs and outputs
+ * four at a time (the output replaces the phase buffer in place) */
+template <unsigned FUNC>
+__device__ __noinline__ void rasg_self_loop(float *main_buf, const uint32_t *cycle_buf, const float *pma,
+		uint32_t n, int sr, uint32_t alpha, int line, float &fb_s_io, float &prev_s_io,
+		unsigned func_dyn = 0) {
+	const unsigned func = FUNC == 0xffu ? func_dyn : FUNC;
+	float fb_s = fb_s_io, prev_s = prev_s_io;
+	uint32_t i = 0;
+	for (; i + 4 <= n; i += 4) {
+		const float4 ph = *reinterpret_cast<const float4*>(main_buf + i);
+		const uint4 cy = *reinterpret_cast<const uint4*>(cycle_buf + i);
+		const float4 pa = *reinterpret_cast<const float4*>(pma + i);
+		float4 out;
+		out.x = rasg_self_step(func, 0u, sr, alpha, line, ph.x, cy.x, pa.x, fb_s, prev_s);
+		out.y = rasg_self_step(func, 0u, sr, alpha, line, ph.y, cy.y, pa.y, fb_s, prev_s);
+		out.z = rasg_self_step(func, 0u, sr, alpha, line, ph.z, cy.z, pa.z, fb_s, prev_s);
+		out.w = rasg_self_step(func, 0u, sr, alpha, line, ph.w, cy.w, pa.w, fb_s, prev_s);
+		*reinterpret_cast<float4*>(main_buf + i) = out;
+	}
+	for (; i < n; ++i)
+		main_buf[i] = rasg_self_step(func, 0u, sr, alpha, line, main_buf[i], cycle_buf[i], pma[i], fb_s, prev_s);
+	fb_s_io = fb_s; prev_s_io = prev_s;
+}
+
 __device__ void rasg_run(Ctx &c, const Instr &in, uint32_t n) {
 	OpState *o = op_ptr(c, in.op);
 	const unsigned flags = o->ras_flags, func = o->ras_func;
@@ -876,17 +993,22 @@ __device__ void rasg_run(Ctx &c, const Instr &in, uint32_t n) {
 			float *main_buf = c.bufs + in.a * CHUNK;
 			const uint32_t *cycle_buf = reinterpret_cast<const uint32_t*>(c.bufs + in.b * CHUNK);
 			const float *pma = c.bufs + in.c * CHUNK;
-			for (uint32_t i = 0; i < n; ++i) {
-				const float pm_a = fb_s * pma[i] * 0.5f;
-				float phase = main_buf[i] + pm_a;
-				const int32_t cycle_adj = (int32_t) floorf(phase);
-				const uint32_t cycle = cycle_buf[i] + (uint32_t) cycle_adj;
-				phase -= (float) cycle_adj;
-				const float s = sau::rasg_sample(func, flags, sr, alpha, line, cycle, phase,
-						true, false);
-				main_buf[i] = s;
-				fb_s = ((fb_s + prev_s) + s) * 0.5f;
-				prev_s = s;
+			/* the plain modes (no option flags) get a loop with the function folded in:
+			 * the serial chain per sample is what this path costs */
+			if ((flags & 0x3ffu & ~(SAUABI_RAS_O_LINE_SET | SAUABI_RAS_O_FUNC_SET | SAUABI_RAS_O_LEVEL_SET |
+					SAUABI_RAS_O_ASUBVAL_SET)) == 0) {
+				switch (func) {
+				case SAUABI_RAS_F_URAND: rasg_self_loop<SAUABI_RAS_F_URAND>(main_buf, cycle_buf, pma, n, sr, alpha, line, fb_s, prev_s); break;
+				case SAUABI_RAS_F_GAUSS: rasg_self_loop<SAUABI_RAS_F_GAUSS>(main_buf, cycle_buf, pma, n, sr, alpha, line, fb_s, prev_s); break;
+				case SAUABI_RAS_F_BIN: rasg_self_loop<SAUABI_RAS_F_BIN>(main_buf, cycle_buf, pma, n, sr, alpha, line, fb_s, prev_s); break;
+				case SAUABI_RAS_F_TERN: rasg_self_loop<SAUABI_RAS_F_TERN>(main_buf, cycle_buf, pma, n, sr, alpha, line, fb_s, prev_s); break;
+				case SAUABI_RAS_F_FIXED: rasg_self_loop<SAUABI_RAS_F_FIXED>(main_buf, cycle_buf, pma, n, sr, alpha, line, fb_s, prev_s); break;
+				default: rasg_self_loop<0xffu>(main_buf, cycle_buf, pma, n, sr, alpha, line, fb_s, prev_s, func); break;
+				}
+			} else {
+				for (uint32_t i = 0; i < n; ++i)
+					main_buf[i] = rasg_self_step(func, flags, sr, alpha, line, main_buf[i], cycle_buf[i],
+							pma[i], fb_s, prev_s);
 			}
 			o->fb_s = fb_s; o->prev_s = prev_s;
 		}
@@ -1360,8 +1482,10 @@ __device__ __forceinline__ bool op_outlasts_block(const OpState *o) {
 
 __device__ __noinline__ bool steady_check(OpState *sops, const Instr *code, uint32_t code_len) {
 	uint32_t seen = 0;         /* operator slots already visited (< 32 of them) */
+	uint4 raw_next = __ldg(reinterpret_cast<const uint4*>(code));
 	for (uint32_t pc = 0; pc < code_len; ++pc) {
-		const uint4 raw = __ldg(reinterpret_cast<const uint4*>(code + pc));
+		const uint4 raw = raw_next;
+		if (pc + 1 < code_len) raw_next = __ldg(reinterpret_cast<const uint4*>(code + pc + 1));
 		Instr in;
 		memcpy(&in, &raw, sizeof(in));
 		const OpState *o = sops + in.op;
@@ -1420,8 +1544,10 @@ __device__ __forceinline__ void line_block_update(OpState *o, int li) {
 
 /* lane 0 only */
 __device__ __noinline__ void steady_update(OpState *sops, const Instr *code, uint32_t code_len) {
+	uint4 raw_next = __ldg(reinterpret_cast<const uint4*>(code));
 	for (uint32_t pc = 0; pc < code_len; ++pc) {
-		const uint4 raw = __ldg(reinterpret_cast<const uint4*>(code + pc));
+		const uint4 raw = raw_next;
+		if (pc + 1 < code_len) raw_next = __ldg(reinterpret_cast<const uint4*>(code + pc + 1));
 		Instr in;
 		memcpy(&in, &raw, sizeof(in));
 		OpState *o = sops + in.op;
@@ -1520,40 +1646,6 @@ struct FastCtx {               /* all registers */
 	const WaveCoeffs *wc;
 	const float *tab;          // generic pointer to the staged tables (rare paths)
 };
-__device__ __forceinline__ float4 lds128(uint32_t a) {
-	float4 v;
-	asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-			: "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
-	return v;
-}
-__device__ __forceinline__ uint4 lds128u(uint32_t a) {
-	uint4 v;
-	asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
-			: "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
-	return v;
-}
-__device__ __forceinline__ double2 lds128d(uint32_t a) {
-	double2 v;
-	asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a));
-	return v;
-}
-__device__ __forceinline__ uint32_t lds32(uint32_t a) {
-	uint32_t v;
-	asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
-	return v;
-}
-__device__ __forceinline__ float lds32f(uint32_t a) {
-	float v;
-	asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
-	return v;
-}
-__device__ __forceinline__ void sts128(uint32_t a, float4 v) {
-	asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};"
-			:: "r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
-__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) {
-	asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory");
-}
 template <int NS>
 __device__ __forceinline__ void fld(const FastCtx &c, uint32_t buf, float v[NS]) {
 	const uint32_t a = c.sb + buf * FastCfg<NS>::FBUF_BYTES;
@@ -1598,10 +1690,30 @@ __device__ __forceinline__ void line_value_steady(const FastCtx &c, uint32_t op,
 	}
 	const float inv = lds32f(op + OS_LINV + 4 * li);
 	{
-		const LineVec<NS> t = line_goal_fill<NS>(v0, __uint_as_float(core.y), inv,
-				core.z + c.oc + c.lane * NS, core.w, LM_TYPE(meta));
+		const float vt = __uint_as_float(core.y);
+		const uint32_t pos = core.z + c.oc + c.lane * NS;
+		int t = (int) LM_TYPE(meta);
+		if (t == sau::L_exp) t = (v0 > vt) ? sau::L_xpe : sau::L_lge;
+		else if (t == sau::L_log) t = (v0 < vt) ? sau::L_xpe : sau::L_lge;
+		if (t == sau::L_lin || t == sau::L_xpe || t == sau::L_lge) {
+			/* the usual envelope shapes stay in line (no call, no stack traffic);
+			 * same set-up as line_goal_fill / sau::line_fill_setup */
+			sau::LineFill f;
+			f.type = t;
+			f.v0 = v0; f.vt = vt; f.pos = pos;
+			f.adj_pos = (int32_t) (pos - (core.w / 2));
+			f.inv = inv;
+			f.vm = (v0 + vt) * 0.5f;
+			f.vd = vt - v0;
+			f.c = 0.f;
+			if (t == sau::L_lin) { f.c = f.vd * f.inv; line_fillN<sau::L_lin, NS>(f, out); }
+			else if (t == sau::L_xpe) { f.c = v0 - vt; line_fillN<sau::L_xpe, NS>(f, out); }
+			else line_fillN<sau::L_lge, NS>(f, out);
+		} else {
+			const LineVec<NS> r = line_goal_fill<NS>(v0, vt, inv, pos, core.w, LM_TYPE(meta));
 #pragma unroll
-		for (int k = 0; k < NS; ++k) out[k] = t.v[k];
+			for (int k = 0; k < NS; ++k) out[k] = r.v[k];
+		}
 	}
 	if (m && (flags & SAUABI_LINEP_GOAL_RATIO)) {
 #pragma unroll
@@ -1793,8 +1905,11 @@ __device__ __noinline__ void vout_unaligned(uint32_t sbuf_s, uint32_t sbuf_r, fl
 template <int NS, bool CTAB>
 __device__ __forceinline__ void run_chunk_fast(const FastCtx &c, const Instr *code,
 		uint32_t code_len, float *row_s, float *row_r) {
+	/* the next instruction is fetched while the current one runs */
+	uint4 raw_next = __ldg(reinterpret_cast<const uint4*>(code));
 	for (uint32_t pc = 0; pc < code_len; ++pc) {
-		const uint4 raw = __ldg(reinterpret_cast<const uint4*>(code + pc));
+		const uint4 raw = raw_next;
+		if (pc + 1 < code_len) raw_next = __ldg(reinterpret_cast<const uint4*>(code + pc + 1));
 		Instr in;
 		memcpy(&in, &raw, sizeof(in));
 		const uint32_t op = c.so + in.op * (uint32_t) sizeof(OpState);

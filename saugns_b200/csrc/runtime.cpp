@@ -802,15 +802,15 @@ static Shape pick_shape(uint32_t ntasks, uint32_t wave_mask, uint32_t nbufs, uin
 	const bool want_ctab = have_coefs && nw >= 1 && nw <= 2 && !(env && env[0] == '0');
 	Shape sh;
 	if (want_ctab) {
+		/* one CTA per SM (the planes fill most of its shared memory): as many warps
+		 * per CTA as it takes to hold every task in one resident wave, up to what fits */
 		sh.mask = wave_mask | CTAB_FLAG;
-		sh.warps = 16;
-		while (sh.warps > 1 && (ntasks + sh.warps - 1) / sh.warps < sms) sh.warps >>= 1;
-		if (sh.warps == 16 || (ntasks + 15) / 16 >= sms) {
-			/* all SMs busy: the largest CTA that fits */
-			sh.warps = 16;
-			while (sh.warps > 4 && render_smem_bytes(sh.mask, nbufs, max_ops, sh.warps) > SMEM_CAP) --sh.warps;
-		}
-		if (render_smem_bytes(sh.mask, nbufs, max_ops, sh.warps) <= SMEM_CAP) return sh;
+		uint32_t fit = 16;
+		while (fit > 1 && render_smem_bytes(sh.mask, nbufs, max_ops, fit) > SMEM_CAP) --fit;
+		sh.warps = (ntasks + sms - 1) / sms;
+		if (sh.warps < 1) sh.warps = 1;
+		if (sh.warps > fit) sh.warps = fit;
+		if (render_smem_bytes(sh.mask, nbufs, max_ops, sh.warps) <= SMEM_CAP && fit >= 4) return sh;
 	}
 	sh.mask = wave_mask;
 	sh.warps = 8;
