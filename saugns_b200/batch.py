@@ -16,41 +16,76 @@ import numpy as np
 from . import generator as G
 
 
+def _capacity_frames(prg, srate, call_len):
+    """Upper bound of the frames a program renders (its duration rounded up to whole calls)."""
+    from . import program as P
+    ms = P.Program.from_address(prg.ptr).duration_ms
+    frames = (ms * srate + 999) // 1000
+    return (frames // call_len + 2) * call_len
+
+
 def render_batch(programs, srate=96000, device=0, call_len=None, tables=None, group_size=256,
                  stereo=True, max_frames=None):
     """Render every program of `programs` -> list of int16 arrays [frames, ch],
-    in input order.  Programs are independent (no mixing between them)."""
+    in input order.  Programs are independent (no mixing between them).
+
+    Each call's PCM lands directly in the program's final array (the C side
+    copies from its pinned staging buffer to the address it is given), so the
+    per-call Python work is a few vector operations over the live set."""
+    import ctypes as C
+    L = G.lib()
     if call_len is None:
         call_len = srate * 256 // 1000            # saugns.c:471
     ch = 2 if stereo else 1
     n = len(programs)
     out = [None] * n
-    chunks = {}
-    live = []                                     # [(index, Generator)]
+    idx, gens, bufs = [], [], []                  # the live set, parallel lists
+    gptr = np.zeros(0, np.uint64)                 # generator handles
+    base = np.zeros(0, np.uint64)                 # address of each output array
+    pos = np.zeros(0, np.int64)                   # frames written so far
+    cap = np.zeros(0, np.int64)
     nxt = 0
-    while nxt < n or live:
-        while nxt < n and len(live) < group_size:
-            g = G.Generator(programs[nxt], srate, tables=tables, device=device,
-                            max_call_len=call_len)
-            live.append((nxt, g))
-            chunks[nxt] = []
-            nxt += 1
-        more, pcm, lens = G.run_many([g for _, g in live], call_len, stereo)
-        keep = []
-        for k, (i, g) in enumerate(live):
-            if lens[k]:
-                chunks[i].append(pcm[k][:lens[k] * ch].copy())
-            done = not more[k]
-            if max_frames and sum(c.size for c in chunks[i]) >= max_frames * ch:
-                done = True
-            if done:
-                g.close()
-                parts = chunks.pop(i)
-                out[i] = (np.concatenate(parts).reshape(-1, ch) if parts
-                          else np.zeros((0, ch), np.int16))
-            else:
-                keep.append((i, g))
-        live = keep
+    while nxt < n or gens:
+        if nxt < n and len(gens) < group_size:
+            while nxt < n and len(gens) < group_size:
+                g = G.Generator(programs[nxt], srate, tables=tables, device=device,
+                                max_call_len=call_len)
+                c = _capacity_frames(programs[nxt], srate, call_len)
+                b = np.empty(c * ch, np.int16)
+                idx.append(nxt); gens.append(g); bufs.append(b)
+                nxt += 1
+            k0 = len(gptr)
+            gptr = np.concatenate([gptr, np.array([g.ptr for g in gens[k0:]], np.uint64)])
+            base = np.concatenate([base, np.array([b.ctypes.data for b in bufs[k0:]], np.uint64)])
+            pos = np.concatenate([pos, np.zeros(len(gens) - k0, np.int64)])
+            cap = np.concatenate([cap, np.array([b.size // ch for b in bufs[k0:]], np.int64)])
+        m = len(gens)
+        for k in np.nonzero(pos + call_len > cap)[0]:      # rare: longer than announced
+            bufs[k] = np.concatenate([bufs[k], np.empty(4 * call_len * ch, np.int16)])
+            base[k] = bufs[k].ctypes.data
+            cap[k] = bufs[k].size // ch
+        ptrs = base + (pos * (2 * ch)).astype(np.uint64)
+        lens = np.zeros(m, np.uint64)
+        more = np.zeros(m, np.int32)
+        r = L.saugen_run_many(gptr.ctypes.data, m, ptrs.ctypes.data, call_len, int(stereo),
+                              lens.ctypes.data, more.ctypes.data)
+        if r < 0:
+            raise RuntimeError("saugen_run_many failed: " + G.last_error())
+        pos += lens.astype(np.int64)
+        done = more == 0
+        if max_frames:
+            done |= pos >= max_frames
+        if done.any():
+            keep = []
+            for k in range(m):
+                if done[k]:
+                    gens[k].close()
+                    out[idx[k]] = bufs[k][:pos[k] * ch].reshape(-1, ch)
+                else:
+                    keep.append(k)
+            idx = [idx[k] for k in keep]; gens = [gens[k] for k in keep]; bufs = [bufs[k] for k in keep]
+            kk = np.array(keep, np.int64)
+            gptr, base, pos, cap = gptr[kk], base[kk], pos[kk], cap[kk]
     return out
 
 

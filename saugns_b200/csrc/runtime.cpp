@@ -20,7 +20,9 @@
 #include <string>
 #include <vector>
 #include <map>
+#include <set>
 #include <mutex>
+#include <thread>
 
 #include "../../include/saugen_b200.h"
 #include "device_types.h"
@@ -117,6 +119,7 @@ struct MemPool {
 	std::mutex mu;
 	std::multimap<size_t, void*> free_[2][MAXDEV];     /* [0] device memory, [1] pinned host */
 	std::map<void*, size_t> live;
+	std::set<void*> slab_piece;                        /* carved out of a slab: recycled only */
 	size_t cached[2][MAXDEV] = {{0}};
 	static size_t round_size(size_t n) {
 		if (n < 4096) return 4096;
@@ -139,16 +142,31 @@ struct MemPool {
 				return p;
 			}
 		}
+		/* small classes come out of slabs: one cudaMalloc / cudaHostAlloc per SLAB bytes
+		 * instead of one per generator (pinned allocations cost about a millisecond) */
+		const size_t SLAB = (size_t) 8 << 20;
+		const size_t want = r <= SLAB / 4 ? SLAB / r * r : r;
 		void *p = nullptr;
-		cudaError_t e = host ? cudaHostAlloc(&p, r, cudaHostAllocPortable) : cudaMalloc(&p, r);
+		cudaError_t e = host ? cudaHostAlloc(&p, want, cudaHostAllocPortable) : cudaMalloc(&p, want);
 		if (e != cudaSuccess) {                        /* give the cache back and retry once */
 			cudaGetLastError();
 			trim(host, d);
-			e = host ? cudaHostAlloc(&p, r, cudaHostAllocPortable) : cudaMalloc(&p, r);
+			e = host ? cudaHostAlloc(&p, want, cudaHostAllocPortable) : cudaMalloc(&p, want);
 			if (e != cudaSuccess) return nullptr;
 		}
 		std::lock_guard<std::mutex> lk(mu);
 		live[p] = r;
+		if (want > r) {
+			/* the rest of the slab goes straight to the free list; slab pieces are
+			 * never handed back to CUDA one by one (trim skips them) */
+			for (size_t off = r; off + r <= want; off += r) {
+				void *q = (unsigned char*) p + off;
+				free_[host][d].insert(std::make_pair(r, q));
+				cached[host][d] += r;
+				slab_piece.insert(q);
+			}
+			slab_piece.insert(p);
+		}
 		return p;
 	}
 	void release(bool host, int dev, void *p) {
@@ -160,7 +178,7 @@ struct MemPool {
 			std::lock_guard<std::mutex> lk(mu);
 			auto it = live.find(p);
 			if (it != live.end()) { r = it->second; live.erase(it); }
-			if (r && cached[host][d] + r <= limit) {
+			if (r && (cached[host][d] + r <= limit || slab_piece.count(p))) {
 				free_[host][d].insert(std::make_pair(r, p));
 				cached[host][d] += r;
 				return;
@@ -172,9 +190,14 @@ struct MemPool {
 		std::vector<void*> v;
 		{
 			std::lock_guard<std::mutex> lk(mu);
-			for (auto &kv : free_[host][d]) v.push_back(kv.second);
-			free_[host][d].clear();
-			cached[host][d] = 0;
+			std::multimap<size_t, void*> keep;
+			size_t kept = 0;
+			for (auto &kv : free_[host][d]) {
+				if (slab_piece.count(kv.second)) { keep.insert(kv); kept += kv.first; }
+				else v.push_back(kv.second);
+			}
+			free_[host][d].swap(keep);
+			cached[host][d] = kept;
 		}
 		for (void *p : v) { if (host) cudaFreeHost(p); else cudaFree(p); }
 	}
@@ -241,6 +264,8 @@ struct saugen_Generator {
 	cudaEvent_t ev_t[3] = {nullptr, nullptr, nullptr};
 	double render_ms = 0.0, mix_ms = 0.0;
 	bool timing = false, timed_call = false;
+	size_t zero_bytes = 0, back_bytes_fixed = 0, units_off_in_call = 0;
+	bool compact = true;               /* [vlen..status] and [status][pcm] still adjacent (no growth yet) */
 	/* every block this generator took from the pool: (pointer, is pinned host) */
 	std::vector<std::pair<void*, bool>> blocks;
 	void *take(bool host, size_t bytes) {
@@ -655,14 +680,21 @@ extern "C" saugen_Generator *saugen_create(const sauabi_Program *prg, uint32_t s
 		const size_t o_ops = cv.take(nops * sizeof(OpState));
 		const size_t o_voices = cv.take(nvo * sizeof(VoiceState));
 		const size_t zero_bytes = cv.off - o_ops;         /* operator + voice state start zeroed */
+		/* zeroed before every call with ONE memset: [vlen][progress + ticket][status];
+		 * read back after every call with ONE copy: [status][pcm] */
 		const size_t o_vlen = cv.take((size_t) o->seg_cap * nl * sizeof(VoiceSeg));
-		const size_t o_status = cv.take((1 + o->seg_cap) * sizeof(uint32_t));
 		const size_t o_progress = cv.take((nl + 1) * sizeof(uint32_t));   /* [nl] = ticket counter */
-		const size_t o_units = cv.take(o->unit_cap * sizeof(UnitDesc));
-		const size_t o_mix = cv.take(2 * (size_t) o->row_len * sizeof(float));
+		const size_t o_status = cv.take((1 + o->seg_cap) * sizeof(uint32_t));
 		const size_t o_pcm = cv.take(2 * (size_t) o->row_len * sizeof(int16_t));
+		o->zero_bytes = o_pcm - o_vlen;
+		o->back_bytes_fixed = o_pcm - o_status;        /* status part of the read-back */
+		const size_t o_mix = cv.take(2 * (size_t) o->row_len * sizeof(float));
+		/* written before every call with ONE copy: [call][segs][units] (same layout in
+		 * the pinned block) */
 		const size_t o_call = cv.take(sizeof(CallDesc));
 		const size_t o_segs = cv.take(o->seg_cap * sizeof(SegDesc));
+		const size_t o_units = cv.take(o->unit_cap * sizeof(UnitDesc));
+		o->units_off_in_call = o_units - o_call;
 		unsigned char *base = (unsigned char*) o->take(false, cv.off);
 		if (!base) { set_err("saugen_create: device memory", cudaGetLastError()); goto fail; }
 		o->d_events = base + o_events; o->d_opdata = base + o_opdata; o->d_code = base + o_code;
@@ -682,6 +714,8 @@ extern "C" saugen_Generator *saugen_create(const sauabi_Program *prg, uint32_t s
 		const size_t h_call = hv.take(sizeof(CallDesc));
 		const size_t h_segs = hv.take(o->seg_cap * sizeof(SegDesc));
 		const size_t h_units = hv.take(o->unit_cap * sizeof(UnitDesc));
+		if (h_pcm - h_status != o_pcm - o_status || h_units - h_call != o_units - o_call ||
+				h_segs - h_call != o_segs - o_call) o->compact = false;
 		unsigned char *hb = (unsigned char*) o->take(true, hv.off);
 		if (!hb) { set_err("saugen_create: pinned host memory", cudaGetLastError()); goto fail; }
 		o->h_status = (uint32_t*) (hb + h_status); o->h_pcm = (int16_t*) (hb + h_pcm);
@@ -812,16 +846,30 @@ static Shape pick_shape(uint32_t ntasks, uint32_t wave_mask, uint32_t nbufs, uin
 		if (sh.warps > fit) sh.warps = fit;
 		if (render_smem_bytes(sh.mask, nbufs, max_ops, sh.warps) <= SMEM_CAP && fit >= 4) return sh;
 	}
+	/* float tables (8 KiB per wave in use), 8-warp CTAs, two per SM where they fit */
 	sh.mask = wave_mask;
 	sh.warps = 8;
-	while (sh.warps > 1 && (ntasks + sh.warps - 1) / sh.warps < sms) sh.warps >>= 1;
 	while (sh.warps > 1 && render_smem_bytes(sh.mask, nbufs, max_ops, sh.warps) > 200 * 1024) sh.warps >>= 1;
+	/* fewer tasks than one wave of such CTAs: small CTAs, spread over the SMs */
+	while (sh.warps > 1 && (ntasks + sh.warps - 1) / sh.warps < sms) sh.warps >>= 1;
 	return sh;
 }
 
 /* mode: 0 = PCM in device memory, 1 = float planes */
+static cudaError_t read_back(saugen_Generator *o, uint32_t nseg, size_t host_pcm_bytes, cudaStream_t st) {
+	if (o->compact && host_pcm_bytes)      /* [status][pcm] in one copy */
+		return cudaMemcpyAsync(o->h_status, o->d_status, o->back_bytes_fixed + host_pcm_bytes,
+				cudaMemcpyDeviceToHost, st);
+	cudaError_t e = cudaMemcpyAsync(o->h_status, o->d_status, (1 + nseg) * sizeof(uint32_t),
+			cudaMemcpyDeviceToHost, st);
+	if (e == cudaSuccess && host_pcm_bytes)
+		e = cudaMemcpyAsync(o->h_pcm, o->d_pcm, host_pcm_bytes, cudaMemcpyDeviceToHost, st);
+	return e;
+}
+
+/* host_pcm_bytes: PCM bytes to bring to the pinned staging buffer (0 = none) */
 static int run_common(saugen_Generator *o, size_t buf_len, int stereo, uint32_t mode,
-		size_t *out_len, int *more_out) {
+		size_t *out_len, int *more_out, size_t host_pcm_bytes = 0) {
 	if (!o) return -1;
 	if (buf_len > o->row_len) { g_err = "saugen_run: buf_len exceeds max_call_len"; return -1; }
 	cudaSetDevice(o->device);
@@ -850,6 +898,7 @@ static int run_common(saugen_Generator *o, size_t buf_len, int stereo, uint32_t 
 			return -1;
 		}
 		o->seg_cap = cap;
+		o->compact = false;
 		o->h_desc.vlen = o->d_vlen; o->h_desc.status = o->d_status; o->h_desc.vlen_cap = cap;
 		cudaMemcpy(o->d_desc, &o->h_desc, sizeof(GenDesc), cudaMemcpyHostToDevice);
 	}
@@ -890,6 +939,7 @@ static int run_common(saugen_Generator *o, size_t buf_len, int stereo, uint32_t 
 			return -1;
 		}
 		o->unit_cap = cap;
+		o->compact = false;
 	}
 	const uint32_t nunits = (uint32_t) o->units_tmp.size();
 	memcpy(o->h_units, o->units_tmp.data(), nunits * sizeof(UnitDesc));
@@ -897,12 +947,19 @@ static int run_common(saugen_Generator *o, size_t buf_len, int stereo, uint32_t 
 	cd.gen = o->d_desc; cd.call_len = (uint32_t) buf_len; cd.nseg = nseg; cd.seg_off = 0;
 	cd.task_base = 0; cd.stereo = stereo ? 1 : 0; cd.unit_off = 0; cd.nunits = nunits; cd._pad = 0;
 	cudaError_t e;
-	e = cudaMemcpyAsync(o->d_segs, o->h_segs, nseg * sizeof(SegDesc), cudaMemcpyHostToDevice, o->stream);
-	if (e == cudaSuccess) e = cudaMemcpyAsync(o->d_units, o->h_units, nunits * sizeof(UnitDesc), cudaMemcpyHostToDevice, o->stream);
-	if (e == cudaSuccess) e = cudaMemsetAsync(o->d_vlen, 0, (size_t) nseg * (o->nlv ? o->nlv : 1) * sizeof(VoiceSeg), o->stream);
-	if (e == cudaSuccess && ticketed_ctas) e = cudaMemsetAsync(o->d_progress, 0, ((size_t) o->nlv + 1) * sizeof(uint32_t), o->stream);
-	if (e == cudaSuccess) e = cudaMemcpyAsync(o->d_call, o->h_call, sizeof(CallDesc), cudaMemcpyHostToDevice, o->stream);
-	if (e == cudaSuccess) e = cudaMemsetAsync(o->d_status, 0, (1 + nseg) * sizeof(uint32_t), o->stream);
+	if (o->compact) {
+		/* one copy in ([call][segs][units]), one memset ([vlen][progress][status]) */
+		e = cudaMemcpyAsync(o->d_call, o->h_call, o->units_off_in_call + nunits * sizeof(UnitDesc),
+				cudaMemcpyHostToDevice, o->stream);
+		if (e == cudaSuccess) e = cudaMemsetAsync(o->d_vlen, 0, o->zero_bytes, o->stream);
+	} else {
+		e = cudaMemcpyAsync(o->d_segs, o->h_segs, nseg * sizeof(SegDesc), cudaMemcpyHostToDevice, o->stream);
+		if (e == cudaSuccess) e = cudaMemcpyAsync(o->d_units, o->h_units, nunits * sizeof(UnitDesc), cudaMemcpyHostToDevice, o->stream);
+		if (e == cudaSuccess) e = cudaMemsetAsync(o->d_vlen, 0, (size_t) nseg * (o->nlv ? o->nlv : 1) * sizeof(VoiceSeg), o->stream);
+		if (e == cudaSuccess && ticketed_ctas) e = cudaMemsetAsync(o->d_progress, 0, ((size_t) o->nlv + 1) * sizeof(uint32_t), o->stream);
+		if (e == cudaSuccess) e = cudaMemcpyAsync(o->d_call, o->h_call, sizeof(CallDesc), cudaMemcpyHostToDevice, o->stream);
+		if (e == cudaSuccess) e = cudaMemsetAsync(o->d_status, 0, (1 + nseg) * sizeof(uint32_t), o->stream);
+	}
 	o->timed_call = o->timing;
 	if (e == cudaSuccess && o->timed_call) e = cudaEventRecord(o->ev_t[0], o->stream);
 	if (e == cudaSuccess) {
@@ -916,8 +973,7 @@ static int run_common(saugen_Generator *o, size_t buf_len, int stereo, uint32_t 
 		o->counters[1]++;
 	}
 	if (e == cudaSuccess && o->timed_call) e = cudaEventRecord(o->ev_t[2], o->stream);
-	if (e == cudaSuccess) e = cudaMemcpyAsync(o->h_status, o->d_status, (1 + nseg) * sizeof(uint32_t),
-			cudaMemcpyDeviceToHost, o->stream);
+	if (e == cudaSuccess) e = read_back(o, nseg, host_pcm_bytes, o->stream);
 	if (e != cudaSuccess) { set_err("saugen_run: launch", e); if (out_len) *out_len = 0; return -1; }
 	(void) more_out;
 	return 1;   /* caller finishes after its own D2H + sync via finish_call */
@@ -949,12 +1005,11 @@ static int finish_call(saugen_Generator *o, size_t buf_len, size_t *out_len) {
 extern "C" int saugen_run(saugen_Generator *o, int16_t *buf, size_t buf_len, int stereo,
 		size_t *out_len) {
 	int more = 0;
-	int r = run_common(o, buf_len, stereo, 0, out_len, &more);
-	if (r < 0) return r;
 	const size_t bytes = buf_len * (stereo ? 2 : 1) * sizeof(int16_t);
+	int r = run_common(o, buf_len, stereo, 0, out_len, &more, bytes);
+	if (r < 0) return r;
 	if (r == 0) { if (buf) memset(buf, 0, bytes); return 0; }
-	cudaError_t e = cudaMemcpyAsync(o->h_pcm, o->d_pcm, bytes, cudaMemcpyDeviceToHost, o->stream);
-	if (e == cudaSuccess) e = cudaStreamSynchronize(o->stream);
+	cudaError_t e = cudaStreamSynchronize(o->stream);
 	if (e != cudaSuccess) { set_err("saugen_run", e); if (out_len) *out_len = 0; return -1; }
 	if (buf) memcpy(buf, o->h_pcm, bytes);
 	return finish_call(o, buf_len, out_len);
@@ -1034,7 +1089,8 @@ extern "C" int saugen_run_many(saugen_Generator *const *gens, size_t n, int16_t 
 		plan_units(o->segs_tmp, o->units_tmp);
 		cd.unit_off = (uint32_t) units.size(); cd.nunits = (uint32_t) o->units_tmp.size();
 		units.insert(units.end(), o->units_tmp.begin(), o->units_tmp.end());
-		cudaMemsetAsync(o->d_vlen, 0, (size_t) cd.nseg * (o->nlv ? o->nlv : 1) * sizeof(VoiceSeg), g0->stream);
+		if (o->compact) cudaMemsetAsync(o->d_vlen, 0, o->zero_bytes, g0->stream);
+		else cudaMemsetAsync(o->d_vlen, 0, (size_t) cd.nseg * (o->nlv ? o->nlv : 1) * sizeof(VoiceSeg), g0->stream);
 		segs.insert(segs.end(), o->segs_tmp.begin(), o->segs_tmp.end());
 		calls.push_back(cd);
 		call_of.push_back(i);
@@ -1042,7 +1098,7 @@ extern "C" int saugen_run_many(saugen_Generator *const *gens, size_t n, int16_t 
 		wave_mask |= o->wave_mask;
 		if (o->nbufs > nbufs) nbufs = o->nbufs;
 		if (o->max_ops > max_ops) max_ops = o->max_ops;
-		cudaMemsetAsync(o->d_status, 0, (1 + cd.nseg) * sizeof(uint32_t), g0->stream);
+		if (!o->compact) cudaMemsetAsync(o->d_status, 0, (1 + cd.nseg) * sizeof(uint32_t), g0->stream);
 	}
 	if (calls.empty()) return 0;
 	cudaError_t e = cudaSuccess;
@@ -1064,31 +1120,52 @@ extern "C" int saugen_run_many(saugen_Generator *const *gens, size_t n, int16_t 
 	if (e == cudaSuccess) e = cudaMemcpyAsync(d_units, units.data(), units.size() * sizeof(UnitDesc), cudaMemcpyHostToDevice, g0->stream);
 	if (e == cudaSuccess) e = cudaMemcpyAsync(d_calls, calls.data(), calls.size() * sizeof(CallDesc), cudaMemcpyHostToDevice, g0->stream);
 	if (e == cudaSuccess) e = cudaMemcpyAsync(d_segs, segs.data(), segs.size() * sizeof(SegDesc), cudaMemcpyHostToDevice, g0->stream);
+	g0->timed_call = g0->timing;       /* kernel times of the batch accumulate on the first generator */
+	if (e == cudaSuccess && g0->timed_call) e = cudaEventRecord(g0->ev_t[0], g0->stream);
 	if (e == cudaSuccess) {
 		const Shape shape = pick_shape(ntasks, wave_mask, nbufs, max_ops, g0->d_coefs != nullptr);
 		e = launch_render(d_calls, (uint32_t) calls.size(), d_segs, d_units, ntasks, g0->d_tables,
 				g0->d_coefs, shape.mask, nbufs, max_ops, shape.warps, 0, 0, g0->stream);
 		g0->counters[0]++;
 	}
+	if (e == cudaSuccess && g0->timed_call) e = cudaEventRecord(g0->ev_t[1], g0->stream);
 	if (e == cudaSuccess) {
 		e = launch_mix(d_calls, (uint32_t) calls.size(), d_segs, (uint32_t) buf_len, 0, g0->stream);
 		g0->counters[1]++;
 	}
+	if (e == cudaSuccess && g0->timed_call) e = cudaEventRecord(g0->ev_t[2], g0->stream);
 	const size_t bytes = buf_len * (stereo ? 2 : 1) * sizeof(int16_t);
 	for (size_t c = 0; c < calls.size() && e == cudaSuccess; ++c) {
 		saugen_Generator *o = gens[call_of[c]];
-		e = cudaMemcpyAsync(o->h_status, o->d_status, (1 + calls[c].nseg) * sizeof(uint32_t),
-				cudaMemcpyDeviceToHost, g0->stream);
-		if (e == cudaSuccess && bufs && bufs[call_of[c]])
-			e = cudaMemcpyAsync(o->h_pcm, o->d_pcm, bytes, cudaMemcpyDeviceToHost, g0->stream);
+		e = read_back(o, calls[c].nseg, (bufs && bufs[call_of[c]]) ? bytes : 0, g0->stream);
 	}
 	if (e == cudaSuccess) e = cudaStreamSynchronize(g0->stream);
 	if (e != cudaSuccess) { set_err("saugen_run_many", e); return -1; }
+	/* pinned staging -> the callers' buffers: fresh destination pages fault on first
+	 * touch, so a large batch is copied by a few threads */
+	if (bufs) {
+		const size_t nc = calls.size();
+		const size_t *co = call_of.data();     /* thread_local: the workers must not name it */
+		auto copy_range = [co, bufs, gens, bytes](size_t lo, size_t hi) {
+			for (size_t c = lo; c < hi; ++c) {
+				const size_t i = co[c];
+				if (bufs[i]) memcpy(bufs[i], gens[i]->h_pcm, bytes);
+			}
+		};
+		size_t nthr = nc * bytes >= ((size_t) 4 << 20) ? std::thread::hardware_concurrency() / 2 : 1;
+		if (nthr > 8) nthr = 8;
+		if (nthr < 2) copy_range(0, nc);
+		else {
+			std::vector<std::thread> th;
+			for (size_t t = 0; t < nthr; ++t)
+				th.emplace_back(copy_range, nc * t / nthr, nc * (t + 1) / nthr);
+			for (auto &x : th) x.join();
+		}
+	}
 	int any = 0;
 	for (size_t c = 0; c < calls.size(); ++c) {
 		const size_t i = call_of[c];
 		saugen_Generator *o = gens[i];
-		if (bufs && bufs[i]) memcpy(bufs[i], o->h_pcm, bytes);
 		size_t ol = 0;
 		int m = finish_call(o, buf_len, &ol);
 		if (out_lens) out_lens[i] = ol;
