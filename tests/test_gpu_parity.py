@@ -230,3 +230,74 @@ def test_voice_sharded_mix_matches(S, ref, tabs):
     got = np.concatenate(out).reshape(-1, 2)
     assert got.shape == full.shape
     assert np.abs(got.astype(np.int32) - full.astype(np.int32)).max() <= 1
+
+
+def test_two_generators_one_program_alternating(S, ref, tabs):
+    """Two generators alive on the same program at different rates, called alternately
+    (Player_run with an audio device whose rate differs, saugns.c:585-599): instances
+    must be fully independent."""
+    prg = ref.Program(scripts.feature_scripts()["seq_overlap"])
+    ra, rb = ref.RefGenerator(prg, 96000), ref.RefGenerator(prg, 44100)
+    ga, gb = S.Generator(prg, 96000, tables=tabs), S.Generator(prg, 44100, tables=tabs)
+    ma = mb = True
+    while ma or mb:
+        if ma:
+            ma, want, n = ra.run(24576)
+            m2, got, n2 = ga.run(24576)
+            assert (ma, n) == (m2, n2) and np.array_equal(want, got)
+        if mb:
+            mb, want, n = rb.run(11289)
+            m2, got, n2 = gb.run(11289)
+            assert (mb, n) == (m2, n2) and np.array_equal(want, got)
+
+
+def test_edge_calls(S, ref, tabs):
+    """Zero-length calls, calls after the end of signal, out_len on the last call,
+    mono/stereo switching between calls -- all as the reference answers them
+    (generator.c:905-973)."""
+    prg = ref.Program("Wsin f330 t0.07 Wtri f200 t0.03 c-0.5")
+    gr, gg = ref.RefGenerator(prg, 48000), S.Generator(prg, 48000, tables=tabs, max_call_len=4096)
+    for call_len, stereo in [(0, True), (1000, True), (0, False), (1000, False), (4096, True),
+                             (4096, True), (333, True), (0, True)]:
+        a = gr.run(call_len, stereo)
+        b = gg.run(call_len, stereo)
+        assert (a[0], a[2]) == (b[0], b[2]), (call_len, stereo)
+        assert np.array_equal(a[1], b[1]), (call_len, stereo)
+    # buf_len beyond the announced maximum is refused, not clipped
+    with pytest.raises(RuntimeError):
+        gg.run(4097)
+
+
+def test_empty_and_silent_programs(S, ref, tabs):
+    """A script with no sound at all, and one whose only voice has zero amplitude."""
+    for text in ["S a.m0.5", "Wsin a0 t0.05", "Wsin t0"]:
+        prg = ref.Program(text)
+        want = ref.render(prg, srate=96000)
+        got = S.render(prg, srate=96000, tables=tabs)
+        assert got.shape == want.shape and np.array_equal(got, want), text
+
+
+def test_many_short_voices_in_sequence(S, ref, port, tabs):
+    """Voice slots reused by hundreds of events, several events inside one call (more
+    inter-event segments per call than the initial tables hold: the growth path)."""
+    import random
+    rnd = random.Random(11)
+    parts = []
+    for i in range(300):
+        parts.append(f"W{rnd.choice(scripts.WAVES)} f{rnd.uniform(100, 900):.2f} t0.004 "
+                     f"a{rnd.uniform(0.1, 0.6):.2f} c{rnd.uniform(-1, 1):.2f} /0.002")
+    prg = ref.Program("\n".join(parts) + "\n")
+    want = port.render(prg, srate=96000, tables=port.ref_tables())
+    got = S.render(prg, srate=96000, tables=tabs)
+    assert got.shape == want.shape and np.array_equal(got, want)
+    assert np.array_equal(want, ref.render(prg, srate=96000))
+
+
+def test_nesting_limit_reported(S, ref, tabs):
+    """Deeper operator nesting than the device interpreter holds fails at create with
+    a message, it does not render garbage."""
+    depth = 40
+    text = "Wsin f200 t0.05 " + "".join("p[Wsin r1.01 a0.3 " for _ in range(depth)) + "]" * depth
+    prg = ref.Program(text)
+    with pytest.raises(RuntimeError, match="nesting too deep"):
+        S.Generator(prg, 96000, tables=tabs)
