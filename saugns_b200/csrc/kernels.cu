@@ -31,7 +31,8 @@ namespace saugen {
 #define FULL 0xffffffffu
 
 /* per-warp shared memory: operator-state cache, work buffers, len stack */
-constexpr int FAST_NS = 8;            // samples per lane in the steady-block fast path
+constexpr int FAST_NS = 4;            // samples per lane in the steady-block fast path (8 measured
+                                      // slower: its registers allow 16 resident warps per SM, 4 allows 32)
 constexpr uint32_t BUF_FLOATS = 32 * (FAST_NS > SPL ? FAST_NS : SPL);   // per work buffer
 __host__ __device__ inline uint32_t warp_smem_bytes(uint32_t nbufs, uint32_t nslots) {
 	return nslots * (uint32_t) sizeof(OpState) + nbufs * BUF_FLOATS * (uint32_t) sizeof(float) +
@@ -96,6 +97,11 @@ __device__ __forceinline__ uint4 lds128u(uint32_t a) {
 __device__ __forceinline__ double2 lds128d(uint32_t a) {
 	double2 v;
 	asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a));
+	return v;
+}
+__device__ __forceinline__ float2 lds64f(uint32_t a) {
+	float2 v;
+	asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
 	return v;
 }
 __device__ __forceinline__ uint32_t lds32(uint32_t a) {
@@ -164,8 +170,8 @@ constexpr uint32_t TAB_STRIDE = WAVE_LEN + 8;
  * coefficients of sauWave_get_herp in double precision (see coef_kernel) instead
  * of the float tables; every table evaluation, hot or rare, goes through them. */
 constexpr uint32_t CTAB_FLAG = 0x80000000u;
-constexpr uint32_t CTAB_WAVE_BYTES = WAVE_LEN * 32;       // {c3,c2} plane + {c1,c0} plane
-constexpr uint32_t CTAB_PLANE_BYTES = WAVE_LEN * 16;
+constexpr uint32_t CTAB_WAVE_BYTES = WAVE_LEN * 24;       // {c3,c2} double plane + {c1,c0} float plane
+constexpr uint32_t CTAB_PLANE_BYTES = WAVE_LEN * 16;      // offset of the float plane
 /* What the out-of-line (rare path) functions need, passed by value. */
 struct ColdCtx {
 	const float *tab;
@@ -196,11 +202,13 @@ __device__ __forceinline__ WaveRef wave_ref(const C &c, uint32_t wave) {
 __device__ __forceinline__ double herp_ref(const WaveRef &w, uint32_t phase, double *poly_out,
 		double *c0_out) {
 	if (w.ct) {
-		const double2 *pl = reinterpret_cast<const double2*>(w.p) + (phase >> sau::WAVE_SLENBITS);
-		const double2 hi = pl[0], lo = pl[WAVE_LEN];
-		const double p = sau::herp_horner(hi.x, hi.y, lo.x, phase);
-		if (poly_out) { *poly_out = p; *c0_out = lo.y; }
-		return p + lo.y;
+		const uint32_t ind = phase >> sau::WAVE_SLENBITS;
+		const double2 hi = reinterpret_cast<const double2*>(w.p)[ind];
+		const float2 lo = reinterpret_cast<const float2*>(
+				reinterpret_cast<const unsigned char*>(w.p) + CTAB_PLANE_BYTES)[ind];
+		const double p = sau::herp_horner(hi.x, hi.y, (double) lo.x, phase);
+		if (poly_out) { *poly_out = p; *c0_out = (double) lo.y; }
+		return p + (double) lo.y;
 	}
 	/* staged float table: taps lut[ind-1 .. ind+2] are consecutive, no masking */
 	const float *t = reinterpret_cast<const float*>(w.p) - 1 + (phase >> sau::WAVE_SLENBITS);
@@ -649,9 +657,10 @@ __device__ __forceinline__ float selfmod_step(uint32_t lut_s, uint32_t phase_in,
 	const int32_t d = (int32_t) (phase - prev_phase);
 	double Is;
 	if (CT) {
-		const uint32_t a = lut_s + ((phase >> sau::WAVE_SLENBITS) << 4);
-		const double2 hi = lds128d(a), lo = lds128d(a + CTAB_PLANE_BYTES);
-		Is = sau::herp_horner(hi.x, hi.y, lo.x, phase) + lo.y;
+		const uint32_t ind = phase >> sau::WAVE_SLENBITS;
+		const double2 hi = lds128d(lut_s + (ind << 4));
+		const float2 lo = lds64f(lut_s + CTAB_PLANE_BYTES + (ind << 3));
+		Is = sau::herp_horner(hi.x, hi.y, (double) lo.x, phase) + (double) lo.y;
 	} else {
 		const uint32_t a = lut_s + ((phase >> sau::WAVE_SLENBITS) << 2);
 		const float s0 = lds32f(a), s1 = lds32f(a + 4), s2 = lds32f(a + 8), s3 = lds32f(a + 12);
@@ -1817,9 +1826,10 @@ __device__ __forceinline__ void wtail_fast(const FastCtx &c, const Instr &in, ui
 			const uint32_t ct = c.st + slot * CTAB_WAVE_BYTES;
 #pragma unroll
 			for (int k = 0; k < NS; ++k) {
-				const uint32_t a = ct + ((ph[k] >> sau::WAVE_SLENBITS) << 4);
-				const double2 hi = lds128d(a), lo = lds128d(a + CTAB_PLANE_BYTES);
-				Is[k] = sau::herp_horner(hi.x, hi.y, lo.x, ph[k]) + lo.y;
+				const uint32_t ind = ph[k] >> sau::WAVE_SLENBITS;
+				const double2 hi = lds128d(ct + (ind << 4));
+				const float2 lo = lds64f(ct + CTAB_PLANE_BYTES + (ind << 3));
+				Is[k] = sau::herp_horner(hi.x, hi.y, (double) lo.x, ph[k]) + (double) lo.y;
 			}
 		} else {
 			const uint32_t taps = c.st + slot * (TAB_STRIDE * 4) + 12;    /* &lut[-1] */
@@ -2309,9 +2319,10 @@ render_kernel(const CallDesc *calls, uint32_t ncalls, const SegDesc *segs, const
 			warps_per_cta, ticketed);
 }
 
-/* same body for CTAs of up to 16 warps, one per SM (coefficient-table mode: the
- * tables take 64 KiB per wave, so one large CTA shares them among more warps) */
-__global__ void __launch_bounds__(512, 1)
+/* same body for CTAs of up to 32 warps (64 registers), one per SM (coefficient-table
+ * mode: the planes take 48 KiB per wave, so one large CTA shares them among all the
+ * warps an SM can hold -- the path is latency-bound, resident warps are what counts) */
+__global__ void __launch_bounds__(1024, 1)
 render_kernel_wide(const CallDesc *calls, uint32_t ncalls, const SegDesc *segs, const UnitDesc *units,
 		uint32_t ntasks, const float *tables, const double *coefs, uint32_t wave_mask, uint32_t nbufs,
 		uint32_t nslots_ops, uint32_t warps_per_cta, uint32_t ticketed) {
@@ -2562,10 +2573,14 @@ size_t render_smem_bytes(uint32_t wave_mask, uint32_t nbufs, uint32_t nslots_ops
  * sauWave_get_herp (wave.h:127-141, as compiled: sau::herp_poly) forms c1, c2,
  * c3 from the four taps around an index before it touches the phase fraction;
  * they depend on the index alone.  One thread per (wave, index) evaluates the
- * SAME expressions once; the fast path then loads {c3, c2} and {c1, (double)
- * s1} with two 128-bit shared-memory loads.  Layout per wave: 2048 x {c3, c2},
- * then 2048 x {c1, c0}. */
-__global__ void coef_kernel(const float *tables, double *coefs) {
+ * SAME expressions once; the fast path then loads {c3, c2} (doubles) with one
+ * 128-bit and {c1, c0} with one 64-bit shared-memory load.  c1 = 0.5 * (s2 - s0)
+ * and c0 = s1 are float values held as floats (24 bytes per index instead of
+ * 32: two waves leave room for 32 warps per SM); the kernel checks that the
+ * float form of c1 is exact and flags the table set otherwise (the runtime then
+ * stays with the float tables).  Layout per wave: 2048 x {c3, c2}, then
+ * 2048 x {c1, c0}. */
+__global__ void coef_kernel(const float *tables, double *coefs, uint32_t *inexact) {
 	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
 	if (t >= NUM_WAVES * WAVE_LEN) return;
 	const uint32_t w = t / WAVE_LEN, i = t % WAVE_LEN;
@@ -2574,13 +2589,15 @@ __global__ void coef_kernel(const float *tables, double *coefs) {
 	const float s2 = lut[(i + 1) & sau::WAVE_LENMASK], s3 = lut[(i + 2) & sau::WAVE_LENMASK];
 	double c1, c2, c3;
 	sau::herp_coefs(s0, s1, s2, s3, &c1, &c2, &c3);
-	double *base = coefs + (size_t) w * (CTAB_WAVE_BYTES / 8);
-	base[2 * i] = c3; base[2 * i + 1] = c2;
-	base[2 * WAVE_LEN + 2 * i] = c1; base[2 * WAVE_LEN + 2 * i + 1] = (double) s1;
+	unsigned char *base = reinterpret_cast<unsigned char*>(coefs) + (size_t) w * CTAB_WAVE_BYTES;
+	reinterpret_cast<double2*>(base)[i] = make_double2(c3, c2);
+	const float c1f = (float) c1;
+	if ((double) c1f != c1) atomicOr(inexact, 1u);
+	reinterpret_cast<float2*>(base + CTAB_PLANE_BYTES)[i] = make_float2(c1f, s1);
 }
 size_t coef_table_bytes() { return (size_t) NUM_WAVES * CTAB_WAVE_BYTES; }
-cudaError_t launch_coefs(const float *d_tables, double *d_coefs, cudaStream_t stream) {
-	coef_kernel<<<(NUM_WAVES * WAVE_LEN + 255) / 256, 256, 0, stream>>>(d_tables, d_coefs);
+cudaError_t launch_coefs(const float *d_tables, double *d_coefs, uint32_t *d_inexact, cudaStream_t stream) {
+	coef_kernel<<<(NUM_WAVES * WAVE_LEN + 255) / 256, 256, 0, stream>>>(d_tables, d_coefs, d_inexact);
 	return cudaGetLastError();
 }
 

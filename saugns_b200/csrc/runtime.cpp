@@ -35,7 +35,7 @@ cudaError_t launch_render(const CallDesc *d_calls, uint32_t ncalls, const SegDes
 		uint32_t ticketed_ctas, uint32_t sched_mode, cudaStream_t stream);
 int render_ctas_per_sm(size_t smem, uint32_t warps);
 size_t coef_table_bytes();
-cudaError_t launch_coefs(const float *d_tables, double *d_coefs, cudaStream_t stream);
+cudaError_t launch_coefs(const float *d_tables, double *d_coefs, uint32_t *d_inexact, cudaStream_t stream);
 cudaError_t launch_mix(const CallDesc *d_calls, uint32_t ncalls, const SegDesc *d_segs,
 		uint32_t max_call_len, uint32_t mode, cudaStream_t stream);
 cudaError_t launch_planes_to_pcm(const float *d_mix, uint32_t plane_stride, uint32_t n,
@@ -97,10 +97,17 @@ static float *get_device_tables(int device, const saugen_WaveTables *t, double *
 		cudaFree(d);
 		return nullptr;
 	}
-	/* per-index cubic coefficients, computed once on the device from the uploaded tables */
-	if (launch_coefs(d, dc, 0) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) {
-		cudaFree(d); cudaFree(dc);
-		return nullptr;
+	/* per-index cubic coefficients, computed once on the device from the uploaded tables;
+	 * a table set whose c1 values are not exact floats gets no planes (never seen) */
+	{
+		uint32_t *d_flag = nullptr, h_flag = 1;
+		bool ok = cudaMalloc(&d_flag, sizeof(uint32_t)) == cudaSuccess &&
+			cudaMemset(d_flag, 0, sizeof(uint32_t)) == cudaSuccess &&
+			launch_coefs(d, dc, d_flag, 0) == cudaSuccess &&
+			cudaMemcpy(&h_flag, d_flag, sizeof h_flag, cudaMemcpyDeviceToHost) == cudaSuccess;
+		if (d_flag) cudaFree(d_flag);
+		if (!ok) { cudaFree(d); cudaFree(dc); return nullptr; }
+		if (h_flag) { cudaFree(dc); dc = nullptr; }
 	}
 	g_tabs[key] = TableBlock{d, dc};
 	if (coefs_out) *coefs_out = dc;
@@ -819,11 +826,13 @@ static void plan_units(const std::vector<SegDesc> &segs, std::vector<UnitDesc> &
 }
 
 /* Launch shape of render_kernel for `ntasks` voice tasks.
- * Coefficient-table mode (kernels.cu:CTAB_FLAG) when the launch uses at most two
- * waves: their coefficient planes (64 KiB each) go to shared memory and one wide
- * CTA per SM shares them among up to 16 warps.  Otherwise the float tables
- * (8 KiB per wave) are staged and 8-warp CTAs run 2 per SM (128 registers).
- * Small CTAs while there are fewer tasks than SMs x warps. */
+ * The path is latency-bound: what counts is how many
+ * voices are resident per SM at once.  One CTA per SM, with as many warps as it
+ * takes to hold every task in ONE resident wave (up to what shared memory
+ * allows, at most 32); up to 8 warps run the 128-register kernel, more the
+ * 64-register one.  Tables: coefficient planes (kernels.cu:CTAB_FLAG, 48 KiB per
+ * wave) when the launch uses at most two waves, else the float tables (8 KiB
+ * per wave in use). */
 static const uint32_t CTAB_FLAG = 0x80000000u;
 static const size_t SMEM_CAP = 227 * 1024;
 struct Shape { uint32_t warps; uint32_t mask; };
@@ -835,23 +844,16 @@ static Shape pick_shape(uint32_t ntasks, uint32_t wave_mask, uint32_t nbufs, uin
 	static const char *env = getenv("SAUGEN_CTAB");       /* developer knob: 0 = off */
 	const bool want_ctab = have_coefs && nw >= 1 && nw <= 2 && !(env && env[0] == '0');
 	Shape sh;
-	if (want_ctab) {
-		/* one CTA per SM (the planes fill most of its shared memory): as many warps
-		 * per CTA as it takes to hold every task in one resident wave, up to what fits */
-		sh.mask = wave_mask | CTAB_FLAG;
-		uint32_t fit = 16;
+	for (int pass = want_ctab ? 0 : 1; pass < 2; ++pass) {
+		sh.mask = pass == 0 ? (wave_mask | CTAB_FLAG) : wave_mask;
+		uint32_t fit = 32;
 		while (fit > 1 && render_smem_bytes(sh.mask, nbufs, max_ops, fit) > SMEM_CAP) --fit;
 		sh.warps = (ntasks + sms - 1) / sms;
 		if (sh.warps < 1) sh.warps = 1;
 		if (sh.warps > fit) sh.warps = fit;
-		if (render_smem_bytes(sh.mask, nbufs, max_ops, sh.warps) <= SMEM_CAP && fit >= 4) return sh;
+		if (render_smem_bytes(sh.mask, nbufs, max_ops, sh.warps) <= SMEM_CAP && (pass == 1 || fit >= 8))
+			return sh;
 	}
-	/* float tables (8 KiB per wave in use), 8-warp CTAs, two per SM where they fit */
-	sh.mask = wave_mask;
-	sh.warps = 8;
-	while (sh.warps > 1 && render_smem_bytes(sh.mask, nbufs, max_ops, sh.warps) > 200 * 1024) sh.warps >>= 1;
-	/* fewer tasks than one wave of such CTAs: small CTAs, spread over the SMs */
-	while (sh.warps > 1 && (ntasks + sh.warps - 1) / sh.warps < sms) sh.warps >>= 1;
 	return sh;
 }
 
