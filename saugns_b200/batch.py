@@ -25,41 +25,82 @@ def _capacity_frames(prg, srate, call_len):
 
 
 def render_batch(programs, srate=96000, device=0, call_len=None, tables=None, group_size=256,
-                 stereo=True, max_frames=None):
+                 stereo=True, max_frames=None, threads=3):
     """Render every program of `programs` -> list of int16 arrays [frames, ch],
     in input order.  Programs are independent (no mixing between them).
+
+    `threads` host threads each keep their own live set of up to `group_size`
+    generators (admitted from one shared queue) on their own stream: while one
+    set's kernels run, the other threads plan calls, create and retire generators
+    and copy PCM (all of that happens inside the C library, without the GIL), so
+    the GPU does not wait for the host between calls.
 
     Each call's PCM lands directly in the program's final array (the C side
     copies from its pinned staging buffer to the address it is given), so the
     per-call Python work is a few vector operations over the live set."""
-    import ctypes as C
-    L = G.lib()
+    import itertools
+    import threading
     if call_len is None:
         call_len = srate * 256 // 1000            # saugns.c:471
-    ch = 2 if stereo else 1
     n = len(programs)
     out = [None] * n
+    queue = itertools.count()                     # next program index; next() is atomic under the GIL
+    threads = max(1, min(int(threads), (n + 15) // 16))
+    if threads == 1:
+        _render_worker(programs, out, queue, srate, device, call_len, tables, group_size, stereo,
+                       max_frames)
+        return out
+    errs = []
+
+    def work():
+        try:
+            _render_worker(programs, out, queue, srate, device, call_len, tables, group_size,
+                           stereo, max_frames)
+        except BaseException as e:                # re-raised on the caller's thread
+            errs.append(e)
+
+    th = [threading.Thread(target=work) for _ in range(threads)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    if errs:
+        raise errs[0]
+    return out
+
+
+def _render_worker(programs, out, queue, srate, device, call_len, tables, group_size, stereo,
+                   max_frames):
+    """One live set: admit from `queue`, advance with saugen_run_many, retire."""
+    L = G.lib()
+    ch = 2 if stereo else 1
+    n = len(programs)
     idx, gens, bufs = [], [], []                  # the live set, parallel lists
     gptr = np.zeros(0, np.uint64)                 # generator handles
     base = np.zeros(0, np.uint64)                 # address of each output array
     pos = np.zeros(0, np.int64)                   # frames written so far
     cap = np.zeros(0, np.int64)
-    nxt = 0
-    while nxt < n or gens:
-        if nxt < n and len(gens) < group_size:
-            while nxt < n and len(gens) < group_size:
-                g = G.Generator(programs[nxt], srate, tables=tables, device=device,
+    drained = False
+    while not drained or gens:
+        if not drained and len(gens) < group_size:
+            k0 = len(gens)
+            while len(gens) < group_size:
+                i = next(queue)
+                if i >= n:
+                    drained = True
+                    break
+                g = G.Generator(programs[i], srate, tables=tables, device=device,
                                 max_call_len=call_len)
-                c = _capacity_frames(programs[nxt], srate, call_len)
+                c = _capacity_frames(programs[i], srate, call_len)
                 b = np.empty(c * ch, np.int16)
-                idx.append(nxt); gens.append(g); bufs.append(b)
-                nxt += 1
-            k0 = len(gptr)
+                idx.append(i); gens.append(g); bufs.append(b)
             gptr = np.concatenate([gptr, np.array([g.ptr for g in gens[k0:]], np.uint64)])
             base = np.concatenate([base, np.array([b.ctypes.data for b in bufs[k0:]], np.uint64)])
             pos = np.concatenate([pos, np.zeros(len(gens) - k0, np.int64)])
             cap = np.concatenate([cap, np.array([b.size // ch for b in bufs[k0:]], np.int64)])
         m = len(gens)
+        if m == 0:
+            break
         for k in np.nonzero(pos + call_len > cap)[0]:      # rare: longer than announced
             bufs[k] = np.concatenate([bufs[k], np.empty(4 * call_len * ch, np.int16)])
             base[k] = bufs[k].ctypes.data
@@ -86,7 +127,6 @@ def render_batch(programs, srate=96000, device=0, call_len=None, tables=None, gr
             idx = [idx[k] for k in keep]; gens = [gens[k] for k in keep]; bufs = [bufs[k] for k in keep]
             kk = np.array(keep, np.int64)
             gptr, base, pos, cap = gptr[kk], base[kk], pos[kk], cap[kk]
-    return out
 
 
 def wav_bytes(pcm, srate):

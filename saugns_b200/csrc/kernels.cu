@@ -34,9 +34,15 @@ namespace saugen {
 constexpr int FAST_NS = 4;            // samples per lane in the steady-block fast path (8 measured
                                       // slower: its registers allow 16 resident warps per SM, 4 allows 32)
 constexpr uint32_t BUF_FLOATS = 32 * (FAST_NS > SPL ? FAST_NS : SPL);   // per work buffer
-__host__ __device__ inline uint32_t warp_smem_bytes(uint32_t nbufs, uint32_t nslots) {
+/* The len stacks (general interpreter, live inside one chunk only) and the block
+ * plan (fast path, live across one steady block, 32 bytes per record) share one
+ * area: whichever is larger. */
+constexpr int WIDE_WARPS = 28;        // most warps of a render_kernel_wide CTA: 72 registers each
+constexpr uint32_t STACK_BYTES = 3 * MAX_NEST * (uint32_t) sizeof(uint32_t);
+__host__ __device__ inline uint32_t warp_smem_bytes(uint32_t nbufs, uint32_t nslots, uint32_t nplan) {
+	const uint32_t plan_bytes = nplan * 32u;
 	return nslots * (uint32_t) sizeof(OpState) + nbufs * BUF_FLOATS * (uint32_t) sizeof(float) +
-		3 * MAX_NEST * (uint32_t) sizeof(uint32_t);
+		(plan_bytes > STACK_BYTES ? plan_bytes : STACK_BYTES);
 }
 
 /* ---- TMA 1-D bulk copy + mbarrier (PTX) --------------------------------- */
@@ -1489,8 +1495,44 @@ __device__ __forceinline__ bool op_outlasts_block(const OpState *o) {
 	return (o->flags & ON_TIME_INF) || o->time >= (uint32_t) REF_BLOCK;
 }
 
-__device__ __noinline__ bool steady_check(OpState *sops, const Instr *code, uint32_t code_len) {
+/* ---- block plan ---------------------------------------------------------- *
+ * steady_plan() proves the block steady and, while it walks the bytecode, writes
+ * the block's PLAN into the warp's shared memory: one 32-byte record per
+ * instruction that does something per chunk (ENTER / VPAN / END and skipped
+ * lines drop out), with everything that is fixed for the block resolved: the
+ * operator's shared address, its table, its differentiator constants, whether
+ * its amplitude holds one value, and whether its FREQUENCY is one value over
+ * the block (a line without a goal, times a parent frequency that is itself
+ * uniform).  A uniform frequency f makes sauPhasor_fill (wosc.h:135-169) a
+ * closed form: every sample adds the same inc = lrintf(coeff * f), so sample i
+ * of the chunk is at phase0 + (i + 1) * inc in wrap-around uint32 arithmetic --
+ * bit-identical to the serial accumulation, without conversions or a scan. */
+enum : uint32_t { P_LINE = 1, P_WHEAD, P_WTAIL, P_WLEAF, P_RANGE, P_VOUT };
+enum : uint32_t {
+	PF_LAYER = 1, PF_WAVEENV = 2,
+	PF_FUNI = 4,       /* frequency (or the LINE's value) is uniform over the block */
+	PF_FMUL = 8,       /* ... and is v0 times the (uniform) multiplier buffer */
+	PF_ACONST = 16,    /* amplitude line holds av */
+};
+constexpr uint32_t PLAN_REC = 32;     /* bytes: w0 kind|flags<<8|a<<16|b<<24, w1 c|e<<8|line<<16,
+                                       * w2 operator state (shared address), w3 table (shared address),
+                                       * w4 diff_scale, w5 diff_offset, w6 v0 of the frequency / LINE, w7 av */
+
+__device__ __forceinline__ void plan_put(uint32_t plan, uint32_t n, uint32_t w0, uint32_t w1, uint32_t w2,
+		uint32_t w3, float w4, float w5, float w6, float w7) {
+	const uint32_t a = plan + n * PLAN_REC;
+	asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(a), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
+	sts128(a + 16, make_float4(w4, w5, w6, w7));
+}
+
+/* returns the number of plan records; 0 = not a steady block (or no room) */
+__device__ __noinline__ uint32_t steady_plan(OpState *sops, uint32_t so, uint32_t st, uint32_t wave_mask,
+		const WaveCoeffs *wc, const Instr *code, uint32_t code_len, uint32_t plan, uint32_t cap) {
 	uint32_t seen = 0;         /* operator slots already visited (< 32 of them) */
+	uint32_t uni = 0;          /* work buffers (< 32) holding one value over the block */
+	uint32_t n = 0;
+	plan += PLAN_REC;          /* slot 0 is the header (render_units) */
+	if (cap) --cap;
 	uint4 raw_next = __ldg(reinterpret_cast<const uint4*>(code));
 	for (uint32_t pc = 0; pc < code_len; ++pc) {
 		const uint4 raw = raw_next;
@@ -1498,43 +1540,86 @@ __device__ __noinline__ bool steady_check(OpState *sops, const Instr *code, uint
 		Instr in;
 		memcpy(&in, &raw, sizeof(in));
 		const OpState *o = sops + in.op;
+		const uint32_t opa = so + in.op * (uint32_t) sizeof(OpState);
 		bool head = false, tail = false;
+		if (n >= cap) return 0;
 		switch (in.opcode) {
 		case I_WLEAF: head = tail = true; break;
 		case I_WHEAD: head = true; break;
 		case I_WTAIL: tail = true; break;
 		case I_ENTER:
-			if (o->type != SAUABI_POPT_wave || !op_outlasts_block(o)) return false;
-			if (in.op >= 32 || (seen & (1u << in.op))) return false;
+			if (o->type != SAUABI_POPT_wave || !op_outlasts_block(o)) return 0;
+			if (in.op >= 32 || (seen & (1u << in.op))) return 0;
 			seen |= 1u << in.op;
 			break;
 		case I_LINE:
-			if (in.d && !line_steady(o, in.c)) return false;
+			if (in.d) {
+				if (!line_steady(o, in.c)) return 0;
+				const uint32_t lf = LM_FLAGS(o->lmeta[in.c]);
+				const bool ratio = in.b != NO_BUF && (lf & SAUABI_LINEP_STATE_RATIO);
+				const bool u = !(lf & SAUABI_LINEP_GOAL) && (!ratio || (in.b < 32 && ((uni >> in.b) & 1u)));
+				plan_put(plan, n++, P_LINE | ((u ? PF_FUNI : 0u) | (u && ratio ? PF_FMUL : 0u)) << 8 |
+						(uint32_t) in.a << 16 | (uint32_t) in.b << 24, (uint32_t) in.c << 16, opa, 0u,
+						0.f, 0.f, o->line[in.c].v0, 0.f);
+				if (in.a < 32) uni = u ? uni | (1u << in.a) : uni & ~(1u << in.a);
+			}
 			break;
-		case I_RANGE: case I_VOUT: case I_END:
+		case I_RANGE:
+			plan_put(plan, n++, P_RANGE | (uint32_t) in.a << 16 | (uint32_t) in.b << 24, in.c, 0u, 0u,
+					0.f, 0.f, 0.f, 0.f);
+			if (in.a < 32) uni &= ~(1u << in.a);
 			break;
+		case I_VOUT:
+			plan_put(plan, n++, P_VOUT | (uint32_t) in.a << 16 | (uint32_t) in.b << 24, 0u, opa, 0u,
+					0.f, 0.f, 0.f, 0.f);
+			return n;
+		case I_END:
+			return n;
 		case I_VPAN:
-			if (in.d || (LM_FLAGS(o->lmeta[LINE_PAN]) & SAUABI_LINEP_GOAL)) return false;
+			if (in.d || (LM_FLAGS(o->lmeta[LINE_PAN]) & SAUABI_LINEP_GOAL)) return 0;
 			break;
 		default:
-			return false;
+			return 0;
 		}
+		bool funi = false, fmul = false;
 		if (head) {
-			if (in.op >= 32 || (seen & (1u << in.op))) return false;
+			if (in.op >= 32 || (seen & (1u << in.op))) return 0;
 			seen |= 1u << in.op;
-			if (!op_outlasts_block(o) || !line_steady(o, LINE_FREQ)) return false;
-		}
-		if (tail) {
-			if (in.d != NO_BUF) return false;                       /* fPM: general path */
-			if (!op_outlasts_block(o) || !line_steady(o, LINE_AMP)) return false;
-			if (o->oscflags & OSC_RESET_DIFF) return false;
-			if (in.flags & F_MAY_SELFMOD) {                          /* generator.c:485-490 */
-				if (o->line[LINE_PMA].v0 != 0.f ||
-						(LM_FLAGS(o->lmeta[LINE_PMA]) & SAUABI_LINEP_GOAL)) return false;
+			if (!op_outlasts_block(o) || !line_steady(o, LINE_FREQ)) return 0;
+			const uint32_t lf = LM_FLAGS(o->lmeta[LINE_FREQ]);
+			fmul = in.e != NO_BUF && (lf & SAUABI_LINEP_STATE_RATIO);
+			funi = !(lf & SAUABI_LINEP_GOAL) && (!fmul || (in.e < 32 && ((uni >> in.e) & 1u)));
+			if (!funi) fmul = false;
+			if (!tail) {
+				plan_put(plan, n++, P_WHEAD | ((funi ? PF_FUNI : 0u) | (fmul ? PF_FMUL : 0u)) << 8 |
+						(uint32_t) in.b << 24, (uint32_t) in.e << 8, opa, 0u,
+						0.f, 0.f, o->line[LINE_FREQ].v0, 0.f);
+				if (in.b < 32) uni = funi ? uni | (1u << in.b) : uni & ~(1u << in.b);
 			}
 		}
+		if (tail) {
+			if (in.d != NO_BUF) return 0;                           /* fPM: general path */
+			if (!op_outlasts_block(o) || !line_steady(o, LINE_AMP)) return 0;
+			if (o->oscflags & OSC_RESET_DIFF) return 0;
+			if (in.flags & F_MAY_SELFMOD) {                          /* generator.c:485-490 */
+				if (o->line[LINE_PMA].v0 != 0.f ||
+						(LM_FLAGS(o->lmeta[LINE_PMA]) & SAUABI_LINEP_GOAL)) return 0;
+			}
+			if (!head) funi = in.b < 32 && ((uni >> in.b) & 1u);
+			const uint32_t wave = o->mode;
+			const uint32_t slot = __popc(wave_mask & ((1u << wave) - 1u));
+			const uint32_t ct = (wave_mask & CTAB_FLAG) ? st + slot * CTAB_WAVE_BYTES :
+				st + slot * (TAB_STRIDE * 4) + 12;                   /* planes, or &lut[-1] */
+			const bool aconst = !(LM_FLAGS(o->lmeta[LINE_AMP]) & SAUABI_LINEP_GOAL);
+			const uint32_t fl = ((in.flags & F_LAYER) ? PF_LAYER : 0u) | ((in.flags & F_WAVEENV) ? PF_WAVEENV : 0u) |
+				(funi ? PF_FUNI : 0u) | (fmul ? PF_FMUL : 0u) | (aconst ? PF_ACONST : 0u);
+			plan_put(plan, n++, (head ? P_WLEAF : P_WTAIL) | fl << 8 | (uint32_t) in.a << 16 | (uint32_t) in.b << 24,
+					(uint32_t) in.c | (uint32_t) in.e << 8, opa, ct,
+					wc->diff_scale[wave], wc->diff_offset[wave], o->line[LINE_FREQ].v0, o->line[LINE_AMP].v0);
+			if (in.a < 32) uni &= ~(1u << in.a);
+		}
 	}
-	return true;
+	return n;
 }
 
 /* sauLine_run's bookkeeping for one whole block of a steady run line */
@@ -1652,11 +1737,23 @@ struct FastCtx {               /* all registers */
 	int lane;
 	float coeff, amp_scale;
 	uint32_t write_r;          // as Ctx::write_r
+	uint32_t plan, plan_cap;   // shared addr of the block plan, records it can hold
 	const WaveCoeffs *wc;
 	const float *tab;          // generic pointer to the staged tables (rare paths)
 };
+/* What the chunk loop of a steady block keeps in registers; everything else it
+ * needs is in the block plan (shared memory): header at c.plan, records after it. */
+struct HotCtx {
+	uint32_t sb;               // as FastCtx::sb
+	uint32_t plan;             // shared addr of the plan header
+	uint32_t oc;               // chunk offset inside the block
+	int lane;
+	float coeff;
+};
+/* plan header (the first 32-byte slot): the cold paths' context and VOUT's constants */
+constexpr uint32_t PH_TAB = 0, PH_WC = 8, PH_WAVE_MASK = 16, PH_AMP_SCALE = 20, PH_WRITE_R = 24;
 template <int NS>
-__device__ __forceinline__ void fld(const FastCtx &c, uint32_t buf, float v[NS]) {
+__device__ __forceinline__ void fld(const HotCtx &c, uint32_t buf, float v[NS]) {
 	const uint32_t a = c.sb + buf * FastCfg<NS>::FBUF_BYTES;
 #pragma unroll
 	for (int h = 0; h < NS / 4; ++h) {
@@ -1665,7 +1762,7 @@ __device__ __forceinline__ void fld(const FastCtx &c, uint32_t buf, float v[NS])
 	}
 }
 template <int NS>
-__device__ __forceinline__ void fst(const FastCtx &c, uint32_t buf, const float v[NS]) {
+__device__ __forceinline__ void fst(const HotCtx &c, uint32_t buf, const float v[NS]) {
 	const uint32_t a = c.sb + buf * FastCfg<NS>::FBUF_BYTES;
 #pragma unroll
 	for (int h = 0; h < NS / 4; ++h)
@@ -1681,7 +1778,7 @@ static_assert(offsetof(OpState, lmeta) == OS_LMETA && offsetof(OpState, linv) ==
 
 /* value of a steady run line for this lane's samples of the chunk at c.oc */
 template <int NS>
-__device__ __forceinline__ void line_value_steady(const FastCtx &c, uint32_t op, int li,
+__device__ __forceinline__ void line_value_steady(const HotCtx &c, uint32_t op, int li,
 		const float *m /* NS multipliers or nullptr */, float out[NS]) {
 	const uint4 core = lds128u(op + OS_LINE + 16 * li);          /* v0, vt, pos, end */
 	const uint32_t meta = lds32(op + OS_LMETA + 4 * li);
@@ -1786,18 +1883,38 @@ __device__ __noinline__ SampVec<NS> wosc_zero_diff(const ColdCtx c, OpState *o, 
 	return sv;
 }
 
+/* the phase fraction as a double, (double) ((float) frac * 2^-21) of sauWave_get_herp
+ * (wave.h:131-133; both steps are exact, frac < 2^21): frac dropped into the low
+ * mantissa bits of 2^31, whose unit in the last place is 2^-21, minus 2^31 --
+ * one FP64 add instead of I2F + FMUL + F2F on the quarter-rate conversion pipe */
+__device__ __forceinline__ double phase_frac(uint32_t phase) {
+	return __hiloint2double(0x41E00000, (int) (phase & sau::WAVE_SLENMASK)) - 2147483648.0;
+}
+__device__ __forceinline__ double horner_frac(double c3, double c2, double c1, uint32_t phase) {
+	const double x = phase_frac(phase);
+	return ((c3 * x + c2) * x + c1) * x;
+}
+
 /* TAIL of a wave operator on a steady full chunk: phase fill, oscillator,
- * amplitude line, block_mix (generator.c:584-601); fr = its frequency values */
+ * amplitude line, block_mix (generator.c:584-601).  funi: every sample adds
+ * `inc` to the phase (see steady_plan); else fr = its frequency values. */
 template <int NS, bool CTAB>
-__device__ __forceinline__ void wtail_fast(const FastCtx &c, const Instr &in, uint32_t op,
-		const float fr[NS]) {
-	const uint4 og = lds128u(op + OS_TIME);      /* time, type|flags|mode|oscflags, i0, i1 */
-	const uint4 pg = lds128u(op + OS_PREV);      /* prev_Is lo/hi, prev_s, fb_s */
-	const uint32_t wave = (og.y >> 16) & 0xffu;
+__device__ __forceinline__ void wtail_plan(const HotCtx &c, const uint4 p0, const uint32_t rec,
+		const bool funi, const uint32_t inc, const float fr[NS]) {
+	const uint32_t flags = (p0.x >> 8) & 0xffu, bufa = (p0.x >> 16) & 0xffu, bufc = p0.y & 0xffu;
+	const uint32_t op = p0.z;
+	uint2 og, pg;                                /* i0, i1 (phase, prev_phase); prev_Is lo / hi */
+	asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(og.x), "=r"(og.y) : "r"(op + OS_I0));
+	asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(pg.x), "=r"(pg.y) : "r"(op + OS_PREV));
 	__syncwarp();              /* every lane holds the accumulators before lane 31 rewrites them */
 	/* sauPhasor_fill, wosc.h:135-169 */
 	uint32_t ph[NS];
-	{
+	if (funi) {
+		const uint32_t base = og.x + inc * (uint32_t) (c.lane * NS);
+#pragma unroll
+		for (int k = 0; k < NS; ++k) ph[k] = base + inc * (uint32_t) (k + 1);
+		if (c.lane == 31) sts32(op + OS_I0, ph[NS - 1]);
+	} else {
 		uint32_t run = 0;
 #pragma unroll
 		for (int k = 0; k < NS; ++k) {
@@ -1805,45 +1922,45 @@ __device__ __forceinline__ void wtail_fast(const FastCtx &c, const Instr &in, ui
 			ph[k] = run;
 		}
 		const uint32_t incl = scan_incl_u32(run, c.lane);
-		const uint32_t base = og.z + (incl - run);
+		const uint32_t base = og.x + (incl - run);
 #pragma unroll
 		for (int k = 0; k < NS; ++k) ph[k] += base;
-		if (c.lane == 31) sts32(op + OS_I0, og.z + incl);
-		if (in.c != NO_BUF) {              /* PM; fPM operators take the general path (steady_check) */
-			float pm[NS];
-			fld<NS>(c, in.c, pm);
+		if (c.lane == 31) sts32(op + OS_I0, og.x + incl);
+	}
+	const bool pm_in = bufc != NO_BUF;       /* PM; fPM operators take the general path (steady_plan) */
+	if (pm_in) {
+		float pm[NS];
+		fld<NS>(c, bufc, pm);
 #pragma unroll
-			for (int k = 0; k < NS; ++k) ph[k] += ftoi_lo32(pm[k] * 2147483648.f);
-		}
+		for (int k = 0; k < NS; ++k) ph[k] += ftoi_lo32(pm[k] * 2147483648.f);
 	}
 	/* sauWOsc_run, wosc.h:238-266 */
 	float s[NS];
 	{
-		const uint32_t slot = __popc(c.wave_mask & ((1u << wave) - 1u));
 		double Is[NS];
 		if (CTAB) {
-			/* per-index coefficients from shared memory: two 128-bit loads, Horner */
-			const uint32_t ct = c.st + slot * CTAB_WAVE_BYTES;
+			/* per-index coefficients from shared memory: two loads, Horner */
 #pragma unroll
 			for (int k = 0; k < NS; ++k) {
 				const uint32_t ind = ph[k] >> sau::WAVE_SLENBITS;
-				const double2 hi = lds128d(ct + (ind << 4));
-				const float2 lo = lds64f(ct + CTAB_PLANE_BYTES + (ind << 3));
-				Is[k] = sau::herp_horner(hi.x, hi.y, (double) lo.x, ph[k]) + (double) lo.y;
+				const double2 hi = lds128d(p0.w + (ind << 4));
+				const float2 lo = lds64f(p0.w + CTAB_PLANE_BYTES + (ind << 3));
+				Is[k] = horner_frac(hi.x, hi.y, (double) lo.x, ph[k]) + (double) lo.y;
 			}
 		} else {
-			const uint32_t taps = c.st + slot * (TAB_STRIDE * 4) + 12;    /* &lut[-1] */
 #pragma unroll
 			for (int k = 0; k < NS; ++k) {
-				const uint32_t a = taps + ((ph[k] >> sau::WAVE_SLENBITS) << 2);
+				const uint32_t a = p0.w + ((ph[k] >> sau::WAVE_SLENBITS) << 2);
 				const float s0 = lds32f(a), s1 = lds32f(a + 4), s2 = lds32f(a + 8), s3 = lds32f(a + 12);
-				Is[k] = sau::herp_poly(s0, s1, s2, s3, ph[k]) + (double) s1;
+				double c1, c2, c3;
+				sau::herp_coefs(s0, s1, s2, s3, &c1, &c2, &c3);
+				Is[k] = horner_frac(c3, c2, c1, ph[k]) + (double) s1;
 			}
 		}
 		uint32_t pph = __shfl_up_sync(FULL, ph[NS - 1], 1);
 		double pIs = __shfl_up_sync(FULL, Is[NS - 1], 1);
 		if (c.lane == 0) {
-			pph = og.w;
+			pph = og.y;
 			pIs = __hiloint2double((int) pg.y, (int) pg.x);
 		}
 		int32_t d[NS];
@@ -1854,7 +1971,11 @@ __device__ __forceinline__ void wtail_fast(const FastCtx &c, const Instr &in, ui
 #pragma unroll
 		for (int k = 0; k < NS; ++k) z |= (d[k] == 0);
 		if (__any_sync(FULL, z)) {
-			ColdCtx cc; cc.tab = c.tab; cc.wc = c.wc; cc.wave_mask = c.wave_mask; cc.lane = c.lane;
+			const uint4 h = lds128u(c.plan);
+			ColdCtx cc;
+			cc.tab = reinterpret_cast<const float*>((uint64_t) h.x | ((uint64_t) h.y << 32));
+			cc.wc = reinterpret_cast<const WaveCoeffs*>((uint64_t) h.z | ((uint64_t) h.w << 32));
+			cc.wave_mask = lds32(c.plan + PH_WAVE_MASK); cc.lane = c.lane;
 			PhaseVec<NS> pv;
 #pragma unroll
 			for (int k = 0; k < NS; ++k) pv.v[k] = ph[k];
@@ -1863,27 +1984,48 @@ __device__ __forceinline__ void wtail_fast(const FastCtx &c, const Instr &in, ui
 #pragma unroll
 			for (int k = 0; k < NS; ++k) s[k] = sv.v[k];
 		} else {
-			const float ds = c.wc->diff_scale[wave];
-			const double doff = (double) c.wc->diff_offset[wave];
+			const float2 dd = lds64f(rec + 16);
+			const float ds = dd.x;
+			const double doff = (double) dd.y;
+			if (funi && !pm_in) {
+				/* a pure tone: every phase difference is inc, one division per lane
+				 * (lane 0's first sample follows the carried phase, which an event
+				 * may have moved) */
+				const float xq = div_scale_by_int(ds, (int32_t) inc);
+				const double xqd = (double) xq;
+				double xq0 = xqd;
+				if (d[0] != (int32_t) inc) xq0 = (double) div_scale_by_int(ds, d[0]);
+				s[0] = (float) ((Is[0] - pIs) * xq0 + doff);
 #pragma unroll
-			for (int k = 0; k < NS; ++k) {                           /* wosc.h:254-256 */
-				const float xq = div_scale_by_int(ds, d[k]);
-				const double dI = Is[k] - (k ? Is[k - 1] : pIs);
-				s[k] = (float) (dI * (double) xq + doff);
+				for (int k = 1; k < NS; ++k) s[k] = (float) ((Is[k] - Is[k - 1]) * xqd + doff);
+			} else {
+#pragma unroll
+				for (int k = 0; k < NS; ++k) {                           /* wosc.h:254-256 */
+					const float xq = div_scale_by_int(ds, d[k]);
+					const double dI = Is[k] - (k ? Is[k - 1] : pIs);
+					s[k] = (float) (dI * (double) xq + doff);
+				}
 			}
 			if (c.lane == 31) {
 				sts32(op + OS_I1, ph[NS - 1]);
-				sts128(op + OS_PREV, make_float4(__int_as_float(__double2loint(Is[NS - 1])),
-						__int_as_float(__double2hiint(Is[NS - 1])), s[NS - 1], __uint_as_float(pg.w)));
+				asm volatile("st.shared.v2.u32 [%0], {%1, %2};" :: "r"(op + OS_PREV),
+						"r"((uint32_t) __double2loint(Is[NS - 1])), "r"((uint32_t) __double2hiint(Is[NS - 1])) : "memory");
+				sts32(op + OS_PREV + 8, __float_as_uint(s[NS - 1]));
 			}
 		}
 	}
 	float am[NS];
-	line_value_steady<NS>(c, op, LINE_AMP, nullptr, am);
-	const bool layer = (in.flags & F_LAYER) != 0;      /* F_LAYER_PMA: no self-PM here */
+	if (flags & PF_ACONST) {
+		const float av = lds32f(rec + 28);
+#pragma unroll
+		for (int k = 0; k < NS; ++k) am[k] = av;
+	} else {
+		line_value_steady<NS>(c, op, LINE_AMP, nullptr, am);
+	}
+	const bool layer = (flags & PF_LAYER) != 0;        /* F_LAYER_PMA: no self-PM here */
 	float ov[NS];
-	if (layer) fld<NS>(c, in.a, ov);
-	if (in.flags & F_WAVEENV) {                                   /* generator.c:407-426 */
+	if (layer) fld<NS>(c, bufa, ov);
+	if (flags & PF_WAVEENV) {                                     /* generator.c:407-426 */
 #pragma unroll
 		for (int k = 0; k < NS; ++k) {
 			const float s_amp = am[k] * 0.5f;
@@ -1897,7 +2039,7 @@ __device__ __forceinline__ void wtail_fast(const FastCtx &c, const Instr &in, ui
 			ov[k] = layer ? ov[k] + v : v;
 		}
 	}
-	fst<NS>(c, in.a, ov);
+	fst<NS>(c, bufa, ov);
 	__syncwarp();
 }
 
@@ -1913,74 +2055,82 @@ __device__ __noinline__ void vout_unaligned(uint32_t sbuf_s, uint32_t sbuf_r, fl
 }
 
 template <int NS, bool CTAB>
-__device__ __forceinline__ void run_chunk_fast(const FastCtx &c, const Instr *code,
-		uint32_t code_len, float *row_s, float *row_r) {
-	/* the next instruction is fetched while the current one runs */
-	uint4 raw_next = __ldg(reinterpret_cast<const uint4*>(code));
-	for (uint32_t pc = 0; pc < code_len; ++pc) {
-		const uint4 raw = raw_next;
-		if (pc + 1 < code_len) raw_next = __ldg(reinterpret_cast<const uint4*>(code + pc + 1));
-		Instr in;
-		memcpy(&in, &raw, sizeof(in));
-		const uint32_t op = c.so + in.op * (uint32_t) sizeof(OpState);
-		switch (in.opcode) {
-		case I_WLEAF: case I_WHEAD: case I_WTAIL: case I_LINE: {
-			/* one line evaluation (frequency, or the LINE's own), then the tail */
-			const bool is_line = in.opcode == I_LINE;
-			if (is_line && !in.d) break;
+__device__ __forceinline__ void run_chunk_plan(const HotCtx &c, const uint32_t nrec,
+		float *row_s, float *row_r) {
+	uint32_t rec = c.plan;
+	for (uint32_t r = 0; r < nrec; ++r) {
+		rec += PLAN_REC;
+		const uint4 p0 = lds128u(rec);
+		const uint32_t kind = p0.x & 0xffu, flags = (p0.x >> 8) & 0xffu;
+		const uint32_t bufa = (p0.x >> 16) & 0xffu, bufb = p0.x >> 24;
+		const uint32_t op = p0.z;
+		if (kind <= P_WLEAF) {
+			/* LINE / WHEAD: one line evaluation into a buffer; WLEAF: the same, kept in
+			 * registers, then the tail; WTAIL: the frequency comes from its buffer */
+			const bool is_line = kind == P_LINE;
+			const bool funi = (flags & PF_FUNI) != 0;
 			float fr[NS];
-			if (in.opcode == I_WTAIL) {
-				fld<NS>(c, in.b, fr);
+			uint32_t inc = 0;
+			if (kind == P_WTAIL) {
+				if (funi) inc = ftoi_lo32(c.coeff * lds32f(c.sb + bufb * FastCfg<NS>::FBUF_BYTES));
+				else fld<NS>(c, bufb, fr);
 			} else {
-				float m[NS];
-				const uint32_t mb = is_line ? in.b : in.e;
-				const bool has_mul = mb != NO_BUF;
-				if (has_mul) fld<NS>(c, mb, m);
-				line_value_steady<NS>(c, op, is_line ? (int) in.c : (int) LINE_FREQ,
-						has_mul ? m : nullptr, fr);
-				if (is_line) { fst<NS>(c, in.a, fr); break; }
-				if (in.opcode == I_WHEAD) { fst<NS>(c, in.b, fr); break; }
+				const uint32_t mb = is_line ? bufb : (p0.y >> 8) & 0xffu;
+				if (funi) {
+					float f = lds32f(rec + 24);
+					if (flags & PF_FMUL) f = f * lds32f(c.sb + mb * FastCfg<NS>::FBUF_BYTES);
+					inc = ftoi_lo32(c.coeff * f);
+#pragma unroll
+					for (int k = 0; k < NS; ++k) fr[k] = f;
+				} else {
+					float m[NS];
+					const bool has_mul = mb != NO_BUF;
+					if (has_mul) fld<NS>(c, mb, m);
+					line_value_steady<NS>(c, op, is_line ? (int) ((p0.y >> 16) & 0xffu) : (int) LINE_FREQ,
+							has_mul ? m : nullptr, fr);
+				}
+				if (kind != P_WLEAF) { fst<NS>(c, is_line ? bufa : bufb, fr); continue; }
 			}
-			wtail_fast<NS, CTAB>(c, in, op, fr);
-			break; }
-		case I_RANGE: {                                            /* generator.c:465-467 */
-			float p[NS], r[NS], m[NS];
-			fld<NS>(c, in.a, p); fld<NS>(c, in.b, r); fld<NS>(c, in.c, m);
+			wtail_plan<NS, CTAB>(c, p0, rec, funi, inc, fr);
+		} else if (kind == P_RANGE) {                              /* generator.c:465-467 */
+			float p[NS], rr[NS], m[NS];
+			fld<NS>(c, bufa, p); fld<NS>(c, bufb, rr); fld<NS>(c, p0.y & 0xffu, m);
 #pragma unroll
-			for (int k = 0; k < NS; ++k) p[k] += (r[k] - p[k]) * m[k];
-			fst<NS>(c, in.a, p);
-			break; }
-		case I_VOUT: {                                             /* generator.c:772-786 */
+			for (int k = 0; k < NS; ++k) p[k] += (rr[k] - p[k]) * m[k];
+			fst<NS>(c, bufa, p);
+		} else {                                                   /* P_VOUT, generator.c:772-786 */
 			float sv[NS];
-			fld<NS>(c, in.a, sv);
+			fld<NS>(c, bufa, sv);
 			const float pan = lds32f(op + OS_LINE + 16 * LINE_PAN);
-			float s[NS], r[NS];
+			float s[NS], rv[NS];
 #pragma unroll
-			for (int k = 0; k < NS; ++k) { s[k] = sv[k] * c.amp_scale; r[k] = s[k] * pan; }
+			const float amp_scale = lds32f(c.plan + PH_AMP_SCALE);
+			const uint32_t write_r = lds32(c.plan + PH_WRITE_R);
+#pragma unroll
+			for (int k = 0; k < NS; ++k) { s[k] = sv[k] * amp_scale; rv[k] = s[k] * pan; }
 			const uint32_t i0 = c.lane * NS;
 			if ((reinterpret_cast<uintptr_t>(row_s) & 15) == 0) {
 #pragma unroll
 				for (int h = 0; h < NS / 4; ++h)                     /* 128-bit streaming stores */
 					__stcs(reinterpret_cast<float4*>(row_s + i0) + h,
 							make_float4(s[4 * h], s[4 * h + 1], s[4 * h + 2], s[4 * h + 3]));
-				if (c.write_r) {
+				if (write_r) {
 #pragma unroll
 					for (int h = 0; h < NS / 4; ++h)
 						__stcs(reinterpret_cast<float4*>(row_r + i0) + h,
-								make_float4(r[4 * h], r[4 * h + 1], r[4 * h + 2], r[4 * h + 3]));
+								make_float4(rv[4 * h], rv[4 * h + 1], rv[4 * h + 2], rv[4 * h + 3]));
 				}
 			} else {
 				/* segment starting at an odd frame: rare, out of line through the buffers */
-				fst<NS>(c, in.a, s);
-				fst<NS>(c, in.b != NO_BUF ? in.b : in.a + 1u, r);
+				const uint32_t rb = bufb != NO_BUF ? bufb : bufa + 1u;
+				fst<NS>(c, bufa, s);
+				fst<NS>(c, rb, rv);
 				__syncwarp();
-				vout_unaligned(c.sb - c.lane * 16 + in.a * FastCfg<NS>::FBUF_BYTES,
-						c.sb - c.lane * 16 + (in.b != NO_BUF ? in.b : in.a + 1u) * FastCfg<NS>::FBUF_BYTES,
-						row_s, row_r, c.lane, NS, c.write_r);
+				vout_unaligned(c.sb - c.lane * 16 + bufa * FastCfg<NS>::FBUF_BYTES,
+						c.sb - c.lane * 16 + rb * FastCfg<NS>::FBUF_BYTES,
+						row_s, row_r, c.lane, NS, write_r);
 			}
-			return; }
-		default:                   /* ENTER, VPAN, END: nothing to do per chunk */
-			break;
+			return;
 		}
 	}
 }
@@ -1988,11 +2138,13 @@ __device__ __forceinline__ void run_chunk_fast(const FastCtx &c, const Instr *co
 /* One steady reference block: its own function, so that the hot loop gets its
  * own register allocation whatever the general path around the call needs. */
 template <bool CTAB>
-__device__ __noinline__ void run_block_fast(FastCtx fc, const Instr *code, uint32_t code_len,
+__device__ __noinline__ void run_block_fast(uint32_t sb, uint32_t plan, int lane, float coeff, uint32_t nrec,
 		float *row_s, float *row_r) {
+	HotCtx c;
+	c.sb = sb; c.plan = plan; c.lane = lane; c.coeff = coeff;
 	for (uint32_t oc = 0; oc < (uint32_t) REF_BLOCK; oc += FastCfg<FAST_NS>::CHUNKF) {
-		fc.oc = oc;
-		run_chunk_fast<FAST_NS, CTAB>(fc, code, code_len, row_s + oc, row_r + oc);
+		c.oc = oc;
+		run_chunk_plan<FAST_NS, CTAB>(c, nrec, row_s + oc, row_r + oc);
 	}
 }
 
@@ -2090,17 +2242,26 @@ __device__ __noinline__ void render_units(Ctx &c, FastCtx &fc, const CallDesc *c
 		const uint32_t uend = ud.off + ud.len;
 		for (uint32_t off = ud.off; off < uend && vs.duration != 0; off += CHUNK) {
 			/* a whole reference block in steady state: the fast path */
+			uint32_t nrec;
 			if (off % REF_BLOCK == 0 && uend - off >= (uint32_t) REF_BLOCK &&
 					vs.duration >= (uint32_t) REF_BLOCK && vs.code_len &&
 					op_ptr(c, vs.carr_slot)->time > 0 &&
-					steady_check(c.sops, g->code + vs.code_off, vs.code_len)) {
+					(nrec = steady_plan(c.sops, fc.so, fc.st, fc.wave_mask, fc.wc, g->code + vs.code_off,
+							vs.code_len, fc.plan, fc.plan_cap)) != 0) {
 				if (pan_mode == PAN_UNSET)       /* steady => the pan stands still */
 					pan_mode = __float_as_uint(op_ptr(c, vs.carr_slot)->line[LINE_PAN].v0);
+				{
+					/* plan header: what the rare paths and VOUT need */
+					const uint64_t tp = reinterpret_cast<uint64_t>(fc.tab), wp = reinterpret_cast<uint64_t>(fc.wc);
+					plan_put(fc.plan, 0, (uint32_t) tp, (uint32_t) (tp >> 32), (uint32_t) wp, (uint32_t) (wp >> 32),
+							__uint_as_float(fc.wave_mask), fc.amp_scale, __uint_as_float(fc.write_r), 0.f);
+					__syncwarp();
+				}
 				if (fc.wave_mask & CTAB_FLAG)
-					run_block_fast<true>(fc, g->code + vs.code_off, vs.code_len,
+					run_block_fast<true>(fc.sb, fc.plan, lane, fc.coeff, nrec,
 							row_s + sd.start + off, row_r + sd.start + off);
 				else
-					run_block_fast<false>(fc, g->code + vs.code_off, vs.code_len,
+					run_block_fast<false>(fc.sb, fc.plan, lane, fc.coeff, nrec,
 							row_s + sd.start + off, row_r + sd.start + off);
 				__syncwarp();
 				if (lane == 0) steady_update(c.sops, g->code + vs.code_off, vs.code_len);
@@ -2153,7 +2314,7 @@ __device__ __noinline__ void render_units(Ctx &c, FastCtx &fc, const CallDesc *c
 
 __device__ __forceinline__ void render_body(const CallDesc *calls, uint32_t ncalls,
 		const SegDesc *segs, const UnitDesc *units, uint32_t ntasks, const float *tables,
-		const double *coefs, uint32_t wave_mask, uint32_t nbufs, uint32_t nslots_ops, uint32_t warps_per_cta,
+		const double *coefs, uint32_t wave_mask, uint32_t nbufs, uint32_t nslots_ops, uint32_t nplan, uint32_t warps_per_cta,
 		uint32_t ticketed) {
 	extern __shared__ __align__(128) unsigned char smem[];
 	uint64_t *bar = reinterpret_cast<uint64_t*>(smem);
@@ -2162,7 +2323,7 @@ __device__ __forceinline__ void render_body(const CallDesc *calls, uint32_t ncal
 	const uint32_t nslots = __popc(wave_mask & ~CTAB_FLAG);
 	const uint32_t slot_bytes = ctab ? CTAB_WAVE_BYTES : TAB_STRIDE * (uint32_t) sizeof(float);
 	unsigned char *warp_area = smem + 128 + nslots * slot_bytes;
-	const uint32_t per_warp = warp_smem_bytes(nbufs, nslots_ops);
+	const uint32_t per_warp = warp_smem_bytes(nbufs, nslots_ops, nplan);
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
 	/* stage the tables this launch needs: TMA bulk copies, one mbarrier */
@@ -2214,6 +2375,8 @@ __device__ __forceinline__ void render_body(const CallDesc *calls, uint32_t ncal
 	fc.st = smem_u32(tab);           /* staged float tables, or the coefficient tables */
 	fc.tab = c.tab; fc.wc = c.wc;
 	fc.wave_mask = wave_mask; fc.lane = lane;
+	fc.plan = smem_u32(c.stk_len);   /* the plan overlays the len stacks */
+	fc.plan_cap = nplan * 32u > STACK_BYTES ? nplan : STACK_BYTES / 32u;
 
 	if (!ticketed) {
 		/* one warp renders every unit of one voice; task -> (call, voice) by
@@ -2314,19 +2477,19 @@ __device__ __forceinline__ void render_body(const CallDesc *calls, uint32_t ncal
 __global__ void __launch_bounds__(256, 2)
 render_kernel(const CallDesc *calls, uint32_t ncalls, const SegDesc *segs, const UnitDesc *units,
 		uint32_t ntasks, const float *tables, const double *coefs, uint32_t wave_mask, uint32_t nbufs,
-		uint32_t nslots_ops, uint32_t warps_per_cta, uint32_t ticketed) {
-	render_body(calls, ncalls, segs, units, ntasks, tables, coefs, wave_mask, nbufs, nslots_ops,
+		uint32_t nslots_ops, uint32_t nplan, uint32_t warps_per_cta, uint32_t ticketed) {
+	render_body(calls, ncalls, segs, units, ntasks, tables, coefs, wave_mask, nbufs, nslots_ops, nplan,
 			warps_per_cta, ticketed);
 }
 
 /* same body for CTAs of up to 32 warps (64 registers), one per SM (coefficient-table
  * mode: the planes take 48 KiB per wave, so one large CTA shares them among all the
  * warps an SM can hold -- the path is latency-bound, resident warps are what counts) */
-__global__ void __launch_bounds__(1024, 1)
+__global__ void __launch_bounds__(WIDE_WARPS * 32, 1)
 render_kernel_wide(const CallDesc *calls, uint32_t ncalls, const SegDesc *segs, const UnitDesc *units,
 		uint32_t ntasks, const float *tables, const double *coefs, uint32_t wave_mask, uint32_t nbufs,
-		uint32_t nslots_ops, uint32_t warps_per_cta, uint32_t ticketed) {
-	render_body(calls, ncalls, segs, units, ntasks, tables, coefs, wave_mask, nbufs, nslots_ops,
+		uint32_t nslots_ops, uint32_t nplan, uint32_t warps_per_cta, uint32_t ticketed) {
+	render_body(calls, ncalls, segs, units, ntasks, tables, coefs, wave_mask, nbufs, nslots_ops, nplan,
 			warps_per_cta, ticketed);
 }
 
@@ -2562,11 +2725,12 @@ cudaError_t launch_selftest(const float *d_tables, unsigned long long *d_bad, cu
 /* ---- host-callable launchers -------------------------------------------- */
 
 /* wave_mask may carry CTAB_FLAG (coefficient tables in shared memory) */
-size_t render_smem_bytes(uint32_t wave_mask, uint32_t nbufs, uint32_t nslots_ops, uint32_t warps) {
+size_t render_smem_bytes(uint32_t wave_mask, uint32_t nbufs, uint32_t nslots_ops, uint32_t nplan,
+		uint32_t warps) {
 	uint32_t nslots = 0;
 	for (uint32_t w = 0; w < NUM_WAVES; ++w) if (wave_mask & (1u << w)) ++nslots;
 	const size_t slot = (wave_mask & CTAB_FLAG) ? CTAB_WAVE_BYTES : TAB_STRIDE * sizeof(float);
-	return 128 + (size_t) nslots * slot + (size_t) warps * warp_smem_bytes(nbufs, nslots_ops);
+	return 128 + (size_t) nslots * slot + (size_t) warps * warp_smem_bytes(nbufs, nslots_ops, nplan);
 }
 
 /* ---- per-index cubic coefficients of every wave table -------------------- *
@@ -2626,11 +2790,11 @@ int render_ctas_per_sm(size_t smem, uint32_t warps) {
 }
 cudaError_t launch_render(const CallDesc *d_calls, uint32_t ncalls, const SegDesc *d_segs,
 		const UnitDesc *d_units, uint32_t ntasks, const float *d_tables, const double *d_coefs,
-		uint32_t wave_mask, uint32_t nbufs, uint32_t nslots_ops, uint32_t warps,
+		uint32_t wave_mask, uint32_t nbufs, uint32_t nslots_ops, uint32_t nplan, uint32_t warps,
 		uint32_t ticketed_ctas, uint32_t sched_mode, cudaStream_t stream) {
 	if (ntasks == 0) return cudaSuccess;
 	if (nslots_ops == 0) nslots_ops = 1;
-	const size_t smem = render_smem_bytes(wave_mask, nbufs, nslots_ops, warps);
+	const size_t smem = render_smem_bytes(wave_mask, nbufs, nslots_ops, nplan, warps);
 	const bool wide = warps > 8;
 	{
 		cudaError_t e = ensure_smem(wide, smem);
@@ -2639,10 +2803,10 @@ cudaError_t launch_render(const CallDesc *d_calls, uint32_t ncalls, const SegDes
 	const uint32_t grid = ticketed_ctas ? ticketed_ctas : (ntasks + warps - 1) / warps;
 	if (wide)
 		render_kernel_wide<<<grid, warps * 32, smem, stream>>>(d_calls, ncalls, d_segs, d_units, ntasks,
-				d_tables, d_coefs, wave_mask, nbufs, nslots_ops, warps, ticketed_ctas ? sched_mode : 0u);
+				d_tables, d_coefs, wave_mask, nbufs, nslots_ops, nplan, warps, ticketed_ctas ? sched_mode : 0u);
 	else
 		render_kernel<<<grid, warps * 32, smem, stream>>>(d_calls, ncalls, d_segs, d_units, ntasks,
-				d_tables, d_coefs, wave_mask, nbufs, nslots_ops, warps, ticketed_ctas ? sched_mode : 0u);
+				d_tables, d_coefs, wave_mask, nbufs, nslots_ops, nplan, warps, ticketed_ctas ? sched_mode : 0u);
 	return cudaGetLastError();
 }
 

@@ -28,10 +28,11 @@
 #include "device_types.h"
 
 namespace saugen {
-size_t render_smem_bytes(uint32_t wave_mask, uint32_t nbufs, uint32_t nslots_ops, uint32_t warps);
+size_t render_smem_bytes(uint32_t wave_mask, uint32_t nbufs, uint32_t nslots_ops, uint32_t nplan,
+		uint32_t warps);
 cudaError_t launch_render(const CallDesc *d_calls, uint32_t ncalls, const SegDesc *d_segs,
 		const UnitDesc *d_units, uint32_t ntasks, const float *d_tables, const double *d_coefs,
-		uint32_t wave_mask, uint32_t nbufs, uint32_t nslots_ops, uint32_t warps,
+		uint32_t wave_mask, uint32_t nbufs, uint32_t nslots_ops, uint32_t nplan, uint32_t warps,
 		uint32_t ticketed_ctas, uint32_t sched_mode, cudaStream_t stream);
 int render_ctas_per_sm(size_t smem, uint32_t warps);
 size_t coef_table_bytes();
@@ -237,6 +238,7 @@ struct saugen_Generator {
 	uint32_t voice_begin = 0, voice_end = 0;
 	uint32_t row_stride = 0;
 	uint32_t row_len = 0, nbufs = 1, max_ops = 1, wave_mask = 0, seg_cap = 0, sched = 0;
+	uint32_t nplan = 0;                // block-plan records the largest voice program needs (kernels.cu)
 	float amp_scale = 0.f;
 	/* timeline (host-only integer bookkeeping) */
 	std::vector<uint64_t> ev_time;     // absolute sample time of each event
@@ -641,6 +643,23 @@ extern "C" saugen_Generator *saugen_create(const sauabi_Program *prg, uint32_t s
 					po.first = (uint32_t) prog_ops.size();
 					po.second = (uint32_t) comp.prog_ops.size();
 					if (po.second > o->max_ops) o->max_ops = po.second;
+					{
+						/* records of the fast path's block plan (kernels.cu:steady_plan): the
+						 * instructions that do something per chunk; a program with any other
+						 * kind of instruction never takes that path */
+						uint32_t np = 0;
+						bool fast = true;
+						for (const Instr &in : comp.out) {
+							switch (in.opcode) {
+							case I_WLEAF: case I_WHEAD: case I_WTAIL: case I_RANGE: case I_VOUT: ++np; break;
+							case I_LINE: if (in.d) ++np; break;
+							case I_ENTER: case I_VPAN: case I_END: break;
+							default: fast = false; break;
+							}
+						}
+						++np;                              /* the plan's header slot */
+						if (fast && np <= 64 && np > o->nplan) o->nplan = np;
+					}
 					prog_ops.insert(prog_ops.end(), comp.prog_ops.begin(), comp.prog_ops.end());
 				}
 				er.code_off = pv.first; er.code_len = pv.second;
@@ -837,7 +856,7 @@ static const uint32_t CTAB_FLAG = 0x80000000u;
 static const size_t SMEM_CAP = 227 * 1024;
 struct Shape { uint32_t warps; uint32_t mask; };
 static Shape pick_shape(uint32_t ntasks, uint32_t wave_mask, uint32_t nbufs, uint32_t max_ops,
-		bool have_coefs) {
+		uint32_t nplan, bool have_coefs) {
 	const uint32_t sms = 148;
 	int nw = 0;
 	for (uint32_t w = 0; w < NUM_WAVES; ++w) if (wave_mask & (1u << w)) ++nw;
@@ -846,12 +865,12 @@ static Shape pick_shape(uint32_t ntasks, uint32_t wave_mask, uint32_t nbufs, uin
 	Shape sh;
 	for (int pass = want_ctab ? 0 : 1; pass < 2; ++pass) {
 		sh.mask = pass == 0 ? (wave_mask | CTAB_FLAG) : wave_mask;
-		uint32_t fit = 32;
-		while (fit > 1 && render_smem_bytes(sh.mask, nbufs, max_ops, fit) > SMEM_CAP) --fit;
+		uint32_t fit = 28;                 /* kernels.cu:WIDE_WARPS */
+		while (fit > 1 && render_smem_bytes(sh.mask, nbufs, max_ops, nplan, fit) > SMEM_CAP) --fit;
 		sh.warps = (ntasks + sms - 1) / sms;
 		if (sh.warps < 1) sh.warps = 1;
 		if (sh.warps > fit) sh.warps = fit;
-		if (render_smem_bytes(sh.mask, nbufs, max_ops, sh.warps) <= SMEM_CAP && (pass == 1 || fit >= 8))
+		if (render_smem_bytes(sh.mask, nbufs, max_ops, nplan, sh.warps) <= SMEM_CAP && (pass == 1 || fit >= 8))
 			return sh;
 	}
 	return sh;
@@ -910,11 +929,11 @@ static int run_common(saugen_Generator *o, size_t buf_len, int stereo, uint32_t 
 	 * persistent grid with (unit, voice) tickets, 3 = balanced contiguous ranges.
 	 * Auto picks balanced when the voices would otherwise need a second, partly
 	 * filled wave of warps (between 1 and 4 waves), else one warp per voice. */
-	const Shape shape = pick_shape(o->nlv, o->wave_mask, o->nbufs, o->max_ops, o->d_coefs != nullptr);
+	const Shape shape = pick_shape(o->nlv, o->wave_mask, o->nbufs, o->max_ops, o->nplan, o->d_coefs != nullptr);
 	const uint32_t warps = shape.warps;
 	uint32_t ticketed_ctas = 0, sched_mode = 0;
 	{
-		const size_t smem = render_smem_bytes(shape.mask, o->nbufs, o->max_ops, warps);
+		const size_t smem = render_smem_bytes(shape.mask, o->nbufs, o->max_ops, o->nplan, warps);
 		int per_sm = render_ctas_per_sm(smem, warps);
 		if (per_sm < 1) per_sm = 1;
 		const uint32_t resident_ctas = 148u * (uint32_t) per_sm;
@@ -966,7 +985,7 @@ static int run_common(saugen_Generator *o, size_t buf_len, int stereo, uint32_t 
 	if (e == cudaSuccess && o->timed_call) e = cudaEventRecord(o->ev_t[0], o->stream);
 	if (e == cudaSuccess) {
 		e = launch_render(o->d_call, 1, o->d_segs, o->d_units, o->nlv, o->d_tables, o->d_coefs,
-				shape.mask, o->nbufs, o->max_ops, warps, ticketed_ctas, sched_mode, o->stream);
+				shape.mask, o->nbufs, o->max_ops, o->nplan, warps, ticketed_ctas, sched_mode, o->stream);
 		o->counters[0]++;
 	}
 	if (e == cudaSuccess && o->timed_call) e = cudaEventRecord(o->ev_t[1], o->stream);
@@ -1070,7 +1089,7 @@ extern "C" int saugen_run_many(saugen_Generator *const *gens, size_t n, int16_t 
 	static thread_local std::vector<UnitDesc> units;
 	static thread_local UnitDesc *d_units = nullptr; static thread_local size_t d_units_cap = 0;
 	calls.clear(); segs.clear(); call_of.clear(); units.clear();
-	uint32_t ntasks = 0, wave_mask = 0, nbufs = 1, max_ops = 1;
+	uint32_t ntasks = 0, wave_mask = 0, nbufs = 1, max_ops = 1, nplan = 0;
 	for (size_t i = 0; i < n; ++i) {
 		saugen_Generator *o = gens[i];
 		if (out_lens) out_lens[i] = 0;
@@ -1100,6 +1119,7 @@ extern "C" int saugen_run_many(saugen_Generator *const *gens, size_t n, int16_t 
 		wave_mask |= o->wave_mask;
 		if (o->nbufs > nbufs) nbufs = o->nbufs;
 		if (o->max_ops > max_ops) max_ops = o->max_ops;
+		if (o->nplan > nplan) nplan = o->nplan;
 		if (!o->compact) cudaMemsetAsync(o->d_status, 0, (1 + cd.nseg) * sizeof(uint32_t), g0->stream);
 	}
 	if (calls.empty()) return 0;
@@ -1125,9 +1145,9 @@ extern "C" int saugen_run_many(saugen_Generator *const *gens, size_t n, int16_t 
 	g0->timed_call = g0->timing;       /* kernel times of the batch accumulate on the first generator */
 	if (e == cudaSuccess && g0->timed_call) e = cudaEventRecord(g0->ev_t[0], g0->stream);
 	if (e == cudaSuccess) {
-		const Shape shape = pick_shape(ntasks, wave_mask, nbufs, max_ops, g0->d_coefs != nullptr);
+		const Shape shape = pick_shape(ntasks, wave_mask, nbufs, max_ops, nplan, g0->d_coefs != nullptr);
 		e = launch_render(d_calls, (uint32_t) calls.size(), d_segs, d_units, ntasks, g0->d_tables,
-				g0->d_coefs, shape.mask, nbufs, max_ops, shape.warps, 0, 0, g0->stream);
+				g0->d_coefs, shape.mask, nbufs, max_ops, nplan, shape.warps, 0, 0, g0->stream);
 		g0->counters[0]++;
 	}
 	if (e == cudaSuccess && g0->timed_call) e = cudaEventRecord(g0->ev_t[1], g0->stream);
