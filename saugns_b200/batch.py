@@ -25,7 +25,7 @@ def _capacity_frames(prg, srate, call_len):
 
 
 def render_batch(programs, srate=96000, device=0, call_len=None, tables=None, group_size=256,
-                 stereo=True, max_frames=None, threads=3):
+                 stereo=True, max_frames=None, threads=1, sink=None):
     """Render every program of `programs` -> list of int16 arrays [frames, ch],
     in input order.  Programs are independent (no mixing between them).
 
@@ -37,7 +37,15 @@ def render_batch(programs, srate=96000, device=0, call_len=None, tables=None, gr
 
     Each call's PCM lands directly in the program's final array (the C side
     copies from its pinned staging buffer to the address it is given), so the
-    per-call Python work is a few vector operations over the live set."""
+    per-call Python work is a few vector operations over the live set.
+
+    `sink(index, pcm)`: called (on a worker thread) with each finished program's
+    PCM instead of keeping it; the array is only valid during the call -- its
+    memory goes back to a pool and carries a later program's samples.  This is
+    the streaming form (what Player_run does with its 256 ms buffer, saugns.c:
+    601-609: write it out, reuse it): a batch of thousands of scripts does not
+    hold gigabytes of PCM, nor pay the first-touch page faults of fresh arrays.
+    The returned list then holds None."""
     import itertools
     import threading
     if call_len is None:
@@ -48,14 +56,14 @@ def render_batch(programs, srate=96000, device=0, call_len=None, tables=None, gr
     threads = max(1, min(int(threads), (n + 15) // 16))
     if threads == 1:
         _render_worker(programs, out, queue, srate, device, call_len, tables, group_size, stereo,
-                       max_frames)
+                       max_frames, sink)
         return out
     errs = []
 
     def work():
         try:
             _render_worker(programs, out, queue, srate, device, call_len, tables, group_size,
-                           stereo, max_frames)
+                           stereo, max_frames, sink)
         except BaseException as e:                # re-raised on the caller's thread
             errs.append(e)
 
@@ -70,7 +78,7 @@ def render_batch(programs, srate=96000, device=0, call_len=None, tables=None, gr
 
 
 def _render_worker(programs, out, queue, srate, device, call_len, tables, group_size, stereo,
-                   max_frames):
+                   max_frames, sink=None):
     """One live set: admit from `queue`, advance with saugen_run_many, retire."""
     L = G.lib()
     ch = 2 if stereo else 1
@@ -81,6 +89,14 @@ def _render_worker(programs, out, queue, srate, device, call_len, tables, group_
     pos = np.zeros(0, np.int64)                   # frames written so far
     cap = np.zeros(0, np.int64)
     drained = False
+    pool = []                                     # recycled output arrays (sink mode)
+
+    def new_buf(size):
+        for j, b in enumerate(pool):
+            if b.size >= size:
+                return pool.pop(j)
+        return np.empty(size, np.int16)
+
     while not drained or gens:
         if not drained and len(gens) < group_size:
             k0 = len(gens)
@@ -92,7 +108,7 @@ def _render_worker(programs, out, queue, srate, device, call_len, tables, group_
                 g = G.Generator(programs[i], srate, tables=tables, device=device,
                                 max_call_len=call_len)
                 c = _capacity_frames(programs[i], srate, call_len)
-                b = np.empty(c * ch, np.int16)
+                b = new_buf(c * ch)
                 idx.append(i); gens.append(g); bufs.append(b)
             gptr = np.concatenate([gptr, np.array([g.ptr for g in gens[k0:]], np.uint64)])
             base = np.concatenate([base, np.array([b.ctypes.data for b in bufs[k0:]], np.uint64)])
@@ -121,7 +137,12 @@ def _render_worker(programs, out, queue, srate, device, call_len, tables, group_
             for k in range(m):
                 if done[k]:
                     gens[k].close()
-                    out[idx[k]] = bufs[k][:pos[k] * ch].reshape(-1, ch)
+                    pcm = bufs[k][:pos[k] * ch].reshape(-1, ch)
+                    if sink is None:
+                        out[idx[k]] = pcm
+                    else:
+                        sink(idx[k], pcm)
+                        pool.append(bufs[k])
                 else:
                     keep.append(k)
             idx = [idx[k] for k in keep]; gens = [gens[k] for k in keep]; bufs = [bufs[k] for k in keep]

@@ -1507,12 +1507,13 @@ __device__ __forceinline__ bool op_outlasts_block(const OpState *o) {
  * closed form: every sample adds the same inc = lrintf(coeff * f), so sample i
  * of the chunk is at phase0 + (i + 1) * inc in wrap-around uint32 arithmetic --
  * bit-identical to the serial accumulation, without conversions or a scan. */
-enum : uint32_t { P_LINE = 1, P_WHEAD, P_WTAIL, P_WLEAF, P_RANGE, P_VOUT };
+enum : uint32_t { P_LINE = 1, P_WHEAD, P_WTAIL, P_WLEAF, P_PHASE, P_WOSC, P_RANGE, P_VOUT };
 enum : uint32_t {
 	PF_LAYER = 1, PF_WAVEENV = 2,
 	PF_FUNI = 4,       /* frequency (or the LINE's value) is uniform over the block */
 	PF_FMUL = 8,       /* ... and is v0 times the (uniform) multiplier buffer */
 	PF_ACONST = 16,    /* amplitude line holds av */
+	PF_ABUF = 32,      /* amplitude comes from work buffer c (the operator has amplitude modulators) */
 };
 constexpr uint32_t PLAN_REC = 32;     /* bytes: w0 kind|flags<<8|a<<16|b<<24, w1 c|e<<8|line<<16,
                                        * w2 operator state (shared address), w3 table (shared address),
@@ -1578,6 +1579,41 @@ __device__ __noinline__ uint32_t steady_plan(OpState *sops, uint32_t so, uint32_
 		case I_VPAN:
 			if (in.d || (LM_FLAGS(o->lmeta[LINE_PAN]) & SAUABI_LINEP_GOAL)) return 0;
 			break;
+		/* a wave operator whose amplitude has modulators (run_block_wosc, generator.c:
+		 * 548-602, unfused): ENTER [frequency] [PM] PHASOR [amplitude + its modulators]
+		 * PMA WOSC MIX LEAVE */
+		case I_PHASOR:
+			if (in.d != NO_BUF) return 0;                            /* fPM: general path */
+			if (o->oscflags & OSC_RESET_DIFF) return 0;
+			plan_put(plan, n++, P_PHASE | ((in.b < 32 && ((uni >> in.b) & 1u)) ? PF_FUNI : 0u) << 8 |
+					(uint32_t) in.a << 16 | (uint32_t) in.b << 24, (uint32_t) in.c, opa, 0u, 0.f, 0.f, 0.f, 0.f);
+			if (in.a < 32) uni &= ~(1u << in.a);
+			break;
+		case I_PMA:                                                  /* generator.c:485-490 */
+			if (o->line[LINE_PMA].v0 != 0.f ||
+					(LM_FLAGS(o->lmeta[LINE_PMA]) & SAUABI_LINEP_GOAL)) return 0;
+			break;
+		case I_WOSC: {
+			if ((in.flags & F_HAS_APMODS) || pc + 2 >= code_len) return 0;
+			Instr mix, leave;
+			memcpy(&mix, &raw_next, sizeof(mix));
+			const uint4 raw_leave = __ldg(reinterpret_cast<const uint4*>(code + pc + 2));
+			memcpy(&leave, &raw_leave, sizeof(leave));
+			if (mix.opcode != I_MIX || mix.b != in.a || leave.opcode != I_LEAVE || leave.op != in.op) return 0;
+			const uint32_t wave = o->mode;
+			const uint32_t slot = __popc(wave_mask & ((1u << wave) - 1u));
+			const uint32_t ct = (wave_mask & CTAB_FLAG) ? st + slot * CTAB_WAVE_BYTES :
+				st + slot * (TAB_STRIDE * 4) + 12;
+			const uint32_t fl = ((leave.flags & F_LAYER) ? PF_LAYER : 0u) |
+				((mix.flags & F_WAVEENV) ? PF_WAVEENV : 0u) | PF_ABUF;
+			plan_put(plan, n++, P_WOSC | fl << 8 | (uint32_t) mix.a << 16 | (uint32_t) in.b << 24,
+					(uint32_t) mix.c, opa, ct, wc->diff_scale[wave], wc->diff_offset[wave], 0.f, 0.f);
+			if (mix.a < 32) uni &= ~(1u << mix.a);
+			if (in.a < 32) uni &= ~(1u << in.a);
+			/* MIX and LEAVE are part of the record */
+			pc += 2;
+			if (pc + 1 < code_len) raw_next = __ldg(reinterpret_cast<const uint4*>(code + pc + 1));
+			break; }
 		default:
 			return 0;
 		}
@@ -1656,6 +1692,13 @@ __device__ __noinline__ void steady_update(OpState *sops, const Instr *code, uin
 			break;
 		case I_VPAN:
 			line_skip(0, 0, o, LINE_PAN, REF_BLOCK);
+			break;
+		case I_PMA:                /* not run in a steady block (steady_plan) */
+			line_skip(0, 0, o, LINE_PMA, REF_BLOCK);
+			o->flags &= ~ON_PMA_RUN;
+			break;
+		case I_LEAVE:              /* unfused wave operator, generator.c:726-727 */
+			if (!(o->flags & ON_TIME_INF)) o->time -= REF_BLOCK;
 			break;
 		default: break;
 		}
@@ -1895,20 +1938,15 @@ __device__ __forceinline__ double horner_frac(double c3, double c2, double c1, u
 	return ((c3 * x + c2) * x + c1) * x;
 }
 
-/* TAIL of a wave operator on a steady full chunk: phase fill, oscillator,
- * amplitude line, block_mix (generator.c:584-601).  funi: every sample adds
- * `inc` to the phase (see steady_plan); else fr = its frequency values. */
-template <int NS, bool CTAB>
-__device__ __forceinline__ void wtail_plan(const HotCtx &c, const uint4 p0, const uint32_t rec,
-		const bool funi, const uint32_t inc, const float fr[NS]) {
-	const uint32_t flags = (p0.x >> 8) & 0xffu, bufa = (p0.x >> 16) & 0xffu, bufc = p0.y & 0xffu;
-	const uint32_t op = p0.z;
-	uint2 og, pg;                                /* i0, i1 (phase, prev_phase); prev_Is lo / hi */
+/* Phase fill of a wave operator on a steady full chunk (sauPhasor_fill,
+ * wosc.h:135-169).  funi: every sample adds `inc` to the phase (see steady_plan);
+ * else fr = its frequency values.  bufc: PM input or NO_BUF. */
+template <int NS>
+__device__ __forceinline__ void phase_plan(const HotCtx &c, const uint32_t op, const uint32_t bufc,
+		const bool funi, const uint32_t inc, const float fr[NS], uint32_t ph[NS]) {
+	uint2 og;                                    /* i0, i1 (phase, prev_phase) */
 	asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(og.x), "=r"(og.y) : "r"(op + OS_I0));
-	asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(pg.x), "=r"(pg.y) : "r"(op + OS_PREV));
-	__syncwarp();              /* every lane holds the accumulators before lane 31 rewrites them */
-	/* sauPhasor_fill, wosc.h:135-169 */
-	uint32_t ph[NS];
+	__syncwarp();              /* every lane holds the accumulator before lane 31 rewrites it */
 	if (funi) {
 		const uint32_t base = og.x + inc * (uint32_t) (c.lane * NS);
 #pragma unroll
@@ -1927,14 +1965,28 @@ __device__ __forceinline__ void wtail_plan(const HotCtx &c, const uint4 p0, cons
 		for (int k = 0; k < NS; ++k) ph[k] += base;
 		if (c.lane == 31) sts32(op + OS_I0, og.x + incl);
 	}
-	const bool pm_in = bufc != NO_BUF;       /* PM; fPM operators take the general path (steady_plan) */
-	if (pm_in) {
+	if (bufc != NO_BUF) {      /* PM; fPM operators take the general path (steady_plan) */
 		float pm[NS];
 		fld<NS>(c, bufc, pm);
 #pragma unroll
 		for (int k = 0; k < NS; ++k) ph[k] += ftoi_lo32(pm[k] * 2147483648.f);
 	}
-	/* sauWOsc_run, wosc.h:238-266 */
+}
+
+/* Oscillator, amplitude and block_mix of a wave operator on a steady full chunk
+ * (sauWOsc_run, wosc.h:238-266; generator.c:584-601) at the phases ph.  pure:
+ * every phase difference is `inc` (uniform frequency, no PM).  The amplitude is
+ * the operator's own line, or (PF_ABUF) a buffer its modulators wrote. */
+template <int NS, bool CTAB>
+__device__ __forceinline__ void osc_plan(const HotCtx &c, const uint4 p0, const uint32_t rec,
+		const bool pure, const uint32_t inc, const uint32_t ph[NS]) {
+	const uint32_t flags = (p0.x >> 8) & 0xffu, bufa = (p0.x >> 16) & 0xffu;
+	const uint32_t op = p0.z;
+	uint2 pg;                                    /* prev_Is lo / hi */
+	uint32_t pph0;                               /* prev_phase */
+	asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(pg.x), "=r"(pg.y) : "r"(op + OS_PREV));
+	pph0 = lds32(op + OS_I1);
+	__syncwarp();              /* every lane holds the carried values before lane 31 rewrites them */
 	float s[NS];
 	{
 		double Is[NS];
@@ -1960,7 +2012,7 @@ __device__ __forceinline__ void wtail_plan(const HotCtx &c, const uint4 p0, cons
 		uint32_t pph = __shfl_up_sync(FULL, ph[NS - 1], 1);
 		double pIs = __shfl_up_sync(FULL, Is[NS - 1], 1);
 		if (c.lane == 0) {
-			pph = og.y;
+			pph = pph0;
 			pIs = __hiloint2double((int) pg.y, (int) pg.x);
 		}
 		int32_t d[NS];
@@ -1987,7 +2039,7 @@ __device__ __forceinline__ void wtail_plan(const HotCtx &c, const uint4 p0, cons
 			const float2 dd = lds64f(rec + 16);
 			const float ds = dd.x;
 			const double doff = (double) dd.y;
-			if (funi && !pm_in) {
+			if (pure) {
 				/* a pure tone: every phase difference is inc, one division per lane
 				 * (lane 0's first sample follows the carried phase, which an event
 				 * may have moved) */
@@ -2019,6 +2071,8 @@ __device__ __forceinline__ void wtail_plan(const HotCtx &c, const uint4 p0, cons
 		const float av = lds32f(rec + 28);
 #pragma unroll
 		for (int k = 0; k < NS; ++k) am[k] = av;
+	} else if (flags & PF_ABUF) {
+		fld<NS>(c, p0.y & 0xffu, am);
 	} else {
 		line_value_steady<NS>(c, op, LINE_AMP, nullptr, am);
 	}
@@ -2064,34 +2118,55 @@ __device__ __forceinline__ void run_chunk_plan(const HotCtx &c, const uint32_t n
 		const uint32_t kind = p0.x & 0xffu, flags = (p0.x >> 8) & 0xffu;
 		const uint32_t bufa = (p0.x >> 16) & 0xffu, bufb = p0.x >> 24;
 		const uint32_t op = p0.z;
-		if (kind <= P_WLEAF) {
+		if (kind <= P_WOSC) {
 			/* LINE / WHEAD: one line evaluation into a buffer; WLEAF: the same, kept in
-			 * registers, then the tail; WTAIL: the frequency comes from its buffer */
-			const bool is_line = kind == P_LINE;
-			const bool funi = (flags & PF_FUNI) != 0;
-			float fr[NS];
+			 * registers, then phase fill and oscillator; WTAIL: the frequency comes from
+			 * its buffer; PHASE / WOSC: the two halves of an operator whose amplitude has
+			 * modulators, with the phases parked in a buffer in between */
+			uint32_t ph[NS];
 			uint32_t inc = 0;
-			if (kind == P_WTAIL) {
-				if (funi) inc = ftoi_lo32(c.coeff * lds32f(c.sb + bufb * FastCfg<NS>::FBUF_BYTES));
-				else fld<NS>(c, bufb, fr);
-			} else {
-				const uint32_t mb = is_line ? bufb : (p0.y >> 8) & 0xffu;
-				if (funi) {
-					float f = lds32f(rec + 24);
-					if (flags & PF_FMUL) f = f * lds32f(c.sb + mb * FastCfg<NS>::FBUF_BYTES);
-					inc = ftoi_lo32(c.coeff * f);
-#pragma unroll
-					for (int k = 0; k < NS; ++k) fr[k] = f;
+			bool pure = false;
+			if (kind != P_WOSC) {
+				const bool is_line = kind == P_LINE;
+				const bool funi = (flags & PF_FUNI) != 0;
+				float fr[NS];
+				if (kind == P_WTAIL || kind == P_PHASE) {
+					if (funi) inc = ftoi_lo32(c.coeff * lds32f(c.sb + bufb * FastCfg<NS>::FBUF_BYTES));
+					else fld<NS>(c, bufb, fr);
 				} else {
-					float m[NS];
-					const bool has_mul = mb != NO_BUF;
-					if (has_mul) fld<NS>(c, mb, m);
-					line_value_steady<NS>(c, op, is_line ? (int) ((p0.y >> 16) & 0xffu) : (int) LINE_FREQ,
-							has_mul ? m : nullptr, fr);
+					const uint32_t mb = is_line ? bufb : (p0.y >> 8) & 0xffu;
+					if (funi) {
+						float f = lds32f(rec + 24);
+						if (flags & PF_FMUL) f = f * lds32f(c.sb + mb * FastCfg<NS>::FBUF_BYTES);
+						inc = ftoi_lo32(c.coeff * f);
+#pragma unroll
+						for (int k = 0; k < NS; ++k) fr[k] = f;
+					} else {
+						float m[NS];
+						const bool has_mul = mb != NO_BUF;
+						if (has_mul) fld<NS>(c, mb, m);
+						line_value_steady<NS>(c, op, is_line ? (int) ((p0.y >> 16) & 0xffu) : (int) LINE_FREQ,
+								has_mul ? m : nullptr, fr);
+					}
+					if (kind != P_WLEAF) { fst<NS>(c, is_line ? bufa : bufb, fr); continue; }
 				}
-				if (kind != P_WLEAF) { fst<NS>(c, is_line ? bufa : bufb, fr); continue; }
+				const uint32_t bufc = p0.y & 0xffu;
+				phase_plan<NS>(c, op, bufc, funi, inc, fr, ph);
+				if (kind == P_PHASE) {
+					float pf[NS];
+#pragma unroll
+					for (int k = 0; k < NS; ++k) pf[k] = __uint_as_float(ph[k]);
+					fst<NS>(c, bufa, pf);
+					continue;
+				}
+				pure = funi && bufc == NO_BUF;
+			} else {
+				float pf[NS];
+				fld<NS>(c, bufb, pf);
+#pragma unroll
+				for (int k = 0; k < NS; ++k) ph[k] = __float_as_uint(pf[k]);
 			}
-			wtail_plan<NS, CTAB>(c, p0, rec, funi, inc, fr);
+			osc_plan<NS, CTAB>(c, p0, rec, pure, inc, ph);
 		} else if (kind == P_RANGE) {                              /* generator.c:465-467 */
 			float p[NS], rr[NS], m[NS];
 			fld<NS>(c, bufa, p); fld<NS>(c, bufb, rr); fld<NS>(c, p0.y & 0xffu, m);

@@ -23,6 +23,8 @@
 #include <set>
 #include <mutex>
 #include <thread>
+#include <atomic>
+#include <chrono>
 
 #include "../../include/saugen_b200.h"
 #include "device_types.h"
@@ -68,7 +70,33 @@ struct TableBlock { float *d; double *coefs; };
 static std::mutex g_tab_mu;
 static std::map<std::pair<int, uint64_t>, TableBlock> g_tabs;
 
+/* A batch render creates thousands of generators on the same table set: the full
+ * content hash (98 KiB) is skipped when the caller's struct address and a sparse
+ * fingerprint of the tables (every 64th value + the per-wave coefficients) were
+ * seen before on this device. */
+struct TableSeen { int device; const void *addr; uint64_t fp; TableBlock blk; };
+static std::vector<TableSeen> g_tab_seen;
+static uint64_t table_fingerprint(const saugen_WaveTables *t) {
+	uint64_t h = 1469598103934665603ull;
+	auto mix = [&h](uint32_t v) { h ^= v; h *= 1099511628211ull; };
+	for (int w = 0; w < NUM_WAVES; ++w) {
+		for (int i = 0; i < WAVE_LEN; i += 64) { uint32_t v; memcpy(&v, &t->pilut[w][i], 4); mix(v); }
+		uint32_t a, b; memcpy(&a, &t->amp_scale[w], 4); memcpy(&b, &t->amp_dc[w], 4);
+		mix(a); mix(b); mix((uint32_t) t->phase_adj[w]);
+	}
+	return h;
+}
+
 static float *get_device_tables(int device, const saugen_WaveTables *t, double **coefs_out = nullptr) {
+	const uint64_t fp = table_fingerprint(t);
+	{
+		std::lock_guard<std::mutex> lk(g_tab_mu);
+		for (const TableSeen &e : g_tab_seen)
+			if (e.device == device && e.addr == (const void*) t && e.fp == fp) {
+				if (coefs_out) *coefs_out = e.blk.coefs;
+				return e.blk.d;
+			}
+	}
 	std::vector<float> host((size_t) NUM_WAVES * WAVE_LEN + sizeof(WaveCoeffs) / sizeof(float));
 	for (int w = 0; w < NUM_WAVES; ++w)
 		memcpy(&host[(size_t) w * WAVE_LEN], t->pilut[w], sizeof(float) * WAVE_LEN);
@@ -88,6 +116,7 @@ static float *get_device_tables(int device, const saugen_WaveTables *t, double *
 	auto it = g_tabs.find(key);
 	if (it != g_tabs.end()) {
 		if (coefs_out) *coefs_out = it->second.coefs;
+		if (g_tab_seen.size() < 64) g_tab_seen.push_back(TableSeen{device, (const void*) t, fp, it->second});
 		return it->second.d;
 	}
 	float *d = nullptr;
@@ -111,6 +140,7 @@ static float *get_device_tables(int device, const saugen_WaveTables *t, double *
 		if (h_flag) { cudaFree(dc); dc = nullptr; }
 	}
 	g_tabs[key] = TableBlock{d, dc};
+	if (g_tab_seen.size() < 64) g_tab_seen.push_back(TableSeen{device, (const void*) t, fp, TableBlock{d, dc}});
 	if (coefs_out) *coefs_out = dc;
 	return d;
 }
@@ -133,7 +163,11 @@ struct MemPool {
 		if (n < 4096) return 4096;
 		size_t p = 4096;
 		while (p * 2 <= n) p *= 2;
-		const size_t step = p / 8;                     /* <= 12.5 % slack */
+		/* up to 32 MiB: powers of two, so that the row blocks of a batch of small
+		 * scripts (a few MiB each, every size different) fall into a handful of
+		 * classes and recycle; above: <= 12.5 % slack */
+		if (n <= ((size_t) 32 << 20)) return p == n ? n : p * 2;
+		const size_t step = p / 8;
 		return (n + step - 1) / step * step;
 	}
 	void *alloc(bool host, int dev, size_t bytes) {
@@ -152,7 +186,7 @@ struct MemPool {
 		}
 		/* small classes come out of slabs: one cudaMalloc / cudaHostAlloc per SLAB bytes
 		 * instead of one per generator (pinned allocations cost about a millisecond) */
-		const size_t SLAB = (size_t) 8 << 20;
+		const size_t SLAB = host ? (size_t) 8 << 20 : (size_t) 128 << 20;
 		const size_t want = r <= SLAB / 4 ? SLAB / r * r : r;
 		void *p = nullptr;
 		cudaError_t e = host ? cudaHostAlloc(&p, want, cudaHostAllocPortable) : cudaMalloc(&p, want);
@@ -212,11 +246,57 @@ struct MemPool {
 };
 MemPool g_pool;
 
+/* cudaStreamCreate / cudaStreamDestroy cost a few hundred microseconds and
+ * serialise with other threads' launches: generators that own their stream take
+ * it from a per-device list and give it back (synchronised) at destroy. */
+struct StreamPool {
+	std::mutex mu;
+	std::vector<cudaStream_t> free_[MemPool::MAXDEV];
+	cudaStream_t get(int dev) {
+		if (dev >= 0 && dev < MemPool::MAXDEV) {
+			std::lock_guard<std::mutex> lk(mu);
+			if (!free_[dev].empty()) { cudaStream_t s = free_[dev].back(); free_[dev].pop_back(); return s; }
+		}
+		cudaStream_t s = nullptr;
+		if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+		return s;
+	}
+	void put(int dev, cudaStream_t s) {
+		if (dev >= 0 && dev < MemPool::MAXDEV) {
+			std::lock_guard<std::mutex> lk(mu);
+			if (free_[dev].size() < 1024) { free_[dev].push_back(s); return; }
+		}
+		cudaStreamDestroy(s);
+	}
+};
+StreamPool g_streams;
+
 /* carve 256-byte aligned pieces out of one block */
 struct Carver {
 	size_t off = 0;
 	size_t take(size_t bytes) { size_t o = off; off = (off + (bytes ? bytes : 1) + 255) & ~(size_t) 255; return o; }
 };
+}
+
+/* developer aid: SAUGEN_PROFILE=1 prints where saugen_create spends its time */
+namespace {
+struct CreateProf {
+	std::atomic<long long> ns[6];
+	std::atomic<long long> n;
+	bool on;
+	CreateProf() : on(getenv("SAUGEN_PROFILE") != nullptr) { for (auto &x : ns) x = 0; n = 0; }
+	~CreateProf() {
+		if (!on || !n) return;
+		static const char *nm[6] = {"flatten", "stream+tables", "device alloc", "pinned alloc", "events", "upload+sync"};
+		fprintf(stderr, "saugen_create x %lld:", (long long) n);
+		for (int i = 0; i < 6; ++i) fprintf(stderr, " %s %.3f ms", nm[i], ns[i] / 1e6 / (double) n);
+		fprintf(stderr, "\n");
+	}
+};
+CreateProf g_cprof;
+inline long long now_ns() {
+	return std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 }
 
 /* ---- generator object ---------------------------------------------------- */
@@ -528,6 +608,8 @@ extern "C" saugen_Generator *saugen_create(const sauabi_Program *prg, uint32_t s
 		return nullptr;
 	}
 	saugen_Generator *o = new saugen_Generator();
+	long long tp = now_ns();
+	auto lap = [&tp](int i) { if (g_cprof.on) { const long long t = now_ns(); g_cprof.ns[i] += t - tp; tp = t; } };
 	std::vector<HostOp> hops(prg->op_count);
 	std::vector<EventRec> events(prg->ev_count);
 	std::vector<OpDataRec> opdata;
@@ -651,9 +733,10 @@ extern "C" saugen_Generator *saugen_create(const sauabi_Program *prg, uint32_t s
 						bool fast = true;
 						for (const Instr &in : comp.out) {
 							switch (in.opcode) {
-							case I_WLEAF: case I_WHEAD: case I_WTAIL: case I_RANGE: case I_VOUT: ++np; break;
+							case I_WLEAF: case I_WHEAD: case I_WTAIL: case I_RANGE: case I_VOUT:
+							case I_PHASOR: case I_WOSC: ++np; break;
 							case I_LINE: if (in.d) ++np; break;
-							case I_ENTER: case I_VPAN: case I_END: break;
+							case I_ENTER: case I_VPAN: case I_END: case I_PMA: case I_MIX: case I_LEAVE: break;
 							default: fast = false; break;
 							}
 						}
@@ -683,12 +766,18 @@ extern "C" saugen_Generator *saugen_create(const sauabi_Program *prg, uint32_t s
 	vev_off[prg->vo_count] = (uint32_t) vev_idx.size();
 
 	/* ---- device allocation: one state block, one row block, one pinned block ---- */
+	lap(0);
 	CK(cudaSetDevice(o->device));
 	if (opt->stream) o->stream = (cudaStream_t) opt->stream;
-	else { CK(cudaStreamCreateWithFlags(&o->stream, cudaStreamNonBlocking)); o->own_stream = true; }
+	else {
+		o->stream = g_streams.get(o->device);
+		if (!o->stream) { set_err("saugen_create: stream", cudaGetLastError()); goto fail; }
+		o->own_stream = true;
+	}
 	o->d_tables = get_device_tables(o->device, tables, &o->d_coefs);
 	if (!o->d_tables) { set_err("wave table upload", cudaGetLastError()); goto fail; }
 	{
+		lap(1);
 		const size_t nops = prg->op_count ? prg->op_count : 1, nvo = prg->vo_count ? prg->vo_count : 1;
 		const size_t nl = o->nlv ? o->nlv : 1;
 		o->seg_cap = 64;
@@ -734,6 +823,7 @@ extern "C" saugen_Generator *saugen_create(const sauabi_Program *prg, uint32_t s
 		float *rows = (float*) o->take(false, 2 * nl * (size_t) o->row_stride * sizeof(float));
 		if (!rows) { set_err("saugen_create: device memory (carrier rows)", cudaGetLastError()); goto fail; }
 		o->d_rows_s = rows; o->d_rows_r = rows + nl * (size_t) o->row_stride;
+		lap(2);
 		Carver hv;
 		const size_t h_status = hv.take((1 + o->seg_cap) * sizeof(uint32_t));
 		const size_t h_pcm = hv.take(2 * (size_t) o->row_len * sizeof(int16_t));
@@ -747,7 +837,8 @@ extern "C" saugen_Generator *saugen_create(const sauabi_Program *prg, uint32_t s
 		o->h_status = (uint32_t*) (hb + h_status); o->h_pcm = (int16_t*) (hb + h_pcm);
 		o->h_call = (CallDesc*) (hb + h_call); o->h_segs = (SegDesc*) (hb + h_segs);
 		o->h_units = (UnitDesc*) (hb + h_units);
-		for (int i = 0; i < 3; ++i) CK(cudaEventCreate(&o->ev_t[i]));
+		lap(3);
+		lap(4);
 
 		GenDesc &d = o->h_desc;
 		memset(&d, 0, sizeof d);
@@ -781,6 +872,8 @@ extern "C" saugen_Generator *saugen_create(const sauabi_Program *prg, uint32_t s
 		CK(cudaMemcpyAsync(base, img.data(), static_bytes, cudaMemcpyHostToDevice, o->stream));
 		CK(cudaMemsetAsync(base + o_ops, 0, zero_bytes, o->stream));
 		CK(cudaStreamSynchronize(o->stream));
+		lap(5);
+		if (g_cprof.on) g_cprof.n++;
 	}
 	return o;
 fail:
@@ -794,7 +887,7 @@ extern "C" void saugen_destroy(saugen_Generator *o) {
 	if (o->stream) cudaStreamSynchronize(o->stream);
 	for (auto &b : o->blocks) g_pool.release(b.second, o->device, b.first);
 	for (int i = 0; i < 3; ++i) if (o->ev_t[i]) cudaEventDestroy(o->ev_t[i]);
-	if (o->own_stream && o->stream) cudaStreamDestroy(o->stream);
+	if (o->own_stream && o->stream) g_streams.put(o->device, o->stream);
 	delete o;
 }
 
@@ -1265,6 +1358,11 @@ extern "C" int saugen_counters(saugen_Generator *o, uint64_t out[4]) {
 /* Per-kernel device time: CUDA events on the launch stream around each kernel. */
 extern "C" int saugen_set_timing(saugen_Generator *o, int on) {
 	if (!o) return -1;
+	if (on && !o->ev_t[0]) {                 /* the events exist only for timed generators */
+		cudaSetDevice(o->device);
+		for (int i = 0; i < 3; ++i)
+			if (cudaEventCreate(&o->ev_t[i]) != cudaSuccess) { set_err("saugen_set_timing", cudaGetLastError()); return -1; }
+	}
 	o->timing = on != 0;
 	o->render_ms = o->mix_ms = 0.0;
 	return 0;

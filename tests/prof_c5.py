@@ -12,6 +12,9 @@ from oracle import pyref, pyport
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 512
 group = int(sys.argv[2]) if len(sys.argv) > 2 else 256
+threads = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+use_sink = len(sys.argv) > 4 and sys.argv[4] == "sink"
+call_len = int(sys.argv[5]) if len(sys.argv) > 5 else None
 t = pyport.ref_tables()
 tabs = saugns_b200.WaveTables.from_buffer_copy(bytes(t))
 tabs._keep = t
@@ -61,9 +64,10 @@ class Wrap:
 
 G.lib = lambda: Wrap()
 t0 = time.perf_counter()
-out = batch.render_batch(prgs, srate=96000, tables=tabs, group_size=group)
+out = batch.render_batch(prgs, srate=96000, tables=tabs, group_size=group, threads=threads, call_len=call_len,
+                         sink=(lambda i, pcm: None) if use_sink else None)
 wall = time.perf_counter() - t0
-print(f"scripts {n} group {group} wall {wall:.3f}s -> {n / wall:.1f} scripts/s")
+print(f"scripts {n} group {group} threads {threads} sink {use_sink} call_len {call_len} wall {wall:.3f}s -> {n / wall:.1f} scripts/s")
 for k, v in acc.items():
     print(f"  {k:10s} {v:.3f}")
 print("  other (python)", wall - acc["create"] - acc["run_many"] - acc["close"])
