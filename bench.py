@@ -308,8 +308,12 @@ def run_gpu_arm(args):
         pass
     peak = peaks.get("hbm_gbs", 6650.0)
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650"
-    # algorithmic bytes: 8 B per voice-sample x voice-samples per launch
-    alg_bytes = 8.0 * vs_step
+    # algorithmic bytes (8 B per voice-sample = one f32 carrier store by the
+    # render kernel + one f32 load by the mix kernel; pans are constant in C3, so no r rows):
+    # 4 B per voice-sample for EACH of the two kernels' launches
+    alg_bytes = 4.0 * vs_step
+    mix_s = (mix_ms / K) / 1000.0
+    mix_alg = 4.0 * vs_step + 4.0 * FRAMES
     rk_s = (render_ms / K) / 1000.0
     achieved = alg_bytes / rk_s / 1e9
     prof = {}
@@ -342,6 +346,9 @@ def run_gpu_arm(args):
                      "kernel": "render_kernel", "kernel_ms_per_launch": render_ms / K,
                      "mix_kernel_ms_per_launch": mix_ms / K, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes,
+                     "mix_kernel": {"bound": "hbm", "achieved": mix_alg / mix_s / 1e9, "peak": peak,
+                                    "unit": "GB/s", "frac": mix_alg / mix_s / 1e9 / peak,
+                                    "algorithmic_bytes_per_launch": mix_alg},
                      "note": "path is issue-/FP64-pipe-bound, not HBM-bound (SURVEY.md 8d); "
                              "issue-slot figures from ncu in profiles/",
                      "issue_slot_frac_ncu": prof.get("issue_slot_frac"),

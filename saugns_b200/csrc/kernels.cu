@@ -1483,16 +1483,23 @@ __device__ __noinline__ uint32_t run_chunk(Ctx &c, const Instr *code, uint32_t c
  * Supported bytecode: the wave-operator forms (HEAD/TAIL/LEAF, ENTER + LINE +
  * RANGE for FM carriers), static pan; anything else makes steady_check fail. */
 
-/* a run line is steady over the next 1024 samples */
-__device__ __forceinline__ bool line_steady(const OpState *o, int li) {
+/* For how many whole 1024-sample blocks, at most `k`, a run line stays steady: it
+ * holds its value, or is on a trajectory that ends after them with no ratio
+ * reconciliation due (line.c:358-369).  0 = not even one. */
+__device__ __forceinline__ uint32_t line_span(const OpState *o, int li, uint32_t k) {
 	const uint32_t flags = LM_FLAGS(o->lmeta[li]);
-	if (!(flags & SAUABI_LINEP_GOAL)) return true;
+	if (!(flags & SAUABI_LINEP_GOAL)) return k;
 	const bool gr = (flags & SAUABI_LINEP_GOAL_RATIO) != 0, sr = (flags & SAUABI_LINEP_STATE_RATIO) != 0;
 	const uint32_t pos = o->line[li].pos, end = o->line[li].end;
-	return gr == sr && pos < end && end - pos > (uint32_t) REF_BLOCK;
+	if (gr != sr || pos >= end) return 0;
+	const uint32_t a = (end - pos - 1u) / (uint32_t) REF_BLOCK;      /* end - pos > a * 1024 */
+	return a < k ? a : k;
 }
-__device__ __forceinline__ bool op_outlasts_block(const OpState *o) {
-	return (o->flags & ON_TIME_INF) || o->time >= (uint32_t) REF_BLOCK;
+/* ... and an operator keeps running (run_block, generator.c:694-698) */
+__device__ __forceinline__ uint32_t op_span(const OpState *o, uint32_t k) {
+	if (o->flags & ON_TIME_INF) return k;
+	const uint32_t a = o->time / (uint32_t) REF_BLOCK;
+	return a < k ? a : k;
 }
 
 /* ---- block plan ---------------------------------------------------------- *
@@ -1526,9 +1533,12 @@ __device__ __forceinline__ void plan_put(uint32_t plan, uint32_t n, uint32_t w0,
 	sts128(a + 16, make_float4(w4, w5, w6, w7));
 }
 
-/* returns the number of plan records; 0 = not a steady block (or no room) */
+/* kb = the whole blocks ahead in this unit.  Returns blocks << 16 | records: how
+ * many of those blocks are steady as ONE stretch (the plan holds for all of them:
+ * nothing in it depends on the block), and the number of plan records; 0 = the
+ * next block is not steady (or there is no room for its plan). */
 __device__ __noinline__ uint32_t steady_plan(OpState *sops, uint32_t so, uint32_t st, uint32_t wave_mask,
-		const WaveCoeffs *wc, const Instr *code, uint32_t code_len, uint32_t plan, uint32_t cap) {
+		const WaveCoeffs *wc, const Instr *code, uint32_t code_len, uint32_t plan, uint32_t cap, uint32_t kb) {
 	uint32_t seen = 0;         /* operator slots already visited (< 32 of them) */
 	uint32_t uni = 0;          /* work buffers (< 32) holding one value over the block */
 	uint32_t n = 0;
@@ -1549,13 +1559,13 @@ __device__ __noinline__ uint32_t steady_plan(OpState *sops, uint32_t so, uint32_
 		case I_WHEAD: head = true; break;
 		case I_WTAIL: tail = true; break;
 		case I_ENTER:
-			if (o->type != SAUABI_POPT_wave || !op_outlasts_block(o)) return 0;
+			if (o->type != SAUABI_POPT_wave || !(kb = op_span(o, kb))) return 0;
 			if (in.op >= 32 || (seen & (1u << in.op))) return 0;
 			seen |= 1u << in.op;
 			break;
 		case I_LINE:
 			if (in.d) {
-				if (!line_steady(o, in.c)) return 0;
+				if (!(kb = line_span(o, in.c, kb))) return 0;
 				const uint32_t lf = LM_FLAGS(o->lmeta[in.c]);
 				const bool ratio = in.b != NO_BUF && (lf & SAUABI_LINEP_STATE_RATIO);
 				const bool u = !(lf & SAUABI_LINEP_GOAL) && (!ratio || (in.b < 32 && ((uni >> in.b) & 1u)));
@@ -1573,9 +1583,9 @@ __device__ __noinline__ uint32_t steady_plan(OpState *sops, uint32_t so, uint32_
 		case I_VOUT:
 			plan_put(plan, n++, P_VOUT | (uint32_t) in.a << 16 | (uint32_t) in.b << 24, 0u, opa, 0u,
 					0.f, 0.f, 0.f, 0.f);
-			return n;
+			return kb << 16 | n;
 		case I_END:
-			return n;
+			return n ? kb << 16 | n : 0u;
 		case I_VPAN:
 			if (in.d || (LM_FLAGS(o->lmeta[LINE_PAN]) & SAUABI_LINEP_GOAL)) return 0;
 			break;
@@ -1621,7 +1631,7 @@ __device__ __noinline__ uint32_t steady_plan(OpState *sops, uint32_t so, uint32_
 		if (head) {
 			if (in.op >= 32 || (seen & (1u << in.op))) return 0;
 			seen |= 1u << in.op;
-			if (!op_outlasts_block(o) || !line_steady(o, LINE_FREQ)) return 0;
+			if (!(kb = op_span(o, kb)) || !(kb = line_span(o, LINE_FREQ, kb))) return 0;
 			const uint32_t lf = LM_FLAGS(o->lmeta[LINE_FREQ]);
 			fmul = in.e != NO_BUF && (lf & SAUABI_LINEP_STATE_RATIO);
 			funi = !(lf & SAUABI_LINEP_GOAL) && (!fmul || (in.e < 32 && ((uni >> in.e) & 1u)));
@@ -1635,7 +1645,7 @@ __device__ __noinline__ uint32_t steady_plan(OpState *sops, uint32_t so, uint32_
 		}
 		if (tail) {
 			if (in.d != NO_BUF) return 0;                           /* fPM: general path */
-			if (!op_outlasts_block(o) || !line_steady(o, LINE_AMP)) return 0;
+			if (!(kb = op_span(o, kb)) || !(kb = line_span(o, LINE_AMP, kb))) return 0;
 			if (o->oscflags & OSC_RESET_DIFF) return 0;
 			if (in.flags & F_MAY_SELFMOD) {                          /* generator.c:485-490 */
 				if (o->line[LINE_PMA].v0 != 0.f ||
@@ -1655,25 +1665,30 @@ __device__ __noinline__ uint32_t steady_plan(OpState *sops, uint32_t so, uint32_
 			if (in.a < 32) uni &= ~(1u << in.a);
 		}
 	}
-	return n;
+	return n ? kb << 16 | n : 0u;
 }
 
-/* sauLine_run's bookkeeping for one whole block of a steady run line */
-__device__ __forceinline__ void line_block_update(OpState *o, int li) {
+/* sauLine_run's bookkeeping for nb whole blocks of a steady run line, block by block */
+__device__ __forceinline__ void line_block_update(OpState *o, int li, uint32_t nb) {
 	const uint32_t meta = o->lmeta[li];
 	uint32_t flags = LM_FLAGS(meta), pos = o->line[li].pos;
 	if (flags & SAUABI_LINEP_GOAL) {
-		pos += REF_BLOCK;
+		pos += nb * (uint32_t) REF_BLOCK;
 	} else {
-		bool ex;
-		line_advance(pos, o->line[li].end, flags, REF_BLOCK, ex);
+		for (uint32_t b = 0; b < nb; ++b) {
+			bool ex;
+			line_advance(pos, o->line[li].end, flags, REF_BLOCK, ex);
+		}
 	}
 	o->line[li].pos = pos;
 	o->lmeta[li] = LM_PACK(LM_TYPE(meta), flags, 0u);
 }
+__device__ __forceinline__ void line_skip_blocks(OpState *o, int li, uint32_t nb) {
+	for (uint32_t b = 0; b < nb; ++b) line_skip(0, 0, o, li, REF_BLOCK);
+}
 
 /* lane 0 only */
-__device__ __noinline__ void steady_update(OpState *sops, const Instr *code, uint32_t code_len) {
+__device__ __noinline__ void steady_update(OpState *sops, const Instr *code, uint32_t code_len, uint32_t nb) {
 	uint4 raw_next = __ldg(reinterpret_cast<const uint4*>(code));
 	for (uint32_t pc = 0; pc < code_len; ++pc) {
 		const uint4 raw = raw_next;
@@ -1687,33 +1702,33 @@ __device__ __noinline__ void steady_update(OpState *sops, const Instr *code, uin
 		case I_WHEAD: head = true; break;
 		case I_WTAIL: tail = true; break;
 		case I_LINE:
-			if (in.d) line_block_update(o, in.c);
-			else line_skip(0, 0, o, in.c, REF_BLOCK);
+			if (in.d) line_block_update(o, in.c, nb);
+			else line_skip_blocks(o, in.c, nb);
 			break;
 		case I_VPAN:
-			line_skip(0, 0, o, LINE_PAN, REF_BLOCK);
+			line_skip_blocks(o, LINE_PAN, nb);
 			break;
 		case I_PMA:                /* not run in a steady block (steady_plan) */
-			line_skip(0, 0, o, LINE_PMA, REF_BLOCK);
+			line_skip_blocks(o, LINE_PMA, nb);
 			o->flags &= ~ON_PMA_RUN;
 			break;
 		case I_LEAVE:              /* unfused wave operator, generator.c:726-727 */
-			if (!(o->flags & ON_TIME_INF)) o->time -= REF_BLOCK;
+			if (!(o->flags & ON_TIME_INF)) o->time -= nb * (uint32_t) REF_BLOCK;
 			break;
 		default: break;
 		}
 		if (head) {
-			line_block_update(o, LINE_FREQ);
-			if (in.flags & F_SKIP_FREQ2) line_skip(0, 0, o, LINE_FREQ2, REF_BLOCK);
+			line_block_update(o, LINE_FREQ, nb);
+			if (in.flags & F_SKIP_FREQ2) line_skip_blocks(o, LINE_FREQ2, nb);
 		}
 		if (tail) {
-			line_block_update(o, LINE_AMP);
-			if (in.flags & F_SKIP_AMP2) line_skip(0, 0, o, LINE_AMP2, REF_BLOCK);
+			line_block_update(o, LINE_AMP, nb);
+			if (in.flags & F_SKIP_AMP2) line_skip_blocks(o, LINE_AMP2, nb);
 			if (in.flags & F_MAY_SELFMOD) {
-				line_skip(0, 0, o, LINE_PMA, REF_BLOCK);
+				line_skip_blocks(o, LINE_PMA, nb);
 				o->flags &= ~ON_PMA_RUN;
 			}
-			if (!(o->flags & ON_TIME_INF)) o->time -= REF_BLOCK;   /* generator.c:726-727 */
+			if (!(o->flags & ON_TIME_INF)) o->time -= nb * (uint32_t) REF_BLOCK;   /* generator.c:726-727 */
 		}
 	}
 }
@@ -2214,10 +2229,10 @@ __device__ __forceinline__ void run_chunk_plan(const HotCtx &c, const uint32_t n
  * own register allocation whatever the general path around the call needs. */
 template <bool CTAB>
 __device__ __noinline__ void run_block_fast(uint32_t sb, uint32_t plan, int lane, float coeff, uint32_t nrec,
-		float *row_s, float *row_r) {
+		uint32_t len, float *row_s, float *row_r) {
 	HotCtx c;
 	c.sb = sb; c.plan = plan; c.lane = lane; c.coeff = coeff;
-	for (uint32_t oc = 0; oc < (uint32_t) REF_BLOCK; oc += FastCfg<FAST_NS>::CHUNKF) {
+	for (uint32_t oc = 0; oc < len; oc += FastCfg<FAST_NS>::CHUNKF) {
 		c.oc = oc;
 		run_chunk_plan<FAST_NS, CTAB>(c, nrec, row_s + oc, row_r + oc);
 	}
@@ -2316,13 +2331,19 @@ __device__ __noinline__ void render_units(Ctx &c, FastCtx &fc, const CallDesc *c
 		uint32_t run_total = 0;
 		const uint32_t uend = ud.off + ud.len;
 		for (uint32_t off = ud.off; off < uend && vs.duration != 0; off += CHUNK) {
-			/* a whole reference block in steady state: the fast path */
-			uint32_t nrec;
+			/* whole reference blocks in steady state: the fast path, for as many of the
+			 * unit's blocks as one plan holds */
+			uint32_t sp = 0;
 			if (off % REF_BLOCK == 0 && uend - off >= (uint32_t) REF_BLOCK &&
 					vs.duration >= (uint32_t) REF_BLOCK && vs.code_len &&
-					op_ptr(c, vs.carr_slot)->time > 0 &&
-					(nrec = steady_plan(c.sops, fc.so, fc.st, fc.wave_mask, fc.wc, g->code + vs.code_off,
-							vs.code_len, fc.plan, fc.plan_cap)) != 0) {
+					op_ptr(c, vs.carr_slot)->time > 0) {
+				uint32_t kb = (uend - off) / (uint32_t) REF_BLOCK;
+				if (vs.duration / (uint32_t) REF_BLOCK < kb) kb = vs.duration / (uint32_t) REF_BLOCK;
+				sp = steady_plan(c.sops, fc.so, fc.st, fc.wave_mask, fc.wc, g->code + vs.code_off,
+						vs.code_len, fc.plan, fc.plan_cap, kb);
+			}
+			if (sp) {
+				const uint32_t nrec = sp & 0xffffu, nb = sp >> 16, span = nb * (uint32_t) REF_BLOCK;
 				if (pan_mode == PAN_UNSET)       /* steady => the pan stands still */
 					pan_mode = __float_as_uint(op_ptr(c, vs.carr_slot)->line[LINE_PAN].v0);
 				{
@@ -2333,17 +2354,17 @@ __device__ __noinline__ void render_units(Ctx &c, FastCtx &fc, const CallDesc *c
 					__syncwarp();
 				}
 				if (fc.wave_mask & CTAB_FLAG)
-					run_block_fast<true>(fc.sb, fc.plan, lane, fc.coeff, nrec,
+					run_block_fast<true>(fc.sb, fc.plan, lane, fc.coeff, nrec, span,
 							row_s + sd.start + off, row_r + sd.start + off);
 				else
-					run_block_fast<false>(fc.sb, fc.plan, lane, fc.coeff, nrec,
+					run_block_fast<false>(fc.sb, fc.plan, lane, fc.coeff, nrec, span,
 							row_s + sd.start + off, row_r + sd.start + off);
 				__syncwarp();
-				if (lane == 0) steady_update(c.sops, g->code + vs.code_off, vs.code_len);
+				if (lane == 0) steady_update(c.sops, g->code + vs.code_off, vs.code_len, nb);
 				__syncwarp();
-				vs.duration -= REF_BLOCK;
-				run_total += REF_BLOCK;
-				off += REF_BLOCK - CHUNK;
+				vs.duration -= span;
+				run_total += span;
+				off += span - CHUNK;
 				continue;
 			}
 			uint32_t clen = uend - off;

@@ -1041,7 +1041,9 @@ static int run_common(saugen_Generator *o, size_t buf_len, int stereo, uint32_t 
 			if (getenv("SAUGEN_ONE_CTA")) ticketed_ctas = 1;
 		}
 	}
-	plan_units(segs, o->units_tmp, sched_mode == 2 ? 1 : 4);
+	/* one warp per voice: a unit is a whole segment (the steady-block plan then covers
+	 * it in one stretch); ticketed: 4 blocks; balanced: 1 */
+	plan_units(segs, o->units_tmp, sched_mode == 2 ? 1 : sched_mode == 1 ? 4 : (1u << 20));
 	if (o->units_tmp.size() > o->unit_cap) {
 		uint32_t cap = o->unit_cap;
 		while (cap < o->units_tmp.size()) cap *= 2;
@@ -1200,7 +1202,7 @@ extern "C" int saugen_run_many(saugen_Generator *const *gens, size_t n, int16_t 
 		CallDesc cd;
 		cd.gen = o->d_desc; cd.call_len = (uint32_t) buf_len; cd.nseg = (uint32_t) o->segs_tmp.size();
 		cd.seg_off = (uint32_t) segs.size(); cd.task_base = ntasks; cd.stereo = stereo ? 1 : 0; cd._pad = 0;
-		plan_units(o->segs_tmp, o->units_tmp);
+		plan_units(o->segs_tmp, o->units_tmp, 1u << 20);
 		cd.unit_off = (uint32_t) units.size(); cd.nunits = (uint32_t) o->units_tmp.size();
 		units.insert(units.end(), o->units_tmp.begin(), o->units_tmp.end());
 		if (o->compact) cudaMemsetAsync(o->d_vlen, 0, o->zero_bytes, g0->stream);

@@ -42,7 +42,13 @@ def test_render_batch_matches_reference(ref, port):
     tabs = gpuutil.ref_tables_for_gpu(port)
     prgs = [ref.Program(scripts.synth_c5_script(i)) for i in range(40)]
     got = batch.render_batch(prgs, srate=96000, tables=tabs, group_size=16)
+    # several driver threads, longer calls, streaming sink with recycled arrays
+    sunk = {}
+    none = batch.render_batch(prgs, srate=96000, tables=tabs, group_size=8, threads=3,
+                              call_len=4 * 24576, sink=lambda i, pcm: sunk.__setitem__(i, pcm.copy()))
+    assert none == [None] * len(prgs) and len(sunk) == len(prgs)
     for i, p in enumerate(prgs):
         want = ref.render(p, srate=96000)
         assert got[i].shape == want.shape, i
         assert np.array_equal(got[i], want), i
+        assert np.array_equal(sunk[i], want), i
