@@ -1517,14 +1517,15 @@ __device__ __forceinline__ uint32_t op_span(const OpState *o, uint32_t k) {
 enum : uint32_t { P_LINE = 1, P_WHEAD, P_WTAIL, P_WLEAF, P_PHASE, P_WOSC, P_RANGE, P_VOUT };
 enum : uint32_t {
 	PF_LAYER = 1, PF_WAVEENV = 2,
-	PF_FUNI = 4,       /* frequency (or the LINE's value) is uniform over the block */
-	PF_FMUL = 8,       /* ... and is v0 times the (uniform) multiplier buffer */
+	PF_FUNI = 4,       /* frequency (or the LINE's value) is uniform over the block: w6 holds the
+	                    * value (LINE, WHEAD) or the phase increment (WTAIL, WLEAF, PHASE) */
 	PF_ACONST = 16,    /* amplitude line holds av */
 	PF_ABUF = 32,      /* amplitude comes from work buffer c (the operator has amplitude modulators) */
 };
+constexpr uint32_t PLAN_FBUF = 32 * FAST_NS * 4;    /* FastCfg<FAST_NS>::FBUF_BYTES */
 constexpr uint32_t PLAN_REC = 32;     /* bytes: w0 kind|flags<<8|a<<16|b<<24, w1 c|e<<8|line<<16,
                                        * w2 operator state (shared address), w3 table (shared address),
-                                       * w4 diff_scale, w5 diff_offset, w6 v0 of the frequency / LINE, w7 av */
+                                       * w4 diff_scale, w5 diff_offset, w6 uniform value / phase increment, w7 av */
 
 __device__ __forceinline__ void plan_put(uint32_t plan, uint32_t n, uint32_t w0, uint32_t w1, uint32_t w2,
 		uint32_t w3, float w4, float w5, float w6, float w7) {
@@ -1538,12 +1539,56 @@ __device__ __forceinline__ void plan_put(uint32_t plan, uint32_t n, uint32_t w0,
  * nothing in it depends on the block), and the number of plan records; 0 = the
  * next block is not steady (or there is no room for its plan). */
 __device__ __noinline__ uint32_t steady_plan(OpState *sops, uint32_t so, uint32_t st, uint32_t wave_mask,
-		const WaveCoeffs *wc, const Instr *code, uint32_t code_len, uint32_t plan, uint32_t cap, uint32_t kb) {
+		const WaveCoeffs *wc, const Instr *code, uint32_t code_len, uint32_t plan, uint32_t cap, uint32_t kb,
+		uint32_t sb, float coeff) {
 	uint32_t seen = 0;         /* operator slots already visited (< 32 of them) */
 	uint32_t uni = 0;          /* work buffers (< 32) holding one value over the block */
+	/* A uniform value is known NOW: it is kept in the buffer's own first word (every
+	 * lane in its own slot) while the plan is built, so that a child's ratio
+	 * frequency and the operator's phase increment are worked out here, once.  A
+	 * frequency buffer that nothing reads as a vector before its operator's phase
+	 * fill (need) then has no per-chunk use at all: its HEAD record is dropped. */
+	uint32_t need = 0;
+	uint8_t head_rec[32];
+	uint32_t killed = 0;
 	uint32_t n = 0;
 	plan += PLAN_REC;          /* slot 0 is the header (render_units) */
 	if (cap) --cap;
+	auto is_uni = [&](uint32_t b) { return b < 32 && ((uni >> b) & 1u); };
+	auto touch = [&](uint32_t b) { if (b < 32) need |= 1u << b; };            /* read as a vector */
+	auto dirty = [&](uint32_t b) { if (b < 32) { uni &= ~(1u << b); need |= 1u << b; } };   /* rewritten */
+	auto uval = [&](uint32_t b) { return lds32f(sb + b * PLAN_FBUF); };
+	auto set_uni = [&](uint32_t b, float f) {
+		if (b < 32) { uni |= 1u << b; need &= ~(1u << b); sts32(sb + b * PLAN_FBUF, __float_as_uint(f)); }
+	};
+	auto finish = [&](uint32_t nrec) -> uint32_t {
+		if (!nrec) return 0u;
+		if (killed) {                              /* close the gaps the dropped records left */
+			uint32_t w = 0;
+			for (uint32_t r = 0; r < nrec; ++r) {
+				const uint4 x = lds128u(plan + r * PLAN_REC), y = lds128u(plan + r * PLAN_REC + 16);
+				__syncwarp();
+				if ((x.x & 0xffu) == 0u) continue;
+				if (w != r) {
+					asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(plan + w * PLAN_REC),
+							"r"(x.x), "r"(x.y), "r"(x.z), "r"(x.w) : "memory");
+					asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(plan + w * PLAN_REC + 16),
+							"r"(y.x), "r"(y.y), "r"(y.z), "r"(y.w) : "memory");
+				}
+				++w;
+			}
+			__syncwarp();
+			nrec = w;
+		}
+		return kb << 16 | nrec;
+	};
+	/* the operator's phase fill takes its frequency from uniform buffer b: the
+	 * increment is known, and the HEAD that filled b may have nothing left to do */
+	auto uni_inc = [&](uint32_t b) -> uint32_t {
+		const uint32_t inc = ftoi_lo32(coeff * uval(b));
+		if (!((need >> b) & 1u)) { sts32(plan + head_rec[b] * PLAN_REC, 0u); ++killed; }
+		return inc;
+	};
 	uint4 raw_next = __ldg(reinterpret_cast<const uint4*>(code));
 	for (uint32_t pc = 0; pc < code_len; ++pc) {
 		const uint4 raw = raw_next;
@@ -1568,24 +1613,28 @@ __device__ __noinline__ uint32_t steady_plan(OpState *sops, uint32_t so, uint32_
 				if (!(kb = line_span(o, in.c, kb))) return 0;
 				const uint32_t lf = LM_FLAGS(o->lmeta[in.c]);
 				const bool ratio = in.b != NO_BUF && (lf & SAUABI_LINEP_STATE_RATIO);
-				const bool u = !(lf & SAUABI_LINEP_GOAL) && (!ratio || (in.b < 32 && ((uni >> in.b) & 1u)));
-				plan_put(plan, n++, P_LINE | ((u ? PF_FUNI : 0u) | (u && ratio ? PF_FMUL : 0u)) << 8 |
+				const bool u = !(lf & SAUABI_LINEP_GOAL) && (!ratio || is_uni(in.b));
+				float f = o->line[in.c].v0;
+				if (u && ratio) f = f * uval(in.b);
+				if (!u && in.b != NO_BUF) touch(in.b);
+				plan_put(plan, n++, P_LINE | (u ? PF_FUNI : 0u) << 8 |
 						(uint32_t) in.a << 16 | (uint32_t) in.b << 24, (uint32_t) in.c << 16, opa, 0u,
-						0.f, 0.f, o->line[in.c].v0, 0.f);
-				if (in.a < 32) uni = u ? uni | (1u << in.a) : uni & ~(1u << in.a);
+						0.f, 0.f, f, 0.f);
+				dirty(in.a);
+				if (u) { set_uni(in.a, f); touch(in.a); }     /* LINE records are never dropped */
 			}
 			break;
 		case I_RANGE:
 			plan_put(plan, n++, P_RANGE | (uint32_t) in.a << 16 | (uint32_t) in.b << 24, in.c, 0u, 0u,
 					0.f, 0.f, 0.f, 0.f);
-			if (in.a < 32) uni &= ~(1u << in.a);
+			dirty(in.a); touch(in.b); touch(in.c);
 			break;
 		case I_VOUT:
 			plan_put(plan, n++, P_VOUT | (uint32_t) in.a << 16 | (uint32_t) in.b << 24, 0u, opa, 0u,
 					0.f, 0.f, 0.f, 0.f);
-			return kb << 16 | n;
+			return finish(n);
 		case I_END:
-			return n ? kb << 16 | n : 0u;
+			return finish(n);
 		case I_VPAN:
 			if (in.d || (LM_FLAGS(o->lmeta[LINE_PAN]) & SAUABI_LINEP_GOAL)) return 0;
 			break;
@@ -1595,9 +1644,15 @@ __device__ __noinline__ uint32_t steady_plan(OpState *sops, uint32_t so, uint32_
 		case I_PHASOR:
 			if (in.d != NO_BUF) return 0;                            /* fPM: general path */
 			if (o->oscflags & OSC_RESET_DIFF) return 0;
-			plan_put(plan, n++, P_PHASE | ((in.b < 32 && ((uni >> in.b) & 1u)) ? PF_FUNI : 0u) << 8 |
-					(uint32_t) in.a << 16 | (uint32_t) in.b << 24, (uint32_t) in.c, opa, 0u, 0.f, 0.f, 0.f, 0.f);
-			if (in.a < 32) uni &= ~(1u << in.a);
+			{
+				const bool u = is_uni(in.b);
+				const uint32_t inc = u ? uni_inc(in.b) : 0u;
+				if (!u) touch(in.b);
+				if (in.c != NO_BUF) touch(in.c);
+				plan_put(plan, n++, P_PHASE | (u ? PF_FUNI : 0u) << 8 | (uint32_t) in.a << 16 | (uint32_t) in.b << 24,
+						(uint32_t) in.c, opa, 0u, 0.f, 0.f, __uint_as_float(inc), 0.f);
+				dirty(in.a);
+			}
 			break;
 		case I_PMA:                                                  /* generator.c:485-490 */
 			if (o->line[LINE_PMA].v0 != 0.f ||
@@ -1618,8 +1673,7 @@ __device__ __noinline__ uint32_t steady_plan(OpState *sops, uint32_t so, uint32_
 				((mix.flags & F_WAVEENV) ? PF_WAVEENV : 0u) | PF_ABUF;
 			plan_put(plan, n++, P_WOSC | fl << 8 | (uint32_t) mix.a << 16 | (uint32_t) in.b << 24,
 					(uint32_t) mix.c, opa, ct, wc->diff_scale[wave], wc->diff_offset[wave], 0.f, 0.f);
-			if (mix.a < 32) uni &= ~(1u << mix.a);
-			if (in.a < 32) uni &= ~(1u << in.a);
+			dirty(mix.a); dirty(in.a); touch(in.b); touch(mix.c);
 			/* MIX and LEAVE are part of the record */
 			pc += 2;
 			if (pc + 1 < code_len) raw_next = __ldg(reinterpret_cast<const uint4*>(code + pc + 1));
@@ -1627,20 +1681,24 @@ __device__ __noinline__ uint32_t steady_plan(OpState *sops, uint32_t so, uint32_
 		default:
 			return 0;
 		}
-		bool funi = false, fmul = false;
+		bool funi = false;
+		float fval = 0.f;          /* the uniform frequency of a HEAD / LEAF */
 		if (head) {
 			if (in.op >= 32 || (seen & (1u << in.op))) return 0;
 			seen |= 1u << in.op;
 			if (!(kb = op_span(o, kb)) || !(kb = line_span(o, LINE_FREQ, kb))) return 0;
 			const uint32_t lf = LM_FLAGS(o->lmeta[LINE_FREQ]);
-			fmul = in.e != NO_BUF && (lf & SAUABI_LINEP_STATE_RATIO);
-			funi = !(lf & SAUABI_LINEP_GOAL) && (!fmul || (in.e < 32 && ((uni >> in.e) & 1u)));
-			if (!funi) fmul = false;
+			const bool fmul = in.e != NO_BUF && (lf & SAUABI_LINEP_STATE_RATIO);
+			funi = !(lf & SAUABI_LINEP_GOAL) && (!fmul || is_uni(in.e));
+			fval = o->line[LINE_FREQ].v0;
+			if (funi && fmul) fval = fval * uval(in.e);
+			if (!funi && in.e != NO_BUF) touch(in.e);
 			if (!tail) {
-				plan_put(plan, n++, P_WHEAD | ((funi ? PF_FUNI : 0u) | (fmul ? PF_FMUL : 0u)) << 8 |
+				plan_put(plan, n++, P_WHEAD | (funi ? PF_FUNI : 0u) << 8 |
 						(uint32_t) in.b << 24, (uint32_t) in.e << 8, opa, 0u,
-						0.f, 0.f, o->line[LINE_FREQ].v0, 0.f);
-				if (in.b < 32) uni = funi ? uni | (1u << in.b) : uni & ~(1u << in.b);
+						0.f, 0.f, fval, 0.f);
+				dirty(in.b);
+				if (funi && in.b < 32) { set_uni(in.b, fval); head_rec[in.b] = (uint8_t) (n - 1); }
 			}
 		}
 		if (tail) {
@@ -1651,21 +1709,29 @@ __device__ __noinline__ uint32_t steady_plan(OpState *sops, uint32_t so, uint32_
 				if (o->line[LINE_PMA].v0 != 0.f ||
 						(LM_FLAGS(o->lmeta[LINE_PMA]) & SAUABI_LINEP_GOAL)) return 0;
 			}
-			if (!head) funi = in.b < 32 && ((uni >> in.b) & 1u);
+			uint32_t inc = 0;
+			if (!head) {
+				funi = is_uni(in.b);
+				if (funi) inc = uni_inc(in.b);
+				else touch(in.b);
+			} else if (funi) {
+				inc = ftoi_lo32(coeff * fval);
+			}
+			if (in.c != NO_BUF) touch(in.c);
 			const uint32_t wave = o->mode;
 			const uint32_t slot = __popc(wave_mask & ((1u << wave) - 1u));
 			const uint32_t ct = (wave_mask & CTAB_FLAG) ? st + slot * CTAB_WAVE_BYTES :
 				st + slot * (TAB_STRIDE * 4) + 12;                   /* planes, or &lut[-1] */
 			const bool aconst = !(LM_FLAGS(o->lmeta[LINE_AMP]) & SAUABI_LINEP_GOAL);
 			const uint32_t fl = ((in.flags & F_LAYER) ? PF_LAYER : 0u) | ((in.flags & F_WAVEENV) ? PF_WAVEENV : 0u) |
-				(funi ? PF_FUNI : 0u) | (fmul ? PF_FMUL : 0u) | (aconst ? PF_ACONST : 0u);
+				(funi ? PF_FUNI : 0u) | (aconst ? PF_ACONST : 0u);
 			plan_put(plan, n++, (head ? P_WLEAF : P_WTAIL) | fl << 8 | (uint32_t) in.a << 16 | (uint32_t) in.b << 24,
 					(uint32_t) in.c | (uint32_t) in.e << 8, opa, ct,
-					wc->diff_scale[wave], wc->diff_offset[wave], o->line[LINE_FREQ].v0, o->line[LINE_AMP].v0);
-			if (in.a < 32) uni &= ~(1u << in.a);
+					wc->diff_scale[wave], wc->diff_offset[wave], __uint_as_float(inc), o->line[LINE_AMP].v0);
+			dirty(in.a);
 		}
 	}
-	return n ? kb << 16 | n : 0u;
+	return finish(n);
 }
 
 /* sauLine_run's bookkeeping for nb whole blocks of a steady run line, block by block */
@@ -2146,16 +2212,15 @@ __device__ __forceinline__ void run_chunk_plan(const HotCtx &c, const uint32_t n
 				const bool funi = (flags & PF_FUNI) != 0;
 				float fr[NS];
 				if (kind == P_WTAIL || kind == P_PHASE) {
-					if (funi) inc = ftoi_lo32(c.coeff * lds32f(c.sb + bufb * FastCfg<NS>::FBUF_BYTES));
+					if (funi) inc = lds32(rec + 24);
 					else fld<NS>(c, bufb, fr);
 				} else {
 					const uint32_t mb = is_line ? bufb : (p0.y >> 8) & 0xffu;
 					if (funi) {
-						float f = lds32f(rec + 24);
-						if (flags & PF_FMUL) f = f * lds32f(c.sb + mb * FastCfg<NS>::FBUF_BYTES);
-						inc = ftoi_lo32(c.coeff * f);
+						const uint32_t w6 = lds32(rec + 24);
+						inc = w6;
 #pragma unroll
-						for (int k = 0; k < NS; ++k) fr[k] = f;
+						for (int k = 0; k < NS; ++k) fr[k] = __uint_as_float(w6);
 					} else {
 						float m[NS];
 						const bool has_mul = mb != NO_BUF;
@@ -2240,6 +2305,7 @@ __device__ __noinline__ void run_block_fast(uint32_t sb, uint32_t plan, int lane
 
 /* ---- render kernel ------------------------------------------------------ */
 
+static_assert(PLAN_FBUF == FastCfg<FAST_NS>::FBUF_BYTES, "plan-time scratch words sit in the fast buffers");
 constexpr uint32_t OP_VEC = sizeof(OpState) / 16;
 static_assert(sizeof(OpState) == 192, "OpState layout (device_types.h)");
 
@@ -2340,7 +2406,7 @@ __device__ __noinline__ void render_units(Ctx &c, FastCtx &fc, const CallDesc *c
 				uint32_t kb = (uend - off) / (uint32_t) REF_BLOCK;
 				if (vs.duration / (uint32_t) REF_BLOCK < kb) kb = vs.duration / (uint32_t) REF_BLOCK;
 				sp = steady_plan(c.sops, fc.so, fc.st, fc.wave_mask, fc.wc, g->code + vs.code_off,
-						vs.code_len, fc.plan, fc.plan_cap, kb);
+						vs.code_len, fc.plan, fc.plan_cap, kb, fc.sb, fc.coeff);
 			}
 			if (sp) {
 				const uint32_t nrec = sp & 0xffffu, nb = sp >> 16, span = nb * (uint32_t) REF_BLOCK;
