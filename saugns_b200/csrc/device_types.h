@@ -17,6 +17,18 @@ constexpr int WAVE_LEN = 2048;        // sau/wave.h:18-19
 constexpr int NUM_WAVES = 12;
 constexpr int MAX_NEST = 24;          // len-stack depth per warp
 constexpr uint32_t NO_BUF = 0xFF;
+/* Carrier rows of a call are stored FRAME-TILE major: tile t (frames 128 t .. 128 t + 127)
+ * holds one 512-byte piece per voice, voices side by side:
+ *     rows[(t * n_local_voices + voice) * 128 + (frame & 127)]
+ * The render kernel writes whole pieces (a chunk is 128 frames), the mix kernel reads
+ * a tile as ONE contiguous stream in voice order (it must add in voice order). */
+constexpr int ROW_TILE = 128;
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+inline size_t row_index(uint32_t frame, uint32_t tile_stride) {
+	return (size_t) (frame / ROW_TILE) * tile_stride + (frame % ROW_TILE);
+}
 
 /* sauLine run-time state (sau/line.h:115-121 minus time_ms), split so that the
  * four words a fill needs come in with one 128-bit shared-memory load. */
@@ -174,8 +186,8 @@ struct GenDesc {
 	const uint32_t *prog_ops;     // operator ids of every compiled voice program
 	const uint32_t *vev_off;      // [vo_count+1] CSR into vev_idx
 	const uint32_t *vev_idx;      // global event indices per voice, in order
-	float *rows_s, *rows_r;       // [n_local_voices][row_len] carrier rows of a call (rows_r: only
-	                              // for voices whose pan moves in the segment, see VoiceSeg)
+	float *rows_s, *rows_r;       // carrier rows of a call, frame-tile major (ROW_TILE above; rows_r:
+	                              // only for voices whose pan moves in the segment, see VoiceSeg)
 	VoiceSeg *vlen;               // [seg][n_local_voices] per segment of a call
 	uint32_t *status;             // [0]=any voice still alive, [1+seg]=per-segment max len
 	uint32_t vlen_cap;            // segments the vlen/status arrays can hold
@@ -186,7 +198,7 @@ struct GenDesc {
 	uint32_t vo_count, op_count;
 	uint32_t voice_begin, voice_end;
 	uint32_t row_len;             // frames per row (max call length)
-	uint32_t row_stride;          // floats between consecutive voice rows (padded, see create)
+	uint32_t row_stride;          // floats between consecutive frame tiles = n_local_voices * ROW_TILE
 	uint32_t nbufs;               // work buffers per voice warp
 	uint32_t srate;
 	float coeff;                  // (float)(2^32 / srate), wosc.h:30, rasg.h:27

@@ -147,6 +147,7 @@ struct Ctx {
 	int sp;
 	bool pma_flag, pan_dyn;
 	bool write_r;              // the segment's pan moves: r rows are written (VoiceSeg)
+	uint32_t tstride;          // g->row_stride: floats between frame tiles of the carrier rows
 	uint32_t last_len, last_rem;
 };
 
@@ -1295,7 +1296,7 @@ __device__ __noinline__ void apply_event(const GenDesc *g, const WaveCoeffs *wc,
 /* ---- bytecode interpreter: one chunk of one voice ----------------------- */
 
 __device__ __noinline__ uint32_t run_chunk(Ctx &c, const Instr *code, uint32_t code_len, uint32_t time,
-		uint32_t rem0, float *row_s, float *row_r) {
+		uint32_t rem0, float *row_s, float *row_r, uint32_t frame) {
 	c.sp = 0;
 	if (c.lane == 0) { c.stk_len[0] = time; c.stk_rem[0] = rem0; c.stk_layer[0] = 0; }
 	__syncwarp();
@@ -1449,14 +1450,21 @@ __device__ __noinline__ uint32_t run_chunk(Ctx &c, const Instr *code, uint32_t c
 			s.z = sv.z * amp_scale; r.z = s.z * pv.z;
 			s.w = sv.w * amp_scale; r.w = s.w * pv.w;
 			const bool wr = c.write_r || c.pan_dyn;      /* see VoiceSeg */
-			if (i0 + 3 < vn && ((reinterpret_cast<uintptr_t>(row_s + i0) & 15) == 0)) {
-				__stcs(reinterpret_cast<float4*>(row_s + i0), s);   /* coalesced 128-bit stores */
-				if (wr) __stcs(reinterpret_cast<float4*>(row_r + i0), r);
+			/* row_s / row_r: this voice's piece of frame tile 0 (device_types.h:ROW_TILE) */
+			const uint32_t fl = frame + i0;
+			if (i0 + 3 < vn && (fl & 3u) == 0) {
+				const size_t at = row_index(fl, c.tstride);
+				__stcs(reinterpret_cast<float4*>(row_s + at), s);   /* coalesced 128-bit stores */
+				if (wr) __stcs(reinterpret_cast<float4*>(row_r + at), r);
 			} else {
-				if (i0 + 0 < vn) { row_s[i0 + 0] = s.x; if (wr) row_r[i0 + 0] = r.x; }
-				if (i0 + 1 < vn) { row_s[i0 + 1] = s.y; if (wr) row_r[i0 + 1] = r.y; }
-				if (i0 + 2 < vn) { row_s[i0 + 2] = s.z; if (wr) row_r[i0 + 2] = r.z; }
-				if (i0 + 3 < vn) { row_s[i0 + 3] = s.w; if (wr) row_r[i0 + 3] = r.w; }
+				const float sa[4] = {s.x, s.y, s.z, s.w}, ra[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+				for (int k = 0; k < 4; ++k)
+					if (i0 + k < vn) {
+						const size_t at = row_index(fl + k, c.tstride);
+						row_s[at] = sa[k];
+						if (wr) row_r[at] = ra[k];
+					}
 			}
 			return vn; }
 		case I_END:
@@ -1875,7 +1883,8 @@ struct HotCtx {
 	float coeff;
 };
 /* plan header (the first 32-byte slot): the cold paths' context and VOUT's constants */
-constexpr uint32_t PH_TAB = 0, PH_WC = 8, PH_WAVE_MASK = 16, PH_AMP_SCALE = 20, PH_WRITE_R = 24;
+constexpr uint32_t PH_TAB = 0, PH_WC = 8, PH_WAVE_MASK = 16, PH_AMP_SCALE = 20, PH_WRITE_R = 24,
+	PH_TSTRIDE = 28;
 template <int NS>
 __device__ __forceinline__ void fld(const HotCtx &c, uint32_t buf, float v[NS]) {
 	const uint32_t a = c.sb + buf * FastCfg<NS>::FBUF_BYTES;
@@ -2180,18 +2189,19 @@ __device__ __forceinline__ void osc_plan(const HotCtx &c, const uint4 p0, const 
 
 /* rows not 16-byte aligned: scalar stores from the (plane-major) fast buffers */
 __device__ __noinline__ void vout_unaligned(uint32_t sbuf_s, uint32_t sbuf_r, float *row_s, float *row_r,
-		int lane, int ns, uint32_t write_r) {
+		int lane, int ns, uint32_t write_r, uint32_t frame, uint32_t tstride) {
 	for (int k = 0; k < ns; ++k) {
 		/* sample lane*ns + k sits in plane k/4, float4 slot `lane`, component k%4 */
 		const uint32_t off = (uint32_t) (k >> 2) * 512u + (uint32_t) lane * 16u + (uint32_t) (k & 3) * 4u;
-		row_s[lane * ns + k] = lds32f(sbuf_s + off);
-		if (write_r) row_r[lane * ns + k] = lds32f(sbuf_r + off);
+		const size_t at = row_index(frame + (uint32_t) (lane * ns + k), tstride);
+		row_s[at] = lds32f(sbuf_s + off);
+		if (write_r) row_r[at] = lds32f(sbuf_r + off);
 	}
 }
 
 template <int NS, bool CTAB>
 __device__ __forceinline__ void run_chunk_plan(const HotCtx &c, const uint32_t nrec,
-		float *row_s, float *row_r) {
+		float *row_s, float *row_r, const uint32_t frame) {
 	uint32_t rec = c.plan;
 	for (uint32_t r = 0; r < nrec; ++r) {
 		rec += PLAN_REC;
@@ -2258,21 +2268,21 @@ __device__ __forceinline__ void run_chunk_plan(const HotCtx &c, const uint32_t n
 			fld<NS>(c, bufa, sv);
 			const float pan = lds32f(op + OS_LINE + 16 * LINE_PAN);
 			float s[NS], rv[NS];
-#pragma unroll
 			const float amp_scale = lds32f(c.plan + PH_AMP_SCALE);
 			const uint32_t write_r = lds32(c.plan + PH_WRITE_R);
+			const uint32_t tstride = lds32(c.plan + PH_TSTRIDE);
 #pragma unroll
 			for (int k = 0; k < NS; ++k) { s[k] = sv[k] * amp_scale; rv[k] = s[k] * pan; }
-			const uint32_t i0 = c.lane * NS;
-			if ((reinterpret_cast<uintptr_t>(row_s) & 15) == 0) {
+			/* row_s / row_r: this voice's piece of frame tile 0 (device_types.h:ROW_TILE) */
+			const uint32_t fl = frame + c.lane * NS;
+			if ((frame & 3u) == 0) {
 #pragma unroll
-				for (int h = 0; h < NS / 4; ++h)                     /* 128-bit streaming stores */
-					__stcs(reinterpret_cast<float4*>(row_s + i0) + h,
+				for (int h = 0; h < NS / 4; ++h) {                   /* 128-bit streaming stores */
+					const size_t at = row_index(fl + 4 * h, tstride);
+					__stcs(reinterpret_cast<float4*>(row_s + at),
 							make_float4(s[4 * h], s[4 * h + 1], s[4 * h + 2], s[4 * h + 3]));
-				if (write_r) {
-#pragma unroll
-					for (int h = 0; h < NS / 4; ++h)
-						__stcs(reinterpret_cast<float4*>(row_r + i0) + h,
+					if (write_r)
+						__stcs(reinterpret_cast<float4*>(row_r + at),
 								make_float4(rv[4 * h], rv[4 * h + 1], rv[4 * h + 2], rv[4 * h + 3]));
 				}
 			} else {
@@ -2283,7 +2293,7 @@ __device__ __forceinline__ void run_chunk_plan(const HotCtx &c, const uint32_t n
 				__syncwarp();
 				vout_unaligned(c.sb - c.lane * 16 + bufa * FastCfg<NS>::FBUF_BYTES,
 						c.sb - c.lane * 16 + rb * FastCfg<NS>::FBUF_BYTES,
-						row_s, row_r, c.lane, NS, write_r);
+						row_s, row_r, c.lane, NS, write_r, frame, tstride);
 			}
 			return;
 		}
@@ -2294,12 +2304,12 @@ __device__ __forceinline__ void run_chunk_plan(const HotCtx &c, const uint32_t n
  * own register allocation whatever the general path around the call needs. */
 template <bool CTAB>
 __device__ __noinline__ void run_block_fast(uint32_t sb, uint32_t plan, int lane, float coeff, uint32_t nrec,
-		uint32_t len, float *row_s, float *row_r) {
+		uint32_t len, float *row_s, float *row_r, uint32_t frame) {
 	HotCtx c;
 	c.sb = sb; c.plan = plan; c.lane = lane; c.coeff = coeff;
 	for (uint32_t oc = 0; oc < len; oc += FastCfg<FAST_NS>::CHUNKF) {
 		c.oc = oc;
-		run_chunk_plan<FAST_NS, CTAB>(c, nrec, row_s + oc, row_r + oc);
+		run_chunk_plan<FAST_NS, CTAB>(c, nrec, row_s, row_r, frame + oc);
 	}
 }
 
@@ -2356,8 +2366,9 @@ __device__ __noinline__ void render_units(Ctx &c, FastCtx &fc, const CallDesc *c
 		}
 	}
 	const uint32_t ev_lo = g->vev_off[v], ev_n = g->vev_off[v + 1] - ev_lo;
-	float *row_s = g->rows_s + (size_t) lv * g->row_stride;
-	float *row_r = g->rows_r + (size_t) lv * g->row_stride;
+	float *row_s = g->rows_s + (size_t) lv * ROW_TILE;      /* the voice's piece of frame tile 0 */
+	float *row_r = g->rows_r + (size_t) lv * ROW_TILE;
+	c.tstride = g->row_stride;
 	uint32_t loaded = 0;        // operator states currently held in shared memory
 
 	for (uint32_t ui = u0; ui < u1; ++ui) {
@@ -2416,15 +2427,14 @@ __device__ __noinline__ void render_units(Ctx &c, FastCtx &fc, const CallDesc *c
 					/* plan header: what the rare paths and VOUT need */
 					const uint64_t tp = reinterpret_cast<uint64_t>(fc.tab), wp = reinterpret_cast<uint64_t>(fc.wc);
 					plan_put(fc.plan, 0, (uint32_t) tp, (uint32_t) (tp >> 32), (uint32_t) wp, (uint32_t) (wp >> 32),
-							__uint_as_float(fc.wave_mask), fc.amp_scale, __uint_as_float(fc.write_r), 0.f);
+							__uint_as_float(fc.wave_mask), fc.amp_scale, __uint_as_float(fc.write_r),
+							__uint_as_float(c.tstride));
 					__syncwarp();
 				}
 				if (fc.wave_mask & CTAB_FLAG)
-					run_block_fast<true>(fc.sb, fc.plan, lane, fc.coeff, nrec, span,
-							row_s + sd.start + off, row_r + sd.start + off);
+					run_block_fast<true>(fc.sb, fc.plan, lane, fc.coeff, nrec, span, row_s, row_r, sd.start + off);
 				else
-					run_block_fast<false>(fc.sb, fc.plan, lane, fc.coeff, nrec, span,
-							row_s + sd.start + off, row_r + sd.start + off);
+					run_block_fast<false>(fc.sb, fc.plan, lane, fc.coeff, nrec, span, row_s, row_r, sd.start + off);
 				__syncwarp();
 				if (lane == 0) steady_update(c.sops, g->code + vs.code_off, vs.code_len, nb);
 				__syncwarp();
@@ -2443,7 +2453,7 @@ __device__ __noinline__ void render_units(Ctx &c, FastCtx &fc, const CallDesc *c
 			uint32_t out_len = 0;
 			if (vs.code_len && op_ptr(c, vs.carr_slot)->time > 0)     /* run_voice, :833-846 */
 				out_len = run_chunk(c, g->code + vs.code_off, vs.code_len, time, rem0,
-						row_s + sd.start + off, row_r + sd.start + off);
+						row_s, row_r, sd.start + off);
 			__syncwarp();
 			if (out_len && pan_mode == PAN_UNSET) {
 				/* first rendered chunk of the segment decides (run_chunk wrote r if moving) */
@@ -2657,18 +2667,19 @@ render_kernel_wide(const CallDesc *calls, uint32_t ncalls, const SegDesc *segs, 
 
 /* ---- mix + clip epilogue ------------------------------------------------- */
 
-/* One CTA mixes MIX_FRAMES consecutive frames, one thread per frame: the sum
- * over voices must run in voice order in ONE thread (float addition is not
- * associative and mix_add adds voice after voice, generator.c:773-786).  The
- * voice rows stream through a ring of shared-memory stages filled by TMA bulk
- * copies (512 contiguous bytes of MIX_TV voice rows per stage, mbarrier
- * completion), issued MIX_STAGES tiles ahead of the adds, so that the HBM
- * requests are long, many and independent of the adds' dependency chain.
+/* One CTA mixes one frame tile (ROW_TILE = 128 consecutive frames), one thread
+ * per frame: the sum over voices must run in voice order in ONE thread (float
+ * addition is not associative and mix_add adds voice after voice,
+ * generator.c:773-786).  The tile's voice pieces lie side by side in HBM
+ * (device_types.h:ROW_TILE), so the CTA reads ONE contiguous stream: the
+ * producer warp moves MIX_TV voices (8 KiB) per stage with a single TMA bulk copy
+ * (cp.async.bulk + mbarrier transaction count) into a ring of MIX_STAGES
+ * stages, the four consumer warps add behind it.
  * A voice whose pan stands still contributes r = s * pan, computed here
- * (VoiceSeg); only moving pans have an r row to fetch. */
-constexpr int MIX_FRAMES = 128;                // = consumer threads (one per frame)
+ * (VoiceSeg); only moving pans have an r piece to fetch (one more bulk copy each). */
+constexpr int MIX_FRAMES = ROW_TILE;           // = consumer threads (one per frame)
 constexpr int MIX_TV = 16;                     // voices per stage
-constexpr int MIX_STAGES = 5;
+constexpr int MIX_STAGES = 6;
 constexpr int MIX_CWARPS = MIX_FRAMES / 32;    // consumer warps; one more warp produces
 struct MixSmem {
 	float s[MIX_STAGES][MIX_TV][MIX_FRAMES];
@@ -2712,7 +2723,7 @@ mix_kernel(const CallDesc *calls, const SegDesc *segs, uint32_t mode /*0 pcm, 1 
 	const uint32_t f = f0 + (producer ? 0u : tid);
 	const bool valid = !producer && f < cd->call_len;
 	const uint32_t nlv = g->voice_end - g->voice_begin;
-	const size_t stride = g->row_stride;
+	const uint32_t tstride = g->row_stride;
 	/* the segment holding each thread's frame */
 	uint32_t si = 0;
 	for (; si < cd->nseg; ++si) {
@@ -2728,7 +2739,7 @@ mix_kernel(const CallDesc *calls, const SegDesc *segs, uint32_t mode /*0 pcm, 1 
 	if (in_seg && fi < g->status[1 + si]) active = 1;
 	if (tid == 0) {
 		for (int st = 0; st < MIX_STAGES; ++st) {
-			mbar_init(&sm.full[st], 32);               /* the producer warp's lanes */
+			mbar_init(&sm.full[st], 1);                /* the producer's arrive.expect_tx */
 			mbar_init(&sm.empty[st], MIX_CWARPS);
 		}
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -2743,9 +2754,9 @@ mix_kernel(const CallDesc *calls, const SegDesc *segs, uint32_t mode /*0 pcm, 1 
 			for (uint32_t lv = 0; lv < nlv; ++lv) {
 				const uint2 v = vl[lv];
 				if (fi < v.x) {
-					const float s = g->rows_s[(size_t) lv * stride + f];
-					const float r = (v.y == PAN_DYNAMIC) ? g->rows_r[(size_t) lv * stride + f] :
-						s * __uint_as_float(v.y);
+					const size_t at = (size_t) lv * ROW_TILE + row_index(f, tstride);
+					const float s = g->rows_s[at];
+					const float r = (v.y == PAN_DYNAMIC) ? g->rows_r[at] : s * __uint_as_float(v.y);
 					L = (L + s) - r;
 					R = (R + s) + r;
 				}
@@ -2761,16 +2772,13 @@ mix_kernel(const CallDesc *calls, const SegDesc *segs, uint32_t mode /*0 pcm, 1 
 	const uint2 *vl = reinterpret_cast<const uint2*>(g->vlen + (size_t) seg0 * nlv);
 	const uint32_t ntiles = (nlv + MIX_TV - 1) / MIX_TV;
 	if (producer) {
-		/* The producer warp: per tile, the VoiceSeg records (one lane each), then every
-		 * voice row's 512-byte piece with ONE 16-bytes-per-lane asynchronous copy
-		 * (a fully coalesced request through the LSU path, which keeps far more
-		 * requests in flight than 512-byte TMA bulk copies did: 1.6 -> x TB/s);
-		 * each lane's mbarrier arrival fires when its copies have landed. */
+		/* The producer warp: per stage, the VoiceSeg records (one lane each), then lane 0
+		 * posts the transaction count and issues the bulk copies: the MIX_TV voices' s
+		 * pieces are contiguous (one copy), r pieces only for moving pans. */
 		const uint32_t lane = tid & 31u;
-		uint32_t piece = (uint32_t) (stride - f0) * 4u;    /* whole 16-byte units, inside the row */
-		if (piece > MIX_FRAMES * 4u) piece = MIX_FRAMES * 4u;
-		const bool lane_on = lane * 16u < piece;
-		/* the records are fetched three tiles ahead of their use (their L2 latency
+		const float *tile_s = g->rows_s + (size_t) blockIdx.x * tstride;
+		const float *tile_r = g->rows_r + (size_t) blockIdx.x * tstride;
+		/* the records are fetched three stages ahead of their use (their L2 latency
 		 * would otherwise sit in this loop's critical path) */
 		auto fetch = [&](uint32_t t) {
 			const uint32_t v = t * MIX_TV + lane;
@@ -2787,18 +2795,16 @@ mix_kernel(const CallDesc *calls, const SegDesc *segs, uint32_t mode /*0 pcm, 1 
 			if (has) sm.vi[st][lane] = info;
 			const uint32_t dynmask = __ballot_sync(FULL, has && info.y == PAN_DYNAMIC && info.x);
 			if (lane == 0) sm.ndyn[st] = __popc(dynmask);
-			const float *src_s = g->rows_s + (size_t) v0 * stride + f0 + lane * 4u;
-			const float *src_r = g->rows_r + (size_t) v0 * stride + f0 + lane * 4u;
-			if (lane_on) {
-#pragma unroll 4
-				for (uint32_t k = 0; k < nv; ++k)
-					cp_async16(&sm.s[st][k][lane * 4u], src_s + (size_t) k * stride);
+			__syncwarp();                      /* vi, ndyn written before lane 0's arrive publishes them */
+			if (lane == 0) {
+				const uint32_t piece = ROW_TILE * (uint32_t) sizeof(float);
+				mbar_expect_tx(&sm.full[st], (nv + __popc(dynmask)) * piece);
+				tma_bulk_g2s(&sm.s[st][0][0], tile_s + (size_t) v0 * ROW_TILE, nv * piece, &sm.full[st]);
 				for (uint32_t m = dynmask; m; m &= m - 1u) {
 					const uint32_t k = __ffs(m) - 1u;
-					cp_async16(&sm.r[st][k][lane * 4u], src_r + (size_t) k * stride);
+					tma_bulk_g2s(&sm.r[st][k][0], tile_r + (size_t) (v0 + k) * ROW_TILE, piece, &sm.full[st]);
 				}
 			}
-			cp_async_arrive(&sm.full[st]);     /* 32 arrivals per phase; also publishes vi, ndyn */
 		}
 		return;
 	}

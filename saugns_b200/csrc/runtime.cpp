@@ -633,11 +633,9 @@ extern "C" saugen_Generator *saugen_create(const sauabi_Program *prg, uint32_t s
 	o->row_len = opt->max_call_len ? opt->max_call_len : ms_in_samples(256, srate, NULL);  /* saugns.c:471 */
 	o->row_len = (o->row_len + 3u) & ~3u;
 	if (o->row_len < 4) o->row_len = 4;
-	/* voice rows start a whole number of 128-byte lines apart, an ODD number of them:
-	 * the mix kernel walks down the rows at a fixed column, and a stride with a large
-	 * power-of-two factor (24576 frames = 96 KiB) keeps hitting the same HBM channels */
-	o->row_stride = (o->row_len + 31u) & ~31u;
-	if (((o->row_stride / 32u) & 1u) == 0) o->row_stride += 32u;
+	/* carrier rows are frame-tile major (device_types.h:ROW_TILE): the stride between
+	 * tiles is one 512-byte piece per local voice */
+	o->row_stride = (o->nlv ? o->nlv : 1u) * (uint32_t) ROW_TILE;
 	o->amp_scale = 0.5f * prg->ampmult;                           /* generator.c:183-185 */
 	if (prg->mode & SAUABI_PMODE_AMP_DIV_VOICES) o->amp_scale /= (float) prg->vo_count;
 
@@ -820,9 +818,10 @@ extern "C" saugen_Generator *saugen_create(const sauabi_Program *prg, uint32_t s
 		o->d_progress = (uint32_t*) (base + o_progress); o->d_units = (UnitDesc*) (base + o_units);
 		o->d_mix = (float*) (base + o_mix); o->d_pcm = (int16_t*) (base + o_pcm);
 		o->d_call = (CallDesc*) (base + o_call); o->d_segs = (SegDesc*) (base + o_segs);
-		float *rows = (float*) o->take(false, 2 * nl * (size_t) o->row_stride * sizeof(float));
+		const size_t ntile = ((size_t) o->row_len + ROW_TILE - 1) / ROW_TILE;
+		float *rows = (float*) o->take(false, 2 * ntile * (size_t) o->row_stride * sizeof(float));
 		if (!rows) { set_err("saugen_create: device memory (carrier rows)", cudaGetLastError()); goto fail; }
-		o->d_rows_s = rows; o->d_rows_r = rows + nl * (size_t) o->row_stride;
+		o->d_rows_s = rows; o->d_rows_r = rows + ntile * (size_t) o->row_stride;
 		lap(2);
 		Carver hv;
 		const size_t h_status = hv.take((1 + o->seg_cap) * sizeof(uint32_t));
@@ -1346,8 +1345,18 @@ extern "C" int saugen_read_voice_rows(saugen_Generator *o, uint32_t vo_id, float
 	cudaSetDevice(o->device);
 	cudaStreamSynchronize(o->stream);
 	const size_t lv = vo_id - o->voice_begin;
-	if (s && cudaMemcpy(s, o->d_rows_s + lv * o->row_stride, n * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
-	if (r && cudaMemcpy(r, o->d_rows_r + lv * o->row_stride, n * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+	/* gather the voice's 512-byte pieces, one per frame tile (device_types.h:ROW_TILE) */
+	const size_t ntile = (n + ROW_TILE - 1) / ROW_TILE;
+	std::vector<float> tmp(ntile * ROW_TILE);
+	const float *src[2] = {o->d_rows_s, o->d_rows_r};
+	float *dst[2] = {s, r};
+	for (int k = 0; k < 2; ++k) {
+		if (!dst[k] || !ntile) continue;
+		if (cudaMemcpy2D(tmp.data(), ROW_TILE * sizeof(float), src[k] + lv * ROW_TILE,
+				(size_t) o->row_stride * sizeof(float), ROW_TILE * sizeof(float), ntile,
+				cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+		memcpy(dst[k], tmp.data(), n * sizeof(float));
+	}
 	return 0;
 }
 
