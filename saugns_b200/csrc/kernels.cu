@@ -996,7 +996,7 @@ __device__ __noinline__ void rasg_self_loop(float *main_buf, const uint32_t *cyc
 	fb_s_io = fb_s; prev_s_io = prev_s;
 }
 
-__device__ void rasg_run(Ctx &c, const Instr &in, uint32_t n) {
+__device__ void rasg_run(Ctx &c, const Instr &in, uint32_t n, uint32_t blk_len) {
 	OpState *o = op_ptr(c, in.op);
 	const unsigned flags = o->ras_flags, func = o->ras_func;
 	const int sr = o->ras_level, line = o->mode;
@@ -1035,7 +1035,6 @@ __device__ void rasg_run(Ctx &c, const Instr &in, uint32_t n) {
 	float ph[SPL];
 	ld4(c, in.a, ph);
 	/* sauLine_map_cub: 4-wide body + scalar tail, counted in the 1024-block */
-	const uint32_t blk_len = c.oc + c.stk_rem[c.sp];
 	const uint32_t tail_from = blk_len & ~3u;
 	float out[SPL];
 #pragma unroll
@@ -1410,7 +1409,7 @@ __device__ __noinline__ uint32_t run_chunk(Ctx &c, const Instr *code, uint32_t c
 			__syncwarp();
 			break;
 		case I_RASG:
-			if (n) rasg_run(c, in, n);
+			if (n) rasg_run(c, in, n, c.oc + c.stk_rem[c.sp]);
 			__syncwarp();
 			break;
 		case I_NOISE:
@@ -1522,7 +1521,8 @@ __device__ __forceinline__ uint32_t op_span(const OpState *o, uint32_t k) {
  * closed form: every sample adds the same inc = lrintf(coeff * f), so sample i
  * of the chunk is at phase0 + (i + 1) * inc in wrap-around uint32 arithmetic --
  * bit-identical to the serial accumulation, without conversions or a scan. */
-enum : uint32_t { P_LINE = 1, P_WHEAD, P_WTAIL, P_WLEAF, P_PHASE, P_WOSC, P_RANGE, P_VOUT };
+enum : uint32_t { P_LINE = 1, P_WHEAD, P_WTAIL, P_WLEAF, P_PHASE, P_WOSC, P_RANGE, P_VOUT,
+	P_NOISE, P_CYCLE, P_RASG, P_MIX };
 enum : uint32_t {
 	PF_LAYER = 1, PF_WAVEENV = 2,
 	PF_FUNI = 4,       /* frequency (or the LINE's value) is uniform over the block: w6 holds the
@@ -1559,6 +1559,8 @@ __device__ __noinline__ uint32_t steady_plan(OpState *sops, uint32_t so, uint32_
 	uint32_t need = 0;
 	uint8_t head_rec[32];
 	uint32_t killed = 0;
+	uint32_t lstack = 0, depth = 0;    /* layer flags of the unfused operators being walked */
+	uint32_t entered = 0;              /* operator slots that came in through an ENTER */
 	uint32_t n = 0;
 	plan += PLAN_REC;          /* slot 0 is the header (render_units) */
 	if (cap) --cap;
@@ -1612,9 +1614,45 @@ __device__ __noinline__ uint32_t steady_plan(OpState *sops, uint32_t so, uint32_
 		case I_WHEAD: head = true; break;
 		case I_WTAIL: tail = true; break;
 		case I_ENTER:
-			if (o->type != SAUABI_POPT_wave || !(kb = op_span(o, kb))) return 0;
+			if (!(kb = op_span(o, kb))) return 0;
 			if (in.op >= 32 || (seen & (1u << in.op))) return 0;
 			seen |= 1u << in.op;
+			if ((in.flags & F_LAYER_PMA) || depth >= 31) return 0;   /* self-PM modulators: general path */
+			lstack = (lstack << 1) | ((in.flags & F_LAYER) ? 1u : 0u);
+			++depth;
+			entered |= 1u << in.op;
+			break;
+		case I_LEAVE:                  /* full chunks: nothing to zero-fill (generator.c:716-725) */
+			if (!depth) return 0;
+			lstack >>= 1;
+			--depth;
+			break;
+		case I_NOISE:                                                /* run_block_noiseg, generator.c:527-541 */
+			plan_put(plan, n++, P_NOISE | (uint32_t) in.a << 16, 0u, opa, 0u, 0.f, 0.f, 0.f, 0.f);
+			dirty(in.a);
+			break;
+		case I_CYCLOR:                                               /* run_block_rasg, generator.c:609-664 */
+			if (in.e != NO_BUF) return 0;                            /* fPM: general path */
+			touch(in.c);
+			if (in.d != NO_BUF) touch(in.d);
+			plan_put(plan, n++, P_CYCLE | (uint32_t) in.a << 16 | (uint32_t) in.b << 24,
+					(uint32_t) in.c | (uint32_t) in.d << 8, opa, 0u, 0.f, 0.f, 0.f, 0.f);
+			dirty(in.a); dirty(in.b);
+			break;
+		case I_RASG:
+			if (in.flags & F_HAS_APMODS) return 0;
+			touch(in.b);
+			plan_put(plan, n++, P_RASG | (uint32_t) in.a << 16 | (uint32_t) in.b << 24, 0u, opa, 0u,
+					0.f, 0.f, 0.f, 0.f);
+			dirty(in.a);
+			break;
+		case I_MIX:                                                  /* generator.c:384-440 */
+			if (!depth) return 0;
+			if (in.b != NO_BUF) touch(in.b);
+			touch(in.c);
+			plan_put(plan, n++, P_MIX | (((lstack & 1u) ? PF_LAYER : 0u) | ((in.flags & F_WAVEENV) ? PF_WAVEENV : 0u)) << 8 |
+					(uint32_t) in.a << 16 | (uint32_t) in.b << 24, (uint32_t) in.c, 0u, 0u, 0.f, 0.f, 0.f, 0.f);
+			dirty(in.a);
 			break;
 		case I_LINE:
 			if (in.d) {
@@ -1677,8 +1715,11 @@ __device__ __noinline__ uint32_t steady_plan(OpState *sops, uint32_t so, uint32_
 			const uint32_t slot = __popc(wave_mask & ((1u << wave) - 1u));
 			const uint32_t ct = (wave_mask & CTAB_FLAG) ? st + slot * CTAB_WAVE_BYTES :
 				st + slot * (TAB_STRIDE * 4) + 12;
-			const uint32_t fl = ((leave.flags & F_LAYER) ? PF_LAYER : 0u) |
+			if (!depth) return 0;
+			const uint32_t fl = ((lstack & 1u) ? PF_LAYER : 0u) |
 				((mix.flags & F_WAVEENV) ? PF_WAVEENV : 0u) | PF_ABUF;
+			lstack >>= 1;
+			--depth;
 			plan_put(plan, n++, P_WOSC | fl << 8 | (uint32_t) mix.a << 16 | (uint32_t) in.b << 24,
 					(uint32_t) mix.c, opa, ct, wc->diff_scale[wave], wc->diff_offset[wave], 0.f, 0.f);
 			dirty(mix.a); dirty(in.a); touch(in.b); touch(mix.c);
@@ -1702,6 +1743,10 @@ __device__ __noinline__ uint32_t steady_plan(OpState *sops, uint32_t so, uint32_
 			if (funi && fmul) fval = fval * uval(in.e);
 			if (!funi && in.e != NO_BUF) touch(in.e);
 			if (!tail) {
+				if (depth >= 31) return 0;
+				lstack = (lstack << 1) | ((in.flags & F_LAYER) ? 1u : 0u);   /* popped by its WTAIL / WOSC */
+				++depth;
+				entered |= 1u << in.op;
 				plan_put(plan, n++, P_WHEAD | (funi ? PF_FUNI : 0u) << 8 |
 						(uint32_t) in.b << 24, (uint32_t) in.e << 8, opa, 0u,
 						0.f, 0.f, fval, 0.f);
@@ -1710,6 +1755,11 @@ __device__ __noinline__ uint32_t steady_plan(OpState *sops, uint32_t so, uint32_
 			}
 		}
 		if (tail) {
+			if (!head && in.op < 32 && ((entered >> in.op) & 1u)) {  /* ENTER ... WTAIL: the TAIL is its LEAVE */
+				if (!depth) return 0;
+				lstack >>= 1;
+				--depth;
+			}
 			if (in.d != NO_BUF) return 0;                           /* fPM: general path */
 			if (!(kb = op_span(o, kb)) || !(kb = line_span(o, LINE_AMP, kb))) return 0;
 			if (o->oscflags & OSC_RESET_DIFF) return 0;
@@ -2199,6 +2249,31 @@ __device__ __noinline__ void vout_unaligned(uint32_t sbuf_s, uint32_t sbuf_r, fl
 	}
 }
 
+/* The other operator types on a steady full chunk: the general interpreter's own
+ * routines (same buffer layout, FAST_NS == SPL), out of line, on a minimal context. */
+static_assert(FAST_NS == SPL, "plan_other runs the general routines on the fast buffers");
+__device__ __noinline__ void plan_other(uint32_t kind, uint32_t sb0, int lane, float coeff, uint32_t oc,
+		uint32_t op, uint32_t w0, uint32_t w1) {
+	Ctx c;
+	c.bufs = reinterpret_cast<float*>(__cvta_shared_to_generic(sb0));
+	c.sops = reinterpret_cast<OpState*>(__cvta_shared_to_generic(op));
+	c.lane = lane; c.coeff = coeff; c.oc = oc % (uint32_t) REF_BLOCK; c.pma_flag = false; c.sp = 0;
+	Instr in;
+	in.opcode = 0; in.op = 0; in.flags = 0; in.aux = 0;
+	in.a = (uint8_t) (w0 >> 16); in.b = (uint8_t) (w0 >> 24);
+	in.c = (uint8_t) w1; in.d = (uint8_t) (w1 >> 8); in.e = (uint8_t) NO_BUF;
+	if (kind == P_MIX) {                                           /* block_mix_*, generator.c:384-440 */
+		float x[SPL] = {1.f, 1.f, 1.f, 1.f}, a[SPL];
+		if (in.b != NO_BUF) ld4(c, in.b, x);
+		ld4(c, in.c, a);
+		mix_eval<true>(c, in.a, x, a, CHUNK, (w0 >> 8) & PF_LAYER, ((w0 >> 8) & PF_WAVEENV) != 0);
+	}
+	else if (kind == P_NOISE) noise_run(c, in, CHUNK);             /* sauNoiseG_run_*, noise.h:41-185 */
+	else if (kind == P_CYCLE) cyclor_fill(c, in, CHUNK);           /* sauCyclor_fill, rasg.h:165-222 */
+	else rasg_run(c, in, CHUNK, REF_BLOCK);                        /* sauRasG_run, rasg.h:692-743 */
+	__syncwarp();
+}
+
 template <int NS, bool CTAB>
 __device__ __forceinline__ void run_chunk_plan(const HotCtx &c, const uint32_t nrec,
 		float *row_s, float *row_r, const uint32_t frame) {
@@ -2263,6 +2338,8 @@ __device__ __forceinline__ void run_chunk_plan(const HotCtx &c, const uint32_t n
 #pragma unroll
 			for (int k = 0; k < NS; ++k) p[k] += (rr[k] - p[k]) * m[k];
 			fst<NS>(c, bufa, p);
+		} else if (kind != P_VOUT) {                               /* P_NOISE, P_CYCLE, P_RASG, P_MIX */
+			plan_other(kind, c.sb - c.lane * 16, c.lane, c.coeff, c.oc, op, p0.x, p0.y);
 		} else {                                                   /* P_VOUT, generator.c:772-786 */
 			float sv[NS];
 			fld<NS>(c, bufa, sv);
