@@ -451,7 +451,8 @@ def run_gpu_config(args):
     frames = sum(v[0] for v in got.values())
     line = {"metric": METRIC, "workload": f"C5: {n} independent mixed scripts (4-16 voices, W/N/R, "
             "1-10 s) on one GPU, batched saugen_run_many, every script's PCM delivered to a host "
-            f"sink (arrays recycled), {args.threads} driver threads, {args.call_frames}-frame calls",
+            f"sink (arrays recycled), {args.threads} driver thread(s) x 2 alternating "
+            f"live sets, {args.call_frames}-frame calls",
             "value": vs / wall, "unit": "voice-samples/s", "scripts": n, "group": args.group,
             "wall_s": wall, "scripts_per_s": n / wall, "audio_s": frames / SRATE,
             "realtime_factor": (frames / SRATE) / wall, "parse_s_reference_front_end": parse_s}
@@ -468,7 +469,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--workload", default="c3", choices=["c3", "c4", "c5"])
     ap.add_argument("--scripts", type=int, default=1250, help="c5: scripts on this GPU")
-    ap.add_argument("--group", type=int, default=256, help="c5: generators in flight per driver thread")
+    ap.add_argument("--group", type=int, default=128, help="c5: generators in flight per driver thread")
     ap.add_argument("--threads", type=int, default=1, help="c5: driver threads")
     ap.add_argument("--call-frames", type=int, default=4 * FRAMES,
                     help="c5: frames per generator call (results do not depend on it)")

@@ -76,6 +76,23 @@ int saugen_run_device(saugen_Generator *o, size_t buf_len, int stereo,
 int saugen_run_many(saugen_Generator *const *gens, size_t n, int16_t *const *bufs,
 		size_t buf_len, int stereo, size_t *out_lens, int *more);
 
+/* The same call in two halves (a batch owns a stream and the launch scratch):
+ * begin() plans, uploads, launches and queues the read-backs without waiting,
+ * end() waits, hands out the PCM and returns what saugen_run_many returns.  A
+ * driver alternates two batches so that the host side of one call (planning,
+ * admitting / retiring generators, consuming PCM) overlaps the kernels of the
+ * other.  dest_pinned: every bufs[i] is page-locked memory (saugen_pinned_alloc)
+ * and receives the device-to-host copy directly, with no staging copy. */
+typedef struct saugen_Batch saugen_Batch;
+saugen_Batch *saugen_batch_create(int device);
+void saugen_batch_destroy(saugen_Batch *b);
+int saugen_batch_begin(saugen_Batch *b, saugen_Generator *const *gens, size_t n,
+		int16_t *const *bufs, size_t buf_len, int stereo, int dest_pinned);
+int saugen_batch_end(saugen_Batch *b, size_t *out_lens, int *more);
+/* Page-locked host memory from the library's pool (recycled, not returned to CUDA). */
+void *saugen_pinned_alloc(size_t bytes);
+void saugen_pinned_free(void *p);
+
 /* Voice-sharded rendering across GPUs: produce this rank's partial float mix
  * (2 x buf_len floats, L then R planes) in device memory; the caller reduces
  * the planes over ranks (NCCL sum) and converts on the root. */

@@ -2,9 +2,10 @@
 rank 1): what `Player_run` (saugns.c:575-665) and `player/sndfile.c` do for
 one script at a time, for thousands of independent programs on one GPU.
 
-`render_batch` keeps `group_size` generators in flight and advances all of them
-with ONE render + ONE mix launch per 256 ms call (`saugen_run_many`), retiring
-finished programs and admitting new ones between calls.  `write_wav` /
+`render_batch` keeps live sets of `group_size` generators and advances each set
+with ONE render + ONE mix launch per call (`saugen_batch_begin` / `_end`, the
+two halves of `saugen_run_many`), retiring finished programs and admitting new
+ones between calls, while the other set's kernels run.  `write_wav` /
 `write_au` keep the reference's byte format (player/sndfile.c:63-109): 44-byte
 RIFF/WAVE header with sizes patched at close, little-endian int16; AU (the
 `-o -` stdout stream) = 28-byte header, size unspecified, big-endian int16.
@@ -24,28 +25,29 @@ def _capacity_frames(prg, srate, call_len):
     return (frames // call_len + 2) * call_len
 
 
-def render_batch(programs, srate=96000, device=0, call_len=None, tables=None, group_size=256,
-                 stereo=True, max_frames=None, threads=1, sink=None):
+def render_batch(programs, srate=96000, device=0, call_len=None, tables=None, group_size=128,
+                 stereo=True, max_frames=None, threads=1, sink=None, depth=2, pinned=False):
     """Render every program of `programs` -> list of int16 arrays [frames, ch],
     in input order.  Programs are independent (no mixing between them).
 
-    `threads` host threads each keep their own live set of up to `group_size`
-    generators (admitted from one shared queue) on their own stream: while one
-    set's kernels run, the other threads plan calls, create and retire generators
-    and copy PCM (all of that happens inside the C library, without the GIL), so
-    the GPU does not wait for the host between calls.
+    A driver thread alternates `depth` live sets of up to `group_size` generators
+    each: while the kernels of one set's call run (`saugen_batch_begin`), the host
+    finishes the other set's previous call (`saugen_batch_end`), retires finished
+    programs, admits new ones from the shared queue and plans the next call.
+    Each call's PCM goes from the generator's page-locked staging block to the
+    program's own array inside `saugen_batch_end` (a few copy threads), or, with
+    `pinned=True`, the arrays themselves are page-locked (`saugen_pinned_alloc`)
+    and the device-to-host copy is the only copy -- worth it when the arrays are
+    recycled for long (page-locking memory costs about as much as copying into
+    it a few times).  `threads` > 1 runs several such drivers (each with its own
+    sets and streams).
 
-    Each call's PCM lands directly in the program's final array (the C side
-    copies from its pinned staging buffer to the address it is given), so the
-    per-call Python work is a few vector operations over the live set.
-
-    `sink(index, pcm)`: called (on a worker thread) with each finished program's
+    `sink(index, pcm)`: called (on a driver thread) with each finished program's
     PCM instead of keeping it; the array is only valid during the call -- its
     memory goes back to a pool and carries a later program's samples.  This is
     the streaming form (what Player_run does with its 256 ms buffer, saugns.c:
     601-609: write it out, reuse it): a batch of thousands of scripts does not
-    hold gigabytes of PCM, nor pay the first-touch page faults of fresh arrays.
-    The returned list then holds None."""
+    hold gigabytes of PCM.  The returned list then holds None."""
     import itertools
     import threading
     if call_len is None:
@@ -54,16 +56,16 @@ def render_batch(programs, srate=96000, device=0, call_len=None, tables=None, gr
     out = [None] * n
     queue = itertools.count()                     # next program index; next() is atomic under the GIL
     threads = max(1, min(int(threads), (n + 15) // 16))
+    args = (programs, out, queue, srate, device, call_len, tables, group_size, stereo, max_frames,
+            sink, max(1, int(depth)), bool(pinned))
     if threads == 1:
-        _render_worker(programs, out, queue, srate, device, call_len, tables, group_size, stereo,
-                       max_frames, sink)
+        _render_worker(*args)
         return out
     errs = []
 
     def work():
         try:
-            _render_worker(programs, out, queue, srate, device, call_len, tables, group_size,
-                           stereo, max_frames, sink)
+            _render_worker(*args)
         except BaseException as e:                # re-raised on the caller's thread
             errs.append(e)
 
@@ -77,77 +79,164 @@ def render_batch(programs, srate=96000, device=0, call_len=None, tables=None, gr
     return out
 
 
+class _ArrayPool:
+    """Recycled int16 output arrays: pageable numpy memory, or page-locked memory
+    from the library's pool."""
+
+    def __init__(self, pinned):
+        self.free = []                            # (array, address)
+        self.pinned = pinned
+        self.L = G.lib()
+
+    def take(self, size):
+        for j, (arr, addr) in enumerate(self.free):
+            if arr.size >= size:
+                return self.free.pop(j)
+        if not self.pinned:
+            arr = np.empty(size, np.int16)
+            return arr, arr.ctypes.data
+        import ctypes as C
+        size = 1 << (size - 1).bit_length()       # few distinct sizes: they recycle
+        addr = self.L.saugen_pinned_alloc(size * 2)
+        if not addr:
+            raise MemoryError("saugen_pinned_alloc failed: " + G.last_error())
+        arr = np.ctypeslib.as_array((C.c_int16 * size).from_address(addr))
+        return arr, addr
+
+    def give(self, arr, addr):
+        self.free.append((arr, addr))
+
+    def close(self):
+        if self.pinned:
+            for _, addr in self.free:
+                self.L.saugen_pinned_free(addr)
+        self.free = []
+
+
+class _LiveSet:
+    """Generators advanced together by one saugen_batch_begin / _end pair per call."""
+
+    def __init__(self, device):
+        self.L = G.lib()
+        self.batch = self.L.saugen_batch_create(device)
+        if not self.batch:
+            raise RuntimeError("saugen_batch_create failed: " + G.last_error())
+        self.idx, self.gens, self.bufs = [], [], []   # parallel lists; bufs = (array, address)
+        self.gptr = np.zeros(0, np.uint64)            # generator handles
+        self.base = np.zeros(0, np.uint64)            # address of each output array
+        self.pos = np.zeros(0, np.int64)              # frames written so far
+        self.cap = np.zeros(0, np.int64)
+        self.in_flight = False
+
+    def close(self):
+        if self.batch:
+            self.L.saugen_batch_destroy(self.batch)
+            self.batch = None
+
+
 def _render_worker(programs, out, queue, srate, device, call_len, tables, group_size, stereo,
-                   max_frames, sink=None):
-    """One live set: admit from `queue`, advance with saugen_run_many, retire."""
+                   max_frames, sink, depth, pinned):
+    """One driver: `depth` live sets, admitted from `queue`, alternated call by call."""
     L = G.lib()
     ch = 2 if stereo else 1
     n = len(programs)
-    idx, gens, bufs = [], [], []                  # the live set, parallel lists
-    gptr = np.zeros(0, np.uint64)                 # generator handles
-    base = np.zeros(0, np.uint64)                 # address of each output array
-    pos = np.zeros(0, np.int64)                   # frames written so far
-    cap = np.zeros(0, np.int64)
+    pool = _ArrayPool(pinned)
+    sets = [_LiveSet(device) for _ in range(depth)]
     drained = False
-    pool = []                                     # recycled output arrays (sink mode)
 
-    def new_buf(size):
-        for j, b in enumerate(pool):
-            if b.size >= size:
-                return pool.pop(j)
-        return np.empty(size, np.int16)
+    def admit(s):
+        nonlocal drained
+        if drained or len(s.gens) >= group_size:
+            return
+        k0 = len(s.gens)
+        while len(s.gens) < group_size:
+            i = next(queue)
+            if i >= n:
+                drained = True
+                break
+            g = G.Generator(programs[i], srate, tables=tables, device=device, max_call_len=call_len)
+            c = _capacity_frames(programs[i], srate, call_len)
+            s.idx.append(i); s.gens.append(g); s.bufs.append(pool.take(c * ch))
+        new = s.bufs[k0:]
+        s.gptr = np.concatenate([s.gptr, np.array([g.ptr for g in s.gens[k0:]], np.uint64)])
+        s.base = np.concatenate([s.base, np.array([a for _, a in new], np.uint64)])
+        s.pos = np.concatenate([s.pos, np.zeros(len(new), np.int64)])
+        s.cap = np.concatenate([s.cap, np.array([b.size // ch for b, _ in new], np.int64)])
 
-    while not drained or gens:
-        if not drained and len(gens) < group_size:
-            k0 = len(gens)
-            while len(gens) < group_size:
-                i = next(queue)
-                if i >= n:
-                    drained = True
-                    break
-                g = G.Generator(programs[i], srate, tables=tables, device=device,
-                                max_call_len=call_len)
-                c = _capacity_frames(programs[i], srate, call_len)
-                b = new_buf(c * ch)
-                idx.append(i); gens.append(g); bufs.append(b)
-            gptr = np.concatenate([gptr, np.array([g.ptr for g in gens[k0:]], np.uint64)])
-            base = np.concatenate([base, np.array([b.ctypes.data for b in bufs[k0:]], np.uint64)])
-            pos = np.concatenate([pos, np.zeros(len(gens) - k0, np.int64)])
-            cap = np.concatenate([cap, np.array([b.size // ch for b in bufs[k0:]], np.int64)])
-        m = len(gens)
-        if m == 0:
-            break
-        for k in np.nonzero(pos + call_len > cap)[0]:      # rare: longer than announced
-            bufs[k] = np.concatenate([bufs[k], np.empty(4 * call_len * ch, np.int16)])
-            base[k] = bufs[k].ctypes.data
-            cap[k] = bufs[k].size // ch
-        ptrs = base + (pos * (2 * ch)).astype(np.uint64)
+    def begin(s):
+        for k in np.nonzero(s.pos + call_len > s.cap)[0]:      # rare: longer than announced
+            old, old_addr = s.bufs[k]
+            arr, addr = pool.take(old.size + 4 * call_len * ch)
+            arr[:s.pos[k] * ch] = old[:s.pos[k] * ch]
+            pool.give(old, old_addr)
+            s.bufs[k] = (arr, addr)
+            s.base[k] = addr
+            s.cap[k] = arr.size // ch
+        s.ptrs = s.base + (s.pos * (2 * ch)).astype(np.uint64)   # kept alive until end()
+        r = L.saugen_batch_begin(s.batch, s.gptr.ctypes.data, len(s.gens), s.ptrs.ctypes.data,
+                                 call_len, int(stereo), int(pinned))
+        if r < 0:
+            raise RuntimeError("saugen_batch_begin failed: " + G.last_error())
+        s.in_flight = True
+
+    def end(s):
+        m = len(s.gens)
         lens = np.zeros(m, np.uint64)
         more = np.zeros(m, np.int32)
-        r = L.saugen_run_many(gptr.ctypes.data, m, ptrs.ctypes.data, call_len, int(stereo),
-                              lens.ctypes.data, more.ctypes.data)
+        r = L.saugen_batch_end(s.batch, lens.ctypes.data, more.ctypes.data)
+        s.in_flight = False
         if r < 0:
-            raise RuntimeError("saugen_run_many failed: " + G.last_error())
-        pos += lens.astype(np.int64)
+            raise RuntimeError("saugen_batch_end failed: " + G.last_error())
+        s.pos += lens.astype(np.int64)
         done = more == 0
         if max_frames:
-            done |= pos >= max_frames
-        if done.any():
-            keep = []
-            for k in range(m):
-                if done[k]:
-                    gens[k].close()
-                    pcm = bufs[k][:pos[k] * ch].reshape(-1, ch)
-                    if sink is None:
-                        out[idx[k]] = pcm
-                    else:
-                        sink(idx[k], pcm)
-                        pool.append(bufs[k])
-                else:
-                    keep.append(k)
-            idx = [idx[k] for k in keep]; gens = [gens[k] for k in keep]; bufs = [bufs[k] for k in keep]
-            kk = np.array(keep, np.int64)
-            gptr, base, pos, cap = gptr[kk], base[kk], pos[kk], cap[kk]
+            done |= s.pos >= max_frames
+        if not done.any():
+            return
+        keep = []
+        for k in range(m):
+            if not done[k]:
+                keep.append(k)
+                continue
+            s.gens[k].close()
+            arr, addr = s.bufs[k]
+            pcm = arr[:s.pos[k] * ch].reshape(-1, ch)
+            if sink is not None:
+                sink(s.idx[k], pcm)
+                pool.give(arr, addr)
+            elif pinned:
+                out[s.idx[k]] = pcm.copy()        # out of the page-locked pool
+                pool.give(arr, addr)
+            else:
+                out[s.idx[k]] = pcm               # the array is the result
+        s.idx = [s.idx[k] for k in keep]; s.gens = [s.gens[k] for k in keep]
+        s.bufs = [s.bufs[k] for k in keep]
+        kk = np.array(keep, np.int64)
+        s.gptr, s.base, s.pos, s.cap = s.gptr[kk], s.base[kk], s.pos[kk], s.cap[kk]
+
+    try:
+        k = 0
+        while True:
+            s = sets[k % depth]
+            k += 1
+            if s.in_flight:
+                end(s)
+            admit(s)
+            if s.gens:
+                begin(s)
+            if drained and not any(x.in_flight for x in sets):
+                break
+    finally:
+        for s in sets:
+            if s.in_flight:
+                try:
+                    end(s)
+                except Exception:
+                    pass
+            for g in s.gens:
+                g.close()
+            s.close()
+        pool.close()
 
 
 def wav_bytes(pcm, srate):

@@ -1169,29 +1169,79 @@ extern "C" int saugen_mix_to_pcm(saugen_Generator *o, const float *dev_mix, size
 	return 0;
 }
 
-/* Batched: one render + one mix launch for n generators (same device, stream
- * and wave tables; the first generator's stream is used). */
-extern "C" int saugen_run_many(saugen_Generator *const *gens, size_t n, int16_t *const *bufs,
-		size_t buf_len, int stereo, size_t *out_lens, int *more) {
-	if (!gens || n == 0) return 0;
-	saugen_Generator *g0 = gens[0];
-	cudaSetDevice(g0->device);
-	static thread_local std::vector<CallDesc> calls;
-	static thread_local std::vector<SegDesc> segs;
-	static thread_local std::vector<size_t> call_of;     // generator index per call
-	static thread_local CallDesc *d_calls = nullptr; static thread_local size_t d_calls_cap = 0;
-	static thread_local SegDesc *d_segs = nullptr; static thread_local size_t d_segs_cap = 0;
-	static thread_local std::vector<UnitDesc> units;
-	static thread_local UnitDesc *d_units = nullptr; static thread_local size_t d_units_cap = 0;
-	calls.clear(); segs.clear(); call_of.clear(); units.clear();
+/* ---- batched calls ----------------------------------------------------------- *
+ * One render + one mix launch for n generators (same device and wave tables), in
+ * two halves so that a driver can keep the GPU busy: begin() plans, uploads,
+ * launches and queues the read-backs on the batch's stream without waiting; end()
+ * waits, hands out the PCM and does the end-of-call bookkeeping.  While one batch
+ * is between begin and end, the host works on another (saugns_b200/batch.py). */
+struct saugen_Batch {
+	int device = 0;
+	cudaStream_t stream = nullptr;
+	std::vector<CallDesc> calls;
+	std::vector<SegDesc> segs;
+	std::vector<UnitDesc> units;
+	std::vector<size_t> call_of;                 // generator index per call
+	std::vector<saugen_Generator*> gens;         // of the call in flight
+	std::vector<int16_t*> bufs;
+	CallDesc *d_calls = nullptr; size_t d_calls_cap = 0;
+	SegDesc *d_segs = nullptr; size_t d_segs_cap = 0;
+	UnitDesc *d_units = nullptr; size_t d_units_cap = 0;
+	size_t buf_len = 0, bytes = 0;
+	bool in_flight = false, dest_pinned = false;
+};
+
+extern "C" saugen_Batch *saugen_batch_create(int device) {
+	int ndev = 0;
+	if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+		set_err("saugen_batch_create: no such CUDA device", cudaGetLastError());
+		return nullptr;
+	}
+	cudaSetDevice(device);
+	saugen_Batch *b = new saugen_Batch();
+	b->device = device;
+	b->stream = g_streams.get(device);
+	if (!b->stream) { set_err("saugen_batch_create: stream", cudaGetLastError()); delete b; return nullptr; }
+	return b;
+}
+
+extern "C" void saugen_batch_destroy(saugen_Batch *b) {
+	if (!b) return;
+	cudaSetDevice(b->device);
+	cudaStreamSynchronize(b->stream);
+	if (b->d_calls) cudaFree(b->d_calls);
+	if (b->d_segs) cudaFree(b->d_segs);
+	if (b->d_units) cudaFree(b->d_units);
+	g_streams.put(b->device, b->stream);
+	delete b;
+}
+
+/* Pinned host memory from the library's pool: PCM destinations allocated here take
+ * the device-to-host copy directly (saugen_batch_begin, dest_pinned). */
+extern "C" void *saugen_pinned_alloc(size_t bytes) { return g_pool.alloc(true, 0, bytes ? bytes : 1); }
+extern "C" void saugen_pinned_free(void *p) { g_pool.release(true, 0, p); }
+
+extern "C" int saugen_batch_begin(saugen_Batch *b, saugen_Generator *const *gens, size_t n,
+		int16_t *const *bufs, size_t buf_len, int stereo, int dest_pinned) {
+	if (!b || b->in_flight) { g_err = "saugen_batch_begin: batch missing or still in flight"; return -1; }
+	b->calls.clear(); b->segs.clear(); b->call_of.clear(); b->units.clear();
+	b->gens.assign(gens, gens + n);
+	b->bufs.assign(n, nullptr);
+	if (bufs) for (size_t i = 0; i < n; ++i) b->bufs[i] = bufs[i];
+	b->buf_len = buf_len;
+	b->bytes = buf_len * (stereo ? 2 : 1) * sizeof(int16_t);
+	b->dest_pinned = dest_pinned != 0;
+	if (n == 0) return 0;
+	cudaSetDevice(b->device);
+	cudaStream_t st = b->stream;
+	saugen_Generator *g0 = nullptr;
 	uint32_t ntasks = 0, wave_mask = 0, nbufs = 1, max_ops = 1, nplan = 0;
 	for (size_t i = 0; i < n; ++i) {
 		saugen_Generator *o = gens[i];
-		if (out_lens) out_lens[i] = 0;
-		if (more) more[i] = 0;
 		if (!o || o->ended) continue;
-		if (buf_len > o->row_len || o->d_tables != g0->d_tables) {
-			g_err = "saugen_run_many: generators must share tables and fit buf_len";
+		if (!g0) g0 = o;
+		if (buf_len > o->row_len || o->d_tables != g0->d_tables || o->device != b->device) {
+			g_err = "saugen_run_many: generators must share device and tables and fit buf_len";
 			return -1;
 		}
 		plan_call(o, (uint32_t) buf_len, o->segs_tmp);
@@ -1201,72 +1251,90 @@ extern "C" int saugen_run_many(saugen_Generator *const *gens, size_t n, int16_t 
 		}
 		CallDesc cd;
 		cd.gen = o->d_desc; cd.call_len = (uint32_t) buf_len; cd.nseg = (uint32_t) o->segs_tmp.size();
-		cd.seg_off = (uint32_t) segs.size(); cd.task_base = ntasks; cd.stereo = stereo ? 1 : 0; cd._pad = 0;
+		cd.seg_off = (uint32_t) b->segs.size(); cd.task_base = ntasks; cd.stereo = stereo ? 1 : 0; cd._pad = 0;
 		plan_units(o->segs_tmp, o->units_tmp, 1u << 20);
-		cd.unit_off = (uint32_t) units.size(); cd.nunits = (uint32_t) o->units_tmp.size();
-		units.insert(units.end(), o->units_tmp.begin(), o->units_tmp.end());
-		if (o->compact) cudaMemsetAsync(o->d_vlen, 0, o->zero_bytes, g0->stream);
-		else cudaMemsetAsync(o->d_vlen, 0, (size_t) cd.nseg * (o->nlv ? o->nlv : 1) * sizeof(VoiceSeg), g0->stream);
-		segs.insert(segs.end(), o->segs_tmp.begin(), o->segs_tmp.end());
-		calls.push_back(cd);
-		call_of.push_back(i);
+		cd.unit_off = (uint32_t) b->units.size(); cd.nunits = (uint32_t) o->units_tmp.size();
+		b->units.insert(b->units.end(), o->units_tmp.begin(), o->units_tmp.end());
+		if (o->compact) cudaMemsetAsync(o->d_vlen, 0, o->zero_bytes, st);
+		else cudaMemsetAsync(o->d_vlen, 0, (size_t) cd.nseg * (o->nlv ? o->nlv : 1) * sizeof(VoiceSeg), st);
+		b->segs.insert(b->segs.end(), o->segs_tmp.begin(), o->segs_tmp.end());
+		b->calls.push_back(cd);
+		b->call_of.push_back(i);
 		ntasks += o->nlv;
 		wave_mask |= o->wave_mask;
 		if (o->nbufs > nbufs) nbufs = o->nbufs;
 		if (o->max_ops > max_ops) max_ops = o->max_ops;
 		if (o->nplan > nplan) nplan = o->nplan;
-		if (!o->compact) cudaMemsetAsync(o->d_status, 0, (1 + cd.nseg) * sizeof(uint32_t), g0->stream);
+		if (!o->compact) cudaMemsetAsync(o->d_status, 0, (1 + cd.nseg) * sizeof(uint32_t), st);
 	}
-	if (calls.empty()) return 0;
+	if (b->calls.empty()) return 0;
 	cudaError_t e = cudaSuccess;
-	if (calls.size() > d_calls_cap) {
-		if (d_calls) cudaFree(d_calls);
-		d_calls_cap = calls.size() * 2;
-		e = cudaMalloc(&d_calls, d_calls_cap * sizeof(CallDesc));
-	}
-	if (e == cudaSuccess && segs.size() > d_segs_cap) {
-		if (d_segs) cudaFree(d_segs);
-		d_segs_cap = segs.size() * 2;
-		e = cudaMalloc(&d_segs, d_segs_cap * sizeof(SegDesc));
-	}
-	if (e == cudaSuccess && units.size() > d_units_cap) {
-		if (d_units) cudaFree(d_units);
-		d_units_cap = units.size() * 2;
-		e = cudaMalloc(&d_units, d_units_cap * sizeof(UnitDesc));
-	}
-	if (e == cudaSuccess) e = cudaMemcpyAsync(d_units, units.data(), units.size() * sizeof(UnitDesc), cudaMemcpyHostToDevice, g0->stream);
-	if (e == cudaSuccess) e = cudaMemcpyAsync(d_calls, calls.data(), calls.size() * sizeof(CallDesc), cudaMemcpyHostToDevice, g0->stream);
-	if (e == cudaSuccess) e = cudaMemcpyAsync(d_segs, segs.data(), segs.size() * sizeof(SegDesc), cudaMemcpyHostToDevice, g0->stream);
+	auto grow = [&](void **p, size_t *cap, size_t need, size_t elem) {
+		if (e != cudaSuccess || need <= *cap) return;
+		cudaStreamSynchronize(st);
+		if (*p) cudaFree(*p);
+		*cap = need * 2;
+		e = cudaMalloc(p, *cap * elem);
+	};
+	grow((void**) &b->d_calls, &b->d_calls_cap, b->calls.size(), sizeof(CallDesc));
+	grow((void**) &b->d_segs, &b->d_segs_cap, b->segs.size(), sizeof(SegDesc));
+	grow((void**) &b->d_units, &b->d_units_cap, b->units.size(), sizeof(UnitDesc));
+	if (e == cudaSuccess) e = cudaMemcpyAsync(b->d_units, b->units.data(), b->units.size() * sizeof(UnitDesc), cudaMemcpyHostToDevice, st);
+	if (e == cudaSuccess) e = cudaMemcpyAsync(b->d_calls, b->calls.data(), b->calls.size() * sizeof(CallDesc), cudaMemcpyHostToDevice, st);
+	if (e == cudaSuccess) e = cudaMemcpyAsync(b->d_segs, b->segs.data(), b->segs.size() * sizeof(SegDesc), cudaMemcpyHostToDevice, st);
 	g0->timed_call = g0->timing;       /* kernel times of the batch accumulate on the first generator */
-	if (e == cudaSuccess && g0->timed_call) e = cudaEventRecord(g0->ev_t[0], g0->stream);
+	if (e == cudaSuccess && g0->timed_call) e = cudaEventRecord(g0->ev_t[0], st);
 	if (e == cudaSuccess) {
 		const Shape shape = pick_shape(ntasks, wave_mask, nbufs, max_ops, nplan, g0->d_coefs != nullptr);
-		e = launch_render(d_calls, (uint32_t) calls.size(), d_segs, d_units, ntasks, g0->d_tables,
-				g0->d_coefs, shape.mask, nbufs, max_ops, nplan, shape.warps, 0, 0, g0->stream);
+		e = launch_render(b->d_calls, (uint32_t) b->calls.size(), b->d_segs, b->d_units, ntasks, g0->d_tables,
+				g0->d_coefs, shape.mask, nbufs, max_ops, nplan, shape.warps, 0, 0, st);
 		g0->counters[0]++;
 	}
-	if (e == cudaSuccess && g0->timed_call) e = cudaEventRecord(g0->ev_t[1], g0->stream);
+	if (e == cudaSuccess && g0->timed_call) e = cudaEventRecord(g0->ev_t[1], st);
 	if (e == cudaSuccess) {
-		e = launch_mix(d_calls, (uint32_t) calls.size(), d_segs, (uint32_t) buf_len, 0, g0->stream);
+		e = launch_mix(b->d_calls, (uint32_t) b->calls.size(), b->d_segs, (uint32_t) buf_len, 0, st);
 		g0->counters[1]++;
 	}
-	if (e == cudaSuccess && g0->timed_call) e = cudaEventRecord(g0->ev_t[2], g0->stream);
-	const size_t bytes = buf_len * (stereo ? 2 : 1) * sizeof(int16_t);
-	for (size_t c = 0; c < calls.size() && e == cudaSuccess; ++c) {
-		saugen_Generator *o = gens[call_of[c]];
-		e = read_back(o, calls[c].nseg, (bufs && bufs[call_of[c]]) ? bytes : 0, g0->stream);
+	if (e == cudaSuccess && g0->timed_call) e = cudaEventRecord(g0->ev_t[2], st);
+	for (size_t c = 0; c < b->calls.size() && e == cudaSuccess; ++c) {
+		const size_t i = b->call_of[c];
+		saugen_Generator *o = gens[i];
+		int16_t *dst = b->bufs[i];
+		if (dst && b->dest_pinned) {
+			/* status to the generator's staging block, PCM straight to its destination */
+			e = cudaMemcpyAsync(o->h_status, o->d_status, (1 + b->calls[c].nseg) * sizeof(uint32_t),
+					cudaMemcpyDeviceToHost, st);
+			if (e == cudaSuccess) e = cudaMemcpyAsync(dst, o->d_pcm, b->bytes, cudaMemcpyDeviceToHost, st);
+		} else {
+			e = read_back(o, b->calls[c].nseg, dst ? b->bytes : 0, st);
+		}
 	}
-	if (e == cudaSuccess) e = cudaStreamSynchronize(g0->stream);
+	if (e != cudaSuccess) { set_err("saugen_run_many", e); cudaStreamSynchronize(st); return -1; }
+	b->in_flight = true;
+	return 1;
+}
+
+extern "C" int saugen_batch_end(saugen_Batch *b, size_t *out_lens, int *more) {
+	if (!b) return -1;
+	const size_t n = b->gens.size();
+	for (size_t i = 0; i < n; ++i) {
+		if (out_lens) out_lens[i] = 0;
+		if (more) more[i] = 0;
+	}
+	if (!b->in_flight) return 0;
+	b->in_flight = false;
+	cudaSetDevice(b->device);
+	cudaError_t e = cudaStreamSynchronize(b->stream);
 	if (e != cudaSuccess) { set_err("saugen_run_many", e); return -1; }
 	/* pinned staging -> the callers' buffers: fresh destination pages fault on first
 	 * touch, so a large batch is copied by a few threads */
-	if (bufs) {
-		const size_t nc = calls.size();
-		const size_t *co = call_of.data();     /* thread_local: the workers must not name it */
-		auto copy_range = [co, bufs, gens, bytes](size_t lo, size_t hi) {
+	if (!b->dest_pinned) {
+		const size_t nc = b->calls.size();
+		const size_t bytes = b->bytes;
+		auto copy_range = [b, bytes](size_t lo, size_t hi) {
 			for (size_t c = lo; c < hi; ++c) {
-				const size_t i = co[c];
-				if (bufs[i]) memcpy(bufs[i], gens[i]->h_pcm, bytes);
+				const size_t i = b->call_of[c];
+				if (b->bufs[i]) memcpy(b->bufs[i], b->gens[i]->h_pcm, bytes);
 			}
 		};
 		size_t nthr = nc * bytes >= ((size_t) 4 << 20) ? std::thread::hardware_concurrency() / 2 : 1;
@@ -1280,16 +1348,34 @@ extern "C" int saugen_run_many(saugen_Generator *const *gens, size_t n, int16_t 
 		}
 	}
 	int any = 0;
-	for (size_t c = 0; c < calls.size(); ++c) {
-		const size_t i = call_of[c];
-		saugen_Generator *o = gens[i];
+	for (size_t c = 0; c < b->calls.size(); ++c) {
+		const size_t i = b->call_of[c];
 		size_t ol = 0;
-		int m = finish_call(o, buf_len, &ol);
+		int m = finish_call(b->gens[i], b->buf_len, &ol);
 		if (out_lens) out_lens[i] = ol;
 		if (more) more[i] = m;
 		any |= m;
 	}
 	return any;
+}
+
+/* == the two halves back to back, on a per-thread batch per device */
+extern "C" int saugen_run_many(saugen_Generator *const *gens, size_t n, int16_t *const *bufs,
+		size_t buf_len, int stereo, size_t *out_lens, int *more) {
+	if (!gens || n == 0) return 0;
+	int device = 0;
+	for (size_t i = 0; i < n; ++i) if (gens[i]) { device = gens[i]->device; break; }
+	struct Holder {
+		std::map<int, saugen_Batch*> by_dev;
+		~Holder() { for (auto &kv : by_dev) saugen_batch_destroy(kv.second); }
+	};
+	static thread_local Holder holder;
+	saugen_Batch *&b = holder.by_dev[device];
+	if (!b) b = saugen_batch_create(device);
+	if (!b) return -1;
+	const int r = saugen_batch_begin(b, gens, n, bufs, buf_len, stereo, 0);
+	if (r < 0) return r;
+	return saugen_batch_end(b, out_lens, more);
 }
 
 /* ---- introspection ------------------------------------------------------- */

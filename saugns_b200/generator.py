@@ -69,6 +69,17 @@ def lib():
         L.saugen_run_many.restype = C.c_int
         L.saugen_run_many.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int,
                                       C.c_void_p, C.c_void_p]
+        L.saugen_batch_create.restype = C.c_void_p
+        L.saugen_batch_create.argtypes = [C.c_int]
+        L.saugen_batch_destroy.argtypes = [C.c_void_p]
+        L.saugen_batch_begin.restype = C.c_int
+        L.saugen_batch_begin.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
+                                         C.c_int, C.c_int]
+        L.saugen_batch_end.restype = C.c_int
+        L.saugen_batch_end.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.saugen_pinned_alloc.restype = C.c_void_p
+        L.saugen_pinned_alloc.argtypes = [C.c_size_t]
+        L.saugen_pinned_free.argtypes = [C.c_void_p]
         L.saugen_run_mix.restype = C.c_int
         L.saugen_run_mix.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p),
                                      C.POINTER(C.c_size_t)]

@@ -47,14 +47,14 @@ def close(self):
 
 _Gen.__init__, _Gen.close = init, close
 L = G.lib()
-_rm = L.saugen_run_many
+_rm = L.saugen_batch_end
 
 
 class Wrap:
     def __getattr__(self, k):
         return getattr(L, k)
 
-    def saugen_run_many(self, *a):
+    def saugen_batch_end(self, *a):
         t0 = time.perf_counter()
         r = _rm(*a)
         acc["run_many"] += time.perf_counter() - t0

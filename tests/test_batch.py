@@ -45,7 +45,8 @@ def test_render_batch_matches_reference(ref, port):
     # several driver threads, longer calls, streaming sink with recycled arrays
     sunk = {}
     none = batch.render_batch(prgs, srate=96000, tables=tabs, group_size=8, threads=3,
-                              call_len=4 * 24576, sink=lambda i, pcm: sunk.__setitem__(i, pcm.copy()))
+                              call_len=4 * 24576, pinned=True,
+                              sink=lambda i, pcm: sunk.__setitem__(i, pcm.copy()))
     assert none == [None] * len(prgs) and len(sunk) == len(prgs)
     for i, p in enumerate(prgs):
         want = ref.render(p, srate=96000)
