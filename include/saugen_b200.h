@@ -50,6 +50,9 @@ typedef struct saugen_Options {
 	                          * (time unit, voice) tickets; 3 = balanced: one contiguous
 	                          * range of (voice, block) items per resident warp (auto picks
 	                          * it when the voices need more than one wave of warps) */
+	uint32_t pcm_big_endian; /* 1 = big-endian int16 samples: the AU stream `saugns -o -` writes
+	                          * (saugns.c:508-511; the swap of player/sndfile.c:160-168 is folded
+	                          * into the mix epilogue); 0 = host order, as sauGenerator_run */
 } saugen_Options;
 
 /* == sau_create_Generator(prg, srate).  Borrows `prg` until destroy. */

@@ -250,14 +250,17 @@ def wav_bytes(pcm, srate):
     return hdr + data
 
 
-def au_bytes(pcm, srate):
+def au_bytes(pcm, srate, swapped=False):
     """The AU stream `saugns -o -` writes to stdout (saugns.c:508-511,
     player/sndfile.c:63-72,160-168): size field left "unspecified" because a
-    stream is never patched (sndfile.c:201-211), big-endian samples."""
-    pcm = np.ascontiguousarray(pcm, dtype="<i2")
+    stream is never patched (sndfile.c:201-211), big-endian samples.
+    swapped: `pcm` was rendered with big_endian=True (the byte swap already
+    happened in the mix epilogue on the GPU) and goes out as it is."""
     ch = pcm.shape[1] if pcm.ndim == 2 else 1
     hdr = b".snd" + struct.pack(">IIIII", 28, 0xffffffff, 3, srate, ch) + struct.pack(">I", 0)
-    return hdr + pcm.astype(">i2").tobytes()
+    if swapped:
+        return hdr + np.ascontiguousarray(pcm).tobytes()
+    return hdr + np.ascontiguousarray(pcm, dtype="<i2").astype(">i2").tobytes()
 
 
 def write_wav(path, pcm, srate):
@@ -265,6 +268,6 @@ def write_wav(path, pcm, srate):
         f.write(wav_bytes(pcm, srate))
 
 
-def write_au(path, pcm, srate):
+def write_au(path, pcm, srate, swapped=False):
     with open(path, "wb") as f:
-        f.write(au_bytes(pcm, srate))
+        f.write(au_bytes(pcm, srate, swapped))

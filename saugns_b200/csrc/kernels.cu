@@ -2773,17 +2773,22 @@ __device__ __forceinline__ void mix_store(const GenDesc *g, const CallDesc *cd, 
 		g->mix[g->row_len + f] = R;
 		return;
 	}
-	if (cd->stereo) {                                              /* generator.c:795-810 */
+	/* CallDesc::stereo: bit 0 = two channels, bit 1 = big-endian samples (the AU stream
+	 * of `saugns -o -`, player/sndfile.c:160-168: the byte swap folded into the epilogue) */
+	const bool be = (cd->stereo & 2u) != 0;
+	if (cd->stereo & 1u) {                                         /* generator.c:795-810 */
 		L = sau::fclampf(L, -1.f, 1.f);
 		R = sau::fclampf(R, -1.f, 1.f);
-		short2 o;
-		o.x = (short) __float2int_rn(L * 32767.f);
-		o.y = (short) __float2int_rn(R * 32767.f);
-		reinterpret_cast<short2*>(g->pcm)[f] = o;
+		uint32_t w = ((uint32_t) (uint16_t) (short) __float2int_rn(L * 32767.f)) |
+			((uint32_t) (uint16_t) (short) __float2int_rn(R * 32767.f) << 16);
+		if (be) w = __byte_perm(w, 0u, 0x2301);
+		reinterpret_cast<uint32_t*>(g->pcm)[f] = w;
 	} else {                                                       /* generator.c:812-825 */
 		float m = (L + R) * 0.5f;
 		m = sau::fclampf(m, -1.f, 1.f);
-		g->pcm[f] = (short) __float2int_rn(m * 32767.f);
+		uint32_t w = (uint16_t) (short) __float2int_rn(m * 32767.f);
+		if (be) w = __byte_perm(w, 0u, 0x3201);
+		reinterpret_cast<uint16_t*>(g->pcm)[f] = (uint16_t) w;
 	}
 }
 
@@ -2926,14 +2931,20 @@ __global__ void planes_to_pcm_kernel(const float *mix, uint32_t plane_stride, ui
 	const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
 	if (f >= n) return;
 	float L = mix[f], R = mix[plane_stride + f];
-	if (stereo) {
+	const bool be = (stereo & 2u) != 0;          /* flags as CallDesc::stereo */
+	uint16_t *out = reinterpret_cast<uint16_t*>(pcm);
+	auto put = [be](uint16_t *p, int v) {
+		const uint16_t u = (uint16_t) (short) v;
+		*p = be ? (uint16_t) ((u << 8) | (u >> 8)) : u;
+	};
+	if (stereo & 1u) {
 		L = sau::fclampf(L, -1.f, 1.f);
 		R = sau::fclampf(R, -1.f, 1.f);
-		pcm[2 * f] = (short) __float2int_rn(L * 32767.f);
-		pcm[2 * f + 1] = (short) __float2int_rn(R * 32767.f);
+		put(out + 2 * f, __float2int_rn(L * 32767.f));
+		put(out + 2 * f + 1, __float2int_rn(R * 32767.f));
 	} else {
 		float m = sau::fclampf((L + R) * 0.5f, -1.f, 1.f);
-		pcm[f] = (short) __float2int_rn(m * 32767.f);
+		put(out + f, __float2int_rn(m * 32767.f));
 	}
 }
 

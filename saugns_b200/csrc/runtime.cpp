@@ -318,6 +318,7 @@ struct saugen_Generator {
 	uint32_t voice_begin = 0, voice_end = 0;
 	uint32_t row_stride = 0;
 	uint32_t row_len = 0, nbufs = 1, max_ops = 1, wave_mask = 0, seg_cap = 0, sched = 0;
+	bool big_endian = false;           // saugen_Options::pcm_big_endian
 	uint32_t nplan = 0;                // block-plan records the largest voice program needs (kernels.cu)
 	float amp_scale = 0.f;
 	/* timeline (host-only integer bookkeeping) */
@@ -623,6 +624,7 @@ extern "C" saugen_Generator *saugen_create(const sauabi_Program *prg, uint32_t s
 	if (!tables) tables = saugen::builtin_wave_tables();
 
 	o->prg = prg; o->srate = srate; o->device = opt->device; o->sched = opt->sched;
+	o->big_endian = opt->pcm_big_endian != 0;
 	o->vo_count = prg->vo_count; o->op_count = prg->op_count;
 	o->voice_begin = 0; o->voice_end = prg->vo_count;
 	if (opt->voice_end > opt->voice_begin) {
@@ -1061,7 +1063,8 @@ static int run_common(saugen_Generator *o, size_t buf_len, int stereo, uint32_t 
 	memcpy(o->h_units, o->units_tmp.data(), nunits * sizeof(UnitDesc));
 	CallDesc &cd = *o->h_call;
 	cd.gen = o->d_desc; cd.call_len = (uint32_t) buf_len; cd.nseg = nseg; cd.seg_off = 0;
-	cd.task_base = 0; cd.stereo = stereo ? 1 : 0; cd.unit_off = 0; cd.nunits = nunits; cd._pad = 0;
+	cd.task_base = 0; cd.stereo = (stereo ? 1u : 0u) | (o->big_endian ? 2u : 0u);
+	cd.unit_off = 0; cd.nunits = nunits; cd._pad = 0;
 	cudaError_t e;
 	if (o->compact) {
 		/* one copy in ([call][segs][units]), one memset ([vlen][progress][status]) */
@@ -1158,7 +1161,8 @@ extern "C" int saugen_mix_to_pcm(saugen_Generator *o, const float *dev_mix, size
 		int stereo, int16_t *host_buf) {
 	if (!o || buf_len > o->row_len) return -1;
 	cudaSetDevice(o->device);
-	cudaError_t e = launch_planes_to_pcm(dev_mix, o->row_len, (uint32_t) buf_len, stereo ? 1 : 0,
+	cudaError_t e = launch_planes_to_pcm(dev_mix, o->row_len, (uint32_t) buf_len,
+			(stereo ? 1u : 0u) | (o->big_endian ? 2u : 0u),
 			o->d_pcm, o->stream);
 	const size_t bytes = buf_len * (stereo ? 2 : 1) * sizeof(int16_t);
 	if (e == cudaSuccess && host_buf)
@@ -1251,7 +1255,8 @@ extern "C" int saugen_batch_begin(saugen_Batch *b, saugen_Generator *const *gens
 		}
 		CallDesc cd;
 		cd.gen = o->d_desc; cd.call_len = (uint32_t) buf_len; cd.nseg = (uint32_t) o->segs_tmp.size();
-		cd.seg_off = (uint32_t) b->segs.size(); cd.task_base = ntasks; cd.stereo = stereo ? 1 : 0; cd._pad = 0;
+		cd.seg_off = (uint32_t) b->segs.size(); cd.task_base = ntasks;
+		cd.stereo = (stereo ? 1u : 0u) | (o->big_endian ? 2u : 0u); cd._pad = 0;
 		plan_units(o->segs_tmp, o->units_tmp, 1u << 20);
 		cd.unit_off = (uint32_t) b->units.size(); cd.nunits = (uint32_t) o->units_tmp.size();
 		b->units.insert(b->units.end(), o->units_tmp.begin(), o->units_tmp.end());

@@ -25,7 +25,8 @@ class WaveTables(C.Structure):
 
 class Options(C.Structure):
     _fields_ = [("device", C.c_int), ("stream", C.c_void_p), ("voice_begin", C.c_uint32),
-                ("voice_end", C.c_uint32), ("max_call_len", C.c_uint32), ("sched", C.c_uint32)]
+                ("voice_end", C.c_uint32), ("max_call_len", C.c_uint32), ("sched", C.c_uint32),
+                ("pcm_big_endian", C.c_uint32)]
 
 
 class LineView(C.Structure):
@@ -144,13 +145,13 @@ class Generator:
     """One sauGenerator instance living on a B200."""
 
     def __init__(self, prg, srate=96000, tables=None, device=0, stream=None,
-                 voice_range=None, max_call_len=0, sched=0):
+                 voice_range=None, max_call_len=0, sched=0, big_endian=False):
         self._prg = prg            # borrowed for the generator's life (generator.c:191)
         self._tables = tables
         opt = Options(device=device, stream=stream or 0,
                       voice_begin=voice_range[0] if voice_range else 0,
                       voice_end=voice_range[1] if voice_range else 0,
-                      max_call_len=max_call_len, sched=sched)
+                      max_call_len=max_call_len, sched=sched, pcm_big_endian=int(big_endian))
         tptr = C.addressof(tables) if tables is not None else None
         self.ptr = lib().saugen_create(prg.ptr, srate, tptr, C.byref(opt))
         if not self.ptr:
@@ -256,11 +257,12 @@ def planes_as_torch(ptr, numel):
 
 
 def render(prg, srate=96000, stereo=True, call_len=None, tables=None, device=0, max_frames=None,
-           sched=0):
+           sched=0, big_endian=False):
     """Render a whole program the way Player_run does (saugns.c:575-623)."""
     if call_len is None:
         call_len = srate * 256 // 1000
-    g = Generator(prg, srate, tables=tables, device=device, max_call_len=call_len, sched=sched)
+    g = Generator(prg, srate, tables=tables, device=device, max_call_len=call_len, sched=sched,
+                  big_endian=big_endian)
     ch = 2 if stereo else 1
     chunks, total, more = [], 0, True
     while more:

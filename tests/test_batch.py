@@ -53,3 +53,24 @@ def test_render_batch_matches_reference(ref, port):
         assert got[i].shape == want.shape, i
         assert np.array_equal(got[i], want), i
         assert np.array_equal(sunk[i], want), i
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("stereo", [True, False])
+def test_gpu_big_endian_epilogue_is_the_reference_au_stream(ref, port, tmp_path, stereo):
+    """Rendered with pcm_big_endian (the byte swap of player/sndfile.c:160-168 folded into the
+    mix epilogue) + the 28-byte header == the AU stream `saugns -o -` writes, byte for byte."""
+    import gpuutil
+    import saugns_b200
+    from saugns_b200 import batch
+    if not os.path.exists(REF_CLI):
+        pytest.skip("oracle/_ref/saugns_ref not built")
+    tabs = gpuutil.ref_tables_for_gpu(port)
+    text = scripts.feature_scripts()["voices3"]
+    args = [REF_CLI, "-m", "-d", "-r", "48000", "-e", text, "-o", "-"]
+    if not stereo:
+        args.insert(1, "--mono")
+    want = subprocess.run(args, check=True, capture_output=True).stdout
+    pcm = saugns_b200.render(ref.Program(text), srate=48000, stereo=stereo, tables=tabs,
+                             call_len=48000 * 256 // 1000, big_endian=True)
+    assert batch.au_bytes(pcm, 48000, swapped=True) == want
