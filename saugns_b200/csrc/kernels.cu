@@ -2753,14 +2753,14 @@ render_kernel_wide(const CallDesc *calls, uint32_t ncalls, const SegDesc *segs, 
  * (cp.async.bulk + mbarrier transaction count) into a ring of MIX_STAGES
  * stages, the four consumer warps add behind it.
  * A voice whose pan stands still contributes r = s * pan, computed here
- * (VoiceSeg); only moving pans have an r piece to fetch (one more bulk copy each). */
+ * (VoiceSeg); only moving pans have an r piece, which the consumers read straight
+ * from HBM (a coalesced 128-byte line per warp; rare). */
 constexpr int MIX_FRAMES = ROW_TILE;           // = consumer threads (one per frame)
-constexpr int MIX_TV = 16;                     // voices per stage
-constexpr int MIX_STAGES = 6;
+constexpr int MIX_TV = 32;                     // voices per stage (16 KiB per bulk copy)
+constexpr int MIX_STAGES = 5;
 constexpr int MIX_CWARPS = MIX_FRAMES / 32;    // consumer warps; one more warp produces
 struct MixSmem {
 	float s[MIX_STAGES][MIX_TV][MIX_FRAMES];
-	float r[MIX_STAGES][MIX_TV][MIX_FRAMES];
 	uint2 vi[MIX_STAGES][MIX_TV];              // the tile's VoiceSeg records
 	uint64_t full[MIX_STAGES], empty[MIX_STAGES];
 	uint32_t ndyn[MIX_STAGES];                 // moving-pan voices in the stage's tile
@@ -2859,7 +2859,6 @@ mix_kernel(const CallDesc *calls, const SegDesc *segs, uint32_t mode /*0 pcm, 1 
 		 * pieces are contiguous (one copy), r pieces only for moving pans. */
 		const uint32_t lane = tid & 31u;
 		const float *tile_s = g->rows_s + (size_t) blockIdx.x * tstride;
-		const float *tile_r = g->rows_r + (size_t) blockIdx.x * tstride;
 		/* the records are fetched three stages ahead of their use (their L2 latency
 		 * would otherwise sit in this loop's critical path) */
 		auto fetch = [&](uint32_t t) {
@@ -2880,12 +2879,8 @@ mix_kernel(const CallDesc *calls, const SegDesc *segs, uint32_t mode /*0 pcm, 1 
 			__syncwarp();                      /* vi, ndyn written before lane 0's arrive publishes them */
 			if (lane == 0) {
 				const uint32_t piece = ROW_TILE * (uint32_t) sizeof(float);
-				mbar_expect_tx(&sm.full[st], (nv + __popc(dynmask)) * piece);
+				mbar_expect_tx(&sm.full[st], nv * piece);
 				tma_bulk_g2s(&sm.s[st][0][0], tile_s + (size_t) v0 * ROW_TILE, nv * piece, &sm.full[st]);
-				for (uint32_t m = dynmask; m; m &= m - 1u) {
-					const uint32_t k = __ffs(m) - 1u;
-					tma_bulk_g2s(&sm.r[st][k][0], tile_r + (size_t) (v0 + k) * ROW_TILE, piece, &sm.full[st]);
-				}
 			}
 		}
 		return;
@@ -2895,7 +2890,8 @@ mix_kernel(const CallDesc *calls, const SegDesc *segs, uint32_t mode /*0 pcm, 1 
 		const uint32_t st = t % MIX_STAGES, v0 = t * MIX_TV;
 		const uint32_t nv = nlv - v0 < (uint32_t) MIX_TV ? nlv - v0 : (uint32_t) MIX_TV;
 		mbar_wait(&sm.full[st], (t / MIX_STAGES) & 1u);
-		const float *sp = &sm.s[st][0][tid], *rp = &sm.r[st][0][tid];
+		const float *sp = &sm.s[st][0][tid];
+		const float *rp = g->rows_r + (size_t) blockIdx.x * tstride + (size_t) v0 * ROW_TILE + tid;
 		const uint2 *ip = &sm.vi[st][0];
 		if (nv == (uint32_t) MIX_TV && sm.ndyn[st] == 0) {
 			/* the common tile: all pans stand still */
