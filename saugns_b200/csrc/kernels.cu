@@ -63,14 +63,6 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_
 			" [%0], [%1], %2, [%3];"
 			:: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
-/* 16-byte asynchronous copy global -> shared through the LSU path (L2 only), and
- * an mbarrier arrival that fires when this thread's earlier copies have landed */
-__device__ __forceinline__ void cp_async16(void *dst, const void *src) {
-	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(smem_u32(dst)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_arrive(uint64_t *bar) {
-	asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
-}
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
 }
