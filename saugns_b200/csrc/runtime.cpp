@@ -14,6 +14,7 @@
  *          audio.  There is no CPU fallback.
  */
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -1035,7 +1036,7 @@ static int run_common(saugen_Generator *o, size_t buf_len, int stereo, uint32_t 
 		const uint32_t need = (o->nlv + warps - 1) / warps;
 		uint32_t sched = o->sched;
 		if (sched == 0)
-			sched = (need > resident_ctas && need < 4 * resident_ctas) ? 3 : 1;
+			sched = need > resident_ctas ? 3 : 1;        /* more than one wave: balanced ranges */
 		if (sched == 3 && need <= resident_ctas) sched = 1;   /* a single wave is balanced already */
 		if (sched == 2 || sched == 3) {
 			ticketed_ctas = resident_ctas < need ? resident_ctas : (need ? need : 1);
@@ -1043,9 +1044,31 @@ static int run_common(saugen_Generator *o, size_t buf_len, int stereo, uint32_t 
 			if (getenv("SAUGEN_ONE_CTA")) ticketed_ctas = 1;
 		}
 	}
-	/* one warp per voice: a unit is a whole segment (the steady-block plan then covers
-	 * it in one stretch); ticketed: 4 blocks; balanced: 1 */
-	plan_units(segs, o->units_tmp, sched_mode == 2 ? 1 : sched_mode == 1 ? 4 : (1u << 20));
+	/* Unit size.  One warp per voice: a unit is a whole segment (the steady-stretch plan
+	 * then covers it in one go).  Ticketed: 4 blocks.  Balanced: the warps of the resident
+	 * grid each take items / warps (+-1) units, so large units leave a coarse split
+	 * (the busiest warp sets the time: ceil(items / warps) units) while small units pay
+	 * the per-stretch plan more often (measured: time ~ 1 + 0.57 / blocks per unit);
+	 * pick the size with the best product of the two. */
+	uint32_t unit_blocks = sched_mode == 1 ? 4u : (1u << 20);
+	if (sched_mode == 2) {
+		static const char *ub = getenv("SAUGEN_UNIT_BLOCKS");     /* developer knob */
+		const double S = (double) ticketed_ctas * warps;
+		double best = -1.0;
+		unit_blocks = 1;
+		for (uint32_t cand : {1u, 2u, 3u, 4u, 6u, 8u, 12u, 16u, 24u, 32u, 48u, 96u}) {
+			double units = 0;
+			for (const SegDesc &sd : segs) {
+				const uint32_t ul = cand * REF_BLOCK;
+				units += sd.len ? (sd.len + ul - 1) / ul : 1;
+			}
+			const double per = units * o->nlv / S;
+			const double eff = per / ceil(per) / (1.0 + 0.57 / cand);
+			if (eff > best) { best = eff; unit_blocks = cand; }
+		}
+		if (ub && atoi(ub) > 0) unit_blocks = (uint32_t) atoi(ub);
+	}
+	plan_units(segs, o->units_tmp, unit_blocks);
 	if (o->units_tmp.size() > o->unit_cap) {
 		uint32_t cap = o->unit_cap;
 		while (cap < o->units_tmp.size()) cap *= 2;

@@ -148,14 +148,15 @@ def test_state_after_every_call(S, ref, port, tabs, call_len):
 
 def test_balanced_scheduler_many_voices(S, ref, port, tabs):
     """More voices than resident warps (the shape auto-scheduling splits into
-    balanced ranges with L2 hand-off of voice state between warps): 3000 voices
-    with different durations, events inside the call, vs the oracle port."""
+    balanced ranges with L2 hand-off of voice state between warps, in units of
+    several blocks): 6000 voices with different durations, events inside the
+    call, vs the oracle port."""
     import random
     rnd = random.Random(7)
-    lines = ["S a.m0.004"]
-    for i in range(3000):
+    lines = ["S a.m0.003"]
+    for i in range(6000):
         f = 110.0 * 2 ** rnd.uniform(0, 4)
-        t = rnd.choice([0.02, 0.05, 0.11, 0.15])
+        t = rnd.choice([0.02, 0.05, 0.11, 0.15, 0.3])
         lines.append(f"Wsin f{f:.3f} t{t} a1[g0.2 lxpe] c{rnd.uniform(-1, 1):.3f} "
                      f"p[Wtri r{rnd.choice([0.5, 1, 2])} a0.8[g0.1 llin]]")
     prg = ref.Program("\n".join(lines) + "\n")
