@@ -1549,6 +1549,7 @@ __device__ __noinline__ uint32_t steady_plan(OpState *sops, uint32_t so, uint32_
 	 * frequency buffer that nothing reads as a vector before its operator's phase
 	 * fill (need) then has no per-chunk use at all: its HEAD record is dropped. */
 	uint32_t need = 0;
+	uint32_t line_uni = 0;     /* buffers filled by a uniform LINE record that nothing has touched since */
 	uint8_t head_rec[32];
 	uint32_t killed = 0;
 	uint32_t lstack = 0, depth = 0;    /* layer flags of the unfused operators being walked */
@@ -1557,8 +1558,10 @@ __device__ __noinline__ uint32_t steady_plan(OpState *sops, uint32_t so, uint32_
 	plan += PLAN_REC;          /* slot 0 is the header (render_units) */
 	if (cap) --cap;
 	auto is_uni = [&](uint32_t b) { return b < 32 && ((uni >> b) & 1u); };
-	auto touch = [&](uint32_t b) { if (b < 32) need |= 1u << b; };            /* read as a vector */
-	auto dirty = [&](uint32_t b) { if (b < 32) { uni &= ~(1u << b); need |= 1u << b; } };   /* rewritten */
+	auto touch = [&](uint32_t b) { if (b < 32) { need |= 1u << b; line_uni &= ~(1u << b); } };   /* read as a vector */
+	auto dirty = [&](uint32_t b) {                                             /* rewritten */
+		if (b < 32) { uni &= ~(1u << b); need |= 1u << b; line_uni &= ~(1u << b); }
+	};
 	auto uval = [&](uint32_t b) { return lds32f(sb + b * PLAN_FBUF); };
 	auto set_uni = [&](uint32_t b, float f) {
 		if (b < 32) { uni |= 1u << b; need &= ~(1u << b); sts32(sb + b * PLAN_FBUF, __float_as_uint(f)); }
@@ -1659,10 +1662,26 @@ __device__ __noinline__ uint32_t steady_plan(OpState *sops, uint32_t so, uint32_
 						(uint32_t) in.a << 16 | (uint32_t) in.b << 24, (uint32_t) in.c << 16, opa, 0u,
 						0.f, 0.f, f, 0.f);
 				dirty(in.a);
-				if (u) { set_uni(in.a, f); touch(in.a); }     /* LINE records are never dropped */
+				if (u) {           /* dropped only by a RANGE that takes the value as a scalar */
+					set_uni(in.a, f); touch(in.a);
+					if (in.a < 32) { line_uni |= 1u << in.a; head_rec[in.a] = (uint8_t) (n - 1); }
+				}
 			}
 			break;
 		case I_RANGE:
+			if (in.a < 32 && in.b < 32 && ((line_uni >> in.a) & 1u) && ((line_uni >> in.b) & 1u)) {
+				/* both ends of the range are uniform lines nothing else has read: they go
+				 * into the record as scalars and their LINE records have no use left */
+				const float pv = uval(in.a), rv = uval(in.b);
+				sts32(plan + head_rec[in.a] * PLAN_REC, 0u);
+				sts32(plan + head_rec[in.b] * PLAN_REC, 0u);
+				killed += 2;
+				touch(in.c);
+				plan_put(plan, n++, P_RANGE | PF_FUNI << 8 | (uint32_t) in.a << 16 | (uint32_t) in.b << 24, in.c,
+						0u, 0u, 0.f, 0.f, pv, rv);
+				dirty(in.a); dirty(in.b);
+				break;
+			}
 			plan_put(plan, n++, P_RANGE | (uint32_t) in.a << 16 | (uint32_t) in.b << 24, in.c, 0u, 0u,
 					0.f, 0.f, 0.f, 0.f);
 			dirty(in.a); touch(in.b); touch(in.c);
@@ -2326,7 +2345,14 @@ __device__ __forceinline__ void run_chunk_plan(const HotCtx &c, const uint32_t n
 			osc_plan<NS, CTAB>(c, p0, rec, pure, inc, ph);
 		} else if (kind == P_RANGE) {                              /* generator.c:465-467 */
 			float p[NS], rr[NS], m[NS];
-			fld<NS>(c, bufa, p); fld<NS>(c, bufb, rr); fld<NS>(c, p0.y & 0xffu, m);
+			fld<NS>(c, p0.y & 0xffu, m);
+			if (flags & PF_FUNI) {             /* both ends uniform: scalars from the record */
+				const float2 pr = lds64f(rec + 24);
+#pragma unroll
+				for (int k = 0; k < NS; ++k) { p[k] = pr.x; rr[k] = pr.y; }
+			} else {
+				fld<NS>(c, bufa, p); fld<NS>(c, bufb, rr);
+			}
 #pragma unroll
 			for (int k = 0; k < NS; ++k) p[k] += (rr[k] - p[k]) * m[k];
 			fst<NS>(c, bufa, p);

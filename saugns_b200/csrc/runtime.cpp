@@ -1037,7 +1037,7 @@ static int run_common(saugen_Generator *o, size_t buf_len, int stereo, uint32_t 
 		uint32_t sched = o->sched;
 		if (sched == 0)
 			sched = need > resident_ctas ? 3 : 1;        /* more than one wave: balanced ranges */
-		if (sched == 3 && need <= resident_ctas) sched = 1;   /* a single wave is balanced already */
+		if (sched == 3 && need <= resident_ctas && !getenv("SAUGEN_FORCE_BALANCED")) sched = 1;   /* a single wave is balanced already */
 		if (sched == 2 || sched == 3) {
 			ticketed_ctas = resident_ctas < need ? resident_ctas : (need ? need : 1);
 			sched_mode = sched == 2 ? 1 : 2;
@@ -1066,6 +1066,10 @@ static int run_common(saugen_Generator *o, size_t buf_len, int stereo, uint32_t 
 			const double eff = per / ceil(per) / (1.0 + 0.57 / cand);
 			if (eff > best) { best = eff; unit_blocks = cand; }
 		}
+		if (ub && atoi(ub) > 0) unit_blocks = (uint32_t) atoi(ub);
+	}
+	if (sched_mode == 1) {
+		static const char *ub = getenv("SAUGEN_UNIT_BLOCKS");
 		if (ub && atoi(ub) > 0) unit_blocks = (uint32_t) atoi(ub);
 	}
 	plan_units(segs, o->units_tmp, unit_blocks);
