@@ -1644,9 +1644,23 @@ __device__ __noinline__ uint32_t steady_plan(OpState *sops, uint32_t so, uint32_
 		case I_MIX:                                                  /* generator.c:384-440 */
 			if (!depth) return 0;
 			if (in.b != NO_BUF) touch(in.b);
-			touch(in.c);
-			plan_put(plan, n++, P_MIX | (((lstack & 1u) ? PF_LAYER : 0u) | ((in.flags & F_WAVEENV) ? PF_WAVEENV : 0u)) << 8 |
-					(uint32_t) in.a << 16 | (uint32_t) in.b << 24, (uint32_t) in.c, 0u, 0u, 0.f, 0.f, 0.f, 0.f);
+			{
+				/* a constant amplitude (uniform LINE nothing else has read) goes into the
+				 * record as a scalar (in the operator word) and its LINE record is dropped */
+				const bool ac = in.c < 32 && ((line_uni >> in.c) & 1u);
+				uint32_t av = 0;
+				if (ac) {
+					av = __float_as_uint(uval(in.c));
+					sts32(plan + head_rec[in.c] * PLAN_REC, 0u);
+					++killed;
+					dirty(in.c);
+				} else {
+					touch(in.c);
+				}
+				plan_put(plan, n++, P_MIX | (((lstack & 1u) ? PF_LAYER : 0u) | ((in.flags & F_WAVEENV) ? PF_WAVEENV : 0u) |
+						(ac ? PF_ACONST : 0u)) << 8 | (uint32_t) in.a << 16 | (uint32_t) in.b << 24,
+						(uint32_t) in.c, av, 0u, 0.f, 0.f, 0.f, 0.f);
+			}
 			dirty(in.a);
 			break;
 		case I_LINE:
@@ -2276,7 +2290,12 @@ __device__ __noinline__ void plan_other(uint32_t kind, uint32_t sb0, int lane, f
 	if (kind == P_MIX) {                                           /* block_mix_*, generator.c:384-440 */
 		float x[SPL] = {1.f, 1.f, 1.f, 1.f}, a[SPL];
 		if (in.b != NO_BUF) ld4(c, in.b, x);
-		ld4(c, in.c, a);
+		if ((w0 >> 8) & PF_ACONST) {               /* `op` carries the constant amplitude */
+#pragma unroll
+			for (int k = 0; k < SPL; ++k) a[k] = __uint_as_float(op);
+		} else {
+			ld4(c, in.c, a);
+		}
 		mix_eval<true>(c, in.a, x, a, CHUNK, (w0 >> 8) & PF_LAYER, ((w0 >> 8) & PF_WAVEENV) != 0);
 	}
 	else if (kind == P_NOISE) noise_run(c, in, CHUNK);             /* sauNoiseG_run_*, noise.h:41-185 */

@@ -5,7 +5,7 @@ sys.path.insert(0, ROOT)
 import saugns_b200
 from saugns_b200 import workloads
 for voices in [int(x) for x in sys.argv[1:]] or [4096]:
-    prg = workloads.build_c3(voices, 60, seed=1, fm="mix")
+    prg = workloads.build_c3(voices, 60, seed=1, fm={"mix": "mix", "1": True, "0": False}[os.environ.get("FM", "mix")])
     g = saugns_b200.Generator(prg, 96000, max_call_len=24576, sched=int(os.environ.get("SCHED", "0")))
     for _ in range(3):
         g.run_device(24576)
