@@ -397,6 +397,38 @@ def run_gpu_config(args):
     tabs = saugns_b200.WaveTables.from_buffer_copy(bytes(t))
     tabs._keep = t
     K, W = args.steps, args.warmup
+    if args.workload == "c3-sharded":
+        # ONE 4096-voice script, its voices spread over the ranks (strong scaling): each rank
+        # renders its voices' float mix planes, one NCCL sum-reduce per call, root converts
+        import torch.distributed as dist
+        from saugns_b200 import multigpu
+        if world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        prg = workloads.build_c3(VOICES, SECS, seed=1, fm="mix")
+        vg = multigpu.VoiceShardedGenerator(prg, SRATE, device=local_rank, max_call_len=FRAMES)
+        for _ in range(W):
+            vg.run(FRAMES)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(K):
+            more, pcm, n = vg.run(FRAMES)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        wall = time.perf_counter() - t0
+        vg.close()
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "workload": "C3, ONE 4096-voice script voice-sharded over "
+                              f"{world} GPU(s): one ncclReduce of the float L/R planes per call, PCM on the "
+                              "root's host buffer", "value": VOICES * FRAMES * K / wall,
+                              "unit": "voice-samples/s", "n_gpus": world, "steps": K,
+                              "ms_per_step": 1000 * wall / K, "scaling": "strong",
+                              "realtime_factor": (FRAMES * K / SRATE) / wall}))
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
     if args.workload == "c4":
         nv = 1024
         prg = pyref.Program(workloads.synth_c4(nv, SECS))
@@ -467,7 +499,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--workload", default="c3", choices=["c3", "c4", "c5"])
+    ap.add_argument("--workload", default="c3", choices=["c3", "c4", "c5", "c3-sharded"])
     ap.add_argument("--scripts", type=int, default=1250, help="c5: scripts on this GPU")
     ap.add_argument("--group", type=int, default=128, help="c5: generators in flight per driver thread")
     ap.add_argument("--threads", type=int, default=1, help="c5: driver threads")
