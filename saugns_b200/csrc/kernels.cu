@@ -2139,8 +2139,9 @@ __device__ __forceinline__ void phase_plan(const HotCtx &c, const uint32_t op, c
 }
 
 /* Oscillator, amplitude and block_mix of a wave operator on a steady full chunk
- * (sauWOsc_run, wosc.h:238-266; generator.c:584-601) at the phases ph.  pure:
- * every phase difference is `inc` (uniform frequency, no PM).  The amplitude is
+ * (sauWOsc_run, wosc.h:238-266; generator.c:584-601) at the phases ph.  (pure:
+ * every phase difference is `inc`; one division instead of four was measured
+ * SLOWER than four in one block with the table evaluation.)  The amplitude is
  * the operator's own line, or (PF_ABUF) a buffer its modulators wrote. */
 template <int NS, bool CTAB>
 __device__ __forceinline__ void osc_plan(const HotCtx &c, const uint4 p0, const uint32_t rec,
@@ -2154,6 +2155,20 @@ __device__ __forceinline__ void osc_plan(const HotCtx &c, const uint4 p0, const 
 	__syncwarp();              /* every lane holds the carried values before lane 31 rewrites them */
 	float s[NS];
 	{
+		/* the phase differences and their quotients diff_scale / d first (FP32, from the
+		 * phases alone; a zero difference gives a quotient nobody uses): in one block
+		 * with the table evaluation below, they fill the FP64 pipe's latency */
+		uint32_t pph = __shfl_up_sync(FULL, ph[NS - 1], 1);
+		if (c.lane == 0) pph = pph0;
+		int32_t d[NS];
+		d[0] = (int32_t) (ph[0] - pph);
+#pragma unroll
+		for (int k = 1; k < NS; ++k) d[k] = (int32_t) (ph[k] - ph[k - 1]);
+		const float2 dd = lds64f(rec + 16);
+		const float ds = dd.x;
+		float xq[NS];
+#pragma unroll
+		for (int k = 0; k < NS; ++k) xq[k] = div_scale_by_int(ds, d[k]);   /* wosc.h:254-256 */
 		double Is[NS];
 		if (CTAB) {
 			/* per-index coefficients from shared memory: two loads, Horner */
@@ -2174,16 +2189,8 @@ __device__ __forceinline__ void osc_plan(const HotCtx &c, const uint4 p0, const 
 				Is[k] = horner_frac(c3, c2, c1, ph[k]) + (double) s1;
 			}
 		}
-		uint32_t pph = __shfl_up_sync(FULL, ph[NS - 1], 1);
 		double pIs = __shfl_up_sync(FULL, Is[NS - 1], 1);
-		if (c.lane == 0) {
-			pph = pph0;
-			pIs = __hiloint2double((int) pg.y, (int) pg.x);
-		}
-		int32_t d[NS];
-		d[0] = (int32_t) (ph[0] - pph);
-#pragma unroll
-		for (int k = 1; k < NS; ++k) d[k] = (int32_t) (ph[k] - ph[k - 1]);
+		if (c.lane == 0) pIs = __hiloint2double((int) pg.y, (int) pg.x);
 		bool z = false;
 #pragma unroll
 		for (int k = 0; k < NS; ++k) z |= (d[k] == 0);
@@ -2201,27 +2208,11 @@ __device__ __forceinline__ void osc_plan(const HotCtx &c, const uint4 p0, const 
 #pragma unroll
 			for (int k = 0; k < NS; ++k) s[k] = sv.v[k];
 		} else {
-			const float2 dd = lds64f(rec + 16);
-			const float ds = dd.x;
 			const double doff = (double) dd.y;
-			if (pure) {
-				/* a pure tone: every phase difference is inc, one division per lane
-				 * (lane 0's first sample follows the carried phase, which an event
-				 * may have moved) */
-				const float xq = div_scale_by_int(ds, (int32_t) inc);
-				const double xqd = (double) xq;
-				double xq0 = xqd;
-				if (d[0] != (int32_t) inc) xq0 = (double) div_scale_by_int(ds, d[0]);
-				s[0] = (float) ((Is[0] - pIs) * xq0 + doff);
 #pragma unroll
-				for (int k = 1; k < NS; ++k) s[k] = (float) ((Is[k] - Is[k - 1]) * xqd + doff);
-			} else {
-#pragma unroll
-				for (int k = 0; k < NS; ++k) {                           /* wosc.h:254-256 */
-					const float xq = div_scale_by_int(ds, d[k]);
-					const double dI = Is[k] - (k ? Is[k - 1] : pIs);
-					s[k] = (float) (dI * (double) xq + doff);
-				}
+			for (int k = 0; k < NS; ++k) {
+				const double dI = Is[k] - (k ? Is[k - 1] : pIs);
+				s[k] = (float) (dI * (double) xq[k] + doff);
 			}
 			if (c.lane == 31) {
 				sts32(op + OS_I1, ph[NS - 1]);
