@@ -456,7 +456,11 @@ def run_gpu_config(args):
         return 0
     # c5: independent scripts, this GPU's share of 10 000 (default 10000/8 = 1250)
     n = args.scripts
-    texts = [workloads.synth_c5_script(i) for i in range(n)]
+    dist = None
+    if world > 1:              # script sharding: every rank its own scripts, no data-path collective
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    texts = [workloads.synth_c5_script(rank * n + i) for i in range(n)]
     t0 = time.perf_counter()
     prgs = [pyref.Program(x) for x in texts]
     parse_s = time.perf_counter() - t0
@@ -469,6 +473,8 @@ def run_gpu_config(args):
                     vs += od["time"][0] * SRATE // 1000
     batch.render_batch(prgs[:16], srate=SRATE, device=local_rank, tables=tabs, group_size=16)  # warm-up
     torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
     t0 = time.perf_counter()
     got = {}
 
@@ -481,8 +487,20 @@ def run_gpu_config(args):
     wall = time.perf_counter() - t0
     assert len(got) == n
     frames = sum(v[0] for v in got.values())
-    line = {"metric": METRIC, "workload": f"C5: {n} independent mixed scripts (4-16 voices, W/N/R, "
-            "1-10 s) on one GPU, batched saugen_run_many, every script's PCM delivered to a host "
+    if dist is not None:       # whole job: all ranks' scripts over the slowest rank's time
+        t = torch.tensor([wall, -float(vs), -float(frames)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        wall = float(t[0].item())
+        tot = torch.tensor([float(vs), float(frames)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        vs, frames = int(tot[0].item()), int(tot[1].item())
+        dist.destroy_process_group()
+        if rank != 0:
+            return 0
+        n = n * world
+    line = {"metric": METRIC, "n_gpus": world, "scaling": "weak",
+            "workload": f"C5: {n} independent mixed scripts (4-16 voices, W/N/R, "
+            f"1-10 s) on {world} GPU(s), batched saugen_run_many, every script's PCM delivered to a host "
             f"sink (arrays recycled), {args.threads} driver thread(s) x 2 alternating "
             f"live sets, {args.call_frames}-frame calls",
             "value": vs / wall, "unit": "voice-samples/s", "scripts": n, "group": args.group,
