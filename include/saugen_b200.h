@@ -59,6 +59,18 @@ typedef struct saugen_Options {
 saugen_Generator *saugen_create(const sauabi_Program *prg, uint32_t srate,
 		const saugen_WaveTables *tables, const saugen_Options *opt);
 
+/* The flat program (the "instruction form" of
+ * sau/parser/parseconv.h:282-331,544-571 taken one step further): everything
+ * saugen_create derives from a sauProgram -- events and op-data with pointers turned
+ * into indices and ms into samples, the per-voice bytecode, the event timeline -- as
+ * one relocatable blob.  saugen_flatten needs no GPU and returns the blob's size
+ * (call with blob = NULL to ask); saugen_create_flat instantiates it on any device
+ * without the sauProgram: parse and flatten once, render anywhere (other
+ * processes, other GPUs).  0 / NULL on error. */
+size_t saugen_flatten(const sauabi_Program *prg, uint32_t srate, void *blob, size_t cap);
+saugen_Generator *saugen_create_flat(const void *blob, size_t size,
+		const saugen_WaveTables *tables, const saugen_Options *opt);
+
 /* == sau_destroy_Generator(o); NULL-safe. */
 void saugen_destroy(saugen_Generator *o);
 

@@ -598,47 +598,36 @@ static void flatten_line(LineDelta *d, const sauabi_Line *s, uint32_t srate) {
 
 extern "C" void saugen_destroy(saugen_Generator *o);
 
-extern "C" saugen_Generator *saugen_create(const sauabi_Program *prg, uint32_t srate,
-		const saugen_WaveTables *tables, const saugen_Options *opt) {
-	saugen_Options defopt;
-	memset(&defopt, 0, sizeof defopt);
-	if (!opt) opt = &defopt;
-	if (!prg || !srate) { g_err = "saugen_create: NULL program or zero sample rate"; return nullptr; }
-	int ndev = 0;
-	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || opt->device >= ndev) {
-		set_err("saugen_create: no usable CUDA device (this back end has no CPU path)", cudaGetLastError());
-		return nullptr;
-	}
-	saugen_Generator *o = new saugen_Generator();
-	long long tp = now_ns();
-	auto lap = [&tp](int i) { if (g_cprof.on) { const long long t = now_ns(); g_cprof.ns[i] += t - tp; tp = t; } };
-	std::vector<HostOp> hops(prg->op_count);
-	std::vector<EventRec> events(prg->ev_count);
+/* ---- the flat program: everything saugen_create derives from a sauProgram ----- *
+ * (the device-ready, index-based "instruction form").
+ * Events and op-data with pointers turned into indices and ms into samples, the
+ * per-voice bytecode, the event timeline.  It does not need the sauProgram any
+ * more, serialises to one relocatable blob (saugen_flatten) and instantiates on
+ * any device (saugen_create_flat): parse and flatten once, render anywhere. */
+struct Flat {
+	uint32_t srate = 0, vo_count = 0, op_count = 0;
+	uint32_t nbufs = 1, max_ops = 1, nplan = 0, wave_mask = 0;
+	float amp_scale = 0.f;
+	std::vector<uint64_t> ev_time;
+	std::vector<EventRec> events;
 	std::vector<OpDataRec> opdata;
 	std::vector<Instr> code;
+	std::vector<uint32_t> prog_ops, vev_off, vev_idx;
+};
+
+static bool flatten_program(const sauabi_Program *prg, uint32_t srate, Flat &f) {
+	Flat *o = &f;
+	f.srate = srate; f.vo_count = prg->vo_count; f.op_count = prg->op_count;
+	std::vector<EventRec> &events = f.events;
+	std::vector<OpDataRec> &opdata = f.opdata;
+	std::vector<Instr> &code = f.code;
+	std::vector<uint32_t> &prog_ops = f.prog_ops, &vev_off = f.vev_off, &vev_idx = f.vev_idx;
+	events.assign(prg->ev_count, EventRec());
+	std::vector<HostOp> hops(prg->op_count);
 	std::vector<std::vector<uint32_t>> vev(prg->vo_count);
-	std::vector<uint32_t> vev_off, vev_idx;
 	std::vector<uint32_t> vcarr(prg->vo_count, 0xffffffffu);
 	std::vector<std::pair<uint32_t, uint32_t>> vprog(prg->vo_count, {0u, 0u});
 	std::vector<std::pair<uint32_t, uint32_t>> vops(prg->vo_count, {0u, 0u});
-	std::vector<uint32_t> prog_ops;
-	if (!tables) tables = saugen::builtin_wave_tables();
-
-	o->prg = prg; o->srate = srate; o->device = opt->device; o->sched = opt->sched;
-	o->big_endian = opt->pcm_big_endian != 0;
-	o->vo_count = prg->vo_count; o->op_count = prg->op_count;
-	o->voice_begin = 0; o->voice_end = prg->vo_count;
-	if (opt->voice_end > opt->voice_begin) {
-		o->voice_begin = opt->voice_begin < prg->vo_count ? opt->voice_begin : prg->vo_count;
-		o->voice_end = opt->voice_end < prg->vo_count ? opt->voice_end : prg->vo_count;
-	}
-	o->nlv = o->voice_end - o->voice_begin;
-	o->row_len = opt->max_call_len ? opt->max_call_len : ms_in_samples(256, srate, NULL);  /* saugns.c:471 */
-	o->row_len = (o->row_len + 3u) & ~3u;
-	if (o->row_len < 4) o->row_len = 4;
-	/* carrier rows are frame-tile major (device_types.h:ROW_TILE): the stride between
-	 * tiles is one 512-byte piece per local voice */
-	o->row_stride = (o->nlv ? o->nlv : 1u) * (uint32_t) ROW_TILE;
 	o->amp_scale = 0.5f * prg->ampmult;                           /* generator.c:183-185 */
 	if (prg->mode & SAUABI_PMODE_AMP_DIV_VOICES) o->amp_scale /= (float) prg->vo_count;
 
@@ -755,8 +744,7 @@ extern "C" saugen_Generator *saugen_create(const sauabi_Program *prg, uint32_t s
 		if (comp.too_deep) {
 			g_err = "saugen_create: operator nesting too deep for the device interpreter";
 			fprintf(stderr, "saugen_b200: error: %s\n", g_err.c_str());
-			delete o;
-			return nullptr;
+			return false;
 		}
 		o->nbufs = comp.max_buf ? comp.max_buf : 1;
 	}
@@ -767,8 +755,49 @@ extern "C" saugen_Generator *saugen_create(const sauabi_Program *prg, uint32_t s
 	}
 	vev_off[prg->vo_count] = (uint32_t) vev_idx.size();
 
-	/* ---- device allocation: one state block, one row block, one pinned block ---- */
+	return true;
+}
+
+static saugen_Generator *create_from_flat(const Flat &f, const saugen_WaveTables *tables,
+		const saugen_Options *opt) {
+	saugen_Options defopt;
+	memset(&defopt, 0, sizeof defopt);
+	if (!opt) opt = &defopt;
+	int ndev = 0;
+	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || opt->device >= ndev) {
+		set_err("saugen_create: no usable CUDA device (this back end has no CPU path)", cudaGetLastError());
+		return nullptr;
+	}
+	saugen_Generator *o = new saugen_Generator();
+	long long tp = now_ns();
+	auto lap = [&tp](int i) { if (g_cprof.on) { const long long t = now_ns(); g_cprof.ns[i] += t - tp; tp = t; } };
+	const std::vector<EventRec> &events = f.events;
+	const std::vector<OpDataRec> &opdata = f.opdata;
+	const std::vector<Instr> &code = f.code;
+	const std::vector<uint32_t> &prog_ops = f.prog_ops, &vev_off = f.vev_off, &vev_idx = f.vev_idx;
+	const uint32_t srate = f.srate;
+	if (!tables) tables = saugen::builtin_wave_tables();
+
+	o->srate = srate; o->device = opt->device; o->sched = opt->sched;
+	o->big_endian = opt->pcm_big_endian != 0;
+	o->vo_count = f.vo_count; o->op_count = f.op_count;
+	o->voice_begin = 0; o->voice_end = f.vo_count;
+	if (opt->voice_end > opt->voice_begin) {
+		o->voice_begin = opt->voice_begin < f.vo_count ? opt->voice_begin : f.vo_count;
+		o->voice_end = opt->voice_end < f.vo_count ? opt->voice_end : f.vo_count;
+	}
+	o->nlv = o->voice_end - o->voice_begin;
+	o->row_len = opt->max_call_len ? opt->max_call_len : ms_in_samples(256, srate, NULL);  /* saugns.c:471 */
+	o->row_len = (o->row_len + 3u) & ~3u;
+	if (o->row_len < 4) o->row_len = 4;
+	/* carrier rows are frame-tile major (device_types.h:ROW_TILE): the stride between
+	 * tiles is one 512-byte piece per local voice */
+	o->row_stride = (o->nlv ? o->nlv : 1u) * (uint32_t) ROW_TILE;
+	o->amp_scale = f.amp_scale;
+	o->ev_time = f.ev_time;
+	o->nbufs = f.nbufs; o->max_ops = f.max_ops; o->nplan = f.nplan; o->wave_mask = f.wave_mask;
 	lap(0);
+	/* ---- device allocation: one state block, one row block, one pinned block ---- */
 	CK(cudaSetDevice(o->device));
 	if (opt->stream) o->stream = (cudaStream_t) opt->stream;
 	else {
@@ -780,7 +809,7 @@ extern "C" saugen_Generator *saugen_create(const sauabi_Program *prg, uint32_t s
 	if (!o->d_tables) { set_err("wave table upload", cudaGetLastError()); goto fail; }
 	{
 		lap(1);
-		const size_t nops = prg->op_count ? prg->op_count : 1, nvo = prg->vo_count ? prg->vo_count : 1;
+		const size_t nops = f.op_count ? f.op_count : 1, nvo = f.vo_count ? f.vo_count : 1;
 		const size_t nl = o->nlv ? o->nlv : 1;
 		o->seg_cap = 64;
 		o->unit_cap = 256;
@@ -882,6 +911,90 @@ extern "C" saugen_Generator *saugen_create(const sauabi_Program *prg, uint32_t s
 fail:
 	saugen_destroy(o);
 	return nullptr;
+}
+
+extern "C" saugen_Generator *saugen_create(const sauabi_Program *prg, uint32_t srate,
+		const saugen_WaveTables *tables, const saugen_Options *opt) {
+	if (!prg || !srate) { g_err = "saugen_create: NULL program or zero sample rate"; return nullptr; }
+	int ndev = 0;              /* no device: fail before anything else (there is no CPU path) */
+	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || (opt && opt->device >= ndev)) {
+		set_err("saugen_create: no usable CUDA device (this back end has no CPU path)", cudaGetLastError());
+		return nullptr;
+	}
+	Flat f;
+	if (!flatten_program(prg, srate, f)) return nullptr;
+	return create_from_flat(f, tables, opt);
+}
+
+/* The flat program as one relocatable blob: a header of counts, then the arrays. */
+namespace {
+struct FlatHeader {
+	uint32_t magic, version, srate, vo_count, op_count, nbufs, max_ops, nplan, wave_mask;
+	float amp_scale;
+	uint64_t n_ev_time, n_events, n_opdata, n_code, n_prog_ops, n_vev_off, n_vev_idx;
+};
+const uint32_t FLAT_MAGIC = 0x46554153u /* "SAUF" */, FLAT_VERSION = 1;
+template <typename T> size_t blob_bytes(const std::vector<T> &v) { return (v.size() * sizeof(T) + 7) & ~(size_t) 7; }
+}
+
+extern "C" size_t saugen_flatten(const sauabi_Program *prg, uint32_t srate, void *blob, size_t cap) {
+	if (!prg || !srate) { g_err = "saugen_flatten: NULL program or zero sample rate"; return 0; }
+	Flat f;
+	if (!flatten_program(prg, srate, f)) return 0;
+	const size_t need = sizeof(FlatHeader) + blob_bytes(f.ev_time) + blob_bytes(f.events) + blob_bytes(f.opdata) +
+		blob_bytes(f.code) + blob_bytes(f.prog_ops) + blob_bytes(f.vev_off) + blob_bytes(f.vev_idx);
+	if (!blob || cap < need) return need;
+	memset(blob, 0, need);
+	FlatHeader h;
+	memset(&h, 0, sizeof h);
+	h.magic = FLAT_MAGIC; h.version = FLAT_VERSION; h.srate = f.srate; h.vo_count = f.vo_count;
+	h.op_count = f.op_count; h.nbufs = f.nbufs; h.max_ops = f.max_ops; h.nplan = f.nplan;
+	h.wave_mask = f.wave_mask; h.amp_scale = f.amp_scale;
+	h.n_ev_time = f.ev_time.size(); h.n_events = f.events.size(); h.n_opdata = f.opdata.size();
+	h.n_code = f.code.size(); h.n_prog_ops = f.prog_ops.size(); h.n_vev_off = f.vev_off.size();
+	h.n_vev_idx = f.vev_idx.size();
+	unsigned char *p = (unsigned char*) blob;
+	memcpy(p, &h, sizeof h); p += sizeof h;
+	auto put = [&p](const void *src, size_t n, size_t padded) { if (n) memcpy(p, src, n); p += padded; };
+	put(f.ev_time.data(), f.ev_time.size() * sizeof(uint64_t), blob_bytes(f.ev_time));
+	put(f.events.data(), f.events.size() * sizeof(EventRec), blob_bytes(f.events));
+	put(f.opdata.data(), f.opdata.size() * sizeof(OpDataRec), blob_bytes(f.opdata));
+	put(f.code.data(), f.code.size() * sizeof(Instr), blob_bytes(f.code));
+	put(f.prog_ops.data(), f.prog_ops.size() * sizeof(uint32_t), blob_bytes(f.prog_ops));
+	put(f.vev_off.data(), f.vev_off.size() * sizeof(uint32_t), blob_bytes(f.vev_off));
+	put(f.vev_idx.data(), f.vev_idx.size() * sizeof(uint32_t), blob_bytes(f.vev_idx));
+	return need;
+}
+
+extern "C" saugen_Generator *saugen_create_flat(const void *blob, size_t size,
+		const saugen_WaveTables *tables, const saugen_Options *opt) {
+	FlatHeader h;
+	if (!blob || size < sizeof h) { g_err = "saugen_create_flat: no blob"; return nullptr; }
+	memcpy(&h, blob, sizeof h);
+	if (h.magic != FLAT_MAGIC || h.version != FLAT_VERSION || !h.srate) {
+		g_err = "saugen_create_flat: not a flat program of this library version";
+		return nullptr;
+	}
+	Flat f;
+	f.srate = h.srate; f.vo_count = h.vo_count; f.op_count = h.op_count; f.nbufs = h.nbufs;
+	f.max_ops = h.max_ops; f.nplan = h.nplan; f.wave_mask = h.wave_mask; f.amp_scale = h.amp_scale;
+	const unsigned char *p = (const unsigned char*) blob + sizeof h, *end = (const unsigned char*) blob + size;
+	bool ok = true;
+	auto get = [&](auto &vec, uint64_t n) {
+		typedef typename std::remove_reference<decltype(vec)>::type::value_type T;
+		const size_t bytes = (size_t) n * sizeof(T), padded = (bytes + 7) & ~(size_t) 7;
+		if (!ok || n > ((uint64_t) 1 << 32) || (size_t) (end - p) < padded) { ok = false; return; }
+		vec.resize((size_t) n);
+		if (bytes) memcpy(vec.data(), p, bytes);
+		p += padded;
+	};
+	get(f.ev_time, h.n_ev_time); get(f.events, h.n_events); get(f.opdata, h.n_opdata); get(f.code, h.n_code);
+	get(f.prog_ops, h.n_prog_ops); get(f.vev_off, h.n_vev_off); get(f.vev_idx, h.n_vev_idx);
+	if (!ok || f.vev_off.size() != (size_t) f.vo_count + 1 || f.ev_time.size() != f.events.size()) {
+		g_err = "saugen_create_flat: truncated or inconsistent blob";
+		return nullptr;
+	}
+	return create_from_flat(f, tables, opt);
 }
 
 extern "C" void saugen_destroy(saugen_Generator *o) {

@@ -61,6 +61,10 @@ def lib():
         L.saugen_create.restype = C.c_void_p
         L.saugen_create.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
         L.saugen_destroy.argtypes = [C.c_void_p]
+        L.saugen_flatten.restype = C.c_size_t
+        L.saugen_flatten.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t]
+        L.saugen_create_flat.restype = C.c_void_p
+        L.saugen_create_flat.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
         L.saugen_run.restype = C.c_int
         L.saugen_run.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int,
                                  C.POINTER(C.c_size_t)]
@@ -148,12 +152,17 @@ class Generator:
                  voice_range=None, max_call_len=0, sched=0, big_endian=False):
         self._prg = prg            # borrowed for the generator's life (generator.c:191)
         self._tables = tables
+        flat = prg if isinstance(prg, (bytes, bytearray)) else None   # a saugen_flatten blob
         opt = Options(device=device, stream=stream or 0,
                       voice_begin=voice_range[0] if voice_range else 0,
                       voice_end=voice_range[1] if voice_range else 0,
                       max_call_len=max_call_len, sched=sched, pcm_big_endian=int(big_endian))
         tptr = C.addressof(tables) if tables is not None else None
-        self.ptr = lib().saugen_create(prg.ptr, srate, tptr, C.byref(opt))
+        if flat is not None:
+            buf = (C.c_char * len(flat)).from_buffer_copy(flat)
+            self.ptr = lib().saugen_create_flat(buf, len(flat), tptr, C.byref(opt))
+        else:
+            self.ptr = lib().saugen_create(prg.ptr, srate, tptr, C.byref(opt))
         if not self.ptr:
             raise RuntimeError("saugen_create failed: " + last_error())
         self.srate = srate
@@ -239,6 +248,19 @@ class Generator:
             self.close()
         except Exception:
             pass
+
+
+def flatten(prg, srate=96000):
+    """saugen_flatten: the program as one relocatable blob (bytes); needs no GPU.
+    Generator(blob, ...) / render(blob, ...) instantiate it (the sample rate is the blob's)."""
+    L = lib()
+    need = L.saugen_flatten(prg.ptr, srate, None, 0)
+    if not need:
+        raise RuntimeError("saugen_flatten failed: " + last_error())
+    buf = (C.c_char * need)()
+    if L.saugen_flatten(prg.ptr, srate, buf, need) != need:
+        raise RuntimeError("saugen_flatten failed: " + last_error())
+    return bytes(buf)
 
 
 class _DevArray:
