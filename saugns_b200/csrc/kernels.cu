@@ -1527,8 +1527,10 @@ constexpr uint32_t PLAN_REC = 32;     /* bytes: w0 kind|flags<<8|a<<16|b<<24, w1
                                        * w2 operator state (shared address), w3 table (shared address),
                                        * w4 diff_scale, w5 diff_offset, w6 uniform value / phase increment, w7 av */
 
+/* every lane walks the bytecode (each needs the result); lane 0 alone writes the plan */
 __device__ __forceinline__ void plan_put(uint32_t plan, uint32_t n, uint32_t w0, uint32_t w1, uint32_t w2,
 		uint32_t w3, float w4, float w5, float w6, float w7) {
+	if ((threadIdx.x & 31u) != 0u) return;
 	const uint32_t a = plan + n * PLAN_REC;
 	asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(a), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
 	sts128(a + 16, make_float4(w4, w5, w6, w7));
@@ -1552,6 +1554,7 @@ __device__ __noinline__ uint32_t steady_plan(OpState *sops, uint32_t so, uint32_
 	uint32_t line_uni = 0;     /* buffers filled by a uniform LINE record that nothing has touched since */
 	uint8_t head_rec[32];
 	uint32_t killed = 0;
+	const bool lane0 = (threadIdx.x & 31u) == 0u;
 	uint32_t lstack = 0, depth = 0;    /* layer flags of the unfused operators being walked */
 	uint32_t entered = 0;              /* operator slots that came in through an ENTER */
 	uint32_t n = 0;
@@ -1568,13 +1571,14 @@ __device__ __noinline__ uint32_t steady_plan(OpState *sops, uint32_t so, uint32_
 	};
 	auto finish = [&](uint32_t nrec) -> uint32_t {
 		if (!nrec) return 0u;
+		__syncwarp();                              /* lane 0's records are in place */
 		if (killed) {                              /* close the gaps the dropped records left */
 			uint32_t w = 0;
 			for (uint32_t r = 0; r < nrec; ++r) {
 				const uint4 x = lds128u(plan + r * PLAN_REC), y = lds128u(plan + r * PLAN_REC + 16);
-				__syncwarp();
+				__syncwarp();                      /* every lane has read slot r before slot w <= r is rewritten */
 				if ((x.x & 0xffu) == 0u) continue;
-				if (w != r) {
+				if (w != r && lane0) {
 					asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(plan + w * PLAN_REC),
 							"r"(x.x), "r"(x.y), "r"(x.z), "r"(x.w) : "memory");
 					asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(plan + w * PLAN_REC + 16),
@@ -1591,7 +1595,7 @@ __device__ __noinline__ uint32_t steady_plan(OpState *sops, uint32_t so, uint32_
 	 * increment is known, and the HEAD that filled b may have nothing left to do */
 	auto uni_inc = [&](uint32_t b) -> uint32_t {
 		const uint32_t inc = ftoi_lo32(coeff * uval(b));
-		if (!((need >> b) & 1u)) { sts32(plan + head_rec[b] * PLAN_REC, 0u); ++killed; }
+		if (!((need >> b) & 1u)) { if (lane0) sts32(plan + head_rec[b] * PLAN_REC, 0u); ++killed; }
 		return inc;
 	};
 	uint4 raw_next = __ldg(reinterpret_cast<const uint4*>(code));
@@ -1651,7 +1655,7 @@ __device__ __noinline__ uint32_t steady_plan(OpState *sops, uint32_t so, uint32_
 				uint32_t av = 0;
 				if (ac) {
 					av = __float_as_uint(uval(in.c));
-					sts32(plan + head_rec[in.c] * PLAN_REC, 0u);
+					if (lane0) sts32(plan + head_rec[in.c] * PLAN_REC, 0u);
 					++killed;
 					dirty(in.c);
 				} else {
@@ -1687,8 +1691,8 @@ __device__ __noinline__ uint32_t steady_plan(OpState *sops, uint32_t so, uint32_
 				/* both ends of the range are uniform lines nothing else has read: they go
 				 * into the record as scalars and their LINE records have no use left */
 				const float pv = uval(in.a), rv = uval(in.b);
-				sts32(plan + head_rec[in.a] * PLAN_REC, 0u);
-				sts32(plan + head_rec[in.b] * PLAN_REC, 0u);
+				if (lane0) sts32(plan + head_rec[in.a] * PLAN_REC, 0u);
+				if (lane0) sts32(plan + head_rec[in.b] * PLAN_REC, 0u);
 				killed += 2;
 				touch(in.c);
 				plan_put(plan, n++, P_RANGE | PF_FUNI << 8 | (uint32_t) in.a << 16 | (uint32_t) in.b << 24, in.c,
