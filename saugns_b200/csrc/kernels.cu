@@ -942,6 +942,7 @@ __device__ void cyclor_fill(Ctx &c, const Instr &in, uint32_t n) {
 	*U4(c, in.a) = make_uint4(cyc[0], cyc[1], cyc[2], cyc[3]);
 	st4(c, in.b, phf);
 	const uint64_t total = __shfl_sync(FULL, incl, 31);
+	__syncwarp();                      /* every lane holds cp0 before lane 0 rewrites it */
 	if (c.lane == 0) {
 		const uint64_t cp = cp0 + total;
 		o->i0 = (uint32_t) cp; o->i1 = (uint32_t) (cp >> 32);
@@ -1417,6 +1418,7 @@ __device__ __noinline__ uint32_t run_chunk(Ctx &c, const Instr *code, uint32_t c
 			break; }
 		case I_VPAN: {                                             /* generator.c:756-762 */
 			/* the voice-level part runs over the carrier's out_len */
+			__syncwarp();              /* every lane has read this iteration's length */
 			if (c.lane == 0) { c.stk_len[0] = c.last_len; c.stk_rem[0] = c.last_rem; }
 			__syncwarp();
 			if (c.last_len == 0) return 0;
