@@ -330,7 +330,7 @@ def run_gpu_arm(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "voices": VOICES, "frames_per_step": FRAMES,
                    "srate": SRATE, "op_samples_per_step": 3 * vs_step,
-                   "l2": "per-step voice rows 805 MB > 126 MB L2 (inputs larger than L2)",
+                   "l2": "per-step voice rows 403 MB > 126 MB L2 (working set larger than L2)",
                    "parallelism": f"independent 4096-voice scripts x{world}"},
         "realtime_factor": (FRAMES * K / SRATE) / (ms / 1000.0),
         "clocks": clocks,
