@@ -302,3 +302,26 @@ def test_nesting_limit_reported(S, ref, tabs):
     prg = ref.Program(text)
     with pytest.raises(RuntimeError, match="nesting too deep"):
         S.Generator(prg, 96000, tables=tabs)
+
+
+def test_c3_full_voice_count_bit_exact(S, ref, tabs):
+    """BASELINE config 3 at its full 4096 voices (one resident wave of 28-warp CTAs with
+    the coefficient planes, the launch shape bench.py times), 0.6 s: every PCM sample and
+    the integer state of every operator equal to the unmodified reference's."""
+    prg = ref.Program(scripts.synth_c3(4096, 0.6, fm="mix"))
+    want = ref.render(prg, srate=96000)
+    g = S.Generator(prg, 96000, tables=tabs, max_call_len=24576)
+    chunks, more = [], True
+    while more:
+        more, buf, n = g.run(24576)
+        chunks.append(buf[:2 * n].copy())
+    got = np.concatenate(chunks).reshape(-1, 2)
+    assert got.shape == want.shape
+    assert np.array_equal(got, want)
+    gr = ref.RefGenerator(prg, 96000)
+    more = True
+    while more:
+        more, _, _ = gr.run(24576)
+    for op in range(0, prg.op_count, 37):
+        a, b = gr.op_state(op), g.op_state(op)
+        assert (a.i0, a.i1, a.time) == (b.i0, b.i1, b.time), op
