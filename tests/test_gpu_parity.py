@@ -325,3 +325,14 @@ def test_c3_full_voice_count_bit_exact(S, ref, tabs):
     for op in range(0, prg.op_count, 37):
         a, b = gr.op_state(op), g.op_state(op)
         assert (a.i0, a.i1, a.time) == (b.i0, b.i1, b.time), op
+
+
+def test_c4_full_voice_count_bit_exact(S, ref, tabs):
+    """BASELINE config 4 at its full 1024 voices (self-PM W and R carriers, range-AM, ring
+    modulation: the serial per-sample path), 0.3 s, bit-exact -- self-PM is chaotic, so
+    this only holds if every feedback iteration reproduces the reference's float sequence."""
+    prg = ref.Program(scripts.synth_c4(1024, 0.3))
+    want = ref.render(prg, srate=96000)
+    got = S.render(prg, srate=96000, tables=tabs)
+    assert got.shape == want.shape
+    assert np.array_equal(got, want)
