@@ -455,8 +455,10 @@ __device__ __noinline__ void line_skip(uint32_t oc, int lane, OpState *o, int li
 /* low 32 bits of sau_ftoi(x) (generator.c:16-17): F2I.S64 saturates where
  * x86 returns INT64_MIN; only the positive overflow differs in the low word */
 __device__ __forceinline__ uint32_t ftoi_lo32(float x) {
-	const uint32_t r = (uint32_t) __float2ll_rn(x);
-	return (x >= 9223372036854775808.f) ? 0u : r;
+	/* every float >= 2^55 is a multiple of 2^32 (low word 0), so capping at 2^62 changes no
+	 * low word below the overflow and gives 0 above it (and for NaN, which min() drops): one
+	 * FMNMX instead of a compare and a select (checked over all floats by saugen_selftest) */
+	return (uint32_t) __float2ll_rn(fminf(x, 4611686018427387904.f));
 }
 
 template <bool FULLC, typename C>
