@@ -3,18 +3,25 @@
  *   render_kernel : one warp per (call, voice).  The warp owns its voice's
  *     timeline for the call: it applies the voice's due events
  *     (handle_event, sau/generator.c:348-377), then renders every inter-event
- *     segment in 128-sample chunks by interpreting the voice's bytecode (the
- *     flattened run_block recursion, generator.c:448-729).  Each lane owns 4
- *     consecutive samples of a chunk; integer phase accumulation is a warp
- *     shuffle scan over the rounded increments (bit-exact with
- *     sauPhasor_fill / sauCyclor_fill), self-PM operators run as a serial
- *     loop on one lane with their state in registers.  Wave tables are
- *     staged into shared memory with TMA bulk copies (cp.async.bulk +
- *     mbarrier).  The carrier block, scaled and panned, goes to HBM rows
- *     (128-bit stores when aligned).
- *   mix_kernel : fused epilogue.  One thread per output frame sums the voice
- *     rows in voice order (same float summation order as mix_add,
- *     generator.c:749-788), clamps and rounds to int16
+ *     segment by interpreting the voice's bytecode (the flattened run_block
+ *     recursion, generator.c:448-729): in 128-sample chunks through the
+ *     general interpreter (run_chunk: any operator, any state), or -- for
+ *     stretches of whole 1024-sample blocks in which nothing changes shape,
+ *     almost all of a render -- from a PLAN the warp compiles once per stretch
+ *     into its shared memory (steady_plan -> run_block_fast -> steady_update).
+ *     Each lane owns 4 consecutive samples of a chunk; integer phase
+ *     accumulation is a warp shuffle scan over the rounded increments, or a
+ *     closed form when the frequency is uniform (bit-exact with
+ *     sauPhasor_fill / sauCyclor_fill either way); self-PM operators run as a
+ *     serial loop on one lane with their state in registers.  Wave tables --
+ *     or their per-index cubic coefficients -- are staged into shared memory
+ *     with TMA bulk copies (cp.async.bulk + mbarrier).  The carrier chunk,
+ *     scaled, goes to the voice's 512-byte piece of the frame tile in HBM
+ *     (device_types.h:ROW_TILE) with 128-bit streaming stores.
+ *   mix_kernel : fused epilogue.  One CTA per frame tile, one thread per
+ *     output frame; the tile's voice pieces stream through a TMA-filled ring
+ *     and are summed in voice order (same float summation order as mix_add,
+ *     generator.c:749-788), clamped and rounded to int16
  *     (mix_write_stereo/mono, generator.c:795-825).
  *
  * Compiled with -fmad=false: every float/double operation is a separately
