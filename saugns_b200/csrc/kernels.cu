@@ -1525,7 +1525,7 @@ __device__ __forceinline__ uint32_t op_span(const OpState *o, uint32_t k) {
  * of the chunk is at phase0 + (i + 1) * inc in wrap-around uint32 arithmetic --
  * bit-identical to the serial accumulation, without conversions or a scan. */
 enum : uint32_t { P_LINE = 1, P_WHEAD, P_WTAIL, P_WLEAF, P_PHASE, P_WOSC, P_RANGE, P_VOUT,
-	P_NOISE, P_CYCLE, P_RASG, P_MIX };
+	P_NOISE, P_CYCLE, P_RASG, P_MIX, P_WSELF };
 enum : uint32_t {
 	PF_LAYER = 1, PF_WAVEENV = 2,
 	PF_FUNI = 4,       /* frequency (or the LINE's value) is uniform over the block: w6 holds the
@@ -1568,6 +1568,8 @@ __device__ __noinline__ uint32_t steady_plan(OpState *sops, uint32_t so, uint32_
 	const bool lane0 = (threadIdx.x & 31u) == 0u;
 	uint32_t lstack = 0, depth = 0;    /* layer flags of the unfused operators being walked */
 	uint32_t entered = 0;              /* operator slots that came in through an ENTER */
+	uint32_t selfmask = 0;             /* operator slots whose pm_a line runs: self-PM (generator.c:485-490) */
+	uint32_t other = 0;                /* the plan has serial self-PM records (bit 31 of the result) */
 	uint32_t n = 0;
 	plan += PLAN_REC;          /* slot 0 is the header (render_units) */
 	if (cap) --cap;
@@ -1600,7 +1602,7 @@ __device__ __noinline__ uint32_t steady_plan(OpState *sops, uint32_t so, uint32_
 			__syncwarp();
 			nrec = w;
 		}
-		return kb << 16 | nrec;
+		return other | kb << 16 | nrec;
 	};
 	/* the operator's phase fill takes its frequency from uniform buffer b: the
 	 * increment is known, and the HEAD that filled b may have nothing left to do */
@@ -1652,8 +1654,14 @@ __device__ __noinline__ uint32_t steady_plan(OpState *sops, uint32_t so, uint32_
 		case I_RASG:
 			if (in.flags & F_HAS_APMODS) return 0;
 			touch(in.b);
-			plan_put(plan, n++, P_RASG | (uint32_t) in.a << 16 | (uint32_t) in.b << 24, 0u, opa, 0u,
-					0.f, 0.f, 0.f, 0.f);
+			{
+				/* self-PM (sauRasG_run_selfmod, rasg.h:242-294): PF_FUNI marks it, c = amount buffer */
+				const bool self = in.op < 32 && ((selfmask >> in.op) & 1u);
+				if (self) touch(in.c);
+				if (self) other = 0x80000000u;
+				plan_put(plan, n++, P_RASG | (self ? PF_FUNI : 0u) << 8 | (uint32_t) in.a << 16 | (uint32_t) in.b << 24,
+						(uint32_t) in.c, opa, 0u, 0.f, 0.f, 0.f, 0.f);
+			}
 			dirty(in.a);
 			break;
 		case I_MIX:                                                  /* generator.c:384-440 */
@@ -1740,10 +1748,19 @@ __device__ __noinline__ uint32_t steady_plan(OpState *sops, uint32_t so, uint32_
 				dirty(in.a);
 			}
 			break;
-		case I_PMA:                                                  /* generator.c:485-490 */
-			if (o->line[LINE_PMA].v0 != 0.f ||
-					(LM_FLAGS(o->lmeta[LINE_PMA]) & SAUABI_LINEP_GOAL)) return 0;
-			break;
+		case I_PMA: {                                                /* generator.c:485-490 */
+			const uint32_t lf = LM_FLAGS(o->lmeta[LINE_PMA]);
+			if (o->line[LINE_PMA].v0 != 0.f || (lf & SAUABI_LINEP_GOAL)) {
+				/* self-PM: the amount line fills its buffer, the operator's WOSC / RASG
+				 * record then runs the serial loop (no self-PM modulator lists here) */
+				if (in.op >= 32 || !(kb = line_span(o, LINE_PMA, kb))) return 0;
+				plan_put(plan, n++, P_LINE | ((lf & SAUABI_LINEP_GOAL) ? 0u : PF_FUNI) << 8 |
+						(uint32_t) in.a << 16 | (uint32_t) NO_BUF << 24, (uint32_t) LINE_PMA << 16, opa, 0u,
+						0.f, 0.f, o->line[LINE_PMA].v0, 0.f);
+				dirty(in.a);
+				selfmask |= 1u << in.op;
+			}
+			break; }
 		case I_WOSC: {
 			if ((in.flags & F_HAS_APMODS) || pc + 2 >= code_len) return 0;
 			Instr mix, leave;
@@ -1760,8 +1777,16 @@ __device__ __noinline__ uint32_t steady_plan(OpState *sops, uint32_t so, uint32_
 				((mix.flags & F_WAVEENV) ? PF_WAVEENV : 0u) | PF_ABUF;
 			lstack >>= 1;
 			--depth;
-			plan_put(plan, n++, P_WOSC | fl << 8 | (uint32_t) mix.a << 16 | (uint32_t) in.b << 24,
-					(uint32_t) mix.c, opa, ct, wc->diff_scale[wave], wc->diff_offset[wave], 0.f, 0.f);
+			if (in.op < 32 && ((selfmask >> in.op) & 1u)) {
+				/* sauWOsc_run_selfmod (wosc.h:273-310) on lane 0, then block_mix */
+				touch(in.c);
+				other = 0x80000000u; plan_put(plan, n++, P_WSELF | fl << 8 | (uint32_t) mix.a << 16 | (uint32_t) in.b << 24,
+						(uint32_t) mix.c | (uint32_t) in.c << 8 | (uint32_t) in.a << 16, opa, 0u,
+						0.f, 0.f, 0.f, 0.f);
+			} else {
+				plan_put(plan, n++, P_WOSC | fl << 8 | (uint32_t) mix.a << 16 | (uint32_t) in.b << 24,
+						(uint32_t) mix.c, opa, ct, wc->diff_scale[wave], wc->diff_offset[wave], 0.f, 0.f);
+			}
 			dirty(mix.a); dirty(in.a); touch(in.b); touch(mix.c);
 			/* MIX and LEAVE are part of the record */
 			pc += 2;
@@ -1872,9 +1897,14 @@ __device__ __noinline__ void steady_update(OpState *sops, const Instr *code, uin
 		case I_VPAN:
 			line_skip_blocks(o, LINE_PAN, nb);
 			break;
-		case I_PMA:                /* not run in a steady block (steady_plan) */
-			line_skip_blocks(o, LINE_PMA, nb);
-			o->flags &= ~ON_PMA_RUN;
+		case I_PMA:                /* as pma_decide / run_osc_selfmod_param, generator.c:485-490 */
+			if (o->line[LINE_PMA].v0 != 0.f || (LM_FLAGS(o->lmeta[LINE_PMA]) & SAUABI_LINEP_GOAL)) {
+				line_block_update(o, LINE_PMA, nb);
+				o->flags |= ON_PMA_RUN;
+			} else {
+				line_skip_blocks(o, LINE_PMA, nb);
+				o->flags &= ~ON_PMA_RUN;
+			}
 			break;
 		case I_LEAVE:              /* unfused wave operator, generator.c:726-727 */
 			if (!(o->flags & ON_TIME_INF)) o->time -= nb * (uint32_t) REF_BLOCK;
@@ -2280,10 +2310,11 @@ __device__ __noinline__ void vout_unaligned(uint32_t sbuf_s, uint32_t sbuf_r, fl
 	}
 }
 
-/* The other operator types on a steady full chunk: the general interpreter's own
- * routines (same buffer layout, FAST_NS == SPL), out of line, on a minimal context. */
-static_assert(FAST_NS == SPL, "plan_other runs the general routines on the fast buffers");
-__device__ __noinline__ void plan_other(uint32_t kind, uint32_t sb0, int lane, float coeff, uint32_t oc,
+/* The feed-forward operator types other than wave oscillators on a steady full chunk
+ * (noise, rumble without self-PM, DC / mix): the general interpreter's own routines
+ * (same buffer layout, FAST_NS == SPL), out of line, on a minimal context. */
+static_assert(FAST_NS == SPL, "plan_ff / plan_other run the general routines on the fast buffers");
+__device__ __noinline__ void plan_ff(uint32_t kind, uint32_t sb0, int lane, float coeff, uint32_t oc,
 		uint32_t op, uint32_t w0, uint32_t w1) {
 	Ctx c;
 	c.bufs = reinterpret_cast<float*>(__cvta_shared_to_generic(sb0));
@@ -2310,7 +2341,55 @@ __device__ __noinline__ void plan_other(uint32_t kind, uint32_t sb0, int lane, f
 	__syncwarp();
 }
 
-template <int NS, bool CTAB>
+/* The same for plans with serial self-PM records (P_WSELF, self-PM P_RASG): they also
+ * need the plan header; such plans run in their own instance of the chunk loop. */
+__device__ __noinline__ void plan_other(uint32_t sb, float coeff, uint32_t oc, uint32_t rec, uint32_t plan) {
+	/* few arguments: the call sits in the hot loop's register allocation */
+	const int lane = (int) (threadIdx.x & 31u);
+	const uint32_t sb0 = sb - (uint32_t) lane * 16u;
+	const uint4 p0 = lds128u(rec);
+	const uint32_t w0 = p0.x, w1 = p0.y, op = p0.z, kind = w0 & 0xffu;
+	Ctx c;
+	c.bufs = reinterpret_cast<float*>(__cvta_shared_to_generic(sb0));
+	c.sops = reinterpret_cast<OpState*>(__cvta_shared_to_generic(op));
+	c.lane = lane; c.coeff = coeff; c.oc = oc % (uint32_t) REF_BLOCK; c.sp = 0;
+	c.pma_flag = kind == P_RASG && ((w0 >> 8) & PF_FUNI);          /* self-PM rumble */
+	Instr in;
+	in.opcode = 0; in.op = 0; in.flags = 0; in.aux = 0;
+	in.a = (uint8_t) (w0 >> 16); in.b = (uint8_t) (w0 >> 24);
+	in.c = (uint8_t) w1; in.d = (uint8_t) (w1 >> 8); in.e = (uint8_t) NO_BUF;
+	if (kind == P_WSELF) {                                         /* sauWOsc_run_selfmod + block_mix */
+		const uint4 h = lds128u(plan);
+		ColdCtx cc;
+		cc.tab = reinterpret_cast<const float*>((uint64_t) h.x | ((uint64_t) h.y << 32));
+		cc.wc = reinterpret_cast<const WaveCoeffs*>((uint64_t) h.z | ((uint64_t) h.w << 32));
+		cc.wave_mask = lds32(plan + PH_WAVE_MASK); cc.lane = lane;
+		const uint32_t amp_buf = w1 & 0xffu, pma_buf = (w1 >> 8) & 0xffu, dst = (w1 >> 16) & 0xffu;
+		wosc_selfmod(cc, c.sops, reinterpret_cast<const uint32_t*>(c.bufs + in.b * CHUNK),
+				c.bufs + pma_buf * CHUNK, c.bufs + dst * CHUNK, CHUNK);
+		float x[SPL], a[SPL];
+		ld4(c, dst, x);
+		ld4(c, amp_buf, a);
+		mix_eval<true>(c, in.a, x, a, CHUNK, (w0 >> 8) & PF_LAYER, ((w0 >> 8) & PF_WAVEENV) != 0);
+	}
+	else if (kind == P_MIX) {                                      /* block_mix_*, generator.c:384-440 */
+		float x[SPL] = {1.f, 1.f, 1.f, 1.f}, a[SPL];
+		if (in.b != NO_BUF) ld4(c, in.b, x);
+		if ((w0 >> 8) & PF_ACONST) {               /* `op` carries the constant amplitude */
+#pragma unroll
+			for (int k = 0; k < SPL; ++k) a[k] = __uint_as_float(op);
+		} else {
+			ld4(c, in.c, a);
+		}
+		mix_eval<true>(c, in.a, x, a, CHUNK, (w0 >> 8) & PF_LAYER, ((w0 >> 8) & PF_WAVEENV) != 0);
+	}
+	else if (kind == P_NOISE) noise_run(c, in, CHUNK);             /* sauNoiseG_run_*, noise.h:41-185 */
+	else if (kind == P_CYCLE) cyclor_fill(c, in, CHUNK);           /* sauCyclor_fill, rasg.h:165-222 */
+	else rasg_run(c, in, CHUNK, REF_BLOCK);                        /* sauRasG_run, rasg.h:692-743 */
+	__syncwarp();
+}
+
+template <int NS, bool CTAB, bool OTHER>
 __device__ __forceinline__ void run_chunk_plan(const HotCtx &c, const uint32_t nrec,
 		float *row_s, float *row_r, const uint32_t frame) {
 	uint32_t rec = c.plan;
@@ -2381,8 +2460,9 @@ __device__ __forceinline__ void run_chunk_plan(const HotCtx &c, const uint32_t n
 #pragma unroll
 			for (int k = 0; k < NS; ++k) p[k] += (rr[k] - p[k]) * m[k];
 			fst<NS>(c, bufa, p);
-		} else if (kind != P_VOUT) {                               /* P_NOISE, P_CYCLE, P_RASG, P_MIX */
-			plan_other(kind, c.sb - c.lane * 16, c.lane, c.coeff, c.oc, op, p0.x, p0.y);
+		} else if (kind != P_VOUT) {                               /* P_NOISE, P_CYCLE, P_RASG, P_MIX, P_WSELF */
+			if (OTHER) plan_other(c.sb, c.coeff, c.oc, rec, c.plan);
+			else plan_ff(kind, c.sb - c.lane * 16, c.lane, c.coeff, c.oc, op, p0.x, p0.y);
 		} else {                                                   /* P_VOUT, generator.c:772-786 */
 			float sv[NS];
 			fld<NS>(c, bufa, sv);
@@ -2420,16 +2500,17 @@ __device__ __forceinline__ void run_chunk_plan(const HotCtx &c, const uint32_t n
 	}
 }
 
-/* One steady reference block: its own function, so that the hot loop gets its
- * own register allocation whatever the general path around the call needs. */
-template <bool CTAB>
+/* One steady stretch: its own function, so that the hot loop gets its own register
+ * allocation whatever the general path around the call needs.  OTHER: the plan has
+ * serial self-PM records (plan_other); feed-forward plans run in the other instance. */
+template <bool CTAB, bool OTHER>
 __device__ __noinline__ void run_block_fast(uint32_t sb, uint32_t plan, int lane, float coeff, uint32_t nrec,
 		uint32_t len, float *row_s, float *row_r, uint32_t frame) {
 	HotCtx c;
 	c.sb = sb; c.plan = plan; c.lane = lane; c.coeff = coeff;
 	for (uint32_t oc = 0; oc < len; oc += FastCfg<FAST_NS>::CHUNKF) {
 		c.oc = oc;
-		run_chunk_plan<FAST_NS, CTAB>(c, nrec, row_s, row_r, frame + oc);
+		run_chunk_plan<FAST_NS, CTAB, OTHER>(c, nrec, row_s, row_r, frame + oc);
 	}
 }
 
@@ -2536,11 +2617,13 @@ __device__ __noinline__ void render_units(Ctx &c, FastCtx &fc, const CallDesc *c
 					op_ptr(c, vs.carr_slot)->time > 0) {
 				uint32_t kb = (uend - off) / (uint32_t) REF_BLOCK;
 				if (vs.duration / (uint32_t) REF_BLOCK < kb) kb = vs.duration / (uint32_t) REF_BLOCK;
+				if (kb > 0x7fffu) kb = 0x7fffu;        /* 15 bits in steady_plan's result */
 				sp = steady_plan(c.sops, fc.so, fc.st, fc.wave_mask, fc.wc, g->code + vs.code_off,
 						vs.code_len, fc.plan, fc.plan_cap, kb, fc.sb, fc.coeff);
 			}
 			if (sp) {
-				const uint32_t nrec = sp & 0xffffu, nb = sp >> 16, span = nb * (uint32_t) REF_BLOCK;
+				const uint32_t nrec = sp & 0xffffu, nb = (sp >> 16) & 0x7fffu, span = nb * (uint32_t) REF_BLOCK;
+				const bool other = (sp >> 31) != 0;
 				if (pan_mode == PAN_UNSET)       /* steady => the pan stands still */
 					pan_mode = __float_as_uint(op_ptr(c, vs.carr_slot)->line[LINE_PAN].v0);
 				{
@@ -2551,10 +2634,13 @@ __device__ __noinline__ void render_units(Ctx &c, FastCtx &fc, const CallDesc *c
 							__uint_as_float(c.tstride));
 					__syncwarp();
 				}
-				if (fc.wave_mask & CTAB_FLAG)
-					run_block_fast<true>(fc.sb, fc.plan, lane, fc.coeff, nrec, span, row_s, row_r, sd.start + off);
-				else
-					run_block_fast<false>(fc.sb, fc.plan, lane, fc.coeff, nrec, span, row_s, row_r, sd.start + off);
+				if (fc.wave_mask & CTAB_FLAG) {
+					if (other) run_block_fast<true, true>(fc.sb, fc.plan, lane, fc.coeff, nrec, span, row_s, row_r, sd.start + off);
+					else run_block_fast<true, false>(fc.sb, fc.plan, lane, fc.coeff, nrec, span, row_s, row_r, sd.start + off);
+				} else {
+					if (other) run_block_fast<false, true>(fc.sb, fc.plan, lane, fc.coeff, nrec, span, row_s, row_r, sd.start + off);
+					else run_block_fast<false, false>(fc.sb, fc.plan, lane, fc.coeff, nrec, span, row_s, row_r, sd.start + off);
+				}
 				__syncwarp();
 				if (lane == 0) steady_update(c.sops, g->code + vs.code_off, vs.code_len, nb);
 				__syncwarp();

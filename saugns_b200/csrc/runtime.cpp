@@ -725,9 +725,10 @@ static bool flatten_program(const sauabi_Program *prg, uint32_t srate, Flat &f) 
 							switch (in.opcode) {
 							case I_WLEAF: case I_WHEAD: case I_WTAIL: case I_RANGE: case I_VOUT:
 							case I_PHASOR: case I_WOSC: case I_NOISE: case I_CYCLOR: case I_RASG: case I_MIX:
+							case I_PMA:
 								++np; break;
 							case I_LINE: if (in.d) ++np; break;
-							case I_ENTER: case I_VPAN: case I_END: case I_PMA: case I_LEAVE: break;
+							case I_ENTER: case I_VPAN: case I_END: case I_LEAVE: break;
 							default: fast = false; break;
 							}
 						}
