@@ -1530,6 +1530,8 @@ enum : uint32_t {
 	PF_LAYER = 1, PF_WAVEENV = 2,
 	PF_FUNI = 4,       /* frequency (or the LINE's value) is uniform over the block: w6 holds the
 	                    * value (LINE, WHEAD) or the phase increment (WTAIL, WLEAF, PHASE) */
+	PF_FMUL = 8,       /* WHEAD / WLEAF, not uniform: the frequency is the constant w6 times the
+	                    * (varying) multiplier buffer: a ratio to a modulated parent frequency */
 	PF_ACONST = 16,    /* amplitude line holds av */
 	PF_ABUF = 32,      /* amplitude comes from work buffer c (the operator has amplitude modulators) */
 };
@@ -1795,7 +1797,7 @@ __device__ __noinline__ uint32_t steady_plan(OpState *sops, uint32_t so, uint32_
 		default:
 			return 0;
 		}
-		bool funi = false;
+		bool funi = false, rmul = false;
 		float fval = 0.f;          /* the uniform frequency of a HEAD / LEAF */
 		if (head) {
 			if (in.op >= 32 || (seen & (1u << in.op))) return 0;
@@ -1807,12 +1809,13 @@ __device__ __noinline__ uint32_t steady_plan(OpState *sops, uint32_t so, uint32_
 			fval = o->line[LINE_FREQ].v0;
 			if (funi && fmul) fval = fval * uval(in.e);
 			if (!funi && in.e != NO_BUF) touch(in.e);
+			rmul = !funi && fmul && !(lf & SAUABI_LINEP_GOAL);      /* v0 * parent[k] */
 			if (!tail) {
 				if (depth >= 31) return 0;
 				lstack = (lstack << 1) | ((in.flags & F_LAYER) ? 1u : 0u);   /* popped by its WTAIL / WOSC */
 				++depth;
 				entered |= 1u << in.op;
-				plan_put(plan, n++, P_WHEAD | (funi ? PF_FUNI : 0u) << 8 |
+				plan_put(plan, n++, P_WHEAD | ((funi ? PF_FUNI : 0u) | (rmul ? PF_FMUL : 0u)) << 8 |
 						(uint32_t) in.b << 24, (uint32_t) in.e << 8, opa, 0u,
 						0.f, 0.f, fval, 0.f);
 				dirty(in.b);
@@ -1847,10 +1850,11 @@ __device__ __noinline__ uint32_t steady_plan(OpState *sops, uint32_t so, uint32_
 				st + slot * (TAB_STRIDE * 4) + 12;                   /* planes, or &lut[-1] */
 			const bool aconst = !(LM_FLAGS(o->lmeta[LINE_AMP]) & SAUABI_LINEP_GOAL);
 			const uint32_t fl = ((in.flags & F_LAYER) ? PF_LAYER : 0u) | ((in.flags & F_WAVEENV) ? PF_WAVEENV : 0u) |
-				(funi ? PF_FUNI : 0u) | (aconst ? PF_ACONST : 0u);
+				(funi ? PF_FUNI : 0u) | (rmul ? PF_FMUL : 0u) | (aconst ? PF_ACONST : 0u);
 			plan_put(plan, n++, (head ? P_WLEAF : P_WTAIL) | fl << 8 | (uint32_t) in.a << 16 | (uint32_t) in.b << 24,
 					(uint32_t) in.c | (uint32_t) in.e << 8, opa, ct,
-					wc->diff_scale[wave], wc->diff_offset[wave], __uint_as_float(inc), o->line[LINE_AMP].v0);
+					wc->diff_scale[wave], wc->diff_offset[wave], rmul ? fval : __uint_as_float(inc),
+					o->line[LINE_AMP].v0);
 			dirty(in.a);
 		}
 	}
@@ -2421,6 +2425,12 @@ __device__ __forceinline__ void run_chunk_plan(const HotCtx &c, const uint32_t n
 						inc = w6;
 #pragma unroll
 						for (int k = 0; k < NS; ++k) fr[k] = __uint_as_float(w6);
+					} else if (!is_line && (flags & PF_FMUL)) {
+						/* a constant ratio to a modulated parent frequency (line.c:417-445, no goal) */
+						const float v0 = lds32f(rec + 24);
+						fld<NS>(c, mb, fr);
+#pragma unroll
+						for (int k = 0; k < NS; ++k) fr[k] = v0 * fr[k];
 					} else {
 						float m[NS];
 						const bool has_mul = mb != NO_BUF;
