@@ -352,6 +352,12 @@ def run_gpu_arm(args):
                      "note": "path is issue-/FP64-pipe-bound, not HBM-bound (SURVEY.md 8d); "
                              "issue-slot figures from ncu in profiles/",
                      "issue_slot_frac_ncu": prof.get("issue_slot_frac"),
+                     # the same launch's instruction count (ncu) over the issue slots of THIS run's
+                     # measured kernel time: 4 schedulers x 148 SMs x SM clock (the ncu capture itself
+                     # is a cold, serialised launch and runs ~40 % longer)
+                     "issue_slot_frac_live": (prof["warp_insts"] / (4 * 148 * (clocks.get("sm_mhz") or 1965.0)
+                                                                  * 1e6 * rk_s)
+                                              if prof.get("warp_insts") else None),
                      "fp64_pipe_frac_ncu": prof.get("fp64_pipe_frac"),
                      "xu_pipe_frac_ncu": prof.get("xu_pipe_frac"),
                      "ncu_profile": prof.get("file")},
