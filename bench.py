@@ -43,6 +43,11 @@ def env_rank():
 # clocks sampling (B200_PROFILING.md "clocks DURING the timed region")
 # ---------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock and throttle reasons DURING the timed region: an in-process NVML poller
+    (5 ms period; nvidia_ml_py), or `nvidia-smi -lms` where NVML cannot be loaded.
+    start() is called before the warm-up steps so that the poller is up when the timed
+    region begins; mark() opens / closes the region and only samples inside it count (all
+    samples when the region was shorter than a polling period)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -50,48 +55,100 @@ class ClockSampler:
     def __init__(self, index):
         self.index = index
         self.proc = None
-        self.lines = []
+        self.samples = []            # (time, sm_mhz, sm_max_mhz, set(reasons))
+        self.marks = []
+        self.stop_flag = False
+        self.thread = None
+        self.how = None
 
     def start(self):
         try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.index
+            if vis:                  # NVML counts physical devices
+                try:
+                    idx = int(vis.split(",")[self.index])
+                except (ValueError, IndexError):
+                    idx = self.index
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            bits = {"hw_slowdown": pynvml.nvmlClocksThrottleReasonHwSlowdown,
+                    "hw_thermal_slowdown": pynvml.nvmlClocksThrottleReasonHwThermalSlowdown,
+                    "sw_thermal_slowdown": pynvml.nvmlClocksThrottleReasonSwThermalSlowdown,
+                    "sw_power_cap": pynvml.nvmlClocksThrottleReasonSwPowerCap}
+
+            def poll():
+                while not self.stop_flag:
+                    try:
+                        sm = float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                        r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                        self.samples.append((time.perf_counter(), sm, mx,
+                                             {k for k, b in bits.items() if r & b}))
+                    except Exception:
+                        pass
+                    time.sleep(0.005)
+
+            self.thread = threading.Thread(target=poll, daemon=True)
+            self.thread.start()
+            self.how = "nvml"
+            return
+        except Exception:
+            pass
+        try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
+                 "-i", str(self.index), "-lms", "20"], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+            self.how = "nvidia-smi"
         except OSError:
             self.proc = None
 
     def _read(self):
-        for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
-
-    def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ln in self.proc.stdout:
             p = [x.strip() for x in ln.split(",")]
             if len(p) < 9:
                 continue
             try:
-                sm.append(float(p[1]))
-                mx.append(float(p[2]))
+                self.samples.append((time.perf_counter(), float(p[1]), float(p[2]),
+                                     {nm for k, nm in enumerate(names)
+                                      if p[5 + k].lower().startswith("active")}))
             except ValueError:
                 continue
-            for k, nm in enumerate(names):
-                if p[5 + k].lower().startswith("active"):
-                    reasons.add(nm)
-        sm.sort()
+
+    def mark(self):
+        self.marks.append(time.perf_counter())
+
+    def stop(self):
+        if self.how is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no NVML, no nvidia-smi"],
+                    "samples": 0}
+        time.sleep(0.02)
+        self.stop_flag = True
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        sel = self.samples
+        if len(self.marks) >= 2:
+            inside = [x for x in self.samples if self.marks[0] <= x[0] <= self.marks[-1]]
+            if inside:
+                sel = inside
+            else:                    # region shorter than a period: the nearest samples
+                mid = 0.5 * (self.marks[0] + self.marks[-1])
+                sel = sorted(self.samples, key=lambda x: abs(x[0] - mid))[:3]
+        sm = sorted(x[1] for x in sel)
+        reasons = set()
+        for x in sel:
+            reasons |= x[3]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None,
-                "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "sm_max_mhz": max((x[2] for x in sel), default=None), "reasons": sorted(reasons),
+                "samples": len(sm), "source": self.how}
 
 
 # ---------------------------------------------------------------------------
@@ -244,13 +301,14 @@ def run_gpu_arm(args):
     sched = int(os.environ.get("SAUGEN_BENCH_SCHED", "0"))   # developer knob; 0 = auto
     g = saugns_b200.Generator(prg, SRATE, device=local_rank, stream=stream.cuda_stream,
                               max_call_len=FRAMES, sched=sched)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(W):
         g.run_device(FRAMES)
     g.set_timing(True)
-    sampler = ClockSampler(local_rank)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
-    sampler.start()
+    sampler.mark()
     c0 = g.counters()
     with torch.cuda.stream(stream):
         ev0.record(stream)
@@ -259,6 +317,7 @@ def run_gpu_arm(args):
             assert more and n == FRAMES
         ev1.record(stream)
     barrier()
+    sampler.mark()
     clocks = sampler.stop()
     ms = max_over_ranks(ev0.elapsed_time(ev1))
     c1 = g.counters()
