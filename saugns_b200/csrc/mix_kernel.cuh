@@ -1,0 +1,205 @@
+/* mix_kernel.cuh -- part of kernels.cu (one translation unit; included inside namespace saugen):
+ * the fused mix-down + clip epilogue and the plane-to-PCM kernel. */
+#pragma once
+
+/* ---- mix + clip epilogue ------------------------------------------------- */
+
+/* One CTA mixes one frame tile (ROW_TILE = 128 consecutive frames), one thread
+ * per frame: the sum over voices must run in voice order in ONE thread (float
+ * addition is not associative and mix_add adds voice after voice,
+ * generator.c:773-786).  The tile's voice pieces lie side by side in HBM
+ * (device_types.h:ROW_TILE), so the CTA reads ONE contiguous stream: the
+ * producer warp moves MIX_TV voices (8 KiB) per stage with a single TMA bulk copy
+ * (cp.async.bulk + mbarrier transaction count) into a ring of MIX_STAGES
+ * stages, the four consumer warps add behind it.
+ * A voice whose pan stands still contributes r = s * pan, computed here
+ * (VoiceSeg); only moving pans have an r piece, which the consumers read straight
+ * from HBM (a coalesced 128-byte line per warp; rare). */
+constexpr int MIX_FRAMES = ROW_TILE;           // = consumer threads (one per frame)
+constexpr int MIX_TV = 32;                     // voices per stage (16 KiB per bulk copy)
+constexpr int MIX_STAGES = 5;
+constexpr int MIX_CWARPS = MIX_FRAMES / 32;    // consumer warps; one more warp produces
+struct MixSmem {
+	float s[MIX_STAGES][MIX_TV][MIX_FRAMES];
+	uint2 vi[MIX_STAGES][MIX_TV];              // the tile's VoiceSeg records
+	uint64_t full[MIX_STAGES], empty[MIX_STAGES];
+	uint32_t ndyn[MIX_STAGES];                 // moving-pan voices in the stage's tile
+};
+
+__device__ __forceinline__ void mix_store(const GenDesc *g, const CallDesc *cd, uint32_t mode,
+		uint32_t f, float L, float R) {
+	if (mode == 1) {
+		g->mix[f] = L;
+		g->mix[g->row_len + f] = R;
+		return;
+	}
+	/* CallDesc::stereo: bit 0 = two channels, bit 1 = big-endian samples (the AU stream
+	 * of `saugns -o -`, player/sndfile.c:160-168: the byte swap folded into the epilogue) */
+	const bool be = (cd->stereo & 2u) != 0;
+	if (cd->stereo & 1u) {                                         /* generator.c:795-810 */
+		L = sau::fclampf(L, -1.f, 1.f);
+		R = sau::fclampf(R, -1.f, 1.f);
+		uint32_t w = ((uint32_t) (uint16_t) (short) __float2int_rn(L * 32767.f)) |
+			((uint32_t) (uint16_t) (short) __float2int_rn(R * 32767.f) << 16);
+		if (be) w = __byte_perm(w, 0u, 0x2301);
+		reinterpret_cast<uint32_t*>(g->pcm)[f] = w;
+	} else {                                                       /* generator.c:812-825 */
+		float m = (L + R) * 0.5f;
+		m = sau::fclampf(m, -1.f, 1.f);
+		uint32_t w = (uint16_t) (short) __float2int_rn(m * 32767.f);
+		if (be) w = __byte_perm(w, 0u, 0x3201);
+		reinterpret_cast<uint16_t*>(g->pcm)[f] = (uint16_t) w;
+	}
+}
+
+__global__ void __launch_bounds__(MIX_FRAMES + 32)
+mix_kernel(const CallDesc *calls, const SegDesc *segs, uint32_t mode /*0 pcm, 1 float planes*/) {
+	extern __shared__ __align__(128) unsigned char mix_smem_raw[];
+	MixSmem &sm = *reinterpret_cast<MixSmem*>(mix_smem_raw);
+	const CallDesc *cd = &calls[blockIdx.y];
+	const GenDesc *g = cd->gen;
+	const uint32_t f0 = blockIdx.x * MIX_FRAMES;
+	if (f0 >= cd->call_len) return;
+	const uint32_t tid = threadIdx.x;
+	const bool producer = tid >= (uint32_t) MIX_FRAMES;          /* the last warp */
+	const uint32_t f = f0 + (producer ? 0u : tid);
+	const bool valid = !producer && f < cd->call_len;
+	const uint32_t nlv = g->voice_end - g->voice_begin;
+	const uint32_t tstride = g->row_stride;
+	/* the segment holding each thread's frame */
+	uint32_t si = 0;
+	for (; si < cd->nseg; ++si) {
+		const SegDesc sd = segs[cd->seg_off + si];
+		if (f >= sd.start && f < sd.start + sd.len) break;
+	}
+	const bool in_seg = valid && si < cd->nseg;
+	const uint32_t fi = in_seg ? f - segs[cd->seg_off + si].start : 0u;
+	__shared__ uint32_t seg0, mixed, active;
+	if (tid == 0) { seg0 = si; mixed = 0; active = 0; }
+	__syncthreads();
+	if (valid && si != seg0) mixed = 1;
+	if (in_seg && fi < g->status[1 + si]) active = 1;
+	if (tid == 0) {
+		for (int st = 0; st < MIX_STAGES; ++st) {
+			mbar_init(&sm.full[st], 1);                /* the producer's arrive.expect_tx */
+			mbar_init(&sm.empty[st], MIX_CWARPS);
+		}
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	__syncthreads();
+	float L = 0.f, R = 0.f;
+	if (mixed || seg0 >= cd->nseg) {
+		/* an event boundary inside these frames: each thread walks its own segment's
+		 * voice list straight from global memory (rare) */
+		if (in_seg && fi < g->status[1 + si]) {
+			const uint2 *vl = reinterpret_cast<const uint2*>(g->vlen + (size_t) si * nlv);
+			for (uint32_t lv = 0; lv < nlv; ++lv) {
+				const uint2 v = vl[lv];
+				if (fi < v.x) {
+					const size_t at = (size_t) lv * ROW_TILE + row_index(f, tstride);
+					const float s = g->rows_s[at];
+					const float r = (v.y == PAN_DYNAMIC) ? g->rows_r[at] : s * __uint_as_float(v.y);
+					L = (L + s) - r;
+					R = (R + s) + r;
+				}
+			}
+		}
+		if (valid) mix_store(g, cd, mode, f, L, R);
+		return;
+	}
+	if (!active) {                       /* nothing was rendered for these frames */
+		if (valid) mix_store(g, cd, mode, f, 0.f, 0.f);
+		return;
+	}
+	const uint2 *vl = reinterpret_cast<const uint2*>(g->vlen + (size_t) seg0 * nlv);
+	const uint32_t ntiles = (nlv + MIX_TV - 1) / MIX_TV;
+	if (producer) {
+		/* The producer warp: per stage, the VoiceSeg records (one lane each), then lane 0
+		 * posts the transaction count and issues the bulk copies: the MIX_TV voices' s
+		 * pieces are contiguous (one copy), r pieces only for moving pans. */
+		const uint32_t lane = tid & 31u;
+		const float *tile_s = g->rows_s + (size_t) blockIdx.x * tstride;
+		/* the records are fetched three stages ahead of their use (their L2 latency
+		 * would otherwise sit in this loop's critical path) */
+		auto fetch = [&](uint32_t t) {
+			const uint32_t v = t * MIX_TV + lane;
+			return (lane < (uint32_t) MIX_TV && v < nlv) ? __ldg(vl + v) : make_uint2(0u, 0u);
+		};
+		uint2 pre0 = fetch(0), pre1 = fetch(1), pre2 = fetch(2);
+		for (uint32_t t = 0; t < ntiles; ++t) {
+			const uint32_t st = t % MIX_STAGES, v0 = t * MIX_TV;
+			const uint32_t nv = nlv - v0 < (uint32_t) MIX_TV ? nlv - v0 : (uint32_t) MIX_TV;
+			const uint2 info = pre0;
+			pre0 = pre1; pre1 = pre2; pre2 = fetch(t + 3);
+			if (t >= (uint32_t) MIX_STAGES) mbar_wait(&sm.empty[st], ((t / MIX_STAGES) - 1u) & 1u);
+			const bool has = lane < nv;
+			if (has) sm.vi[st][lane] = info;
+			const uint32_t dynmask = __ballot_sync(FULL, has && info.y == PAN_DYNAMIC && info.x);
+			if (lane == 0) sm.ndyn[st] = __popc(dynmask);
+			__syncwarp();                      /* vi, ndyn written before lane 0's arrive publishes them */
+			if (lane == 0) {
+				const uint32_t piece = ROW_TILE * (uint32_t) sizeof(float);
+				mbar_expect_tx(&sm.full[st], nv * piece);
+				tma_bulk_g2s(&sm.s[st][0][0], tile_s + (size_t) v0 * ROW_TILE, nv * piece, &sm.full[st]);
+			}
+		}
+		return;
+	}
+	const uint32_t fx = in_seg ? fi : 0xffffffffu;               /* frames outside take nothing */
+	for (uint32_t t = 0; t < ntiles; ++t) {
+		const uint32_t st = t % MIX_STAGES, v0 = t * MIX_TV;
+		const uint32_t nv = nlv - v0 < (uint32_t) MIX_TV ? nlv - v0 : (uint32_t) MIX_TV;
+		mbar_wait(&sm.full[st], (t / MIX_STAGES) & 1u);
+		const float *sp = &sm.s[st][0][tid];
+		const float *rp = g->rows_r + (size_t) blockIdx.x * tstride + (size_t) v0 * ROW_TILE + tid;
+		const uint2 *ip = &sm.vi[st][0];
+		if (nv == (uint32_t) MIX_TV && sm.ndyn[st] == 0) {
+			/* the common tile: all pans stand still */
+#pragma unroll
+			for (int k = 0; k < MIX_TV; ++k) {
+				const uint2 info = ip[k];
+				const float s = fx < info.x ? sp[k * MIX_FRAMES] : 0.f;
+				const float rr = s * __uint_as_float(info.y);
+				L = (L + s) - rr;                              /* as compiled, Appendix B.3; */
+				R = (R + s) + rr;                              /* adding 0 is exact */
+			}
+		} else {
+			for (uint32_t k = 0; k < nv; ++k) {
+				const uint2 info = ip[k];
+				const bool on = fx < info.x;
+				const float s = on ? sp[k * MIX_FRAMES] : 0.f;
+				float rr;
+				if (info.y == PAN_DYNAMIC) rr = on ? rp[k * MIX_FRAMES] : 0.f;
+				else rr = s * __uint_as_float(info.y);
+				L = (L + s) - rr;
+				R = (R + s) + rr;
+			}
+		}
+		__syncwarp();
+		if ((tid & 31u) == 0) mbar_arrive(&sm.empty[st]);        /* this warp is done with the stage */
+	}
+	if (valid) mix_store(g, cd, mode, f, L, R);
+}
+
+/* float planes (already reduced over ranks) -> int16, for voice-sharded runs */
+__global__ void planes_to_pcm_kernel(const float *mix, uint32_t plane_stride, uint32_t n,
+		uint32_t stereo, int16_t *pcm) {
+	const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+	if (f >= n) return;
+	float L = mix[f], R = mix[plane_stride + f];
+	const bool be = (stereo & 2u) != 0;          /* flags as CallDesc::stereo */
+	uint16_t *out = reinterpret_cast<uint16_t*>(pcm);
+	auto put = [be](uint16_t *p, int v) {
+		const uint16_t u = (uint16_t) (short) v;
+		*p = be ? (uint16_t) ((u << 8) | (u >> 8)) : u;
+	};
+	if (stereo & 1u) {
+		L = sau::fclampf(L, -1.f, 1.f);
+		R = sau::fclampf(R, -1.f, 1.f);
+		put(out + 2 * f, __float2int_rn(L * 32767.f));
+		put(out + 2 * f + 1, __float2int_rn(R * 32767.f));
+	} else {
+		float m = sau::fclampf((L + R) * 0.5f, -1.f, 1.f);
+		put(out + f, __float2int_rn(m * 32767.f));
+	}
+}

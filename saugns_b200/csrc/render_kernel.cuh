@@ -1,0 +1,360 @@
+/* render_kernel.cuh -- part of kernels.cu (one translation unit; included inside namespace saugen):
+ * the render kernels: per-voice unit loop, schedulers, table staging. */
+#pragma once
+
+/* ---- render kernel ------------------------------------------------------ */
+
+static_assert(PLAN_FBUF == FastCfg<FAST_NS>::FBUF_BYTES, "plan-time scratch words sit in the fast buffers");
+constexpr uint32_t OP_VEC = sizeof(OpState) / 16;
+static_assert(sizeof(OpState) == 192, "OpState layout (device_types.h)");
+
+/* operator states of the current voice program: HBM <-> shared memory */
+__device__ __forceinline__ void ops_load(Ctx &c, uint32_t cnt) {
+	uint4 *dst = reinterpret_cast<uint4*>(c.sops);
+	for (uint32_t i = c.lane; i < cnt * OP_VEC; i += 32) {
+		const uint32_t slot = i / OP_VEC, w = i % OP_VEC;
+		dst[i] = __ldcg(reinterpret_cast<const uint4*>(c.gops + c.prog_ops[slot]) + w);
+	}
+	__syncwarp();
+}
+__device__ __forceinline__ void ops_store(Ctx &c, uint32_t cnt) {
+	__syncwarp();
+	const uint4 *src = reinterpret_cast<const uint4*>(c.sops);
+	for (uint32_t i = c.lane; i < cnt * OP_VEC; i += 32) {
+		const uint32_t slot = i / OP_VEC, w = i % OP_VEC;
+		__stcg(reinterpret_cast<uint4*>(c.gops + c.prog_ops[slot]) + w, src[i]);
+	}
+	__syncwarp();
+}
+
+/* Units [u0, u1) of one voice of one call.  A unit is a stretch of one
+ * inter-event segment, starting at a multiple of REF_BLOCK inside it (the
+ * reference's own block grid, generator.c:854-878). */
+__device__ __noinline__ void render_units(Ctx &c, FastCtx &fc, const CallDesc *cd,
+		const SegDesc *segs, const UnitDesc *units, uint32_t lv, uint32_t u0, uint32_t u1) {
+	const GenDesc *g = cd->gen;
+	const int lane = c.lane;
+	const uint32_t v = g->voice_begin + lv;
+	const uint32_t nlv = g->voice_end - g->voice_begin;
+	c.g = g;
+	c.gops = g->ops;
+	c.coeff = g->coeff;
+	fc.coeff = g->coeff; fc.amp_scale = g->amp_scale;
+	VoiceState *vsp = &g->voices[v];
+	VoiceState vs;
+	{
+		/* lane 0 reads (from L2: another SM may have written it), every lane gets
+		 * the same copy */
+		const uint32_t *src = reinterpret_cast<const uint32_t*>(vsp);
+		uint32_t *dst = reinterpret_cast<uint32_t*>(&vs);
+#pragma unroll
+		for (uint32_t i = 0; i < sizeof(VoiceState) / 4; ++i) {
+			uint32_t w = 0;
+			if (lane == 0) w = __ldcg(src + i);
+			dst[i] = __shfl_sync(FULL, w, 0);
+		}
+	}
+	const uint32_t ev_lo = g->vev_off[v], ev_n = g->vev_off[v + 1] - ev_lo;
+	float *row_s = g->rows_s + (size_t) lv * ROW_TILE;      /* the voice's piece of frame tile 0 */
+	float *row_r = g->rows_r + (size_t) lv * ROW_TILE;
+	c.tstride = g->row_stride;
+	uint32_t loaded = 0;        // operator states currently held in shared memory
+
+	for (uint32_t ui = u0; ui < u1; ++ui) {
+		const UnitDesc ud = units[cd->unit_off + ui];
+		const uint32_t si = ud.seg;
+		const SegDesc sd = segs[cd->seg_off + si];
+		/* this voice's events due at the segment start, in order */
+		if (ud.off == 0 && vs.ev_cursor < ev_n && g->vev_idx[ev_lo + vs.ev_cursor] < sd.ev_end) {
+			if (loaded) { ops_store(c, loaded); loaded = 0; }
+			while (vs.ev_cursor < ev_n && g->vev_idx[ev_lo + vs.ev_cursor] < sd.ev_end) {
+				if (lane == 0) {
+					apply_event(g, c.wc, &g->events[g->vev_idx[ev_lo + vs.ev_cursor]], &vs);
+					vs.ev_cursor++;
+				}
+				__syncwarp();
+				uint32_t *w = reinterpret_cast<uint32_t*>(&vs);
+#pragma unroll
+				for (uint32_t i = 0; i < sizeof(VoiceState) / 4; ++i) w[i] = __shfl_sync(FULL, w[i], 0);
+			}
+		}
+		if (vs.duration == 0 || ud.len == 0) continue;
+		/* this voice's pan in this segment (VoiceSeg): undecided at the segment's
+		 * first unit, else what the unit that started the segment recorded */
+		VoiceSeg *vsg = g->vlen + (size_t) si * nlv + lv;
+		uint32_t pan_mode = PAN_UNSET;
+		if (ud.off != 0) {
+			const uint2 pv = __ldcg(reinterpret_cast<const uint2*>(vsg));
+			if (pv.x != 0) pan_mode = pv.y;
+		}
+		c.write_r = pan_mode == PAN_DYNAMIC;
+		fc.write_r = c.write_r ? 1u : 0u;
+		c.prog_ops = g->prog_ops + vs.ops_off;
+		if (!loaded && vs.ops_cnt > 0) {
+			ops_load(c, vs.ops_cnt);
+			loaded = vs.ops_cnt;
+		}
+		uint32_t run_total = 0;
+		const uint32_t uend = ud.off + ud.len;
+		for (uint32_t off = ud.off; off < uend && vs.duration != 0; off += CHUNK) {
+			/* whole reference blocks in steady state: the fast path, for as many of the
+			 * unit's blocks as one plan holds */
+			uint32_t sp = 0;
+			if (off % REF_BLOCK == 0 && uend - off >= (uint32_t) REF_BLOCK &&
+					vs.duration >= (uint32_t) REF_BLOCK && vs.code_len &&
+					op_ptr(c, vs.carr_slot)->time > 0) {
+				uint32_t kb = (uend - off) / (uint32_t) REF_BLOCK;
+				if (vs.duration / (uint32_t) REF_BLOCK < kb) kb = vs.duration / (uint32_t) REF_BLOCK;
+				if (kb > 0x7fffu) kb = 0x7fffu;        /* 15 bits in steady_plan's result */
+				sp = steady_plan(c.sops, fc.so, fc.st, fc.wave_mask, fc.wc, g->code + vs.code_off,
+						vs.code_len, fc.plan, fc.plan_cap, kb, fc.sb, fc.coeff);
+			}
+			if (sp) {
+				const uint32_t nrec = sp & 0xffffu, nb = (sp >> 16) & 0x7fffu, span = nb * (uint32_t) REF_BLOCK;
+				const bool other = (sp >> 31) != 0;
+				if (pan_mode == PAN_UNSET)       /* steady => the pan stands still */
+					pan_mode = __float_as_uint(op_ptr(c, vs.carr_slot)->line[LINE_PAN].v0);
+				{
+					/* plan header: what the rare paths and VOUT need */
+					const uint64_t tp = reinterpret_cast<uint64_t>(fc.tab), wp = reinterpret_cast<uint64_t>(fc.wc);
+					plan_put(fc.plan, 0, (uint32_t) tp, (uint32_t) (tp >> 32), (uint32_t) wp, (uint32_t) (wp >> 32),
+							__uint_as_float(fc.wave_mask), fc.amp_scale, __uint_as_float(fc.write_r),
+							__uint_as_float(c.tstride));
+					__syncwarp();
+				}
+				if (fc.wave_mask & CTAB_FLAG) {
+					if (other) run_block_fast<true, true>(fc.sb, fc.plan, lane, fc.coeff, nrec, span, row_s, row_r, sd.start + off);
+					else run_block_fast<true, false>(fc.sb, fc.plan, lane, fc.coeff, nrec, span, row_s, row_r, sd.start + off);
+				} else {
+					if (other) run_block_fast<false, true>(fc.sb, fc.plan, lane, fc.coeff, nrec, span, row_s, row_r, sd.start + off);
+					else run_block_fast<false, false>(fc.sb, fc.plan, lane, fc.coeff, nrec, span, row_s, row_r, sd.start + off);
+				}
+				__syncwarp();
+				if (lane == 0) steady_update(c.sops, g->code + vs.code_off, vs.code_len, nb);
+				__syncwarp();
+				vs.duration -= span;
+				run_total += span;
+				off += span - CHUNK;
+				continue;
+			}
+			uint32_t clen = uend - off;
+			if (clen > (uint32_t) CHUNK) clen = CHUNK;
+			const uint32_t time = vs.duration < clen ? vs.duration : clen;
+			c.oc = off % REF_BLOCK;
+			uint32_t rem0 = vs.duration;
+			if (sd.len - off < rem0) rem0 = sd.len - off;
+			if (REF_BLOCK - c.oc < rem0) rem0 = REF_BLOCK - c.oc;
+			uint32_t out_len = 0;
+			if (vs.code_len && op_ptr(c, vs.carr_slot)->time > 0)     /* run_voice, :833-846 */
+				out_len = run_chunk(c, g->code + vs.code_off, vs.code_len, time, rem0,
+						row_s, row_r, sd.start + off);
+			__syncwarp();
+			if (out_len && pan_mode == PAN_UNSET) {
+				/* first rendered chunk of the segment decides (run_chunk wrote r if moving) */
+				pan_mode = c.pan_dyn ? PAN_DYNAMIC :
+					__float_as_uint(op_ptr(c, vs.carr_slot)->line[LINE_PAN].v0);
+				c.write_r = c.pan_dyn;
+				fc.write_r = c.write_r ? 1u : 0u;
+			}
+			vs.duration -= time;
+			run_total += out_len;
+		}
+		if (lane == 0 && run_total) {
+			/* frames this voice has run in the segment so far (units of a voice are
+			 * rendered in order, by one warp at a time) */
+			const uint32_t tot = __ldcg(&vsg->len) + run_total;
+			__stcg(reinterpret_cast<uint2*>(vsg), make_uint2(tot, pan_mode));
+			/* the maximum only grows: skip the atomic when it is already there */
+			if (__ldcg(&g->status[1 + si]) < tot) atomicMax(&g->status[1 + si], tot);
+		}
+	}
+	if (loaded) ops_store(c, loaded);
+	if (lane == 0) {
+		const uint32_t *w = reinterpret_cast<const uint32_t*>(&vs);
+#pragma unroll
+		for (uint32_t i = 0; i < sizeof(VoiceState) / 4; ++i)
+			__stcg(reinterpret_cast<uint32_t*>(vsp) + i, w[i]);
+		if (u1 == cd->nunits && vs.duration != 0) atomicOr(&g->status[0], 1u);
+	}
+}
+
+__device__ __forceinline__ void render_body(const CallDesc *calls, uint32_t ncalls,
+		const SegDesc *segs, const UnitDesc *units, uint32_t ntasks, const float *tables,
+		const double *coefs, uint32_t wave_mask, uint32_t nbufs, uint32_t nslots_ops, uint32_t nplan, uint32_t warps_per_cta,
+		uint32_t ticketed) {
+	extern __shared__ __align__(128) unsigned char smem[];
+	uint64_t *bar = reinterpret_cast<uint64_t*>(smem);
+	float *tab = reinterpret_cast<float*>(smem + 128);
+	const bool ctab = (wave_mask & CTAB_FLAG) != 0;
+	const uint32_t nslots = __popc(wave_mask & ~CTAB_FLAG);
+	const uint32_t slot_bytes = ctab ? CTAB_WAVE_BYTES : TAB_STRIDE * (uint32_t) sizeof(float);
+	unsigned char *warp_area = smem + 128 + nslots * slot_bytes;
+	const uint32_t per_warp = warp_smem_bytes(nbufs, nslots_ops, nplan);
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+	/* stage the tables this launch needs: TMA bulk copies, one mbarrier */
+	if (threadIdx.x == 0) {
+		mbar_init(bar, 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	__syncthreads();
+	if (threadIdx.x == 0 && nslots) {
+		mbar_expect_tx(bar, nslots * (ctab ? CTAB_WAVE_BYTES : WAVE_LEN * (uint32_t) sizeof(float)));
+		uint32_t slot = 0;
+		for (uint32_t w = 0; w < NUM_WAVES; ++w) {
+			if (!(wave_mask & (1u << w))) continue;
+			if (ctab)
+				tma_bulk_g2s(smem + 128 + slot * CTAB_WAVE_BYTES,
+						reinterpret_cast<const unsigned char*>(coefs) + (size_t) w * CTAB_WAVE_BYTES,
+						CTAB_WAVE_BYTES, bar);
+			else
+				tma_bulk_g2s(tab + slot * TAB_STRIDE + 4, tables + w * WAVE_LEN,
+						WAVE_LEN * sizeof(float), bar);
+			++slot;
+		}
+	}
+	if (nslots) {
+		mbar_wait(bar, 0);
+		/* wrapped neighbours: lut[-1], lut[2048], lut[2049] */
+		if (!ctab && threadIdx.x < nslots) {
+			float *t = tab + threadIdx.x * TAB_STRIDE + 4;
+			t[-1] = t[WAVE_LEN - 1];
+			t[WAVE_LEN] = t[0];
+			t[WAVE_LEN + 1] = t[1];
+		}
+		__syncthreads();
+	}
+
+	Ctx c;
+	c.sops = reinterpret_cast<OpState*>(warp_area + warp * per_warp);
+	c.bufs = reinterpret_cast<float*>(c.sops + nslots_ops);
+	c.stk_len = reinterpret_cast<uint32_t*>(c.bufs + nbufs * BUF_FLOATS);
+	c.stk_rem = c.stk_len + MAX_NEST;
+	c.stk_layer = c.stk_rem + MAX_NEST;
+	c.tab = tab;                     /* staged float tables, or the coefficient planes */
+	c.wc = reinterpret_cast<const WaveCoeffs*>(tables + NUM_WAVES * WAVE_LEN);
+	c.wave_mask = wave_mask;
+	c.lane = lane;
+	FastCtx fc;
+	fc.so = smem_u32(c.sops);
+	fc.sb = smem_u32(c.bufs) + lane * 16;
+	fc.st = smem_u32(tab);           /* staged float tables, or the coefficient tables */
+	fc.tab = c.tab; fc.wc = c.wc;
+	fc.wave_mask = wave_mask; fc.lane = lane;
+	fc.plan = smem_u32(c.stk_len);   /* the plan overlays the len stacks */
+	fc.plan_cap = nplan * 32u > STACK_BYTES ? nplan : STACK_BYTES / 32u;
+
+	if (!ticketed) {
+		/* one warp renders every unit of one voice; task -> (call, voice) by
+		 * binary search on task_base */
+		const uint32_t task = blockIdx.x * warps_per_cta + warp;
+		if (task >= ntasks) return;
+		uint32_t ci = 0, hi = ncalls;
+		while (hi - ci > 1) {
+			const uint32_t mid = (ci + hi) >> 1;
+			if (calls[mid].task_base <= task) ci = mid; else hi = mid;
+		}
+		const CallDesc *cd = &calls[ci];
+		render_units(c, fc, cd, segs, units, task - cd->task_base, 0, cd->nunits);
+		return;
+	}
+	const CallDesc *cd = &calls[0];
+	const GenDesc *g = cd->gen;
+	const uint32_t nlv = g->voice_end - g->voice_begin;
+	if (ticketed == 2) {
+		/* Balanced: more voices than resident warps, all of them alike.  The
+		 * (voice, unit) items of the call, voice-major, are cut into one contiguous
+		 * range per warp of a grid that is resident all at once, so every warp gets
+		 * the same amount of work (+-1 unit) and there is no second, partly filled
+		 * wave.  A range covers the tail of one voice, whole voices, and the head
+		 * of another.  The head comes FIRST (it depends on nothing), the tail LAST:
+		 * it continues what the previous warp rendered as its first action, handed
+		 * over through L2 (progress[], release / acquire).  Warp ranks are taken
+		 * from a counter, so the warp holding the previous rank has already started. */
+		const uint32_t U = cd->nunits;
+		const uint64_t items = (uint64_t) nlv * U;
+		const uint64_t S = (uint64_t) gridDim.x * warps_per_cta;
+		uint32_t rank = 0;
+		if (lane == 0) rank = atomicAdd(g->ticket, 1u);
+		rank = __shfl_sync(FULL, rank, 0);
+		const uint64_t begin = rank * items / S, end = (rank + 1ull) * items / S;
+		if (begin >= end) return;
+		const uint32_t vA = (uint32_t) (begin / U), uA = (uint32_t) (begin - (uint64_t) vA * U);
+		const uint32_t vB = (uint32_t) ((end - 1) / U), uB = (uint32_t) (end - (uint64_t) vB * U);
+		auto publish = [&](uint32_t lv, uint32_t u) {
+			__threadfence();
+			__syncwarp();
+			if (lane == 0) *(volatile uint32_t*) (g->progress + lv) = u;
+		};
+		auto await = [&](uint32_t lv, uint32_t u) {
+			if (lane == 0) {
+				volatile uint32_t *pr = g->progress + lv;
+				while (*pr != u) __nanosleep(64);
+				__threadfence();
+			}
+			__syncwarp();
+		};
+		if (vA == vB) {
+			if (uA) await(vA, uA);
+			render_units(c, fc, cd, segs, units, vA, uA, uB);
+			if (uB < U) publish(vA, uB);
+			return;
+		}
+		uint32_t v_hi = vB;                    /* whole voices are [v_lo, v_hi] */
+		if (uB < U) {
+			render_units(c, fc, cd, segs, units, vB, 0, uB);
+			publish(vB, uB);
+			--v_hi;
+		}
+		const uint32_t v_lo = uA ? vA + 1 : vA;
+		for (uint32_t v = v_lo; v <= v_hi; ++v)
+			render_units(c, fc, cd, segs, units, v, 0, U);
+		if (uA) {
+			await(vA, uA);
+			render_units(c, fc, cd, segs, units, vA, uA, U);
+		}
+		return;
+	}
+	/* Ticketed: a persistent grid hands out (unit, voice) pairs in time order, so
+	 * that SMs stay evenly loaded when there are more voices than resident warps.
+	 * Unit u of a voice may start once its unit u-1 is done (progress[], release /
+	 * acquire through global memory); the holder of every earlier ticket is
+	 * already running, so the wait always ends. */
+	const uint32_t total = nlv * cd->nunits;
+	for (;;) {
+		uint32_t t = 0;
+		if (lane == 0) t = atomicAdd(g->ticket, 1u);
+		t = __shfl_sync(FULL, t, 0);
+		if (t >= total) break;
+		const uint32_t u = t / nlv, lv = t - u * nlv;
+		if (lane == 0) {
+			volatile uint32_t *pr = g->progress + lv;
+			while (*pr != u) __nanosleep(32);
+			__threadfence();
+		}
+		__syncwarp();
+		render_units(c, fc, cd, segs, units, lv, u, u + 1);
+		__threadfence();
+		__syncwarp();
+		if (lane == 0) *(volatile uint32_t*) (g->progress + lv) = u + 1;
+	}
+}
+
+__global__ void __launch_bounds__(256, 2)
+render_kernel(const CallDesc *calls, uint32_t ncalls, const SegDesc *segs, const UnitDesc *units,
+		uint32_t ntasks, const float *tables, const double *coefs, uint32_t wave_mask, uint32_t nbufs,
+		uint32_t nslots_ops, uint32_t nplan, uint32_t warps_per_cta, uint32_t ticketed) {
+	render_body(calls, ncalls, segs, units, ntasks, tables, coefs, wave_mask, nbufs, nslots_ops, nplan,
+			warps_per_cta, ticketed);
+}
+
+/* same body for CTAs of up to 32 warps (64 registers), one per SM (coefficient-table
+ * mode: the planes take 48 KiB per wave, so one large CTA shares them among all the
+ * warps an SM can hold -- the path is latency-bound, resident warps are what counts) */
+__global__ void __launch_bounds__(WIDE_WARPS * 32, 1)
+render_kernel_wide(const CallDesc *calls, uint32_t ncalls, const SegDesc *segs, const UnitDesc *units,
+		uint32_t ntasks, const float *tables, const double *coefs, uint32_t wave_mask, uint32_t nbufs,
+		uint32_t nslots_ops, uint32_t nplan, uint32_t warps_per_cta, uint32_t ticketed) {
+	render_body(calls, ncalls, segs, units, ntasks, tables, coefs, wave_mask, nbufs, nslots_ops, nplan,
+			warps_per_cta, ticketed);
+}

@@ -320,7 +320,7 @@ struct saugen_Generator {
 	uint32_t row_stride = 0;
 	uint32_t row_len = 0, nbufs = 1, max_ops = 1, wave_mask = 0, seg_cap = 0, sched = 0;
 	bool big_endian = false;           // saugen_Options::pcm_big_endian
-	uint32_t nplan = 0;                // block-plan records the largest voice program needs (kernels.cu)
+	uint32_t nplan = 0;                // block-plan records the largest voice program needs (render_plan.cuh)
 	float amp_scale = 0.f;
 	/* timeline (host-only integer bookkeeping) */
 	std::vector<uint64_t> ev_time;     // absolute sample time of each event
@@ -716,7 +716,7 @@ static bool flatten_program(const sauabi_Program *prg, uint32_t srate, Flat &f) 
 					po.second = (uint32_t) comp.prog_ops.size();
 					if (po.second > o->max_ops) o->max_ops = po.second;
 					{
-						/* records of the fast path's block plan (kernels.cu:steady_plan): the
+						/* records of the fast path's block plan (render_plan.cuh:steady_plan): the
 						 * instructions that do something per chunk; a program with any other
 						 * kind of instruction never takes that path */
 						uint32_t np = 0;
@@ -1059,7 +1059,7 @@ static void plan_units(const std::vector<SegDesc> &segs, std::vector<UnitDesc> &
  * voices are resident per SM at once.  One CTA per SM, with as many warps as it
  * takes to hold every task in ONE resident wave (up to what shared memory
  * allows, at most 32); up to 8 warps run the 128-register kernel, more the
- * 64-register one.  Tables: coefficient planes (kernels.cu:CTAB_FLAG, 48 KiB per
+ * 64-register one.  Tables: coefficient planes (render_ops.cuh:CTAB_FLAG, 48 KiB per
  * wave) when the launch uses at most two waves, else the float tables (8 KiB
  * per wave in use). */
 static const uint32_t CTAB_FLAG = 0x80000000u;

@@ -2,7 +2,7 @@
 random delays, durations that put line goals and operator ends in the middle of calls and
 of 1024-sample blocks, compared bit for bit (PCM, then integer and float operator state)
 against the unmodified reference at several call sizes.  Aimed at the steady-stretch plan
-(kernels.cu:steady_plan): stretches of many blocks next to blocks the general interpreter
+(render_plan.cuh:steady_plan): stretches of many blocks next to blocks the general interpreter
 has to take, uniform-frequency ratio chains, amplitude modulators, N / R operators."""
 import random
 
