@@ -50,7 +50,8 @@ __device__ __forceinline__ uint32_t op_span(const OpState *o, uint32_t k) {
  * of the chunk is at phase0 + (i + 1) * inc in wrap-around uint32 arithmetic --
  * bit-identical to the serial accumulation, without conversions or a scan. */
 enum : uint32_t { P_LINE = 1, P_WHEAD, P_WTAIL, P_WLEAF, P_PHASE, P_WOSC, P_RANGE, P_VOUT,
-	P_NOISE, P_CYCLE, P_RASG, P_MIX, P_WSELF };
+	P_NOISE, P_CYCLE, P_RASG, P_MIX, P_WSELF,
+	P_EXT };           /* second slot of the record before it (never dispatched on its own) */
 enum : uint32_t {
 	PF_LAYER = 1, PF_WAVEENV = 2,
 	PF_FUNI = 4,       /* frequency (or the LINE's value) is uniform over the block: w6 holds the
@@ -59,6 +60,9 @@ enum : uint32_t {
 	                    * (varying) multiplier buffer: a ratio to a modulated parent frequency */
 	PF_ACONST = 16,    /* amplitude line holds av */
 	PF_ABUF = 32,      /* amplitude comes from work buffer c (the operator has amplitude modulators) */
+	PF_AEXT = 64,      /* amplitude line on a lin / xpe / lge trajectory: its constants for the stretch
+	                    * are in the P_EXT slot after the record (w0 type << 8, w1 position or centred
+	                    * position at the stretch start, w2 1/time, w3 slope / span, w4 offset) */
 };
 constexpr uint32_t PLAN_FBUF = 32 * FAST_NS * 4;    /* FastCfg<FAST_NS>::FBUF_BYTES */
 constexpr uint32_t PLAN_REC = 32;     /* bytes: w0 kind|flags<<8|a<<16|b<<24, w1 c|e<<8|line<<16,
@@ -380,6 +384,29 @@ __device__ __noinline__ uint32_t steady_plan(OpState *sops, uint32_t so, uint32_
 					(uint32_t) in.c | (uint32_t) in.e << 8, opa, ct,
 					wc->diff_scale[wave], wc->diff_offset[wave], rmul ? fval : __uint_as_float(inc),
 					o->line[LINE_AMP].v0);
+			if (!aconst && n < cap) {
+				/* the amplitude trajectory's constants, worked out once (sau::line_fill_setup) */
+				const LineState &al = o->line[LINE_AMP];
+				int t = (int) LM_TYPE(o->lmeta[LINE_AMP]);
+				if (t == sau::L_exp) t = (al.v0 > al.vt) ? sau::L_xpe : sau::L_lge;
+				else if (t == sau::L_log) t = (al.v0 < al.vt) ? sau::L_xpe : sau::L_lge;
+				if (t == sau::L_lin || t == sau::L_xpe || t == sau::L_lge) {
+					const float inv = o->linv[LINE_AMP], vd = al.vt - al.v0;
+					uint32_t w1 = al.pos;
+					float w3, w4;
+					if (t == sau::L_lin) {
+						w1 = al.pos - (al.end / 2);
+						w3 = vd * inv; w4 = (al.v0 + al.vt) * 0.5f;
+					} else if (t == sau::L_xpe) {
+						w3 = al.v0 - al.vt; w4 = al.vt;
+					} else {
+						w3 = vd; w4 = al.v0;
+					}
+					if (lane0) sts32(plan + (n - 1) * PLAN_REC, lds32(plan + (n - 1) * PLAN_REC) | PF_AEXT << 8);
+					plan_put(plan, n++, P_EXT | (uint32_t) t << 8, w1, __float_as_uint(inv), __float_as_uint(w3),
+							w4, 0.f, 0.f, 0.f);
+				}
+			}
 			dirty(in.a);
 		}
 	}
@@ -803,6 +830,24 @@ __device__ __forceinline__ void osc_plan(const HotCtx &c, const uint4 p0, const 
 		for (int k = 0; k < NS; ++k) am[k] = av;
 	} else if (flags & PF_ABUF) {
 		fld<NS>(c, p0.y & 0xffu, am);
+	} else if (flags & PF_AEXT) {
+		/* sauLine_fill_lin / _xpe / _lge (line.c:65-140, as sau::line_fill_at) from the
+		 * stretch constants in the record's second slot */
+		const uint4 e = lds128u(rec + PLAN_REC);
+		const float w4 = lds32f(rec + PLAN_REC + 16);
+		const float inv = __uint_as_float(e.z), w3 = __uint_as_float(e.w);
+		const uint32_t i0 = e.y + c.oc + (uint32_t) (c.lane * NS);
+		const uint32_t t = e.x >> 8;
+		if (t == (uint32_t) sau::L_lin) {
+#pragma unroll
+			for (int k = 0; k < NS; ++k) am[k] = (sau::i2f((int32_t) (i0 + k)) * w3) + w4;
+		} else if (t == (uint32_t) sau::L_xpe) {
+#pragma unroll
+			for (int k = 0; k < NS; ++k) am[k] = sau::expramp6(1.f - sau::u2f(i0 + k) * inv) * w3 + w4;
+		} else {
+#pragma unroll
+			for (int k = 0; k < NS; ++k) am[k] = sau::expramp6(sau::u2f(i0 + k) * inv) * w3 + w4;
+		}
 	} else {
 		line_value_steady<NS>(c, op, LINE_AMP, nullptr, am);
 	}
@@ -982,6 +1027,7 @@ __device__ __forceinline__ void run_chunk_plan(const HotCtx &c, const uint32_t n
 				for (int k = 0; k < NS; ++k) ph[k] = __float_as_uint(pf[k]);
 			}
 			osc_plan<NS, CTAB>(c, p0, rec, pure, inc, ph);
+			if (flags & PF_AEXT) { rec += PLAN_REC; ++r; }         /* the record's second slot */
 		} else if (kind == P_RANGE) {                              /* generator.c:465-467 */
 			float p[NS], rr[NS], m[NS];
 			fld<NS>(c, p0.y & 0xffu, m);

@@ -723,7 +723,8 @@ static bool flatten_program(const sauabi_Program *prg, uint32_t srate, Flat &f) 
 						bool fast = true;
 						for (const Instr &in : comp.out) {
 							switch (in.opcode) {
-							case I_WLEAF: case I_WHEAD: case I_WTAIL: case I_RANGE: case I_VOUT:
+							case I_WLEAF: case I_WTAIL: np += 2; break;      /* + the amplitude trajectory's slot */
+							case I_WHEAD: case I_RANGE: case I_VOUT:
 							case I_PHASOR: case I_WOSC: case I_NOISE: case I_CYCLOR: case I_RASG: case I_MIX:
 							case I_PMA:
 								++np; break;
