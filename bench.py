@@ -244,7 +244,10 @@ def run_reference_arm(args):
         "ms_per_step": 1000.0 * t_tot / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "voices": VOICES, "frames_per_step": FRAMES,
-                   "srate": SRATE},
+                   "srate": SRATE, "op_samples_per_step": 3 * VOICES * FRAMES,
+                   "l2": "host arm: the reference's block buffers live in the CPU caches",
+                   "parallelism": f"one 4096-voice script, voices split over {used} host processes "
+                                  "(the reference is single-threaded)"},
         "realtime_factor": (FRAMES * args.steps / SRATE) / t_tot,
         "cpu_baseline": {"value": value, "unit": "voice-samples/s", "cores": used,
                          "kind": "reference",
