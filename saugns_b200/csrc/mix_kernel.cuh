@@ -9,12 +9,19 @@
  * addition is not associative and mix_add adds voice after voice,
  * generator.c:773-786).  The tile's voice pieces lie side by side in HBM
  * (device_types.h:ROW_TILE), so the CTA reads ONE contiguous stream: the
- * producer warp moves MIX_TV voices (8 KiB) per stage with a single TMA bulk copy
+ * producer warp moves MIX_TV voices (16 KiB) per stage with a single TMA bulk copy
  * (cp.async.bulk + mbarrier transaction count) into a ring of MIX_STAGES
  * stages, the four consumer warps add behind it.
  * A voice whose pan stands still contributes r = s * pan, computed here
  * (VoiceSeg); only moving pans have an r piece, which the consumers read straight
- * from HBM (a coalesced 128-byte line per warp; rare). */
+ * from HBM (a coalesced 128-byte line per warp; rare).
+ * The producer also classifies each stage: when its MIX_TV voices all run through the
+ * whole tile with pans standing still (MixSmem::slow == 0, the common case) the
+ * consumers take a loop with unconditional loads and no per-voice decisions, whose
+ * critical path is the two dependent additions per voice and channel (with one warp
+ * per scheduler every exposed latency counts: the per-voice compare + predicated load
+ * of the general loop held a CTA to 25 GB/s).  The bulk copies carry an L2
+ * evict-first hint (render_ops.cuh:tma_bulk_g2s_stream). */
 constexpr int MIX_FRAMES = ROW_TILE;           // = consumer threads (one per frame)
 constexpr int MIX_TV = 32;                     // voices per stage (16 KiB per bulk copy)
 constexpr int MIX_STAGES = 5;
@@ -22,8 +29,9 @@ constexpr int MIX_CWARPS = MIX_FRAMES / 32;    // consumer warps; one more warp 
 struct MixSmem {
 	float s[MIX_STAGES][MIX_TV][MIX_FRAMES];
 	uint2 vi[MIX_STAGES][MIX_TV];              // the tile's VoiceSeg records
+	float pan[MIX_STAGES][MIX_TV];             // their (constant) pans, packed for 128-bit reads
 	uint64_t full[MIX_STAGES], empty[MIX_STAGES];
-	uint32_t ndyn[MIX_STAGES];                 // moving-pan voices in the stage's tile
+	uint32_t slow[MIX_STAGES];                 // the stage has a moving pan or a voice ending inside the tile
 };
 
 __device__ __forceinline__ void mix_store(const GenDesc *g, const CallDesc *cd, uint32_t mode,
@@ -126,6 +134,11 @@ mix_kernel(const CallDesc *calls, const SegDesc *segs, uint32_t mode /*0 pcm, 1 
 			return (lane < (uint32_t) MIX_TV && v < nlv) ? __ldg(vl + v) : make_uint2(0u, 0u);
 		};
 		uint2 pre0 = fetch(0), pre1 = fetch(1), pre2 = fetch(2);
+		/* the tile's last frame, counted from the segment start: a voice running beyond it
+		 * contributes to every frame of the tile */
+		const uint32_t last = cd->call_len - 1u - f0 < (uint32_t) (MIX_FRAMES - 1) ?
+			cd->call_len - 1u - f0 : (uint32_t) (MIX_FRAMES - 1);
+		const uint32_t fi_last = f0 - segs[cd->seg_off + seg0].start + last;
 		for (uint32_t t = 0; t < ntiles; ++t) {
 			const uint32_t st = t % MIX_STAGES, v0 = t * MIX_TV;
 			const uint32_t nv = nlv - v0 < (uint32_t) MIX_TV ? nlv - v0 : (uint32_t) MIX_TV;
@@ -133,35 +146,42 @@ mix_kernel(const CallDesc *calls, const SegDesc *segs, uint32_t mode /*0 pcm, 1 
 			pre0 = pre1; pre1 = pre2; pre2 = fetch(t + 3);
 			if (t >= (uint32_t) MIX_STAGES) mbar_wait(&sm.empty[st], ((t / MIX_STAGES) - 1u) & 1u);
 			const bool has = lane < nv;
-			if (has) sm.vi[st][lane] = info;
-			const uint32_t dynmask = __ballot_sync(FULL, has && info.y == PAN_DYNAMIC && info.x);
-			if (lane == 0) sm.ndyn[st] = __popc(dynmask);
-			__syncwarp();                      /* vi, ndyn written before lane 0's arrive publishes them */
+			if (has) { sm.vi[st][lane] = info; sm.pan[st][lane] = __uint_as_float(info.y); }
+			const uint32_t slowmask = __ballot_sync(FULL, !has || info.y == PAN_DYNAMIC || info.x <= fi_last);
+			if (lane == 0) sm.slow[st] = slowmask;
+			__syncwarp();                      /* vi, pan, slow written before lane 0's arrive publishes them */
 			if (lane == 0) {
 				const uint32_t piece = ROW_TILE * (uint32_t) sizeof(float);
 				mbar_expect_tx(&sm.full[st], nv * piece);
-				tma_bulk_g2s(&sm.s[st][0][0], tile_s + (size_t) v0 * ROW_TILE, nv * piece, &sm.full[st]);
+				tma_bulk_g2s_stream(&sm.s[st][0][0], tile_s + (size_t) v0 * ROW_TILE, nv * piece, &sm.full[st]);
 			}
 		}
 		return;
 	}
 	const uint32_t fx = in_seg ? fi : 0xffffffffu;               /* frames outside take nothing */
+	const float *tile_r = g->rows_r + (size_t) blockIdx.x * tstride + tid;
 	for (uint32_t t = 0; t < ntiles; ++t) {
 		const uint32_t st = t % MIX_STAGES, v0 = t * MIX_TV;
 		const uint32_t nv = nlv - v0 < (uint32_t) MIX_TV ? nlv - v0 : (uint32_t) MIX_TV;
 		mbar_wait(&sm.full[st], (t / MIX_STAGES) & 1u);
 		const float *sp = &sm.s[st][0][tid];
-		const float *rp = g->rows_r + (size_t) blockIdx.x * tstride + (size_t) v0 * ROW_TILE + tid;
+		const float *rp = tile_r + (size_t) v0 * ROW_TILE;
 		const uint2 *ip = &sm.vi[st][0];
-		if (nv == (uint32_t) MIX_TV && sm.ndyn[st] == 0) {
-			/* the common tile: all pans stand still */
+		if (sm.slow[st] == 0) {
+			/* the common stage: MIX_TV voices that all run through the whole tile with pans
+			 * standing still -- unconditional loads, no per-voice decisions; the two
+			 * dependent additions per voice and channel are the critical path */
+			const float4 *pp = reinterpret_cast<const float4*>(&sm.pan[st][0]);
 #pragma unroll
-			for (int k = 0; k < MIX_TV; ++k) {
-				const uint2 info = ip[k];
-				const float s = fx < info.x ? sp[k * MIX_FRAMES] : 0.f;
-				const float rr = s * __uint_as_float(info.y);
-				L = (L + s) - rr;                              /* as compiled, Appendix B.3; */
-				R = (R + s) + rr;                              /* adding 0 is exact */
+			for (int k = 0; k < MIX_TV; k += 4) {
+				const float4 pan = pp[k >> 2];
+				const float s0 = sp[(k + 0) * MIX_FRAMES], s1 = sp[(k + 1) * MIX_FRAMES];
+				const float s2 = sp[(k + 2) * MIX_FRAMES], s3 = sp[(k + 3) * MIX_FRAMES];
+				const float r0 = s0 * pan.x, r1 = s1 * pan.y, r2 = s2 * pan.z, r3 = s3 * pan.w;
+				L = (L + s0) - r0; R = (R + s0) + r0;          /* as compiled, Appendix B.3 */
+				L = (L + s1) - r1; R = (R + s1) + r1;
+				L = (L + s2) - r2; R = (R + s2) + r2;
+				L = (L + s3) - r3; R = (R + s3) + r3;
 			}
 		} else {
 			for (uint32_t k = 0; k < nv; ++k) {
