@@ -304,6 +304,29 @@ def test_nesting_limit_reported(S, ref, tabs):
         S.Generator(prg, 96000, tables=tabs)
 
 
+def test_mix_stage_classes(S, ref, tabs):
+    """The mix kernel's stage classes side by side (mix_kernel.cuh): 32-voice stages whose
+    voices all run through a frame tile with constant pans (decision-free loop), stages with
+    a voice ending inside the tile, with a moving pan, with fewer than 32 voices; stereo and
+    mono, two call sizes.  Voice order of the float sums is the reference's: bit-exact."""
+    import random
+    rnd = random.Random(23)
+    lines = []
+    for i in range(107):                               # 3 full stages + one of 11 voices
+        t = 0.30 if i < 64 else rnd.choice([0.30, 0.30, rnd.uniform(0.05, 0.29)])
+        pan = f"c{rnd.uniform(-1, 1):.3f}"
+        if i in (40, 70, 71, 100):
+            pan = f"c-1[g1 t{rnd.uniform(0.05, 0.25):.3f}]"     # moving pan: r pieces
+        lines.append(f"W{rnd.choice(scripts.WAVES)} f{rnd.uniform(80, 2000):.2f} t{t:.4f} "
+                     f"a{rnd.uniform(0.2, 0.9):.2f} {pan}")
+    prg = ref.Program("S a.m(1/107)\n" + "\n".join(lines) + "\n")
+    for stereo in (True, False):
+        want = ref.render(prg, srate=96000, stereo=stereo)
+        for call_len in (24576, 1000):
+            got = S.render(prg, srate=96000, tables=tabs, call_len=call_len, stereo=stereo)
+            assert got.shape == want.shape and np.array_equal(got, want), (stereo, call_len)
+
+
 def test_c3_full_voice_count_bit_exact(S, ref, tabs):
     """BASELINE config 3 at its full 4096 voices (one resident wave of 28-warp CTAs with
     the coefficient planes, the launch shape bench.py times), 0.6 s: every PCM sample and
