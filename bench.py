@@ -551,7 +551,7 @@ def run_gpu_config(args):
 
     batch.render_batch(prgs, srate=SRATE, device=local_rank, tables=tabs,
                        group_size=args.group, threads=args.threads, sink=sink,
-                       call_len=args.call_frames)
+                       call_len=args.call_frames, pinned=args.pinned, depth=args.depth)
     wall = time.perf_counter() - t0
     assert len(got) == n
     frames = sum(v[0] for v in got.values())
@@ -589,6 +589,8 @@ def main():
     ap.add_argument("--scripts", type=int, default=1250, help="c5: scripts on this GPU")
     ap.add_argument("--group", type=int, default=128, help="c5: generators in flight per driver thread")
     ap.add_argument("--threads", type=int, default=1, help="c5: driver threads")
+    ap.add_argument("--pinned", action="store_true", help="c5: page-locked (recycled) PCM arrays, no staging copy")
+    ap.add_argument("--depth", type=int, default=2, help="c5: alternating live sets per driver thread")
     ap.add_argument("--call-frames", type=int, default=4 * FRAMES,
                     help="c5: frames per generator call (results do not depend on it)")
     args = ap.parse_args()
