@@ -49,7 +49,8 @@ __device__ __forceinline__ uint32_t op_span(const OpState *o, uint32_t k) {
  * closed form: every sample adds the same inc = lrintf(coeff * f), so sample i
  * of the chunk is at phase0 + (i + 1) * inc in wrap-around uint32 arithmetic --
  * bit-identical to the serial accumulation, without conversions or a scan. */
-enum : uint32_t { P_LINE = 1, P_WHEAD, P_WTAIL, P_WLEAF, P_PHASE, P_WOSC, P_RANGE, P_VOUT,
+enum : uint32_t { P_STOP = 0,          /* end mark after the last record (steady_plan's finish) */
+	P_LINE = 1, P_WHEAD, P_WTAIL, P_WLEAF, P_PHASE, P_WOSC, P_RANGE, P_VOUT,
 	P_NOISE, P_CYCLE, P_RASG, P_MIX, P_WSELF,
 	P_EXT };           /* second slot of the record before it (never dispatched on its own) */
 enum : uint32_t {
@@ -65,6 +66,7 @@ enum : uint32_t {
 	                    * position at the stretch start, w2 1/time, w3 slope / span, w4 offset) */
 };
 constexpr uint32_t PLAN_FBUF = 32 * FAST_NS * 4;    /* FastCfg<FAST_NS>::FBUF_BYTES */
+constexpr uint32_t PLAN_WALK_MAX = 66 * 32;   /* bytes: more than any plan holds (runtime.cpp: np <= 64) */
 constexpr uint32_t PLAN_REC = 32;     /* bytes: w0 kind|flags<<8|a<<16|b<<24, w1 c|e<<8|line<<16,
                                        * w2 operator state (shared address), w3 table (shared address),
                                        * w4 diff_scale, w5 diff_offset, w6 uniform value / phase increment, w7 av */
@@ -103,7 +105,7 @@ __device__ __noinline__ uint32_t steady_plan(OpState *sops, uint32_t so, uint32_
 	uint32_t other = 0;                /* the plan has serial self-PM records (bit 31 of the result) */
 	uint32_t n = 0;
 	plan += PLAN_REC;          /* slot 0 is the header (render_units) */
-	if (cap) --cap;
+	cap = cap > 2u ? cap - 2u : 0u;   /* ... and one slot stays free for the end mark */
 	auto is_uni = [&](uint32_t b) { return b < 32 && ((uni >> b) & 1u); };
 	auto touch = [&](uint32_t b) { if (b < 32) { need |= 1u << b; line_uni &= ~(1u << b); } };   /* read as a vector */
 	auto dirty = [&](uint32_t b) {                                             /* rewritten */
@@ -133,6 +135,9 @@ __device__ __noinline__ uint32_t steady_plan(OpState *sops, uint32_t so, uint32_
 			__syncwarp();
 			nrec = w;
 		}
+		/* the end mark: the chunk loop runs until it meets it (no record count to keep) */
+		if (lane0) sts32(plan + nrec * PLAN_REC, P_STOP);
+		__syncwarp();
 		return other | kb << 16 | nrec;
 	};
 	/* the operator's phase fill takes its frequency from uniform buffer b: the
@@ -964,13 +969,15 @@ __device__ __noinline__ void plan_other(uint32_t sb, float coeff, uint32_t oc, u
 }
 
 template <int NS, bool CTAB, bool OTHER>
-__device__ __forceinline__ void run_chunk_plan(const HotCtx &c, const uint32_t nrec,
+__device__ __forceinline__ void run_chunk_plan(const HotCtx &c,
 		float *row_s, float *row_r, const uint32_t frame) {
 	uint32_t rec = c.plan;
-	for (uint32_t r = 0; r < nrec; ++r) {
+	for (;;) {
 		rec += PLAN_REC;
 		const uint4 p0 = lds128u(rec);
 		const uint32_t kind = p0.x & 0xffu, flags = (p0.x >> 8) & 0xffu;
+		/* the end mark (the second test only bounds the walk should a plan ever lack it) */
+		if (kind == P_STOP || rec - c.plan > PLAN_WALK_MAX) break;
 		const uint32_t bufa = (p0.x >> 16) & 0xffu, bufb = p0.x >> 24;
 		const uint32_t op = p0.z;
 		if (kind <= P_WOSC) {
@@ -1027,7 +1034,7 @@ __device__ __forceinline__ void run_chunk_plan(const HotCtx &c, const uint32_t n
 				for (int k = 0; k < NS; ++k) ph[k] = __float_as_uint(pf[k]);
 			}
 			osc_plan<NS, CTAB>(c, p0, rec, pure, inc, ph);
-			if (flags & PF_AEXT) { rec += PLAN_REC; ++r; }         /* the record's second slot */
+			if (flags & PF_AEXT) rec += PLAN_REC;                  /* the record's second slot */
 		} else if (kind == P_RANGE) {                              /* generator.c:465-467 */
 			float p[NS], rr[NS], m[NS];
 			fld<NS>(c, p0.y & 0xffu, m);
@@ -1091,6 +1098,6 @@ __device__ __noinline__ void run_block_fast(uint32_t sb, uint32_t plan, int lane
 	c.sb = sb; c.plan = plan; c.lane = lane; c.coeff = coeff;
 	for (uint32_t oc = 0; oc < len; oc += FastCfg<FAST_NS>::CHUNKF) {
 		c.oc = oc;
-		run_chunk_plan<FAST_NS, CTAB, OTHER>(c, nrec, row_s, row_r, frame + oc);
+		run_chunk_plan<FAST_NS, CTAB, OTHER>(c, row_s, row_r, frame + oc);
 	}
 }

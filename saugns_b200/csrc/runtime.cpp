@@ -733,7 +733,7 @@ static bool flatten_program(const sauabi_Program *prg, uint32_t srate, Flat &f) 
 							default: fast = false; break;
 							}
 						}
-						++np;                              /* the plan's header slot */
+						np += 2;                           /* the plan's header slot and its end mark */
 						if (fast && np <= 64 && np > o->nplan) o->nplan = np;
 					}
 					prog_ops.insert(prog_ops.end(), comp.prog_ops.begin(), comp.prog_ops.end());
