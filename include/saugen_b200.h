@@ -28,8 +28,11 @@ typedef struct saugen_Generator saugen_Generator;
 
 /* The 12 pre-integrated wave tables + per-wave coefficients, as built on the
  * host by the front-end library (sau/wave.c:49-66,105-221; sau/wave.h:33-70).
- * The drop-in passes libsau's own arrays; NULL selects the built-in tables
- * (saugns_b200/csrc/wavetab.cpp). */
+ * They are INPUT DATA of the generator path: the drop-in passes libsau's own arrays
+ * (sauWave_piluts / sauWave_picoeffs after sau_global_init_Wave, sau/generator.c:215);
+ * a caller without libsau in its process loads the file those arrays were written to
+ * (saugen_wave_tables_load; saugns_b200/data/sau_wave_tables.bin, tools/make_wave_tables.py).
+ * The back end never regenerates them; saugen_create fails on NULL. */
 typedef struct saugen_WaveTables {
 	const float *pilut[SAUABI_WAVE_NAMED];   /* 2048 floats each */
 	float amp_scale[SAUABI_WAVE_NAMED];
@@ -37,7 +40,9 @@ typedef struct saugen_WaveTables {
 	int32_t phase_adj[SAUABI_WAVE_NAMED];
 } saugen_WaveTables;
 
-const saugen_WaveTables *saugen_builtin_wave_tables(void);
+/* Reads a table file into one malloc'd block (NULL on error); release with _free. */
+saugen_WaveTables *saugen_wave_tables_load(const char *path);
+void saugen_wave_tables_free(saugen_WaveTables *t);
 
 /* Creation options (zero-initialise for defaults). */
 typedef struct saugen_Options {
@@ -70,6 +75,14 @@ saugen_Generator *saugen_create(const sauabi_Program *prg, uint32_t srate,
 size_t saugen_flatten(const sauabi_Program *prg, uint32_t srate, void *blob, size_t cap);
 saugen_Generator *saugen_create_flat(const void *blob, size_t size,
 		const saugen_WaveTables *tables, const saugen_Options *opt);
+
+/* Which voices must stay on one generator when a script is voice-sharded: parseconv re-homes an
+ * operator whose voice slot was recycled (a later `@label` update gives the same op id a new
+ * voice); voices linked by such hand-overs share operator state.  group_of_voice[v] (vo_count
+ * entries, may be NULL) = smallest voice index of v's group; returns the number of hand-over
+ * events, <0 on error.  No GPU needed.  (Within one generator a hand-over cuts the call into
+ * separate render launches, so the state passes through a kernel boundary.) */
+int saugen_voice_groups(const sauabi_Program *prg, uint32_t srate, uint32_t *group_of_voice);
 
 /* == sau_destroy_Generator(o); NULL-safe. */
 void saugen_destroy(saugen_Generator *o);

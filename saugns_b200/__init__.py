@@ -7,7 +7,7 @@ package without the built extension, or using it without a CUDA device,
 raises -- there is no CPU fallback.
 """
 from .generator import (Generator, LIB_PATH, lib, render, run_many, device_count,  # noqa: F401
-                        WaveTables, OpView, last_error, flatten)
+                        WaveTables, OpView, last_error, flatten, voice_groups, default_tables)
 
 __all__ = ["Generator", "render", "run_many", "lib", "LIB_PATH", "device_count", "WaveTables",
-           "OpView", "last_error", "flatten"]
+           "OpView", "last_error", "flatten", "voice_groups", "default_tables"]

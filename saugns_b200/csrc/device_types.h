@@ -241,7 +241,8 @@ struct CallDesc {
 	uint32_t stereo;
 	uint32_t unit_off;     // first UnitDesc of this call
 	uint32_t nunits;
-	uint32_t _pad;
+	uint32_t more_launches;   // 1 = another render launch of this call follows (hand-over cut, runtime.cpp:
+	                          // plan_call): the voices' alive flag is set by the last launch only
 };
 
 } // namespace saugen

@@ -29,6 +29,7 @@
  */
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <mutex>
 #include "device_types.h"
 #include "sau_arith.h"
 #include "../../include/sau_program_abi.h"
@@ -83,8 +84,39 @@ __global__ void selftest_kernel(const float *tables, unsigned long long *bad) {
 	if (nbad) atomicAdd(bad, nbad);
 }
 
+/* multiprocessors of the current device (queried once per device) */
+int device_sm_count() {
+	static std::mutex mu;
+	static int sms[64] = {0};
+	int dev = 0;
+	cudaGetDevice(&dev);
+	if (dev < 0 || dev >= 64) dev = 0;
+	std::lock_guard<std::mutex> lk(mu);
+	if (!sms[dev]) {
+		int n = 0;
+		if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 1;
+		sms[dev] = n;
+	}
+	return sms[dev];
+}
+/* the most dynamic shared memory one CTA may opt in to on the current device */
+size_t device_smem_optin() {
+	static std::mutex mu;
+	static size_t cap[64] = {0};
+	int dev = 0;
+	cudaGetDevice(&dev);
+	if (dev < 0 || dev >= 64) dev = 0;
+	std::lock_guard<std::mutex> lk(mu);
+	if (!cap[dev]) {
+		int n = 0;
+		if (cudaDeviceGetAttribute(&n, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess || n <= 0) n = 48 * 1024;
+		cap[dev] = (size_t) n;
+	}
+	return cap[dev];
+}
+
 cudaError_t launch_selftest(const float *d_tables, unsigned long long *d_bad, cudaStream_t stream) {
-	selftest_kernel<<<148 * 8, 256, 0, stream>>>(d_tables, d_bad);
+	selftest_kernel<<<device_sm_count() * 8, 256, 0, stream>>>(d_tables, d_bad);
 	return cudaGetLastError();
 }
 
@@ -133,16 +165,24 @@ cudaError_t launch_coefs(const float *d_tables, double *d_coefs, uint32_t *d_ine
 
 /* grid: one warp per voice task, or a persistent grid of `ticketed_ctas` CTAs with
  * sched_mode 1 = (unit, voice) tickets, 2 = balanced contiguous ranges */
+/* The opt-in shared-memory size of a kernel is set ONCE per device, to the device's
+ * maximum, under a lock: batch driver threads launch concurrently on one device, and a
+ * per-size cache could let one thread lower what another had just raised. */
 static cudaError_t ensure_smem(bool wide, size_t smem) {
+	static std::mutex mu;
+	static bool configured[2][64] = {{false}, {false}};
 	int dev = 0;
 	cudaGetDevice(&dev);
-	static size_t configured[2][64] = {{0}, {0}};
-	if (dev >= 0 && dev < 64 && smem > configured[wide][dev]) {
+	if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+	if (smem > device_smem_optin()) return cudaErrorInvalidValue;
+	std::lock_guard<std::mutex> lk(mu);
+	if (!configured[wide][dev]) {
+		const int cap = (int) device_smem_optin();
 		cudaError_t e = wide ?
-			cudaFuncSetAttribute(render_kernel_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem) :
-			cudaFuncSetAttribute(render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+			cudaFuncSetAttribute(render_kernel_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, cap) :
+			cudaFuncSetAttribute(render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
 		if (e != cudaSuccess) return e;
-		configured[wide][dev] = smem;
+		configured[wide][dev] = true;
 	}
 	return cudaSuccess;
 }
@@ -180,14 +220,19 @@ cudaError_t launch_mix(const CallDesc *d_calls, uint32_t ncalls, const SegDesc *
 		uint32_t max_call_len, uint32_t mode, cudaStream_t stream) {
 	if (ncalls == 0 || max_call_len == 0) return cudaSuccess;
 	dim3 grid((max_call_len + MIX_FRAMES - 1) / MIX_FRAMES, ncalls);
-	static bool configured[64] = {false};
-	int dev = 0;
-	cudaGetDevice(&dev);
-	if (dev >= 0 && dev < 64 && !configured[dev]) {
-		cudaError_t e = cudaFuncSetAttribute(mix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-				(int) sizeof(MixSmem));
-		if (e != cudaSuccess) return e;
-		configured[dev] = true;
+	{
+		static std::mutex mu;
+		static bool configured[64] = {false};
+		int dev = 0;
+		cudaGetDevice(&dev);
+		if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+		std::lock_guard<std::mutex> lk(mu);
+		if (!configured[dev]) {
+			cudaError_t e = cudaFuncSetAttribute(mix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+					(int) sizeof(MixSmem));
+			if (e != cudaSuccess) return e;
+			configured[dev] = true;
+		}
 	}
 	mix_kernel<<<grid, MIX_FRAMES + 32, sizeof(MixSmem), stream>>>(d_calls, d_segs, mode);
 	return cudaGetLastError();

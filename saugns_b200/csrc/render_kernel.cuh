@@ -174,7 +174,7 @@ __device__ __noinline__ void render_units(Ctx &c, FastCtx &fc, const CallDesc *c
 #pragma unroll
 		for (uint32_t i = 0; i < sizeof(VoiceState) / 4; ++i)
 			__stcg(reinterpret_cast<uint32_t*>(vsp) + i, w[i]);
-		if (u1 == cd->nunits && vs.duration != 0) atomicOr(&g->status[0], 1u);
+		if (u1 == cd->nunits && !cd->more_launches && vs.duration != 0) atomicOr(&g->status[0], 1u);
 	}
 }
 

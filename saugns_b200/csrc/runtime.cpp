@@ -45,7 +45,8 @@ cudaError_t launch_mix(const CallDesc *d_calls, uint32_t ncalls, const SegDesc *
 cudaError_t launch_planes_to_pcm(const float *d_mix, uint32_t plane_stride, uint32_t n,
 		uint32_t stereo, int16_t *d_pcm, cudaStream_t stream);
 cudaError_t launch_selftest(const float *d_tables, unsigned long long *d_bad, cudaStream_t stream);
-const saugen_WaveTables *builtin_wave_tables();
+int device_sm_count();
+size_t device_smem_optin();
 }
 
 using namespace saugen;
@@ -71,19 +72,20 @@ struct TableBlock { float *d; double *coefs; };
 static std::mutex g_tab_mu;
 static std::map<std::pair<int, uint64_t>, TableBlock> g_tabs;
 
-/* A batch render creates thousands of generators on the same table set: the full
- * content hash (98 KiB) is skipped when the caller's struct address and a sparse
- * fingerprint of the tables (every 64th value + the per-wave coefficients) were
- * seen before on this device. */
+/* A batch render creates thousands of generators on the same table set: the upload
+ * image and its byte-wise hash are skipped when the caller's struct address and a
+ * word-wise hash of EVERY table value and coefficient were seen before on this device
+ * (tables edited in place at the same address get a new device copy). */
 struct TableSeen { int device; const void *addr; uint64_t fp; TableBlock blk; };
 static std::vector<TableSeen> g_tab_seen;
+/* every table value and coefficient, eight bytes per step (~10 us for the 96 KiB) */
 static uint64_t table_fingerprint(const saugen_WaveTables *t) {
 	uint64_t h = 1469598103934665603ull;
-	auto mix = [&h](uint32_t v) { h ^= v; h *= 1099511628211ull; };
+	auto mix = [&h](uint64_t v) { h = (h ^ v) * 0x9E3779B97F4A7C15ull; h ^= h >> 29; };
 	for (int w = 0; w < NUM_WAVES; ++w) {
-		for (int i = 0; i < WAVE_LEN; i += 64) { uint32_t v; memcpy(&v, &t->pilut[w][i], 4); mix(v); }
+		for (int i = 0; i < WAVE_LEN; i += 2) { uint64_t v; memcpy(&v, &t->pilut[w][i], 8); mix(v); }
 		uint32_t a, b; memcpy(&a, &t->amp_scale[w], 4); memcpy(&b, &t->amp_dc[w], 4);
-		mix(a); mix(b); mix((uint32_t) t->phase_adj[w]);
+		mix(((uint64_t) a << 32) | b); mix((uint32_t) t->phase_adj[w]);
 	}
 	return h;
 }
@@ -324,6 +326,8 @@ struct saugen_Generator {
 	float amp_scale = 0.f;
 	/* timeline (host-only integer bookkeeping) */
 	std::vector<uint64_t> ev_time;     // absolute sample time of each event
+	std::vector<uint32_t> ev_handover; // Flat::ev_handover
+	std::vector<uint32_t> group_first; // first segment of every render launch after the first, of the planned call
 	size_t next_event = 0;
 	uint64_t cur_time = 0;
 	bool ended = false;
@@ -613,6 +617,14 @@ struct Flat {
 	std::vector<OpDataRec> opdata;
 	std::vector<Instr> code;
 	std::vector<uint32_t> prog_ops, vev_off, vev_idx;
+	/* Hand-over events.  Each voice's warp applies its own events and renders on its own,
+	 * which equals the reference's global event order (generator.c:915-949) as long as an
+	 * operator stays with one voice.  parseconv re-homes an operator whose voice slot was
+	 * recycled (a later `@label` update gives the same op id a new voice): the event that
+	 * touches an operator last touched under ANOTHER voice is a hand-over.  ev_handover[e]
+	 * = that other voice + 1 (0 = none); a call is cut into separate render launches there
+	 * (plan_call), so the operator's state passes through a kernel boundary. */
+	std::vector<uint32_t> ev_handover;
 };
 
 static bool flatten_program(const sauabi_Program *prg, uint32_t srate, Flat &f) {
@@ -623,6 +635,8 @@ static bool flatten_program(const sauabi_Program *prg, uint32_t srate, Flat &f) 
 	std::vector<Instr> &code = f.code;
 	std::vector<uint32_t> &prog_ops = f.prog_ops, &vev_off = f.vev_off, &vev_idx = f.vev_idx;
 	events.assign(prg->ev_count, EventRec());
+	f.ev_handover.assign(prg->ev_count, 0u);
+	std::vector<uint32_t> op_voice(prg->op_count, 0xffffffffu);   /* voice an operator was last touched under */
 	std::vector<HostOp> hops(prg->op_count);
 	std::vector<std::vector<uint32_t>> vev(prg->vo_count);
 	std::vector<uint32_t> vcarr(prg->vo_count, 0xffffffffu);
@@ -741,6 +755,15 @@ static bool flatten_program(const sauabi_Program *prg, uint32_t srate, Flat &f) 
 				er.code_off = pv.first; er.code_len = pv.second;
 				er.ops_off = po.first; er.ops_cnt = po.second; er.carr_slot = 0;
 				vev[pe->vo_id].push_back((uint32_t) ei);
+				/* operators this event updates or this voice now renders, met under another voice before */
+				auto touch = [&](uint32_t id) {
+					if (id >= op_voice.size()) return;
+					if (op_voice[id] != 0xffffffffu && op_voice[id] != pe->vo_id && !f.ev_handover[ei])
+						f.ev_handover[ei] = op_voice[id] + 1u;
+					op_voice[id] = pe->vo_id;
+				};
+				for (uint32_t k = 0; k < pe->op_data_count; ++k) touch(pe->op_data[k].id);
+				for (uint32_t id : comp.prog_ops) touch(id);
 			}
 		}
 		if (comp.too_deep) {
@@ -770,6 +793,13 @@ static saugen_Generator *create_from_flat(const Flat &f, const saugen_WaveTables
 		set_err("saugen_create: no usable CUDA device (this back end has no CPU path)", cudaGetLastError());
 		return nullptr;
 	}
+	if (!tables) {
+		/* the tables are input data built by the front-end library on the host (sau/wave.c:105-221);
+		 * this back end does not regenerate them */
+		g_err = "saugen_create: wave tables required (libsau's sauWave_piluts, or saugen_wave_tables_load)";
+		fprintf(stderr, "saugen_b200: error: %s\n", g_err.c_str());
+		return nullptr;
+	}
 	saugen_Generator *o = new saugen_Generator();
 	long long tp = now_ns();
 	auto lap = [&tp](int i) { if (g_cprof.on) { const long long t = now_ns(); g_cprof.ns[i] += t - tp; tp = t; } };
@@ -778,8 +808,6 @@ static saugen_Generator *create_from_flat(const Flat &f, const saugen_WaveTables
 	const std::vector<Instr> &code = f.code;
 	const std::vector<uint32_t> &prog_ops = f.prog_ops, &vev_off = f.vev_off, &vev_idx = f.vev_idx;
 	const uint32_t srate = f.srate;
-	if (!tables) tables = saugen::builtin_wave_tables();
-
 	o->srate = srate; o->device = opt->device; o->sched = opt->sched;
 	o->big_endian = opt->pcm_big_endian != 0;
 	o->vo_count = f.vo_count; o->op_count = f.op_count;
@@ -797,6 +825,23 @@ static saugen_Generator *create_from_flat(const Flat &f, const saugen_WaveTables
 	o->row_stride = (o->nlv ? o->nlv : 1u) * (uint32_t) ROW_TILE;
 	o->amp_scale = f.amp_scale;
 	o->ev_time = f.ev_time;
+	o->ev_handover = f.ev_handover;
+	if (o->voice_end - o->voice_begin < f.vo_count) {
+		/* a voice shard keeps operator state for its own voices only: a hand-over between a
+		 * voice inside and one outside cannot be rendered (multigpu.py shards around them) */
+		for (size_t e = 0; e < f.ev_handover.size(); ++e) {
+			if (!f.ev_handover[e]) continue;
+			const uint32_t a = f.ev_handover[e] - 1u, b = f.events[e].vo_id;
+			const bool ia = a >= o->voice_begin && a < o->voice_end, ib = b >= o->voice_begin && b < o->voice_end;
+			if (ia != ib) {
+				g_err = "saugen_create: an operator moves between voices on different shards "
+					"(use saugen_voice_groups to choose shard boundaries)";
+				fprintf(stderr, "saugen_b200: error: %s\n", g_err.c_str());
+				delete o;
+				return nullptr;
+			}
+		}
+	}
 	o->nbufs = f.nbufs; o->max_ops = f.max_ops; o->nplan = f.nplan; o->wave_mask = f.wave_mask;
 	lap(0);
 	/* ---- device allocation: one state block, one row block, one pinned block ---- */
@@ -928,14 +973,35 @@ extern "C" saugen_Generator *saugen_create(const sauabi_Program *prg, uint32_t s
 	return create_from_flat(f, tables, opt);
 }
 
+/* Voices linked by operator hand-overs (Flat::ev_handover) must be rendered by one generator:
+ * group_of_voice[v] = the smallest voice index of v's group.  Returns the number of hand-over
+ * events (0 = every voice is independent), <0 on error.  Needs no GPU. */
+extern "C" int saugen_voice_groups(const sauabi_Program *prg, uint32_t srate, uint32_t *group_of_voice) {
+	if (!prg || !srate) { g_err = "saugen_voice_groups: NULL program or zero sample rate"; return -1; }
+	Flat f;
+	if (!flatten_program(prg, srate, f)) return -1;
+	std::vector<uint32_t> parent(f.vo_count);
+	for (uint32_t v = 0; v < f.vo_count; ++v) parent[v] = v;
+	auto find = [&](uint32_t v) { while (parent[v] != v) { parent[v] = parent[parent[v]]; v = parent[v]; } return v; };
+	int n = 0;
+	for (size_t e = 0; e < f.ev_handover.size(); ++e) {
+		if (!f.ev_handover[e]) continue;
+		++n;
+		const uint32_t a = find(f.ev_handover[e] - 1u), b = find(f.events[e].vo_id);
+		if (a != b) { if (a < b) parent[b] = a; else parent[a] = b; }
+	}
+	if (group_of_voice) for (uint32_t v = 0; v < f.vo_count; ++v) group_of_voice[v] = find(v);
+	return n;
+}
+
 /* The flat program as one relocatable blob: a header of counts, then the arrays. */
 namespace {
 struct FlatHeader {
 	uint32_t magic, version, srate, vo_count, op_count, nbufs, max_ops, nplan, wave_mask;
 	float amp_scale;
-	uint64_t n_ev_time, n_events, n_opdata, n_code, n_prog_ops, n_vev_off, n_vev_idx;
+	uint64_t n_ev_time, n_events, n_opdata, n_code, n_prog_ops, n_vev_off, n_vev_idx, n_ev_handover;
 };
-const uint32_t FLAT_MAGIC = 0x46554153u /* "SAUF" */, FLAT_VERSION = 1;
+const uint32_t FLAT_MAGIC = 0x46554153u /* "SAUF" */, FLAT_VERSION = 2;
 template <typename T> size_t blob_bytes(const std::vector<T> &v) { return (v.size() * sizeof(T) + 7) & ~(size_t) 7; }
 }
 
@@ -944,7 +1010,8 @@ extern "C" size_t saugen_flatten(const sauabi_Program *prg, uint32_t srate, void
 	Flat f;
 	if (!flatten_program(prg, srate, f)) return 0;
 	const size_t need = sizeof(FlatHeader) + blob_bytes(f.ev_time) + blob_bytes(f.events) + blob_bytes(f.opdata) +
-		blob_bytes(f.code) + blob_bytes(f.prog_ops) + blob_bytes(f.vev_off) + blob_bytes(f.vev_idx);
+		blob_bytes(f.code) + blob_bytes(f.prog_ops) + blob_bytes(f.vev_off) + blob_bytes(f.vev_idx) +
+		blob_bytes(f.ev_handover);
 	if (!blob || cap < need) return need;
 	memset(blob, 0, need);
 	FlatHeader h;
@@ -954,7 +1021,7 @@ extern "C" size_t saugen_flatten(const sauabi_Program *prg, uint32_t srate, void
 	h.wave_mask = f.wave_mask; h.amp_scale = f.amp_scale;
 	h.n_ev_time = f.ev_time.size(); h.n_events = f.events.size(); h.n_opdata = f.opdata.size();
 	h.n_code = f.code.size(); h.n_prog_ops = f.prog_ops.size(); h.n_vev_off = f.vev_off.size();
-	h.n_vev_idx = f.vev_idx.size();
+	h.n_vev_idx = f.vev_idx.size(); h.n_ev_handover = f.ev_handover.size();
 	unsigned char *p = (unsigned char*) blob;
 	memcpy(p, &h, sizeof h); p += sizeof h;
 	auto put = [&p](const void *src, size_t n, size_t padded) { if (n) memcpy(p, src, n); p += padded; };
@@ -965,7 +1032,55 @@ extern "C" size_t saugen_flatten(const sauabi_Program *prg, uint32_t srate, void
 	put(f.prog_ops.data(), f.prog_ops.size() * sizeof(uint32_t), blob_bytes(f.prog_ops));
 	put(f.vev_off.data(), f.vev_off.size() * sizeof(uint32_t), blob_bytes(f.vev_off));
 	put(f.vev_idx.data(), f.vev_idx.size() * sizeof(uint32_t), blob_bytes(f.vev_idx));
+	put(f.ev_handover.data(), f.ev_handover.size() * sizeof(uint32_t), blob_bytes(f.ev_handover));
 	return need;
+}
+
+/* A blob comes from outside the process: every index and count in it is checked against
+ * the arrays it refers to before anything goes to the device (a stale or corrupt blob
+ * must not become out-of-bounds accesses in render_kernel). */
+static const char *validate_flat(const Flat &f) {
+	const size_t nev = f.events.size();
+	if (f.vo_count > 65535u || !f.nbufs || f.nbufs > 250u || !f.max_ops || f.nplan > 64u) return "header counts";
+	if (f.vev_off.size() != (size_t) f.vo_count + 1 || f.vev_off[0] != 0) return "voice event index";
+	for (uint32_t v = 0; v < f.vo_count; ++v)
+		if (f.vev_off[v] > f.vev_off[v + 1]) return "voice event index";
+	if (f.vev_off[f.vo_count] != f.vev_idx.size()) return "voice event index";
+	for (uint32_t i : f.vev_idx) if (i >= nev) return "voice event list";
+	for (size_t i = 1; i < f.ev_time.size(); ++i) if (f.ev_time[i] < f.ev_time[i - 1]) return "event times";
+	for (uint32_t h : f.ev_handover) if (h > f.vo_count) return "hand-over voice";
+	for (const OpDataRec &r : f.opdata) {
+		if (r.id >= f.op_count || r.type > SAUABI_POPT_raseg) return "op-data record";
+		if (r.type == SAUABI_POPT_wave && (r.params & SAUABI_POPP_MODE) && r.mode_main >= NUM_WAVES) return "wave id";
+		for (int l = 0; l < LINE_COUNT; ++l) if (r.line[l].present && r.line[l].type >= SAUABI_LINE_NAMED) return "line type";
+	}
+	for (uint32_t id : f.prog_ops) if (id >= f.op_count) return "program operator list";
+	for (const EventRec &e : f.events) {
+		if ((size_t) e.opdata_off + e.opdata_count > f.opdata.size()) return "event op-data range";
+		if ((size_t) e.code_off + e.code_len > f.code.size()) return "event code range";
+		if ((size_t) e.ops_off + e.ops_cnt > f.prog_ops.size() || e.ops_cnt > f.max_ops) return "event operator range";
+		if (e.vo_id != SAUABI_PVO_NO_ID && e.vo_id >= f.vo_count) return "event voice";
+		if (e.code_len && (e.carr_slot >= e.ops_cnt && e.ops_cnt)) return "carrier slot";
+		uint32_t depth = 0;
+		for (uint32_t k = 0; k < e.code_len; ++k) {
+			const Instr &in = f.code[e.code_off + k];
+			if (in.opcode < I_ENTER || in.opcode > I_WLEAF) return "opcode";
+			const uint8_t m = Compiler::buf_fields(in.opcode, in.d, in.flags);
+			const uint8_t fld[5] = {in.a, in.b, in.c, in.d, in.e};
+			for (int q = 0; q < 5; ++q)
+				if ((m >> q & 1) && fld[q] != NO_BUF && fld[q] >= f.nbufs) return "work buffer id";
+			if ((m & 32) && in.b != NO_BUF && (uint32_t) in.b + 1 >= f.nbufs) return "work buffer id";
+			if (in.opcode == I_LINE && in.c >= LINE_COUNT) return "line index";
+			const bool uses_op = in.opcode != I_ZERO && in.opcode != I_RANGE && in.opcode != I_MIX && in.opcode != I_END;
+			if (uses_op && in.op >= (e.ops_cnt ? e.ops_cnt : 1u)) return "operator slot";
+			if (in.opcode == I_ENTER || in.opcode == I_WHEAD) {
+				if (++depth >= (uint32_t) MAX_NEST - 1) return "nesting depth";
+				if (in.aux > e.code_len) return "enter target";
+			}
+			if ((in.opcode == I_LEAVE || in.opcode == I_WTAIL) && depth) --depth;
+		}
+	}
+	return nullptr;
 }
 
 extern "C" saugen_Generator *saugen_create_flat(const void *blob, size_t size,
@@ -992,8 +1107,14 @@ extern "C" saugen_Generator *saugen_create_flat(const void *blob, size_t size,
 	};
 	get(f.ev_time, h.n_ev_time); get(f.events, h.n_events); get(f.opdata, h.n_opdata); get(f.code, h.n_code);
 	get(f.prog_ops, h.n_prog_ops); get(f.vev_off, h.n_vev_off); get(f.vev_idx, h.n_vev_idx);
-	if (!ok || f.vev_off.size() != (size_t) f.vo_count + 1 || f.ev_time.size() != f.events.size()) {
+	get(f.ev_handover, h.n_ev_handover);
+	if (!ok || f.vev_off.size() != (size_t) f.vo_count + 1 || f.ev_time.size() != f.events.size() ||
+			f.ev_handover.size() != f.events.size()) {
 		g_err = "saugen_create_flat: truncated or inconsistent blob";
+		return nullptr;
+	}
+	if (const char *bad = validate_flat(f)) {
+		g_err = std::string("saugen_create_flat: blob fails validation (") + bad + ")";
 		return nullptr;
 	}
 	return create_from_flat(f, tables, opt);
@@ -1013,12 +1134,34 @@ extern "C" void saugen_destroy(saugen_Generator *o) {
  * call into inter-event segments; ev_end says which events are due by then. */
 static void plan_call(saugen_Generator *o, uint32_t buf_len, std::vector<SegDesc> &segs) {
 	segs.clear();
+	o->group_first.clear();
 	uint64_t t = o->cur_time;
 	const uint64_t t_end = t + buf_len;
 	size_t ev = o->next_event;
 	const size_t nev = o->ev_time.size();
+	/* events due at time t, in order.  A hand-over event (Flat::ev_handover) starts a new
+	 * render launch: the events due before it at the same instant get a zero-length
+	 * segment of their own in the launch before, so that every earlier touch of the
+	 * operator has gone through a kernel boundary when its new voice picks it up. */
+	auto take_due = [&](uint64_t now) {
+		bool cut = false;
+		size_t from = ev;
+		while (ev < nev && o->ev_time[ev] <= now) {
+			if (o->ev_handover[ev]) {
+				if (ev > from) {
+					SegDesc z; z.start = (uint32_t) (now - o->cur_time); z.len = 0; z.ev_end = (uint32_t) ev;
+					if (cut && !segs.empty()) o->group_first.push_back((uint32_t) segs.size());
+					segs.push_back(z);
+					from = ev;
+				}
+				cut = true;
+			}
+			++ev;
+		}
+		if (cut && !segs.empty()) o->group_first.push_back((uint32_t) segs.size());
+	};
 	while (t < t_end) {
-		while (ev < nev && o->ev_time[ev] <= t) ++ev;
+		take_due(t);
 		uint64_t stop = t_end;
 		if (ev < nev && o->ev_time[ev] < stop) stop = o->ev_time[ev];
 		SegDesc s;
@@ -1029,7 +1172,7 @@ static void plan_call(saugen_Generator *o, uint32_t buf_len, std::vector<SegDesc
 		t = stop;
 	}
 	if (buf_len == 0) {                  /* events due now are still handled */
-		while (ev < nev && o->ev_time[ev] <= t) ++ev;
+		take_due(t);
 		SegDesc s; s.start = 0; s.len = 0; s.ev_end = (uint32_t) ev;
 		segs.push_back(s);
 	}
@@ -1064,11 +1207,11 @@ static void plan_units(const std::vector<SegDesc> &segs, std::vector<UnitDesc> &
  * wave) when the launch uses at most two waves, else the float tables (8 KiB
  * per wave in use). */
 static const uint32_t CTAB_FLAG = 0x80000000u;
-static const size_t SMEM_CAP = 227 * 1024;
 struct Shape { uint32_t warps; uint32_t mask; };
 static Shape pick_shape(uint32_t ntasks, uint32_t wave_mask, uint32_t nbufs, uint32_t max_ops,
 		uint32_t nplan, bool have_coefs) {
-	const uint32_t sms = 148;
+	const uint32_t sms = (uint32_t) device_sm_count();
+	const size_t SMEM_CAP = device_smem_optin();
 	int nw = 0;
 	for (uint32_t w = 0; w < NUM_WAVES; ++w) if (wave_mask & (1u << w)) ++nw;
 	static const char *env = getenv("SAUGEN_CTAB");       /* developer knob: 0 = off */
@@ -1084,6 +1227,8 @@ static Shape pick_shape(uint32_t ntasks, uint32_t wave_mask, uint32_t nbufs, uin
 		if (render_smem_bytes(sh.mask, nbufs, max_ops, nplan, sh.warps) <= SMEM_CAP && (pass == 1 || fit >= 8))
 			return sh;
 	}
+	/* not even one warp of this voice program fits the SM's shared memory */
+	if (render_smem_bytes(sh.mask, nbufs, max_ops, nplan, sh.warps) > SMEM_CAP) sh.warps = 0;
 	return sh;
 }
 
@@ -1097,6 +1242,29 @@ static cudaError_t read_back(saugen_Generator *o, uint32_t nseg, size_t host_pcm
 	if (e == cudaSuccess && host_pcm_bytes)
 		e = cudaMemcpyAsync(o->h_pcm, o->d_pcm, host_pcm_bytes, cudaMemcpyDeviceToHost, st);
 	return e;
+}
+
+/* Room for n inter-event segments of one call (rare: > 64 events inside a call): new,
+ * larger pieces; the old ones stay with the generator until destroy. */
+static bool ensure_seg_cap(saugen_Generator *o, size_t n) {
+	if (n <= o->seg_cap) return true;
+	uint32_t cap = o->seg_cap;
+	while (cap < n) cap *= 2;
+	size_t nl = o->nlv ? o->nlv : 1;
+	cudaStreamSynchronize(o->stream);
+	o->d_vlen = (VoiceSeg*) o->take(false, (size_t) cap * nl * sizeof(VoiceSeg));
+	o->d_status = (uint32_t*) o->take(false, (1 + cap) * sizeof(uint32_t));
+	o->d_segs = (SegDesc*) o->take(false, cap * sizeof(SegDesc));
+	o->h_status = (uint32_t*) o->take(true, (1 + cap) * sizeof(uint32_t));
+	o->h_segs = (SegDesc*) o->take(true, cap * sizeof(SegDesc));
+	if (!o->d_vlen || !o->d_status || !o->d_segs || !o->h_status || !o->h_segs) {
+		set_err("saugen_run: segment table growth", cudaGetLastError());
+		return false;
+	}
+	o->seg_cap = cap;
+	o->compact = false;
+	o->h_desc.vlen = o->d_vlen; o->h_desc.status = o->d_status; o->h_desc.vlen_cap = cap;
+	return cudaMemcpy(o->d_desc, &o->h_desc, sizeof(GenDesc), cudaMemcpyHostToDevice) == cudaSuccess;
 }
 
 /* host_pcm_bytes: PCM bytes to bring to the pinned staging buffer (0 = none) */
@@ -1113,27 +1281,7 @@ static int run_common(saugen_Generator *o, size_t buf_len, int stereo, uint32_t 
 	}
 	std::vector<SegDesc> &segs = o->segs_tmp;
 	plan_call(o, (uint32_t) buf_len, segs);
-	if (segs.size() > o->seg_cap) {
-		/* grow the per-segment arrays (rare: > 64 events inside one call) */
-		uint32_t cap = o->seg_cap;
-		while (cap < segs.size()) cap *= 2;
-		size_t nl = o->nlv ? o->nlv : 1;
-		cudaStreamSynchronize(o->stream);
-		/* new, larger pieces; the old ones stay with the generator until destroy */
-		o->d_vlen = (VoiceSeg*) o->take(false, (size_t) cap * nl * sizeof(VoiceSeg));
-		o->d_status = (uint32_t*) o->take(false, (1 + cap) * sizeof(uint32_t));
-		o->d_segs = (SegDesc*) o->take(false, cap * sizeof(SegDesc));
-		o->h_status = (uint32_t*) o->take(true, (1 + cap) * sizeof(uint32_t));
-		o->h_segs = (SegDesc*) o->take(true, cap * sizeof(SegDesc));
-		if (!o->d_vlen || !o->d_status || !o->d_segs || !o->h_status || !o->h_segs) {
-			set_err("saugen_run: segment table growth", cudaGetLastError());
-			return -1;
-		}
-		o->seg_cap = cap;
-		o->compact = false;
-		o->h_desc.vlen = o->d_vlen; o->h_desc.status = o->d_status; o->h_desc.vlen_cap = cap;
-		cudaMemcpy(o->d_desc, &o->h_desc, sizeof(GenDesc), cudaMemcpyHostToDevice);
-	}
+	if (!ensure_seg_cap(o, segs.size())) { if (out_len) *out_len = 0; return -1; }
 	const uint32_t nseg = (uint32_t) segs.size();
 	memcpy(o->h_segs, segs.data(), nseg * sizeof(SegDesc));
 	/* Launch shape and scheduling.  sched: 0 = auto, 1 = one warp per voice, 2 =
@@ -1142,12 +1290,18 @@ static int run_common(saugen_Generator *o, size_t buf_len, int stereo, uint32_t 
 	 * filled wave of warps (between 1 and 4 waves), else one warp per voice. */
 	const Shape shape = pick_shape(o->nlv, o->wave_mask, o->nbufs, o->max_ops, o->nplan, o->d_coefs != nullptr);
 	const uint32_t warps = shape.warps;
+	if (!warps) {
+		g_err = "saugen_run: a voice program of this script needs more shared memory than one SM has";
+		fprintf(stderr, "saugen_b200: error: %s\n", g_err.c_str());
+		if (out_len) *out_len = 0;
+		return -1;
+	}
 	uint32_t ticketed_ctas = 0, sched_mode = 0;
 	{
 		const size_t smem = render_smem_bytes(shape.mask, o->nbufs, o->max_ops, o->nplan, warps);
 		int per_sm = render_ctas_per_sm(smem, warps);
 		if (per_sm < 1) per_sm = 1;
-		const uint32_t resident_ctas = 148u * (uint32_t) per_sm;
+		const uint32_t resident_ctas = (uint32_t) device_sm_count() * (uint32_t) per_sm;
 		const uint32_t need = (o->nlv + warps - 1) / warps;
 		uint32_t sched = o->sched;
 		if (sched == 0)
@@ -1203,10 +1357,18 @@ static int run_common(saugen_Generator *o, size_t buf_len, int stereo, uint32_t 
 	}
 	const uint32_t nunits = (uint32_t) o->units_tmp.size();
 	memcpy(o->h_units, o->units_tmp.data(), nunits * sizeof(UnitDesc));
+	/* render launches of this call: one, or one per hand-over cut (plan_call) */
+	std::vector<uint32_t> gunit;              /* first unit of every launch, then nunits */
+	gunit.push_back(0);
+	for (uint32_t gs : o->group_first)
+		for (uint32_t u = gunit.back(); u < nunits; ++u)
+			if (o->units_tmp[u].seg >= gs) { if (u > gunit.back()) gunit.push_back(u); break; }
+	gunit.push_back(nunits);
+	const size_t ngroups = gunit.size() - 1;
 	CallDesc &cd = *o->h_call;
 	cd.gen = o->d_desc; cd.call_len = (uint32_t) buf_len; cd.nseg = nseg; cd.seg_off = 0;
 	cd.task_base = 0; cd.stereo = (stereo ? 1u : 0u) | (o->big_endian ? 2u : 0u);
-	cd.unit_off = 0; cd.nunits = nunits; cd._pad = 0;
+	cd.unit_off = 0; cd.nunits = gunit[1]; cd.more_launches = ngroups > 1 ? 1u : 0u;
 	cudaError_t e;
 	if (o->compact) {
 		/* one copy in ([call][segs][units]), one memset ([vlen][progress][status]) */
@@ -1223,10 +1385,26 @@ static int run_common(saugen_Generator *o, size_t buf_len, int stereo, uint32_t 
 	}
 	o->timed_call = o->timing;
 	if (e == cudaSuccess && o->timed_call) e = cudaEventRecord(o->ev_t[0], o->stream);
-	if (e == cudaSuccess) {
+	for (size_t gi = 0; gi < ngroups && e == cudaSuccess; ++gi) {
+		if (gi > 0) {
+			/* the next launch's unit range (pageable source: staged before the call returns) */
+			CallDesc next = cd;
+			next.unit_off = gunit[gi]; next.nunits = gunit[gi + 1] - gunit[gi];
+			next.more_launches = gi + 1 < ngroups ? 1u : 0u;
+			e = cudaMemcpyAsync(o->d_call, &next, sizeof(CallDesc), cudaMemcpyHostToDevice, o->stream);
+			if (e == cudaSuccess && ticketed_ctas)
+				e = cudaMemsetAsync(o->d_progress, 0, ((size_t) o->nlv + 1) * sizeof(uint32_t), o->stream);
+			if (e != cudaSuccess) break;
+		}
 		e = launch_render(o->d_call, 1, o->d_segs, o->d_units, o->nlv, o->d_tables, o->d_coefs,
 				shape.mask, o->nbufs, o->max_ops, o->nplan, warps, ticketed_ctas, sched_mode, o->stream);
 		o->counters[0]++;
+	}
+	if (e == cudaSuccess && ngroups > 1) {
+		/* the mix kernel reads the call's whole unit / segment tables */
+		CallDesc all = cd;
+		all.nunits = nunits; all.more_launches = 0;
+		e = cudaMemcpyAsync(o->d_call, &all, sizeof(CallDesc), cudaMemcpyHostToDevice, o->stream);
 	}
 	if (e == cudaSuccess && o->timed_call) e = cudaEventRecord(o->ev_t[1], o->stream);
 	if (e == cudaSuccess) {
@@ -1382,6 +1560,9 @@ extern "C" int saugen_batch_begin(saugen_Batch *b, saugen_Generator *const *gens
 	cudaStream_t st = b->stream;
 	saugen_Generator *g0 = nullptr;
 	uint32_t ntasks = 0, wave_mask = 0, nbufs = 1, max_ops = 1, nplan = 0;
+	std::vector<std::vector<CallDesc>> later;    /* render launches after the first (hand-over cuts; rare) */
+	/* every generator is checked BEFORE any timeline moves: a refused batch leaves all
+	 * of them where they were */
 	for (size_t i = 0; i < n; ++i) {
 		saugen_Generator *o = gens[i];
 		if (!o || o->ended) continue;
@@ -1390,18 +1571,40 @@ extern "C" int saugen_batch_begin(saugen_Batch *b, saugen_Generator *const *gens
 			g_err = "saugen_run_many: generators must share device and tables and fit buf_len";
 			return -1;
 		}
+	}
+	for (size_t i = 0; i < n; ++i) {
+		saugen_Generator *o = gens[i];
+		if (o && o->ended && b->bufs[i]) memset(b->bufs[i], 0, b->bytes);   /* as saugen_run does */
+		if (!o || o->ended) continue;
 		plan_call(o, (uint32_t) buf_len, o->segs_tmp);
-		if (o->segs_tmp.size() > o->seg_cap) {
-			g_err = "saugen_run_many: too many events inside one call (use saugen_run)";
-			return -1;
-		}
+		if (!ensure_seg_cap(o, o->segs_tmp.size())) return -1;
 		CallDesc cd;
 		cd.gen = o->d_desc; cd.call_len = (uint32_t) buf_len; cd.nseg = (uint32_t) o->segs_tmp.size();
 		cd.seg_off = (uint32_t) b->segs.size(); cd.task_base = ntasks;
-		cd.stereo = (stereo ? 1u : 0u) | (o->big_endian ? 2u : 0u); cd._pad = 0;
+		cd.stereo = (stereo ? 1u : 0u) | (o->big_endian ? 2u : 0u); cd.more_launches = 0;
 		plan_units(o->segs_tmp, o->units_tmp, 1u << 20);
 		cd.unit_off = (uint32_t) b->units.size(); cd.nunits = (uint32_t) o->units_tmp.size();
 		b->units.insert(b->units.end(), o->units_tmp.begin(), o->units_tmp.end());
+		if (!o->group_first.empty()) {
+			/* hand-over cuts (plan_call): this call's later launches go into later rounds */
+			uint32_t first = 0, round = 0;
+			const uint32_t nu = cd.nunits;
+			std::vector<uint32_t> cutu;
+			for (uint32_t gs : o->group_first)
+				for (uint32_t u = first; u < nu; ++u)
+					if (o->units_tmp[u].seg >= gs) { if (u > first) { cutu.push_back(u); first = u; } break; }
+			cutu.push_back(nu);
+			first = cutu[0];
+			for (size_t k = 1; k < cutu.size(); ++k) {
+				CallDesc nx = cd;
+				nx.unit_off = cd.unit_off + first; nx.nunits = cutu[k] - first;
+				nx.more_launches = k + 1 < cutu.size() ? 1u : 0u;
+				if (later.size() < ++round) later.emplace_back();
+				later[round - 1].push_back(nx);
+				first = cutu[k];
+			}
+			if (cutu.size() > 1) { cd.nunits = cutu[0]; cd.more_launches = 1; }
+		}
 		if (o->compact) cudaMemsetAsync(o->d_vlen, 0, o->zero_bytes, st);
 		else cudaMemsetAsync(o->d_vlen, 0, (size_t) cd.nseg * (o->nlv ? o->nlv : 1) * sizeof(VoiceSeg), st);
 		b->segs.insert(b->segs.end(), o->segs_tmp.begin(), o->segs_tmp.end());
@@ -1423,19 +1626,49 @@ extern "C" int saugen_batch_begin(saugen_Batch *b, saugen_Generator *const *gens
 		*cap = need * 2;
 		e = cudaMalloc(p, *cap * elem);
 	};
-	grow((void**) &b->d_calls, &b->d_calls_cap, b->calls.size(), sizeof(CallDesc));
+	size_t ncalls_all = b->calls.size();
+	for (auto &r : later) {
+		uint32_t tb = 0;
+		for (CallDesc &c : r) {                     /* tasks of a round: its own calls' voices */
+			c.task_base = tb;
+			for (size_t k = 0; k < b->calls.size(); ++k)
+				if (b->calls[k].gen == c.gen) { tb += gens[b->call_of[k]]->nlv; break; }
+		}
+		ncalls_all += r.size();
+	}
+	grow((void**) &b->d_calls, &b->d_calls_cap, ncalls_all, sizeof(CallDesc));
 	grow((void**) &b->d_segs, &b->d_segs_cap, b->segs.size(), sizeof(SegDesc));
 	grow((void**) &b->d_units, &b->d_units_cap, b->units.size(), sizeof(UnitDesc));
 	if (e == cudaSuccess) e = cudaMemcpyAsync(b->d_units, b->units.data(), b->units.size() * sizeof(UnitDesc), cudaMemcpyHostToDevice, st);
 	if (e == cudaSuccess) e = cudaMemcpyAsync(b->d_calls, b->calls.data(), b->calls.size() * sizeof(CallDesc), cudaMemcpyHostToDevice, st);
+	{
+		size_t at = b->calls.size();
+		for (auto &r : later) {
+			if (e == cudaSuccess)       /* pageable source: staged before the call returns */
+				e = cudaMemcpyAsync(b->d_calls + at, r.data(), r.size() * sizeof(CallDesc), cudaMemcpyHostToDevice, st);
+			at += r.size();
+		}
+	}
 	if (e == cudaSuccess) e = cudaMemcpyAsync(b->d_segs, b->segs.data(), b->segs.size() * sizeof(SegDesc), cudaMemcpyHostToDevice, st);
 	g0->timed_call = g0->timing;       /* kernel times of the batch accumulate on the first generator */
 	if (e == cudaSuccess && g0->timed_call) e = cudaEventRecord(g0->ev_t[0], st);
 	if (e == cudaSuccess) {
 		const Shape shape = pick_shape(ntasks, wave_mask, nbufs, max_ops, nplan, g0->d_coefs != nullptr);
-		e = launch_render(b->d_calls, (uint32_t) b->calls.size(), b->d_segs, b->d_units, ntasks, g0->d_tables,
+		if (!shape.warps) e = cudaErrorInvalidConfiguration;
+		else e = launch_render(b->d_calls, (uint32_t) b->calls.size(), b->d_segs, b->d_units, ntasks, g0->d_tables,
 				g0->d_coefs, shape.mask, nbufs, max_ops, nplan, shape.warps, 0, 0, st);
 		g0->counters[0]++;
+		size_t at = b->calls.size();
+		for (auto &r : later) {
+			uint32_t nt = 0;
+			for (size_t k = 0; k < b->calls.size(); ++k)
+				for (const CallDesc &c : r) if (b->calls[k].gen == c.gen) nt += gens[b->call_of[k]]->nlv;
+			if (e == cudaSuccess && shape.warps)
+				e = launch_render(b->d_calls + at, (uint32_t) r.size(), b->d_segs, b->d_units, nt, g0->d_tables,
+						g0->d_coefs, shape.mask, nbufs, max_ops, nplan, shape.warps, 0, 0, st);
+			g0->counters[0]++;
+			at += r.size();
+		}
 	}
 	if (e == cudaSuccess && g0->timed_call) e = cudaEventRecord(g0->ev_t[1], st);
 	if (e == cudaSuccess) {
@@ -1621,7 +1854,7 @@ extern "C" int saugen_kernel_ms(saugen_Generator *o, double out[2]) {
  * which a fast-path primitive differs from the statement it replaces, <0 on error. */
 extern "C" long long saugen_selftest(int device, const saugen_WaveTables *tables) {
 	if (cudaSetDevice(device) != cudaSuccess) { set_err("saugen_selftest", cudaGetLastError()); return -1; }
-	if (!tables) tables = saugen::builtin_wave_tables();
+	if (!tables) { g_err = "saugen_selftest: wave tables required"; return -1; }
 	float *d_tab = get_device_tables(device, tables);
 	unsigned long long *d_bad = nullptr, h_bad = 0;
 	if (!d_tab || cudaMalloc(&d_bad, sizeof h_bad) != cudaSuccess) { set_err("saugen_selftest", cudaGetLastError()); return -1; }
@@ -1639,7 +1872,29 @@ extern "C" int saugen_device_count(void) {
 	if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
 	return n;
 }
-extern "C" const saugen_WaveTables *saugen_builtin_wave_tables(void) { return saugen::builtin_wave_tables(); }
+
+/* The table file tools/make_wave_tables.py writes (libsau's host-built tables, verbatim):
+ * "SAUT", version, 12, 2048, 12 x 2048 floats, amp_scale[12], amp_dc[12], phase_adj[12]. */
+extern "C" saugen_WaveTables *saugen_wave_tables_load(const char *path) {
+	FILE *f = path ? fopen(path, "rb") : nullptr;
+	if (!f) { g_err = std::string("saugen_wave_tables_load: cannot open ") + (path ? path : "(null)"); return nullptr; }
+	uint32_t hdr[4] = {0, 0, 0, 0};
+	const size_t nt = (size_t) NUM_WAVES * WAVE_LEN;
+	unsigned char *blk = (unsigned char*) malloc(sizeof(saugen_WaveTables) + nt * sizeof(float));
+	saugen_WaveTables *t = (saugen_WaveTables*) blk;
+	float *tab = blk ? (float*) (blk + sizeof(saugen_WaveTables)) : nullptr;
+	bool ok = blk && fread(hdr, sizeof hdr, 1, f) == 1 && hdr[0] == 0x54554153u /* "SAUT" */ && hdr[1] == 1 &&
+		hdr[2] == (uint32_t) NUM_WAVES && hdr[3] == (uint32_t) WAVE_LEN &&
+		fread(tab, sizeof(float), nt, f) == nt &&
+		fread(t->amp_scale, sizeof(float), NUM_WAVES, f) == (size_t) NUM_WAVES &&
+		fread(t->amp_dc, sizeof(float), NUM_WAVES, f) == (size_t) NUM_WAVES &&
+		fread(t->phase_adj, sizeof(int32_t), NUM_WAVES, f) == (size_t) NUM_WAVES;
+	fclose(f);
+	if (!ok) { free(blk); g_err = std::string("saugen_wave_tables_load: not a wave table file: ") + path; return nullptr; }
+	for (int w = 0; w < NUM_WAVES; ++w) t->pilut[w] = tab + (size_t) w * WAVE_LEN;
+	return t;
+}
+extern "C" void saugen_wave_tables_free(saugen_WaveTables *t) { free(t); }
 
 extern "C" size_t saugen_abi_layout(uint32_t *out, size_t cap) {
 	const uint32_t v[] = {

@@ -107,7 +107,11 @@ def lib():
         L.saugen_amp_scale.argtypes = [C.c_void_p]
         L.saugen_last_error.restype = C.c_char_p
         L.saugen_device_count.restype = C.c_int
-        L.saugen_builtin_wave_tables.restype = C.POINTER(WaveTables)
+        L.saugen_wave_tables_load.restype = C.POINTER(WaveTables)
+        L.saugen_wave_tables_load.argtypes = [C.c_char_p]
+        L.saugen_wave_tables_free.argtypes = [C.c_void_p]
+        L.saugen_voice_groups.restype = C.c_int
+        L.saugen_voice_groups.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
         L.saugen_abi_layout.restype = C.c_size_t
         L.saugen_abi_layout.argtypes = [C.POINTER(C.c_uint32), C.c_size_t]
         _lib = L
@@ -124,15 +128,34 @@ def device_count():
 
 def selftest(device=0, tables=None):
     """Mismatches of the fast-path arithmetic primitives vs their plain forms (0 = exact)."""
-    r = lib().saugen_selftest(device, C.addressof(tables) if tables is not None else None)
+    if tables is None:
+        tables = default_tables()
+    r = lib().saugen_selftest(device, C.addressof(tables))
     if r < 0:
         raise RuntimeError("saugen_selftest failed: " + last_error())
     return r
 
 
-def builtin_tables():
-    """(piluts[12,2048] float32, [(amp_scale, amp_dc, phase_adj)]*12) built by wavetab.cpp."""
-    t = lib().saugen_builtin_wave_tables().contents
+TABLES_PATH = os.path.join(_HERE, "data", "sau_wave_tables.bin")
+_default_tables = None
+
+
+def default_tables():
+    """libsau's host-built wave tables (sau/wave.c:105-221), read verbatim from the data file
+    tools/make_wave_tables.py wrote: what a caller without libsau in its process passes to
+    saugen_create (the drop-in passes libsau's live arrays instead, csrc/dropin.c)."""
+    global _default_tables
+    if _default_tables is None:
+        p = lib().saugen_wave_tables_load(TABLES_PATH.encode())
+        if not p:
+            raise RuntimeError("wave tables: " + last_error())
+        _default_tables = p.contents        # lives for the process
+    return _default_tables
+
+
+def tables_arrays(t=None):
+    """(piluts[12,2048] float32, [(amp_scale, amp_dc, phase_adj)]*12) of a WaveTables."""
+    t = t if t is not None else default_tables()
     tabs = np.zeros((12, 2048), np.float32)
     for w in range(12):
         tabs[w] = np.ctypeslib.as_array(C.cast(t.pilut[w], C.POINTER(C.c_float)), shape=(2048,))
@@ -151,13 +174,15 @@ class Generator:
     def __init__(self, prg, srate=96000, tables=None, device=0, stream=None,
                  voice_range=None, max_call_len=0, sched=0, big_endian=False):
         self._prg = prg            # borrowed for the generator's life (generator.c:191)
+        if tables is None:
+            tables = default_tables()
         self._tables = tables
         flat = prg if isinstance(prg, (bytes, bytearray)) else None   # a saugen_flatten blob
         opt = Options(device=device, stream=stream or 0,
                       voice_begin=voice_range[0] if voice_range else 0,
                       voice_end=voice_range[1] if voice_range else 0,
                       max_call_len=max_call_len, sched=sched, pcm_big_endian=int(big_endian))
-        tptr = C.addressof(tables) if tables is not None else None
+        tptr = C.addressof(tables)
         if flat is not None:
             buf = (C.c_char * len(flat)).from_buffer_copy(flat)
             self.ptr = lib().saugen_create_flat(buf, len(flat), tptr, C.byref(opt))
@@ -248,6 +273,17 @@ class Generator:
             self.close()
         except Exception:
             pass
+
+
+def voice_groups(prg, srate=96000):
+    """saugen_voice_groups: (hand-over events, [group id per voice]); needs no GPU."""
+    from . import program as P
+    nvo = P.Program.from_address(prg.ptr).vo_count
+    out = (C.c_uint32 * max(nvo, 1))()
+    r = lib().saugen_voice_groups(prg.ptr, srate, out)
+    if r < 0:
+        raise RuntimeError("saugen_voice_groups failed: " + last_error())
+    return r, list(out[:nvo])
 
 
 def flatten(prg, srate=96000):

@@ -145,10 +145,13 @@ class ProgramBuilder:
     # -- operator descriptions (nested dicts) --
     @staticmethod
     def wave(wave="sin", freq=None, amp=None, time_ms=None, pan=None, phase=0, mods=None,
-             amp2=None, freq2=None, pm_a=None):
+             amp2=None, freq2=None, pm_a=None, raw_mods=None):
+        """raw_mods: {use: [operator ids]} appended to the lists as given -- ids of operators
+        emitted elsewhere (ids count up in visiting order, parent before its modulators); the
+        way to state graphs the script language cannot, e.g. a circular reference."""
         return {"type": POPT_WAVE, "mode": WAVES.index(wave), "freq": freq, "amp": amp,
                 "time_ms": time_ms, "pan": pan, "phase": phase, "mods": mods or {},
-                "amp2": amp2, "freq2": freq2, "pm_a": pm_a}
+                "amp2": amp2, "freq2": freq2, "pm_a": pm_a, "raw_mods": raw_mods or {}}
 
     def _line(self, spec, default_time_ms, sub=False):
         """sauLine as the parser leaves it for a parameter of a NEW operator:
@@ -200,6 +203,8 @@ class ProgramBuilder:
             for child in lst:
                 ids.append(self._emit(child, use_name, level + 1, out, dur_ms))
             mod_ids[use_name] = ids
+        for use_name, ids in node.get("raw_mods", {}).items():
+            mod_ids[use_name] = mod_ids.get(use_name, []) + list(ids)
         implicit = node["time_ms"] is None and level > 0
         t_ms = node["time_ms"] if node["time_ms"] is not None else (
             self.default_time_ms if level > 0 else dur_ms)

@@ -81,7 +81,29 @@ def feature_scripts():
     s["high_freq"] = "Wsqr f30000 t0.1"
     s["deep"] = "Wsin f200 t0.3 p[Wsin r2 p[Wsin r2 p[Wsin r2 p[Wsin r0.5 a0.3]]]]"
     s["silence_mid"] = "Wsin f200 t0.1 /0.6 Wsin f300 t0.1"
+    # an operator handed over between voices: its voice slot is recycled by another carrier, a later
+    # `@label` update then gives the same op id a NEW voice (parseconv); both events in one call
+    s["handover"] = "'a Wsin f440 t0.01\n/0.02 Wsin f220 t0.5\n/0.01 @a t0.5 f880"
+    s["handover_pm"] = ("'a Wsin f300 t0.02 p[Wtri f70 a0.6]\n/0.03 Wsaw f110 t0.3 a0.5\n"
+                        "/0.001 @a t0.3 f450[g200 lexp t0.2]\n/0.1 @a a0.3 t0.1")
+    s["handover_same_time"] = "'a Wsin f440 t0.01\n/0.02 Wsin f220 t0.5 @a t0.4 f660"
+    s["handover_twice"] = ("'a Wsin f440 t0.01 'b Wtri f330 t0.01\n/0.02 Wsin f220 t0.3 Wsin f275 t0.3\n"
+                           "/0.01 @b t0.3 f700\n/0.005 @a t0.3 f880\n/0.2 @b f350 t0.1")
     return s
+
+
+def circular_program():
+    """A modulator graph with a circular reference (carrier <- tri <- sin <- carrier), which the
+    script language cannot state but the generator guards against (ON_VISITED, sau/generator.c:
+    685-690: the revisited operator renders zeros); built directly as a sauProgram."""
+    from saugns_b200 import program as P
+    pb = P.ProgramBuilder(ampmult=1.0)
+    m2 = P.ProgramBuilder.wave("sin", freq=50.0, amp=0.4, raw_mods={"pmod": [0]})   # back to the carrier
+    m1 = P.ProgramBuilder.wave("tri", freq=300.0, amp=0.7, mods={"pmod": [m2]})
+    pb.add_voice(P.ProgramBuilder.wave("sin", freq=200.0, time_ms=300, pan=0.2, mods={"pmod": [m1]}))
+    # a second voice whose only modulator is itself
+    pb.add_voice(P.ProgramBuilder.wave("saw", freq=120.0, time_ms=200, pan=-0.4, raw_mods={"pmod": [3], "fmod": [3]}))
+    return pb.finish()
 
 
 # BASELINE config 2: the reference's examples/misc1-4fm_pm.sau (saugns v0.4.7,

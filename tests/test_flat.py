@@ -49,3 +49,23 @@ def test_render_from_blob_equals_render_from_program(ref, port):
         if got.shape != want.shape or not np.array_equal(got, want):
             bad.append(name)
     assert not bad, bad
+
+
+def test_operator_handover_between_voices_is_found(ref):
+    """parseconv re-homes an operator whose voice slot was recycled; the flattener must see it
+    (the run time cuts the call there, runtime.cpp:plan_call), and voice sharding must keep the
+    linked voices together (saugen_voice_groups)."""
+    import saugns_b200
+    feats = scripts.feature_scripts()
+    n, groups = saugns_b200.voice_groups(ref.Program(feats["handover"]))
+    assert n == 1 and groups == [0, 0]
+    n, groups = saugns_b200.voice_groups(ref.Program(feats["handover_same_time"]))
+    assert n == 1 and groups == [0, 0]
+    n, groups = saugns_b200.voice_groups(ref.Program(feats["handover_twice"]))
+    assert n >= 2 and len(set(groups)) < len(groups)
+    for name in ["voices3", "seq_overlap", "seq_update", "pm_addrem", "seq_bar"]:
+        prg = ref.Program(feats[name])
+        n, groups = saugns_b200.voice_groups(prg)
+        assert n == 0 and groups == list(range(prg.vo_count)), name
+    n, groups = saugns_b200.voice_groups(ref.Program(scripts.synth_c3(64, 1, fm="mix")))
+    assert n == 0 and groups == list(range(64))

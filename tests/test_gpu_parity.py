@@ -125,7 +125,8 @@ def test_state_after_every_call(S, ref, port, tabs, call_len):
     names = ["pm_chain", "fm_both", "self_w_mod", "self_r_pm", "seq_update", "voices3",
              "noise_am", "R_cub_self", "R_cub", "sweep_f_cub", "sweep_a_cub", "regoal", "pan_mod",
              "mod_finite", "self_w_off", "ratio_sweep", "noise_re", "noise_vi", "noise_bv",
-             "wave_change", "pm_addrem", "seq_overlap", "silence_mid"]
+             "wave_change", "pm_addrem", "seq_overlap", "silence_mid",
+             "handover", "handover_pm", "handover_same_time", "handover_twice"]
     feats = scripts.feature_scripts()
     for name in names:
         prg = ref.Program(feats[name])
@@ -144,6 +145,54 @@ def test_state_after_every_call(S, ref, port, tabs, call_len):
             for vo in range(prg.vo_count):
                 assert gr.voice_state(vo)[:3] == gg.voice_state(vo)[:3], (name, ncall, vo)
             ncall += 1
+
+
+def test_circular_modulator_graph(S, ref, port, tabs):
+    """A program whose modulator lists loop back (sau/generator.c:685-690, ON_VISITED: the
+    revisited operator renders zeros) -- built directly, the script language cannot state it."""
+    prg = scripts.circular_program()
+    for call_len in (24576, 1000):
+        gr = ref.RefGenerator(prg, 96000)
+        gg = S.Generator(prg, 96000, tables=tabs, max_call_len=call_len)
+        more, ncall = True, 0
+        while more:
+            more, ba, na = gr.run(call_len)
+            more2, bb, nb = gg.run(call_len)
+            assert (more, na) == (more2, nb), ncall
+            assert np.array_equal(ba, bb), ncall
+            for op in range(prg.op_count):
+                assert port.op_state_tuple(gr.op_state(op)) == port.op_state_tuple(gg.op_state(op)), (ncall, op)
+            ncall += 1
+        assert ncall >= 2
+
+
+@pytest.mark.parametrize("sched", [1, 2, 3])
+def test_operator_handover_all_schedulers(S, ref, tabs, sched):
+    """An operator re-homed to another voice inside ONE call: the call is cut into separate
+    render launches at the hand-over event (runtime.cpp:plan_call), under every scheduler and
+    through the batched entry."""
+    feats = scripts.feature_scripts()
+    for name in ["handover", "handover_pm", "handover_same_time", "handover_twice"]:
+        prg = ref.Program(feats[name])
+        want = ref.render(prg, srate=96000)
+        got = S.render(prg, srate=96000, tables=tabs, sched=sched)
+        assert got.shape == want.shape and np.array_equal(got, want), (name, sched)
+    if sched == 1:
+        prgs = [ref.Program(feats[n]) for n in ["handover", "voices3", "handover_twice", "pm_chain"]]
+        gens = [S.Generator(p, 96000, tables=tabs, max_call_len=24576) for p in prgs]
+        refs = [ref.RefGenerator(p, 96000) for p in prgs]
+        alive = [True] * len(gens)
+        for _ in range(4):
+            more, outs, lens = S.run_many(gens, 24576)
+            for i, (g, r) in enumerate(zip(gens, refs)):
+                if not alive[i]:
+                    continue
+                m, b, n = r.run(24576)
+                assert (bool(more[i]), lens[i]) == (m, n), i
+                assert np.array_equal(outs[i], b), i
+                alive[i] = m
+        for g in gens:
+            g.close()
 
 
 def test_balanced_scheduler_many_voices(S, ref, port, tabs):
