@@ -585,6 +585,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extra", action="store_true", help="skip the C4 / C5 / voice-sharded legs (`extra`)")
     ap.add_argument("--workload", default="c3", choices=["c3", "c4", "c5", "c3-sharded"])
     ap.add_argument("--scripts", type=int, default=1250, help="c5: scripts on this GPU")
     ap.add_argument("--group", type=int, default=128, help="c5: generators in flight per driver thread")

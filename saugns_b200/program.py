@@ -37,8 +37,30 @@ class Time(C.Structure):
 
 
 class RasOpt(C.Structure):
-    _fields_ = [("line", C.c_uint8), ("flags", C.c_uint, 10), ("func", C.c_uint, 6),
-                ("level", C.c_uint, 8), ("alpha", C.c_uint32)]
+    """sauRasOpt (sau/program.h:126-132): uint8 line, then flags:10, func:6, level:8 packed by gcc
+    into the same 32-bit unit (bits 8.., 18.., 24..); stated as the raw word, ctypes would start a
+    new unit for the bit-fields."""
+    _fields_ = [("w0", C.c_uint32), ("alpha", C.c_uint32)]
+
+    @property
+    def line(self):
+        return self.w0 & 0xff
+
+    @property
+    def flags(self):
+        return (self.w0 >> 8) & 0x3ff
+
+    @property
+    def func(self):
+        return (self.w0 >> 18) & 0x3f
+
+    @property
+    def level(self):
+        return (self.w0 >> 24) & 0xff
+
+    @staticmethod
+    def pack(line, flags, func, level):
+        return (line & 0xff) | ((flags & 0x3ff) << 8) | ((func & 0x3f) << 18) | ((level & 0xff) << 24)
 
 
 class Mode(C.Union):
@@ -153,6 +175,44 @@ class ProgramBuilder:
                 "time_ms": time_ms, "pan": pan, "phase": phase, "mods": mods or {},
                 "amp2": amp2, "freq2": freq2, "pm_a": pm_a, "raw_mods": raw_mods or {}}
 
+    # -- the other operator types (sau/parser.c:1157-1172, 1601-1680, 1990-2000) --
+    RAS_FUNCS = "ugbtfa"
+    RAS_OPTS = {"p": 1, "h": 2, "z": 4, "s": 8, "v": 16}
+    RAS_O_LINE_SET, RAS_O_FUNC_SET = 1 << 6, 1 << 7
+
+    @staticmethod
+    def noise(noise="wh", amp=None, time_ms=None, pan=None, mods=None, amp2=None):
+        """`N<noise>`: the parser gives every operator the default 440 Hz frequency line."""
+        return {"type": POPT_NOISE, "mode": NOISES.index(noise), "freq": 440.0, "amp": amp,
+                "time_ms": time_ms, "pan": pan, "phase": 0, "mods": mods or {}, "amp2": amp2,
+                "freq2": None, "pm_a": None, "raw_mods": {}, "seeded": True}
+
+    @staticmethod
+    def raseg(line="lin", mode="", freq=None, amp=None, time_ms=None, pan=None, mods=None,
+              amp2=None, freq2=None, pm_a=None):
+        """`R<line> m<mode>`: mode = one function letter of "ugbtfa" and / or option letters
+        "hpsvz" (parse_op_mode, sau/parser.c:1601-1680)."""
+        flags, func = ProgramBuilder.RAS_O_LINE_SET, 0
+        for ch in mode:
+            if ch in ProgramBuilder.RAS_FUNCS:
+                func = ProgramBuilder.RAS_FUNCS.index(ch)
+                flags |= ProgramBuilder.RAS_O_FUNC_SET
+            else:
+                flags |= ProgramBuilder.RAS_OPTS[ch]
+        return {"type": POPT_RASEG, "mode": RasOpt.pack(LINES.index(line), flags, func, 0), "freq": freq,
+                "amp": amp, "time_ms": time_ms, "pan": pan, "phase": 0, "mods": mods or {},
+                "amp2": amp2, "freq2": freq2, "pm_a": pm_a, "raw_mods": {}, "seeded": True}
+
+    def _next_seed(self):
+        """Seeds of N and R operators in deterministic mode: sau_rand32 = SplitMix32 from state 0,
+        one draw per seeded operator in script order (sau/parser.c:1169-1170, sau/math.h:329-353)."""
+        m = 0xffffffff
+        self._seed_pos = (getattr(self, "_seed_pos", 0) + 0x9e3779b9) & m
+        z = self._seed_pos
+        z = ((z ^ (z >> 16)) * 0x21f0aaad) & m
+        z = ((z ^ (z >> 15)) * 0xf35a2d97) & m
+        return z ^ (z >> 15)
+
     def _line(self, spec, default_time_ms, sub=False):
         """sauLine as the parser leaves it for a parameter of a NEW operator:
         STATE|TIME|TIME_IF_NEW with the operator's default time, TYPE unless it
@@ -193,6 +253,7 @@ class ProgramBuilder:
         self._depth = max(self._depth, level)
         op_id = self._next_op
         self._next_op += 1
+        seed = self._next_seed() if node.get("seeded") else 0
         # ids are allocated in visiting order: parent before its modulators
         # (sauOpAlloc_update runs before the recursion, parseconv.h:350-356)
         mod_ids = {}
@@ -209,7 +270,7 @@ class ProgramBuilder:
         t_ms = node["time_ms"] if node["time_ms"] is not None else (
             self.default_time_ms if level > 0 else dur_ms)
         od = {"id": op_id, "node": node, "use": POP_USES.index(use), "mods": mod_ids,
-              "implicit": implicit, "t_ms": t_ms}
+              "implicit": implicit, "t_ms": t_ms, "seed": seed}
         out.append(od)
         return op_id
 
@@ -237,9 +298,12 @@ class ProgramBuilder:
                     o.time = Time(od["t_ms"], TIMEP_SET)
                 o.use_type = od["use"]
                 o.type = node["type"]
-                o.mode.main = node["mode"]
+                if node["type"] == POPT_RASEG:
+                    o.mode.ras.w0 = node["mode"]
+                else:
+                    o.mode.main = node["mode"]
                 o.phase = node["phase"]
-                o.seed = 0
+                o.seed = od["seed"]
                 dflt = od["t_ms"]
                 o.amp = self._line(node["amp"] if node["amp"] is not None else 1.0, dflt) or None
                 o.freq = self._line(node["freq"], dflt) or None
@@ -249,7 +313,7 @@ class ProgramBuilder:
                     if node[name] is not None:
                         setattr(o, name, self._line(node[name], dflt, sub=True))
                 if node["pm_a"] is not None:
-                    o.pm_a = self._line(node["pm_a"], dflt)
+                    o.pm_a = self._line(node["pm_a"], dflt, sub=True)
                 for use_name, ids in od["mods"].items():
                     setattr(o, use_name + "s", self._idarr(ids))
             self._keep.append(ods)

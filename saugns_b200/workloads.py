@@ -87,6 +87,68 @@ def synth_c4(n_voices=1024, secs=60, seed=2):
     return "\n".join(lines) + "\n"
 
 
+def build_c4(n_voices=1024, secs=60, seed=2):
+    """The program synth_c4() describes, built without a script front end."""
+    from saugns_b200 import program as P
+    B = P.ProgramBuilder
+    rnd = random.Random(seed)
+    pb = B(ampmult=float(f"{0.3 / n_voices ** 0.5:.6f}"))
+    ms = int(round(secs * 1000))
+    for i in range(n_voices):
+        f = float(f"{110.0 * 2 ** rnd.uniform(0, 4):.3f}")
+        c = float(f"{rnd.uniform(-1, 1):.3f}")
+        pa = float(f"{rnd.uniform(0.3, 1.0):.3f}")
+        fm = rnd.uniform(0.5, 8)
+        k = i % 3
+        if k == 0:
+            carr = B.wave("sin", freq=f, time_ms=ms, pm_a=pa, amp=0.5, amp2=1.0, pan=c,
+                          mods={"ramod": [B.wave("sin", freq=float(f"{fm:.3f}"))]})
+        elif k == 1:
+            carr = B.raseg("lin", freq=f, time_ms=ms, pm_a=pa, amp=0.5, amp2=1.0, pan=c,
+                           mods={"ramod": [B.wave("sin", freq=float(f"{fm:.3f}"))]})
+        else:
+            carr = B.wave("tri", freq=f, time_ms=ms, pm_a=pa, amp=0.0, pan=c,
+                          mods={"amod": [B.wave("sin", freq=float(f"{fm * 20:.3f}"), amp=0.8)]})
+        pb.add_voice(carr)
+    return pb.finish()
+
+
+def build_c5_script(index):
+    """The program synth_c5_script(index) describes, built without a script front end."""
+    from saugns_b200 import program as P
+    B = P.ProgramBuilder
+    rnd = random.Random(1000 + index)
+    nv = rnd.randint(4, 16)
+    pb = B(ampmult=float(f"{0.3 / nv ** 0.5:.6f}"))
+    for _ in range(nv):
+        t = rnd.uniform(1, 10)
+        ms = int(round(float(f"{t:.3f}") * 1000))
+        f_raw = 110.0 * 2 ** rnd.uniform(0, 4)
+        f = float(f"{f_raw:.3f}")
+        c = float(f"{rnd.uniform(-1, 1):.3f}")
+        kind = rnd.randrange(4)
+        if kind == 0:
+            w, w2 = rnd.choice(WAVES), rnd.choice(WAVES)
+            r = rnd.choice([0.5, 1, 2, 3])
+            a = float(f"{rnd.uniform(0.1, 1):.3f}")
+            carr = B.wave(w, freq=f, time_ms=ms, pan=c,
+                          mods={"pmod": [B.wave(w2, freq=P.value(r, ratio=True), amp=a)]})
+        elif kind == 1:
+            n = rnd.choice(NOISES)
+            carr = B.noise(n, time_ms=ms, pan=c, amp=float(f"{rnd.uniform(0.1, 0.8):.3f}"))
+        elif kind == 2:
+            mode = rnd.choice("ugbtfa") + rnd.choice(["", "h", "p", "s", "v", "z"])
+            carr = B.raseg(rnd.choice(LINES), mode, freq=f, time_ms=ms, pan=c)
+        else:
+            w = rnd.choice(WAVES)
+            g = float(f"{f_raw * rnd.uniform(0.5, 2):.3f}")
+            ln = rnd.choice(LINES)
+            carr = B.wave(w, freq=P.value(f, goal=g, line=ln), time_ms=ms, pan=c, amp=1.0, amp2=0.0,
+                          mods={"ramod": [B.wave("sin", freq=float(f"{rnd.uniform(0.5, 9):.3f}"))]})
+        pb.add_voice(carr)
+    return pb.finish()
+
+
 def synth_c5_script(index):
     """BASELINE config 5: one of the independent mixed scripts (seed 1000+index)."""
     rnd = random.Random(1000 + index)
