@@ -152,9 +152,32 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------
-# reference CPU arm / cpu_baseline
+# the workloads: script text for the reference's front end, the identical sauProgram for the
+# product arm (saugns_b200.workloads; tests/test_program_builder.py pins the two field by field)
 # ---------------------------------------------------------------------------
-def _ref_worker(conn, text):
+def c3_text(seed=1):
+    from saugns_b200 import workloads
+    return workloads.synth_c3(VOICES, SECS, seed=seed, fm="mix")
+
+
+def c3_program(seed=1):
+    from saugns_b200 import workloads
+    return workloads.build_c3(VOICES, SECS, seed=seed, fm="mix")
+
+
+def c3_config():
+    """Identical in both arms (the driver compares the two lines' `config`)."""
+    return {"workload": WORKLOAD, "voices": VOICES, "frames_per_step": FRAMES, "srate": SRATE,
+            "op_samples_per_step": 3 * VOICES * FRAMES,
+            "l2": "per-step voice rows 403 MB > 126 MB L2 (working set larger than L2)",
+            "parallelism": "one independent 4096-voice script per GPU (per host-core group in the "
+                           "reference arm: the reference is single-threaded, voices split over processes)"}
+
+
+# ---------------------------------------------------------------------------
+# reference CPU arm / cpu_baseline / parity (the only users of oracle/)
+# ---------------------------------------------------------------------------
+def _ref_worker(conn, text, frames):
     """One host process = one single-threaded reference generator (the reference has no
     threading of its own) over a slice of the workload's voices, kept alive across steps."""
     from oracle import pyref
@@ -167,25 +190,24 @@ def _ref_worker(conn, text):
         t0 = time.perf_counter()
         if gen is None:
             gen = pyref.RefGenerator(prg, SRATE)          # sau_create_Generator, timed
-        frames = 0
+        n_tot = 0
         for _ in range(cmd[1]):
-            more, _, n = gen.run(FRAMES)                  # sauGenerator_run, 24576 frames
-            frames += n
-        conn.send((frames, prg.vo_count, time.perf_counter() - t0))
+            more, _, n = gen.run(frames)                  # sauGenerator_run
+            n_tot += n
+        conn.send((n_tot, prg.vo_count, time.perf_counter() - t0))
     conn.close()
 
 
 class ReferencePool:
     """The unmodified reference generator (oracle/_ref/libsauref.so) on `procs` host
-    processes, each rendering a disjoint slice of the C3 voices call by call."""
+    processes, each rendering a disjoint slice of a many-voice script call by call."""
 
-    def __init__(self, voices, procs, seed=1):
+    def __init__(self, text, procs, frames=FRAMES):
         import multiprocessing as mp
-        from saugns_b200 import workloads
         from oracle import pyref
         if not pyref.available():
             raise RuntimeError("oracle/_ref/libsauref.so missing")
-        full = workloads.synth_c3(voices, SECS, seed=seed, fm="mix").splitlines()
+        full = text.splitlines()
         head, body = full[0], full[1:]
         per = (len(body) + procs - 1) // procs
         ctx = mp.get_context("fork")
@@ -195,7 +217,7 @@ class ReferencePool:
             if not part:
                 continue
             a, b = ctx.Pipe()
-            pr = ctx.Process(target=_ref_worker, args=(b, "\n".join([head] + part) + "\n"),
+            pr = ctx.Process(target=_ref_worker, args=(b, "\n".join([head] + part) + "\n", frames),
                              daemon=True)
             pr.start()
             self.conns.append(a)
@@ -218,6 +240,65 @@ class ReferencePool:
             p.join(timeout=10)
 
 
+def _parity_worker(conn, text, ncalls, frames, table_file):
+    """The unmodified reference generator on the WHOLE script (one process, in voice order:
+    the mix's float summation order) for the first `ncalls` calls.  The wave tables are input
+    data of the path: the GPU arm reads them from `table_file`, written from
+    libsau on the build host; libm's last bits differ between host CPUs (tests/golden/
+    make_golden.py), so when this host's libsau builds other bits the reference's table
+    arrays are overwritten with the file's before it renders -- same input on both sides."""
+    import ctypes as C
+    import numpy as np
+    from oracle import pyref
+    L = pyref.lib()
+    prg = pyref.Program(text)            # sau_global_init_Wave has run by now
+    t = pyref.piluts()
+    blob = open(table_file, "rb").read()
+    want = np.frombuffer(blob, "<f4", 12 * 2048, 16).reshape(12, 2048)
+    same = bool(np.array_equal(t, want))
+    if not same:
+        for w in range(12):
+            C.memmove(L.refwb_pilut(w), want[w].ctypes.data, 2048 * 4)
+    gen = pyref.RefGenerator(prg, SRATE)
+    out = []
+    t0 = time.perf_counter()
+    for _ in range(ncalls):
+        more, buf, n = gen.run(frames)
+        out.append(buf.tobytes())
+    conn.send((same, out, time.perf_counter() - t0))
+    conn.close()
+
+
+def start_parity(text, ncalls, frames=FRAMES):
+    import multiprocessing as mp
+    from saugns_b200 import generator as G
+    ctx = mp.get_context("fork")
+    a, b = ctx.Pipe()
+    pr = ctx.Process(target=_parity_worker, args=(b, text, ncalls, frames, G.TABLES_PATH), daemon=True)
+    pr.start()
+    return a, pr
+
+
+def finish_parity(handle, gpu_calls, what):
+    """-> the `parity` object: max |GPU - reference| in LSB over the compared calls."""
+    import hashlib
+    import numpy as np
+    conn, pr = handle
+    same, ref_calls, secs = conn.recv()
+    pr.join(timeout=10)
+    mx, nz = 0, 0
+    for g, r in zip(gpu_calls, ref_calls):
+        d = np.abs(np.asarray(g, np.int32) - np.frombuffer(r, np.int16).astype(np.int32))
+        mx = max(mx, int(d.max()) if d.size else 0)
+        nz += int(np.count_nonzero(np.frombuffer(r, np.int16)))
+    return {"checked": True, "max_lsb": mx, "calls": len(ref_calls), "what": what,
+            "reference": "unmodified reference generator (oracle/_ref), whole script in one process",
+            "nonzero_reference_samples": nz,
+            "sha256_gpu": hashlib.sha256(b"".join(np.asarray(g, np.int16).tobytes() for g in gpu_calls)).hexdigest(),
+            "sha256_reference": hashlib.sha256(b"".join(ref_calls)).hexdigest(),
+            "host_tables_match_table_file": same, "reference_seconds": round(secs, 2)}
+
+
 def run_reference_arm(args):
     rank, _, world = env_rank()
     if rank != 0:
@@ -226,7 +307,7 @@ def run_reference_arm(args):
     procs = max(1, min(cores, 64))
     if args.warmup + args.steps > SECS * SRATE // FRAMES:
         raise SystemExit("steps+warmup exceed the workload's calls")
-    pool = ReferencePool(VOICES, procs)
+    pool = ReferencePool(c3_text(1), procs)
     # one step = the same 24576-frame call over all 4096 voices, on all host cores
     for _ in range(args.warmup):
         pool.step()
@@ -243,11 +324,7 @@ def run_reference_arm(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1000.0 * t_tot / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "voices": VOICES, "frames_per_step": FRAMES,
-                   "srate": SRATE, "op_samples_per_step": 3 * VOICES * FRAMES,
-                   "l2": "host arm: the reference's block buffers live in the CPU caches",
-                   "parallelism": f"one 4096-voice script, voices split over {used} host processes "
-                                  "(the reference is single-threaded)"},
+        "config": c3_config(),
         "realtime_factor": (FRAMES * args.steps / SRATE) / t_tot,
         "cpu_baseline": {"value": value, "unit": "voice-samples/s", "cores": used,
                          "kind": "reference",
@@ -265,10 +342,42 @@ def run_reference_arm(args):
 # ---------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------
+def load_peaks():
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = peaks.get("hbm_gbs", 6650.0)
+    return peak, ("measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650")
+
+
+def program_bytes(prg):
+    try:
+        import ctypes
+        from saugns_b200 import program as P
+        pp = P.Program.from_address(prg.ptr)
+        return (ctypes.sizeof(P.Program) + pp.ev_count * ctypes.sizeof(P.Event) +
+                pp.op_count * (ctypes.sizeof(P.OpData) + 3 * ctypes.sizeof(P.Line)))
+    except Exception:
+        return 0
+
+
+def latest_profile(pattern):
+    try:
+        import glob
+        latest = sorted(glob.glob(os.path.join(ROOT, "profiles", pattern)))[-1]
+        prof = json.load(open(latest))
+        prof["file"] = os.path.relpath(latest, ROOT)
+        return prof
+    except Exception:
+        return {}
+
+
 def run_gpu_arm(args):
+    import numpy as np
     import torch
     import saugns_b200
-    from saugns_b200 import workloads
 
     rank, local_rank, world = env_rank()
     dist = None
@@ -282,11 +391,17 @@ def run_gpu_arm(args):
     K, W = args.steps, args.warmup
     if W + K > SECS * SRATE // FRAMES - 1:
         raise SystemExit("steps+warmup exceed the workload's calls")
+    PARITY_CALLS = 2
 
-    def build_program():
-        return workloads.build_c3(VOICES, SECS, seed=1 + rank, fm="mix")
+    # the reference renders the same script's first calls on a host core meanwhile (rank 0)
+    parity = None
+    if rank == 0 and not args.no_cpu:
+        try:
+            parity = start_parity(c3_text(1), PARITY_CALLS)
+        except Exception:
+            parity = None
 
-    prg = build_program()
+    prg = c3_program(1 + rank)
 
     def barrier():
         if dist is not None:
@@ -333,27 +448,29 @@ def run_gpu_arm(args):
     # bytecode, tables) + W+K x sauGenerator_run with a host PCM buffer (D2H every call)
     # + destroy; the W warm-up calls are part of the same render, so they are timed and
     # counted too (a renderer cannot skip the start of its script).
-    import ctypes
-    prg_bytes = 0
-    try:
-        from saugns_b200 import program as P
-        pp = P.Program.from_address(prg.ptr)
-        prg_bytes = (ctypes.sizeof(P.Program) + pp.ev_count * ctypes.sizeof(P.Event) +
-                     pp.op_count * (ctypes.sizeof(P.OpData) + 3 * ctypes.sizeof(P.Line)))
-    except Exception:
-        pass
+    prg_bytes = program_bytes(prg)
     barrier()
+    first_calls = []
     t0 = time.perf_counter()
     g2 = saugns_b200.Generator(prg, SRATE, device=local_rank, stream=stream.cuda_stream,
                                max_call_len=FRAMES)
-    for _ in range(W + K):
+    for i in range(W + K):
         more, pcm, n = g2.run(FRAMES)
+        if i < PARITY_CALLS:
+            first_calls.append(pcm)
     g2.close()
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_steps = W + K
     assert int(abs(pcm.astype("int32")).max()) > 0, "silent output"
     barrier()
+
+    extra = {}
+    if world > 1 and not args.no_extra:
+        try:
+            extra["c3_voice_sharded"] = leg_c3_sharded(args, dist, rank, local_rank, world)
+        except Exception as e:      # an extra leg never takes the headline line down
+            extra["c3_voice_sharded"] = {"error": repr(e)}
 
     if rank != 0:
         if dist is not None:
@@ -363,13 +480,7 @@ def run_gpu_arm(args):
     vs_step = VOICES * FRAMES
     value = world * vs_step * K / (ms / 1000.0)
     e2e = world * vs_step * e2e_steps / e2e_s
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    peak = peaks.get("hbm_gbs", 6650.0)
-    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650"
+    peak, peak_src = load_peaks()
     # algorithmic bytes (8 B per voice-sample = one f32 carrier store by the
     # render kernel + one f32 load by the mix kernel; pans are constant in C3, so no r rows):
     # 4 B per voice-sample for EACH of the two kernels' launches
@@ -378,22 +489,14 @@ def run_gpu_arm(args):
     mix_alg = 4.0 * vs_step + 4.0 * FRAMES
     rk_s = (render_ms / K) / 1000.0
     achieved = alg_bytes / rk_s / 1e9
-    prof = {}
-    try:
-        import glob
-        latest = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_render_kernel.json")))[-1]
-        prof = json.load(open(latest))
-        prof["file"] = os.path.relpath(latest, ROOT)
-    except Exception:
-        pass
+    prof = latest_profile("r*_render_kernel.json")
+    sm_hz = (clocks.get("sm_mhz") or 1965.0) * 1e6
+    sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
     line = {
         "metric": METRIC, "value": value, "unit": "voice-samples/s", "n_gpus": world,
         "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "voices": VOICES, "frames_per_step": FRAMES,
-                   "srate": SRATE, "op_samples_per_step": 3 * vs_step,
-                   "l2": "per-step voice rows 403 MB > 126 MB L2 (working set larger than L2)",
-                   "parallelism": f"independent 4096-voice scripts x{world}"},
+        "config": c3_config(),
         "realtime_factor": (FRAMES * K / SRATE) / (ms / 1000.0),
         "clocks": clocks,
         "e2e": {"value": e2e, "unit": "voice-samples/s",
@@ -411,23 +514,34 @@ def run_gpu_arm(args):
                      "mix_kernel": {"bound": "hbm", "achieved": mix_alg / mix_s / 1e9, "peak": peak,
                                     "unit": "GB/s", "frac": mix_alg / mix_s / 1e9 / peak,
                                     "algorithmic_bytes_per_launch": mix_alg},
-                     "note": "path is issue-/FP64-pipe-bound, not HBM-bound (SURVEY.md 8d); "
-                             "issue-slot figures from ncu in profiles/",
+                     "note": "render_kernel is bound by instruction issue and the shared-memory data "
+                             "pipe, not HBM (SURVEY.md 8d); the issue / pipe figures come from the "
+                             "committed steady-state ncu capture named in ncu_profile, whose own "
+                             "duration is ncu_duration_ms (this run's event timing: kernel_ms_per_launch)",
+                     "ncu_profile": prof.get("file"),
+                     "ncu_duration_ms": (prof.get("duration_ns") or 0) / 1e6 or None,
                      "issue_slot_frac_ncu": prof.get("issue_slot_frac"),
-                     # the same launch's instruction count (ncu) over the issue slots of THIS run's
-                     # measured kernel time: 4 schedulers x 148 SMs x SM clock (the ncu capture itself
-                     # is a cold, serialised launch and runs ~40 % longer)
-                     "issue_slot_frac_live": (prof["warp_insts"] / (4 * 148 * (clocks.get("sm_mhz") or 1965.0)
-                                                                  * 1e6 * rk_s)
-                                              if prof.get("warp_insts") else None),
+                     "smem_pipe_frac_ncu": (prof.get("lsu_wavefronts_pct") or 0) / 100.0 or None,
                      "fp64_pipe_frac_ncu": prof.get("fp64_pipe_frac"),
                      "xu_pipe_frac_ncu": prof.get("xu_pipe_frac"),
-                     "ncu_profile": prof.get("file")},
+                     "warp_insts_per_32_op_samples_ncu": prof.get("warp_insts_per_32_op_samples"),
+                     # the capture's instruction count over the issue slots of THIS run's kernel time
+                     "issue_slot_frac_live": (prof["warp_insts"] / (4 * sms * sm_hz * rk_s)
+                                              if prof.get("warp_insts") else None)},
     }
+    if parity is not None:
+        try:
+            line["parity"] = finish_parity(
+                parity, first_calls,
+                f"first {PARITY_CALLS} calls ({PARITY_CALLS * FRAMES} frames x {VOICES} voices) of the timed "
+                "end-to-end run's own PCM (program from ProgramBuilder) against the reference "
+                "(script through its own parser)")
+        except Exception as e:
+            line["parity"] = {"checked": False, "error": repr(e)}
     if world == 1 and not args.no_cpu:
         try:
             cores = min(os.cpu_count() or 1, 64)
-            pool = ReferencePool(VOICES, cores)
+            pool = ReferencePool(c3_text(1), cores)
             pool.step(1)                    # create + first call (warm-up)
             ncalls = 40                     # ~10 s of audio for all 4096 voices
             vs, wall = pool.step(ncalls)
@@ -441,140 +555,287 @@ def run_gpu_arm(args):
         except Exception as e:   # the baseline is reported, never required for the GPU number
             line["cpu_baseline"] = {"value": None, "unit": "voice-samples/s", "cores": 0,
                                     "kind": "reference", "sample": f"unavailable: {e}"}
+    if world == 1 and not args.no_extra:
+        for name, leg in (("c4", leg_c4), ("c5", leg_c5)):
+            try:
+                extra[name] = leg(args, local_rank, clocks)
+            except Exception as e:
+                extra[name] = {"error": repr(e)}
+    if extra:
+        line["extra"] = extra
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
     return 0
 
 
-def run_gpu_config(args):
-    """The other BASELINE configs on one GPU (numbers for DESIGN.md section 8; the
-    headline line stays C3).  Scripts go through the reference's own script front end
-    on the host, exactly as in the drop-in (north star): oracle/_ref/libsauref.so is used
-    here for PARSING only; every sample is rendered by the CUDA back end."""
+# ---------------------------------------------------------------------------
+# the other BASELINE configs, as legs of the default run (`extra`)
+# ---------------------------------------------------------------------------
+C4_VOICES = 1024
+
+
+def leg_c4(args, device, clocks, steps=20, warmup=3):
+    """BASELINE config 4: 1024 voices with self-feedback PM carriers (W and R) and range-AM /
+    ring modulation -- the sequential-per-sample path.  Every feedback operator is ONE serial
+    chain over the render, so the figure of merit is cycles per feedback iteration."""
+    import torch
+    import saugns_b200
+    from saugns_b200 import workloads
+    text = workloads.synth_c4(C4_VOICES, SECS)
+    par = None
+    if not args.no_cpu:
+        par = start_parity(text, 1)
+    prg = workloads.build_c4(C4_VOICES, SECS)
+    g = saugns_b200.Generator(prg, SRATE, device=device, max_call_len=FRAMES)
+    for _ in range(warmup):
+        g.run_device(FRAMES)
+    g.set_timing(True)
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(steps):
+        g.run_device(FRAMES)
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    rk, mk = g.kernel_ms()
+    g.close()
+    first = []
+    t0 = time.perf_counter()
+    g2 = saugns_b200.Generator(prg, SRATE, device=device, max_call_len=FRAMES)
+    for i in range(warmup + steps):
+        more, pcm, n = g2.run(FRAMES)
+        if i < 1:
+            first.append(pcm)
+    g2.close()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    vs_step = C4_VOICES * FRAMES
+    peak, peak_src = load_peaks()
+    sm_mhz = clocks.get("sm_mhz") or 1965.0
+    prof = latest_profile("r*_c4_render_kernel.json")
+    leg = {"metric": METRIC, "unit": "voice-samples/s", "value": vs_step * steps / (ms / 1000.0),
+           "steps": steps, "warmup": warmup, "ms_per_step": ms / steps,
+           "config": {"workload": "C4: 1024 voices, self-PM carriers (Wsin / Rlin / Wtri with p.a 0.3-1.0) "
+                                  "with range-AM or ring modulation, 96 kHz stereo; step = one 24576-frame call",
+                      "voices": C4_VOICES, "frames_per_step": FRAMES, "srate": SRATE},
+           "realtime_factor": (FRAMES * steps / SRATE) / (ms / 1000.0),
+           "e2e": {"value": vs_step * (warmup + steps) / e2e_s, "unit": "voice-samples/s",
+                   "h2d_bytes_per_step": 40 + 12 + 6 * 12 + program_bytes(prg) // (warmup + steps),
+                   "d2h_bytes_per_step": FRAMES * 2 * 2 + 8,
+                   "timed": "create + calls with host PCM buffers + destroy, wall clock"},
+           "roofline": {"bound": "latency", "kernel": "render_kernel",
+                        "kernel_ms_per_launch": rk / steps, "mix_kernel_ms_per_launch": mk / steps,
+                        "cycles_per_feedback_iteration": (rk / steps) * 1e-3 * sm_mhz * 1e6 / FRAMES,
+                        "achieved": 4.0 * vs_step / (rk / steps / 1000.0) / 1e9, "peak": peak, "unit": "GB/s",
+                        "frac": 4.0 * vs_step / (rk / steps / 1000.0) / 1e9 / peak, "peak_source": peak_src,
+                        "traffic": prof.get("dram_bytes_per_launch"), "ncu_profile": prof.get("file"),
+                        "note": "serial self-PM chains (SURVEY.md section 7): a call takes FRAMES dependent "
+                                "feedback iterations whatever the voice count; the HBM fraction is reported "
+                                "by contract, the bound is the iteration's dependent-issue latency"}}
+    if par is not None:
+        leg["parity"] = finish_parity(par, first, "first call of the end-to-end run against the reference")
+        cores = min(os.cpu_count() or 1, 64)
+        pool = ReferencePool(text, cores)
+        pool.step(1)
+        vs, wall = pool.step(8)
+        used = pool.used
+        pool.close()
+        leg["cpu_baseline"] = {"value": vs / wall, "unit": "voice-samples/s", "cores": used, "kind": "reference",
+                               "sample": f"unmodified reference generator, same script, calls 2..9, voices split "
+                                         f"over {used} single-threaded processes; {wall:.2f} s wall"}
+    return leg
+
+
+def _cli_render(job):
+    """One `saugns -m -d -o x.wav script.sau` of the stock reference CLI (the C5
+    baseline is the reference's own program, one script per process, `xargs -P <cores>`)."""
+    cli, src, out = job
+    r = subprocess.run([cli, "-m", "-d", "-r", str(SRATE), "-o", out, src], capture_output=True)
+    return r.returncode
+
+
+def leg_c5(args, device, clocks):
+    """BASELINE config 5: independent mixed scripts (4-16 voices of W+PM / N / R / swept W with
+    range-AM, 1-10 s), this GPU's share of the 10 000 (1250 = 10 000 / 8), through the batched
+    driver, every script's PCM delivered to the host."""
+    import hashlib
+    import shutil
+    import tempfile
     import numpy as np
     import torch
     import saugns_b200
     from saugns_b200 import workloads, batch
     from saugns_b200 import program as P
-    from oracle import pyref, pyport
-    import ctypes as C
-    rank, local_rank, world = env_rank()
-    torch.cuda.set_device(local_rank)
-    t = pyport.ref_tables()
-    tabs = saugns_b200.WaveTables.from_buffer_copy(bytes(t))
-    tabs._keep = t
-    K, W = args.steps, args.warmup
-    if args.workload == "c3-sharded":
-        # ONE 4096-voice script, its voices spread over the ranks (strong scaling): each rank
-        # renders its voices' float mix planes, one NCCL sum-reduce per call, root converts
-        import torch.distributed as dist
-        from saugns_b200 import multigpu
-        if world > 1:
-            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        prg = workloads.build_c3(VOICES, SECS, seed=1, fm="mix")
-        vg = multigpu.VoiceShardedGenerator(prg, SRATE, device=local_rank, max_call_len=FRAMES)
-        for _ in range(W):
-            vg.run(FRAMES)
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(K):
-            more, pcm, n = vg.run(FRAMES)
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        wall = time.perf_counter() - t0
-        vg.close()
-        if rank == 0:
-            print(json.dumps({"metric": METRIC, "workload": "C3, ONE 4096-voice script voice-sharded over "
-                              f"{world} GPU(s): one ncclReduce of the float L/R planes per call, PCM on the "
-                              "root's host buffer", "value": VOICES * FRAMES * K / wall,
-                              "unit": "voice-samples/s", "n_gpus": world, "steps": K,
-                              "ms_per_step": 1000 * wall / K, "scaling": "strong",
-                              "realtime_factor": (FRAMES * K / SRATE) / wall}))
-        if world > 1:
-            dist.destroy_process_group()
-        return 0
-    if args.workload == "c4":
-        nv = 1024
-        prg = pyref.Program(workloads.synth_c4(nv, SECS))
-        g = saugns_b200.Generator(prg, SRATE, tables=tabs, device=local_rank, max_call_len=FRAMES)
-        for _ in range(W):
-            g.run_device(FRAMES)
-        g.set_timing(True)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(K):
-            g.run(FRAMES)
-        torch.cuda.synchronize()
-        wall = time.perf_counter() - t0
-        rk, mk = g.kernel_ms()
-        g.close()
-        # latency model: every self-PM operator is one serial chain over the call
-        sm_mhz = 1965.0
-        line = {"metric": METRIC, "workload": "C4: 1024 voices, self-PM carriers (W and R) with "
-                "range-AM / ring-mod, 96 kHz; step = one 24576-frame call, host PCM buffers",
-                "value": nv * FRAMES * K / wall, "unit": "voice-samples/s", "steps": K,
-                "ms_per_step": 1000 * wall / K, "render_kernel_ms": rk / K, "mix_kernel_ms": mk / K,
-                "realtime_factor": (FRAMES * K / SRATE) / wall,
-                "cycles_per_feedback_iteration_at_max_clock": (rk / K) * 1e-3 * sm_mhz * 1e6 / FRAMES}
-        print(json.dumps(line))
-        return 0
-    # c5: independent scripts, this GPU's share of 10 000 (default 10000/8 = 1250)
     n = args.scripts
-    dist = None
-    if world > 1:              # script sharding: every rank its own scripts, no data-path collective
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    texts = [workloads.synth_c5_script(rank * n + i) for i in range(n)]
     t0 = time.perf_counter()
-    prgs = [pyref.Program(x) for x in texts]
-    parse_s = time.perf_counter() - t0
+    prgs = [workloads.build_c5_script(i) for i in range(n)]
+    build_s = time.perf_counter() - t0
     vs = 0
     for p in prgs:
-        d = P.dump(p.ptr)
-        for ev in d["events"]:
-            for od in ev["ops"]:
-                if od["id"] == ev["carr_op_id"]:
-                    vs += od["time"][0] * SRATE // 1000
-    batch.render_batch(prgs[:16], srate=SRATE, device=local_rank, tables=tabs, group_size=16)  # warm-up
+        pp = P.Program.from_address(p.ptr)
+        for e in range(pp.ev_count):
+            ev = pp.events[e]
+            for k in range(ev.op_data_count):
+                od = ev.op_data[k]
+                if od.id == ev.carr_op_id:
+                    vs += od.time.v_ms * SRATE // 1000
+    batch.render_batch(prgs[:16], srate=SRATE, device=device, group_size=16)      # warm-up
     torch.cuda.synchronize()
-    if dist is not None:
-        dist.barrier()
-    t0 = time.perf_counter()
     got = {}
+    keep = set(range(0, n, max(1, n // 16)))      # scripts whose PCM is compared with the reference
 
     def sink(i, pcm):          # what a file writer would get: every script's PCM, once
-        got[i] = (pcm.shape[0], int(pcm[::997].astype(np.int64).sum()))
+        got[i] = (pcm.shape[0], hashlib.sha256(np.ascontiguousarray(pcm).tobytes()).hexdigest()
+                  if i in keep else None)
 
-    batch.render_batch(prgs, srate=SRATE, device=local_rank, tables=tabs,
-                       group_size=args.group, threads=args.threads, sink=sink,
-                       call_len=args.call_frames, pinned=args.pinned, depth=args.depth)
+    t0 = time.perf_counter()
+    batch.render_batch(prgs, srate=SRATE, device=device, group_size=args.group, threads=args.threads,
+                       sink=sink, call_len=args.call_frames, pinned=args.pinned, depth=args.depth)
     wall = time.perf_counter() - t0
     assert len(got) == n
     frames = sum(v[0] for v in got.values())
-    if dist is not None:       # whole job: all ranks' scripts over the slowest rank's time
-        t = torch.tensor([wall, -float(vs), -float(frames)], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        wall = float(t[0].item())
-        tot = torch.tensor([float(vs), float(frames)], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-        vs, frames = int(tot[0].item()), int(tot[1].item())
+    # device-resident figure: the same batch with no PCM delivered to the host
+    t0 = time.perf_counter()
+    batch.render_batch(prgs, srate=SRATE, device=device, group_size=args.group, threads=args.threads,
+                       sink=lambda i, pcm: None, call_len=args.call_frames, pinned=True, depth=args.depth)
+    wall_dev = time.perf_counter() - t0
+    leg = {"metric": METRIC, "unit": "voice-samples/s", "value": vs / wall_dev,
+           "config": {"workload": f"C5: {n} independent mixed scripts (one GPU's share of 10 000 over 8), "
+                                  f"4-16 voices each (W+PM / N / R / swept W + range-AM), 1-10 s, 96 kHz stereo",
+                      "scripts": n, "srate": SRATE, "call_frames": args.call_frames, "group": args.group},
+           "scripts_per_s": n / wall_dev, "audio_s": frames / SRATE,
+           "realtime_factor": (frames / SRATE) / wall_dev,
+           "timed": "batched saugen_batch_begin/_end over live sets; value: page-locked recycled PCM arrays, "
+                    "nothing kept; e2e: every script's PCM copied to pageable host arrays and handed to a sink",
+           "e2e": {"value": vs / wall, "unit": "voice-samples/s", "scripts_per_s": n / wall, "wall_s": wall,
+                   "h2d_bytes_per_step": sum(program_bytes(p) for p in prgs) // n,
+                   "d2h_bytes_per_step": frames * 4 // n, "step": "one script"},
+           "program_build_s": build_s}
+    if not args.no_cpu:
+        from oracle import pyref
+        from concurrent.futures import ThreadPoolExecutor
+        cores = min(os.cpu_count() or 1, 64)
+        m = min(n, 20 * cores)             # bounded sample: ~20 scripts per core
+        tmp = tempfile.mkdtemp(prefix="c5ref_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+        try:
+            jobs = []
+            for i in range(m):
+                src = os.path.join(tmp, f"s{i}.sau")
+                with open(src, "w") as f:
+                    f.write(workloads.synth_c5_script(i))
+                jobs.append((pyref.REF_EXE, src, os.path.join(tmp, f"s{i}.wav")))
+            t0 = time.perf_counter()
+            with ThreadPoolExecutor(cores) as ex:          # one reference process per script, `cores` at a time
+                rcs = list(ex.map(_cli_render, jobs))
+            cpu_wall = time.perf_counter() - t0
+            assert not any(rcs), "reference CLI failed"
+            vs_m = 0
+            for p in prgs[:m]:
+                pp = P.Program.from_address(p.ptr)
+                for e in range(pp.ev_count):
+                    ev = pp.events[e]
+                    for k in range(ev.op_data_count):
+                        if ev.op_data[k].id == ev.carr_op_id:
+                            vs_m += ev.op_data[k].time.v_ms * SRATE // 1000
+            bad, cmp_n = 0, 0
+            for i in sorted(keep):
+                if i >= m:
+                    continue
+                data = open(jobs[i][2], "rb").read()[44:]
+                cmp_n += 1
+                if hashlib.sha256(data).hexdigest() != got[i][1]:
+                    bad += 1
+            leg["cpu_baseline"] = {"value": vs_m / cpu_wall, "unit": "voice-samples/s", "cores": cores,
+                                   "kind": "reference", "scripts_per_s": m / cpu_wall,
+                                   "sample": f"the stock reference CLI (`saugns -m -d -o x.wav`, oracle/_ref), one "
+                                             f"process per script, {cores} at a time, first {m} scripts, WAV files "
+                                             f"on a RAM disk; {cpu_wall:.2f} s wall (parse + render + write)"}
+            leg["parity"] = {"checked": True, "scripts_compared": cmp_n, "scripts_differing": bad,
+                             "what": "sha256 of each compared script's whole PCM: the batch driver's host array "
+                                     "against the data chunk of the reference CLI's WAV file"}
+        finally:
+            shutil.rmtree(tmp, ignore_errors=True)
+    return leg
+
+
+def leg_c3_sharded(args, dist, rank, local_rank, world, steps=20, warmup=3):
+    """ONE C3 script (seed 1), its voices spread over the ranks (strong scaling): each rank
+    renders its voices' float mix planes, one NCCL sum-reduce per call, the root converts.
+    Compared with the same script rendered unsharded on the root's GPU."""
+    import numpy as np
+    import torch
+    import saugns_b200
+    from saugns_b200 import multigpu
+    prg = c3_program(1)
+    vg = multigpu.VoiceShardedGenerator(prg, SRATE, device=local_rank, max_call_len=FRAMES)
+    first = []
+    for i in range(warmup):
+        more, pcm, n = vg.run(FRAMES)
+        if rank == 0 and i < 2:
+            first.append(pcm.copy())
+    dist.barrier()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(steps):
+        vg.run(FRAMES)
+    ev1.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    ncoll = getattr(vg, "collectives", None)
+    vg.close()
+    leg = None
+    if rank == 0:
+        g = saugns_b200.Generator(prg, SRATE, device=local_rank, max_call_len=FRAMES)
+        mx = 0
+        for i in range(len(first)):
+            more, pcm, n = g.run(FRAMES)
+            mx = max(mx, int(np.abs(pcm.astype(np.int32) - first[i].astype(np.int32)).max()))
+        g.set_timing(True)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            g.run(FRAMES)
+        e1.record()
+        torch.cuda.synchronize()
+        one_ms = e0.elapsed_time(e1)
+        g.close()
+        leg = {"metric": METRIC, "unit": "voice-samples/s", "scaling": "strong", "n_gpus": world,
+               "value": VOICES * FRAMES * steps / (ms / 1000.0), "ms_per_step": ms / steps,
+               "one_gpu_ms_per_step": one_ms / steps, "speedup_vs_one_gpu": one_ms / ms,
+               "config": {"workload": "C3, ONE 4096-voice script voice-sharded over the ranks: one reduce of the "
+                                      "float L/R planes per call, PCM on the root's host buffer",
+                          "voices": VOICES, "frames_per_step": FRAMES},
+               "collectives_per_call": ncoll,
+               "parity": {"checked": True, "max_lsb": mx, "calls": len(first),
+                          "what": "sharded PCM against the same script rendered unsharded on one GPU "
+                                  "(the float summation order across ranks differs: <= 1 LSB allowed)"}}
+    return leg
+
+
+def run_gpu_config(args):
+    """One of the `extra` legs on its own (developer use): --workload c4 | c5 | c3-sharded."""
+    import torch
+    rank, local_rank, world = env_rank()
+    torch.cuda.set_device(local_rank)
+    clocks = {"sm_mhz": None}
+    if args.workload == "c3-sharded":
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        leg = leg_c3_sharded(args, dist, rank, local_rank, world, steps=args.steps)
+        if rank == 0:
+            print(json.dumps(leg))
         dist.destroy_process_group()
-        if rank != 0:
-            return 0
-        n = n * world
-    line = {"metric": METRIC, "n_gpus": world, "scaling": "weak",
-            "workload": f"C5: {n} independent mixed scripts (4-16 voices, W/N/R, "
-            f"1-10 s) on {world} GPU(s), batched saugen_run_many, every script's PCM delivered to a host "
-            f"sink (arrays recycled), {args.threads} driver thread(s) x 2 alternating "
-            f"live sets, {args.call_frames}-frame calls",
-            "value": vs / wall, "unit": "voice-samples/s", "scripts": n, "group": args.group,
-            "wall_s": wall, "scripts_per_s": n / wall, "audio_s": frames / SRATE,
-            "realtime_factor": (frames / SRATE) / wall, "parse_s_reference_front_end": parse_s}
-    print(json.dumps(line))
+        return 0
+    leg = leg_c4(args, local_rank, clocks, steps=args.steps) if args.workload == "c4" else \
+        leg_c5(args, local_rank, clocks)
+    print(json.dumps(leg))
     return 0
 
 
@@ -584,7 +845,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / parity legs")
     ap.add_argument("--no-extra", action="store_true", help="skip the C4 / C5 / voice-sharded legs (`extra`)")
     ap.add_argument("--workload", default="c3", choices=["c3", "c4", "c5", "c3-sharded"])
     ap.add_argument("--scripts", type=int, default=1250, help="c5: scripts on this GPU")

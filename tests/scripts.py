@@ -10,6 +10,7 @@ finite-time modulators, event sequencing and voice reuse.
 import random
 
 from saugns_b200.workloads import (synth_c3, build_c3, synth_c4, synth_c5_script,  # noqa: F401
+                                   build_c4, build_c5_script,
                                    WAVES, LINES, NOISES)   # the BASELINE workloads live with the product
 
 

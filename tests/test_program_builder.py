@@ -27,3 +27,37 @@ def test_builder_program_renders_identically_on_oracle(ref, port):
     a = port.render(prg, srate=48000)
     b = port.render(built, srate=48000)
     assert np.array_equal(a, b)
+
+
+def _same_program(P, a_ptr, b_ptr):
+    a, b = P.dump(a_ptr), P.dump(b_ptr)
+    assert a["events"] == b["events"]
+    for k in ("mode", "vo_count", "op_count", "op_nest_depth", "duration_ms", "ampmult"):
+        assert a[k] == b[k], k
+
+
+def test_builder_matches_parser_c4(ref):
+    """BASELINE config 4 (self-PM W and R carriers, range-AM, ring modulation): bench.py's C4 leg."""
+    from saugns_b200 import program as P
+    prg = ref.Program(scripts.synth_c4(96, 60))
+    built = scripts.build_c4(96, 60)
+    _same_program(P, prg.ptr, built.ptr)
+
+
+def test_builder_matches_parser_c5(ref):
+    """BASELINE config 5 (mixed W+PM / N / R modes / swept W with range-AM scripts, seeded operators
+    drawing from the front end's deterministic SplitMix32): bench.py's C5 leg."""
+    from saugns_b200 import program as P
+    for i in list(range(0, 200)) + list(range(1250, 10000, 173)):
+        prg = ref.Program(scripts.synth_c5_script(i))
+        built = scripts.build_c5_script(i)
+        _same_program(P, prg.ptr, built.ptr)
+
+
+def test_builder_programs_render_identically_on_oracle_c4_c5(ref, port):
+    import numpy as np
+    for prg, built in [(ref.Program(scripts.synth_c4(12, 1)), scripts.build_c4(12, 1)),
+                       (ref.Program(scripts.synth_c5_script(7)), scripts.build_c5_script(7))]:
+        a = port.render(prg, srate=48000, max_frames=48000)
+        b = port.render(built, srate=48000, max_frames=48000)
+        assert np.array_equal(a, b)
