@@ -121,9 +121,39 @@ int saugen_batch_end(saugen_Batch *b, size_t *out_lens, int *more);
 void *saugen_pinned_alloc(size_t bytes);
 void saugen_pinned_free(void *p);
 
-/* Voice-sharded rendering across GPUs: produce this rank's partial float mix
- * (2 x buf_len floats, L then R planes) in device memory; the caller reduces
- * the planes over ranks (NCCL sum) and converts on the root. */
+/* ---- the native batched front end (saugns_b200/csrc/batch_driver.cpp) ----
+ * What Player_run (saugns.c:575-623) + the script loop (saugns.c:648-659) + player/sndfile.c do
+ * for one script at a time, for n independent programs on one GPU: live sets of generators
+ * advanced with one render + one mix launch per call, each program's PCM rendered into ONE
+ * page-locked array that takes the device-to-host copies directly. */
+typedef struct saugen_BatchOptions {
+	int device;              /* CUDA device ordinal */
+	uint32_t call_len;       /* frames per generator call; 0 = 4 x 256 ms (results do not depend on it) */
+	uint32_t group;          /* generators per live set; 0 = 128 */
+	uint32_t depth;          /* alternating live sets; 0 = 2 */
+	uint32_t mono;           /* 1 = mono downmix (saugns --mono) */
+	uint32_t io_threads;     /* saugen_render_batch_wav: file writer threads; 0 = 4 */
+} saugen_BatchOptions;
+/* Receives a finished program's whole PCM (frames x channels int16, interleaved) on the driver
+ * thread.  The array is page-locked memory of the library's pool and now belongs to the sink:
+ * release it with saugen_pinned_free (from any thread) when done with it. */
+typedef void (*saugen_pcm_sink)(void *user, size_t index, int16_t *pcm, size_t frames, int channels);
+/* 0 = every program rendered; <0 = error (saugen_batch_last_error). */
+int saugen_render_batch(const sauabi_Program *const *prgs, size_t n, uint32_t srate,
+		const saugen_WaveTables *tables, const saugen_BatchOptions *opt, saugen_pcm_sink sink, void *user);
+/* The same with the reference's WAV files as the sink (player/sndfile.c:63-109: 44-byte header,
+ * little-endian int16): program i goes to paths[i]. */
+int saugen_render_batch_wav(const sauabi_Program *const *prgs, size_t n, uint32_t srate,
+		const saugen_WaveTables *tables, const saugen_BatchOptions *opt, const char *const *paths);
+const char *saugen_batch_last_error(void);
+
+/* Voice-sharded rendering across GPUs: produce this rank's partial float mix in device
+ * memory -- L plane at [0, buf_len), R plane at [row_len, row_len + buf_len), row_len =
+ * max_call_len rounded up to 4 -- valid until the call after the next (two blocks alternate);
+ * the caller reduces the planes over ranks (NCCL sum) and converts on the root.  The block is
+ * followed by SAUGEN_MIX_TAIL floats of the caller's own (saugns_b200/multigpu.py puts every
+ * rank's `more` / out_len there so that ONE collective carries data and control). */
+#define SAUGEN_MIX_TAIL 64
 int saugen_run_mix(saugen_Generator *o, size_t buf_len, float **dev_mix,
 		size_t *out_len);
 int saugen_mix_to_pcm(saugen_Generator *o, const float *dev_mix, size_t buf_len,

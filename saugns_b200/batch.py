@@ -10,6 +10,7 @@ ones between calls, while the other set's kernels run.  `write_wav` /
 RIFF/WAVE header with sizes patched at close, little-endian int16; AU (the
 `-o -` stdout stream) = 28-byte header, size unspecified, big-endian int16.
 """
+import os
 import struct
 
 import numpy as np
@@ -237,6 +238,61 @@ def _render_worker(programs, out, queue, srate, device, call_len, tables, group_
                 g.close()
             s.close()
         pool.close()
+
+
+class BatchOptions(__import__("ctypes").Structure):
+    """saugen_BatchOptions (include/saugen_b200.h)."""
+    _fields_ = [("device", __import__("ctypes").c_int), ("call_len", __import__("ctypes").c_uint32),
+                ("group", __import__("ctypes").c_uint32), ("depth", __import__("ctypes").c_uint32),
+                ("mono", __import__("ctypes").c_uint32), ("io_threads", __import__("ctypes").c_uint32)]
+
+
+def render_batch_native(programs, srate=96000, device=0, call_len=0, tables=None, group_size=128, depth=2,
+                        stereo=True, sink=None, wav_paths=None, io_threads=4):
+    """The same batch through the NATIVE driver (saugen_render_batch / saugen_render_batch_wav,
+    csrc/batch_driver.cpp): no Python between the calls.  `wav_paths`: program i is written to
+    wav_paths[i] by the library's writer threads (the reference's WAV format); else `sink(index,
+    pcm)` gets every finished program's int16 array [frames, ch] (valid during the call) on the
+    driver thread, or, with neither, the arrays are returned as a list (copies)."""
+    import ctypes as C
+    L = G.lib()
+    if tables is None:
+        tables = G.default_tables()
+    n = len(programs)
+    ptrs = (C.c_void_p * max(n, 1))(*[p.ptr for p in programs])
+    opt = BatchOptions(device=device, call_len=call_len, group=group_size, depth=depth,
+                       mono=0 if stereo else 1, io_threads=io_threads)
+    if wav_paths is not None:
+        keep = [os.fsencode(p) for p in wav_paths]
+        arr = (C.c_char_p * max(n, 1))(*keep)
+        r = L.saugen_render_batch_wav(ptrs, n, srate, C.addressof(tables), C.byref(opt), arr)
+        if r < 0:
+            raise RuntimeError("saugen_render_batch_wav failed: " + L.saugen_batch_last_error().decode())
+        return None
+    out = [None] * n
+    ch = 2 if stereo else 1
+    errs = []
+
+    @C.CFUNCTYPE(None, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int)
+    def cb(user, index, pcm, frames, channels):
+        try:
+            a = np.ctypeslib.as_array((C.c_int16 * (frames * channels)).from_address(pcm)).reshape(-1, channels) \
+                if frames else np.zeros((0, ch), np.int16)
+            if sink is not None:
+                sink(index, a)
+            else:
+                out[index] = a.copy()
+        except BaseException as e:        # never unwind through the C driver
+            errs.append(e)
+        finally:
+            L.saugen_pinned_free(pcm)
+
+    r = L.saugen_render_batch(ptrs, n, srate, C.addressof(tables), C.byref(opt), cb, None)
+    if errs:
+        raise errs[0]
+    if r < 0:
+        raise RuntimeError("saugen_render_batch failed: " + L.saugen_batch_last_error().decode())
+    return out
 
 
 def wav_bytes(pcm, srate):

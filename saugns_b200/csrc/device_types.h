@@ -243,6 +243,8 @@ struct CallDesc {
 	uint32_t nunits;
 	uint32_t more_launches;   // 1 = another render launch of this call follows (hand-over cut, runtime.cpp:
 	                          // plan_call): the voices' alive flag is set by the last launch only
+	int16_t *pcm;             // where this call's PCM goes (two alternate: the call after this one may
+	                          // already be rendering while the caller reads this one's, runtime.cpp run-ahead)
 };
 
 } // namespace saugen

@@ -47,15 +47,24 @@ constexpr uint32_t BUF_FLOATS = 32 * (FAST_NS > SPL ? FAST_NS : SPL);   // per w
  * area: whichever is larger. */
 constexpr int WIDE_WARPS = 28;        // most warps of a render_kernel_wide CTA: 72 registers each
 constexpr uint32_t STACK_BYTES = 3 * MAX_NEST * (uint32_t) sizeof(uint32_t);
-__host__ __device__ inline uint32_t warp_smem_bytes(uint32_t nbufs, uint32_t nslots, uint32_t nplan) {
+/* team > 1 (render_team.cuh): a second set of operator states (the member's work copy), a
+ * second plan area (its executable plan) and the team's command block */
+constexpr uint32_t TEAM_CMD_BYTES = 64;
+__host__ __device__ inline uint32_t warp_plan_bytes(uint32_t nplan) {
 	const uint32_t plan_bytes = nplan * 32u;
-	return nslots * (uint32_t) sizeof(OpState) + nbufs * BUF_FLOATS * (uint32_t) sizeof(float) +
-		(plan_bytes > STACK_BYTES ? plan_bytes : STACK_BYTES);
+	return plan_bytes > STACK_BYTES ? plan_bytes : STACK_BYTES;
+}
+__host__ __device__ inline uint32_t warp_smem_bytes(uint32_t nbufs, uint32_t nslots, uint32_t nplan, uint32_t team) {
+	const uint32_t k = team > 1u ? 2u : 1u;
+	return k * nslots * (uint32_t) sizeof(OpState) + nbufs * BUF_FLOATS * (uint32_t) sizeof(float) +
+		k * warp_plan_bytes(nplan) + (team > 1u ? TEAM_CMD_BYTES : 0u);
 }
 
 #include "render_ops.cuh"
 #include "render_interp.cuh"
 #include "render_plan.cuh"
+#include "render_fast.cuh"
+#include "render_team.cuh"
 #include "render_kernel.cuh"
 #include "mix_kernel.cuh"
 
@@ -124,11 +133,11 @@ cudaError_t launch_selftest(const float *d_tables, unsigned long long *d_bad, cu
 
 /* wave_mask may carry CTAB_FLAG (coefficient tables in shared memory) */
 size_t render_smem_bytes(uint32_t wave_mask, uint32_t nbufs, uint32_t nslots_ops, uint32_t nplan,
-		uint32_t warps) {
+		uint32_t warps, uint32_t team) {
 	uint32_t nslots = 0;
 	for (uint32_t w = 0; w < NUM_WAVES; ++w) if (wave_mask & (1u << w)) ++nslots;
 	const size_t slot = (wave_mask & CTAB_FLAG) ? CTAB_WAVE_BYTES : TAB_STRIDE * sizeof(float);
-	return 128 + (size_t) nslots * slot + (size_t) warps * warp_smem_bytes(nbufs, nslots_ops, nplan);
+	return 128 + (size_t) nslots * slot + (size_t) warps * warp_smem_bytes(nbufs, nslots_ops, nplan, team);
 }
 
 /* ---- per-index cubic coefficients of every wave table -------------------- *
@@ -197,22 +206,24 @@ int render_ctas_per_sm(size_t smem, uint32_t warps) {
 cudaError_t launch_render(const CallDesc *d_calls, uint32_t ncalls, const SegDesc *d_segs,
 		const UnitDesc *d_units, uint32_t ntasks, const float *d_tables, const double *d_coefs,
 		uint32_t wave_mask, uint32_t nbufs, uint32_t nslots_ops, uint32_t nplan, uint32_t warps,
-		uint32_t ticketed_ctas, uint32_t sched_mode, cudaStream_t stream) {
+		uint32_t ticketed_ctas, uint32_t sched_mode, uint32_t team, cudaStream_t stream) {
 	if (ntasks == 0) return cudaSuccess;
 	if (nslots_ops == 0) nslots_ops = 1;
-	const size_t smem = render_smem_bytes(wave_mask, nbufs, nslots_ops, nplan, warps);
+	if (team < 1 || ticketed_ctas) team = 1;
+	const size_t smem = render_smem_bytes(wave_mask, nbufs, nslots_ops, nplan, warps, team);
 	const bool wide = warps > 8;
 	{
 		cudaError_t e = ensure_smem(wide, smem);
 		if (e != cudaSuccess) return e;
 	}
-	const uint32_t grid = ticketed_ctas ? ticketed_ctas : (ntasks + warps - 1) / warps;
+	const uint32_t per_cta = warps / team;      /* voices per CTA */
+	const uint32_t grid = ticketed_ctas ? ticketed_ctas : (ntasks + per_cta - 1) / per_cta;
 	if (wide)
 		render_kernel_wide<<<grid, warps * 32, smem, stream>>>(d_calls, ncalls, d_segs, d_units, ntasks,
-				d_tables, d_coefs, wave_mask, nbufs, nslots_ops, nplan, warps, ticketed_ctas ? sched_mode : 0u);
+				d_tables, d_coefs, wave_mask, nbufs, nslots_ops, nplan, warps, ticketed_ctas ? sched_mode : 0u, team);
 	else
 		render_kernel<<<grid, warps * 32, smem, stream>>>(d_calls, ncalls, d_segs, d_units, ntasks,
-				d_tables, d_coefs, wave_mask, nbufs, nslots_ops, nplan, warps, ticketed_ctas ? sched_mode : 0u);
+				d_tables, d_coefs, wave_mask, nbufs, nslots_ops, nplan, warps, ticketed_ctas ? sched_mode : 0u, team);
 	return cudaGetLastError();
 }
 

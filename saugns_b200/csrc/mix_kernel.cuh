@@ -36,9 +36,10 @@ struct MixSmem {
 
 __device__ __forceinline__ void mix_store(const GenDesc *g, const CallDesc *cd, uint32_t mode,
 		uint32_t f, float L, float R) {
-	if (mode == 1) {
-		g->mix[f] = L;
-		g->mix[g->row_len + f] = R;
+	if (mode == 1) {                  /* float planes: CallDesc::pcm is the call slot's plane block */
+		float *mix = reinterpret_cast<float*>(cd->pcm);
+		mix[f] = L;
+		mix[g->row_len + f] = R;
 		return;
 	}
 	/* CallDesc::stereo: bit 0 = two channels, bit 1 = big-endian samples (the AU stream
@@ -50,13 +51,13 @@ __device__ __forceinline__ void mix_store(const GenDesc *g, const CallDesc *cd, 
 		uint32_t w = ((uint32_t) (uint16_t) (short) __float2int_rn(L * 32767.f)) |
 			((uint32_t) (uint16_t) (short) __float2int_rn(R * 32767.f) << 16);
 		if (be) w = __byte_perm(w, 0u, 0x2301);
-		reinterpret_cast<uint32_t*>(g->pcm)[f] = w;
+		reinterpret_cast<uint32_t*>(cd->pcm)[f] = w;
 	} else {                                                       /* generator.c:812-825 */
 		float m = (L + R) * 0.5f;
 		m = sau::fclampf(m, -1.f, 1.f);
 		uint32_t w = (uint16_t) (short) __float2int_rn(m * 32767.f);
 		if (be) w = __byte_perm(w, 0u, 0x3201);
-		reinterpret_cast<uint16_t*>(g->pcm)[f] = (uint16_t) w;
+		reinterpret_cast<uint16_t*>(cd->pcm)[f] = (uint16_t) w;
 	}
 }
 

@@ -120,14 +120,24 @@ __device__ __noinline__ void render_units(Ctx &c, FastCtx &fc, const CallDesc *c
 					plan_put(fc.plan, 0, (uint32_t) tp, (uint32_t) (tp >> 32), (uint32_t) wp, (uint32_t) (wp >> 32),
 							__uint_as_float(fc.wave_mask), fc.amp_scale, __uint_as_float(fc.write_r),
 							__uint_as_float(c.tstride));
+					const uint64_t rs = reinterpret_cast<uint64_t>(row_s), rr = reinterpret_cast<uint64_t>(row_r);
+					plan_put(fc.plan, 1, (uint32_t) rs, (uint32_t) (rs >> 32), (uint32_t) rr, (uint32_t) (rr >> 32),
+							__uint_as_float(sd.start + off), fc.coeff, 0.f, 0.f);
 					__syncwarp();
 				}
 				if (fc.wave_mask & CTAB_FLAG) {
-					if (other) run_block_fast<true, true>(fc.sb, fc.plan, lane, fc.coeff, nrec, span, row_s, row_r, sd.start + off);
-					else run_block_fast<true, false>(fc.sb, fc.plan, lane, fc.coeff, nrec, span, row_s, row_r, sd.start + off);
+					/* coefficient planes: the plan is lowered (render_fast.cuh) */
+					if (lane == 0) plan_lower(fc.plan + PLAN_HDR, nrec);
+					__syncwarp();
+					/* few voices: the stretch is split along time over the voice's team of warps */
+					const bool shared = fc.team && !other &&
+						team_stretch(*fc.team, fc.sb, lane, fc.plan, nrec, vs.ops_cnt, span);
+					if (shared) { }
+					else if (other) run_block_lowered<true>(fc.sb, fc.plan, lane, 0u, span);
+					else run_block_lowered<false>(fc.sb, fc.plan, lane, 0u, span);
 				} else {
-					if (other) run_block_fast<false, true>(fc.sb, fc.plan, lane, fc.coeff, nrec, span, row_s, row_r, sd.start + off);
-					else run_block_fast<false, false>(fc.sb, fc.plan, lane, fc.coeff, nrec, span, row_s, row_r, sd.start + off);
+					if (other) run_block_fast<false, true>(fc.sb, fc.plan, lane, fc.coeff, span, row_s, row_r, sd.start + off);
+					else run_block_fast<false, false>(fc.sb, fc.plan, lane, fc.coeff, span, row_s, row_r, sd.start + off);
 				}
 				__syncwarp();
 				if (lane == 0) steady_update(c.sops, g->code + vs.code_off, vs.code_len, nb);
@@ -181,7 +191,7 @@ __device__ __noinline__ void render_units(Ctx &c, FastCtx &fc, const CallDesc *c
 __device__ __forceinline__ void render_body(const CallDesc *calls, uint32_t ncalls,
 		const SegDesc *segs, const UnitDesc *units, uint32_t ntasks, const float *tables,
 		const double *coefs, uint32_t wave_mask, uint32_t nbufs, uint32_t nslots_ops, uint32_t nplan, uint32_t warps_per_cta,
-		uint32_t ticketed) {
+		uint32_t ticketed, uint32_t team) {
 	extern __shared__ __align__(128) unsigned char smem[];
 	uint64_t *bar = reinterpret_cast<uint64_t*>(smem);
 	float *tab = reinterpret_cast<float*>(smem + 128);
@@ -189,7 +199,7 @@ __device__ __forceinline__ void render_body(const CallDesc *calls, uint32_t ncal
 	const uint32_t nslots = __popc(wave_mask & ~CTAB_FLAG);
 	const uint32_t slot_bytes = ctab ? CTAB_WAVE_BYTES : TAB_STRIDE * (uint32_t) sizeof(float);
 	unsigned char *warp_area = smem + 128 + nslots * slot_bytes;
-	const uint32_t per_warp = warp_smem_bytes(nbufs, nslots_ops, nplan);
+	const uint32_t per_warp = warp_smem_bytes(nbufs, nslots_ops, nplan, team);
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
 	/* stage the tables this launch needs: TMA bulk copies, one mbarrier */
@@ -227,7 +237,7 @@ __device__ __forceinline__ void render_body(const CallDesc *calls, uint32_t ncal
 
 	Ctx c;
 	c.sops = reinterpret_cast<OpState*>(warp_area + warp * per_warp);
-	c.bufs = reinterpret_cast<float*>(c.sops + nslots_ops);
+	c.bufs = reinterpret_cast<float*>(c.sops + (team > 1u ? 2u : 1u) * nslots_ops);
 	c.stk_len = reinterpret_cast<uint32_t*>(c.bufs + nbufs * BUF_FLOATS);
 	c.stk_rem = c.stk_len + MAX_NEST;
 	c.stk_layer = c.stk_rem + MAX_NEST;
@@ -243,12 +253,27 @@ __device__ __forceinline__ void render_body(const CallDesc *calls, uint32_t ncal
 	fc.wave_mask = wave_mask; fc.lane = lane;
 	fc.plan = smem_u32(c.stk_len);   /* the plan overlays the len stacks */
 	fc.plan_cap = nplan * 32u > STACK_BYTES ? nplan : STACK_BYTES / 32u;
+	fc.team = nullptr;
 
 	if (!ticketed) {
-		/* one warp renders every unit of one voice; task -> (call, voice) by
-		 * binary search on task_base */
-		const uint32_t task = blockIdx.x * warps_per_cta + warp;
+		/* one warp (or, with few voices, a team of warps: render_team.cuh) renders every unit
+		 * of one voice; task -> (call, voice) by binary search on task_base */
+		const uint32_t per_cta = warps_per_cta / team;
+		const uint32_t team_i = warp / team, rank = warp - team_i * team;
+		if (team_i >= per_cta) return;
+		const uint32_t task = blockIdx.x * per_cta + team_i;
 		if (task >= ntasks) return;
+		TeamCtx tc;
+		if (team > 1u) {
+			tc.T = team; tc.rank = rank; tc.bar = 1u + team_i;
+			tc.so_a = fc.so; tc.so_b = fc.so + nslots_ops * (uint32_t) sizeof(OpState);
+			tc.plan_x = fc.plan + warp_plan_bytes(nplan);
+			tc.per_warp = per_warp;
+			tc.cmd = tc.plan_x + warp_plan_bytes(nplan) - rank * per_warp;
+			tc.lead_so = fc.so - rank * per_warp; tc.lead_plan = fc.plan - rank * per_warp;
+			if (rank) { team_helper(tc, fc.sb, lane); return; }
+			fc.team = &tc;
+		}
 		uint32_t ci = 0, hi = ncalls;
 		while (hi - ci > 1) {
 			const uint32_t mid = (ci + hi) >> 1;
@@ -256,6 +281,7 @@ __device__ __forceinline__ void render_body(const CallDesc *calls, uint32_t ncal
 		}
 		const CallDesc *cd = &calls[ci];
 		render_units(c, fc, cd, segs, units, task - cd->task_base, 0, cd->nunits);
+		if (team > 1u) team_dismiss(tc, lane);
 		return;
 	}
 	const CallDesc *cd = &calls[0];
@@ -343,9 +369,9 @@ __device__ __forceinline__ void render_body(const CallDesc *calls, uint32_t ncal
 __global__ void __launch_bounds__(256, 2)
 render_kernel(const CallDesc *calls, uint32_t ncalls, const SegDesc *segs, const UnitDesc *units,
 		uint32_t ntasks, const float *tables, const double *coefs, uint32_t wave_mask, uint32_t nbufs,
-		uint32_t nslots_ops, uint32_t nplan, uint32_t warps_per_cta, uint32_t ticketed) {
+		uint32_t nslots_ops, uint32_t nplan, uint32_t warps_per_cta, uint32_t ticketed, uint32_t team) {
 	render_body(calls, ncalls, segs, units, ntasks, tables, coefs, wave_mask, nbufs, nslots_ops, nplan,
-			warps_per_cta, ticketed);
+			warps_per_cta, ticketed, team);
 }
 
 /* same body for CTAs of up to 32 warps (64 registers), one per SM (coefficient-table
@@ -354,7 +380,7 @@ render_kernel(const CallDesc *calls, uint32_t ncalls, const SegDesc *segs, const
 __global__ void __launch_bounds__(WIDE_WARPS * 32, 1)
 render_kernel_wide(const CallDesc *calls, uint32_t ncalls, const SegDesc *segs, const UnitDesc *units,
 		uint32_t ntasks, const float *tables, const double *coefs, uint32_t wave_mask, uint32_t nbufs,
-		uint32_t nslots_ops, uint32_t nplan, uint32_t warps_per_cta, uint32_t ticketed) {
+		uint32_t nslots_ops, uint32_t nplan, uint32_t warps_per_cta, uint32_t ticketed, uint32_t team) {
 	render_body(calls, ncalls, segs, units, ntasks, tables, coefs, wave_mask, nbufs, nslots_ops, nplan,
-			warps_per_cta, ticketed);
+			warps_per_cta, ticketed, team);
 }

@@ -66,7 +66,8 @@ enum : uint32_t {
 	                    * position at the stretch start, w2 1/time, w3 slope / span, w4 offset) */
 };
 constexpr uint32_t PLAN_FBUF = 32 * FAST_NS * 4;    /* FastCfg<FAST_NS>::FBUF_BYTES */
-constexpr uint32_t PLAN_WALK_MAX = 66 * 32;   /* bytes: more than any plan holds (runtime.cpp: np <= 64) */
+constexpr uint32_t PLAN_WALK_MAX = 67 * 32;   /* bytes: more than any plan holds (runtime.cpp: np <= 64) */
+constexpr uint32_t PLAN_HDR = 64;     /* bytes of the plan header (two slots) before the first record */
 constexpr uint32_t PLAN_REC = 32;     /* bytes: w0 kind|flags<<8|a<<16|b<<24, w1 c|e<<8|line<<16,
                                        * w2 operator state (shared address), w3 table (shared address),
                                        * w4 diff_scale, w5 diff_offset, w6 uniform value / phase increment, w7 av */
@@ -104,8 +105,8 @@ __device__ __noinline__ uint32_t steady_plan(OpState *sops, uint32_t so, uint32_
 	uint32_t selfmask = 0;             /* operator slots whose pm_a line runs: self-PM (generator.c:485-490) */
 	uint32_t other = 0;                /* the plan has serial self-PM records (bit 31 of the result) */
 	uint32_t n = 0;
-	plan += PLAN_REC;          /* slot 0 is the header (render_units) */
-	cap = cap > 2u ? cap - 2u : 0u;   /* ... and one slot stays free for the end mark */
+	plan += PLAN_HDR;          /* the first two slots are the header (render_units) */
+	cap = cap > 3u ? cap - 3u : 0u;   /* ... and one slot stays free for the end mark */
 	auto is_uni = [&](uint32_t b) { return b < 32 && ((uni >> b) & 1u); };
 	auto touch = [&](uint32_t b) { if (b < 32) { need |= 1u << b; line_uni &= ~(1u << b); } };   /* read as a vector */
 	auto dirty = [&](uint32_t b) {                                             /* rewritten */
@@ -553,6 +554,7 @@ struct FastCtx {               /* all registers */
 	uint32_t plan, plan_cap;   // shared addr of the block plan, records it can hold
 	const WaveCoeffs *wc;
 	const float *tab;          // generic pointer to the staged tables (rare paths)
+	const struct TeamCtx *team;   // the voice's team of warps (render_team.cuh), or null
 };
 /* What the chunk loop of a steady block keeps in registers; everything else it
  * needs is in the block plan (shared memory): header at c.plan, records after it. */
@@ -563,9 +565,10 @@ struct HotCtx {
 	int lane;
 	float coeff;
 };
-/* plan header (the first 32-byte slot): the cold paths' context and VOUT's constants */
+/* plan header (PLAN_HDR bytes): the cold paths' context, VOUT's constants, the voice's rows and
+ * the frame of the stretch's first sample */
 constexpr uint32_t PH_TAB = 0, PH_WC = 8, PH_WAVE_MASK = 16, PH_AMP_SCALE = 20, PH_WRITE_R = 24,
-	PH_TSTRIDE = 28;
+	PH_TSTRIDE = 28, PH_ROW_S = 32, PH_ROW_R = 40, PH_FRAME0 = 48, PH_COEFF = 52;
 template <int NS>
 __device__ __forceinline__ void fld(const HotCtx &c, uint32_t buf, float v[NS]) {
 	const uint32_t a = c.sb + buf * FastCfg<NS>::FBUF_BYTES;
@@ -968,123 +971,132 @@ __device__ __noinline__ void plan_other(uint32_t sb, float coeff, uint32_t oc, u
 	__syncwarp();
 }
 
+/* One record of the plan in its general form (anything steady_plan emits).  May consume the
+ * record's second slot (rec advances).  Returns true after the voice output (the chunk is done). */
+template <int NS, bool CTAB, bool OTHER>
+__device__ __forceinline__ bool plan_record_generic(const HotCtx &c, uint32_t &rec, const uint4 p0,
+		float *row_s, float *row_r, const uint32_t frame) {
+	const uint32_t kind = p0.x & 0xffu, flags = (p0.x >> 8) & 0xffu;
+	const uint32_t bufa = (p0.x >> 16) & 0xffu, bufb = p0.x >> 24;
+	const uint32_t op = p0.z;
+	if (kind <= P_WOSC) {
+		/* LINE / WHEAD: one line evaluation into a buffer; WLEAF: the same, kept in
+		 * registers, then phase fill and oscillator; WTAIL: the frequency comes from
+		 * its buffer; PHASE / WOSC: the two halves of an operator whose amplitude has
+		 * modulators, with the phases parked in a buffer in between */
+		uint32_t ph[NS];
+		uint32_t inc = 0;
+		bool pure = false;
+		if (kind != P_WOSC) {
+			const bool is_line = kind == P_LINE;
+			const bool funi = (flags & PF_FUNI) != 0;
+			float fr[NS];
+			if (kind == P_WTAIL || kind == P_PHASE) {
+				if (funi) inc = lds32(rec + 24);
+				else fld<NS>(c, bufb, fr);
+			} else {
+				const uint32_t mb = is_line ? bufb : (p0.y >> 8) & 0xffu;
+				if (funi) {
+					const uint32_t w6 = lds32(rec + 24);
+					inc = w6;
+#pragma unroll
+					for (int k = 0; k < NS; ++k) fr[k] = __uint_as_float(w6);
+				} else if (!is_line && (flags & PF_FMUL)) {
+					/* a constant ratio to a modulated parent frequency (line.c:417-445, no goal) */
+					const float v0 = lds32f(rec + 24);
+					fld<NS>(c, mb, fr);
+#pragma unroll
+					for (int k = 0; k < NS; ++k) fr[k] = v0 * fr[k];
+				} else {
+					float m[NS];
+					const bool has_mul = mb != NO_BUF;
+					if (has_mul) fld<NS>(c, mb, m);
+					line_value_steady<NS>(c, op, is_line ? (int) ((p0.y >> 16) & 0xffu) : (int) LINE_FREQ,
+							has_mul ? m : nullptr, fr);
+				}
+				if (kind != P_WLEAF) { fst<NS>(c, is_line ? bufa : bufb, fr); return false; }
+			}
+			const uint32_t bufc = p0.y & 0xffu;
+			phase_plan<NS>(c, op, bufc, funi, inc, fr, ph);
+			if (kind == P_PHASE) {
+				float pf[NS];
+#pragma unroll
+				for (int k = 0; k < NS; ++k) pf[k] = __uint_as_float(ph[k]);
+				fst<NS>(c, bufa, pf);
+				return false;
+			}
+			pure = funi && bufc == NO_BUF;
+		} else {
+			float pf[NS];
+			fld<NS>(c, bufb, pf);
+#pragma unroll
+			for (int k = 0; k < NS; ++k) ph[k] = __float_as_uint(pf[k]);
+		}
+		osc_plan<NS, CTAB>(c, p0, rec, pure, inc, ph);
+		if (flags & PF_AEXT) rec += PLAN_REC;                  /* the record's second slot */
+	} else if (kind == P_RANGE) {                              /* generator.c:465-467 */
+		float p[NS], rr[NS], m[NS];
+		fld<NS>(c, p0.y & 0xffu, m);
+		if (flags & PF_FUNI) {             /* both ends uniform: scalars from the record */
+			const float2 pr = lds64f(rec + 24);
+#pragma unroll
+			for (int k = 0; k < NS; ++k) { p[k] = pr.x; rr[k] = pr.y; }
+		} else {
+			fld<NS>(c, bufa, p); fld<NS>(c, bufb, rr);
+		}
+#pragma unroll
+		for (int k = 0; k < NS; ++k) p[k] += (rr[k] - p[k]) * m[k];
+		fst<NS>(c, bufa, p);
+	} else if (kind != P_VOUT) {                               /* P_NOISE, P_CYCLE, P_RASG, P_MIX, P_WSELF */
+		if (OTHER) plan_other(c.sb, c.coeff, c.oc, rec, c.plan);
+		else plan_ff(kind, c.sb - c.lane * 16, c.lane, c.coeff, c.oc, op, p0.x, p0.y);
+	} else {                                                   /* P_VOUT, generator.c:772-786 */
+		float sv[NS];
+		fld<NS>(c, bufa, sv);
+		const float pan = lds32f(op + OS_LINE + 16 * LINE_PAN);
+		float s[NS], rv[NS];
+		const float amp_scale = lds32f(c.plan + PH_AMP_SCALE);
+		const uint32_t write_r = lds32(c.plan + PH_WRITE_R);
+		const uint32_t tstride = lds32(c.plan + PH_TSTRIDE);
+#pragma unroll
+		for (int k = 0; k < NS; ++k) { s[k] = sv[k] * amp_scale; rv[k] = s[k] * pan; }
+		/* row_s / row_r: this voice's piece of frame tile 0 (device_types.h:ROW_TILE) */
+		const uint32_t fl = frame + c.lane * NS;
+		if ((frame & 3u) == 0) {
+#pragma unroll
+			for (int h = 0; h < NS / 4; ++h) {                   /* 128-bit streaming stores */
+				const size_t at = row_index(fl + 4 * h, tstride);
+				__stcs(reinterpret_cast<float4*>(row_s + at),
+						make_float4(s[4 * h], s[4 * h + 1], s[4 * h + 2], s[4 * h + 3]));
+				if (write_r)
+					__stcs(reinterpret_cast<float4*>(row_r + at),
+							make_float4(rv[4 * h], rv[4 * h + 1], rv[4 * h + 2], rv[4 * h + 3]));
+			}
+		} else {
+			/* segment starting at an odd frame: rare, out of line through the buffers */
+			const uint32_t rb = bufb != NO_BUF ? bufb : bufa + 1u;
+			fst<NS>(c, bufa, s);
+			fst<NS>(c, rb, rv);
+			__syncwarp();
+			vout_unaligned(c.sb - c.lane * 16 + bufa * FastCfg<NS>::FBUF_BYTES,
+					c.sb - c.lane * 16 + rb * FastCfg<NS>::FBUF_BYTES,
+					row_s, row_r, c.lane, NS, write_r, frame, tstride);
+		}
+		return true;
+	}
+	return false;
+}
+
 template <int NS, bool CTAB, bool OTHER>
 __device__ __forceinline__ void run_chunk_plan(const HotCtx &c,
 		float *row_s, float *row_r, const uint32_t frame) {
-	uint32_t rec = c.plan;
+	uint32_t rec = c.plan + PLAN_HDR - PLAN_REC;
 	for (;;) {
 		rec += PLAN_REC;
 		const uint4 p0 = lds128u(rec);
-		const uint32_t kind = p0.x & 0xffu, flags = (p0.x >> 8) & 0xffu;
 		/* the end mark (the second test only bounds the walk should a plan ever lack it) */
-		if (kind == P_STOP || rec - c.plan > PLAN_WALK_MAX) break;
-		const uint32_t bufa = (p0.x >> 16) & 0xffu, bufb = p0.x >> 24;
-		const uint32_t op = p0.z;
-		if (kind <= P_WOSC) {
-			/* LINE / WHEAD: one line evaluation into a buffer; WLEAF: the same, kept in
-			 * registers, then phase fill and oscillator; WTAIL: the frequency comes from
-			 * its buffer; PHASE / WOSC: the two halves of an operator whose amplitude has
-			 * modulators, with the phases parked in a buffer in between */
-			uint32_t ph[NS];
-			uint32_t inc = 0;
-			bool pure = false;
-			if (kind != P_WOSC) {
-				const bool is_line = kind == P_LINE;
-				const bool funi = (flags & PF_FUNI) != 0;
-				float fr[NS];
-				if (kind == P_WTAIL || kind == P_PHASE) {
-					if (funi) inc = lds32(rec + 24);
-					else fld<NS>(c, bufb, fr);
-				} else {
-					const uint32_t mb = is_line ? bufb : (p0.y >> 8) & 0xffu;
-					if (funi) {
-						const uint32_t w6 = lds32(rec + 24);
-						inc = w6;
-#pragma unroll
-						for (int k = 0; k < NS; ++k) fr[k] = __uint_as_float(w6);
-					} else if (!is_line && (flags & PF_FMUL)) {
-						/* a constant ratio to a modulated parent frequency (line.c:417-445, no goal) */
-						const float v0 = lds32f(rec + 24);
-						fld<NS>(c, mb, fr);
-#pragma unroll
-						for (int k = 0; k < NS; ++k) fr[k] = v0 * fr[k];
-					} else {
-						float m[NS];
-						const bool has_mul = mb != NO_BUF;
-						if (has_mul) fld<NS>(c, mb, m);
-						line_value_steady<NS>(c, op, is_line ? (int) ((p0.y >> 16) & 0xffu) : (int) LINE_FREQ,
-								has_mul ? m : nullptr, fr);
-					}
-					if (kind != P_WLEAF) { fst<NS>(c, is_line ? bufa : bufb, fr); continue; }
-				}
-				const uint32_t bufc = p0.y & 0xffu;
-				phase_plan<NS>(c, op, bufc, funi, inc, fr, ph);
-				if (kind == P_PHASE) {
-					float pf[NS];
-#pragma unroll
-					for (int k = 0; k < NS; ++k) pf[k] = __uint_as_float(ph[k]);
-					fst<NS>(c, bufa, pf);
-					continue;
-				}
-				pure = funi && bufc == NO_BUF;
-			} else {
-				float pf[NS];
-				fld<NS>(c, bufb, pf);
-#pragma unroll
-				for (int k = 0; k < NS; ++k) ph[k] = __float_as_uint(pf[k]);
-			}
-			osc_plan<NS, CTAB>(c, p0, rec, pure, inc, ph);
-			if (flags & PF_AEXT) rec += PLAN_REC;                  /* the record's second slot */
-		} else if (kind == P_RANGE) {                              /* generator.c:465-467 */
-			float p[NS], rr[NS], m[NS];
-			fld<NS>(c, p0.y & 0xffu, m);
-			if (flags & PF_FUNI) {             /* both ends uniform: scalars from the record */
-				const float2 pr = lds64f(rec + 24);
-#pragma unroll
-				for (int k = 0; k < NS; ++k) { p[k] = pr.x; rr[k] = pr.y; }
-			} else {
-				fld<NS>(c, bufa, p); fld<NS>(c, bufb, rr);
-			}
-#pragma unroll
-			for (int k = 0; k < NS; ++k) p[k] += (rr[k] - p[k]) * m[k];
-			fst<NS>(c, bufa, p);
-		} else if (kind != P_VOUT) {                               /* P_NOISE, P_CYCLE, P_RASG, P_MIX, P_WSELF */
-			if (OTHER) plan_other(c.sb, c.coeff, c.oc, rec, c.plan);
-			else plan_ff(kind, c.sb - c.lane * 16, c.lane, c.coeff, c.oc, op, p0.x, p0.y);
-		} else {                                                   /* P_VOUT, generator.c:772-786 */
-			float sv[NS];
-			fld<NS>(c, bufa, sv);
-			const float pan = lds32f(op + OS_LINE + 16 * LINE_PAN);
-			float s[NS], rv[NS];
-			const float amp_scale = lds32f(c.plan + PH_AMP_SCALE);
-			const uint32_t write_r = lds32(c.plan + PH_WRITE_R);
-			const uint32_t tstride = lds32(c.plan + PH_TSTRIDE);
-#pragma unroll
-			for (int k = 0; k < NS; ++k) { s[k] = sv[k] * amp_scale; rv[k] = s[k] * pan; }
-			/* row_s / row_r: this voice's piece of frame tile 0 (device_types.h:ROW_TILE) */
-			const uint32_t fl = frame + c.lane * NS;
-			if ((frame & 3u) == 0) {
-#pragma unroll
-				for (int h = 0; h < NS / 4; ++h) {                   /* 128-bit streaming stores */
-					const size_t at = row_index(fl + 4 * h, tstride);
-					__stcs(reinterpret_cast<float4*>(row_s + at),
-							make_float4(s[4 * h], s[4 * h + 1], s[4 * h + 2], s[4 * h + 3]));
-					if (write_r)
-						__stcs(reinterpret_cast<float4*>(row_r + at),
-								make_float4(rv[4 * h], rv[4 * h + 1], rv[4 * h + 2], rv[4 * h + 3]));
-				}
-			} else {
-				/* segment starting at an odd frame: rare, out of line through the buffers */
-				const uint32_t rb = bufb != NO_BUF ? bufb : bufa + 1u;
-				fst<NS>(c, bufa, s);
-				fst<NS>(c, rb, rv);
-				__syncwarp();
-				vout_unaligned(c.sb - c.lane * 16 + bufa * FastCfg<NS>::FBUF_BYTES,
-						c.sb - c.lane * 16 + rb * FastCfg<NS>::FBUF_BYTES,
-						row_s, row_r, c.lane, NS, write_r, frame, tstride);
-			}
-			return;
-		}
+		if ((p0.x & 0xffu) == P_STOP || rec - c.plan > PLAN_WALK_MAX) break;
+		if (plan_record_generic<NS, CTAB, OTHER>(c, rec, p0, row_s, row_r, frame)) return;
 	}
 }
 
@@ -1092,7 +1104,7 @@ __device__ __forceinline__ void run_chunk_plan(const HotCtx &c,
  * allocation whatever the general path around the call needs.  OTHER: the plan has
  * serial self-PM records (plan_other); feed-forward plans run in the other instance. */
 template <bool CTAB, bool OTHER>
-__device__ __noinline__ void run_block_fast(uint32_t sb, uint32_t plan, int lane, float coeff, uint32_t nrec,
+__device__ __noinline__ void run_block_fast(uint32_t sb, uint32_t plan, int lane, float coeff,
 		uint32_t len, float *row_s, float *row_r, uint32_t frame) {
 	HotCtx c;
 	c.sb = sb; c.plan = plan; c.lane = lane; c.coeff = coeff;

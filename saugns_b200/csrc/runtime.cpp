@@ -32,11 +32,11 @@
 
 namespace saugen {
 size_t render_smem_bytes(uint32_t wave_mask, uint32_t nbufs, uint32_t nslots_ops, uint32_t nplan,
-		uint32_t warps);
+		uint32_t warps, uint32_t team);
 cudaError_t launch_render(const CallDesc *d_calls, uint32_t ncalls, const SegDesc *d_segs,
 		const UnitDesc *d_units, uint32_t ntasks, const float *d_tables, const double *d_coefs,
 		uint32_t wave_mask, uint32_t nbufs, uint32_t nslots_ops, uint32_t nplan, uint32_t warps,
-		uint32_t ticketed_ctas, uint32_t sched_mode, cudaStream_t stream);
+		uint32_t ticketed_ctas, uint32_t sched_mode, uint32_t team, cudaStream_t stream);
 int render_ctas_per_sm(size_t smem, uint32_t warps);
 size_t coef_table_bytes();
 cudaError_t launch_coefs(const float *d_tables, double *d_coefs, uint32_t *d_inexact, cudaStream_t stream);
@@ -78,16 +78,24 @@ static std::map<std::pair<int, uint64_t>, TableBlock> g_tabs;
  * (tables edited in place at the same address get a new device copy). */
 struct TableSeen { int device; const void *addr; uint64_t fp; TableBlock blk; };
 static std::vector<TableSeen> g_tab_seen;
-/* every table value and coefficient, eight bytes per step (~10 us for the 96 KiB) */
+/* every table value and coefficient: four independent multiply-xor chains over 64-bit words
+ * (~10 us for the 96 KiB; a batch creates thousands of generators on the same tables) */
 static uint64_t table_fingerprint(const saugen_WaveTables *t) {
-	uint64_t h = 1469598103934665603ull;
-	auto mix = [&h](uint64_t v) { h = (h ^ v) * 0x9E3779B97F4A7C15ull; h ^= h >> 29; };
+	uint64_t h[4] = {1469598103934665603ull, 0x9E3779B97F4A7C15ull, 0xC2B2AE3D27D4EB4Full, 0x165667B19E3779F9ull};
 	for (int w = 0; w < NUM_WAVES; ++w) {
-		for (int i = 0; i < WAVE_LEN; i += 2) { uint64_t v; memcpy(&v, &t->pilut[w][i], 8); mix(v); }
+		const unsigned char *p = (const unsigned char*) t->pilut[w];
+		for (int i = 0; i < WAVE_LEN * 4; i += 32) {
+			uint64_t v[4];
+			memcpy(v, p + i, 32);
+			for (int k = 0; k < 4; ++k) h[k] = (h[k] ^ v[k]) * 0x9E3779B97F4A7C15ull + (h[k] >> 31);
+		}
 		uint32_t a, b; memcpy(&a, &t->amp_scale[w], 4); memcpy(&b, &t->amp_dc[w], 4);
-		mix(((uint64_t) a << 32) | b); mix((uint32_t) t->phase_adj[w]);
+		h[w & 3] = (h[w & 3] ^ (((uint64_t) a << 32) | b)) * 0x9E3779B97F4A7C15ull;
+		h[(w + 1) & 3] ^= (uint32_t) t->phase_adj[w] * 0x85EBCA6Bull;
 	}
-	return h;
+	uint64_t r = 0;
+	for (int k = 0; k < 4; ++k) { r = (r ^ h[k]) * 0xFF51AFD7ED558CCDull; r ^= r >> 33; }
+	return r;
 }
 
 static float *get_device_tables(int device, const saugen_WaveTables *t, double **coefs_out = nullptr) {
@@ -189,7 +197,7 @@ struct MemPool {
 		}
 		/* small classes come out of slabs: one cudaMalloc / cudaHostAlloc per SLAB bytes
 		 * instead of one per generator (pinned allocations cost about a millisecond) */
-		const size_t SLAB = host ? (size_t) 8 << 20 : (size_t) 128 << 20;
+		const size_t SLAB = host ? (size_t) 32 << 20 : (size_t) 128 << 20;
 		const size_t want = r <= SLAB / 4 ? SLAB / r * r : r;
 		void *p = nullptr;
 		cudaError_t e = host ? cudaHostAlloc(&p, want, cudaHostAllocPortable) : cudaMalloc(&p, want);
@@ -355,10 +363,38 @@ struct saugen_Generator {
 	SegDesc *h_segs = nullptr;
 	uint64_t counters[4] = {0, 0, 0, 0};
 	std::vector<SegDesc> segs_tmp;
+	/* One call in flight or just completed.  Two alternate: while the caller consumes call k,
+	 * call k + 1 may already be rendering (run-ahead, see saugen_run). */
+	struct CallSlot {
+		bool in_flight = false, timed = false;
+		size_t buf_len = 0, host_bytes = 0, gen_base = 0;
+		int stereo = 0;
+		uint32_t mode = 0, nseg = 0;
+		cudaEvent_t done = nullptr;
+		cudaEvent_t ev_t[3] = {nullptr, nullptr, nullptr};
+		uint32_t *h_status = nullptr;
+		int16_t *h_pcm = nullptr, *d_pcm = nullptr;
+		float *d_mix = nullptr;            /* float L / R planes (saugen_run_mix) + MIX_TAIL floats for the caller */
+		CallDesc *h_call = nullptr;        /* pinned staging of the call's descriptors ([call][segs][units]) */
+		SegDesc *h_segs = nullptr;
+		UnitDesc *h_units = nullptr;
+		size_t ev_after = 0;               /* next_event once this call was planned */
+	} slot[2];
+	int cur_slot = 0;                  /* the slot of the call returned last */
+	/* run-ahead: the next call, launched with the parameters of the last one before the caller
+	 * asks for it.  The operator / voice state and the host timeline of before it are kept
+	 * (d_snap, spec_*) so that it can be undone when the caller asks for something else. */
+	bool spec_valid = false;
+	int spec_slot = 0;
+	size_t spec_next_event = 0;
+	uint64_t spec_cur_time = 0;
+	void *d_snap = nullptr;
+	size_t state_bytes = 0;
+	int streak = 0;                    /* consecutive calls with the same parameters, no inspection between */
+	bool rows_stale = false;           /* the carrier rows hold a run-ahead call's, not the last returned call's */
 	/* device time of the two kernels, measured with events on the launch stream */
-	cudaEvent_t ev_t[3] = {nullptr, nullptr, nullptr};
 	double render_ms = 0.0, mix_ms = 0.0;
-	bool timing = false, timed_call = false;
+	bool timing = false;
 	size_t zero_bytes = 0, back_bytes_fixed = 0, units_off_in_call = 0;
 	bool compact = true;               /* [vlen..status] and [status][pcm] still adjacent (no growth yet) */
 	/* every block this generator took from the pool: (pointer, is pinned host) */
@@ -747,7 +783,7 @@ static bool flatten_program(const sauabi_Program *prg, uint32_t srate, Flat &f) 
 							default: fast = false; break;
 							}
 						}
-						np += 2;                           /* the plan's header slot and its end mark */
+						np += 3;                           /* the plan's two header slots and its end mark */
 						if (fast && np <= 64 && np > o->nplan) o->nplan = np;
 					}
 					prog_ops.insert(prog_ops.end(), comp.prog_ops.begin(), comp.prog_ops.end());
@@ -881,7 +917,13 @@ static saugen_Generator *create_from_flat(const Flat &f, const saugen_WaveTables
 		const size_t o_pcm = cv.take(2 * (size_t) o->row_len * sizeof(int16_t));
 		o->zero_bytes = o_pcm - o_vlen;
 		o->back_bytes_fixed = o_pcm - o_status;        /* status part of the read-back */
-		const size_t o_mix = cv.take(2 * (size_t) o->row_len * sizeof(float));
+		/* two sets of float planes (one per call slot), each followed by MIX_TAIL floats the
+		 * caller may use (multigpu.py folds its control words into the ONE reduced buffer) */
+		const size_t mix_floats = 2 * (size_t) o->row_len + SAUGEN_MIX_TAIL;
+		const size_t o_mix = cv.take(mix_floats * sizeof(float));
+		const size_t o_mix1 = cv.take(mix_floats * sizeof(float));
+		const size_t o_pcm1 = cv.take(2 * (size_t) o->row_len * sizeof(int16_t));      /* the alternate call slot's */
+		const size_t o_snap = cv.take(zero_bytes);                                      /* run-ahead: state before it */
 		/* written before every call with ONE copy: [call][segs][units] (same layout in
 		 * the pinned block) */
 		const size_t o_call = cv.take(sizeof(CallDesc));
@@ -898,6 +940,9 @@ static saugen_Generator *create_from_flat(const Flat &f, const saugen_WaveTables
 		o->d_progress = (uint32_t*) (base + o_progress); o->d_units = (UnitDesc*) (base + o_units);
 		o->d_mix = (float*) (base + o_mix); o->d_pcm = (int16_t*) (base + o_pcm);
 		o->d_call = (CallDesc*) (base + o_call); o->d_segs = (SegDesc*) (base + o_segs);
+		o->d_snap = base + o_snap; o->state_bytes = zero_bytes;
+		o->slot[0].d_pcm = o->d_pcm; o->slot[1].d_pcm = (int16_t*) (base + o_pcm1);
+		o->slot[0].d_mix = o->d_mix; o->slot[1].d_mix = (float*) (base + o_mix1);
 		const size_t ntile = ((size_t) o->row_len + ROW_TILE - 1) / ROW_TILE;
 		float *rows = (float*) o->take(false, 2 * ntile * (size_t) o->row_stride * sizeof(float));
 		if (!rows) { set_err("saugen_create: device memory (carrier rows)", cudaGetLastError()); goto fail; }
@@ -909,6 +954,12 @@ static saugen_Generator *create_from_flat(const Flat &f, const saugen_WaveTables
 		const size_t h_call = hv.take(sizeof(CallDesc));
 		const size_t h_segs = hv.take(o->seg_cap * sizeof(SegDesc));
 		const size_t h_units = hv.take(o->unit_cap * sizeof(UnitDesc));
+		const size_t h_status1 = hv.take((1 + o->seg_cap) * sizeof(uint32_t));
+		const size_t h_pcm1 = hv.take(2 * (size_t) o->row_len * sizeof(int16_t));
+		const size_t h_call1 = hv.take(sizeof(CallDesc));
+		const size_t h_segs1 = hv.take(o->seg_cap * sizeof(SegDesc));
+		const size_t h_units1 = hv.take(o->unit_cap * sizeof(UnitDesc));
+		if (h_units1 - h_call1 != o_units - o_call || h_segs1 - h_call1 != o_segs - o_call) o->compact = false;
 		if (h_pcm - h_status != o_pcm - o_status || h_units - h_call != o_units - o_call ||
 				h_segs - h_call != o_segs - o_call) o->compact = false;
 		unsigned char *hb = (unsigned char*) o->take(true, hv.off);
@@ -916,6 +967,11 @@ static saugen_Generator *create_from_flat(const Flat &f, const saugen_WaveTables
 		o->h_status = (uint32_t*) (hb + h_status); o->h_pcm = (int16_t*) (hb + h_pcm);
 		o->h_call = (CallDesc*) (hb + h_call); o->h_segs = (SegDesc*) (hb + h_segs);
 		o->h_units = (UnitDesc*) (hb + h_units);
+		o->slot[0].h_status = o->h_status; o->slot[0].h_pcm = o->h_pcm;
+		o->slot[1].h_status = (uint32_t*) (hb + h_status1); o->slot[1].h_pcm = (int16_t*) (hb + h_pcm1);
+		o->slot[0].h_call = o->h_call; o->slot[0].h_segs = o->h_segs; o->slot[0].h_units = o->h_units;
+		o->slot[1].h_call = (CallDesc*) (hb + h_call1); o->slot[1].h_segs = (SegDesc*) (hb + h_segs1);
+		o->slot[1].h_units = (UnitDesc*) (hb + h_units1);
 		lap(3);
 		lap(4);
 
@@ -1125,7 +1181,10 @@ extern "C" void saugen_destroy(saugen_Generator *o) {
 	cudaSetDevice(o->device);
 	if (o->stream) cudaStreamSynchronize(o->stream);
 	for (auto &b : o->blocks) g_pool.release(b.second, o->device, b.first);
-	for (int i = 0; i < 3; ++i) if (o->ev_t[i]) cudaEventDestroy(o->ev_t[i]);
+	for (auto &sl : o->slot) {
+		if (sl.done) cudaEventDestroy(sl.done);
+		for (int i = 0; i < 3; ++i) if (sl.ev_t[i]) cudaEventDestroy(sl.ev_t[i]);
+	}
 	if (o->own_stream && o->stream) g_streams.put(o->device, o->stream);
 	delete o;
 }
@@ -1207,40 +1266,60 @@ static void plan_units(const std::vector<SegDesc> &segs, std::vector<UnitDesc> &
  * wave) when the launch uses at most two waves, else the float tables (8 KiB
  * per wave in use). */
 static const uint32_t CTAB_FLAG = 0x80000000u;
-struct Shape { uint32_t warps; uint32_t mask; };
+struct Shape { uint32_t warps; uint32_t mask; uint32_t team; };
+/* team: with fewer voices than an SM has room for warps, every voice gets a TEAM of warps of
+ * its CTA that split steady stretches along time (render_team.cuh): as many members as fit,
+ * one named barrier per team (ids 1..15).  allow_team: not under the ticketed schedulers. */
 static Shape pick_shape(uint32_t ntasks, uint32_t wave_mask, uint32_t nbufs, uint32_t max_ops,
-		uint32_t nplan, bool have_coefs) {
+		uint32_t nplan, bool have_coefs, bool allow_team = true) {
 	const uint32_t sms = (uint32_t) device_sm_count();
 	const size_t SMEM_CAP = device_smem_optin();
 	int nw = 0;
 	for (uint32_t w = 0; w < NUM_WAVES; ++w) if (wave_mask & (1u << w)) ++nw;
 	static const char *env = getenv("SAUGEN_CTAB");       /* developer knob: 0 = off */
-	const bool want_ctab = have_coefs && nw >= 1 && nw <= 2 && !(env && env[0] == '0');
+	static const char *tenv = getenv("SAUGEN_TEAM");      /* developer knob: 0 = off, n = at most n members */
+	/* coefficient planes (48 KiB per wave): two waves leave room for a full CTA of voices; with few
+	 * voices (fewer warps) up to four waves' planes fit beside them */
+	const bool want_ctab = have_coefs && nw >= 1 && nw <= 4 && !(env && env[0] == '0');
 	Shape sh;
+	sh.team = 1;
 	for (int pass = want_ctab ? 0 : 1; pass < 2; ++pass) {
 		sh.mask = pass == 0 ? (wave_mask | CTAB_FLAG) : wave_mask;
 		uint32_t fit = 28;                 /* kernels.cu:WIDE_WARPS */
-		while (fit > 1 && render_smem_bytes(sh.mask, nbufs, max_ops, nplan, fit) > SMEM_CAP) --fit;
+		while (fit > 1 && render_smem_bytes(sh.mask, nbufs, max_ops, nplan, fit, 1) > SMEM_CAP) --fit;
 		sh.warps = (ntasks + sms - 1) / sms;
 		if (sh.warps < 1) sh.warps = 1;
 		if (sh.warps > fit) sh.warps = fit;
-		if (render_smem_bytes(sh.mask, nbufs, max_ops, nplan, sh.warps) <= SMEM_CAP && (pass == 1 || fit >= 8))
+		if (render_smem_bytes(sh.mask, nbufs, max_ops, nplan, sh.warps, 1) <= SMEM_CAP &&
+				(pass == 1 || fit >= 8) && (pass == 1 || nw <= 2 || fit >= (ntasks + sms - 1) / sms)) {
+			/* (teams split lowered plans: coefficient-plane launches only) */
+			const uint32_t per_cta = sh.warps;             /* voices per CTA */
+			if (allow_team && pass == 0 && nplan && per_cta <= 14 && ntasks <= per_cta * sms &&
+					!(tenv && tenv[0] == '0')) {
+				uint32_t t = 28 / per_cta;
+				if (tenv && atoi(tenv) > 0 && (uint32_t) atoi(tenv) < t) t = (uint32_t) atoi(tenv);
+				while (t > 1 && render_smem_bytes(sh.mask, nbufs, max_ops, nplan, per_cta * t, t) > SMEM_CAP) --t;
+				if (t > 1) { sh.team = t; sh.warps = per_cta * t; }
+			}
 			return sh;
+		}
 	}
 	/* not even one warp of this voice program fits the SM's shared memory */
-	if (render_smem_bytes(sh.mask, nbufs, max_ops, nplan, sh.warps) > SMEM_CAP) sh.warps = 0;
+	if (render_smem_bytes(sh.mask, nbufs, max_ops, nplan, sh.warps, 1) > SMEM_CAP) sh.warps = 0;
 	return sh;
 }
 
 /* mode: 0 = PCM in device memory, 1 = float planes */
-static cudaError_t read_back(saugen_Generator *o, uint32_t nseg, size_t host_pcm_bytes, cudaStream_t st) {
-	if (o->compact && host_pcm_bytes)      /* [status][pcm] in one copy */
-		return cudaMemcpyAsync(o->h_status, o->d_status, o->back_bytes_fixed + host_pcm_bytes,
+static cudaError_t read_back(saugen_Generator *o, uint32_t nseg, size_t host_pcm_bytes, cudaStream_t st,
+		int si = 0) {
+	saugen_Generator::CallSlot &sl = o->slot[si];
+	if (si == 0 && o->compact && host_pcm_bytes)      /* [status][pcm] in one copy */
+		return cudaMemcpyAsync(sl.h_status, o->d_status, o->back_bytes_fixed + host_pcm_bytes,
 				cudaMemcpyDeviceToHost, st);
-	cudaError_t e = cudaMemcpyAsync(o->h_status, o->d_status, (1 + nseg) * sizeof(uint32_t),
+	cudaError_t e = cudaMemcpyAsync(sl.h_status, o->d_status, (1 + nseg) * sizeof(uint32_t),
 			cudaMemcpyDeviceToHost, st);
 	if (e == cudaSuccess && host_pcm_bytes)
-		e = cudaMemcpyAsync(o->h_pcm, o->d_pcm, host_pcm_bytes, cudaMemcpyDeviceToHost, st);
+		e = cudaMemcpyAsync(sl.h_pcm, sl.d_pcm, host_pcm_bytes, cudaMemcpyDeviceToHost, st);
 	return e;
 }
 
@@ -1257,7 +1336,12 @@ static bool ensure_seg_cap(saugen_Generator *o, size_t n) {
 	o->d_segs = (SegDesc*) o->take(false, cap * sizeof(SegDesc));
 	o->h_status = (uint32_t*) o->take(true, (1 + cap) * sizeof(uint32_t));
 	o->h_segs = (SegDesc*) o->take(true, cap * sizeof(SegDesc));
-	if (!o->d_vlen || !o->d_status || !o->d_segs || !o->h_status || !o->h_segs) {
+	o->slot[0].h_status = o->h_status;
+	o->slot[1].h_status = (uint32_t*) o->take(true, (1 + cap) * sizeof(uint32_t));
+	o->slot[0].h_segs = o->h_segs;
+	o->slot[1].h_segs = (SegDesc*) o->take(true, cap * sizeof(SegDesc));
+	if (!o->d_vlen || !o->d_status || !o->d_segs || !o->h_status || !o->h_segs || !o->slot[1].h_status ||
+			!o->slot[1].h_segs) {
 		set_err("saugen_run: segment table growth", cudaGetLastError());
 		return false;
 	}
@@ -1267,28 +1351,25 @@ static bool ensure_seg_cap(saugen_Generator *o, size_t n) {
 	return cudaMemcpy(o->d_desc, &o->h_desc, sizeof(GenDesc), cudaMemcpyHostToDevice) == cudaSuccess;
 }
 
-/* host_pcm_bytes: PCM bytes to bring to the pinned staging buffer (0 = none) */
-static int run_common(saugen_Generator *o, size_t buf_len, int stereo, uint32_t mode,
-		size_t *out_len, int *more_out, size_t host_pcm_bytes = 0) {
-	if (!o) return -1;
-	if (buf_len > o->row_len) { g_err = "saugen_run: buf_len exceeds max_call_len"; return -1; }
-	cudaSetDevice(o->device);
-	if (o->ended) {
-		cudaMemsetAsync(o->d_pcm, 0, 2 * (size_t) o->row_len * sizeof(int16_t), o->stream);
-		if (out_len) *out_len = 0;
-		*more_out = 0;
-		return 0;
-	}
+/* Plans and launches one call into slot `si` (kernels + read-back queued on the generator's
+ * stream, an event recorded after them); nothing waits.  host_pcm_bytes: PCM bytes to bring to
+ * the slot's pinned staging buffer (0 = none).  <0 on error. */
+static int launch_call(saugen_Generator *o, int si, size_t buf_len, int stereo, uint32_t mode,
+		size_t host_pcm_bytes) {
+	saugen_Generator::CallSlot &sl = o->slot[si];
+	size_t *out_len = nullptr;
 	std::vector<SegDesc> &segs = o->segs_tmp;
 	plan_call(o, (uint32_t) buf_len, segs);
 	if (!ensure_seg_cap(o, segs.size())) { if (out_len) *out_len = 0; return -1; }
 	const uint32_t nseg = (uint32_t) segs.size();
-	memcpy(o->h_segs, segs.data(), nseg * sizeof(SegDesc));
+	sl.ev_after = o->next_event;
+	memcpy(sl.h_segs, segs.data(), nseg * sizeof(SegDesc));
 	/* Launch shape and scheduling.  sched: 0 = auto, 1 = one warp per voice, 2 =
 	 * persistent grid with (unit, voice) tickets, 3 = balanced contiguous ranges.
 	 * Auto picks balanced when the voices would otherwise need a second, partly
 	 * filled wave of warps (between 1 and 4 waves), else one warp per voice. */
-	const Shape shape = pick_shape(o->nlv, o->wave_mask, o->nbufs, o->max_ops, o->nplan, o->d_coefs != nullptr);
+	Shape shape = pick_shape(o->nlv, o->wave_mask, o->nbufs, o->max_ops, o->nplan, o->d_coefs != nullptr,
+			o->sched == 0 || o->sched == 1);
 	const uint32_t warps = shape.warps;
 	if (!warps) {
 		g_err = "saugen_run: a voice program of this script needs more shared memory than one SM has";
@@ -1298,11 +1379,11 @@ static int run_common(saugen_Generator *o, size_t buf_len, int stereo, uint32_t 
 	}
 	uint32_t ticketed_ctas = 0, sched_mode = 0;
 	{
-		const size_t smem = render_smem_bytes(shape.mask, o->nbufs, o->max_ops, o->nplan, warps);
+		const size_t smem = render_smem_bytes(shape.mask, o->nbufs, o->max_ops, o->nplan, warps, shape.team);
 		int per_sm = render_ctas_per_sm(smem, warps);
 		if (per_sm < 1) per_sm = 1;
 		const uint32_t resident_ctas = (uint32_t) device_sm_count() * (uint32_t) per_sm;
-		const uint32_t need = (o->nlv + warps - 1) / warps;
+		const uint32_t need = (o->nlv + warps / shape.team - 1) / (warps / shape.team);
 		uint32_t sched = o->sched;
 		if (sched == 0)
 			sched = need > resident_ctas ? 3 : 1;        /* more than one wave: balanced ranges */
@@ -1348,7 +1429,9 @@ static int run_common(saugen_Generator *o, size_t buf_len, int stereo, uint32_t 
 		cudaStreamSynchronize(o->stream);
 		o->d_units = (UnitDesc*) o->take(false, cap * sizeof(UnitDesc));
 		o->h_units = (UnitDesc*) o->take(true, cap * sizeof(UnitDesc));
-		if (!o->d_units || !o->h_units) {
+		o->slot[0].h_units = o->h_units;
+		o->slot[1].h_units = (UnitDesc*) o->take(true, cap * sizeof(UnitDesc));
+		if (!o->d_units || !o->h_units || !o->slot[1].h_units) {
 			set_err("saugen_run: unit table growth", cudaGetLastError());
 			return -1;
 		}
@@ -1356,7 +1439,7 @@ static int run_common(saugen_Generator *o, size_t buf_len, int stereo, uint32_t 
 		o->compact = false;
 	}
 	const uint32_t nunits = (uint32_t) o->units_tmp.size();
-	memcpy(o->h_units, o->units_tmp.data(), nunits * sizeof(UnitDesc));
+	memcpy(sl.h_units, o->units_tmp.data(), nunits * sizeof(UnitDesc));
 	/* render launches of this call: one, or one per hand-over cut (plan_call) */
 	std::vector<uint32_t> gunit;              /* first unit of every launch, then nunits */
 	gunit.push_back(0);
@@ -1365,26 +1448,30 @@ static int run_common(saugen_Generator *o, size_t buf_len, int stereo, uint32_t 
 			if (o->units_tmp[u].seg >= gs) { if (u > gunit.back()) gunit.push_back(u); break; }
 	gunit.push_back(nunits);
 	const size_t ngroups = gunit.size() - 1;
-	CallDesc &cd = *o->h_call;
+	CallDesc &cd = *sl.h_call;
 	cd.gen = o->d_desc; cd.call_len = (uint32_t) buf_len; cd.nseg = nseg; cd.seg_off = 0;
 	cd.task_base = 0; cd.stereo = (stereo ? 1u : 0u) | (o->big_endian ? 2u : 0u);
 	cd.unit_off = 0; cd.nunits = gunit[1]; cd.more_launches = ngroups > 1 ? 1u : 0u;
+	cd.pcm = mode == 1 ? (int16_t*) sl.d_mix : sl.d_pcm;      /* (float planes in mode 1) */
 	cudaError_t e;
 	if (o->compact) {
 		/* one copy in ([call][segs][units]), one memset ([vlen][progress][status]) */
-		e = cudaMemcpyAsync(o->d_call, o->h_call, o->units_off_in_call + nunits * sizeof(UnitDesc),
+		e = cudaMemcpyAsync(o->d_call, sl.h_call, o->units_off_in_call + nunits * sizeof(UnitDesc),
 				cudaMemcpyHostToDevice, o->stream);
 		if (e == cudaSuccess) e = cudaMemsetAsync(o->d_vlen, 0, o->zero_bytes, o->stream);
 	} else {
-		e = cudaMemcpyAsync(o->d_segs, o->h_segs, nseg * sizeof(SegDesc), cudaMemcpyHostToDevice, o->stream);
-		if (e == cudaSuccess) e = cudaMemcpyAsync(o->d_units, o->h_units, nunits * sizeof(UnitDesc), cudaMemcpyHostToDevice, o->stream);
+		e = cudaMemcpyAsync(o->d_segs, sl.h_segs, nseg * sizeof(SegDesc), cudaMemcpyHostToDevice, o->stream);
+		if (e == cudaSuccess) e = cudaMemcpyAsync(o->d_units, sl.h_units, nunits * sizeof(UnitDesc), cudaMemcpyHostToDevice, o->stream);
 		if (e == cudaSuccess) e = cudaMemsetAsync(o->d_vlen, 0, (size_t) nseg * (o->nlv ? o->nlv : 1) * sizeof(VoiceSeg), o->stream);
 		if (e == cudaSuccess && ticketed_ctas) e = cudaMemsetAsync(o->d_progress, 0, ((size_t) o->nlv + 1) * sizeof(uint32_t), o->stream);
-		if (e == cudaSuccess) e = cudaMemcpyAsync(o->d_call, o->h_call, sizeof(CallDesc), cudaMemcpyHostToDevice, o->stream);
+		if (e == cudaSuccess) e = cudaMemcpyAsync(o->d_call, sl.h_call, sizeof(CallDesc), cudaMemcpyHostToDevice, o->stream);
 		if (e == cudaSuccess) e = cudaMemsetAsync(o->d_status, 0, (1 + nseg) * sizeof(uint32_t), o->stream);
 	}
-	o->timed_call = o->timing;
-	if (e == cudaSuccess && o->timed_call) e = cudaEventRecord(o->ev_t[0], o->stream);
+	sl.timed = o->timing;
+	if (sl.timed && !sl.ev_t[0])
+		for (int i = 0; i < 3 && e == cudaSuccess; ++i) e = cudaEventCreate(&sl.ev_t[i]);
+	if (!sl.done && e == cudaSuccess) e = cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming);
+	if (e == cudaSuccess && sl.timed) e = cudaEventRecord(sl.ev_t[0], o->stream);
 	for (size_t gi = 0; gi < ngroups && e == cudaSuccess; ++gi) {
 		if (gi > 0) {
 			/* the next launch's unit range (pageable source: staged before the call returns) */
@@ -1397,7 +1484,7 @@ static int run_common(saugen_Generator *o, size_t buf_len, int stereo, uint32_t 
 			if (e != cudaSuccess) break;
 		}
 		e = launch_render(o->d_call, 1, o->d_segs, o->d_units, o->nlv, o->d_tables, o->d_coefs,
-				shape.mask, o->nbufs, o->max_ops, o->nplan, warps, ticketed_ctas, sched_mode, o->stream);
+				shape.mask, o->nbufs, o->max_ops, o->nplan, warps, ticketed_ctas, sched_mode, shape.team, o->stream);
 		o->counters[0]++;
 	}
 	if (e == cudaSuccess && ngroups > 1) {
@@ -1406,75 +1493,177 @@ static int run_common(saugen_Generator *o, size_t buf_len, int stereo, uint32_t 
 		all.nunits = nunits; all.more_launches = 0;
 		e = cudaMemcpyAsync(o->d_call, &all, sizeof(CallDesc), cudaMemcpyHostToDevice, o->stream);
 	}
-	if (e == cudaSuccess && o->timed_call) e = cudaEventRecord(o->ev_t[1], o->stream);
+	if (e == cudaSuccess && sl.timed) e = cudaEventRecord(sl.ev_t[1], o->stream);
 	if (e == cudaSuccess) {
 		e = launch_mix(o->d_call, 1, o->d_segs, (uint32_t) buf_len, mode, o->stream);
 		o->counters[1]++;
 	}
-	if (e == cudaSuccess && o->timed_call) e = cudaEventRecord(o->ev_t[2], o->stream);
-	if (e == cudaSuccess) e = read_back(o, nseg, host_pcm_bytes, o->stream);
-	if (e != cudaSuccess) { set_err("saugen_run: launch", e); if (out_len) *out_len = 0; return -1; }
-	(void) more_out;
-	return 1;   /* caller finishes after its own D2H + sync via finish_call */
+	if (e == cudaSuccess && sl.timed) e = cudaEventRecord(sl.ev_t[2], o->stream);
+	if (e == cudaSuccess) e = read_back(o, nseg, host_pcm_bytes, o->stream, si);
+	if (e == cudaSuccess) e = cudaEventRecord(sl.done, o->stream);
+	if (e != cudaSuccess) { set_err("saugen_run: launch", e); return -1; }
+	sl.in_flight = true;
+	sl.buf_len = buf_len; sl.stereo = stereo; sl.mode = mode; sl.host_bytes = host_pcm_bytes;
+	sl.nseg = nseg;
+	sl.gen_base = 0;
+	for (uint32_t q = 0; q + 1 < nseg; ++q) sl.gen_base += segs[q].len;
+	return 1;
 }
 
-/* After the stream is synchronised: out_len / return value (generator.c:938-972). */
-static int finish_call(saugen_Generator *o, size_t buf_len, size_t *out_len) {
-	const uint32_t nseg = (uint32_t) o->segs_tmp.size();
-	if (o->timed_call) {
+/* After the slot's call has completed: out_len / return value (generator.c:938-972). */
+static int finish_call(saugen_Generator *o, int si, size_t *out_len) {
+	saugen_Generator::CallSlot &sl = o->slot[si];
+	sl.in_flight = false;
+	if (sl.timed) {
 		float a = 0.f, b = 0.f;
-		if (cudaEventElapsedTime(&a, o->ev_t[0], o->ev_t[1]) == cudaSuccess) o->render_ms += a;
-		if (cudaEventElapsedTime(&b, o->ev_t[1], o->ev_t[2]) == cudaSuccess) o->mix_ms += b;
-		o->timed_call = false;
+		if (cudaEventElapsedTime(&a, sl.ev_t[0], sl.ev_t[1]) == cudaSuccess) o->render_ms += a;
+		if (cudaEventElapsedTime(&b, sl.ev_t[1], sl.ev_t[2]) == cudaSuccess) o->mix_ms += b;
+		sl.timed = false;
 	}
-	size_t gen_len = 0;
-	for (uint32_t s = 0; s + 1 < nseg; ++s) gen_len += o->segs_tmp[s].len;
-	if (nseg) gen_len += o->h_status[1 + (nseg - 1)];
-	const bool alive = o->h_status[0] != 0;
-	const bool more = alive || o->next_event < o->ev_time.size();
+	size_t gen_len = sl.gen_base;
+	if (sl.nseg) gen_len += sl.h_status[1 + (sl.nseg - 1)];
+	const bool alive = sl.h_status[0] != 0;
+	const bool more = alive || sl.ev_after < o->ev_time.size();
 	if (!more) {
 		o->ended = true;
 		if (out_len) *out_len = gen_len;
 		return 0;
 	}
-	if (out_len) *out_len = buf_len;
+	if (out_len) *out_len = sl.buf_len;
+	return 1;
+}
+
+/* Undo a run-ahead call the caller did not ask for: wait for it, put the operator / voice state
+ * and the host timeline back to where the last returned call left them. */
+static void cancel_runahead(saugen_Generator *o) {
+	if (!o->spec_valid) return;
+	saugen_Generator::CallSlot &sl = o->slot[o->spec_slot];
+	cudaEventSynchronize(sl.done);
+	sl.in_flight = false; sl.timed = false;
+	cudaMemcpyAsync(o->d_ops, o->d_snap, o->state_bytes, cudaMemcpyDeviceToDevice, o->stream);
+	o->next_event = o->spec_next_event;
+	o->cur_time = o->spec_cur_time;
+	o->spec_valid = false;
+	o->streak = -1;
+	o->rows_stale = true;          /* the rows are the undone call's */
+}
+
+/* The generator's state as of the last RETURNED call: the live arrays, or the copy made before
+ * a run-ahead call started on them. */
+static const unsigned char *state_base(saugen_Generator *o) {
+	return (const unsigned char*) (o->spec_valid ? o->d_snap : o->d_ops);
+}
+
+static bool runahead_enabled() {
+	static const char *env = getenv("SAUGEN_RUNAHEAD");       /* 0 = off */
+	return !(env && env[0] == '0');
+}
+
+/* sauGenerator_run's driver.  The call the caller asks for is either already in flight (the
+ * run-ahead of the previous call: same length, channels and mode) or launched now; after it has
+ * completed and while the caller consumes its PCM, the NEXT call is launched with the same
+ * parameters (a player calls with one buffer size until the end, saugns.c:601-609), so the GPU
+ * never waits for the host between calls.  Run-ahead starts once two
+ * consecutive calls had the same parameters with no state inspection in between, and never
+ * past the end of the signal.  Returns <0 error, 0 ended before this call, else 1 with *slot. */
+static int run_call(saugen_Generator *o, size_t buf_len, int stereo, uint32_t mode, size_t host_bytes,
+		int *slot_out, size_t *out_len, int *more_out) {
+	if (!o) return -1;
+	if (buf_len > o->row_len) { g_err = "saugen_run: buf_len exceeds max_call_len"; return -1; }
+	cudaSetDevice(o->device);
+	int si;
+	if (o->spec_valid) {
+		saugen_Generator::CallSlot &sp = o->slot[o->spec_slot];
+		if (sp.buf_len == buf_len && sp.stereo == stereo && sp.mode == mode && sp.host_bytes == host_bytes) {
+			si = o->spec_slot;
+			o->spec_valid = false;
+			o->rows_stale = false;
+		} else {
+			cancel_runahead(o);
+			si = -1;
+		}
+	} else {
+		si = -1;
+	}
+	if (si < 0) {
+		if (o->ended) {
+			cudaMemsetAsync(o->slot[o->cur_slot].d_pcm, 0, 2 * (size_t) o->row_len * sizeof(int16_t), o->stream);
+			if (out_len) *out_len = 0;
+			*more_out = 0;
+			*slot_out = o->cur_slot;
+			return 0;
+		}
+		const saugen_Generator::CallSlot &last = o->slot[o->cur_slot];
+		o->streak = (last.buf_len == buf_len && last.stereo == stereo && last.mode == mode &&
+				last.host_bytes == host_bytes) ? o->streak + 1 : 0;
+		si = o->cur_slot ^ 1;
+		if (launch_call(o, si, buf_len, stereo, mode, host_bytes) < 0) { if (out_len) *out_len = 0; return -1; }
+		o->rows_stale = false;
+	} else {
+		o->streak++;
+	}
+	saugen_Generator::CallSlot &sl = o->slot[si];
+	/* the call after this one goes out BEFORE this one is waited for: its state snapshot and
+	 * its kernels queue up behind this call's on the stream, so the GPU runs on while the host
+	 * finishes this call (should this call turn out to be the last, the extra one is undone) */
+	if (o->streak >= 1 && runahead_enabled() &&
+			cudaMemcpyAsync(o->d_snap, o->d_ops, o->state_bytes, cudaMemcpyDeviceToDevice, o->stream) == cudaSuccess) {
+		o->spec_next_event = o->next_event;
+		o->spec_cur_time = o->cur_time;
+		if (launch_call(o, si ^ 1, buf_len, stereo, mode, host_bytes) >= 0) {
+			o->spec_valid = true;
+			o->spec_slot = si ^ 1;
+			o->rows_stale = true;
+		} else {
+			o->next_event = o->spec_next_event;
+			o->cur_time = o->spec_cur_time;
+		}
+	}
+	cudaError_t e = cudaEventSynchronize(sl.done);
+	if (e != cudaSuccess) { set_err("saugen_run", e); if (out_len) *out_len = 0; return -1; }
+	o->cur_slot = si;
+	*slot_out = si;
+	const int more = finish_call(o, si, out_len);
+	*more_out = more;
+	if (!more && o->spec_valid) {
+		cancel_runahead(o);
+		o->ended = true;
+	}
 	return 1;
 }
 
 extern "C" int saugen_run(saugen_Generator *o, int16_t *buf, size_t buf_len, int stereo,
 		size_t *out_len) {
-	int more = 0;
+	int more = 0, si = 0;
 	const size_t bytes = buf_len * (stereo ? 2 : 1) * sizeof(int16_t);
-	int r = run_common(o, buf_len, stereo, 0, out_len, &more, bytes);
+	int r = run_call(o, buf_len, stereo, 0, bytes, &si, out_len, &more);
 	if (r < 0) return r;
 	if (r == 0) { if (buf) memset(buf, 0, bytes); return 0; }
-	cudaError_t e = cudaStreamSynchronize(o->stream);
-	if (e != cudaSuccess) { set_err("saugen_run", e); if (out_len) *out_len = 0; return -1; }
-	if (buf) memcpy(buf, o->h_pcm, bytes);
-	return finish_call(o, buf_len, out_len);
+	if (buf) memcpy(buf, o->slot[si].h_pcm, bytes);
+	return more;
 }
 
 extern "C" int saugen_run_device(saugen_Generator *o, size_t buf_len, int stereo,
 		int16_t **dev_pcm, size_t *out_len) {
-	int more = 0;
-	int r = run_common(o, buf_len, stereo, 0, out_len, &more);
+	int more = 0, si = 0;
+	int r = run_call(o, buf_len, stereo, 0, 0, &si, out_len, &more);
 	if (r < 0) return r;
-	if (dev_pcm) *dev_pcm = o->d_pcm;
-	if (r == 0) return 0;
-	cudaError_t e = cudaStreamSynchronize(o->stream);
-	if (e != cudaSuccess) { set_err("saugen_run_device", e); if (out_len) *out_len = 0; return -1; }
-	return finish_call(o, buf_len, out_len);
+	if (dev_pcm) *dev_pcm = o->slot[si].d_pcm;
+	if (r == 0) { cudaStreamSynchronize(o->stream); return 0; }
+	return more;
 }
 
 extern "C" int saugen_run_mix(saugen_Generator *o, size_t buf_len, float **dev_mix, size_t *out_len) {
-	int more = 0;
-	int r = run_common(o, buf_len, 1, 1, out_len, &more);
+	int more = 0, si = 0;
+	int r = run_call(o, buf_len, 1, 1, 0, &si, out_len, &more);
 	if (r < 0) return r;
-	if (dev_mix) *dev_mix = o->d_mix;
-	if (r == 0) { cudaMemsetAsync(o->d_mix, 0, 2 * (size_t) o->row_len * sizeof(float), o->stream); cudaStreamSynchronize(o->stream); return 0; }
-	cudaError_t e = cudaStreamSynchronize(o->stream);
-	if (e != cudaSuccess) { set_err("saugen_run_mix", e); if (out_len) *out_len = 0; return -1; }
-	return finish_call(o, buf_len, out_len);
+	if (dev_mix) *dev_mix = o->slot[si].d_mix;
+	if (r == 0) {
+		cudaMemsetAsync(o->slot[si].d_mix, 0, 2 * (size_t) o->row_len * sizeof(float), o->stream);
+		cudaStreamSynchronize(o->stream);
+		return 0;
+	}
+	return more;
 }
 
 extern "C" int saugen_mix_to_pcm(saugen_Generator *o, const float *dev_mix, size_t buf_len,
@@ -1574,6 +1763,7 @@ extern "C" int saugen_batch_begin(saugen_Batch *b, saugen_Generator *const *gens
 	}
 	for (size_t i = 0; i < n; ++i) {
 		saugen_Generator *o = gens[i];
+		if (o) cancel_runahead(o);
 		if (o && o->ended && b->bufs[i]) memset(b->bufs[i], 0, b->bytes);   /* as saugen_run does */
 		if (!o || o->ended) continue;
 		plan_call(o, (uint32_t) buf_len, o->segs_tmp);
@@ -1582,6 +1772,14 @@ extern "C" int saugen_batch_begin(saugen_Batch *b, saugen_Generator *const *gens
 		cd.gen = o->d_desc; cd.call_len = (uint32_t) buf_len; cd.nseg = (uint32_t) o->segs_tmp.size();
 		cd.seg_off = (uint32_t) b->segs.size(); cd.task_base = ntasks;
 		cd.stereo = (stereo ? 1u : 0u) | (o->big_endian ? 2u : 0u); cd.more_launches = 0;
+		cd.pcm = o->d_pcm;
+		{
+			saugen_Generator::CallSlot &sl = o->slot[0];
+			sl.buf_len = buf_len; sl.stereo = stereo; sl.mode = 0; sl.host_bytes = b->bytes;
+			sl.nseg = cd.nseg; sl.gen_base = 0; sl.timed = false; sl.ev_after = o->next_event;
+			for (uint32_t q = 0; q + 1 < cd.nseg; ++q) sl.gen_base += o->segs_tmp[q].len;
+			o->cur_slot = 0; o->streak = 0;
+		}
 		plan_units(o->segs_tmp, o->units_tmp, 1u << 20);
 		cd.unit_off = (uint32_t) b->units.size(); cd.nunits = (uint32_t) o->units_tmp.size();
 		b->units.insert(b->units.end(), o->units_tmp.begin(), o->units_tmp.end());
@@ -1650,13 +1848,17 @@ extern "C" int saugen_batch_begin(saugen_Batch *b, saugen_Generator *const *gens
 		}
 	}
 	if (e == cudaSuccess) e = cudaMemcpyAsync(b->d_segs, b->segs.data(), b->segs.size() * sizeof(SegDesc), cudaMemcpyHostToDevice, st);
-	g0->timed_call = g0->timing;       /* kernel times of the batch accumulate on the first generator */
-	if (e == cudaSuccess && g0->timed_call) e = cudaEventRecord(g0->ev_t[0], st);
+	/* kernel times of the batch accumulate on the first generator */
+	saugen_Generator::CallSlot &t0 = g0->slot[0];
+	t0.timed = g0->timing;
+	if (t0.timed && !t0.ev_t[0])
+		for (int i = 0; i < 3 && e == cudaSuccess; ++i) e = cudaEventCreate(&t0.ev_t[i]);
+	if (e == cudaSuccess && t0.timed) e = cudaEventRecord(t0.ev_t[0], st);
 	if (e == cudaSuccess) {
 		const Shape shape = pick_shape(ntasks, wave_mask, nbufs, max_ops, nplan, g0->d_coefs != nullptr);
 		if (!shape.warps) e = cudaErrorInvalidConfiguration;
 		else e = launch_render(b->d_calls, (uint32_t) b->calls.size(), b->d_segs, b->d_units, ntasks, g0->d_tables,
-				g0->d_coefs, shape.mask, nbufs, max_ops, nplan, shape.warps, 0, 0, st);
+				g0->d_coefs, shape.mask, nbufs, max_ops, nplan, shape.warps, 0, 0, shape.team, st);
 		g0->counters[0]++;
 		size_t at = b->calls.size();
 		for (auto &r : later) {
@@ -1665,17 +1867,17 @@ extern "C" int saugen_batch_begin(saugen_Batch *b, saugen_Generator *const *gens
 				for (const CallDesc &c : r) if (b->calls[k].gen == c.gen) nt += gens[b->call_of[k]]->nlv;
 			if (e == cudaSuccess && shape.warps)
 				e = launch_render(b->d_calls + at, (uint32_t) r.size(), b->d_segs, b->d_units, nt, g0->d_tables,
-						g0->d_coefs, shape.mask, nbufs, max_ops, nplan, shape.warps, 0, 0, st);
+						g0->d_coefs, shape.mask, nbufs, max_ops, nplan, shape.warps, 0, 0, shape.team, st);
 			g0->counters[0]++;
 			at += r.size();
 		}
 	}
-	if (e == cudaSuccess && g0->timed_call) e = cudaEventRecord(g0->ev_t[1], st);
+	if (e == cudaSuccess && t0.timed) e = cudaEventRecord(t0.ev_t[1], st);
 	if (e == cudaSuccess) {
 		e = launch_mix(b->d_calls, (uint32_t) b->calls.size(), b->d_segs, (uint32_t) buf_len, 0, st);
 		g0->counters[1]++;
 	}
-	if (e == cudaSuccess && g0->timed_call) e = cudaEventRecord(g0->ev_t[2], st);
+	if (e == cudaSuccess && t0.timed) e = cudaEventRecord(t0.ev_t[2], st);
 	for (size_t c = 0; c < b->calls.size() && e == cudaSuccess; ++c) {
 		const size_t i = b->call_of[c];
 		saugen_Generator *o = gens[i];
@@ -1731,7 +1933,7 @@ extern "C" int saugen_batch_end(saugen_Batch *b, size_t *out_lens, int *more) {
 	for (size_t c = 0; c < b->calls.size(); ++c) {
 		const size_t i = b->call_of[c];
 		size_t ol = 0;
-		int m = finish_call(b->gens[i], b->buf_len, &ol);
+		int m = finish_call(b->gens[i], 0, &ol);
 		if (out_lens) out_lens[i] = ol;
 		if (more) more[i] = m;
 		any |= m;
@@ -1771,7 +1973,8 @@ extern "C" int saugen_read_op(saugen_Generator *o, uint32_t op_id, saugen_OpView
 	cudaSetDevice(o->device);
 	OpState s;
 	cudaStreamSynchronize(o->stream);
-	if (cudaMemcpy(&s, (OpState*) o->d_ops + op_id, sizeof s, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+	o->streak = -1;                 /* inspected: not a streaming caller */
+	if (cudaMemcpy(&s, (const OpState*) state_base(o) + op_id, sizeof s, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
 	memset(out, 0, sizeof *out);
 	out->inited = (s.flags & ON_INIT) != 0;
 	if (!out->inited) return 0;
@@ -1802,7 +2005,9 @@ extern "C" int saugen_read_voice(saugen_Generator *o, uint32_t vo_id, uint32_t o
 	cudaSetDevice(o->device);
 	VoiceState s;
 	cudaStreamSynchronize(o->stream);
-	if (cudaMemcpy(&s, (VoiceState*) o->d_voices + vo_id, sizeof s, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+	o->streak = -1;
+	if (cudaMemcpy(&s, (const VoiceState*) (state_base(o) + ((const unsigned char*) o->d_voices - (const unsigned char*) o->d_ops)) + vo_id,
+			sizeof s, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
 	out[0] = s.duration; out[1] = s.flags; out[2] = s.carr_op; out[3] = 0;
 	return 0;
 }
@@ -1810,6 +2015,13 @@ extern "C" int saugen_read_voice(saugen_Generator *o, uint32_t vo_id, uint32_t o
 extern "C" int saugen_read_voice_rows(saugen_Generator *o, uint32_t vo_id, float *s, float *r, size_t n) {
 	if (!o || vo_id < o->voice_begin || vo_id >= o->voice_end || n > o->row_len) return -1;
 	cudaSetDevice(o->device);
+	o->streak = -1;
+	if (o->rows_stale) {
+		/* a run-ahead call has overwritten the last returned call's rows (a caller that inspects
+		 * rows does so from the first calls on, before run-ahead starts; SAUGEN_RUNAHEAD=0 turns it off) */
+		g_err = "saugen_read_voice_rows: the rows hold a run-ahead call (inspect before streaming, or SAUGEN_RUNAHEAD=0)";
+		return -1;
+	}
 	cudaStreamSynchronize(o->stream);
 	const size_t lv = vo_id - o->voice_begin;
 	/* gather the voice's 512-byte pieces, one per frame tile (device_types.h:ROW_TILE) */
@@ -1836,12 +2048,7 @@ extern "C" int saugen_counters(saugen_Generator *o, uint64_t out[4]) {
 /* Per-kernel device time: CUDA events on the launch stream around each kernel. */
 extern "C" int saugen_set_timing(saugen_Generator *o, int on) {
 	if (!o) return -1;
-	if (on && !o->ev_t[0]) {                 /* the events exist only for timed generators */
-		cudaSetDevice(o->device);
-		for (int i = 0; i < 3; ++i)
-			if (cudaEventCreate(&o->ev_t[i]) != cudaSuccess) { set_err("saugen_set_timing", cudaGetLastError()); return -1; }
-	}
-	o->timing = on != 0;
+	o->timing = on != 0;                     /* (the events are made per call slot when first timed) */
 	o->render_ms = o->mix_ms = 0.0;
 	return 0;
 }

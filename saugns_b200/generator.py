@@ -110,6 +110,13 @@ def lib():
         L.saugen_wave_tables_load.restype = C.POINTER(WaveTables)
         L.saugen_wave_tables_load.argtypes = [C.c_char_p]
         L.saugen_wave_tables_free.argtypes = [C.c_void_p]
+        L.saugen_render_batch.restype = C.c_int
+        L.saugen_render_batch.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p, C.c_void_p,
+                                          C.c_void_p, C.c_void_p]
+        L.saugen_render_batch_wav.restype = C.c_int
+        L.saugen_render_batch_wav.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p, C.c_void_p,
+                                              C.c_void_p]
+        L.saugen_batch_last_error.restype = C.c_char_p
         L.saugen_voice_groups.restype = C.c_int
         L.saugen_voice_groups.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
         L.saugen_abi_layout.restype = C.c_size_t

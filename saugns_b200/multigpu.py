@@ -82,6 +82,41 @@ def render_scripts(programs, srate=96000, rank=0, world=1, device=0, call_len=No
 # ---------------------------------------------------------------------------
 # voice sharding
 # ---------------------------------------------------------------------------
+MIX_TAIL = 64        # SAUGEN_MIX_TAIL (include/saugen_b200.h): floats after the planes for control words
+
+
+def voice_shards(prg, srate, world):
+    """Contiguous voice ranges per rank that keep together the voices an operator is handed
+    over between (saugen_voice_groups: parseconv re-homes an operator whose voice slot was
+    recycled; its state lives on one generator).  Boundaries of the even split move up past
+    the end of any group they would cut; a script that is one big group lands on rank 0."""
+    from .generator import voice_groups
+    vo_count = P.Program.from_address(prg.ptr).vo_count
+    ranges = voice_ranges(vo_count, world)
+    n, groups = voice_groups(prg, srate)
+    if n == 0:
+        return ranges
+    last = {}
+    for v, g in enumerate(groups):
+        last[g] = v
+    cuts = [b for b, _ in ranges[1:]]
+    out, begin = [], 0
+    for c in cuts:
+        c = max(c, begin)
+        moved = True
+        while moved:                      # no group may straddle the cut
+            moved = False
+            for v in range(begin, min(c, vo_count)):
+                if last[groups[v]] >= c:
+                    c = last[groups[v]] + 1
+                    moved = True
+        c = min(c, vo_count)
+        out.append((begin, c))
+        begin = c
+    out.append((begin, vo_count))
+    return out
+
+
 class _CudaShard:
     """This rank's voices of the program on its GPU."""
 
@@ -94,17 +129,21 @@ class _CudaShard:
                              max_call_len=max_call_len)
 
     def run_mix(self, buf_len):
-        """-> (more, planes tensor [2 * buf_len] on the GPU, out_len)."""
+        """-> (more, tensor on the GPU: the float planes + MIX_TAIL spare floats, out_len)."""
         from .generator import planes_as_torch
         more, ptr, n = self.gen.run_mix(buf_len)
         row = self.row_len
-        t = planes_as_torch(ptr, 2 * row)
+        t = planes_as_torch(ptr, 2 * row + MIX_TAIL)
         # L plane at [0, buf_len), R plane at [row_len, row_len + buf_len)
         return more, t, n
 
     @property
     def row_len(self):
         return self._row_len
+
+    @property
+    def tail_offset(self):
+        return 2 * self._row_len
 
     def set_row_len(self, n):
         self._row_len = n
@@ -121,7 +160,12 @@ class VoiceShardedGenerator:
     spread over the ranks of a process group.
 
     run() must be called by every rank; rank `root` gets the PCM, the others
-    get None.  All ranks get the same (more, out_len).
+    get None.  All ranks get the same (more, out_len).  Each call costs exactly ONE
+    collective: an all-reduce (sum) of a buffer holding the rank's float L / R planes
+    followed by 2 x world control words -- slot r of the first `world` holds rank r's
+    "more signal follows", slot r of the second its out_len, zeros elsewhere -- so the
+    same reduction that mixes the voices tells every rank whether any shard is still
+    alive and how long the longest one ran (`collectives` counts them).
 
     `shard` (optional) is this rank's renderer: an object with
     run_mix(buf_len) -> (more, planes, out_len), to_pcm(planes, buf_len,
@@ -138,10 +182,13 @@ class VoiceShardedGenerator:
         self.group = group
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        if 2 * self.world > MIX_TAIL:
+            raise ValueError("voice sharding over more than 32 ranks")
         self.root = root
-        vo_count = P.Program.from_address(prg.ptr).vo_count if prg is not None else 0
-        self.voice_range = voice_ranges(vo_count, self.world)[self.rank]
+        self.collectives = 0
         if shard is None:
+            vo_count = P.Program.from_address(prg.ptr).vo_count
+            self.voice_range = voice_shards(prg, srate, self.world)[self.rank]
             if device is None:
                 device = torch.cuda.current_device()
             row = max_call_len if max_call_len else srate * 256 // 1000
@@ -153,29 +200,39 @@ class VoiceShardedGenerator:
             shard.set_row_len(row)
         self.shard = shard
         self.ended = False
+        self._ctrl = None
 
     def run(self, buf_len, stereo=True):
-        """-> (more, pcm or None, out_len); one reduce of the float planes per call."""
+        """-> (more, pcm or None, out_len); ONE all-reduce of planes + control words per call."""
         dist, torch = self.dist, self.torch
         more, planes, n = self.shard.run_mix(buf_len)
+        body = planes
         if self.world > 1:
-            # data path: ONE sum-reduce of the L/R planes to the root
-            dist.reduce(planes, dst=self._global(self.root), op=dist.ReduceOp.SUM, group=self.group)
-            # control: any rank alive? longest shard's out_len (max), 2 integers
-            flag = torch.tensor([int(bool(more)), int(n)], dtype=torch.int64, device=planes.device)
-            dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=self.group)
-            more, n = bool(flag[0].item()), int(flag[1].item())
+            w = self.world
+            off = getattr(self.shard, "tail_offset", None)
+            if off is None or planes.numel() < off + 2 * w:      # a stand-in without spare floats
+                off = planes.numel()
+                planes = torch.cat([planes, torch.zeros(2 * w, dtype=planes.dtype, device=planes.device)])
+            if self._ctrl is None:
+                self._ctrl = torch.zeros(2 * w, dtype=torch.float32)
+                if planes.is_cuda:
+                    self._ctrl = self._ctrl.pin_memory()
+            self._ctrl.zero_()
+            self._ctrl[self.rank] = 1.0 if more else 0.0
+            self._ctrl[w + self.rank] = float(n)
+            planes[off:off + 2 * w].copy_(self._ctrl, non_blocking=True)
+            dist.all_reduce(planes, op=dist.ReduceOp.SUM, group=self.group)
+            self.collectives += 1
+            tail = planes[off:off + 2 * w].cpu()                 # (the root needs the sum on the host anyway)
+            more = bool(tail[:w].max().item() > 0)
+            n = int(tail[w:].max().item())
+            body = planes[:off]
         pcm = None
         if self.rank == self.root:
-            pcm = self.shard.to_pcm(planes, buf_len, stereo)
+            pcm = self.shard.to_pcm(body, buf_len, stereo)
         if not more:
             self.ended = True
         return more, pcm, (buf_len if more else n)
-
-    def _global(self, r):
-        if self.group is None:
-            return r
-        return self.dist.get_global_rank(self.group, r)
 
     def render(self, call_len, stereo=True):
         """Whole program -> int16 [frames, ch] on the root, None elsewhere."""

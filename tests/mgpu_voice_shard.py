@@ -25,18 +25,22 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     tabs = gpuutil.ref_tables_for_gpu(pyport)
     # --- voice sharding: C3 sample and C4 sample (self-PM, AM) ---
+    feats = scripts.feature_scripts()
     for text in [scripts.synth_c3(64, 1, fm="mix"), scripts.synth_c4(45, 1),
-                 scripts.feature_scripts()["seq_overlap"]]:
+                 feats["seq_overlap"], feats["handover_twice"], feats["handover"]]:
         prg = pyref.Program(text)
         vg = M.VoiceShardedGenerator(prg, 96000, device=local, tables=tabs)
         got = vg.render(24576)
+        ncalls = -(-max(1, pyref.render(prg, srate=96000).shape[0]) // 24576)
+        assert vg.collectives == ncalls, (vg.collectives, ncalls)      # ONE NCCL op per call
         vg.close()
         if rank == 0:
             want = pyref.render(prg, srate=96000)
             assert got.shape == want.shape, (got.shape, want.shape)
             d = int(np.abs(got.astype(np.int32) - want.astype(np.int32)).max())
             assert d <= 1, d
-            print(f"voice-sharded x{world}: {want.shape[0]} frames, max diff {d} LSB", flush=True)
+            print(f"voice-sharded x{world}: {want.shape[0]} frames, {ncalls} calls = {ncalls} all-reduces, "
+                  f"max diff {d} LSB", flush=True)
         else:
             assert got is None
     # --- script sharding: no collective, bit-exact ---

@@ -74,3 +74,52 @@ def test_gpu_big_endian_epilogue_is_the_reference_au_stream(ref, port, tmp_path,
     pcm = saugns_b200.render(ref.Program(text), srate=48000, stereo=stereo, tables=tabs,
                              call_len=48000 * 256 // 1000, big_endian=True)
     assert batch.au_bytes(pcm, 48000, swapped=True) == want
+
+
+@pytest.mark.gpu
+def test_native_batch_driver_matches_reference(ref, port):
+    """saugen_render_batch (csrc/batch_driver.cpp): the batch loop with no Python between the calls."""
+    import gpuutil
+    from saugns_b200 import batch
+    tabs = gpuutil.ref_tables_for_gpu(port)
+    texts = [scripts.synth_c5_script(i) for i in range(40)] + [scripts.feature_scripts()[k] for k in
+                                                               ("voices3", "seq_overlap", "handover_twice", "self_w_mod")]
+    prgs = [ref.Program(t) for t in texts]
+    got = batch.render_batch_native(prgs, srate=96000, tables=tabs, group_size=16)
+    for i, p in enumerate(prgs):
+        want = ref.render(p, srate=96000)
+        assert got[i].shape == want.shape and np.array_equal(got[i], want), i
+    seen = {}
+    batch.render_batch_native(prgs[:12], srate=48000, tables=tabs, group_size=5, stereo=False,
+                              sink=lambda i, pcm: seen.__setitem__(i, pcm.copy()))
+    for i in range(12):
+        assert np.array_equal(seen[i], ref.render(prgs[i], srate=48000, stereo=False)), i
+
+
+@pytest.mark.gpu
+def test_batch_cli_writes_the_references_wav_files(tmp_path):
+    """`saugns_b200_batch -o dir a.sau b.sau ...` (the reference's own front end + the native batch
+    driver + its WAV writer threads) == `saugns -m -d -o x.wav x.sau` of the stock reference, per file."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ref_cli = os.path.join(root, "oracle", "_ref", "saugns_ref")
+    cli = os.path.join(root, "oracle", "_ref", "saugns_b200_batch")
+    if not (os.path.exists(ref_cli) and os.path.exists(cli)):
+        pytest.skip("oracle/_ref CLIs not built")
+    files = []
+    for i in range(24):
+        p = tmp_path / f"s{i}.sau"
+        p.write_text(scripts.synth_c5_script(100 + i))
+        files.append(str(p))
+    out = tmp_path / "out"
+    out.mkdir()
+    lst = tmp_path / "list.txt"
+    lst.write_text("\n".join(files) + "\n")
+    r = subprocess.run([cli, "-r", "96000", "-o", str(out), "-l", str(lst)], capture_output=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-500:]
+    for i, f in enumerate(files):
+        a = tmp_path / f"ref{i}.wav"
+        rr = subprocess.run([ref_cli, "-m", "-d", "-r", "96000", "-o", str(a), f], capture_output=True, timeout=600)
+        assert rr.returncode == 0
+        assert a.read_bytes() == (out / f"s{i}.wav").read_bytes(), i
