@@ -138,7 +138,8 @@ typedef struct saugen_BatchOptions {
  * thread.  The array is page-locked memory of the library's pool and now belongs to the sink:
  * release it with saugen_pinned_free (from any thread) when done with it. */
 typedef void (*saugen_pcm_sink)(void *user, size_t index, int16_t *pcm, size_t frames, int channels);
-/* 0 = every program rendered; <0 = error (saugen_batch_last_error). */
+/* 0 = every program rendered; <0 = error (saugen_batch_last_error).  sink NULL: the PCM is
+ * delivered to host memory and dropped. */
 int saugen_render_batch(const sauabi_Program *const *prgs, size_t n, uint32_t srate,
 		const saugen_WaveTables *tables, const saugen_BatchOptions *opt, saugen_pcm_sink sink, void *user);
 /* The same with the reference's WAV files as the sink (player/sndfile.c:63-109: 44-byte header,

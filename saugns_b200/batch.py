@@ -248,7 +248,7 @@ class BatchOptions(__import__("ctypes").Structure):
 
 
 def render_batch_native(programs, srate=96000, device=0, call_len=0, tables=None, group_size=128, depth=2,
-                        stereo=True, sink=None, wav_paths=None, io_threads=4):
+                        stereo=True, sink=None, wav_paths=None, io_threads=4, discard=False):
     """The same batch through the NATIVE driver (saugen_render_batch / saugen_render_batch_wav,
     csrc/batch_driver.cpp): no Python between the calls.  `wav_paths`: program i is written to
     wav_paths[i] by the library's writer threads (the reference's WAV format); else `sink(index,
@@ -268,6 +268,11 @@ def render_batch_native(programs, srate=96000, device=0, call_len=0, tables=None
         r = L.saugen_render_batch_wav(ptrs, n, srate, C.addressof(tables), C.byref(opt), arr)
         if r < 0:
             raise RuntimeError("saugen_render_batch_wav failed: " + L.saugen_batch_last_error().decode())
+        return None
+    if discard:                # every script's PCM reaches host memory and is dropped there
+        r = L.saugen_render_batch(ptrs, n, srate, C.addressof(tables), C.byref(opt), None, None)
+        if r < 0:
+            raise RuntimeError("saugen_render_batch failed: " + L.saugen_batch_last_error().decode())
         return None
     out = [None] * n
     ch = 2 if stereo else 1

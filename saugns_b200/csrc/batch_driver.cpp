@@ -212,9 +212,11 @@ thread_local std::string g_batch_err;
 
 extern "C" int saugen_render_batch(const sauabi_Program *const *prgs, size_t n, uint32_t srate,
 		const saugen_WaveTables *tables, const saugen_BatchOptions *opt, saugen_pcm_sink sink, void *user) {
-	if (!prgs || !sink || !srate || !tables) { g_batch_err = "saugen_render_batch: NULL argument"; return -1; }
+	if (!prgs || !srate || !tables) { g_batch_err = "saugen_render_batch: NULL argument"; return -1; }
 	Driver d;
 	d.prgs = prgs; d.n = n; d.srate = srate; d.tables = tables; d.sink = sink; d.user = user;
+	if (!sink)             /* no sink: the PCM reaches host memory and is dropped (throughput measurements) */
+		d.sink = [](void*, size_t, int16_t *pcm, size_t, int) { saugen_pinned_free(pcm); };
 	fill_defaults(d.opt, srate, opt);
 	const int r = d.run();
 	if (r < 0) g_batch_err = d.err;

@@ -54,8 +54,9 @@ enum {
 enum { OSC_RESET_DIFF = 1 << 0 };   // sau/generator/wosc.h:37-38
 
 /* 192 bytes, every hot group 16-byte aligned: line[i] at 16*i, the
- * {time, type/flags/mode/oscflags, i0, i1} group at 144, {prev_Is, prev_s,
- * fb_s} at 160. */
+ * {time, type/flags/mode/oscflags, prev_s, fb_s} group at 144 and everything an
+ * oscillator carries from chunk to chunk, {i0, i1, prev_Is}, in ONE 128-bit
+ * group at 160 (one load, one store by the lane that holds the chunk's last sample). */
 struct __align__(16) OpState {
 	LineState line[LINE_COUNT];
 	uint32_t lmeta[LINE_COUNT];
@@ -65,10 +66,10 @@ struct __align__(16) OpState {
 	uint8_t flags;         // ON_*
 	uint8_t mode;          // W: wave, N: noise type, R: line type
 	uint8_t oscflags;      // W: OSC_RESET_DIFF, R: bit0 = rate2x
+	float prev_s, fb_s;
 	/* W: phasor.phase / prev_phase; N: n / prev; R: cycle_phase lo / hi */
 	uint32_t i0, i1;
 	double prev_Is;
-	float prev_s, fb_s;
 	/* R options (sau/program.h:126-132) */
 	uint16_t ras_flags;
 	uint8_t ras_func, ras_level;

@@ -114,17 +114,18 @@ __device__ __noinline__ void plan_lower(uint32_t plan, uint32_t nrec) {
 /* ---- the specialised fused wave operator ------------------------------------ */
 
 /* phases of this lane's four samples (sauPhasor_fill, wosc.h:135-169); `st` = the operator's
- * {time, flags, i0, i1} group, already loaded */
+ * {i0, i1, prev_Is} group, already loaded.  Returns the accumulator after the chunk (what
+ * lane 31 writes back with the oscillator's look-back values, xosc_core). */
 template <int FS, int PM>
-__device__ __forceinline__ void xphase(const HotCtx &c, const uint4 p0, const uint32_t rec, const uint32_t xf,
+__device__ __forceinline__ uint32_t xphase(const HotCtx &c, const uint4 p0, const uint32_t rec, const uint32_t xf,
 		const uint4 st, const float val[4], uint32_t ph[4]) {
-	const uint32_t op = p0.z;
+	uint32_t acc;
 	if (FS == 0) {
 		const uint32_t inc = lds32(rec + 24);
-		const uint32_t base = st.z + inc * (uint32_t) (c.lane * 4);
+		const uint32_t base = st.x + inc * (uint32_t) (c.lane * 4);
 #pragma unroll
 		for (int k = 0; k < 4; ++k) ph[k] = base + inc * (uint32_t) (k + 1);
-		if (c.lane == 31) sts32(op + OS_I0, ph[3]);
+		acc = ph[3];                   /* (lane 31's is the chunk's last) */
 	} else {
 		float fr[4];
 		const uint32_t src = FS == 1 ? p0.x >> 24 : (p0.y >> 8) & 0xffu;
@@ -147,10 +148,10 @@ __device__ __forceinline__ void xphase(const HotCtx &c, const uint4 p0, const ui
 			ph[k] = run;
 		}
 		const uint32_t incl = scan_incl_u32(run, c.lane);
-		const uint32_t base = st.z + (incl - run);
+		const uint32_t base = st.x + (incl - run);
 #pragma unroll
 		for (int k = 0; k < 4; ++k) ph[k] += base;
-		if (c.lane == 31) sts32(op + OS_I0, st.z + incl);
+		acc = st.x + incl;
 	}
 	if (PM == 1) {
 		float pm[4];
@@ -161,16 +162,16 @@ __device__ __forceinline__ void xphase(const HotCtx &c, const uint4 p0, const ui
 #pragma unroll
 		for (int k = 0; k < 4; ++k) ph[k] += ftoi_lo32(val[k] * 2147483648.f);
 	}
+	return acc;
 }
 
-/* sauWOsc_run (wosc.h:238-266) at the phases ph -> s; carried state written back by lane 31 */
+/* sauWOsc_run (wosc.h:238-266) at the phases ph -> s; the accumulator `acc` and the look-back
+ * values go back in one 128-bit store by lane 31 */
 __device__ __forceinline__ void xosc_core(const HotCtx &c, const uint4 p0, const uint32_t rec, const uint4 st,
-		const uint32_t ph[4], float s[4]) {
+		const uint32_t acc, const uint32_t ph[4], float s[4]) {
 	const uint32_t op = p0.z;
-	uint2 pg;                                    /* prev_Is lo / hi */
-	asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(pg.x), "=r"(pg.y) : "r"(op + OS_PREV));
 	uint32_t pph = __shfl_up_sync(FULL, ph[3], 1);
-	if (c.lane == 0) pph = st.w;
+	if (c.lane == 0) pph = lds32(op + OS_I1);
 	int32_t d[4];
 	d[0] = (int32_t) (ph[0] - pph);
 #pragma unroll
@@ -188,12 +189,18 @@ __device__ __forceinline__ void xosc_core(const HotCtx &c, const uint4 p0, const
 		Is[k] = horner_frac(hi.x, hi.y, (double) lo.x, ph[k]) + (double) lo.y;
 	}
 	double pIs = __shfl_up_sync(FULL, Is[3], 1);
-	if (c.lane == 0) pIs = __hiloint2double((int) pg.y, (int) pg.x);
+	if (c.lane == 0) {
+		uint2 pg;
+		asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(pg.x), "=r"(pg.y) : "r"(op + OS_PREV));
+		pIs = __hiloint2double((int) pg.y, (int) pg.x);
+	}
+	__syncwarp();              /* lane 0 holds the look-back values before lane 31 rewrites them */
 	bool z = false;
 #pragma unroll
 	for (int k = 0; k < 4; ++k) z |= (d[k] == 0);
 	if (__any_sync(FULL, z)) {
 		/* some phase difference is zero: the output repeats (wosc.h:251-252), out of line */
+		if (c.lane == 31) sts32(op + OS_I0, acc);
 		const uint4 h = lds128u(c.plan);
 		ColdCtx cc;
 		cc.tab = reinterpret_cast<const float*>((uint64_t) h.x | ((uint64_t) h.y << 32));
@@ -214,10 +221,9 @@ __device__ __forceinline__ void xosc_core(const HotCtx &c, const uint4 p0, const
 			s[k] = (float) (dI * (double) xq[k] + doff);
 		}
 		if (c.lane == 31) {
-			sts32(op + OS_I1, ph[3]);
-			asm volatile("st.shared.v2.u32 [%0], {%1, %2};" :: "r"(op + OS_PREV),
+			asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(op + OS_I0), "r"(acc), "r"(ph[3]),
 					"r"((uint32_t) __double2loint(Is[3])), "r"((uint32_t) __double2hiint(Is[3])) : "memory");
-			sts32(op + OS_PREV + 8, __float_as_uint(s[3]));
+			sts32(op + OS_PREVS, __float_as_uint(s[3]));
 		}
 	}
 }
@@ -248,6 +254,19 @@ __device__ __forceinline__ void xamp(const HotCtx &c, const uint32_t rec, float 
 	}
 }
 
+/* A record in the general form, out of line: the lowered loop's registers are for its own
+ * straight-line variants.  Returns the record's address after it (the second slot consumed). */
+template <bool OTHER>
+__device__ __noinline__ uint32_t lowered_generic(uint32_t sb, uint32_t plan, int lane, uint32_t oc, uint32_t rec) {
+	HotCtx g;
+	g.sb = sb; g.plan = plan; g.lane = lane; g.oc = oc;
+	g.coeff = lds32f(plan + PH_COEFF);
+	const uint4 p0 = lds128u(rec);
+	/* (the voice output of a lowered plan is always X_VOUT: no rows needed here) */
+	plan_record_generic<FAST_NS, true, OTHER>(g, rec, p0, nullptr, nullptr, 0u);
+	return rec;
+}
+
 /* One chunk of a lowered plan.  val: the four samples the previous specialised record produced. */
 template <bool OTHER>
 __device__ __forceinline__ void run_chunk_lowered(const HotCtx &c) {
@@ -259,33 +278,28 @@ __device__ __forceinline__ void run_chunk_lowered(const HotCtx &c) {
 		const uint32_t kind = p0.x & 0xffu;
 		if (kind == P_STOP || rec - c.plan > PLAN_WALK_MAX) break;
 		if (kind < X_OSC0) {
-			/* (the voice output of a lowered plan is always X_VOUT: no rows needed here) */
-			HotCtx g = c;
-			g.coeff = lds32f(c.plan + PH_COEFF);
-			if (plan_record_generic<FAST_NS, true, OTHER>(g, rec, p0, nullptr, nullptr, 0u)) return;
+			rec = lowered_generic<OTHER>(c.sb, c.plan, c.lane, c.oc, rec);
 			continue;
 		}
 		const uint32_t flags = (p0.x >> 8) & 0xffu, xf = (p0.y >> 16) & 0xffu;
 		const uint32_t bufa = (p0.x >> 16) & 0xffu;
 		if (kind < X_RANGE) {
-			uint4 st;                                /* time, type|flags|mode|oscflags, i0, i1 */
-			asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
-					: "=r"(st.x), "=r"(st.y), "=r"(st.z), "=r"(st.w) : "r"(p0.z + OS_TIME));
-			__syncwarp();              /* every lane holds the carried values before lane 31 rewrites them */
-			uint32_t ph[4];
+			uint4 st;                                /* i0 now; i1, prev_Is where they are needed (xosc_core) */
+			st.x = lds32(p0.z + OS_I0); st.y = st.z = st.w = 0u;
+			uint32_t ph[4], acc;
 			switch (kind - X_OSC0) {
-			case 0: xphase<0, 0>(c, p0, rec, xf, st, val, ph); break;
-			case 1: xphase<0, 1>(c, p0, rec, xf, st, val, ph); break;
-			case 2: xphase<0, 2>(c, p0, rec, xf, st, val, ph); break;
-			case 3: xphase<1, 0>(c, p0, rec, xf, st, val, ph); break;
-			case 4: xphase<1, 1>(c, p0, rec, xf, st, val, ph); break;
-			case 5: xphase<1, 2>(c, p0, rec, xf, st, val, ph); break;
-			case 6: xphase<2, 0>(c, p0, rec, xf, st, val, ph); break;
-			case 7: xphase<2, 1>(c, p0, rec, xf, st, val, ph); break;
-			default: xphase<2, 2>(c, p0, rec, xf, st, val, ph); break;
+			case 0: acc = xphase<0, 0>(c, p0, rec, xf, st, val, ph); break;
+			case 1: acc = xphase<0, 1>(c, p0, rec, xf, st, val, ph); break;
+			case 2: acc = xphase<0, 2>(c, p0, rec, xf, st, val, ph); break;
+			case 3: acc = xphase<1, 0>(c, p0, rec, xf, st, val, ph); break;
+			case 4: acc = xphase<1, 1>(c, p0, rec, xf, st, val, ph); break;
+			case 5: acc = xphase<1, 2>(c, p0, rec, xf, st, val, ph); break;
+			case 6: acc = xphase<2, 0>(c, p0, rec, xf, st, val, ph); break;
+			case 7: acc = xphase<2, 1>(c, p0, rec, xf, st, val, ph); break;
+			default: acc = xphase<2, 2>(c, p0, rec, xf, st, val, ph); break;
 			}
 			float s[4];
-			xosc_core(c, p0, rec, st, ph, s);
+			xosc_core(c, p0, rec, st, acc, ph, s);
 			float am[4];
 			switch ((xf >> XF_AMP_SHIFT) & 3u) {
 			case 0: xamp<0>(c, rec, am); break;
@@ -293,21 +307,26 @@ __device__ __forceinline__ void run_chunk_lowered(const HotCtx &c) {
 			case 2: xamp<2>(c, rec, am); break;
 			default: xamp<3>(c, rec, am); break;
 			}
-			const bool layer = (flags & PF_LAYER) != 0;
-			float lay[4];
-			if (layer) fld<4>(c, bufa, lay);
 			if (flags & PF_WAVEENV) {                                     /* generator.c:407-426 */
 #pragma unroll
 				for (int k = 0; k < 4; ++k) {
 					const float s_amp = am[k] * 0.5f;
-					const float v = (s[k] * s_amp) + fabsf(s_amp);
-					val[k] = layer ? lay[k] * v : v;
+					val[k] = (s[k] * s_amp) + fabsf(s_amp);
+				}
+				if (flags & PF_LAYER) {
+					float lay[4];
+					fld<4>(c, bufa, lay);
+#pragma unroll
+					for (int k = 0; k < 4; ++k) val[k] = lay[k] * val[k];
 				}
 			} else {                                                      /* generator.c:384-397 */
 #pragma unroll
-				for (int k = 0; k < 4; ++k) {
-					const float v = s[k] * am[k];
-					val[k] = layer ? lay[k] + v : v;
+				for (int k = 0; k < 4; ++k) val[k] = s[k] * am[k];
+				if (flags & PF_LAYER) {
+					float lay[4];
+					fld<4>(c, bufa, lay);
+#pragma unroll
+					for (int k = 0; k < 4; ++k) val[k] = lay[k] + val[k];
 				}
 			}
 			if (xf & XF_ST) fst<4>(c, bufa, val);

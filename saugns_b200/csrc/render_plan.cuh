@@ -587,11 +587,12 @@ __device__ __forceinline__ void fst(const HotCtx &c, uint32_t buf, const float v
 }
 
 /* byte offsets inside OpState (device_types.h) */
-constexpr uint32_t OS_LINE = 0, OS_LMETA = 96, OS_LINV = 120, OS_TIME = 144, OS_I0 = 152,
-	OS_I1 = 156, OS_PREV = 160;
+constexpr uint32_t OS_LINE = 0, OS_LMETA = 96, OS_LINV = 120, OS_TIME = 144, OS_PREVS = 152,
+	OS_I0 = 160, OS_I1 = 164, OS_PREV = 168;
 static_assert(offsetof(OpState, lmeta) == OS_LMETA && offsetof(OpState, linv) == OS_LINV &&
 		offsetof(OpState, time) == OS_TIME && offsetof(OpState, i0) == OS_I0 &&
-		offsetof(OpState, i1) == OS_I1 && offsetof(OpState, prev_Is) == OS_PREV, "OpState offsets");
+		offsetof(OpState, i1) == OS_I1 && offsetof(OpState, prev_Is) == OS_PREV &&
+		offsetof(OpState, prev_s) == OS_PREVS, "OpState offsets");
 
 /* value of a steady run line for this lane's samples of the chunk at c.oc */
 template <int NS>
@@ -827,7 +828,7 @@ __device__ __forceinline__ void osc_plan(const HotCtx &c, const uint4 p0, const 
 				sts32(op + OS_I1, ph[NS - 1]);
 				asm volatile("st.shared.v2.u32 [%0], {%1, %2};" :: "r"(op + OS_PREV),
 						"r"((uint32_t) __double2loint(Is[NS - 1])), "r"((uint32_t) __double2hiint(Is[NS - 1])) : "memory");
-				sts32(op + OS_PREV + 8, __float_as_uint(s[NS - 1]));
+				sts32(op + OS_PREVS, __float_as_uint(s[NS - 1]));
 			}
 		}
 	}

@@ -312,7 +312,8 @@ __device__ __noinline__ bool team_stretch(const TeamCtx &tc, uint32_t sb, int la
 	/* the last active member's accumulators and look-back values are the voice's */
 	const uint32_t last = tc.so_b + (t_eff - 1u) * tc.per_warp;
 	for (uint32_t i = lane; i < nops * 5u; i += 32) {
-		const uint32_t slot = i / 5u, off = OS_I0 + (i % 5u) * 4u;         /* i0, i1, prev_Is, prev_s */
+		const uint32_t slot = i / 5u, k = i % 5u;
+		const uint32_t off = k == 4u ? OS_PREVS : OS_I0 + k * 4u;          /* i0, i1, prev_Is; prev_s */
 		sts32(tc.so_a + slot * 192u + off, lds32(last + slot * 192u + off));
 	}
 	__syncwarp();

@@ -170,3 +170,7 @@ def test_nccl_voice_and_script_sharding_two_gpus():
                        capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "rank 0 OK" in r.stdout and "rank 1 OK" in r.stdout
+    out = os.path.join(ROOT, "gpurun_out")          # kept as evidence (copied to profiles/ by hand)
+    if os.path.isdir(out):
+        with open(os.path.join(out, "nccl_voice_shard_x2.log"), "w") as f:
+            f.write(r.stdout)

@@ -127,17 +127,26 @@ def main():
     launches = sys.argv[4] if len(sys.argv) > 4 else f"gpurun_out/{tag}_launches.csv"
     pdir = os.path.join(ROOT, "profiles")
     os.makedirs(pdir, exist_ok=True)
+    c4 = f"gpurun_out/{tag}_c4.ncu-rep"
     jobs = [(render, "render_kernel", 3 * 4096 * 24576, "op_samples"),
-            (mix, "mix_kernel", 4096 * 24576, "voice_samples")]
+            (mix, "mix_kernel", 4096 * 24576, "voice_samples"),
+            (c4, "c4_render_kernel", 1024 * 24576, "voice_samples")]
     for rep, name, units, uname in jobs:
         if not os.path.exists(rep):
             continue
         d = summarize(rep, name, units, uname)
+        if name == "c4_render_kernel":
+            # C4 (1024 self-PM voices): every feedback operator is one serial chain of 24576
+            # dependent iterations per call; the figure of merit is cycles per iteration
+            d["feedback_iterations_per_launch"] = 24576
+            d["cycles_per_feedback_iteration"] = (d["cycles_elapsed"] or 0) / 24576.0
         with open(os.path.join(pdir, f"{tag}_{name}.json"), "w") as f:
             json.dump(d, f, indent=1)
         with open(os.path.join(pdir, f"{tag}_{name}.txt"), "w") as f:
-            f.write(f"# {name}: ncu --set full --clock-control none, one launch of the C3 step "
-                    f"(4096 voices x 24576 frames), from {os.path.basename(rep)}\n")
+            what = ("the C4 step (1024 self-PM voices x 24576 frames)" if name == "c4_render_kernel" else
+                    "the C3 step (4096 voices x 24576 frames)")
+            f.write(f"# {name}: ncu --set full --clock-control none --cache-control none, one steady-state launch "
+                    f"of {what}, from {os.path.basename(rep)}\n")
             for k, v in d.items():
                 f.write(f"{k:32s} {v}\n")
             f.write("\n".join(sass_mix(rep, units / 32.0)) + "\n")
