@@ -408,3 +408,82 @@ def test_c4_full_voice_count_bit_exact(S, ref, tabs):
     got = S.render(prg, srate=96000, tables=tabs)
     assert got.shape == want.shape
     assert np.array_equal(got, want)
+
+
+def test_runahead_streaming_and_undo(S, ref, port, tabs):
+    """A streaming caller (same call size again and again) gets the next call launched before it
+    asks (runtime.cpp: run_call); a change of call size or channel count undoes the call that ran
+    ahead, reading operator state in mid-stream sees the state of the last RETURNED call, and the
+    end of the signal is reported by the right call."""
+    feats = scripts.feature_scripts()
+    for name in ["pm_chain", "seq_update", "voices3", "self_w_mod", "handover_twice", "fm_both", "regoal"]:
+        prg = ref.Program(feats[name])
+        gr = ref.RefGenerator(prg, 96000)
+        gg = S.Generator(prg, 96000, tables=tabs, max_call_len=4096)
+        sizes = [1024] * 5 + [777] * 3 + [1024] * 4 + [4096] * 100
+        stereo = [True] * 6 + [False] * 4 + [True] * 200
+        more, k = True, 0
+        while more and k < len(sizes):
+            more, ba, na = gr.run(sizes[k], stereo[k])
+            more2, bb, nb = gg.run(sizes[k], stereo[k])
+            assert (more, na) == (more2, nb), (name, k)
+            assert np.array_equal(ba, bb), (name, k)
+            if k in (3, 4, 9, 14):      # mid-stream inspection: the last returned call's state
+                for op in range(prg.op_count):
+                    assert port.op_state_tuple(gr.op_state(op)) == port.op_state_tuple(gg.op_state(op)), (name, k, op)
+            k += 1
+        assert not more, name
+        for op in range(prg.op_count):   # final state: the call that ran past the end was undone
+            assert port.op_state_tuple(gr.op_state(op)) == port.op_state_tuple(gg.op_state(op)), (name, op)
+        more2, bb, nb = gg.run(1024)     # after the end: silence, no frames
+        assert not more2 and nb == 0 and not bb.any()
+        gg.close()
+
+
+def test_runahead_device_calls_keep_two_buffers(S, ref, tabs):
+    """run_device: the PCM of call k stays valid while call k+1 (already rendering) fills the other buffer."""
+    import ctypes as C
+    prg = ref.Program(scripts.synth_c3(48, 1, fm="mix"))
+    want = ref.render(prg, srate=96000, call_len=8192)
+    gg = S.Generator(prg, 96000, tables=tabs, max_call_len=8192)
+    import torch
+    got, more = [], True
+    while more:
+        more, ptr, n = gg.run_device(8192)
+        t = torch.empty(8192 * 2, dtype=torch.int16, device="cuda")
+        C.cdll.LoadLibrary("libcudart.so").cudaMemcpy(C.c_void_p(t.data_ptr()), C.c_void_p(ptr), C.c_size_t(8192 * 4), 3)
+        got.append(t.cpu().numpy()[:2 * n])
+    gg.close()
+    assert np.array_equal(np.concatenate(got).reshape(-1, 2), want)
+
+
+def test_time_split_teams_deep_fm(S, ref, port, tabs):
+    """Few voices: steady stretches are split along time over a team of warps (render_team.cuh).
+    Nested frequency modulation needs one counting pass per nesting level for the members' start
+    phases; everything stays bit-exact, including the state after every call."""
+    texts = {
+        "fm3": "Wsin f300.r600[Wsin f7.r11[Wtri f0.5.r3[Wsin f0.31]]] t3 p[Wsin r2 a0.4]",
+        "fm2_pm2": "Wsin f200.r320[Wsqr f3] t3 p[Wsin r1.5 a0.5 p[Wsin f90.r140[Wsin f2] a0.3] Wtri f50 a0.2]",
+        "c2": scripts.C2_MISC1_4FM_PM.split("|")[0],
+        "ratio_chain": "Wsin f110 t3 a1[g0.2 lxpe] p[Wtri r2 a0.8[g0.1 llin] p[Wsin r3.5 a0.5 p[Wsin r0.25 a0.3]]]",
+        "five_voices": "\n".join(f"Wsin f{150 + 37 * i}.r{300 + 50 * i}[Wtri r0.{3 + i} a0.8[g0.1 llin]] t2.5 a0.5[g0.1 lxpe] "
+                                 f"c{-0.8 + 0.4 * i} p[Wsin r{1 + i} a0.4]" for i in range(5)),
+        "mixed_kinds": "Wsin f200 t2 p[Wsin r2 a0.5]\nNre t2 a0.2\nRlin f300 t2\nWsin f300 p.a0.6 t2\nWsaw f120[g400 lexp t1.5] t2",
+        "slow_lfo": "Wsin f0.37 t3 a0.8\nWsin f440.r470[Wsin f0.11] t3",
+    }
+    for name, text in texts.items():
+        prg = ref.Program(text)
+        for call_len in (24576, 100000, 5000):
+            want = ref.render(prg, srate=96000, call_len=call_len)
+            got = S.render(prg, srate=96000, tables=tabs, call_len=call_len)
+            assert got.shape == want.shape and np.array_equal(got, want), (name, call_len)
+        gr = ref.RefGenerator(prg, 96000)
+        gg = S.Generator(prg, 96000, tables=tabs, max_call_len=40000)
+        more = True
+        while more:
+            more, ba, na = gr.run(40000)
+            more2, bb, nb = gg.run(40000)
+            assert (more, na) == (more2, nb) and np.array_equal(ba, bb), name
+            for op in range(prg.op_count):
+                assert port.op_state_tuple(gr.op_state(op)) == port.op_state_tuple(gg.op_state(op)), (name, op)
+        gg.close()
