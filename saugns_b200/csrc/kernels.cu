@@ -249,6 +249,11 @@ cudaError_t launch_mix(const CallDesc *d_calls, uint32_t ncalls, const SegDesc *
 	return cudaGetLastError();
 }
 
+/* developer aid: the lowered-plan signature of the first stretch of the launch's first voice */
+cudaError_t read_signature_dump(uint32_t out[36]) {
+	return cudaMemcpyFromSymbol(out, g_sig_dump, sizeof(uint32_t) * 36);
+}
+
 cudaError_t launch_planes_to_pcm(const float *d_mix, uint32_t plane_stride, uint32_t n,
 		uint32_t stereo, int16_t *d_pcm, cudaStream_t stream) {
 	if (!n) return cudaSuccess;

@@ -418,3 +418,174 @@ __device__ __noinline__ void run_block_lowered(uint32_t sb, uint32_t plan, int l
 		run_chunk_lowered<OTHER>(c);
 	}
 }
+
+/* ---- fused shapes ------------------------------------------------------------ *
+ * Most voices of a script share a handful of plan SIGNATURES (the same operator graph with
+ * other constants: C3 has two).  For the signatures listed below the chunk loop exists as ONE
+ * straight-line function -- the same xphase / xosc_core / xamp statements, instantiated with
+ * the record variants as template parameters: no record dispatch, no flag tests.  A plan whose
+ * lowered records spell one of the listed signatures runs through it; every other plan through
+ * run_chunk_lowered.  The list is a compile-time table; a signature is the sequence of the
+ * records' 16-bit codes (below). */
+__device__ __forceinline__ uint32_t rec_code(uint32_t w0, uint32_t w1) {
+	const uint32_t kind = w0 & 0xffu, fl = (w0 >> 8) & 0xffu, xf = (w1 >> 16) & 0xffu;
+	if (kind >= X_OSC0 && kind < X_RANGE)
+		return 0x1000u | (kind - X_OSC0) | ((xf >> XF_AMP_SHIFT) & 3u) << 4 | ((fl & PF_WAVEENV) ? 0x40u : 0u) |
+			((fl & PF_LAYER) ? 0x80u : 0u) | ((xf & XF_ST) ? 0x100u : 0u) | ((xf & XF_SRC_VAL) ? 0x200u : 0u);
+	if (kind == X_RANGE) return 0x2000u | ((xf & XF_ST) ? 0x100u : 0u) | ((xf & XF_SRC_VAL) ? 0x200u : 0u);
+	if (kind == X_VOUT) return 0x3000u | ((xf & XF_SRC_VAL) ? 0x200u : 0u);
+	return 0xffffu;            /* not a fusable record */
+}
+
+template <int FS, int PM, int AMP, bool ENV, bool LAYER, bool ST, bool SRCVAL>
+struct FOsc {
+	static constexpr uint32_t SLOTS = AMP ? 2 : 1;
+	static constexpr uint16_t CODE = 0x1000u | (3 * FS + PM) | AMP << 4 | (ENV ? 0x40u : 0u) | (LAYER ? 0x80u : 0u) |
+		(ST ? 0x100u : 0u) | (SRCVAL ? 0x200u : 0u);
+	static __device__ __forceinline__ void exec(const HotCtx &c, const uint32_t rec, float val[4]) {
+		const uint4 p0 = lds128u(rec);
+		uint4 st;
+		st.x = lds32(p0.z + OS_I0); st.y = st.z = st.w = 0u;
+		uint32_t ph[4];
+		const uint32_t acc = xphase<FS, PM>(c, p0, rec, SRCVAL ? XF_SRC_VAL : 0u, st, val, ph);
+		float s[4], am[4];
+		xosc_core(c, p0, rec, st, acc, ph, s);
+		xamp<AMP>(c, rec, am);
+		const uint32_t bufa = (p0.x >> 16) & 0xffu;
+		if (ENV) {
+#pragma unroll
+			for (int k = 0; k < 4; ++k) {
+				const float s_amp = am[k] * 0.5f;
+				val[k] = (s[k] * s_amp) + fabsf(s_amp);
+			}
+		} else {
+#pragma unroll
+			for (int k = 0; k < 4; ++k) val[k] = s[k] * am[k];
+		}
+		if (LAYER) {
+			float lay[4];
+			fld<4>(c, bufa, lay);
+#pragma unroll
+			for (int k = 0; k < 4; ++k) val[k] = ENV ? lay[k] * val[k] : lay[k] + val[k];
+		}
+		if (ST) fst<4>(c, bufa, val);
+		__syncwarp();
+	}
+};
+template <bool ST, bool SRCVAL>
+struct FRange {
+	static constexpr uint32_t SLOTS = 1;
+	static constexpr uint16_t CODE = 0x2000u | (ST ? 0x100u : 0u) | (SRCVAL ? 0x200u : 0u);
+	static __device__ __forceinline__ void exec(const HotCtx &c, const uint32_t rec, float val[4]) {
+		float m[4];
+		if (SRCVAL) {
+#pragma unroll
+			for (int k = 0; k < 4; ++k) m[k] = val[k];
+		} else {
+			fld<4>(c, lds32(rec + 4) & 0xffu, m);
+		}
+		const float2 pr = lds64f(rec + 24);
+#pragma unroll
+		for (int k = 0; k < 4; ++k) { float p = pr.x; p += (pr.y - p) * m[k]; val[k] = p; }
+		if (ST) fst<4>(c, (lds32(rec) >> 16) & 0xffu, val);
+	}
+};
+template <bool SRCVAL>
+struct FVout {
+	static constexpr uint32_t SLOTS = 1;
+	static constexpr uint16_t CODE = 0x3000u | (SRCVAL ? 0x200u : 0u);
+	static __device__ __forceinline__ void exec(const HotCtx &c, const uint32_t rec, float val[4]) {
+		const uint4 p0 = lds128u(rec);
+		const uint32_t bufa = (p0.x >> 16) & 0xffu;
+		float sv[4];
+		if (SRCVAL) {
+#pragma unroll
+			for (int k = 0; k < 4; ++k) sv[k] = val[k];
+		} else {
+			fld<4>(c, bufa, sv);
+		}
+		const float pan = lds32f(p0.z + OS_LINE + 16 * LINE_PAN);
+		const uint4 h1 = lds128u(c.plan + 16);
+		const uint4 h2 = lds128u(c.plan + PH_ROW_S);
+		const float amp_scale = __uint_as_float(h1.y);
+		const uint32_t write_r = h1.z, tstride = h1.w;
+		float *row_s = reinterpret_cast<float*>((uint64_t) h2.x | ((uint64_t) h2.y << 32));
+		float *row_r = reinterpret_cast<float*>((uint64_t) h2.z | ((uint64_t) h2.w << 32));
+		const uint32_t frame = lds32(c.plan + PH_FRAME0) + c.oc;
+		float s[4], rv[4];
+#pragma unroll
+		for (int k = 0; k < 4; ++k) { s[k] = sv[k] * amp_scale; rv[k] = s[k] * pan; }
+		const size_t at = row_index(frame + c.lane * 4, tstride);       /* (fused plans: aligned frames only) */
+		__stcs(reinterpret_cast<float4*>(row_s + at), make_float4(s[0], s[1], s[2], s[3]));
+		if (write_r) __stcs(reinterpret_cast<float4*>(row_r + at), make_float4(rv[0], rv[1], rv[2], rv[3]));
+	}
+};
+
+template <class... R>
+struct Shape {
+	static constexpr uint32_t N = sizeof...(R);
+	static __device__ __forceinline__ bool match(const uint16_t *codes, uint32_t n) {
+		if (n != N) return false;
+		const uint16_t want[N] = {R::CODE...};
+		bool ok = true;
+#pragma unroll
+		for (uint32_t i = 0; i < N; ++i) ok = ok && codes[i] == want[i];
+		return ok;
+	}
+	static __device__ __noinline__ void run(uint32_t sb, uint32_t plan, int lane, uint32_t oc0, uint32_t len) {
+		HotCtx c;
+		c.sb = sb; c.plan = plan; c.lane = lane; c.coeff = 0.f;
+		for (uint32_t oc = oc0; oc < oc0 + len; oc += FastCfg<FAST_NS>::CHUNKF) {
+			c.oc = oc;
+			float val[4] = {0.f, 0.f, 0.f, 0.f};
+			uint32_t rec = plan + PLAN_HDR;
+			((R::exec(c, rec, val), rec += R::SLOTS * PLAN_REC), ...);
+		}
+	}
+};
+
+/* The listed signatures.  (FOsc<FS, PM, AMP, ENV, LAYER, ST, SRCVAL>: FS 0 uniform / 1 vector / 2
+ * constant x vector; PM 0 none / 1 buffer / 2 val; AMP 0 held / 1 lin / 2 xpe / 3 lge.) */
+using ShapeW1      = Shape<FOsc<0, 0, 0, false, false, false, false>, FVout<true>>;                 /* one plain wave operator */
+using ShapeW1x     = Shape<FOsc<0, 0, 2, false, false, false, false>, FVout<true>>;                 /* ... with an xpe amplitude ramp */
+using ShapePM2     = Shape<FOsc<0, 0, 0, false, false, false, false>,
+                           FOsc<0, 2, 0, false, false, false, false>, FVout<true>>;                 /* carrier + one PM modulator */
+using ShapeC3PM    = Shape<FOsc<0, 0, 0, false, false, false, false>, FOsc<0, 2, 1, false, false, false, false>,
+                           FOsc<0, 2, 2, false, false, false, false>, FVout<true>>;                 /* 3-operator PM chain, lin / xpe ramps */
+using ShapeC3FM    = Shape<FOsc<0, 0, 1, true, false, false, false>, FRange<true, true>,
+                           FOsc<2, 0, 0, false, false, false, true>, FOsc<1, 2, 2, false, false, false, false>,
+                           FVout<true>>;                                                             /* range-FM carrier + ratio PM modulator */
+constexpr uint32_t FUSED_NONE = 0;
+__device__ uint32_t g_sig_dump[36];           /* developer aid: the first stretch's signature (saugen_debug_signature) */
+
+/* lane 0: which listed shape the lowered plan spells (0 = none) */
+__device__ __noinline__ uint32_t fused_match(uint32_t plan, uint32_t nrec, bool dump) {
+	uint16_t codes[16];
+	uint32_t n = 0;
+	for (uint32_t r = 0; r < nrec; ++r) {
+		const uint32_t a = plan + PLAN_HDR + r * PLAN_REC;
+		const uint32_t w0 = lds32(a), w1 = lds32(a + 4);
+		if ((w0 & 0xffu) == P_EXT) continue;
+		if (n >= 16) return FUSED_NONE;
+		codes[n++] = (uint16_t) rec_code(w0, w1);
+	}
+	if (dump) {
+		g_sig_dump[0] = n;
+		for (uint32_t i = 0; i < n; ++i) g_sig_dump[1 + i] = codes[i];
+	}
+	if (ShapeC3PM::match(codes, n)) return 1;
+	if (ShapeC3FM::match(codes, n)) return 2;
+	if (ShapePM2::match(codes, n)) return 3;
+	if (ShapeW1::match(codes, n)) return 4;
+	if (ShapeW1x::match(codes, n)) return 5;
+	return FUSED_NONE;
+}
+__device__ __forceinline__ void fused_run(uint32_t which, uint32_t sb, uint32_t plan, int lane, uint32_t oc0, uint32_t len) {
+	switch (which) {
+	case 1: ShapeC3PM::run(sb, plan, lane, oc0, len); break;
+	case 2: ShapeC3FM::run(sb, plan, lane, oc0, len); break;
+	case 3: ShapePM2::run(sb, plan, lane, oc0, len); break;
+	case 4: ShapeW1::run(sb, plan, lane, oc0, len); break;
+	default: ShapeW1x::run(sb, plan, lane, oc0, len); break;
+	}
+}

@@ -134,7 +134,16 @@ __device__ __noinline__ void render_units(Ctx &c, FastCtx &fc, const CallDesc *c
 						team_stretch(*fc.team, fc.sb, lane, fc.plan, nrec, vs.ops_cnt, span);
 					if (shared) { }
 					else if (other) run_block_lowered<true>(fc.sb, fc.plan, lane, 0u, span);
-					else run_block_lowered<false>(fc.sb, fc.plan, lane, 0u, span);
+					else {
+						/* a listed signature runs as one straight-line function (fused shapes);
+						 * segments starting at an odd frame keep to the general voice output */
+						uint32_t which = 0;
+						if (lane == 0 && ((sd.start + off) & 3u) == 0u)
+							which = fused_match(fc.plan, nrec, blockIdx.x == 0 && threadIdx.x == 0 && off == 0);
+						which = __shfl_sync(FULL, which, 0);
+						if (which) fused_run(which, fc.sb, fc.plan, lane, 0u, span);
+						else run_block_lowered<false>(fc.sb, fc.plan, lane, 0u, span);
+					}
 				} else {
 					if (other) run_block_fast<false, true>(fc.sb, fc.plan, lane, fc.coeff, span, row_s, row_r, sd.start + off);
 					else run_block_fast<false, false>(fc.sb, fc.plan, lane, fc.coeff, span, row_s, row_r, sd.start + off);

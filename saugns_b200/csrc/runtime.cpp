@@ -47,6 +47,7 @@ cudaError_t launch_planes_to_pcm(const float *d_mix, uint32_t plane_stride, uint
 cudaError_t launch_selftest(const float *d_tables, unsigned long long *d_bad, cudaStream_t stream);
 int device_sm_count();
 size_t device_smem_optin();
+cudaError_t read_signature_dump(uint32_t out[36]);
 }
 
 using namespace saugen;
@@ -2071,6 +2072,13 @@ extern "C" long long saugen_selftest(int device, const saugen_WaveTables *tables
 	cudaFree(d_bad);
 	if (e != cudaSuccess) { set_err("saugen_selftest", e); return -1; }
 	return (long long) h_bad;
+}
+/* developer aid (not in the header): out[0] = records, out[1..] = their codes (render_fast.cuh:rec_code) */
+extern "C" int saugen_debug_signature(saugen_Generator *o, uint32_t out[36]) {
+	if (!o) return -1;
+	cudaSetDevice(o->device);
+	cudaStreamSynchronize(o->stream);
+	return read_signature_dump(out) == cudaSuccess ? 0 : -1;
 }
 extern "C" float saugen_amp_scale(saugen_Generator *o) { return o ? o->amp_scale : 0.f; }
 extern "C" const char *saugen_last_error(void) { return g_err.c_str(); }
