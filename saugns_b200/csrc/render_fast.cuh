@@ -552,6 +552,16 @@ using ShapePM2     = Shape<FOsc<0, 0, 0, false, false, false, false>,
                            FOsc<0, 2, 0, false, false, false, false>, FVout<true>>;                 /* carrier + one PM modulator */
 using ShapeC3PM    = Shape<FOsc<0, 0, 0, false, false, false, false>, FOsc<0, 2, 1, false, false, false, false>,
                            FOsc<0, 2, 2, false, false, false, false>, FVout<true>>;                 /* 3-operator PM chain, lin / xpe ramps */
+using ShapeC3PMh   = Shape<FOsc<0, 0, 0, false, false, false, false>, FOsc<0, 2, 0, false, false, false, false>,
+                           FOsc<0, 2, 2, false, false, false, false>, FVout<true>>;                 /* ... once the modulator's ramp has ended */
+using ShapePM3     = Shape<FOsc<0, 0, 0, false, false, false, false>, FOsc<0, 2, 0, false, false, false, false>,
+                           FOsc<0, 2, 0, false, false, false, false>, FVout<true>>;                 /* ... all amplitudes held */
+using ShapeC3FMh   = Shape<FOsc<0, 0, 0, true, false, false, false>, FRange<true, true>,
+                           FOsc<2, 0, 0, false, false, false, true>, FOsc<1, 2, 2, false, false, false, false>,
+                           FVout<true>>;                                                             /* range-FM, modulator ramp ended */
+using ShapeFM3h    = Shape<FOsc<0, 0, 0, true, false, false, false>, FRange<true, true>,
+                           FOsc<2, 0, 0, false, false, false, true>, FOsc<1, 2, 0, false, false, false, false>,
+                           FVout<true>>;                                                             /* ... all amplitudes held */
 using ShapeC3FM    = Shape<FOsc<0, 0, 1, true, false, false, false>, FRange<true, true>,
                            FOsc<2, 0, 0, false, false, false, true>, FOsc<1, 2, 2, false, false, false, false>,
                            FVout<true>>;                                                             /* range-FM carrier + ratio PM modulator */
@@ -573,11 +583,15 @@ __device__ __noinline__ uint32_t fused_match(uint32_t plan, uint32_t nrec, bool 
 		g_sig_dump[0] = n;
 		for (uint32_t i = 0; i < n; ++i) g_sig_dump[1 + i] = codes[i];
 	}
+	if (ShapeC3PMh::match(codes, n)) return 6;
+	if (ShapeC3FMh::match(codes, n)) return 7;
 	if (ShapeC3PM::match(codes, n)) return 1;
 	if (ShapeC3FM::match(codes, n)) return 2;
 	if (ShapePM2::match(codes, n)) return 3;
 	if (ShapeW1::match(codes, n)) return 4;
 	if (ShapeW1x::match(codes, n)) return 5;
+	if (ShapePM3::match(codes, n)) return 8;
+	if (ShapeFM3h::match(codes, n)) return 9;
 	return FUSED_NONE;
 }
 __device__ __forceinline__ void fused_run(uint32_t which, uint32_t sb, uint32_t plan, int lane, uint32_t oc0, uint32_t len) {
@@ -586,6 +600,10 @@ __device__ __forceinline__ void fused_run(uint32_t which, uint32_t sb, uint32_t 
 	case 2: ShapeC3FM::run(sb, plan, lane, oc0, len); break;
 	case 3: ShapePM2::run(sb, plan, lane, oc0, len); break;
 	case 4: ShapeW1::run(sb, plan, lane, oc0, len); break;
-	default: ShapeW1x::run(sb, plan, lane, oc0, len); break;
+	case 5: ShapeW1x::run(sb, plan, lane, oc0, len); break;
+	case 6: ShapeC3PMh::run(sb, plan, lane, oc0, len); break;
+	case 7: ShapeC3FMh::run(sb, plan, lane, oc0, len); break;
+	case 8: ShapePM3::run(sb, plan, lane, oc0, len); break;
+	default: ShapeFM3h::run(sb, plan, lane, oc0, len); break;
 	}
 }

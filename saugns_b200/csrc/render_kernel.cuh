@@ -130,20 +130,21 @@ __device__ __noinline__ void render_units(Ctx &c, FastCtx &fc, const CallDesc *c
 					if (lane == 0) plan_lower(fc.plan + PLAN_HDR, nrec);
 					__syncwarp();
 					/* few voices: the stretch is split along time over the voice's team of warps */
+					/* a listed signature runs as one straight-line function (fused shapes);
+					 * segments starting at an odd frame keep to the general voice output */
+					uint32_t which = 0;
+					if (!other) {
+						if (lane == 0 && ((sd.start + off) & 3u) == 0u && !(fc.wave_mask & NOFUSE_FLAG))
+							which = fused_match(fc.plan, nrec, blockIdx.x == 0 && threadIdx.x == 0);
+						which = __shfl_sync(FULL, which, 0);
+					}
+					/* few voices: the stretch is split along time over the voice's team of warps */
 					const bool shared = fc.team && !other &&
-						team_stretch(*fc.team, fc.sb, lane, fc.plan, nrec, vs.ops_cnt, span);
+						team_stretch(*fc.team, fc.sb, lane, fc.plan, nrec, vs.ops_cnt, span, which);
 					if (shared) { }
 					else if (other) run_block_lowered<true>(fc.sb, fc.plan, lane, 0u, span);
-					else {
-						/* a listed signature runs as one straight-line function (fused shapes);
-						 * segments starting at an odd frame keep to the general voice output */
-						uint32_t which = 0;
-						if (lane == 0 && ((sd.start + off) & 3u) == 0u)
-							which = fused_match(fc.plan, nrec, blockIdx.x == 0 && threadIdx.x == 0 && off == 0);
-						which = __shfl_sync(FULL, which, 0);
-						if (which) fused_run(which, fc.sb, fc.plan, lane, 0u, span);
-						else run_block_lowered<false>(fc.sb, fc.plan, lane, 0u, span);
-					}
+					else if (which) fused_run(which, fc.sb, fc.plan, lane, 0u, span);
+					else run_block_lowered<false>(fc.sb, fc.plan, lane, 0u, span);
 				} else {
 					if (other) run_block_fast<false, true>(fc.sb, fc.plan, lane, fc.coeff, span, row_s, row_r, sd.start + off);
 					else run_block_fast<false, false>(fc.sb, fc.plan, lane, fc.coeff, span, row_s, row_r, sd.start + off);
@@ -205,7 +206,7 @@ __device__ __forceinline__ void render_body(const CallDesc *calls, uint32_t ncal
 	uint64_t *bar = reinterpret_cast<uint64_t*>(smem);
 	float *tab = reinterpret_cast<float*>(smem + 128);
 	const bool ctab = (wave_mask & CTAB_FLAG) != 0;
-	const uint32_t nslots = __popc(wave_mask & ~CTAB_FLAG);
+	const uint32_t nslots = __popc(wave_mask & 0xfffu);
 	const uint32_t slot_bytes = ctab ? CTAB_WAVE_BYTES : TAB_STRIDE * (uint32_t) sizeof(float);
 	unsigned char *warp_area = smem + 128 + nslots * slot_bytes;
 	const uint32_t per_warp = warp_smem_bytes(nbufs, nslots_ops, nplan, team);

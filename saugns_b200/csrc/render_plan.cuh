@@ -306,7 +306,7 @@ __device__ __noinline__ uint32_t steady_plan(OpState *sops, uint32_t so, uint32_
 			memcpy(&leave, &raw_leave, sizeof(leave));
 			if (mix.opcode != I_MIX || mix.b != in.a || leave.opcode != I_LEAVE || leave.op != in.op) return 0;
 			const uint32_t wave = o->mode;
-			const uint32_t slot = __popc(wave_mask & ((1u << wave) - 1u));
+			const uint32_t slot = __popc(wave_mask & 0xfffu & ((1u << wave) - 1u));
 			const uint32_t ct = (wave_mask & CTAB_FLAG) ? st + slot * CTAB_WAVE_BYTES :
 				st + slot * (TAB_STRIDE * 4) + 12;
 			if (!depth) return 0;
@@ -380,7 +380,7 @@ __device__ __noinline__ uint32_t steady_plan(OpState *sops, uint32_t so, uint32_
 			}
 			if (in.c != NO_BUF) touch(in.c);
 			const uint32_t wave = o->mode;
-			const uint32_t slot = __popc(wave_mask & ((1u << wave) - 1u));
+			const uint32_t slot = __popc(wave_mask & 0xfffu & ((1u << wave) - 1u));
 			const uint32_t ct = (wave_mask & CTAB_FLAG) ? st + slot * CTAB_WAVE_BYTES :
 				st + slot * (TAB_STRIDE * 4) + 12;                   /* planes, or &lut[-1] */
 			const bool aconst = !(LM_FLAGS(o->lmeta[LINE_AMP]) & SAUABI_LINEP_GOAL);

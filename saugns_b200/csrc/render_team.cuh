@@ -32,7 +32,8 @@ constexpr uint32_t TEAM_INELIGIBLE = 0xffu;
 constexpr uint32_t TEAM_MAX_P = 6;
 constexpr uint32_t OS_PAD0 = 184, OS_PAD1 = 188;      /* OpState::_pad: a member's count / its start value */
 static_assert(offsetof(OpState, _pad) == OS_PAD0, "OpState::_pad offset");
-constexpr uint32_t TC_OP = 0, TC_NREC = 4, TC_NOPS = 8, TC_CHUNKS = 12, TC_P = 16, TC_TEFF = 20;   /* the command block */
+constexpr uint32_t TC_OP = 0, TC_NREC = 4, TC_NOPS = 8, TC_CHUNKS = 12, TC_P = 16, TC_TEFF = 20,
+	TC_FUSED = 24;       /* the command block */
 
 __device__ __forceinline__ void team_bar(uint32_t id, uint32_t nthreads) {
 	asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(nthreads) : "memory");
@@ -191,6 +192,7 @@ struct TeamCtx {
 __device__ __noinline__ void team_run(const TeamCtx &tc, uint32_t sb, int lane) {
 	const uint32_t nrec = lds32(tc.cmd + TC_NREC), nops = lds32(tc.cmd + TC_NOPS), C = lds32(tc.cmd + TC_CHUNKS);
 	const uint32_t P = lds32(tc.cmd + TC_P), t_eff = lds32(tc.cmd + TC_TEFF);
+	const uint32_t fused = lds32(tc.cmd + TC_FUSED);       /* the plan spells a listed shape (render_fast.cuh) */
 	const uint32_t w = tc.rank, nthreads = tc.T * 32u;
 	const bool active = w < t_eff;
 	const uint32_t L = P + 1u;
@@ -280,7 +282,11 @@ __device__ __noinline__ void team_run(const TeamCtx &tc, uint32_t sb, int lane) 
 			__syncwarp();
 			if (lane == 0) sts32(vout, (lds32(vout) & ~0xffu) | X_VOUT);
 		}
-		run(cur, a_next);
+		__syncwarp();
+		if (fused && a_next > cur)         /* the member's own range: the full plan, as one straight-line function */
+			fused_run(fused, sb, tc.plan_x, lane, cur * (uint32_t) CHUNK, (a_next - cur) * (uint32_t) CHUNK);
+		else run(cur, a_next);
+		__syncwarp();
 	}
 	__threadfence_block();
 	team_bar(tc.bar, nthreads);
@@ -290,7 +296,7 @@ __device__ __noinline__ void team_run(const TeamCtx &tc, uint32_t sb, int lane) 
  * it is not eligible (the caller renders it alone); else the stretch is rendered and the voice's
  * operator accumulators / look-back values (tc.so_a) are those after it. */
 __device__ __noinline__ bool team_stretch(const TeamCtx &tc, uint32_t sb, int lane, uint32_t plan, uint32_t nrec,
-		uint32_t nops, uint32_t span) {
+		uint32_t nops, uint32_t span, uint32_t fused) {
 	const uint32_t C = span / (uint32_t) CHUNK;
 	uint32_t P = 0;
 	if (lane == 0) P = team_analyse(plan + PLAN_HDR, nrec);
@@ -304,6 +310,7 @@ __device__ __noinline__ bool team_stretch(const TeamCtx &tc, uint32_t sb, int la
 	if (lane == 0) {
 		sts32(tc.cmd + TC_OP, 1u); sts32(tc.cmd + TC_NREC, nrec); sts32(tc.cmd + TC_NOPS, nops);
 		sts32(tc.cmd + TC_CHUNKS, C); sts32(tc.cmd + TC_P, P); sts32(tc.cmd + TC_TEFF, t_eff);
+		sts32(tc.cmd + TC_FUSED, fused);
 	}
 	__syncwarp();
 	__threadfence_block();

@@ -1282,10 +1282,12 @@ static Shape pick_shape(uint32_t ntasks, uint32_t wave_mask, uint32_t nbufs, uin
 	/* coefficient planes (48 KiB per wave): two waves leave room for a full CTA of voices; with few
 	 * voices (fewer warps) up to four waves' planes fit beside them */
 	const bool want_ctab = have_coefs && nw >= 1 && nw <= 4 && !(env && env[0] == '0');
+	static const char *fenv = getenv("SAUGEN_FUSED");     /* developer knob: 0 = no fused shapes */
+	const uint32_t nofuse = (fenv && fenv[0] == '0') ? 0x40000000u : 0u;
 	Shape sh;
 	sh.team = 1;
 	for (int pass = want_ctab ? 0 : 1; pass < 2; ++pass) {
-		sh.mask = pass == 0 ? (wave_mask | CTAB_FLAG) : wave_mask;
+		sh.mask = (pass == 0 ? (wave_mask | CTAB_FLAG) : wave_mask) | nofuse;
 		uint32_t fit = 28;                 /* kernels.cu:WIDE_WARPS */
 		while (fit > 1 && render_smem_bytes(sh.mask, nbufs, max_ops, nplan, fit, 1) > SMEM_CAP) --fit;
 		sh.warps = (ntasks + sms - 1) / sms;
