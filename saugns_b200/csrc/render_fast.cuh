@@ -66,6 +66,10 @@ __device__ __noinline__ void plan_lower(uint32_t plan, uint32_t nrec) {
 				if (fs && src == prev_out && pm != 2u) xf |= XF_SRC_VAL;
 				sts32(a, (w0 & ~0xffu) | (X_OSC0 + 3u * fs + pm));
 				sts32(a + 4, (w1 & 0xffffu) | xf << 16);
+				/* second half reordered for the lowered code: {diff_scale, inc / v0} are needed early
+				 * (one 64-bit load), {diff_offset, held amplitude} late (another) */
+				const uint32_t doff = lds32(a + 20), incv = lds32(a + 24);
+				sts32(a + 20, incv); sts32(a + 24, doff);
 				out = bufa;
 			}
 			if (fl & PF_AEXT) ++r;             /* the second slot */
@@ -117,11 +121,11 @@ __device__ __noinline__ void plan_lower(uint32_t plan, uint32_t nrec) {
  * {i0, i1, prev_Is} group, already loaded.  Returns the accumulator after the chunk (what
  * lane 31 writes back with the oscillator's look-back values, xosc_core). */
 template <int FS, int PM>
-__device__ __forceinline__ uint32_t xphase(const HotCtx &c, const uint4 p0, const uint32_t rec, const uint32_t xf,
+__device__ __forceinline__ uint32_t xphase(const HotCtx &c, const uint4 p0, const uint32_t incv, const uint32_t xf,
 		const uint4 st, const float val[4], uint32_t ph[4]) {
 	uint32_t acc;
 	if (FS == 0) {
-		const uint32_t inc = lds32(rec + 24);
+		const uint32_t inc = incv;
 		const uint32_t base = st.x + inc * (uint32_t) (c.lane * 4);
 #pragma unroll
 		for (int k = 0; k < 4; ++k) ph[k] = base + inc * (uint32_t) (k + 1);
@@ -136,7 +140,7 @@ __device__ __forceinline__ uint32_t xphase(const HotCtx &c, const uint4 p0, cons
 			fld<4>(c, src, fr);
 		}
 		if (FS == 2) {                 /* a constant ratio to a modulated parent frequency (line.c:417-445, no goal) */
-			const float v0 = lds32f(rec + 24);
+			const float v0 = __uint_as_float(incv);
 #pragma unroll
 			for (int k = 0; k < 4; ++k) fr[k] = v0 * fr[k];
 		}
@@ -167,8 +171,8 @@ __device__ __forceinline__ uint32_t xphase(const HotCtx &c, const uint4 p0, cons
 
 /* sauWOsc_run (wosc.h:238-266) at the phases ph -> s; the accumulator `acc` and the look-back
  * values go back in one 128-bit store by lane 31 */
-__device__ __forceinline__ void xosc_core(const HotCtx &c, const uint4 p0, const uint32_t rec, const uint4 st,
-		const uint32_t acc, const uint32_t ph[4], float s[4]) {
+__device__ __forceinline__ float xosc_core(const HotCtx &c, const uint4 p0, const uint32_t rec, const uint4 st,
+		const uint32_t acc, const float ds, const uint32_t ph[4], float s[4]) {
 	const uint32_t op = p0.z;
 	uint32_t pph = __shfl_up_sync(FULL, ph[3], 1);
 	if (c.lane == 0) pph = lds32(op + OS_I1);
@@ -176,10 +180,9 @@ __device__ __forceinline__ void xosc_core(const HotCtx &c, const uint4 p0, const
 	d[0] = (int32_t) (ph[0] - pph);
 #pragma unroll
 	for (int k = 1; k < 4; ++k) d[k] = (int32_t) (ph[k] - ph[k - 1]);
-	const float2 dd = lds64f(rec + 16);
 	float xq[4];
 #pragma unroll
-	for (int k = 0; k < 4; ++k) xq[k] = div_scale_by_int(dd.x, d[k]);      /* wosc.h:254-256 */
+	for (int k = 0; k < 4; ++k) xq[k] = div_scale_by_int(ds, d[k]);        /* wosc.h:254-256 */
 	double Is[4];
 #pragma unroll
 	for (int k = 0; k < 4; ++k) {
@@ -195,6 +198,7 @@ __device__ __forceinline__ void xosc_core(const HotCtx &c, const uint4 p0, const
 		pIs = __hiloint2double((int) pg.y, (int) pg.x);
 	}
 	__syncwarp();              /* lane 0 holds the look-back values before lane 31 rewrites them */
+	const float2 late = lds64f(rec + 24);          /* diff_offset, held amplitude */
 	bool z = false;
 #pragma unroll
 	for (int k = 0; k < 4; ++k) z |= (d[k] == 0);
@@ -214,7 +218,7 @@ __device__ __forceinline__ void xosc_core(const HotCtx &c, const uint4 p0, const
 #pragma unroll
 		for (int k = 0; k < 4; ++k) s[k] = sv.v[k];
 	} else {
-		const double doff = (double) dd.y;
+		const double doff = (double) late.x;
 #pragma unroll
 		for (int k = 0; k < 4; ++k) {
 			const double dI = Is[k] - (k ? Is[k - 1] : pIs);
@@ -226,14 +230,14 @@ __device__ __forceinline__ void xosc_core(const HotCtx &c, const uint4 p0, const
 			sts32(op + OS_PREVS, __float_as_uint(s[3]));
 		}
 	}
+	return late.y;
 }
 
 /* the operator's amplitude for this lane's samples: held, or on a lin / xpe / lge trajectory
  * (sauLine_fill_lin / _xpe / _lge, line.c:65-140, from the stretch constants in the second slot) */
 template <int AMP>
-__device__ __forceinline__ void xamp(const HotCtx &c, const uint32_t rec, float am[4]) {
+__device__ __forceinline__ void xamp(const HotCtx &c, const uint32_t rec, const float av, float am[4]) {
 	if (AMP == 0) {
-		const float av = lds32f(rec + 28);
 #pragma unroll
 		for (int k = 0; k < 4; ++k) am[k] = av;
 		return;
@@ -286,26 +290,28 @@ __device__ __forceinline__ void run_chunk_lowered(const HotCtx &c) {
 		if (kind < X_RANGE) {
 			uint4 st;                                /* i0 now; i1, prev_Is where they are needed (xosc_core) */
 			st.x = lds32(p0.z + OS_I0); st.y = st.z = st.w = 0u;
+			const float2 early = lds64f(rec + 16);         /* diff_scale, inc / v0 */
+			const uint32_t incv = __float_as_uint(early.y);
 			uint32_t ph[4], acc;
 			switch (kind - X_OSC0) {
-			case 0: acc = xphase<0, 0>(c, p0, rec, xf, st, val, ph); break;
-			case 1: acc = xphase<0, 1>(c, p0, rec, xf, st, val, ph); break;
-			case 2: acc = xphase<0, 2>(c, p0, rec, xf, st, val, ph); break;
-			case 3: acc = xphase<1, 0>(c, p0, rec, xf, st, val, ph); break;
-			case 4: acc = xphase<1, 1>(c, p0, rec, xf, st, val, ph); break;
-			case 5: acc = xphase<1, 2>(c, p0, rec, xf, st, val, ph); break;
-			case 6: acc = xphase<2, 0>(c, p0, rec, xf, st, val, ph); break;
-			case 7: acc = xphase<2, 1>(c, p0, rec, xf, st, val, ph); break;
-			default: acc = xphase<2, 2>(c, p0, rec, xf, st, val, ph); break;
+			case 0: acc = xphase<0, 0>(c, p0, incv, xf, st, val, ph); break;
+			case 1: acc = xphase<0, 1>(c, p0, incv, xf, st, val, ph); break;
+			case 2: acc = xphase<0, 2>(c, p0, incv, xf, st, val, ph); break;
+			case 3: acc = xphase<1, 0>(c, p0, incv, xf, st, val, ph); break;
+			case 4: acc = xphase<1, 1>(c, p0, incv, xf, st, val, ph); break;
+			case 5: acc = xphase<1, 2>(c, p0, incv, xf, st, val, ph); break;
+			case 6: acc = xphase<2, 0>(c, p0, incv, xf, st, val, ph); break;
+			case 7: acc = xphase<2, 1>(c, p0, incv, xf, st, val, ph); break;
+			default: acc = xphase<2, 2>(c, p0, incv, xf, st, val, ph); break;
 			}
 			float s[4];
-			xosc_core(c, p0, rec, st, acc, ph, s);
+			const float av = xosc_core(c, p0, rec, st, acc, early.x, ph, s);
 			float am[4];
 			switch ((xf >> XF_AMP_SHIFT) & 3u) {
-			case 0: xamp<0>(c, rec, am); break;
-			case 1: xamp<1>(c, rec, am); break;
-			case 2: xamp<2>(c, rec, am); break;
-			default: xamp<3>(c, rec, am); break;
+			case 0: xamp<0>(c, rec, av, am); break;
+			case 1: xamp<1>(c, rec, av, am); break;
+			case 2: xamp<2>(c, rec, av, am); break;
+			default: xamp<3>(c, rec, av, am); break;
 			}
 			if (flags & PF_WAVEENV) {                                     /* generator.c:407-426 */
 #pragma unroll
@@ -355,7 +361,7 @@ __device__ __forceinline__ void run_chunk_lowered(const HotCtx &c) {
 				fld<4>(c, src, fr);
 			}
 			if (kind == X_COUNT2) {
-				const float v0 = lds32f(rec + 24);
+				const float v0 = lds32f(rec + 20);
 #pragma unroll
 				for (int k = 0; k < 4; ++k) fr[k] = v0 * fr[k];
 			}
@@ -444,13 +450,14 @@ struct FOsc {
 		(ST ? 0x100u : 0u) | (SRCVAL ? 0x200u : 0u);
 	static __device__ __forceinline__ void exec(const HotCtx &c, const uint32_t rec, float val[4]) {
 		const uint4 p0 = lds128u(rec);
+		const float2 early = lds64f(rec + 16);             /* diff_scale, inc / v0 */
 		uint4 st;
 		st.x = lds32(p0.z + OS_I0); st.y = st.z = st.w = 0u;
 		uint32_t ph[4];
-		const uint32_t acc = xphase<FS, PM>(c, p0, rec, SRCVAL ? XF_SRC_VAL : 0u, st, val, ph);
+		const uint32_t acc = xphase<FS, PM>(c, p0, __float_as_uint(early.y), SRCVAL ? XF_SRC_VAL : 0u, st, val, ph);
 		float s[4], am[4];
-		xosc_core(c, p0, rec, st, acc, ph, s);
-		xamp<AMP>(c, rec, am);
+		const float av = xosc_core(c, p0, rec, st, acc, early.x, ph, s);
+		xamp<AMP>(c, rec, av, am);
 		const uint32_t bufa = (p0.x >> 16) & 0xffu;
 		if (ENV) {
 #pragma unroll

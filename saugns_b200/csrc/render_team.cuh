@@ -59,7 +59,7 @@ __device__ __noinline__ uint32_t team_analyse(uint32_t plan, uint32_t nrec) {
 			if (bufa >= 32u) return TEAM_INELIGIBLE;
 			if (fs == 0) {
 				A = 0;
-				if (pm == 0 && lds32(a + 24) == 0u) return TEAM_INELIGIBLE;     /* stands still */
+				if (pm == 0 && lds32(a + 20) == 0u) return TEAM_INELIGIBLE;     /* stands still */
 			} else {
 				const uint32_t src = fs == 1 ? bufb : (w1 >> 8) & 0xffu;
 				if (!(xf & XF_SRC_VAL) && src >= 32u) return TEAM_INELIGIBLE;
@@ -174,7 +174,7 @@ __device__ __noinline__ void team_patch(uint32_t exec, uint32_t k, uint32_t at, 
 		if (kind == P_STOP || a - exec > PLAN_WALK_MAX) break;
 		const bool osc = kind >= X_OSC0 && kind < X_RANGE, cnt = kind == X_COUNT1 || kind == X_COUNT2;
 		if (!(osc || cnt) || ((x.y >> 24) & 0xfu) != k) continue;
-		if (k == 0) sts32(x.z + OS_I0, lds32(x.z + OS_I0) + lds32(a + 24) * (at * (uint32_t) CHUNK));
+		if (k == 0) sts32(x.z + OS_I0, lds32(x.z + OS_I0) + lds32(a + 20) * (at * (uint32_t) CHUNK));
 		else sts32(x.z + OS_I0, zero ? 0u : lds32(x.z + OS_PAD1));
 	}
 }
