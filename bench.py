@@ -471,6 +471,10 @@ def run_gpu_arm(args):
             extra["c3_voice_sharded"] = leg_c3_sharded(args, dist, rank, local_rank, world)
         except Exception as e:      # an extra leg never takes the headline line down
             extra["c3_voice_sharded"] = {"error": repr(e)}
+        try:
+            extra["c5_script_sharded"] = leg_c5_sharded(args, dist, rank, local_rank, world)
+        except Exception as e:
+            extra["c5_script_sharded"] = {"error": repr(e)}
 
     if rank != 0:
         if dist is not None:
@@ -755,6 +759,57 @@ def leg_c5(args, device, clocks):
     return leg
 
 
+def leg_c5_sharded(args, dist, rank, local_rank, world):
+    """BASELINE config 5 over the ranks: `--scripts` scripts PER GPU (1250 x 8 = the 10 000), script i
+    on rank i % world, every rank through the native batched driver with its WAV files written to
+    a RAM disk; no collective on the data path.  Wall clock from a barrier to the last rank's end."""
+    import shutil
+    import tempfile
+    import torch
+    from saugns_b200 import workloads, batch
+    from saugns_b200 import program as P
+    n_total = args.scripts * world
+    mine = list(range(rank, n_total, world))
+    prgs = [workloads.build_c5_script(i) for i in mine]
+    vs = 0
+    for p in prgs:
+        pp = P.Program.from_address(p.ptr)
+        for e in range(pp.ev_count):
+            ev = pp.events[e]
+            for k in range(ev.op_data_count):
+                if ev.op_data[k].id == ev.carr_op_id:
+                    vs += ev.op_data[k].time.v_ms * SRATE // 1000
+    ramdisk = "/dev/shm" if os.path.isdir("/dev/shm") else None
+    tmp = tempfile.mkdtemp(prefix=f"c5r{rank}_", dir=ramdisk)
+    try:
+        batch.render_batch_native(prgs[:32], srate=SRATE, device=local_rank, group_size=16)      # warm-up
+        torch.cuda.synchronize()
+        paths = [os.path.join(tmp, f"g{i}.wav") for i in mine]
+        dist.barrier()
+        t0 = time.perf_counter()
+        batch.render_batch_native(prgs, srate=SRATE, device=local_rank, group_size=args.group, depth=args.depth,
+                                  call_len=args.call_frames, wav_paths=paths, io_threads=4)
+        wall = time.perf_counter() - t0
+        nbytes = sum(os.path.getsize(p) for p in paths)
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    t = torch.tensor([wall, float(vs), float(nbytes)], dtype=torch.float64, device="cuda")
+    tmax = t.clone()
+    dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    wall_max, vs_all, bytes_all = float(tmax[0].item()), float(t[1].item()), float(t[2].item())
+    if rank != 0:
+        return None
+    return {"metric": METRIC, "unit": "voice-samples/s", "scaling": "weak", "n_gpus": world,
+            "value": vs_all / wall_max, "scripts": n_total, "scripts_per_s": n_total / wall_max,
+            "wall_s": wall_max, "wav_bytes": bytes_all,
+            "config": {"workload": f"C5: {n_total} independent mixed scripts dealt to {world} GPUs ({args.scripts} each), "
+                                   f"every WAV file written to a RAM disk", "srate": SRATE,
+                       "call_frames": args.call_frames, "group": args.group},
+            "timed": "per rank: saugen_render_batch_wav over its scripts (create + batched calls + destroy + "
+                     "4 writer threads); wall clock, max over ranks; programs built beforehand"}
+
+
 def leg_c3_sharded(args, dist, rank, local_rank, world, steps=20, warmup=3):
     """ONE C3 script (seed 1), its voices spread over the ranks (strong scaling): each rank
     renders its voices' float mix planes, one NCCL sum-reduce per call, the root converts.
@@ -772,6 +827,9 @@ def leg_c3_sharded(args, dist, rank, local_rank, world, steps=20, warmup=3):
             first.append(pcm.copy())
     dist.barrier()
     torch.cuda.synchronize()
+    gen = getattr(vg.shard, "gen", None)
+    if gen is not None:
+        gen.set_timing(True)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(steps):
@@ -782,6 +840,12 @@ def leg_c3_sharded(args, dist, rank, local_rank, world, steps=20, warmup=3):
     t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
+    # each rank's own kernels (device-timed, per call): what the collective and the host add is ms/steps minus these
+    km = gen.kernel_ms() if gen is not None else (0.0, 0.0)
+    per_rank = torch.zeros(2 * world, dtype=torch.float64, device="cuda")
+    per_rank[2 * rank], per_rank[2 * rank + 1] = km[0] / steps, km[1] / steps
+    dist.all_reduce(per_rank)
+    per_rank = [round(float(x), 4) for x in per_rank.tolist()]
     ncoll = getattr(vg, "collectives", None)
     if ncoll is not None:
         ncoll = ncoll / float(warmup + steps)
@@ -810,6 +874,7 @@ def leg_c3_sharded(args, dist, rank, local_rank, world, steps=20, warmup=3):
                                       "float L/R planes per call, PCM on the root's host buffer",
                           "voices": VOICES, "frames_per_step": FRAMES},
                "collectives_per_call": ncoll,
+               "shard_render_ms_per_call": per_rank[0::2], "shard_mix_ms_per_call": per_rank[1::2],
                "parity": {"checked": True, "max_lsb": mx, "calls": len(first),
                           "what": "sharded PCM against the same script rendered unsharded on one GPU "
                                   "(the float summation order across ranks differs: <= 1 LSB allowed)"}}

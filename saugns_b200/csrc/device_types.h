@@ -190,7 +190,7 @@ struct GenDesc {
 	float *rows_s, *rows_r;       // carrier rows of a call, frame-tile major (ROW_TILE above; rows_r:
 	                              // only for voices whose pan moves in the segment, see VoiceSeg)
 	VoiceSeg *vlen;               // [seg][n_local_voices] per segment of a call
-	uint32_t *status;             // [0]=any voice still alive, [1+seg]=per-segment max len
+	uint32_t *status;             // (host bookkeeping; the kernels use CallDesc::status)
 	uint32_t vlen_cap;            // segments the vlen/status arrays can hold
 	uint32_t *progress;           // [n_local_voices] units done in the current call (ticketed launches)
 	uint32_t *ticket;             // next (unit, voice) ticket of the current call
@@ -206,6 +206,7 @@ struct GenDesc {
 	float amp_scale;
 	uint32_t wave_mask;           // waves referenced by any op-data
 	const float *tables;          // 12 x 2048 floats, then a WaveCoeffs
+	float *tap;                   // debug (saugen_debug_tap): [op_count][row_len], every operator's output buffer
 };
 
 /* Per-wave constants derived from sauWave_picoeffs (sau/wave.h:33-70,144-149),
@@ -246,6 +247,31 @@ struct CallDesc {
 	                          // plan_call): the voices' alive flag is set by the last launch only
 	int16_t *pcm;             // where this call's PCM goes (two alternate: the call after this one may
 	                          // already be rendering while the caller reads this one's, runtime.cpp run-ahead)
+	uint32_t *status;         // [0]=any voice still alive, [1+seg]=per-segment max len; one per call slot (the
+	                          // read-back of call k runs on the copy stream while call k+1 renders)
+};
+
+/* A call's descriptors small enough to travel as kernel parameters (prologue_kernel): no
+ * host-to-device copy in front of the render launch. */
+constexpr uint32_t INLINE_SEGS = 16, INLINE_UNITS = 64;
+struct InlineCall {
+	CallDesc cd;
+	uint32_t nseg, nunits;
+	SegDesc segs[INLINE_SEGS];
+	UnitDesc units[INLINE_UNITS];
+};
+/* What the prologue does before a call's render launch (one small kernel instead of a copy, a
+ * memset and the run-ahead snapshot copy): descriptors -> device, [vlen][progress] and the slot's
+ * status zeroed, operator / voice state -> snapshot. */
+struct PrologueArgs {
+	CallDesc *d_call;
+	SegDesc *d_segs;
+	UnitDesc *d_units;
+	uint32_t *zero_a, *zero_b;
+	uint32_t zero_a_words, zero_b_words;
+	const uint4 *snap_src;
+	uint4 *snap_dst;
+	uint32_t snap_n16;        // 0 = no snapshot
 };
 
 } // namespace saugen

@@ -227,6 +227,28 @@ cudaError_t launch_render(const CallDesc *d_calls, uint32_t ncalls, const SegDes
 	return cudaGetLastError();
 }
 
+/* see device_types.h:PrologueArgs */
+__global__ void prologue_kernel(const __grid_constant__ InlineCall ic, const __grid_constant__ PrologueArgs a) {
+	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+	if (blockIdx.x == 0) {
+		if (threadIdx.x == 0) *a.d_call = ic.cd;
+		for (uint32_t i = threadIdx.x; i < ic.nseg; i += blockDim.x) a.d_segs[i] = ic.segs[i];
+		for (uint32_t i = threadIdx.x; i < ic.nunits; i += blockDim.x) a.d_units[i] = ic.units[i];
+	}
+	for (uint32_t i = t; i < a.zero_a_words; i += nt) a.zero_a[i] = 0u;
+	for (uint32_t i = t; i < a.zero_b_words; i += nt) a.zero_b[i] = 0u;
+	for (uint32_t i = t; i < a.snap_n16; i += nt) a.snap_dst[i] = a.snap_src[i];
+}
+cudaError_t launch_prologue(const InlineCall &ic, const PrologueArgs &a, cudaStream_t stream) {
+	const uint32_t work = a.snap_n16 + (a.zero_a_words + a.zero_b_words) / 4u;
+	uint32_t blocks = (work + 1023u) / 1024u;           /* ~4 items per thread */
+	const uint32_t cap = 2u * (uint32_t) device_sm_count();
+	if (blocks > cap) blocks = cap;
+	if (blocks < 1) blocks = 1;
+	prologue_kernel<<<blocks, 256, 0, stream>>>(ic, a);
+	return cudaGetLastError();
+}
+
 cudaError_t launch_mix(const CallDesc *d_calls, uint32_t ncalls, const SegDesc *d_segs,
 		uint32_t max_call_len, uint32_t mode, cudaStream_t stream) {
 	if (ncalls == 0 || max_call_len == 0) return cudaSuccess;

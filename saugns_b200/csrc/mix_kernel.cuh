@@ -87,7 +87,7 @@ mix_kernel(const CallDesc *calls, const SegDesc *segs, uint32_t mode /*0 pcm, 1 
 	if (tid == 0) { seg0 = si; mixed = 0; active = 0; }
 	__syncthreads();
 	if (valid && si != seg0) mixed = 1;
-	if (in_seg && fi < g->status[1 + si]) active = 1;
+	if (in_seg && fi < cd->status[1 + si]) active = 1;
 	if (tid == 0) {
 		for (int st = 0; st < MIX_STAGES; ++st) {
 			mbar_init(&sm.full[st], 1);                /* the producer's arrive.expect_tx */
@@ -100,7 +100,7 @@ mix_kernel(const CallDesc *calls, const SegDesc *segs, uint32_t mode /*0 pcm, 1 
 	if (mixed || seg0 >= cd->nseg) {
 		/* an event boundary inside these frames: each thread walks its own segment's
 		 * voice list straight from global memory (rare) */
-		if (in_seg && fi < g->status[1 + si]) {
+		if (in_seg && fi < cd->status[1 + si]) {
 			const uint2 *vl = reinterpret_cast<const uint2*>(g->vlen + (size_t) si * nlv);
 			for (uint32_t lv = 0; lv < nlv; ++lv) {
 				const uint2 v = vl[lv];

@@ -7,6 +7,7 @@
 __device__ __noinline__ uint32_t run_chunk(Ctx &c, const Instr *code, uint32_t code_len, uint32_t time,
 		uint32_t rem0, float *row_s, float *row_r, uint32_t frame) {
 	c.sp = 0;
+	c.frame = frame;
 	if (c.lane == 0) { c.stk_len[0] = time; c.stk_rem[0] = rem0; c.stk_layer[0] = 0; }
 	__syncwarp();
 	c.pma_flag = false; c.pan_dyn = false;
@@ -43,6 +44,7 @@ __device__ __noinline__ uint32_t run_chunk(Ctx &c, const Instr *code, uint32_t c
 			--c.sp;
 			leave_eval(c, o, in.a, len, c.stk_len[c.sp], layer);
 			__syncwarp();
+			if (c.wave_mask & TAP_FLAG) { tap_store(c, in.op, in.a, c.stk_len[c.sp]); __syncwarp(); }
 			break; }
 		case I_ZERO:
 			*B4(c, in.a) = make_float4(0.f, 0.f, 0.f, 0.f);

@@ -101,7 +101,7 @@ __device__ __noinline__ void render_units(Ctx &c, FastCtx &fc, const CallDesc *c
 			 * unit's blocks as one plan holds */
 			uint32_t sp = 0;
 			if (off % REF_BLOCK == 0 && uend - off >= (uint32_t) REF_BLOCK &&
-					vs.duration >= (uint32_t) REF_BLOCK && vs.code_len &&
+					vs.duration >= (uint32_t) REF_BLOCK && vs.code_len && !(fc.wave_mask & TAP_FLAG) &&
 					op_ptr(c, vs.carr_slot)->time > 0) {
 				uint32_t kb = (uend - off) / (uint32_t) REF_BLOCK;
 				if (vs.duration / (uint32_t) REF_BLOCK < kb) kb = vs.duration / (uint32_t) REF_BLOCK;
@@ -185,7 +185,7 @@ __device__ __noinline__ void render_units(Ctx &c, FastCtx &fc, const CallDesc *c
 			const uint32_t tot = __ldcg(&vsg->len) + run_total;
 			__stcg(reinterpret_cast<uint2*>(vsg), make_uint2(tot, pan_mode));
 			/* the maximum only grows: skip the atomic when it is already there */
-			if (__ldcg(&g->status[1 + si]) < tot) atomicMax(&g->status[1 + si], tot);
+			if (__ldcg(&cd->status[1 + si]) < tot) atomicMax(&cd->status[1 + si], tot);
 		}
 	}
 	if (loaded) ops_store(c, loaded);
@@ -194,7 +194,7 @@ __device__ __noinline__ void render_units(Ctx &c, FastCtx &fc, const CallDesc *c
 #pragma unroll
 		for (uint32_t i = 0; i < sizeof(VoiceState) / 4; ++i)
 			__stcg(reinterpret_cast<uint32_t*>(vsp) + i, w[i]);
-		if (u1 == cd->nunits && !cd->more_launches && vs.duration != 0) atomicOr(&g->status[0], 1u);
+		if (u1 == cd->nunits && !cd->more_launches && vs.duration != 0) atomicOr(&cd->status[0], 1u);
 	}
 }
 

@@ -42,6 +42,7 @@ size_t coef_table_bytes();
 cudaError_t launch_coefs(const float *d_tables, double *d_coefs, uint32_t *d_inexact, cudaStream_t stream);
 cudaError_t launch_mix(const CallDesc *d_calls, uint32_t ncalls, const SegDesc *d_segs,
 		uint32_t max_call_len, uint32_t mode, cudaStream_t stream);
+cudaError_t launch_prologue(const InlineCall &ic, const PrologueArgs &a, cudaStream_t stream);
 cudaError_t launch_planes_to_pcm(const float *d_mix, uint32_t plane_stride, uint32_t n,
 		uint32_t stereo, int16_t *d_pcm, cudaStream_t stream);
 cudaError_t launch_selftest(const float *d_tables, unsigned long long *d_bad, cudaStream_t stream);
@@ -326,6 +327,9 @@ struct saugen_Generator {
 	int device = 0;
 	cudaStream_t stream = nullptr;
 	bool own_stream = false;
+	cudaStream_t aux_stream = nullptr;    /* saugen_mix_to_pcm */
+	cudaStream_t copy_stream = nullptr;   /* read-backs (and saugen_mix_to_pcm): off the kernels' stream, so that
+	                                       * the next call's launches never queue behind a device-to-host copy */
 	uint32_t vo_count = 0, op_count = 0, nlv = 0;
 	uint32_t voice_begin = 0, voice_end = 0;
 	uint32_t row_stride = 0;
@@ -343,6 +347,7 @@ struct saugen_Generator {
 	/* device */
 	GenDesc h_desc;
 	GenDesc *d_desc = nullptr;
+	float *d_tap = nullptr;           /* saugen_debug_tap */
 	float *d_tables = nullptr;
 	double *d_coefs = nullptr;
 	bool ctab_ok = false;              // every voice program is fast-path material (see create)
@@ -371,9 +376,10 @@ struct saugen_Generator {
 		size_t buf_len = 0, host_bytes = 0, gen_base = 0;
 		int stereo = 0;
 		uint32_t mode = 0, nseg = 0;
-		cudaEvent_t done = nullptr;
+		cudaEvent_t done = nullptr;        /* the call's read-back has arrived (copy stream) */
+		cudaEvent_t mixed = nullptr;       /* its kernels are through (launch stream) */
 		cudaEvent_t ev_t[3] = {nullptr, nullptr, nullptr};
-		uint32_t *h_status = nullptr;
+		uint32_t *h_status = nullptr, *d_status = nullptr;
 		int16_t *h_pcm = nullptr, *d_pcm = nullptr;
 		float *d_mix = nullptr;            /* float L / R planes (saugen_run_mix) + MIX_TAIL floats for the caller */
 		CallDesc *h_call = nullptr;        /* pinned staging of the call's descriptors ([call][segs][units]) */
@@ -396,7 +402,7 @@ struct saugen_Generator {
 	/* device time of the two kernels, measured with events on the launch stream */
 	double render_ms = 0.0, mix_ms = 0.0;
 	bool timing = false;
-	size_t zero_bytes = 0, back_bytes_fixed = 0, units_off_in_call = 0;
+	size_t zero_bytes = 0, zero_bytes0 = 0, back_bytes_fixed = 0, units_off_in_call = 0;
 	bool compact = true;               /* [vlen..status] and [status][pcm] still adjacent (no growth yet) */
 	/* every block this generator took from the pool: (pointer, is pinned host) */
 	std::vector<std::pair<void*, bool>> blocks;
@@ -916,14 +922,16 @@ static saugen_Generator *create_from_flat(const Flat &f, const saugen_WaveTables
 		const size_t o_progress = cv.take((nl + 1) * sizeof(uint32_t));   /* [nl] = ticket counter */
 		const size_t o_status = cv.take((1 + o->seg_cap) * sizeof(uint32_t));
 		const size_t o_pcm = cv.take(2 * (size_t) o->row_len * sizeof(int16_t));
-		o->zero_bytes = o_pcm - o_vlen;
+		o->zero_bytes = o_status - o_vlen;             /* [vlen][progress + ticket]; the slot's status apart */
+		o->zero_bytes0 = o_pcm - o_vlen;               /* ... with slot 0's status (the batched calls) */
 		o->back_bytes_fixed = o_pcm - o_status;        /* status part of the read-back */
 		/* two sets of float planes (one per call slot), each followed by MIX_TAIL floats the
 		 * caller may use (multigpu.py folds its control words into the ONE reduced buffer) */
 		const size_t mix_floats = 2 * (size_t) o->row_len + SAUGEN_MIX_TAIL;
 		const size_t o_mix = cv.take(mix_floats * sizeof(float));
 		const size_t o_mix1 = cv.take(mix_floats * sizeof(float));
-		const size_t o_pcm1 = cv.take(2 * (size_t) o->row_len * sizeof(int16_t));      /* the alternate call slot's */
+		const size_t o_status1 = cv.take((1 + o->seg_cap) * sizeof(uint32_t));         /* the alternate call slot's */
+		const size_t o_pcm1 = cv.take(2 * (size_t) o->row_len * sizeof(int16_t));
 		const size_t o_snap = cv.take(zero_bytes);                                      /* run-ahead: state before it */
 		/* written before every call with ONE copy: [call][segs][units] (same layout in
 		 * the pinned block) */
@@ -943,6 +951,7 @@ static saugen_Generator *create_from_flat(const Flat &f, const saugen_WaveTables
 		o->d_call = (CallDesc*) (base + o_call); o->d_segs = (SegDesc*) (base + o_segs);
 		o->d_snap = base + o_snap; o->state_bytes = zero_bytes;
 		o->slot[0].d_pcm = o->d_pcm; o->slot[1].d_pcm = (int16_t*) (base + o_pcm1);
+		o->slot[0].d_status = o->d_status; o->slot[1].d_status = (uint32_t*) (base + o_status1);
 		o->slot[0].d_mix = o->d_mix; o->slot[1].d_mix = (float*) (base + o_mix1);
 		const size_t ntile = ((size_t) o->row_len + ROW_TILE - 1) / ROW_TILE;
 		float *rows = (float*) o->take(false, 2 * ntile * (size_t) o->row_stride * sizeof(float));
@@ -961,6 +970,7 @@ static saugen_Generator *create_from_flat(const Flat &f, const saugen_WaveTables
 		const size_t h_segs1 = hv.take(o->seg_cap * sizeof(SegDesc));
 		const size_t h_units1 = hv.take(o->unit_cap * sizeof(UnitDesc));
 		if (h_units1 - h_call1 != o_units - o_call || h_segs1 - h_call1 != o_segs - o_call) o->compact = false;
+		if (h_pcm1 - h_status1 != o_pcm1 - o_status1) o->compact = false;
 		if (h_pcm - h_status != o_pcm - o_status || h_units - h_call != o_units - o_call ||
 				h_segs - h_call != o_segs - o_call) o->compact = false;
 		unsigned char *hb = (unsigned char*) o->take(true, hv.off);
@@ -1181,9 +1191,13 @@ extern "C" void saugen_destroy(saugen_Generator *o) {
 	if (!o) return;
 	cudaSetDevice(o->device);
 	if (o->stream) cudaStreamSynchronize(o->stream);
+	if (o->copy_stream) { cudaStreamSynchronize(o->copy_stream); g_streams.put(o->device, o->copy_stream); }
+	if (o->aux_stream) { cudaStreamSynchronize(o->aux_stream); g_streams.put(o->device, o->aux_stream); }
+	if (o->d_tap) cudaFree(o->d_tap);
 	for (auto &b : o->blocks) g_pool.release(b.second, o->device, b.first);
 	for (auto &sl : o->slot) {
 		if (sl.done) cudaEventDestroy(sl.done);
+		if (sl.mixed) cudaEventDestroy(sl.mixed);
 		for (int i = 0; i < 3; ++i) if (sl.ev_t[i]) cudaEventDestroy(sl.ev_t[i]);
 	}
 	if (o->own_stream && o->stream) g_streams.put(o->device, o->stream);
@@ -1316,10 +1330,10 @@ static Shape pick_shape(uint32_t ntasks, uint32_t wave_mask, uint32_t nbufs, uin
 static cudaError_t read_back(saugen_Generator *o, uint32_t nseg, size_t host_pcm_bytes, cudaStream_t st,
 		int si = 0) {
 	saugen_Generator::CallSlot &sl = o->slot[si];
-	if (si == 0 && o->compact && host_pcm_bytes)      /* [status][pcm] in one copy */
-		return cudaMemcpyAsync(sl.h_status, o->d_status, o->back_bytes_fixed + host_pcm_bytes,
+	if (o->compact && host_pcm_bytes)                 /* [status][pcm] in one copy */
+		return cudaMemcpyAsync(sl.h_status, sl.d_status, o->back_bytes_fixed + host_pcm_bytes,
 				cudaMemcpyDeviceToHost, st);
-	cudaError_t e = cudaMemcpyAsync(sl.h_status, o->d_status, (1 + nseg) * sizeof(uint32_t),
+	cudaError_t e = cudaMemcpyAsync(sl.h_status, sl.d_status, (1 + nseg) * sizeof(uint32_t),
 			cudaMemcpyDeviceToHost, st);
 	if (e == cudaSuccess && host_pcm_bytes)
 		e = cudaMemcpyAsync(sl.h_pcm, sl.d_pcm, host_pcm_bytes, cudaMemcpyDeviceToHost, st);
@@ -1336,6 +1350,8 @@ static bool ensure_seg_cap(saugen_Generator *o, size_t n) {
 	cudaStreamSynchronize(o->stream);
 	o->d_vlen = (VoiceSeg*) o->take(false, (size_t) cap * nl * sizeof(VoiceSeg));
 	o->d_status = (uint32_t*) o->take(false, (1 + cap) * sizeof(uint32_t));
+	o->slot[0].d_status = o->d_status;
+	o->slot[1].d_status = (uint32_t*) o->take(false, (1 + cap) * sizeof(uint32_t));
 	o->d_segs = (SegDesc*) o->take(false, cap * sizeof(SegDesc));
 	o->h_status = (uint32_t*) o->take(true, (1 + cap) * sizeof(uint32_t));
 	o->h_segs = (SegDesc*) o->take(true, cap * sizeof(SegDesc));
@@ -1358,12 +1374,18 @@ static bool ensure_seg_cap(saugen_Generator *o, size_t n) {
  * stream, an event recorded after them); nothing waits.  host_pcm_bytes: PCM bytes to bring to
  * the slot's pinned staging buffer (0 = none).  <0 on error. */
 static int launch_call(saugen_Generator *o, int si, size_t buf_len, int stereo, uint32_t mode,
-		size_t host_pcm_bytes) {
+		size_t host_pcm_bytes, bool ahead = false) {
 	saugen_Generator::CallSlot &sl = o->slot[si];
 	size_t *out_len = nullptr;
 	std::vector<SegDesc> &segs = o->segs_tmp;
 	plan_call(o, (uint32_t) buf_len, segs);
+	/* (a run-ahead call never grows the tables: the call before it is still in flight on them) */
+	if (ahead && segs.size() > o->seg_cap) return -2;
 	if (!ensure_seg_cap(o, segs.size())) { if (out_len) *out_len = 0; return -1; }
+	if (!o->copy_stream) {
+		o->copy_stream = g_streams.get(o->device);
+		if (!o->copy_stream) { set_err("saugen_run: stream", cudaGetLastError()); return -1; }
+	}
 	const uint32_t nseg = (uint32_t) segs.size();
 	sl.ev_after = o->next_event;
 	memcpy(sl.h_segs, segs.data(), nseg * sizeof(SegDesc));
@@ -1371,8 +1393,9 @@ static int launch_call(saugen_Generator *o, int si, size_t buf_len, int stereo, 
 	 * persistent grid with (unit, voice) tickets, 3 = balanced contiguous ranges.
 	 * Auto picks balanced when the voices would otherwise need a second, partly
 	 * filled wave of warps (between 1 and 4 waves), else one warp per voice. */
-	Shape shape = pick_shape(o->nlv, o->wave_mask, o->nbufs, o->max_ops, o->nplan, o->d_coefs != nullptr,
-			o->sched == 0 || o->sched == 1);
+	Shape shape = pick_shape(o->nlv, o->wave_mask, o->nbufs, o->max_ops, o->nplan, o->d_coefs != nullptr && !o->d_tap,
+			(o->sched == 0 || o->sched == 1) && !o->d_tap);
+	if (o->d_tap) shape.mask |= 0x20000000u;         /* render_ops.cuh:TAP_FLAG */
 	const uint32_t warps = shape.warps;
 	if (!warps) {
 		g_err = "saugen_run: a voice program of this script needs more shared memory than one SM has";
@@ -1426,6 +1449,7 @@ static int launch_call(saugen_Generator *o, int si, size_t buf_len, int stereo, 
 		if (ub && atoi(ub) > 0) unit_blocks = (uint32_t) atoi(ub);
 	}
 	plan_units(segs, o->units_tmp, unit_blocks);
+	if (ahead && o->units_tmp.size() > o->unit_cap) return -2;
 	if (o->units_tmp.size() > o->unit_cap) {
 		uint32_t cap = o->unit_cap;
 		while (cap < o->units_tmp.size()) cap *= 2;
@@ -1456,24 +1480,47 @@ static int launch_call(saugen_Generator *o, int si, size_t buf_len, int stereo, 
 	cd.task_base = 0; cd.stereo = (stereo ? 1u : 0u) | (o->big_endian ? 2u : 0u);
 	cd.unit_off = 0; cd.nunits = gunit[1]; cd.more_launches = ngroups > 1 ? 1u : 0u;
 	cd.pcm = mode == 1 ? (int16_t*) sl.d_mix : sl.d_pcm;      /* (float planes in mode 1) */
+	cd.status = sl.d_status;
 	cudaError_t e;
-	if (o->compact) {
-		/* one copy in ([call][segs][units]), one memset ([vlen][progress][status]) */
-		e = cudaMemcpyAsync(o->d_call, sl.h_call, o->units_off_in_call + nunits * sizeof(UnitDesc),
+	if (o->compact && ngroups == 1 && nseg <= INLINE_SEGS && nunits <= INLINE_UNITS) {
+		/* the usual call: its descriptors travel as kernel parameters of one small kernel that also
+		 * zeroes [vlen][progress] + the slot's status and takes the run-ahead snapshot of the state
+		 * -- no copy-engine work between the previous call's kernels and this call's */
+		InlineCall ic;
+		ic.cd = cd; ic.nseg = nseg; ic.nunits = nunits;
+		memcpy(ic.segs, segs.data(), nseg * sizeof(SegDesc));
+		memcpy(ic.units, o->units_tmp.data(), nunits * sizeof(UnitDesc));
+		PrologueArgs pa;
+		pa.d_call = o->d_call; pa.d_segs = o->d_segs; pa.d_units = o->d_units;
+		pa.zero_a = (uint32_t*) o->d_vlen; pa.zero_a_words = (uint32_t) (o->zero_bytes / 4);
+		pa.zero_b = sl.d_status; pa.zero_b_words = 1 + nseg;
+		pa.snap_src = (const uint4*) o->d_ops; pa.snap_dst = (uint4*) o->d_snap;
+		pa.snap_n16 = ahead ? (uint32_t) ((o->state_bytes + 15) / 16) : 0u;
+		e = launch_prologue(ic, pa, o->stream);
+	} else if (o->compact) {
+		/* one copy in ([call][segs][units]), the memsets ([vlen][progress], [status]) */
+		if (ahead) e = cudaMemcpyAsync(o->d_snap, o->d_ops, o->state_bytes, cudaMemcpyDeviceToDevice, o->stream);
+		else e = cudaSuccess;
+		if (e == cudaSuccess) e = cudaMemcpyAsync(o->d_call, sl.h_call, o->units_off_in_call + nunits * sizeof(UnitDesc),
 				cudaMemcpyHostToDevice, o->stream);
 		if (e == cudaSuccess) e = cudaMemsetAsync(o->d_vlen, 0, o->zero_bytes, o->stream);
+		if (e == cudaSuccess) e = cudaMemsetAsync(sl.d_status, 0, (1 + nseg) * sizeof(uint32_t), o->stream);
 	} else {
+		if (ahead) e = cudaMemcpyAsync(o->d_snap, o->d_ops, o->state_bytes, cudaMemcpyDeviceToDevice, o->stream);
+		else e = cudaSuccess;
+		if (e != cudaSuccess) { set_err("saugen_run: launch", e); return -1; }
 		e = cudaMemcpyAsync(o->d_segs, sl.h_segs, nseg * sizeof(SegDesc), cudaMemcpyHostToDevice, o->stream);
 		if (e == cudaSuccess) e = cudaMemcpyAsync(o->d_units, sl.h_units, nunits * sizeof(UnitDesc), cudaMemcpyHostToDevice, o->stream);
 		if (e == cudaSuccess) e = cudaMemsetAsync(o->d_vlen, 0, (size_t) nseg * (o->nlv ? o->nlv : 1) * sizeof(VoiceSeg), o->stream);
 		if (e == cudaSuccess && ticketed_ctas) e = cudaMemsetAsync(o->d_progress, 0, ((size_t) o->nlv + 1) * sizeof(uint32_t), o->stream);
 		if (e == cudaSuccess) e = cudaMemcpyAsync(o->d_call, sl.h_call, sizeof(CallDesc), cudaMemcpyHostToDevice, o->stream);
-		if (e == cudaSuccess) e = cudaMemsetAsync(o->d_status, 0, (1 + nseg) * sizeof(uint32_t), o->stream);
+		if (e == cudaSuccess) e = cudaMemsetAsync(sl.d_status, 0, (1 + nseg) * sizeof(uint32_t), o->stream);
 	}
 	sl.timed = o->timing;
 	if (sl.timed && !sl.ev_t[0])
 		for (int i = 0; i < 3 && e == cudaSuccess; ++i) e = cudaEventCreate(&sl.ev_t[i]);
 	if (!sl.done && e == cudaSuccess) e = cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming);
+	if (!sl.mixed && e == cudaSuccess) e = cudaEventCreateWithFlags(&sl.mixed, cudaEventDisableTiming);
 	if (e == cudaSuccess && sl.timed) e = cudaEventRecord(sl.ev_t[0], o->stream);
 	for (size_t gi = 0; gi < ngroups && e == cudaSuccess; ++gi) {
 		if (gi > 0) {
@@ -1502,8 +1549,11 @@ static int launch_call(saugen_Generator *o, int si, size_t buf_len, int stereo, 
 		o->counters[1]++;
 	}
 	if (e == cudaSuccess && sl.timed) e = cudaEventRecord(sl.ev_t[2], o->stream);
-	if (e == cudaSuccess) e = read_back(o, nseg, host_pcm_bytes, o->stream, si);
-	if (e == cudaSuccess) e = cudaEventRecord(sl.done, o->stream);
+	/* the read-back: on the copy stream, behind this call's kernels only */
+	if (e == cudaSuccess) e = cudaEventRecord(sl.mixed, o->stream);
+	if (e == cudaSuccess) e = cudaStreamWaitEvent(o->copy_stream, sl.mixed, 0);
+	if (e == cudaSuccess) e = read_back(o, nseg, host_pcm_bytes, o->copy_stream, si);
+	if (e == cudaSuccess) e = cudaEventRecord(sl.done, o->copy_stream);
 	if (e != cudaSuccess) { set_err("saugen_run: launch", e); return -1; }
 	sl.in_flight = true;
 	sl.buf_len = buf_len; sl.stereo = stereo; sl.mode = mode; sl.host_bytes = host_pcm_bytes;
@@ -1609,11 +1659,10 @@ static int run_call(saugen_Generator *o, size_t buf_len, int stereo, uint32_t mo
 	/* the call after this one goes out BEFORE this one is waited for: its state snapshot and
 	 * its kernels queue up behind this call's on the stream, so the GPU runs on while the host
 	 * finishes this call (should this call turn out to be the last, the extra one is undone) */
-	if (o->streak >= 1 && runahead_enabled() &&
-			cudaMemcpyAsync(o->d_snap, o->d_ops, o->state_bytes, cudaMemcpyDeviceToDevice, o->stream) == cudaSuccess) {
+	if (o->streak >= 1 && runahead_enabled() && !o->d_tap) {
 		o->spec_next_event = o->next_event;
 		o->spec_cur_time = o->cur_time;
-		if (launch_call(o, si ^ 1, buf_len, stereo, mode, host_bytes) >= 0) {
+		if (launch_call(o, si ^ 1, buf_len, stereo, mode, host_bytes, true) >= 0) {
 			o->spec_valid = true;
 			o->spec_slot = si ^ 1;
 			o->rows_stale = true;
@@ -1673,13 +1722,18 @@ extern "C" int saugen_mix_to_pcm(saugen_Generator *o, const float *dev_mix, size
 		int stereo, int16_t *host_buf) {
 	if (!o || buf_len > o->row_len) return -1;
 	cudaSetDevice(o->device);
+	/* on a stream of its own: the launch stream and the copy stream may already hold the next call
+	 * (run-ahead), and the conversion of THIS call's reduced planes must not wait behind it
+	 * (mix-mode calls leave d_pcm alone) */
+	if (!o->aux_stream) o->aux_stream = g_streams.get(o->device);
+	cudaStream_t st = o->aux_stream ? o->aux_stream : o->stream;
 	cudaError_t e = launch_planes_to_pcm(dev_mix, o->row_len, (uint32_t) buf_len,
 			(stereo ? 1u : 0u) | (o->big_endian ? 2u : 0u),
-			o->d_pcm, o->stream);
+			o->d_pcm, st);
 	const size_t bytes = buf_len * (stereo ? 2 : 1) * sizeof(int16_t);
 	if (e == cudaSuccess && host_buf)
-		e = cudaMemcpyAsync(o->h_pcm, o->d_pcm, bytes, cudaMemcpyDeviceToHost, o->stream);
-	if (e == cudaSuccess) e = cudaStreamSynchronize(o->stream);
+		e = cudaMemcpyAsync(o->h_pcm, o->d_pcm, bytes, cudaMemcpyDeviceToHost, st);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(st);
 	if (e != cudaSuccess) { set_err("saugen_mix_to_pcm", e); return -1; }
 	if (host_buf) memcpy(host_buf, o->h_pcm, bytes);
 	return 0;
@@ -1776,6 +1830,7 @@ extern "C" int saugen_batch_begin(saugen_Batch *b, saugen_Generator *const *gens
 		cd.seg_off = (uint32_t) b->segs.size(); cd.task_base = ntasks;
 		cd.stereo = (stereo ? 1u : 0u) | (o->big_endian ? 2u : 0u); cd.more_launches = 0;
 		cd.pcm = o->d_pcm;
+		cd.status = o->d_status;
 		{
 			saugen_Generator::CallSlot &sl = o->slot[0];
 			sl.buf_len = buf_len; sl.stereo = stereo; sl.mode = 0; sl.host_bytes = b->bytes;
@@ -1806,7 +1861,7 @@ extern "C" int saugen_batch_begin(saugen_Batch *b, saugen_Generator *const *gens
 			}
 			if (cutu.size() > 1) { cd.nunits = cutu[0]; cd.more_launches = 1; }
 		}
-		if (o->compact) cudaMemsetAsync(o->d_vlen, 0, o->zero_bytes, st);
+		if (o->compact) cudaMemsetAsync(o->d_vlen, 0, o->zero_bytes0, st);
 		else cudaMemsetAsync(o->d_vlen, 0, (size_t) cd.nseg * (o->nlv ? o->nlv : 1) * sizeof(VoiceSeg), st);
 		b->segs.insert(b->segs.end(), o->segs_tmp.begin(), o->segs_tmp.end());
 		b->calls.push_back(cd);
@@ -2081,6 +2136,29 @@ extern "C" int saugen_debug_signature(saugen_Generator *o, uint32_t out[36]) {
 	cudaSetDevice(o->device);
 	cudaStreamSynchronize(o->stream);
 	return read_signature_dump(out) == cudaSuccess ? 0 : -1;
+}
+/* developer aid (tests; not in the header): keep every operator's output buffer of the calls that
+ * follow -- what the reference's run_block leaves in the operator's mix_buf (generator.c:664-730).
+ * The voices then run on the general interpreter only (no steady plans, teams or run-ahead). */
+extern "C" int saugen_debug_tap(saugen_Generator *o) {
+	if (!o) return -1;
+	cudaSetDevice(o->device);
+	cancel_runahead(o);
+	cudaStreamSynchronize(o->stream);
+	if (!o->d_tap) {
+		const size_t bytes = (size_t) (o->h_desc.op_count ? o->h_desc.op_count : 1) * o->row_len * sizeof(float);
+		if (cudaMalloc(&o->d_tap, bytes) != cudaSuccess) return -1;
+		cudaMemset(o->d_tap, 0, bytes);
+		o->h_desc.tap = o->d_tap;
+		if (cudaMemcpy(o->d_desc, &o->h_desc, sizeof(GenDesc), cudaMemcpyHostToDevice) != cudaSuccess) return -1;
+	}
+	return 0;
+}
+extern "C" int saugen_debug_read_tap(saugen_Generator *o, uint32_t op_id, float *out, size_t n) {
+	if (!o || !o->d_tap || op_id >= o->h_desc.op_count || n > o->row_len) return -1;
+	cudaSetDevice(o->device);
+	cudaStreamSynchronize(o->stream);
+	return cudaMemcpy(out, o->d_tap + (size_t) op_id * o->row_len, n * sizeof(float), cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -1;
 }
 extern "C" float saugen_amp_scale(saugen_Generator *o) { return o ? o->amp_scale : 0.f; }
 extern "C" const char *saugen_last_error(void) { return g_err.c_str(); }

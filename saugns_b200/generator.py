@@ -252,6 +252,23 @@ class Generator:
             raise IndexError(vo_id)
         return s, r
 
+    def debug_tap(self):
+        """Developer aid: from now on keep every operator's output buffer of a call (general interpreter only)."""
+        L = lib()
+        L.saugen_debug_tap.restype = C.c_int
+        L.saugen_debug_tap.argtypes = [C.c_void_p]
+        if L.saugen_debug_tap(self.ptr) != 0:
+            raise RuntimeError("saugen_debug_tap")
+
+    def read_tap(self, op_id, n):
+        L = lib()
+        L.saugen_debug_read_tap.restype = C.c_int
+        L.saugen_debug_read_tap.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t]
+        out = np.zeros(n, np.float32)
+        if L.saugen_debug_read_tap(self.ptr, op_id, out.ctypes.data, n) != 0:
+            raise IndexError(op_id)
+        return out
+
     def counters(self):
         out = (C.c_uint64 * 4)()
         lib().saugen_counters(self.ptr, out)

@@ -133,3 +133,11 @@ Wsin t15 f222.r666[Wsin f0.1] p[
 	Wsin r3/7
 ]
 """
+
+
+def long_sweep_script():
+    """Sweeps that run past 2**24 samples at 96 kHz (the as-compiled vector body converts the
+    unsigned position in two halves there), on the shapes that use the unsigned and the signed position."""
+    return ("Wsin f100[g1000 lxpe t180] t180 a0.5 c-0.5\n"
+            "Wtri f2000[g50 llge t178] t180 a0.3[g0.05 lsmo t179] c0.5\n"
+            "Wsaw f300[g600 lcub t177] t180 a0.2[g0.1 lsqe t179.5]\n")

@@ -239,6 +239,53 @@ def test_float_rows_within_1e5(S, ref, tabs):
             assert np.array_equal(s.view(np.uint32), want.view(np.uint32)), name
 
 
+# Modulator buffers (north_star: "float oscillator buffers within 1e-5").  The reference leaves, after a block, an
+# operator's raw oscillator output (tmp_buf) and amplitude buffer in gen_bufs where nothing later reuses them
+# (generator.c:548-605 buffer order); block_mix (generator.c:384-440) of those two is the operator's output.
+# (op id, how the reference's output is rebuilt, gen_bufs indices)
+MOD_TAPS = {
+    "Wsin f200 t0.3 p[Wtri r2 a0.8[g0.1 llin] p[Wsqr r3.5 a0.5]]":
+        [(0, "direct", 0), (1, "mul", 7, 6), (2, "mul", 10, 9)],
+    "Wsin f300.r600[Wtri f7 a0.9] t0.3": [(0, "direct", 0), (1, "env", 8, 7)],
+    "Wsin f300 a1.r0.2[Wsaw f6 p[Wtri f2 a0.3]] t0.3":
+        [(0, "direct", 0), (1, "direct", 5), (1, "env", 9, 8), (2, "mul", 12, 11)],
+    "Wsin f300[Wtri f11 a25] t0.3": [(0, "direct", 0), (1, "direct", 2)],
+    "Wsin f200 t0.3 p.f[Wtri f50 a0.4]": [(0, "direct", 0), (1, "mul", 8, 7)],
+    "Wsin f300 a1.r0.1[Rxpe f9 a0.7] t0.3": [(0, "direct", 0), (1, "direct", 5)],
+    "Wcat f220 t0.5 p.a0.5[Wtri f1 a0.4]": [(0, "direct", 0), (1, "direct", 5)],
+}
+
+
+def test_modulator_buffers_within_1e5(S, ref, tabs):
+    """Every operator's float output buffer (carrier AND modulators, through the debug tap of the general
+    interpreter) vs the reference's gen_bufs, per 1024-frame block."""
+    checked = 0
+    for text, taps in MOD_TAPS.items():
+        prg = ref.Program(text)
+        gr = ref.RefGenerator(prg, 96000)
+        gg = S.Generator(prg, 96000, tables=tabs, max_call_len=1024)
+        gg.debug_tap()
+        for call in range(6):
+            _, pr, n = gr.run(1024)
+            _, pg, ng = gg.run(1024)
+            assert n == ng and np.array_equal(pr, pg), (text, call)
+            for tap in taps:
+                b = [gr.gen_buf(k)[:n] for k in tap[2:]]
+                if tap[1] == "direct":
+                    want = b[0]
+                elif tap[1] == "mul":
+                    want = b[0] * b[1]
+                else:
+                    s_amp = b[1] * np.float32(0.5)
+                    want = b[0] * s_amp + np.abs(s_amp)
+                got = gg.read_tap(tap[0], n)
+                tol = 1e-5 * np.maximum(np.abs(want), 1e-30)
+                assert np.all(np.abs(got - want) <= tol), (text, call, tap)
+                assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (text, call, tap)
+                checked += 1
+    assert checked == 6 * sum(len(t) for t in MOD_TAPS.values())
+
+
 def test_run_many_matches_single(S, ref, tabs):
     """Batched entry point: same PCM as rendering each script alone."""
     texts = [scripts.synth_c5_script(i) for i in range(12)]
@@ -405,6 +452,35 @@ def test_c4_full_voice_count_bit_exact(S, ref, tabs):
     this only holds if every feedback iteration reproduces the reference's float sequence."""
     prg = ref.Program(scripts.synth_c4(1024, 0.3))
     want = ref.render(prg, srate=96000)
+    got = S.render(prg, srate=96000, tables=tabs)
+    assert got.shape == want.shape
+    assert np.array_equal(got, want)
+
+
+def test_c3_full_size_longer(S, ref, tabs):
+    """Config 3 at full size for 2 s (83 calls of 24 576 frames, past the end of every modulator's 1 s ramps
+    and into the steady fused shapes bench.py times), streamed with run-ahead, bit-exact."""
+    prg = ref.Program(scripts.synth_c3(4096, 2.0, fm="mix"))
+    want = ref.render(prg, srate=96000)
+    got = S.render(prg, srate=96000, tables=tabs)
+    assert got.shape == want.shape
+    assert np.array_equal(got, want)
+
+
+def test_c4_full_size_longer(S, ref, tabs):
+    """Config 4 at its full 1024 voices for 1.5 s, bit-exact."""
+    prg = ref.Program(scripts.synth_c4(1024, 1.5))
+    want = ref.render(prg, srate=96000)
+    got = S.render(prg, srate=96000, tables=tabs)
+    assert got.shape == want.shape
+    assert np.array_equal(got, want)
+
+
+def test_sweeps_past_2_24_samples(S, ref, tabs):
+    """180 s sweeps at 96 kHz: line positions beyond 2**24 (SURVEY.md App. B.1's untested note), bit-exact."""
+    prg = ref.Program(scripts.long_sweep_script())
+    want = ref.render(prg, srate=96000)
+    assert want.shape[0] > (1 << 24)
     got = S.render(prg, srate=96000, tables=tabs)
     assert got.shape == want.shape
     assert np.array_equal(got, want)

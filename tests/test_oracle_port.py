@@ -132,3 +132,12 @@ def test_port_reproduces_golden_answers(ref, port):
         assert gpuutil.sha(pcm) == g["sha256"], key
         checked += 1
     assert checked >= 150
+
+
+def test_sweeps_past_2_24_samples(ref, port):
+    """Line positions beyond 2**24 samples of one sweep (SURVEY.md App. B.1's untested note): the
+    port's single conversion equals the as-compiled two-halves conversion."""
+    prg = ref.Program(scripts.long_sweep_script())
+    a = ref.render(prg, srate=96000)
+    assert a.shape[0] > (1 << 24)
+    assert np.array_equal(a, port.render(prg, srate=96000))
