@@ -207,6 +207,8 @@ struct GenDesc {
 	uint32_t wave_mask;           // waves referenced by any op-data
 	const float *tables;          // 12 x 2048 floats, then a WaveCoeffs
 	float *tap;                   // debug (saugen_debug_tap): [op_count][row_len], every operator's output buffer
+	float *team_cache;            // teams (render_team.cuh): [n_local_voices][TEAM_SLOTS][team_cache_stride] floats, the
+	uint32_t team_cache_stride;   // values that pass from one phase of a stretch to a later one
 };
 
 /* Per-wave constants derived from sauWave_picoeffs (sau/wave.h:33-70,144-149),
@@ -250,6 +252,10 @@ struct CallDesc {
 	uint32_t *status;         // [0]=any voice still alive, [1+seg]=per-segment max len; one per call slot (the
 	                          // read-back of call k runs on the copy stream while call k+1 renders)
 };
+
+/* teams (render_team.cuh): outputs of one plan that cross a phase = cache slots per voice; the most
+ * lead-in chunks a member renders before its range */
+constexpr uint32_t TEAM_SLOTS = 12, TEAM_LEAD_CHUNKS = 7;
 
 /* A call's descriptors small enough to travel as kernel parameters (prologue_kernel): no
  * host-to-device copy in front of the render launch. */

@@ -49,15 +49,19 @@ constexpr int WIDE_WARPS = 28;        // most warps of a render_kernel_wide CTA:
 constexpr uint32_t STACK_BYTES = 3 * MAX_NEST * (uint32_t) sizeof(uint32_t);
 /* team > 1 (render_team.cuh): a second set of operator states (the member's work copy), a
  * second plan area (its executable plan) and the team's command block */
-constexpr uint32_t TEAM_CMD_BYTES = 64;
+constexpr uint32_t TEAM_CMD_BYTES = 352;       /* 64 + a word per record of the master plan (render_team.cuh:TC_INFO) */
 __host__ __device__ inline uint32_t warp_plan_bytes(uint32_t nplan) {
 	const uint32_t plan_bytes = nplan * 32u;
 	return plan_bytes > STACK_BYTES ? plan_bytes : STACK_BYTES;
 }
+/* a member's executable plan: the master's records + a save per cache slot */
+__host__ __device__ inline uint32_t team_plan_bytes(uint32_t nplan) {
+	return warp_plan_bytes(nplan) + TEAM_SLOTS * 32u;
+}
 __host__ __device__ inline uint32_t warp_smem_bytes(uint32_t nbufs, uint32_t nslots, uint32_t nplan, uint32_t team) {
 	const uint32_t k = team > 1u ? 2u : 1u;
 	return k * nslots * (uint32_t) sizeof(OpState) + nbufs * BUF_FLOATS * (uint32_t) sizeof(float) +
-		k * warp_plan_bytes(nplan) + (team > 1u ? TEAM_CMD_BYTES : 0u);
+		warp_plan_bytes(nplan) + (team > 1u ? team_plan_bytes(nplan) + TEAM_CMD_BYTES : 0u);
 }
 
 #include "render_ops.cuh"
@@ -274,6 +278,9 @@ cudaError_t launch_mix(const CallDesc *d_calls, uint32_t ncalls, const SegDesc *
 /* developer aid: the lowered-plan signature of the first stretch of the launch's first voice */
 cudaError_t read_signature_dump(uint32_t out[36]) {
 	return cudaMemcpyFromSymbol(out, g_sig_dump, sizeof(uint32_t) * 36);
+}
+cudaError_t read_team_dump(uint32_t out[32]) {
+	return cudaMemcpyFromSymbol(out, g_team_dump, sizeof(uint32_t) * 32);
 }
 
 cudaError_t launch_planes_to_pcm(const float *d_mix, uint32_t plane_stride, uint32_t n,

@@ -29,6 +29,11 @@ enum : uint32_t {
 	X_COUNT1,              /* counting pass of a team (render_team.cuh): add the rounded increments of a
 	                        * frequency vector to the accumulator ... */
 	X_COUNT2,              /* ... of a constant (w6) times a vector */
+	X_SAVE,                /* team phases: the value just produced (val, or buffer a: flag 1) -> the stretch's
+	                        * cache in global memory (64-bit address in w2, w3; index = frame in the stretch) */
+	X_LOAD,                /* ... and back: -> val (and buffer a: flag 1), in the place of the record that
+	                        * produced it in an earlier phase */
+	X_NOP,                 /* a counting record outside its window */
 };
 /* w1 bits 16..23 of a lowered record */
 enum : uint32_t {
@@ -272,7 +277,7 @@ __device__ __noinline__ uint32_t lowered_generic(uint32_t sb, uint32_t plan, int
 }
 
 /* One chunk of a lowered plan.  val: the four samples the previous specialised record produced. */
-template <bool OTHER>
+template <bool OTHER, bool TEAM = false>
 __device__ __forceinline__ void run_chunk_lowered(const HotCtx &c) {
 	uint32_t rec = c.plan + PLAN_HDR - PLAN_REC;
 	float val[4] = {0.f, 0.f, 0.f, 0.f};
@@ -350,6 +355,18 @@ __device__ __forceinline__ void run_chunk_lowered(const HotCtx &c) {
 #pragma unroll
 			for (int k = 0; k < 4; ++k) { float p = pr.x; p += (pr.y - p) * m[k]; val[k] = p; }
 			if (xf & XF_ST) fst<4>(c, bufa, val);
+		} else if (TEAM && kind >= X_SAVE) {
+			if (kind != X_NOP) {
+				float *g = reinterpret_cast<float*>((uint64_t) p0.z | ((uint64_t) p0.w << 32)) + c.oc + c.lane * 4;
+				if (kind == X_SAVE) {
+					if (flags & 1u) fld<4>(c, bufa, val);
+					__stcg(reinterpret_cast<float4*>(g), make_float4(val[0], val[1], val[2], val[3]));
+				} else {
+					const float4 v = __ldcg(reinterpret_cast<const float4*>(g));
+					val[0] = v.x; val[1] = v.y; val[2] = v.z; val[3] = v.w;
+					if (flags & 1u) { fst<4>(c, bufa, val); __syncwarp(); }
+				}
+			}
 		} else if (kind >= X_COUNT1) {
 			/* sauPhasor_fill's accumulation alone (wosc.h:145-166): sum of lrintf(coeff * f) */
 			float fr[4];
@@ -415,13 +432,13 @@ __device__ __forceinline__ void run_chunk_lowered(const HotCtx &c) {
 /* One steady stretch on a lowered plan (the coefficient-plane launches); see run_block_fast. */
 /* chunks [oc0, oc0 + len) of the stretch; rows, frame of the stretch's first sample and the
  * rest of the context come from the plan header */
-template <bool OTHER>
+template <bool OTHER, bool TEAM = false>
 __device__ __noinline__ void run_block_lowered(uint32_t sb, uint32_t plan, int lane, uint32_t oc0, uint32_t len) {
 	HotCtx c;
 	c.sb = sb; c.plan = plan; c.lane = lane; c.coeff = 0.f;
 	for (uint32_t oc = oc0; oc < oc0 + len; oc += FastCfg<FAST_NS>::CHUNKF) {
 		c.oc = oc;
-		run_chunk_lowered<OTHER>(c);
+		run_chunk_lowered<OTHER, TEAM>(c);
 	}
 }
 

@@ -30,6 +30,10 @@ __device__ __forceinline__ void ops_store(Ctx &c, uint32_t cnt) {
 /* Units [u0, u1) of one voice of one call.  A unit is a stretch of one
  * inter-event segment, starting at a multiple of REF_BLOCK inside it (the
  * reference's own block grid, generator.c:854-878). */
+/* developer aid: a time line of the launch's first warp (g_team_dump[18..]: cycles since the kernel started) */
+#define SAUGEN_TRACE(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_team_dump[i] = (uint32_t) (clock64() - g_trace_t0); } while (0)
+__device__ long long g_trace_t0;
+
 __device__ __noinline__ void render_units(Ctx &c, FastCtx &fc, const CallDesc *cd,
 		const SegDesc *segs, const UnitDesc *units, uint32_t lv, uint32_t u0, uint32_t u1) {
 	const GenDesc *g = cd->gen;
@@ -47,13 +51,17 @@ __device__ __noinline__ void render_units(Ctx &c, FastCtx &fc, const CallDesc *c
 		 * the same copy */
 		const uint32_t *src = reinterpret_cast<const uint32_t*>(vsp);
 		uint32_t *dst = reinterpret_cast<uint32_t*>(&vs);
+		static_assert(sizeof(VoiceState) / 4 <= 32, "one word per lane");
+		uint32_t w = 0;
+		if (lane < (int) (sizeof(VoiceState) / 4)) w = __ldcg(src + lane);      /* one round trip */
 #pragma unroll
-		for (uint32_t i = 0; i < sizeof(VoiceState) / 4; ++i) {
-			uint32_t w = 0;
-			if (lane == 0) w = __ldcg(src + i);
-			dst[i] = __shfl_sync(FULL, w, 0);
-		}
+		for (uint32_t i = 0; i < sizeof(VoiceState) / 4; ++i) dst[i] = __shfl_sync(FULL, w, i);
 	}
+	/* the voice program's bytecode and operator list: towards L1 now, read one by one later */
+	for (uint32_t i = lane; i < vs.code_len; i += 32)
+		asm volatile("prefetch.global.L1 [%0];" :: "l"(g->code + vs.code_off + i));
+	if (lane == 0) asm volatile("prefetch.global.L1 [%0];" :: "l"(g->prog_ops + vs.ops_off));
+	SAUGEN_TRACE(19);                  /* voice state read */
 	const uint32_t ev_lo = g->vev_off[v], ev_n = g->vev_off[v + 1] - ev_lo;
 	float *row_s = g->rows_s + (size_t) lv * ROW_TILE;      /* the voice's piece of frame tile 0 */
 	float *row_r = g->rows_r + (size_t) lv * ROW_TILE;
@@ -106,8 +114,10 @@ __device__ __noinline__ void render_units(Ctx &c, FastCtx &fc, const CallDesc *c
 				uint32_t kb = (uend - off) / (uint32_t) REF_BLOCK;
 				if (vs.duration / (uint32_t) REF_BLOCK < kb) kb = vs.duration / (uint32_t) REF_BLOCK;
 				if (kb > 0x7fffu) kb = 0x7fffu;        /* 15 bits in steady_plan's result */
+				SAUGEN_TRACE(20);          /* operator states loaded, events applied */
 				sp = steady_plan(c.sops, fc.so, fc.st, fc.wave_mask, fc.wc, g->code + vs.code_off,
 						vs.code_len, fc.plan, fc.plan_cap, kb, fc.sb, fc.coeff);
+				SAUGEN_TRACE(21);          /* plan built */
 			}
 			if (sp) {
 				const uint32_t nrec = sp & 0xffffu, nb = (sp >> 16) & 0x7fffu, span = nb * (uint32_t) REF_BLOCK;
@@ -129,6 +139,7 @@ __device__ __noinline__ void render_units(Ctx &c, FastCtx &fc, const CallDesc *c
 					/* coefficient planes: the plan is lowered (render_fast.cuh) */
 					if (lane == 0) plan_lower(fc.plan + PLAN_HDR, nrec);
 					__syncwarp();
+					SAUGEN_TRACE(22);      /* lowered */
 					/* few voices: the stretch is split along time over the voice's team of warps */
 					/* a listed signature runs as one straight-line function (fused shapes);
 					 * segments starting at an odd frame keep to the general voice output */
@@ -138,9 +149,12 @@ __device__ __noinline__ void render_units(Ctx &c, FastCtx &fc, const CallDesc *c
 							which = fused_match(fc.plan, nrec, blockIdx.x == 0 && threadIdx.x == 0);
 						which = __shfl_sync(FULL, which, 0);
 					}
+					SAUGEN_TRACE(23);      /* matched */
 					/* few voices: the stretch is split along time over the voice's team of warps */
 					const bool shared = fc.team && !other &&
-						team_stretch(*fc.team, fc.sb, lane, fc.plan, nrec, vs.ops_cnt, span, which);
+						team_stretch(*fc.team, fc.sb, lane, fc.plan, nrec, vs.ops_cnt, span, which,
+								g->team_cache ? g->team_cache + (size_t) lv * TEAM_SLOTS * g->team_cache_stride : nullptr,
+								g->team_cache_stride);
 					if (shared) { }
 					else if (other) run_block_lowered<true>(fc.sb, fc.plan, lane, 0u, span);
 					else if (which) fused_run(which, fc.sb, fc.plan, lane, 0u, span);
@@ -150,8 +164,10 @@ __device__ __noinline__ void render_units(Ctx &c, FastCtx &fc, const CallDesc *c
 					else run_block_fast<false, false>(fc.sb, fc.plan, lane, fc.coeff, span, row_s, row_r, sd.start + off);
 				}
 				__syncwarp();
+				SAUGEN_TRACE(24);          /* stretch rendered */
 				if (lane == 0) steady_update(c.sops, g->code + vs.code_off, vs.code_len, nb);
 				__syncwarp();
+				SAUGEN_TRACE(25);
 				vs.duration -= span;
 				run_total += span;
 				off += span - CHUNK;
@@ -189,6 +205,7 @@ __device__ __noinline__ void render_units(Ctx &c, FastCtx &fc, const CallDesc *c
 		}
 	}
 	if (loaded) ops_store(c, loaded);
+	SAUGEN_TRACE(26);
 	if (lane == 0) {
 		const uint32_t *w = reinterpret_cast<const uint32_t*>(&vs);
 #pragma unroll
@@ -203,6 +220,7 @@ __device__ __forceinline__ void render_body(const CallDesc *calls, uint32_t ncal
 		const double *coefs, uint32_t wave_mask, uint32_t nbufs, uint32_t nslots_ops, uint32_t nplan, uint32_t warps_per_cta,
 		uint32_t ticketed, uint32_t team) {
 	extern __shared__ __align__(128) unsigned char smem[];
+	if (blockIdx.x == 0 && threadIdx.x == 0) g_trace_t0 = clock64();
 	uint64_t *bar = reinterpret_cast<uint64_t*>(smem);
 	float *tab = reinterpret_cast<float*>(smem + 128);
 	const bool ctab = (wave_mask & CTAB_FLAG) != 0;
@@ -245,6 +263,7 @@ __device__ __forceinline__ void render_body(const CallDesc *calls, uint32_t ncal
 		__syncthreads();
 	}
 
+	SAUGEN_TRACE(18);                  /* tables staged */
 	Ctx c;
 	c.sops = reinterpret_cast<OpState*>(warp_area + warp * per_warp);
 	c.bufs = reinterpret_cast<float*>(c.sops + (team > 1u ? 2u : 1u) * nslots_ops);
@@ -279,7 +298,7 @@ __device__ __forceinline__ void render_body(const CallDesc *calls, uint32_t ncal
 			tc.so_a = fc.so; tc.so_b = fc.so + nslots_ops * (uint32_t) sizeof(OpState);
 			tc.plan_x = fc.plan + warp_plan_bytes(nplan);
 			tc.per_warp = per_warp;
-			tc.cmd = tc.plan_x + warp_plan_bytes(nplan) - rank * per_warp;
+			tc.cmd = tc.plan_x + team_plan_bytes(nplan) - rank * per_warp;
 			tc.lead_so = fc.so - rank * per_warp; tc.lead_plan = fc.plan - rank * per_warp;
 			if (rank) { team_helper(tc, fc.sb, lane); return; }
 			fc.team = &tc;

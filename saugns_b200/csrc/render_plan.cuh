@@ -419,23 +419,56 @@ __device__ __noinline__ uint32_t steady_plan(OpState *sops, uint32_t so, uint32_
 	return finish(n);
 }
 
-/* sauLine_run's bookkeeping for nb whole blocks of a steady run line, block by block */
+/* nb > 0 steps of line_advance(pos, end, flags, REF_BLOCK) (line.c:385-398) in closed form: the
+ * position runs up to `end` in whole blocks, falls back to 0 where it gets there, and goes round
+ * again.  Returns bit 0: some step expired, bit 1: the last one did. */
+__device__ __forceinline__ uint32_t line_cycle(uint32_t &pos, uint32_t end, uint32_t nb) {
+	const uint32_t B = (uint32_t) REF_BLOCK;
+	uint32_t k = nb, any = 0;
+	if (pos >= end) {                  /* nothing left to advance: expires at once */
+		pos = 0;
+		if (end == 0 || --k == 0) return 3u;
+		any = 1;
+	}
+	const uint32_t s = (end - pos + B - 1u) / B;       /* steps up to and with the next expiry */
+	if (k < s) { pos += k * B; return any; }
+	k -= s;
+	const uint32_t r = k % ((end + B - 1u) / B);       /* steps into the round the stretch ends in */
+	pos = r * B;
+	return 1u | (r == 0u ? 2u : 0u);
+}
+/* sauLine_run's bookkeeping for nb whole blocks of a steady run line */
 __device__ __forceinline__ void line_block_update(OpState *o, int li, uint32_t nb) {
+	if (!nb) return;
 	const uint32_t meta = o->lmeta[li];
 	uint32_t flags = LM_FLAGS(meta), pos = o->line[li].pos;
 	if (flags & SAUABI_LINEP_GOAL) {
 		pos += nb * (uint32_t) REF_BLOCK;
-	} else {
-		for (uint32_t b = 0; b < nb; ++b) {
-			bool ex;
-			line_advance(pos, o->line[li].end, flags, REF_BLOCK, ex);
-		}
+	} else if (line_cycle(pos, o->line[li].end, nb) & 1u) {
+		flags &= ~SAUABI_LINEP_TIME;
 	}
 	o->line[li].pos = pos;
 	o->lmeta[li] = LM_PACK(LM_TYPE(meta), flags, 0u);
 }
+/* nb x line_skip(.., REF_BLOCK) from a block start (sauLine_skip, line.c:449-473): the goal is
+ * taken at the first expiry, the position keeps going round */
 __device__ __forceinline__ void line_skip_blocks(OpState *o, int li, uint32_t nb) {
-	for (uint32_t b = 0; b < nb; ++b) line_skip(0, 0, o, li, REF_BLOCK);
+	if (!nb) return;
+	LineState *ls = &o->line[li];
+	const uint32_t meta = o->lmeta[li];
+	uint32_t pos = ls->pos, flags = LM_FLAGS(meta);
+	const uint32_t r = line_cycle(pos, ls->end, nb);
+	if (r & 1u) {
+		flags &= ~SAUABI_LINEP_TIME;
+		if (flags & SAUABI_LINEP_GOAL) {
+			ls->v0 = ls->vt;
+			if (flags & SAUABI_LINEP_GOAL_RATIO) flags |= SAUABI_LINEP_STATE_RATIO;
+			else flags &= ~SAUABI_LINEP_STATE_RATIO;
+			flags &= ~(SAUABI_LINEP_GOAL | SAUABI_LINEP_GOAL_RATIO);
+		}
+	}
+	ls->pos = pos;
+	o->lmeta[li] = LM_PACK(LM_TYPE(meta), flags, r >> 1);
 }
 
 /* lane 0 only */

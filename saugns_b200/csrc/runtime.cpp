@@ -49,6 +49,7 @@ cudaError_t launch_selftest(const float *d_tables, unsigned long long *d_bad, cu
 int device_sm_count();
 size_t device_smem_optin();
 cudaError_t read_signature_dump(uint32_t out[36]);
+cudaError_t read_team_dump(uint32_t out[32]);
 }
 
 using namespace saugen;
@@ -348,6 +349,7 @@ struct saugen_Generator {
 	GenDesc h_desc;
 	GenDesc *d_desc = nullptr;
 	float *d_tap = nullptr;           /* saugen_debug_tap */
+	bool team_cache_failed = false;
 	float *d_tables = nullptr;
 	double *d_coefs = nullptr;
 	bool ctab_ok = false;              // every voice program is fast-path material (see create)
@@ -1370,6 +1372,21 @@ static bool ensure_seg_cap(saugen_Generator *o, size_t n) {
 	return cudaMemcpy(o->d_desc, &o->h_desc, sizeof(GenDesc), cudaMemcpyHostToDevice) == cudaSuccess;
 }
 
+/* The cache of a team launch (render_team.cuh): per voice TEAM_SLOTS slots of one call's frames + every
+ * member's lead-in.  Made when the first team launch needs it; none (allocation refused) = only plans
+ * without frequency modulation are split along time. */
+static bool ensure_team_cache(saugen_Generator *o, uint32_t team) {
+	const uint32_t stride = (o->row_len + (team - 1u) * TEAM_LEAD_CHUNKS * 128u + 3u) & ~3u;
+	if (o->h_desc.team_cache && o->h_desc.team_cache_stride >= stride) return true;
+	if (o->team_cache_failed) return false;
+	const size_t bytes = (size_t) (o->nlv ? o->nlv : 1) * TEAM_SLOTS * stride * sizeof(float);
+	float *p = (float*) o->take(false, bytes);
+	if (!p) { o->team_cache_failed = true; cudaGetLastError(); return false; }
+	cudaStreamSynchronize(o->stream);
+	o->h_desc.team_cache = p; o->h_desc.team_cache_stride = stride;
+	return cudaMemcpy(o->d_desc, &o->h_desc, sizeof(GenDesc), cudaMemcpyHostToDevice) == cudaSuccess;
+}
+
 /* Plans and launches one call into slot `si` (kernels + read-back queued on the generator's
  * stream, an event recorded after them); nothing waits.  host_pcm_bytes: PCM bytes to bring to
  * the slot's pinned staging buffer (0 = none).  <0 on error. */
@@ -1396,6 +1413,7 @@ static int launch_call(saugen_Generator *o, int si, size_t buf_len, int stereo, 
 	Shape shape = pick_shape(o->nlv, o->wave_mask, o->nbufs, o->max_ops, o->nplan, o->d_coefs != nullptr && !o->d_tap,
 			(o->sched == 0 || o->sched == 1) && !o->d_tap);
 	if (o->d_tap) shape.mask |= 0x20000000u;         /* render_ops.cuh:TAP_FLAG */
+	if (shape.team > 1) ensure_team_cache(o, shape.team);      /* (none: PM-only plans still split) */
 	const uint32_t warps = shape.warps;
 	if (!warps) {
 		g_err = "saugen_run: a voice program of this script needs more shared memory than one SM has";
@@ -2159,6 +2177,13 @@ extern "C" int saugen_debug_read_tap(saugen_Generator *o, uint32_t op_id, float 
 	cudaSetDevice(o->device);
 	cudaStreamSynchronize(o->stream);
 	return cudaMemcpy(out, o->d_tap + (size_t) op_id * o->row_len, n * sizeof(float), cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -1;
+}
+/* developer aid (not in the header): render_team.cuh:g_team_dump */
+extern "C" int saugen_debug_team(saugen_Generator *o, uint32_t out[32]) {
+	if (!o) return -1;
+	cudaSetDevice(o->device);
+	cudaStreamSynchronize(o->stream);
+	return read_team_dump(out) == cudaSuccess ? 0 : -1;
 }
 extern "C" float saugen_amp_scale(saugen_Generator *o) { return o ? o->amp_scale : 0.f; }
 extern "C" const char *saugen_last_error(void) { return g_err.c_str(); }
