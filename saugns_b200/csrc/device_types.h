@@ -88,6 +88,10 @@ struct VoiceState {
 	uint32_t ops_off;      // the program's operator list (offset into GenDesc::prog_ops)
 	uint32_t ops_cnt;
 	uint32_t carr_slot;    // carrier's slot in that list
+	/* the voice's lowered steady plan as kept in GenDesc::plan_cache (render_kernel.cuh): generation
+	 * (0 = none valid), the shared-memory layout its addresses are for */
+	uint32_t plan_gen, plan_so, plan_st;
+	uint32_t plan_left;    // whole blocks the kept plan still holds for (steady_plan's spans)
 };
 
 /* Flattened sauLine delta carried by an event (NULL pointer => present = 0). */
@@ -207,6 +211,8 @@ struct GenDesc {
 	uint32_t wave_mask;           // waves referenced by any op-data
 	const float *tables;          // 12 x 2048 floats, then a WaveCoeffs
 	float *tap;                   // debug (saugen_debug_tap): [op_count][row_len], every operator's output buffer
+	uint4 *plan_cache;            // [n_local_voices][1 + 2 * plan_cache_recs] 16-byte words: {generation, records,
+	uint32_t plan_cache_recs;     // fused shape, -} and the voice's last stable lowered plan (render_kernel.cuh)
 	float *team_cache;            // teams (render_team.cuh): [n_local_voices][TEAM_SLOTS][team_cache_stride] floats, the
 	uint32_t team_cache_stride;   // values that pass from one phase of a stretch to a later one
 };

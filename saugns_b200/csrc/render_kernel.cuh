@@ -30,6 +30,13 @@ __device__ __forceinline__ void ops_store(Ctx &c, uint32_t cnt) {
 /* Units [u0, u1) of one voice of one call.  A unit is a stretch of one
  * inter-event segment, starting at a multiple of REF_BLOCK inside it (the
  * reference's own block grid, generator.c:854-878). */
+/* The position word of an amplitude trajectory's P_EXT slot (steady_plan, render_plan.cuh) at a stretch
+ * start, from the operator's line: the position, centred for a linear one.  op = shared address. */
+__device__ __forceinline__ uint32_t plan_ext_pos(uint32_t op, uint32_t type) {
+	const uint32_t pos = lds32(op + OS_LINE + 16u * LINE_AMP + 8u), end = lds32(op + OS_LINE + 16u * LINE_AMP + 12u);
+	return type == (uint32_t) sau::L_lin ? pos - (end / 2u) : pos;
+}
+
 /* developer aid: a time line of the launch's first warp (g_team_dump[18..]: cycles since the kernel started) */
 #define SAUGEN_TRACE(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_team_dump[i] = (uint32_t) (clock64() - g_trace_t0); } while (0)
 __device__ long long g_trace_t0;
@@ -79,6 +86,7 @@ __device__ __noinline__ void render_units(Ctx &c, FastCtx &fc, const CallDesc *c
 				if (lane == 0) {
 					apply_event(g, c.wc, &g->events[g->vev_idx[ev_lo + vs.ev_cursor]], &vs);
 					vs.ev_cursor++;
+					vs.plan_gen = 0;           /* the kept plan is for the voice as it was */
 				}
 				__syncwarp();
 				uint32_t *w = reinterpret_cast<uint32_t*>(&vs);
@@ -108,6 +116,9 @@ __device__ __noinline__ void render_units(Ctx &c, FastCtx &fc, const CallDesc *c
 			/* whole reference blocks in steady state: the fast path, for as many of the
 			 * unit's blocks as one plan holds */
 			uint32_t sp = 0;
+			uint32_t which_kept = 0xffu;   /* the stretch's fused shape, where it was looked up */
+			uint32_t kmax = 0;             /* blocks the plan holds for, from this stretch's start */
+			uint32_t kept = 0;         /* the plan came from the voice's kept one: 1 + its fused shape (0xff: not looked up) */
 			if (off % REF_BLOCK == 0 && uend - off >= (uint32_t) REF_BLOCK &&
 					vs.duration >= (uint32_t) REF_BLOCK && vs.code_len && !(fc.wave_mask & TAP_FLAG) &&
 					op_ptr(c, vs.carr_slot)->time > 0) {
@@ -115,12 +126,51 @@ __device__ __noinline__ void render_units(Ctx &c, FastCtx &fc, const CallDesc *c
 				if (vs.duration / (uint32_t) REF_BLOCK < kb) kb = vs.duration / (uint32_t) REF_BLOCK;
 				if (kb > 0x7fffu) kb = 0x7fffu;        /* 15 bits in steady_plan's result */
 				SAUGEN_TRACE(20);          /* operator states loaded, events applied */
-				sp = steady_plan(c.sops, fc.so, fc.st, fc.wave_mask, fc.wc, g->code + vs.code_off,
-						vs.code_len, fc.plan, fc.plan_cap, kb, fc.sb, fc.coeff);
+				/* A voice's plan holds, as it is, until an event touches the voice or one of the spans
+				 * steady_plan found runs out (an operator's time, a line reaching its goal): it is kept,
+				 * lowered, in global memory with the number of blocks it still holds for, and comes back
+				 * with one coalesced read instead of the walk over the bytecode, the lowering and the
+				 * shape look-up.  What moves inside it -- the position of an amplitude trajectory at the
+				 * stretch start (the P_EXT slots) -- is put in again from the operator's line. */
+				uint4 *kp = nullptr;
+				bool have = false;
+				if (fc.keep_plans && g->plan_cache && (fc.wave_mask & CTAB_FLAG)) {
+					kp = g->plan_cache + (size_t) lv * (1u + 2u * g->plan_cache_recs);
+					if (vs.plan_gen && vs.plan_left && vs.plan_so == fc.so && vs.plan_st == fc.st) {
+						const uint4 kh = __ldcg(kp);
+						if (kh.x == vs.plan_gen && kh.y <= g->plan_cache_recs && kh.y + 3u <= fc.plan_cap) {
+							have = true;
+							if (!(fc.wave_mask & VERIFY_FLAG)) {
+								for (uint32_t i = lane; i < 2u * kh.y; i += 32) {
+									const uint4 x = __ldcg(kp + 1 + i);
+									asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(fc.plan + PLAN_HDR + 16u * i),
+											"r"(x.x), "r"(x.y), "r"(x.z), "r"(x.w) : "memory");
+								}
+								if (lane == 0) sts32(fc.plan + PLAN_HDR + kh.y * PLAN_REC, P_STOP);
+								__syncwarp();
+								for (uint32_t r = 1 + lane; r < kh.y; r += 32) {
+									const uint32_t a = fc.plan + PLAN_HDR + r * PLAN_REC, w0 = lds32(a);
+									if ((w0 & 0xffu) == P_EXT) sts32(a + 4, plan_ext_pos(lds32(a - PLAN_REC + 8), w0 >> 8));
+								}
+								__syncwarp();
+								kmax = vs.plan_left;
+								sp = (kmax < kb ? kmax : kb) << 16 | kh.y;
+								kept = 1u + (kh.z & 0xffu);
+							}
+						}
+					}
+				}
+				if (!kept) {
+					sp = steady_plan(c.sops, fc.so, fc.st, fc.wave_mask, fc.wc, g->code + vs.code_off,
+							vs.code_len, fc.plan, fc.plan_cap, 0x7fffu, fc.sb, fc.coeff);
+					kmax = (sp >> 16) & 0x7fffu;       /* blocks the plan holds for; this unit has kb */
+					if (sp) sp = (sp & 0x8000ffffu) | (kmax < kb ? kmax : kb) << 16;
+				}
+				if (!sp) vs.plan_gen = 0;
 				SAUGEN_TRACE(21);          /* plan built */
 			}
 			if (sp) {
-				const uint32_t nrec = sp & 0xffffu, nb = (sp >> 16) & 0x7fffu, span = nb * (uint32_t) REF_BLOCK;
+				const uint32_t nrec = sp & 0x7fffu, nb = (sp >> 16) & 0x7fffu, span = nb * (uint32_t) REF_BLOCK;
 				const bool other = (sp >> 31) != 0;
 				if (pan_mode == PAN_UNSET)       /* steady => the pan stands still */
 					pan_mode = __float_as_uint(op_ptr(c, vs.carr_slot)->line[LINE_PAN].v0);
@@ -137,19 +187,41 @@ __device__ __noinline__ void render_units(Ctx &c, FastCtx &fc, const CallDesc *c
 				}
 				if (fc.wave_mask & CTAB_FLAG) {
 					/* coefficient planes: the plan is lowered (render_fast.cuh) */
-					if (lane == 0) plan_lower(fc.plan + PLAN_HDR, nrec);
+					if (lane == 0 && !kept) plan_lower(fc.plan + PLAN_HDR, nrec);
 					__syncwarp();
 					SAUGEN_TRACE(22);      /* lowered */
-					/* few voices: the stretch is split along time over the voice's team of warps */
-					/* a listed signature runs as one straight-line function (fused shapes);
-					 * segments starting at an odd frame keep to the general voice output */
+					const bool aligned = ((sd.start + off) & 3u) == 0u;
+					if ((fc.wave_mask & VERIFY_FLAG) && fc.keep_plans && g->plan_cache && vs.plan_gen && vs.plan_left &&
+							vs.plan_so == fc.so && vs.plan_st == fc.st) {
+						/* developer knob: the kept plan, had it been used, against the fresh one */
+						const uint4 *kq = g->plan_cache + (size_t) lv * (1u + 2u * g->plan_cache_recs);
+						const uint4 kh = __ldcg(kq);
+						if (kh.x == vs.plan_gen) {
+							uint32_t bad = kh.y != nrec || (kmax < 0x7fffu && kmax != vs.plan_left) ? 1u : 0u;
+							for (uint32_t i = lane; i < 2u * nrec && !bad; i += 32) {
+								uint4 x = __ldcg(kq + 1 + i);
+								const uint4 y = lds128u(fc.plan + PLAN_HDR + 16u * i);
+								uint32_t m = (i & 1u) ? 0xffffffffu : 0x00ffffffu;      /* (w1's top byte: the teams' levels) */
+								if (!(i & 1u) && (x.x & 0xffu) == P_EXT) {
+									x.y = plan_ext_pos(lds32(fc.plan + PLAN_HDR + 16u * i - PLAN_REC + 8), x.x >> 8);
+									m = 0xffffffffu;
+								}
+								if (x.x != y.x || (x.y & m) != (y.y & m) || x.z != y.z || x.w != y.w) bad = 1u;
+							}
+							bad = __any_sync(FULL, bad != 0u) ? 1u : 0u;
+							if (lane == 0) { atomicAdd(&g_team_dump[31], 1u); if (bad) atomicAdd(&g_team_dump[30], 1u); }
+						}
+					}
 					uint32_t which = 0;
-					if (!other) {
-						if (lane == 0 && ((sd.start + off) & 3u) == 0u && !(fc.wave_mask & NOFUSE_FLAG))
+					if (!other && kept && kept != 0x100u) {
+						which = aligned ? kept - 1u : 0u;
+					} else if (!other) {
+						if (lane == 0 && aligned && !(fc.wave_mask & NOFUSE_FLAG))
 							which = fused_match(fc.plan, nrec, blockIdx.x == 0 && threadIdx.x == 0);
 						which = __shfl_sync(FULL, which, 0);
 					}
 					SAUGEN_TRACE(23);      /* matched */
+					if (aligned && !(fc.wave_mask & NOFUSE_FLAG) && !other) which_kept = which;
 					/* few voices: the stretch is split along time over the voice's team of warps */
 					const bool shared = fc.team && !other &&
 						team_stretch(*fc.team, fc.sb, lane, fc.plan, nrec, vs.ops_cnt, span, which,
@@ -168,6 +240,23 @@ __device__ __noinline__ void render_units(Ctx &c, FastCtx &fc, const CallDesc *c
 				if (lane == 0) steady_update(c.sops, g->code + vs.code_off, vs.code_len, nb);
 				__syncwarp();
 				SAUGEN_TRACE(25);
+				if ((fc.wave_mask & CTAB_FLAG) && fc.keep_plans && g->plan_cache) {
+					const uint32_t left = kmax - nb;
+					if (kept) {
+						vs.plan_left = left;
+					} else if (left && !other && nrec <= g->plan_cache_recs) {
+						/* keep the plan for the stretches to come (a new generation: a call that is undone
+						 * later -- run-ahead -- leaves the voice's older generation number behind, not this plan) */
+						uint4 *kq = g->plan_cache + (size_t) lv * (1u + 2u * g->plan_cache_recs);
+						const uint32_t gen = (__ldcg(kq).x & 0x7fffffffu) + 1u;
+						__syncwarp();
+						for (uint32_t i = lane; i < 2u * nrec; i += 32) __stcg(kq + 1 + i, lds128u(fc.plan + PLAN_HDR + 16u * i));
+						if (lane == 0) __stcg(kq, make_uint4(gen, nrec, which_kept, 0u));
+						vs.plan_gen = gen; vs.plan_so = fc.so; vs.plan_st = fc.st; vs.plan_left = left;
+					} else {
+						vs.plan_gen = 0;
+					}
+				}
 				vs.duration -= span;
 				run_total += span;
 				off += span - CHUNK;
@@ -176,6 +265,7 @@ __device__ __noinline__ void render_units(Ctx &c, FastCtx &fc, const CallDesc *c
 			uint32_t clen = uend - off;
 			if (clen > (uint32_t) CHUNK) clen = CHUNK;
 			const uint32_t time = vs.duration < clen ? vs.duration : clen;
+			vs.plan_gen = 0;           /* (the general interpreter may leave the voice in another shape) */
 			c.oc = off % REF_BLOCK;
 			uint32_t rem0 = vs.duration;
 			if (sd.len - off < rem0) rem0 = sd.len - off;
@@ -283,6 +373,7 @@ __device__ __forceinline__ void render_body(const CallDesc *calls, uint32_t ncal
 	fc.plan = smem_u32(c.stk_len);   /* the plan overlays the len stacks */
 	fc.plan_cap = nplan * 32u > STACK_BYTES ? nplan : STACK_BYTES / 32u;
 	fc.team = nullptr;
+	fc.keep_plans = !ticketed;
 
 	if (!ticketed) {
 		/* one warp (or, with few voices, a team of warps: render_team.cuh) renders every unit

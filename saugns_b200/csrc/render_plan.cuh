@@ -588,6 +588,7 @@ struct FastCtx {               /* all registers */
 	const WaveCoeffs *wc;
 	const float *tab;          // generic pointer to the staged tables (rare paths)
 	const struct TeamCtx *team;   // the voice's team of warps (render_team.cuh), or null
+	bool keep_plans;           // one warp renders all of a voice's units: its plan is kept (GenDesc::plan_cache)
 };
 /* What the chunk loop of a steady block keeps in registers; everything else it
  * needs is in the block plan (shared memory): header at c.plan, records after it. */

@@ -349,6 +349,7 @@ struct saugen_Generator {
 	GenDesc h_desc;
 	GenDesc *d_desc = nullptr;
 	float *d_tap = nullptr;           /* saugen_debug_tap */
+	void *d_plan_cache = nullptr;     /* GenDesc::plan_cache */
 	bool team_cache_failed = false;
 	float *d_tables = nullptr;
 	double *d_coefs = nullptr;
@@ -955,6 +956,12 @@ static saugen_Generator *create_from_flat(const Flat &f, const saugen_WaveTables
 		o->slot[0].d_pcm = o->d_pcm; o->slot[1].d_pcm = (int16_t*) (base + o_pcm1);
 		o->slot[0].d_status = o->d_status; o->slot[1].d_status = (uint32_t*) (base + o_status1);
 		o->slot[0].d_mix = o->d_mix; o->slot[1].d_mix = (float*) (base + o_mix1);
+		static const char *pcenv = getenv("SAUGEN_PLANCACHE");    /* developer knob: 0 = stable plans are not kept */
+		if (o->nplan && o->d_coefs && !(pcenv && pcenv[0] == '0')) {
+			const size_t pcb = nl * (1 + 2 * (size_t) o->nplan) * 16;
+			o->d_plan_cache = o->take(false, pcb);
+			if (o->d_plan_cache) CK(cudaMemsetAsync(o->d_plan_cache, 0, pcb, o->stream));
+		}
 		const size_t ntile = ((size_t) o->row_len + ROW_TILE - 1) / ROW_TILE;
 		float *rows = (float*) o->take(false, 2 * ntile * (size_t) o->row_stride * sizeof(float));
 		if (!rows) { set_err("saugen_create: device memory (carrier rows)", cudaGetLastError()); goto fail; }
@@ -1005,6 +1012,7 @@ static saugen_Generator *create_from_flat(const Flat &f, const saugen_WaveTables
 		d.coeff = (float) (4294967296.0 / srate);                 /* wosc.h:30, math.h:386 */
 		d.amp_scale = o->amp_scale;
 		d.wave_mask = o->wave_mask; d.tables = o->d_tables;
+		d.plan_cache = (uint4*) o->d_plan_cache; d.plan_cache_recs = o->nplan;
 
 		/* one H2D copy of the static image, one memset of the run-time state; the
 		 * stream is synchronised before the staging image goes away */
@@ -1413,6 +1421,10 @@ static int launch_call(saugen_Generator *o, int si, size_t buf_len, int stereo, 
 	Shape shape = pick_shape(o->nlv, o->wave_mask, o->nbufs, o->max_ops, o->nplan, o->d_coefs != nullptr && !o->d_tap,
 			(o->sched == 0 || o->sched == 1) && !o->d_tap);
 	if (o->d_tap) shape.mask |= 0x20000000u;         /* render_ops.cuh:TAP_FLAG */
+	{
+		static const char *venv = getenv("SAUGEN_PLAN_VERIFY");
+		if (venv && venv[0] == '1') shape.mask |= 0x10000000u;     /* render_ops.cuh:VERIFY_FLAG */
+	}
 	if (shape.team > 1) ensure_team_cache(o, shape.team);      /* (none: PM-only plans still split) */
 	const uint32_t warps = shape.warps;
 	if (!warps) {

@@ -3,6 +3,8 @@
 scalar port, and the committed golden answers.  Bar: bit-exact PCM and
 integer state (stricter than the +/-1 LSB the north star allows); float
 oscillator rows within 1e-5 relative (observed: identical bits)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -484,6 +486,19 @@ def test_sweeps_past_2_24_samples(S, ref, tabs):
     got = S.render(prg, srate=96000, tables=tabs)
     assert got.shape == want.shape
     assert np.array_equal(got, want)
+
+
+def test_kept_plans_equal_fresh_ones(S):
+    """A voice's stable lowered plan is kept in global memory and reused call after call
+    (render_kernel.cuh).  Under SAUGEN_PLAN_VERIFY=1 the kernel builds the plan afresh every time and
+    compares it with the kept one wherever that would have been used: none may differ, across scripts
+    with events, hand-overs, sweeps and two call sizes (a subprocess: the knob is read once)."""
+    import subprocess
+    import sys
+    env = dict(os.environ, SAUGEN_PLAN_VERIFY="1")
+    r = subprocess.run([sys.executable, os.path.join(os.path.dirname(__file__), "gpu_plan_verify.py")],
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
 def test_runahead_streaming_and_undo(S, ref, port, tabs):
