@@ -58,10 +58,21 @@ __host__ __device__ inline uint32_t warp_plan_bytes(uint32_t nplan) {
 __host__ __device__ inline uint32_t team_plan_bytes(uint32_t nplan) {
 	return warp_plan_bytes(nplan) + TEAM_SLOTS * 32u;
 }
-__host__ __device__ inline uint32_t warp_smem_bytes(uint32_t nbufs, uint32_t nslots, uint32_t nplan, uint32_t team) {
-	const uint32_t k = team > 1u ? 2u : 1u;
-	return k * nslots * (uint32_t) sizeof(OpState) + nbufs * BUF_FLOATS * (uint32_t) sizeof(float) +
-		warp_plan_bytes(nplan) + (team > 1u ? team_plan_bytes(nplan) + TEAM_CMD_BYTES : 0u);
+/* one warp per voice: operator states, work buffers, plan / len stacks */
+__host__ __device__ inline uint32_t warp_smem_bytes(uint32_t nbufs, uint32_t nslots, uint32_t nplan) {
+	return nslots * (uint32_t) sizeof(OpState) + nbufs * BUF_FLOATS * (uint32_t) sizeof(float) + warp_plan_bytes(nplan);
+}
+/* a team of warps per voice: the voice's part (its operator states, the master plan / the leader's len
+ * stacks, the command block) and, per member, a work copy of the operator states, work buffers and the
+ * member's executable plan */
+__host__ __device__ inline uint32_t team_lead_bytes(uint32_t nslots, uint32_t nplan) {
+	return nslots * (uint32_t) sizeof(OpState) + warp_plan_bytes(nplan) + TEAM_CMD_BYTES;
+}
+__host__ __device__ inline uint32_t team_member_bytes(uint32_t nbufs, uint32_t nslots, uint32_t nplan) {
+	return nslots * (uint32_t) sizeof(OpState) + nbufs * BUF_FLOATS * (uint32_t) sizeof(float) + team_plan_bytes(nplan);
+}
+__host__ __device__ inline uint32_t team_smem_bytes(uint32_t nbufs, uint32_t nslots, uint32_t nplan, uint32_t team) {
+	return team_lead_bytes(nslots, nplan) + team * team_member_bytes(nbufs, nslots, nplan);
 }
 
 #include "render_ops.cuh"
@@ -141,7 +152,9 @@ size_t render_smem_bytes(uint32_t wave_mask, uint32_t nbufs, uint32_t nslots_ops
 	uint32_t nslots = 0;
 	for (uint32_t w = 0; w < NUM_WAVES; ++w) if (wave_mask & (1u << w)) ++nslots;
 	const size_t slot = (wave_mask & CTAB_FLAG) ? CTAB_WAVE_BYTES : TAB_STRIDE * sizeof(float);
-	return 128 + (size_t) nslots * slot + (size_t) warps * warp_smem_bytes(nbufs, nslots_ops, nplan, team);
+	if (team > 1u)
+		return 128 + (size_t) nslots * slot + (size_t) (warps / team) * team_smem_bytes(nbufs, nslots_ops, nplan, team);
+	return 128 + (size_t) nslots * slot + (size_t) warps * warp_smem_bytes(nbufs, nslots_ops, nplan);
 }
 
 /* ---- per-index cubic coefficients of every wave table -------------------- *

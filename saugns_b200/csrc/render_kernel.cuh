@@ -317,7 +317,7 @@ __device__ __forceinline__ void render_body(const CallDesc *calls, uint32_t ncal
 	const uint32_t nslots = __popc(wave_mask & 0xfffu);
 	const uint32_t slot_bytes = ctab ? CTAB_WAVE_BYTES : TAB_STRIDE * (uint32_t) sizeof(float);
 	unsigned char *warp_area = smem + 128 + nslots * slot_bytes;
-	const uint32_t per_warp = warp_smem_bytes(nbufs, nslots_ops, nplan, team);
+	const uint32_t per_warp = warp_smem_bytes(nbufs, nslots_ops, nplan);
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
 	/* stage the tables this launch needs: TMA bulk copies, one mbarrier */
@@ -355,9 +355,19 @@ __device__ __forceinline__ void render_body(const CallDesc *calls, uint32_t ncal
 
 	SAUGEN_TRACE(18);                  /* tables staged */
 	Ctx c;
-	c.sops = reinterpret_cast<OpState*>(warp_area + warp * per_warp);
-	c.bufs = reinterpret_cast<float*>(c.sops + (team > 1u ? 2u : 1u) * nslots_ops);
-	c.stk_len = reinterpret_cast<uint32_t*>(c.bufs + nbufs * BUF_FLOATS);
+	/* team > 1 (no ticketed scheduler then): per team the voice's part, then one part per member (kernels.cu) */
+	unsigned char *team_base = warp_area + (warp / team) * team_smem_bytes(nbufs, nslots_ops, nplan, team);
+	unsigned char *member = team_base + team_lead_bytes(nslots_ops, nplan) +
+		(warp % team) * team_member_bytes(nbufs, nslots_ops, nplan);
+	if (team > 1u) {
+		c.sops = reinterpret_cast<OpState*>(team_base);
+		c.bufs = reinterpret_cast<float*>(member + nslots_ops * sizeof(OpState));
+		c.stk_len = reinterpret_cast<uint32_t*>(team_base + nslots_ops * sizeof(OpState));
+	} else {
+		c.sops = reinterpret_cast<OpState*>(warp_area + warp * per_warp);
+		c.bufs = reinterpret_cast<float*>(c.sops + nslots_ops);
+		c.stk_len = reinterpret_cast<uint32_t*>(c.bufs + nbufs * BUF_FLOATS);
+	}
 	c.stk_rem = c.stk_len + MAX_NEST;
 	c.stk_layer = c.stk_rem + MAX_NEST;
 	c.tab = tab;                     /* staged float tables, or the coefficient planes */
@@ -386,11 +396,11 @@ __device__ __forceinline__ void render_body(const CallDesc *calls, uint32_t ncal
 		TeamCtx tc;
 		if (team > 1u) {
 			tc.T = team; tc.rank = rank; tc.bar = 1u + team_i;
-			tc.so_a = fc.so; tc.so_b = fc.so + nslots_ops * (uint32_t) sizeof(OpState);
-			tc.plan_x = fc.plan + warp_plan_bytes(nplan);
-			tc.per_warp = per_warp;
-			tc.cmd = tc.plan_x + team_plan_bytes(nplan) - rank * per_warp;
-			tc.lead_so = fc.so - rank * per_warp; tc.lead_plan = fc.plan - rank * per_warp;
+			tc.so_a = fc.so; tc.so_b = smem_u32(member);
+			tc.plan_x = smem_u32(member) + nslots_ops * (uint32_t) sizeof(OpState) + nbufs * BUF_FLOATS * (uint32_t) sizeof(float);
+			tc.per_warp = team_member_bytes(nbufs, nslots_ops, nplan);
+			tc.cmd = fc.plan + warp_plan_bytes(nplan);
+			tc.lead_so = fc.so; tc.lead_plan = fc.plan;
 			if (rank) { team_helper(tc, fc.sb, lane); return; }
 			fc.team = &tc;
 		}
