@@ -187,7 +187,8 @@ int saugen_read_voice(saugen_Generator *o, uint32_t vo_id, uint32_t out[4]);
  * mix kernel and leaves r untouched. */
 int saugen_read_voice_rows(saugen_Generator *o, uint32_t vo_id, float *s, float *r,
 		size_t n);
-/* Counters: [0] render launches, [1] mix launches, [2] voice-chunks rendered */
+/* Counters: [0] render launches, [1] launches of the call's other kernels (mix, prologue), [2] work buffers
+ * per voice warp, [3] wave mask */
 int saugen_counters(saugen_Generator *o, uint64_t out[4]);
 /* Device time of render_kernel / mix_kernel accumulated since timing was
  * switched on (CUDA events on the launch stream; for bench.py's roofline). */

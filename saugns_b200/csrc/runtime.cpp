@@ -1529,6 +1529,7 @@ static int launch_call(saugen_Generator *o, int si, size_t buf_len, int stereo, 
 		pa.snap_src = (const uint4*) o->d_ops; pa.snap_dst = (uint4*) o->d_snap;
 		pa.snap_n16 = ahead ? (uint32_t) ((o->state_bytes + 15) / 16) : 0u;
 		e = launch_prologue(ic, pa, o->stream);
+		o->counters[1]++;
 	} else if (o->compact) {
 		/* one copy in ([call][segs][units]), the memsets ([vlen][progress], [status]) */
 		if (ahead) e = cudaMemcpyAsync(o->d_snap, o->d_ops, o->state_bytes, cudaMemcpyDeviceToDevice, o->stream);
