@@ -252,6 +252,7 @@ __device__ __noinline__ void render_units(Ctx &c, FastCtx &fc, const CallDesc *c
 						__syncwarp();
 						for (uint32_t i = lane; i < 2u * nrec; i += 32) __stcg(kq + 1 + i, lds128u(fc.plan + PLAN_HDR + 16u * i));
 						if (lane == 0) __stcg(kq, make_uint4(gen, nrec, which_kept, 0u));
+						__syncwarp();          /* every lane has read the plan before the area is used again */
 						vs.plan_gen = gen; vs.plan_so = fc.so; vs.plan_st = fc.st; vs.plan_left = left;
 					} else {
 						vs.plan_gen = 0;
@@ -266,6 +267,7 @@ __device__ __noinline__ void render_units(Ctx &c, FastCtx &fc, const CallDesc *c
 			if (clen > (uint32_t) CHUNK) clen = CHUNK;
 			const uint32_t time = vs.duration < clen ? vs.duration : clen;
 			vs.plan_gen = 0;           /* (the general interpreter may leave the voice in another shape) */
+			__syncwarp();              /* (its len stacks overlay the plan area) */
 			c.oc = off % REF_BLOCK;
 			uint32_t rem0 = vs.duration;
 			if (sd.len - off < rem0) rem0 = sd.len - off;

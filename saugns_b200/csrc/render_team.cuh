@@ -383,6 +383,7 @@ __device__ __noinline__ bool team_stretch(const TeamCtx &tc, uint32_t sb, int la
 	uint32_t P = 0;
 	const long long t0 = clock64();
 	if (lane == 0) P = team_analyse(plan + PLAN_HDR, nrec, tc.cmd);
+	__syncwarp();              /* (it wrote the records' levels) */
 	P = __shfl_sync(FULL, P, 0);
 	if (lane == 0 && team_traced(tc.bar)) {
 		uint32_t ns = 0;

@@ -1027,6 +1027,9 @@ static saugen_Generator *create_from_flat(const Flat &f, const saugen_WaveTables
 		put(o_desc, &d, sizeof d);
 		CK(cudaMemcpyAsync(base, img.data(), static_bytes, cudaMemcpyHostToDevice, o->stream));
 		CK(cudaMemsetAsync(base + o_ops, 0, zero_bytes, o->stream));
+		/* (the status blocks are read back whole with the PCM: no uninitialised bytes in that copy) */
+		CK(cudaMemsetAsync(base + o_status, 0, o_pcm - o_status, o->stream));
+		CK(cudaMemsetAsync(base + o_status1, 0, o_pcm1 - o_status1, o->stream));
 		CK(cudaStreamSynchronize(o->stream));
 		lap(5);
 		if (g_cprof.on) g_cprof.n++;

@@ -32,4 +32,16 @@ want = pyref.render(prg, srate=96000)
 for sched in (1, 2):
     if not np.array_equal(saugns_b200.render(prg, srate=96000, tables=tabs, sched=sched), want):
         bad.append(("c3", sched))
+# teams in phases (nested FM: loads / saves through the per-voice cache, counting windows), kept plans and
+# the run-ahead call chain (prologue kernel, copy stream), streamed at two call sizes
+c2_short = scripts.C2_MISC1_4FM_PM.replace("t15", "t0.6")
+deep = ("Wsin f300 t0.7 p[Wtri f200.r400[Wsin f50.r90[Wsaw f7 a0.9] a0.8] a0.6] a0.5\n"
+        "Wsin f220.r330[Wsin f3.r5[Wtri f0.7]] t0.7 a0.4 c0.5\n")
+for text in (c2_short, deep):
+    prg = pyref.Program(text)
+    want = pyref.render(prg, srate=96000)
+    for call in (24576, 8192):
+        got = saugns_b200.render(prg, srate=96000, tables=tabs, call_len=call)
+        if got.shape != want.shape or not np.array_equal(got, want):
+            bad.append(("teams", call))
 print("sanitize workload done; mismatches:", bad)
