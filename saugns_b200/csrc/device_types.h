@@ -213,6 +213,11 @@ struct GenDesc {
 	float *tap;                   // debug (saugen_debug_tap): [op_count][row_len], every operator's output buffer
 	uint4 *plan_cache;            // [n_local_voices][1 + 2 * plan_cache_recs] 16-byte words: {generation, records,
 	uint32_t plan_cache_recs;     // fused shape, -} and the voice's last stable lowered plan (render_kernel.cuh)
+	/* a team that spans several CTAs (render_team.cuh): per voice 16 words {arrivals, epoch, ...} zeroed before
+	 * every launch, and a mailbox (TEAM_MAIL_* below) the leader's CTA and the others exchange through */
+	uint32_t *team_hdr;
+	unsigned char *team_mail;
+	uint32_t team_mail_stride;
 	float *team_cache;            // teams (render_team.cuh): [n_local_voices][TEAM_SLOTS][team_cache_stride] floats, the
 	uint32_t team_cache_stride;   // values that pass from one phase of a stretch to a later one
 };
@@ -263,6 +268,23 @@ struct CallDesc {
  * lead-in chunks a member renders before its range */
 constexpr uint32_t TEAM_SLOTS = 12, TEAM_LEAD_CHUNKS = 7;
 
+/* the mailbox of a team over several CTAs: the leader's command block, master plan and operator states (what
+ * the other CTAs mirror in their own shared memory), every member's counts of a phase, and the last member's
+ * oscillator state on its way back to the voice */
+constexpr uint32_t TEAM_MAX_CTAS = 8, TEAM_MAX_MEMBERS = TEAM_MAX_CTAS * 28, TEAM_MAIL_OPS = 32;
+constexpr uint32_t TEAM_CMD_BYTES = 352;       /* 64 + a word per record of the master plan (render_team.cuh:TC_INFO) + 16 */
+__host__ __device__ inline uint32_t team_mail_plan_off() { return TEAM_CMD_BYTES; }
+__host__ __device__ inline uint32_t team_mail_ops_off(uint32_t plan_bytes) { return TEAM_CMD_BYTES + plan_bytes; }
+__host__ __device__ inline uint32_t team_mail_counts_off(uint32_t plan_bytes, uint32_t max_ops) {
+	return team_mail_ops_off(plan_bytes) + max_ops * 192u;
+}
+__host__ __device__ inline uint32_t team_mail_final_off(uint32_t plan_bytes, uint32_t max_ops) {
+	return team_mail_counts_off(plan_bytes, max_ops) + TEAM_MAX_MEMBERS * TEAM_MAIL_OPS * 4u;
+}
+__host__ __device__ inline uint32_t team_mail_bytes(uint32_t plan_bytes, uint32_t max_ops) {
+	return (team_mail_final_off(plan_bytes, max_ops) + TEAM_MAIL_OPS * 5u * 4u + 255u) & ~255u;
+}
+
 /* A call's descriptors small enough to travel as kernel parameters (prologue_kernel): no
  * host-to-device copy in front of the render launch. */
 constexpr uint32_t INLINE_SEGS = 16, INLINE_UNITS = 64;
@@ -279,8 +301,8 @@ struct PrologueArgs {
 	CallDesc *d_call;
 	SegDesc *d_segs;
 	UnitDesc *d_units;
-	uint32_t *zero_a, *zero_b;
-	uint32_t zero_a_words, zero_b_words;
+	uint32_t *zero_a, *zero_b, *zero_c;
+	uint32_t zero_a_words, zero_b_words, zero_c_words;
 	const uint4 *snap_src;
 	uint4 *snap_dst;
 	uint32_t snap_n16;        // 0 = no snapshot

@@ -49,7 +49,6 @@ constexpr int WIDE_WARPS = 28;        // most warps of a render_kernel_wide CTA:
 constexpr uint32_t STACK_BYTES = 3 * MAX_NEST * (uint32_t) sizeof(uint32_t);
 /* team > 1 (render_team.cuh): a second set of operator states (the member's work copy), a
  * second plan area (its executable plan) and the team's command block */
-constexpr uint32_t TEAM_CMD_BYTES = 352;       /* 64 + a word per record of the master plan (render_team.cuh:TC_INFO) */
 __host__ __device__ inline uint32_t warp_plan_bytes(uint32_t nplan) {
 	const uint32_t plan_bytes = nplan * 32u;
 	return plan_bytes > STACK_BYTES ? plan_bytes : STACK_BYTES;
@@ -212,6 +211,7 @@ static cudaError_t ensure_smem(bool wide, size_t smem) {
 	}
 	return cudaSuccess;
 }
+uint32_t plan_area_bytes(uint32_t nplan) { return warp_plan_bytes(nplan); }
 int render_ctas_per_sm(size_t smem, uint32_t warps) {
 	int n = 0;
 	if (ensure_smem(warps > 8, smem) != cudaSuccess) return 0;
@@ -223,7 +223,7 @@ int render_ctas_per_sm(size_t smem, uint32_t warps) {
 cudaError_t launch_render(const CallDesc *d_calls, uint32_t ncalls, const SegDesc *d_segs,
 		const UnitDesc *d_units, uint32_t ntasks, const float *d_tables, const double *d_coefs,
 		uint32_t wave_mask, uint32_t nbufs, uint32_t nslots_ops, uint32_t nplan, uint32_t warps,
-		uint32_t ticketed_ctas, uint32_t sched_mode, uint32_t team, cudaStream_t stream) {
+		uint32_t ticketed_ctas, uint32_t sched_mode, uint32_t team, cudaStream_t stream, uint32_t multi) {
 	if (ntasks == 0) return cudaSuccess;
 	if (nslots_ops == 0) nslots_ops = 1;
 	if (team < 1 || ticketed_ctas) team = 1;
@@ -234,7 +234,17 @@ cudaError_t launch_render(const CallDesc *d_calls, uint32_t ncalls, const SegDes
 		if (e != cudaSuccess) return e;
 	}
 	const uint32_t per_cta = warps / team;      /* voices per CTA */
-	const uint32_t grid = ticketed_ctas ? ticketed_ctas : (ntasks + per_cta - 1) / per_cta;
+	uint32_t grid = ticketed_ctas ? ticketed_ctas : (ntasks + per_cta - 1) / per_cta;
+	if (multi > 1u && team > 1u && per_cta == 1u) {
+		/* a team per voice over `multi` CTAs: they wait for one another through global memory, so all of
+		 * them have to be resident at once -- a cooperative launch (it fails rather than hang) */
+		grid *= multi;
+		uint32_t team_arg = team | multi << 8, sched_arg = 0u;
+		void *args[] = {&d_calls, &ncalls, &d_segs, &d_units, &ntasks, &d_tables, &d_coefs, &wave_mask, &nbufs,
+			&nslots_ops, &nplan, &warps, &sched_arg, &team_arg};
+		return cudaLaunchCooperativeKernel(wide ? (const void*) render_kernel_wide : (const void*) render_kernel,
+				dim3(grid), dim3(warps * 32), args, smem, stream);
+	}
 	if (wide)
 		render_kernel_wide<<<grid, warps * 32, smem, stream>>>(d_calls, ncalls, d_segs, d_units, ntasks,
 				d_tables, d_coefs, wave_mask, nbufs, nslots_ops, nplan, warps, ticketed_ctas ? sched_mode : 0u, team);
@@ -254,6 +264,7 @@ __global__ void prologue_kernel(const __grid_constant__ InlineCall ic, const __g
 	}
 	for (uint32_t i = t; i < a.zero_a_words; i += nt) a.zero_a[i] = 0u;
 	for (uint32_t i = t; i < a.zero_b_words; i += nt) a.zero_b[i] = 0u;
+	for (uint32_t i = t; i < a.zero_c_words; i += nt) a.zero_c[i] = 0u;
 	for (uint32_t i = t; i < a.snap_n16; i += nt) a.snap_dst[i] = a.snap_src[i];
 }
 cudaError_t launch_prologue(const InlineCall &ic, const PrologueArgs &a, cudaStream_t stream) {

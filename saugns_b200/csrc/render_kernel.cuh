@@ -310,8 +310,10 @@ __device__ __noinline__ void render_units(Ctx &c, FastCtx &fc, const CallDesc *c
 __device__ __forceinline__ void render_body(const CallDesc *calls, uint32_t ncalls,
 		const SegDesc *segs, const UnitDesc *units, uint32_t ntasks, const float *tables,
 		const double *coefs, uint32_t wave_mask, uint32_t nbufs, uint32_t nslots_ops, uint32_t nplan, uint32_t warps_per_cta,
-		uint32_t ticketed, uint32_t team) {
+		uint32_t ticketed, uint32_t team_arg) {
 	extern __shared__ __align__(128) unsigned char smem[];
+	const uint32_t team = team_arg & 0xffu;        /* warps per voice in a CTA ... */
+	const uint32_t multi = team_arg >> 8 ? team_arg >> 8 : 1u;   /* ... and CTAs per voice (render_team.cuh) */
 	if (blockIdx.x == 0 && threadIdx.x == 0) g_trace_t0 = clock64();
 	uint64_t *bar = reinterpret_cast<uint64_t*>(smem);
 	float *tab = reinterpret_cast<float*>(smem + 128);
@@ -393,25 +395,36 @@ __device__ __forceinline__ void render_body(const CallDesc *calls, uint32_t ncal
 		const uint32_t per_cta = warps_per_cta / team;
 		const uint32_t team_i = warp / team, rank = warp - team_i * team;
 		if (team_i >= per_cta) return;
-		const uint32_t task = blockIdx.x * per_cta + team_i;
+		const uint32_t task = (blockIdx.x / multi) * per_cta + team_i;
 		if (task >= ntasks) return;
-		TeamCtx tc;
-		if (team > 1u) {
-			tc.T = team; tc.rank = rank; tc.bar = 1u + team_i;
-			tc.so_a = fc.so; tc.so_b = smem_u32(member);
-			tc.plan_x = smem_u32(member) + nslots_ops * (uint32_t) sizeof(OpState) + nbufs * BUF_FLOATS * (uint32_t) sizeof(float);
-			tc.per_warp = team_member_bytes(nbufs, nslots_ops, nplan);
-			tc.cmd = fc.plan + warp_plan_bytes(nplan);
-			tc.lead_so = fc.so; tc.lead_plan = fc.plan;
-			if (rank) { team_helper(tc, fc.sb, lane); return; }
-			fc.team = &tc;
-		}
 		uint32_t ci = 0, hi = ncalls;
 		while (hi - ci > 1) {
 			const uint32_t mid = (ci + hi) >> 1;
 			if (calls[mid].task_base <= task) ci = mid; else hi = mid;
 		}
 		const CallDesc *cd = &calls[ci];
+		TeamCtx tc;
+		if (team > 1u) {
+			tc.T = team; tc.rank = rank; tc.bar = 1u + team_i;
+			tc.K = multi; tc.part = blockIdx.x % multi;
+			tc.hdr = nullptr; tc.mail = nullptr;
+			tc.plan_bytes = warp_plan_bytes(nplan); tc.max_ops = nslots_ops;
+			if (multi > 1u) {
+				const GenDesc *gd = cd->gen;
+				const uint32_t lvt = task - cd->task_base;
+				tc.hdr = gd->team_hdr + (size_t) lvt * 16u;
+				tc.mail = gd->team_mail + (size_t) lvt * gd->team_mail_stride;
+			}
+			tc.so_a = fc.so; tc.so_b = smem_u32(member);
+			tc.plan_x = smem_u32(member) + nslots_ops * (uint32_t) sizeof(OpState) + nbufs * BUF_FLOATS * (uint32_t) sizeof(float);
+			tc.per_warp = team_member_bytes(nbufs, nslots_ops, nplan);
+			tc.cmd = fc.plan + warp_plan_bytes(nplan);
+			tc.lead_so = fc.so; tc.lead_plan = fc.plan;
+			if (rank == 0u && lane == 0) sts32(tc.cmd + TC_SYNCS, 0u);     /* (before the team's first barrier) */
+			if (tc.part) { team_remote(tc, fc.sb, lane); return; }
+			if (rank) { team_helper(tc, fc.sb, lane); return; }
+			fc.team = &tc;
+		}
 		render_units(c, fc, cd, segs, units, task - cd->task_base, 0, cd->nunits);
 		if (team > 1u) team_dismiss(tc, lane);
 		return;

@@ -26,6 +26,12 @@
  * a_w - L + q; its inputs (levels < q) are exact from that chunk on (they started a chunk earlier),
  * so all but its first sample there is exact, and everything from chunk a_w - L + q + 1 on.  An
  * oscillator r is therefore counted over [a_w - L + O_r, a_w+1 - L + O_r) by member w.
+ * A TEAM CAN SPAN SEVERAL CTAs (one voice per CTA, K CTAs per voice, member = CTA part x T + warp): with one
+ * voice alive, one SM's issue slots and shared memory bound the team.  The other CTAs mirror the leader's command
+ * block, master plan and operator states in their own shared memory (same layout, so the plan's shared addresses
+ * hold), fetched from the voice's mailbox in global memory when the leader's epoch word moves; barriers become
+ * "every CTA's team barrier, then an arrival count in global memory", the counts of a phase and the last member's
+ * oscillator state travel through the mailbox.  The launch is cooperative: all CTAs are resident.
  * The leader (member 0) is the voice's own warp: it applies events, renders everything that is not
  * a steady stretch, builds and lowers the plan, and hands eligible stretches to the team; the last
  * member's operator state becomes the voice's state.  Members synchronise on one named barrier per
@@ -45,7 +51,9 @@ static_assert(offsetof(OpState, _pad) == OS_PAD0, "OpState::_pad offset");
  * TC_INFO + 4r: phases that need the record's output (bits 0..7) | its cache slot << 8 */
 constexpr uint32_t TC_OP = 0, TC_NREC = 4, TC_NOPS = 8, TC_CHUNKS = 12, TC_P = 16, TC_TEFF = 20,
 	TC_FUSED = 24, TC_STRIDE = 28, TC_CACHE = 32, TC_INFO = 64;
-static_assert(TC_INFO + 4 * 68 <= TEAM_CMD_BYTES, "command block");
+constexpr uint32_t TC_SHARED_BYTES = TC_INFO + 4 * 68;      /* what the other CTAs of a team mirror */
+constexpr uint32_t TC_SYNCS = TC_SHARED_BYTES;              /* this CTA's own: team-wide barriers passed in this launch */
+static_assert(TC_SYNCS + 4 <= TEAM_CMD_BYTES, "command block");
 
 /* developer aid (saugen_debug_team): the last stretch the first team of CTA 0 was offered --
  * [0] stretches offered, [1] P (0xff = not eligible), [2] t_eff, [3] records, [4] chunks, [5] cache slots,
@@ -58,6 +66,11 @@ __device__ __forceinline__ void team_bar(uint32_t id, uint32_t nthreads) {
 	asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(nthreads) : "memory");
 }
 
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t *p) {
+	uint32_t v;
+	asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+	return v;
+}
 /* what a record reads (buffers < 32, or TEAM_VAL = the record before it) and writes */
 constexpr uint32_t TEAM_VAL = 0x100u;
 struct RecIO { uint32_t out, freq, in[3], nin; };
@@ -265,13 +278,34 @@ __device__ __noinline__ void team_phase_init(uint32_t exec, uint32_t at, uint32_
 }
 
 struct TeamCtx {
-	uint32_t T, rank, bar;     /* members, this member, its named barrier */
+	uint32_t T, rank, bar;     /* members of this CTA, this member among them, their named barrier */
+	uint32_t K, part;          /* CTAs of the team, this CTA among them (member = part * T + rank) */
+	uint32_t *hdr;             /* K > 1: the voice's {arrivals, epoch} words ... */
+	unsigned char *mail;       /* ... and its mailbox (device_types.h:team_mail_*) */
+	uint32_t plan_bytes, max_ops;  /* (the mailbox's layout) */
 	uint32_t so_a, so_b;       /* shared addr of this member's operator states: the voice's own (leader) / work copy */
 	uint32_t plan_x;           /* ... of its executable plan */
 	uint32_t cmd;              /* ... of the LEADER's command block */
 	uint32_t per_warp;         /* bytes between consecutive members' areas */
 	uint32_t lead_so, lead_plan;   /* the leader's operator states and master plan */
 };
+
+/* Every member of the team, on every CTA it spans: the CTA's named barrier; with K > 1 then one arrival per CTA
+ * in global memory (the n-th barrier of the launch is passed when n * K have arrived) and the named barrier again. */
+__device__ __forceinline__ void team_sync(const TeamCtx &tc, int lane) {
+	__threadfence_block();
+	team_bar(tc.bar, tc.T * 32u);
+	if (tc.K > 1u) {
+		if (tc.rank == 0u && lane == 0) {
+			const uint32_t n = lds32(tc.cmd + TC_SYNCS) + 1u;
+			sts32(tc.cmd + TC_SYNCS, n);
+			__threadfence();
+			atomicAdd(tc.hdr, 1u);
+			while (ld_acquire_gpu(tc.hdr) < n * tc.K) __nanosleep(64);
+		}
+		team_bar(tc.bar, tc.T * 32u);
+	}
+}
 
 /* One team stretch, run by every member (those beyond t_eff only keep the barriers). */
 __device__ __noinline__ void team_run(const TeamCtx &tc, uint32_t sb, int lane) {
@@ -280,8 +314,10 @@ __device__ __noinline__ void team_run(const TeamCtx &tc, uint32_t sb, int lane) 
 	const uint32_t fused = lds32(tc.cmd + TC_FUSED);       /* the plan spells a listed shape (render_fast.cuh) */
 	const uint32_t stride = lds32(tc.cmd + TC_STRIDE);
 	float *cache = reinterpret_cast<float*>((uint64_t) lds32(tc.cmd + TC_CACHE) | ((uint64_t) lds32(tc.cmd + TC_CACHE + 4) << 32));
-	const uint32_t w = tc.rank, nthreads = tc.T * 32u;
+	const uint32_t w = tc.part * tc.T + tc.rank;
 	const bool active = w < t_eff;
+	uint32_t *mcounts = reinterpret_cast<uint32_t*>(tc.mail + team_mail_counts_off(tc.plan_bytes, tc.max_ops));
+	uint32_t *final_st = reinterpret_cast<uint32_t*>(tc.mail + team_mail_final_off(tc.plan_bytes, tc.max_ops));
 	const uint32_t L = P + 1u;
 	const uint32_t a_w = active ? (uint32_t) ((uint64_t) w * C / t_eff) : 0u;
 	const uint32_t a_next = active ? (uint32_t) ((uint64_t) (w + 1u) * C / t_eff) : 0u;
@@ -346,12 +382,15 @@ __device__ __noinline__ void team_run(const TeamCtx &tc, uint32_t sb, int lane) 
 					const uint4 x = lds128u(a);
 					const uint32_t kind = x.x & 0xffu;
 					if (kind == P_STOP || a - tc.plan_x > PLAN_WALK_MAX + TEAM_SLOTS * PLAN_REC) break;
-					if (kind == X_NOP || kind == X_COUNT1 || kind == X_COUNT2) sts32(x.z + OS_PAD0, lds32(x.z + OS_I0));
+					if (kind == X_NOP || kind == X_COUNT1 || kind == X_COUNT2) {
+						const uint32_t cnt = lds32(x.z + OS_I0);
+						sts32(x.z + OS_PAD0, cnt);
+						if (tc.K > 1u) __stcg(mcounts + w * TEAM_MAIL_OPS + (x.z - tc.so_b) / 192u, cnt);
+					}
 				}
 			}
 		}
-		__threadfence_block();
-		team_bar(tc.bar, nthreads);
+		team_sync(tc, lane);
 		if (!w && lane == 0 && q < 8u && team_traced(tc.bar)) g_team_dump[8 + q] = (uint32_t) (clock64() - tq);
 		if (q < P && active && w && lane == 0) {
 			/* this member's start values of the accumulators counted in this phase: the voice's own +
@@ -363,12 +402,25 @@ __device__ __noinline__ void team_run(const TeamCtx &tc, uint32_t sb, int lane) 
 				if (kind == P_EXT || !(kind >= X_OSC0 && kind < X_RANGE) || ((x.y >> 24) & 0xfu) != q + 1u) continue;
 				const uint32_t off = x.z - tc.lead_so;         /* the operator's offset in a member's area */
 				uint32_t acc = lds32(x.z + OS_I0);
-				for (uint32_t j = 0; j < w; ++j)
-					acc += lds32(tc.so_b + off - (w - j) * tc.per_warp + OS_PAD0);
+				if (tc.K > 1u) {
+					for (uint32_t j = 0; j < w; ++j) acc += __ldcg(mcounts + j * TEAM_MAIL_OPS + off / 192u);
+				} else {
+					for (uint32_t j = 0; j < w; ++j)
+						acc += lds32(tc.so_b + off - (w - j) * tc.per_warp + OS_PAD0);
+				}
 				sts32(tc.so_b + off + OS_PAD1, acc);
 			}
 		}
 		__syncwarp();
+	}
+	if (tc.K > 1u) {
+		/* the last active member's accumulators and look-back values, on their way to the voice */
+		if (w + 1u == t_eff)
+			for (uint32_t i = lane; i < nops * 5u; i += 32) {
+				const uint32_t slot = i / 5u, k = i % 5u;
+				__stcg(final_st + i, lds32(tc.so_b + slot * 192u + (k == 4u ? OS_PREVS : OS_I0 + k * 4u)));
+			}
+		team_sync(tc, lane);
 	}
 }
 
@@ -399,9 +451,11 @@ __device__ __noinline__ bool team_stretch(const TeamCtx &tc, uint32_t sb, int la
 	if (P == TEAM_INELIGIBLE) return false;
 	if (P > 0 && !cache) return false;
 	/* every member but the first renders up to P + 1 lead-in chunks: worth it from twice that per member */
-	uint32_t t_eff = C / (2u * (P + 2u));
-	if (t_eff > tc.T) t_eff = tc.T;
+	uint32_t t_eff = C / (tc.K > 1u ? (P + 2u) : 2u * (P + 2u));
+	if (t_eff > tc.T * tc.K) t_eff = tc.T * tc.K;
+	if (t_eff > TEAM_MAX_MEMBERS) t_eff = TEAM_MAX_MEMBERS;
 	if (t_eff < 2u) return false;
+	if (tc.K > 1u && (nops > TEAM_MAIL_OPS || nops > tc.max_ops || PLAN_HDR + (nrec + 1u) * PLAN_REC > tc.plan_bytes)) return false;
 	if (P > 0 && (uint64_t) span + (uint64_t) (t_eff - 1u) * (P + 1u) * (uint32_t) CHUNK > stride) return false;
 	if (lane == 0) {
 		sts32(tc.cmd + TC_OP, 1u); sts32(tc.cmd + TC_NREC, nrec); sts32(tc.cmd + TC_NOPS, nops);
@@ -411,6 +465,17 @@ __device__ __noinline__ bool team_stretch(const TeamCtx &tc, uint32_t sb, int la
 		sts32(tc.cmd + TC_CACHE, (uint32_t) cp); sts32(tc.cmd + TC_CACHE + 4, (uint32_t) (cp >> 32));
 	}
 	__syncwarp();
+	if (tc.K > 1u) {
+		/* the other CTAs' copy: command block, master plan with its end mark, operator states; then the epoch */
+		const uint32_t np = (PLAN_HDR + (nrec + 1u) * PLAN_REC) / 16u, no = nops * 12u, nc = TC_SHARED_BYTES / 16u;
+		uint4 *m = reinterpret_cast<uint4*>(tc.mail);
+		for (uint32_t i = lane; i < nc; i += 32) __stcg(m + i, lds128u(tc.cmd + 16u * i));
+		for (uint32_t i = lane; i < np; i += 32) __stcg(m + team_mail_plan_off() / 16u + i, lds128u(plan + 16u * i));
+		for (uint32_t i = lane; i < no; i += 32) __stcg(m + team_mail_ops_off(tc.plan_bytes) / 16u + i, lds128u(tc.lead_so + 16u * i));
+		__threadfence();
+		__syncwarp();
+		if (lane == 0) atomicAdd(tc.hdr + 1, 1u);
+	}
 	__threadfence_block();
 	team_bar(tc.bar, tc.T * 32u);
 	team_run(tc, sb, lane);
@@ -419,10 +484,11 @@ __device__ __noinline__ bool team_stretch(const TeamCtx &tc, uint32_t sb, int la
 	}
 	/* the last active member's accumulators and look-back values are the voice's */
 	const uint32_t last = tc.so_b + (t_eff - 1u) * tc.per_warp;
+	const uint32_t *final_st = reinterpret_cast<const uint32_t*>(tc.mail + team_mail_final_off(tc.plan_bytes, tc.max_ops));
 	for (uint32_t i = lane; i < nops * 5u; i += 32) {
 		const uint32_t slot = i / 5u, k = i % 5u;
 		const uint32_t off = k == 4u ? OS_PREVS : OS_I0 + k * 4u;          /* i0, i1, prev_Is; prev_s */
-		sts32(tc.so_a + slot * 192u + off, lds32(last + slot * 192u + off));
+		sts32(tc.so_a + slot * 192u + off, tc.K > 1u ? __ldcg(final_st + i) : lds32(last + slot * 192u + off));
 	}
 	__syncwarp();
 	return true;
@@ -437,10 +503,50 @@ __device__ __noinline__ void team_helper(const TeamCtx &tc, uint32_t sb, int lan
 	}
 }
 
+/* every warp of a CTA other than the leader's (K > 1): warp 0 waits for the leader's next epoch, mirrors the
+ * command block, master plan and operator states from the mailbox, and releases the CTA's members */
+__device__ __noinline__ void team_remote(const TeamCtx &tc, uint32_t sb, int lane) {
+	uint32_t seen = 0;
+	for (;;) {
+		if (tc.rank == 0u) {
+			if (lane == 0) while (ld_acquire_gpu(tc.hdr + 1) == seen) __nanosleep(128);
+			__syncwarp();
+			++seen;
+			const uint4 *m = reinterpret_cast<const uint4*>(tc.mail);
+			for (uint32_t i = lane; i < TC_SHARED_BYTES / 16u; i += 32) {
+				const uint4 x = __ldcg(m + i);
+				asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(tc.cmd + 16u * i), "r"(x.x), "r"(x.y), "r"(x.z), "r"(x.w) : "memory");
+			}
+			__syncwarp();
+			if (lds32(tc.cmd + TC_OP) != 0u) {
+				const uint32_t np = (PLAN_HDR + (lds32(tc.cmd + TC_NREC) + 1u) * PLAN_REC) / 16u, no = lds32(tc.cmd + TC_NOPS) * 12u;
+				for (uint32_t i = lane; i < np; i += 32) {
+					const uint4 x = __ldcg(m + team_mail_plan_off() / 16u + i);
+					asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(tc.lead_plan + 16u * i), "r"(x.x), "r"(x.y), "r"(x.z), "r"(x.w) : "memory");
+				}
+				for (uint32_t i = lane; i < no; i += 32) {
+					const uint4 x = __ldcg(m + team_mail_ops_off(tc.plan_bytes) / 16u + i);
+					asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(tc.lead_so + 16u * i), "r"(x.x), "r"(x.y), "r"(x.z), "r"(x.w) : "memory");
+				}
+			}
+			__syncwarp();
+			__threadfence_block();
+		}
+		team_bar(tc.bar, tc.T * 32u);
+		if (lds32(tc.cmd + TC_OP) == 0u) return;
+		team_run(tc, sb, lane);
+	}
+}
+
 /* the leader, when its voice is done */
 __device__ __forceinline__ void team_dismiss(const TeamCtx &tc, int lane) {
 	if (lane == 0) sts32(tc.cmd + TC_OP, 0u);
 	__syncwarp();
+	if (tc.K > 1u && lane == 0) {
+		__stcg(reinterpret_cast<uint32_t*>(tc.mail) + TC_OP / 4u, 0u);
+		__threadfence();
+		atomicAdd(tc.hdr + 1, 1u);
+	}
 	__threadfence_block();
 	team_bar(tc.bar, tc.T * 32u);
 }

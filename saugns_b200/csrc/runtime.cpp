@@ -36,8 +36,9 @@ size_t render_smem_bytes(uint32_t wave_mask, uint32_t nbufs, uint32_t nslots_ops
 cudaError_t launch_render(const CallDesc *d_calls, uint32_t ncalls, const SegDesc *d_segs,
 		const UnitDesc *d_units, uint32_t ntasks, const float *d_tables, const double *d_coefs,
 		uint32_t wave_mask, uint32_t nbufs, uint32_t nslots_ops, uint32_t nplan, uint32_t warps,
-		uint32_t ticketed_ctas, uint32_t sched_mode, uint32_t team, cudaStream_t stream);
+		uint32_t ticketed_ctas, uint32_t sched_mode, uint32_t team, cudaStream_t stream, uint32_t multi = 1);
 int render_ctas_per_sm(size_t smem, uint32_t warps);
+uint32_t plan_area_bytes(uint32_t nplan);
 size_t coef_table_bytes();
 cudaError_t launch_coefs(const float *d_tables, double *d_coefs, uint32_t *d_inexact, cudaStream_t stream);
 cudaError_t launch_mix(const CallDesc *d_calls, uint32_t ncalls, const SegDesc *d_segs,
@@ -1388,16 +1389,31 @@ static bool ensure_seg_cap(saugen_Generator *o, size_t n) {
 /* The cache of a team launch (render_team.cuh): per voice TEAM_SLOTS slots of one call's frames + every
  * member's lead-in.  Made when the first team launch needs it; none (allocation refused) = only plans
  * without frequency modulation are split along time. */
-static bool ensure_team_cache(saugen_Generator *o, uint32_t team) {
+static bool ensure_team_cache(saugen_Generator *o, uint32_t team, bool mail) {
 	const uint32_t stride = (o->row_len + (team - 1u) * TEAM_LEAD_CHUNKS * 128u + 3u) & ~3u;
-	if (o->h_desc.team_cache && o->h_desc.team_cache_stride >= stride) return true;
-	if (o->team_cache_failed) return false;
-	const size_t bytes = (size_t) (o->nlv ? o->nlv : 1) * TEAM_SLOTS * stride * sizeof(float);
-	float *p = (float*) o->take(false, bytes);
-	if (!p) { o->team_cache_failed = true; cudaGetLastError(); return false; }
-	cudaStreamSynchronize(o->stream);
-	o->h_desc.team_cache = p; o->h_desc.team_cache_stride = stride;
-	return cudaMemcpy(o->d_desc, &o->h_desc, sizeof(GenDesc), cudaMemcpyHostToDevice) == cudaSuccess;
+	const size_t nl = o->nlv ? o->nlv : 1;
+	bool changed = false;
+	if (!(o->h_desc.team_cache && o->h_desc.team_cache_stride >= stride) && !o->team_cache_failed) {
+		float *p = (float*) o->take(false, nl * TEAM_SLOTS * stride * sizeof(float));
+		if (!p) { o->team_cache_failed = true; cudaGetLastError(); }
+		else { o->h_desc.team_cache = p; o->h_desc.team_cache_stride = stride; changed = true; }
+	}
+	if (mail && !o->h_desc.team_mail && !o->team_cache_failed) {
+		/* a team over several CTAs: the voices' mailboxes and {arrivals, epoch} words */
+		const uint32_t mb = team_mail_bytes(plan_area_bytes(o->nplan), o->max_ops ? o->max_ops : 1);
+		unsigned char *p = (unsigned char*) o->take(false, nl * mb + nl * 64);
+		if (!p) { o->team_cache_failed = true; cudaGetLastError(); }
+		else {
+			o->h_desc.team_mail = p; o->h_desc.team_mail_stride = mb;
+			o->h_desc.team_hdr = (uint32_t*) (p + nl * mb);
+			changed = true;
+		}
+	}
+	if (changed) {
+		cudaStreamSynchronize(o->stream);
+		if (cudaMemcpy(o->d_desc, &o->h_desc, sizeof(GenDesc), cudaMemcpyHostToDevice) != cudaSuccess) return false;
+	}
+	return o->h_desc.team_cache != nullptr && (!mail || o->h_desc.team_mail != nullptr);
 }
 
 /* Plans and launches one call into slot `si` (kernels + read-back queued on the generator's
@@ -1430,7 +1446,20 @@ static int launch_call(saugen_Generator *o, int si, size_t buf_len, int stereo, 
 		static const char *venv = getenv("SAUGEN_PLAN_VERIFY");
 		if (venv && venv[0] == '1') shape.mask |= 0x10000000u;     /* render_ops.cuh:VERIFY_FLAG */
 	}
-	if (shape.team > 1) ensure_team_cache(o, shape.team);      /* (none: PM-only plans still split) */
+	/* one voice per CTA and SMs to spare: the voice's team spans `multi` CTAs (render_team.cuh) -- as many as
+	 * its members can use at this call length, at most what leaves every voice the same number */
+	uint32_t multi = 1;
+	if (shape.team > 1 && shape.warps == shape.team) {
+		static const char *menv = getenv("SAUGEN_MULTI");      /* developer knob: 0 = off, n = at most n CTAs */
+		const uint32_t sms = (uint32_t) device_sm_count(), nl = o->nlv ? o->nlv : 1;
+		const uint32_t wanted = (uint32_t) (buf_len / 128) / 2u;       /* members at two chunks each */
+		uint32_t k = (wanted + shape.team - 1) / shape.team;
+		if (k > TEAM_MAX_CTAS) k = TEAM_MAX_CTAS;
+		if (k > sms / nl) k = sms / nl;
+		if (menv && (uint32_t) atoi(menv) < k) k = (uint32_t) atoi(menv);
+		if (k >= 2 && o->max_ops <= TEAM_MAIL_OPS && ensure_team_cache(o, shape.team * k, true)) multi = k;
+	}
+	if (shape.team > 1 && multi == 1) ensure_team_cache(o, shape.team, false);      /* (none: PM-only plans still split) */
 	const uint32_t warps = shape.warps;
 	if (!warps) {
 		g_err = "saugen_run: a voice program of this script needs more shared memory than one SM has";
@@ -1517,7 +1546,8 @@ static int launch_call(saugen_Generator *o, int si, size_t buf_len, int stereo, 
 	cd.pcm = mode == 1 ? (int16_t*) sl.d_mix : sl.d_pcm;      /* (float planes in mode 1) */
 	cd.status = sl.d_status;
 	cudaError_t e;
-	if (o->compact && ngroups == 1 && nseg <= INLINE_SEGS && nunits <= INLINE_UNITS) {
+	const bool prologue = o->compact && ngroups == 1 && nseg <= INLINE_SEGS && nunits <= INLINE_UNITS;
+	if (prologue) {
 		/* the usual call: its descriptors travel as kernel parameters of one small kernel that also
 		 * zeroes [vlen][progress] + the slot's status and takes the run-ahead snapshot of the state
 		 * -- no copy-engine work between the previous call's kernels and this call's */
@@ -1531,6 +1561,7 @@ static int launch_call(saugen_Generator *o, int si, size_t buf_len, int stereo, 
 		pa.zero_b = sl.d_status; pa.zero_b_words = 1 + nseg;
 		pa.snap_src = (const uint4*) o->d_ops; pa.snap_dst = (uint4*) o->d_snap;
 		pa.snap_n16 = ahead ? (uint32_t) ((o->state_bytes + 15) / 16) : 0u;
+		pa.zero_c = o->h_desc.team_hdr; pa.zero_c_words = multi > 1 ? (o->nlv ? o->nlv : 1) * 16u : 0u;
 		e = launch_prologue(ic, pa, o->stream);
 		o->counters[1]++;
 	} else if (o->compact) {
@@ -1569,8 +1600,11 @@ static int launch_call(saugen_Generator *o, int si, size_t buf_len, int stereo, 
 				e = cudaMemsetAsync(o->d_progress, 0, ((size_t) o->nlv + 1) * sizeof(uint32_t), o->stream);
 			if (e != cudaSuccess) break;
 		}
-		e = launch_render(o->d_call, 1, o->d_segs, o->d_units, o->nlv, o->d_tables, o->d_coefs,
-				shape.mask, o->nbufs, o->max_ops, o->nplan, warps, ticketed_ctas, sched_mode, shape.team, o->stream);
+		if (multi > 1 && (gi > 0 || !prologue))
+			e = cudaMemsetAsync(o->h_desc.team_hdr, 0, (size_t) (o->nlv ? o->nlv : 1) * 64, o->stream);
+		if (e == cudaSuccess)
+			e = launch_render(o->d_call, 1, o->d_segs, o->d_units, o->nlv, o->d_tables, o->d_coefs,
+					shape.mask, o->nbufs, o->max_ops, o->nplan, warps, ticketed_ctas, sched_mode, shape.team, o->stream, multi);
 		o->counters[0]++;
 	}
 	if (e == cudaSuccess && ngroups > 1) {
