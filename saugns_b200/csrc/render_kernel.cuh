@@ -118,6 +118,8 @@ __device__ __noinline__ void render_units(Ctx &c, FastCtx &fc, const CallDesc *c
 			uint32_t sp = 0;
 			uint32_t which_kept = 0xffu;   /* the stretch's fused shape, where it was looked up */
 			uint32_t kmax = 0;             /* blocks the plan holds for, from this stretch's start */
+			uint32_t teamP = 0;            /* the teams' analysis of the plan: 0 unknown, 1 + P, 0x100 not eligible */
+			bool teamP_kept = false;
 			uint32_t kept = 0;         /* the plan came from the voice's kept one: 1 + its fused shape (0xff: not looked up) */
 			if (off % REF_BLOCK == 0 && uend - off >= (uint32_t) REF_BLOCK &&
 					vs.duration >= (uint32_t) REF_BLOCK && vs.code_len && !(fc.wave_mask & TAP_FLAG) &&
@@ -135,7 +137,7 @@ __device__ __noinline__ void render_units(Ctx &c, FastCtx &fc, const CallDesc *c
 				uint4 *kp = nullptr;
 				bool have = false;
 				if (fc.keep_plans && g->plan_cache && (fc.wave_mask & CTAB_FLAG)) {
-					kp = g->plan_cache + (size_t) lv * (1u + 2u * g->plan_cache_recs);
+					kp = g->plan_cache + (size_t) lv * (18u + 2u * g->plan_cache_recs);
 					if (vs.plan_gen && vs.plan_left && vs.plan_so == fc.so && vs.plan_st == fc.st) {
 						const uint4 kh = __ldcg(kp);
 						if (kh.x == vs.plan_gen && kh.y <= g->plan_cache_recs && kh.y + 3u <= fc.plan_cap) {
@@ -156,6 +158,7 @@ __device__ __noinline__ void render_units(Ctx &c, FastCtx &fc, const CallDesc *c
 								kmax = vs.plan_left;
 								sp = (kmax < kb ? kmax : kb) << 16 | kh.y;
 								kept = 1u + (kh.z & 0xffu);
+								teamP = kh.w; teamP_kept = kh.w != 0u;
 							}
 						}
 					}
@@ -194,7 +197,7 @@ __device__ __noinline__ void render_units(Ctx &c, FastCtx &fc, const CallDesc *c
 					if ((fc.wave_mask & VERIFY_FLAG) && fc.keep_plans && g->plan_cache && vs.plan_gen && vs.plan_left &&
 							vs.plan_so == fc.so && vs.plan_st == fc.st) {
 						/* developer knob: the kept plan, had it been used, against the fresh one */
-						const uint4 *kq = g->plan_cache + (size_t) lv * (1u + 2u * g->plan_cache_recs);
+						const uint4 *kq = g->plan_cache + (size_t) lv * (18u + 2u * g->plan_cache_recs);
 						const uint4 kh = __ldcg(kq);
 						if (kh.x == vs.plan_gen) {
 							uint32_t bad = kh.y != nrec || (kmax < 0x7fffu && kmax != vs.plan_left) ? 1u : 0u;
@@ -226,7 +229,9 @@ __device__ __noinline__ void render_units(Ctx &c, FastCtx &fc, const CallDesc *c
 					const bool shared = fc.team && !other &&
 						team_stretch(*fc.team, fc.sb, lane, fc.plan, nrec, vs.ops_cnt, span, which,
 								g->team_cache ? g->team_cache + (size_t) lv * TEAM_SLOTS * g->team_cache_stride : nullptr,
-								g->team_cache_stride);
+								g->team_cache_stride,
+								g->plan_cache ? g->plan_cache + (size_t) lv * (18u + 2u * g->plan_cache_recs) + 1u + 2u * g->plan_cache_recs : nullptr,
+								teamP);
 					if (shared) { }
 					else if (other) run_block_lowered<true>(fc.sb, fc.plan, lane, 0u, span);
 					else if (which) fused_run(which, fc.sb, fc.plan, lane, 0u, span);
@@ -244,14 +249,25 @@ __device__ __noinline__ void render_units(Ctx &c, FastCtx &fc, const CallDesc *c
 					const uint32_t left = kmax - nb;
 					if (kept) {
 						vs.plan_left = left;
+						if (fc.team && teamP && !teamP_kept) {
+							/* the teams' analysis of the kept plan, made in this stretch: kept too (levels -> the records) */
+							uint4 *kq = g->plan_cache + (size_t) lv * (18u + 2u * g->plan_cache_recs);
+							__syncwarp();
+							for (uint32_t i = lane; i < 2u * nrec; i += 32) __stcg(kq + 1 + i, lds128u(fc.plan + PLAN_HDR + 16u * i));
+							for (uint32_t i = lane; i < 17u; i += 32) __stcg(kq + 1 + 2u * g->plan_cache_recs + i, lds128u(fc.team->cmd + TC_INFO + 16u * i));
+							if (lane == 0) __stcg(reinterpret_cast<uint32_t*>(kq) + 3, teamP);
+							__syncwarp();
+						}
 					} else if (left && !other && nrec <= g->plan_cache_recs) {
 						/* keep the plan for the stretches to come (a new generation: a call that is undone
 						 * later -- run-ahead -- leaves the voice's older generation number behind, not this plan) */
-						uint4 *kq = g->plan_cache + (size_t) lv * (1u + 2u * g->plan_cache_recs);
+						uint4 *kq = g->plan_cache + (size_t) lv * (18u + 2u * g->plan_cache_recs);
 						const uint32_t gen = (__ldcg(kq).x & 0x7fffffffu) + 1u;
 						__syncwarp();
 						for (uint32_t i = lane; i < 2u * nrec; i += 32) __stcg(kq + 1 + i, lds128u(fc.plan + PLAN_HDR + 16u * i));
-						if (lane == 0) __stcg(kq, make_uint4(gen, nrec, which_kept, 0u));
+						if (fc.team && teamP)
+							for (uint32_t i = lane; i < 17u; i += 32) __stcg(kq + 1 + 2u * g->plan_cache_recs + i, lds128u(fc.team->cmd + TC_INFO + 16u * i));
+						if (lane == 0) __stcg(kq, make_uint4(gen, nrec, which_kept, fc.team ? teamP : 0u));
 						__syncwarp();          /* every lane has read the plan before the area is used again */
 						vs.plan_gen = gen; vs.plan_so = fc.so; vs.plan_st = fc.st; vs.plan_left = left;
 					} else {

@@ -392,23 +392,24 @@ __device__ __noinline__ void team_run(const TeamCtx &tc, uint32_t sb, int lane) 
 		}
 		team_sync(tc, lane);
 		if (!w && lane == 0 && q < 8u && team_traced(tc.bar)) g_team_dump[8 + q] = (uint32_t) (clock64() - tq);
-		if (q < P && active && w && lane == 0) {
+		if (q < P && active && w) {
 			/* this member's start values of the accumulators counted in this phase: the voice's own +
-			 * every earlier member's count (the master plan names them) */
+			 * every earlier member's count (the master plan names them; the lanes share the members) */
 			for (uint32_t r = 0; r < nrec; ++r) {
 				const uint32_t a = tc.lead_plan + PLAN_HDR + r * PLAN_REC;
 				const uint4 x = lds128u(a);
 				const uint32_t kind = x.x & 0xffu;
 				if (kind == P_EXT || !(kind >= X_OSC0 && kind < X_RANGE) || ((x.y >> 24) & 0xfu) != q + 1u) continue;
 				const uint32_t off = x.z - tc.lead_so;         /* the operator's offset in a member's area */
-				uint32_t acc = lds32(x.z + OS_I0);
+				uint32_t sum = 0;
 				if (tc.K > 1u) {
-					for (uint32_t j = 0; j < w; ++j) acc += __ldcg(mcounts + j * TEAM_MAIL_OPS + off / 192u);
+					for (uint32_t j = lane; j < w; j += 32) sum += __ldcg(mcounts + j * TEAM_MAIL_OPS + off / 192u);
 				} else {
-					for (uint32_t j = 0; j < w; ++j)
-						acc += lds32(tc.so_b + off - (w - j) * tc.per_warp + OS_PAD0);
+					for (uint32_t j = lane; j < w; j += 32)
+						sum += lds32(tc.so_b + off - (w - j) * tc.per_warp + OS_PAD0);
 				}
-				sts32(tc.so_b + off + OS_PAD1, acc);
+				sum = __reduce_add_sync(FULL, sum);
+				if (lane == 0) sts32(tc.so_b + off + OS_PAD1, lds32(x.z + OS_I0) + sum);
 			}
 		}
 		__syncwarp();
@@ -430,13 +431,25 @@ __device__ __noinline__ void team_run(const TeamCtx &tc, uint32_t sb, int lane) 
  * voice's cache in global memory (TEAM_SLOTS slots of `stride` floats; none: plans with P > 0 are
  * not eligible). */
 __device__ __noinline__ bool team_stretch(const TeamCtx &tc, uint32_t sb, int lane, uint32_t plan, uint32_t nrec,
-		uint32_t nops, uint32_t span, uint32_t fused, float *cache, uint32_t stride) {
+		uint32_t nops, uint32_t span, uint32_t fused, float *cache, uint32_t stride, const uint4 *kinfo, uint32_t &kP) {
 	const uint32_t C = span / (uint32_t) CHUNK;
 	uint32_t P = 0;
 	const long long t0 = clock64();
-	if (lane == 0) P = team_analyse(plan + PLAN_HDR, nrec, tc.cmd);
-	__syncwarp();              /* (it wrote the records' levels) */
-	P = __shfl_sync(FULL, P, 0);
+	if (kP != 0u && kinfo) {
+		/* a kept plan whose analysis was kept with it (render_kernel.cuh): levels are in the records */
+		P = kP == 0x100u ? TEAM_INELIGIBLE : kP - 1u;
+		if (P != TEAM_INELIGIBLE)
+			for (uint32_t i = lane; i < 17u; i += 32) {
+				const uint4 x = __ldcg(kinfo + i);
+				asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(tc.cmd + TC_INFO + 16u * i), "r"(x.x), "r"(x.y), "r"(x.z), "r"(x.w) : "memory");
+			}
+		__syncwarp();
+	} else {
+		if (lane == 0) P = team_analyse(plan + PLAN_HDR, nrec, tc.cmd);
+		__syncwarp();              /* (it wrote the records' levels) */
+		P = __shfl_sync(FULL, P, 0);
+		kP = P == TEAM_INELIGIBLE ? 0x100u : P + 1u;
+	}
 	if (lane == 0 && team_traced(tc.bar)) {
 		uint32_t ns = 0;
 		if (P != TEAM_INELIGIBLE)

@@ -959,7 +959,7 @@ static saugen_Generator *create_from_flat(const Flat &f, const saugen_WaveTables
 		o->slot[0].d_mix = o->d_mix; o->slot[1].d_mix = (float*) (base + o_mix1);
 		static const char *pcenv = getenv("SAUGEN_PLANCACHE");    /* developer knob: 0 = stable plans are not kept */
 		if (o->nplan && o->d_coefs && !(pcenv && pcenv[0] == '0')) {
-			const size_t pcb = nl * (1 + 2 * (size_t) o->nplan) * 16;
+			const size_t pcb = nl * (18 + 2 * (size_t) o->nplan) * 16;     /* header, records, the teams' analysis */
 			o->d_plan_cache = o->take(false, pcb);
 			if (o->d_plan_cache) CK(cudaMemsetAsync(o->d_plan_cache, 0, pcb, o->stream));
 		}
