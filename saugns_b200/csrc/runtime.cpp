@@ -1404,6 +1404,7 @@ static bool ensure_team_cache(saugen_Generator *o, uint32_t team, bool mail) {
 		unsigned char *p = (unsigned char*) o->take(false, nl * mb + nl * 64);
 		if (!p) { o->team_cache_failed = true; cudaGetLastError(); }
 		else {
+			cudaMemsetAsync(p, 0, nl * mb + nl * 64, o->stream);
 			o->h_desc.team_mail = p; o->h_desc.team_mail_stride = mb;
 			o->h_desc.team_hdr = (uint32_t*) (p + nl * mb);
 			changed = true;
