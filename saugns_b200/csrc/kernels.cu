@@ -242,8 +242,12 @@ cudaError_t launch_render(const CallDesc *d_calls, uint32_t ncalls, const SegDes
 		uint32_t team_arg = team | multi << 8, sched_arg = 0u;
 		void *args[] = {&d_calls, &ncalls, &d_segs, &d_units, &ntasks, &d_tables, &d_coefs, &wave_mask, &nbufs,
 			&nslots_ops, &nplan, &warps, &sched_arg, &team_arg};
-		return cudaLaunchCooperativeKernel(wide ? (const void*) render_kernel_wide : (const void*) render_kernel,
+		cudaError_t e = cudaLaunchCooperativeKernel(wide ? (const void*) render_kernel_wide : (const void*) render_kernel,
 				dim3(grid), dim3(warps * 32), args, smem, stream);
+		if (e == cudaSuccess) return e;
+		/* refused (the device cannot hold the grid at once, e.g. under MPS): one CTA per voice */
+		cudaGetLastError();
+		grid /= multi;
 	}
 	if (wide)
 		render_kernel_wide<<<grid, warps * 32, smem, stream>>>(d_calls, ncalls, d_segs, d_units, ntasks,
