@@ -457,6 +457,11 @@ __device__ __forceinline__ uint32_t rec_code(uint32_t w0, uint32_t w1) {
 			((fl & PF_LAYER) ? 0x80u : 0u) | ((xf & XF_ST) ? 0x100u : 0u) | ((xf & XF_SRC_VAL) ? 0x200u : 0u);
 	if (kind == X_RANGE) return 0x2000u | ((xf & XF_ST) ? 0x100u : 0u) | ((xf & XF_SRC_VAL) ? 0x200u : 0u);
 	if (kind == X_VOUT) return 0x3000u | ((xf & XF_SRC_VAL) ? 0x200u : 0u);
+	/* the records of a team's phase plans (render_team.cuh); a counting record keeps its code in and out of its window */
+	if (kind == X_SAVE) return 0x4000u | (fl & 1u);
+	if (kind == X_LOAD) return 0x5000u | (fl & 1u);
+	if (kind == X_COUNT1 || kind == X_COUNT2) return 0x6000u | (kind == X_COUNT1 ? 1u : 2u) | ((xf & XF_SRC_VAL) ? 0x200u : 0u);
+	if (kind == X_NOP) return 0x6000u | (fl & 3u) | ((xf & XF_SRC_VAL) ? 0x200u : 0u);
 	return 0xffffu;            /* not a fusable record */
 }
 
@@ -545,6 +550,59 @@ struct FVout {
 	}
 };
 
+/* a team's phase plans: value to / from the stretch's cache, counting records */
+template <bool FROMBUF>
+struct FSave {
+	static constexpr uint32_t SLOTS = 1;
+	static constexpr uint16_t CODE = 0x4000u | (FROMBUF ? 1u : 0u);
+	static __device__ __forceinline__ void exec(const HotCtx &c, const uint32_t rec, float val[4]) {
+		const uint4 p0 = lds128u(rec);
+		float *g = reinterpret_cast<float*>((uint64_t) p0.z | ((uint64_t) p0.w << 32)) + c.oc + c.lane * 4;
+		if (FROMBUF) fld<4>(c, (p0.x >> 16) & 0xffu, val);
+		__stcg(reinterpret_cast<float4*>(g), make_float4(val[0], val[1], val[2], val[3]));
+	}
+};
+template <bool TOBUF>
+struct FLoad {
+	static constexpr uint32_t SLOTS = 1;
+	static constexpr uint16_t CODE = 0x5000u | (TOBUF ? 1u : 0u);
+	static __device__ __forceinline__ void exec(const HotCtx &c, const uint32_t rec, float val[4]) {
+		const uint4 p0 = lds128u(rec);
+		const float *g = reinterpret_cast<const float*>((uint64_t) p0.z | ((uint64_t) p0.w << 32)) + c.oc + c.lane * 4;
+		const float4 v = __ldcg(reinterpret_cast<const float4*>(g));
+		val[0] = v.x; val[1] = v.y; val[2] = v.z; val[3] = v.w;
+		if (TOBUF) { fst<4>(c, (p0.x >> 16) & 0xffu, val); __syncwarp(); }
+	}
+};
+template <int WHICH, bool SRCVAL>
+struct FCount {
+	static constexpr uint32_t SLOTS = 1;
+	static constexpr uint16_t CODE = 0x6000u | WHICH | (SRCVAL ? 0x200u : 0u);
+	static __device__ __forceinline__ void exec(const HotCtx &c, const uint32_t rec, float val[4]) {
+		const uint4 p0 = lds128u(rec);
+		if ((p0.x & 0xffu) == X_NOP) return;           /* outside its window */
+		float fr[4];
+		if (SRCVAL) {
+#pragma unroll
+			for (int k = 0; k < 4; ++k) fr[k] = val[k];
+		} else {
+			fld<4>(c, WHICH == 1 ? p0.x >> 24 : (p0.y >> 8) & 0xffu, fr);
+		}
+		if (WHICH == 2) {
+			const float v0 = lds32f(rec + 20);
+#pragma unroll
+			for (int k = 0; k < 4; ++k) fr[k] = v0 * fr[k];
+		}
+		const float coeff = lds32f(c.plan + PH_COEFF);
+		uint32_t run = 0;
+#pragma unroll
+		for (int k = 0; k < 4; ++k) run += ftoi_lo32(coeff * fr[k]);
+		const uint32_t tot = __reduce_add_sync(FULL, run);
+		if (c.lane == 0) sts32(p0.z + OS_I0, lds32(p0.z + OS_I0) + tot);
+		__syncwarp();
+	}
+};
+
 template <class... R>
 struct Shape {
 	static constexpr uint32_t N = sizeof...(R);
@@ -589,6 +647,12 @@ using ShapeFM3h    = Shape<FOsc<0, 0, 0, true, false, false, false>, FRange<true
 using ShapeC3FM    = Shape<FOsc<0, 0, 1, true, false, false, false>, FRange<true, true>,
                            FOsc<2, 0, 0, false, false, false, true>, FOsc<1, 2, 2, false, false, false, false>,
                            FVout<true>>;                                                             /* range-FM carrier + ratio PM modulator */
+/* the two phases of a team on the range-FM voice (render_team.cuh): modulator + range, kept, with the two
+ * oscillators counted that it feeds; then those two and the voice output */
+using ShapeC3FMq0  = Shape<FOsc<0, 0, 1, true, false, false, false>, FRange<true, true>, FSave<false>,
+                           FCount<2, true>, FCount<1, false>>;
+using ShapeC3FMq1  = Shape<FLoad<true>, FOsc<2, 0, 0, false, false, false, true>,
+                           FOsc<1, 2, 2, false, false, false, false>, FVout<true>>;
 constexpr uint32_t FUSED_NONE = 0;
 __device__ uint32_t g_sig_dump[36];           /* developer aid: the first stretch's signature (saugen_debug_signature) */
 
@@ -616,6 +680,8 @@ __device__ __noinline__ uint32_t fused_match(uint32_t plan, uint32_t nrec, bool 
 	if (ShapeW1x::match(codes, n)) return 5;
 	if (ShapePM3::match(codes, n)) return 8;
 	if (ShapeFM3h::match(codes, n)) return 9;
+	if (ShapeC3FMq0::match(codes, n)) return 10;
+	if (ShapeC3FMq1::match(codes, n)) return 11;
 	return FUSED_NONE;
 }
 __device__ __forceinline__ void fused_run(uint32_t which, uint32_t sb, uint32_t plan, int lane, uint32_t oc0, uint32_t len) {
@@ -628,6 +694,8 @@ __device__ __forceinline__ void fused_run(uint32_t which, uint32_t sb, uint32_t 
 	case 6: ShapeC3PMh::run(sb, plan, lane, oc0, len); break;
 	case 7: ShapeC3FMh::run(sb, plan, lane, oc0, len); break;
 	case 8: ShapePM3::run(sb, plan, lane, oc0, len); break;
+	case 10: ShapeC3FMq0::run(sb, plan, lane, oc0, len); break;
+	case 11: ShapeC3FMq1::run(sb, plan, lane, oc0, len); break;
 	default: ShapeFM3h::run(sb, plan, lane, oc0, len); break;
 	}
 }

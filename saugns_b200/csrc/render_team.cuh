@@ -207,7 +207,7 @@ __device__ __forceinline__ bool rec_has_op(uint32_t kind) {
  * with A = q + 1.  `cache`: this member's window of the voice's cache (slot stride `stride` floats).
  * Returns the shared address of the voice-output record in the copy (0 when the phase has none). */
 __device__ __noinline__ uint32_t team_build_phase(uint32_t master, uint32_t exec, uint32_t nrec, uint32_t delta,
-		uint32_t q, uint32_t P, uint32_t cmd, float *cache, uint32_t stride) {
+		uint32_t q, uint32_t P, uint32_t cmd, float *cache, uint32_t stride, uint32_t &nout) {
 	for (uint32_t i = 0; i < PLAN_HDR; i += 16) {
 		const uint4 h = lds128u(master + i);
 		asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(exec + i), "r"(h.x), "r"(h.y), "r"(h.z), "r"(h.w) : "memory");
@@ -258,6 +258,7 @@ __device__ __noinline__ uint32_t team_build_phase(uint32_t master, uint32_t exec
 		}
 	}
 	sts32(out, P_STOP);
+	nout = (out - exec - PLAN_HDR) / PLAN_REC;
 	return vout;
 }
 
@@ -337,12 +338,16 @@ __device__ __noinline__ void team_run(const TeamCtx &tc, uint32_t sb, int lane) 
 		if (active) {
 			const uint32_t start = w ? a_w - L + q : 0u;
 			const bool counts = q < P && w + 1u < t_eff;           /* a later member needs this one's counts */
-			uint32_t vout = 0;
+			uint32_t vout = 0, fq = 0;
 			if (lane == 0) {
-				vout = team_build_phase(tc.lead_plan, tc.plan_x, nrec, delta, q, P, tc.cmd, cache, stride);
+				uint32_t nx = 0;
+				vout = team_build_phase(tc.lead_plan, tc.plan_x, nrec, delta, q, P, tc.cmd, cache, stride, nx);
 				team_phase_init(tc.plan_x, start, w, delta);
+				/* P = 0: the full plan, whose shape the leader looked up; else this phase's own */
+				fq = P == 0u ? fused : (fused ? fused_match(tc.plan_x, nx, false) : 0u);
 			}
 			vout = __shfl_sync(FULL, vout, 0);
+			fq = __shfl_sync(FULL, fq, 0);
 			uint32_t cur = start;
 			while (cur < a_next) {
 				uint32_t nxt = a_next;
@@ -370,8 +375,8 @@ __device__ __noinline__ void team_run(const TeamCtx &tc, uint32_t sb, int lane) 
 				}
 				nxt = __shfl_sync(FULL, nxt, 0);
 				__syncwarp();
-				if (P == 0 && fused && (!w || cur >= a_w))      /* the full plan as one straight-line function */
-					fused_run(fused, sb, tc.plan_x, lane, cur * (uint32_t) CHUNK, (nxt - cur) * (uint32_t) CHUNK);
+				if (fq && (!vout || !w || cur >= a_w))          /* the phase's plan as one straight-line function */
+					fused_run(fq, sb, tc.plan_x, lane, cur * (uint32_t) CHUNK, (nxt - cur) * (uint32_t) CHUNK);
 				else
 					run_block_lowered<false, true>(sb, tc.plan_x, lane, cur * (uint32_t) CHUNK, (nxt - cur) * (uint32_t) CHUNK);
 				__syncwarp();
