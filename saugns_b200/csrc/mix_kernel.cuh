@@ -67,7 +67,10 @@ mix_kernel(const CallDesc *calls, const SegDesc *segs, uint32_t mode /*0 pcm, 1 
 	MixSmem &sm = *reinterpret_cast<MixSmem*>(mix_smem_raw);
 	const CallDesc *cd = &calls[blockIdx.y];
 	const GenDesc *g = cd->gen;
-	const uint32_t f0 = blockIdx.x * MIX_FRAMES;
+	/* frame tiles in DESCENDING order of launch: the render kernel wrote the call's last tiles last, so the
+	 * L2 still holds a good part of them (dirty); taking them first turns those reads into L2 hits */
+	const uint32_t bx = gridDim.x - 1u - blockIdx.x;
+	const uint32_t f0 = bx * MIX_FRAMES;
 	if (f0 >= cd->call_len) return;
 	const uint32_t tid = threadIdx.x;
 	const bool producer = tid >= (uint32_t) MIX_FRAMES;          /* the last warp */
@@ -127,7 +130,7 @@ mix_kernel(const CallDesc *calls, const SegDesc *segs, uint32_t mode /*0 pcm, 1 
 		 * posts the transaction count and issues the bulk copies: the MIX_TV voices' s
 		 * pieces are contiguous (one copy), r pieces only for moving pans. */
 		const uint32_t lane = tid & 31u;
-		const float *tile_s = g->rows_s + (size_t) blockIdx.x * tstride;
+		const float *tile_s = g->rows_s + (size_t) bx * tstride;
 		/* the records are fetched three stages ahead of their use (their L2 latency
 		 * would otherwise sit in this loop's critical path) */
 		auto fetch = [&](uint32_t t) {
@@ -160,7 +163,7 @@ mix_kernel(const CallDesc *calls, const SegDesc *segs, uint32_t mode /*0 pcm, 1 
 		return;
 	}
 	const uint32_t fx = in_seg ? fi : 0xffffffffu;               /* frames outside take nothing */
-	const float *tile_r = g->rows_r + (size_t) blockIdx.x * tstride + tid;
+	const float *tile_r = g->rows_r + (size_t) bx * tstride + tid;
 	for (uint32_t t = 0; t < ntiles; ++t) {
 		const uint32_t st = t % MIX_STAGES, v0 = t * MIX_TV;
 		const uint32_t nv = nlv - v0 < (uint32_t) MIX_TV ? nlv - v0 : (uint32_t) MIX_TV;
