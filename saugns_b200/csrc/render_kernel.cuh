@@ -53,32 +53,44 @@ __device__ __noinline__ void render_units(Ctx &c, FastCtx &fc, const CallDesc *c
 	fc.coeff = g->coeff; fc.amp_scale = g->amp_scale;
 	VoiceState *vsp = &g->voices[v];
 	VoiceState vs;
+	uint32_t first_w;
 	{
 		/* lane 0 reads (from L2: another SM may have written it), every lane gets
 		 * the same copy */
 		const uint32_t *src = reinterpret_cast<const uint32_t*>(vsp);
 		uint32_t *dst = reinterpret_cast<uint32_t*>(&vs);
-		static_assert(sizeof(VoiceState) / 4 <= 32, "one word per lane");
-		uint32_t w = 0;
-		if (lane < (int) (sizeof(VoiceState) / 4)) w = __ldcg(src + lane);      /* one round trip */
+		/* ONE round trip for everything whose address is known now: the voice's state (lanes 0..15), its
+		 * event-list bounds (16, 17), the first unit (20..22) and, in case it is the unit's, segment 0 (24..26) */
+		static_assert(sizeof(VoiceState) / 4 <= 16 && sizeof(UnitDesc) == 12 && sizeof(SegDesc) == 12, "lane map");
+		const uint32_t *p = nullptr;
+		if (lane < (int) (sizeof(VoiceState) / 4)) p = src + lane;
+		else if (lane == 16 || lane == 17) p = g->vev_off + v + (lane - 16);
+		else if (lane >= 20 && lane < 23 && u0 < u1) p = reinterpret_cast<const uint32_t*>(units + cd->unit_off + u0) + (lane - 20);
+		else if (lane >= 24 && lane < 27 && u0 < u1) p = reinterpret_cast<const uint32_t*>(segs + cd->seg_off) + (lane - 24);
+		const uint32_t w = p ? __ldcg(p) : 0u;
 #pragma unroll
 		for (uint32_t i = 0; i < sizeof(VoiceState) / 4; ++i) dst[i] = __shfl_sync(FULL, w, i);
+		first_w = w;
 	}
 	/* the voice program's bytecode and operator list: towards L1 now, read one by one later */
 	for (uint32_t i = lane; i < vs.code_len; i += 32)
 		asm volatile("prefetch.global.L1 [%0];" :: "l"(g->code + vs.code_off + i));
 	if (lane == 0) asm volatile("prefetch.global.L1 [%0];" :: "l"(g->prog_ops + vs.ops_off));
 	SAUGEN_TRACE(19);                  /* voice state read */
-	const uint32_t ev_lo = g->vev_off[v], ev_n = g->vev_off[v + 1] - ev_lo;
+	const uint32_t ev_lo = __shfl_sync(FULL, first_w, 16), ev_n = __shfl_sync(FULL, first_w, 17) - ev_lo;
+	UnitDesc ud0;
+	SegDesc sd0;
+	ud0.seg = __shfl_sync(FULL, first_w, 20); ud0.off = __shfl_sync(FULL, first_w, 21); ud0.len = __shfl_sync(FULL, first_w, 22);
+	sd0.start = __shfl_sync(FULL, first_w, 24); sd0.len = __shfl_sync(FULL, first_w, 25); sd0.ev_end = __shfl_sync(FULL, first_w, 26);
 	float *row_s = g->rows_s + (size_t) lv * ROW_TILE;      /* the voice's piece of frame tile 0 */
 	float *row_r = g->rows_r + (size_t) lv * ROW_TILE;
 	c.tstride = g->row_stride;
 	uint32_t loaded = 0;        // operator states currently held in shared memory
 
 	for (uint32_t ui = u0; ui < u1; ++ui) {
-		const UnitDesc ud = units[cd->unit_off + ui];
+		const UnitDesc ud = ui == u0 ? ud0 : units[cd->unit_off + ui];
 		const uint32_t si = ud.seg;
-		const SegDesc sd = segs[cd->seg_off + si];
+		const SegDesc sd = (ui == u0 && si == 0u) ? sd0 : segs[cd->seg_off + si];
 		/* this voice's events due at the segment start, in order */
 		if (ud.off == 0 && vs.ev_cursor < ev_n && g->vev_idx[ev_lo + vs.ev_cursor] < sd.ev_end) {
 			if (loaded) { ops_store(c, loaded); loaded = 0; }
@@ -242,7 +254,7 @@ __device__ __noinline__ void render_units(Ctx &c, FastCtx &fc, const CallDesc *c
 				}
 				__syncwarp();
 				SAUGEN_TRACE(24);          /* stretch rendered */
-				if (lane == 0) steady_update(c.sops, g->code + vs.code_off, vs.code_len, nb);
+				steady_update(c.sops, g->code + vs.code_off, vs.code_len, nb, lane);
 				__syncwarp();
 				SAUGEN_TRACE(25);
 				if ((fc.wave_mask & CTAB_FLAG) && fc.keep_plans && g->plan_cache) {

@@ -471,12 +471,12 @@ __device__ __forceinline__ void line_skip_blocks(OpState *o, int li, uint32_t nb
 	o->lmeta[li] = LM_PACK(LM_TYPE(meta), flags, r >> 1);
 }
 
-/* lane 0 only */
-__device__ __noinline__ void steady_update(OpState *sops, const Instr *code, uint32_t code_len, uint32_t nb) {
-	uint4 raw_next = __ldg(reinterpret_cast<const uint4*>(code));
-	for (uint32_t pc = 0; pc < code_len; ++pc) {
-		const uint4 raw = raw_next;
-		if (pc + 1 < code_len) raw_next = __ldg(reinterpret_cast<const uint4*>(code + pc + 1));
+/* every lane: the instructions are shared out (each touches its own lines / time word of its operator: an
+ * operator's frequency, amplitude and other lines, its time and its self-PM flag each belong to ONE instruction
+ * of a voice program, runtime.cpp:Compiler) */
+__device__ __noinline__ void steady_update(OpState *sops, const Instr *code, uint32_t code_len, uint32_t nb, int lane) {
+	for (uint32_t pc = lane; pc < code_len; pc += 32) {
+		const uint4 raw = __ldg(reinterpret_cast<const uint4*>(code + pc));
 		Instr in;
 		memcpy(&in, &raw, sizeof(in));
 		OpState *o = sops + in.op;
