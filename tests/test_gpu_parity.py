@@ -488,6 +488,20 @@ def test_sweeps_past_2_24_samples(S, ref, tabs):
     assert np.array_equal(got, want)
 
 
+@pytest.mark.parametrize("knobs", [{"SAUGEN_MULTI": "0"}, {"SAUGEN_MULTI": "2"}, {"SAUGEN_MULTI": "3", "SAUGEN_TEAM": "5"},
+                                   {"SAUGEN_MULTI": "8"}, {"SAUGEN_TEAM": "0"}])
+def test_teams_over_several_ctas(S, knobs):
+    """Few-voice scripts with nested FM under every way of spreading a voice: no teams, teams inside one CTA,
+    teams over 2 / 3 (odd member counts) / up to 8 CTAs (render_team.cuh); each in its own process (the knobs
+    are read once), every result bit-exact."""
+    import subprocess
+    import sys
+    env = dict(os.environ, **knobs)
+    r = subprocess.run([sys.executable, os.path.join(os.path.dirname(__file__), "gpu_multi_cta.py")],
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 def test_kept_plans_equal_fresh_ones(S):
     """A voice's stable lowered plan is kept in global memory and reused call after call
     (render_kernel.cuh).  Under SAUGEN_PLAN_VERIFY=1 the kernel builds the plan afresh every time and
