@@ -2177,6 +2177,9 @@ extern "C" int saugen_counters(saugen_Generator *o, uint64_t out[4]) {
 /* Per-kernel device time: CUDA events on the launch stream around each kernel. */
 extern "C" int saugen_set_timing(saugen_Generator *o, int on) {
 	if (!o) return -1;
+	/* (a call that ran ahead was launched under the old setting: it is undone and launched again, so that
+	 * every call between two settings is timed, or none) */
+	if ((on != 0) != o->timing) { cudaSetDevice(o->device); cancel_runahead(o); }
 	o->timing = on != 0;                     /* (the events are made per call slot when first timed) */
 	o->render_ms = o->mix_ms = 0.0;
 	return 0;

@@ -14,7 +14,7 @@ import scripts
 
 def time_calls(prg, n=20, frames=24576):
     g = saugns_b200.Generator(prg, 96000, max_call_len=frames)
-    for _ in range(3):
+    for _ in range(6):             # past the scripts' first second (C3: a slower call where its 1 s ramps end)
         g.run_device(frames)
     g.set_timing(True)
     t0 = time.perf_counter()
