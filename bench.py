@@ -423,7 +423,8 @@ def run_gpu_arm(args):
     sampler.start()
     for _ in range(W):
         g.run_device(FRAMES)
-    g.set_timing(True)
+    g.set_timing(True)         # (undoes the call that ran ahead: the timed region is calls W+1 .. W+K for the events AND the kernel times)
+    km0 = g.kernel_ms()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     sampler.mark()
@@ -439,7 +440,8 @@ def run_gpu_arm(args):
     clocks = sampler.stop()
     ms = max_over_ranks(ev0.elapsed_time(ev1))
     c1 = g.counters()
-    render_ms, mix_ms = g.kernel_ms()
+    km1 = g.kernel_ms()
+    render_ms, mix_ms = km1[0] - km0[0], km1[1] - km0[1]
     launches = (c1[0] - c0[0]) + (c1[1] - c0[1])
     g.close()
 
@@ -594,7 +596,8 @@ def leg_c4(args, device, clocks, steps=20, warmup=3):
     g = saugns_b200.Generator(prg, SRATE, device=device, max_call_len=FRAMES)
     for _ in range(warmup):
         g.run_device(FRAMES)
-    g.set_timing(True)
+    g.set_timing(True)         # (undoes the call that ran ahead: events and kernel times cover the same calls)
+    km0 = g.kernel_ms()
     torch.cuda.synchronize()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
@@ -604,6 +607,7 @@ def leg_c4(args, device, clocks, steps=20, warmup=3):
     torch.cuda.synchronize()
     ms = ev0.elapsed_time(ev1)
     rk, mk = g.kernel_ms()
+    rk, mk = rk - km0[0], mk - km0[1]
     g.close()
     first = []
     t0 = time.perf_counter()
@@ -842,15 +846,16 @@ def leg_c3_sharded(args, dist, rank, local_rank, world, steps=20, warmup=3):
     prg = c3_program(1)
     vg = multigpu.VoiceShardedGenerator(prg, SRATE, device=local_rank, max_call_len=FRAMES)
     first = []
+    gen = getattr(vg.shard, "gen", None)
+    if gen is not None:
+        gen.set_timing(True)       # (before the warm-up: switching it re-launches a call that ran ahead)
     for i in range(warmup):
         more, pcm, n = vg.run(FRAMES)
         if rank == 0 and i < 2:
             first.append(pcm.copy())
     dist.barrier()
     torch.cuda.synchronize()
-    gen = getattr(vg.shard, "gen", None)
-    if gen is not None:
-        gen.set_timing(True)
+    km0 = gen.kernel_ms() if gen is not None else (0.0, 0.0)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(steps):
@@ -864,7 +869,7 @@ def leg_c3_sharded(args, dist, rank, local_rank, world, steps=20, warmup=3):
     # each rank's own kernels (device-timed, per call): what the collective and the host add is ms/steps minus these
     km = gen.kernel_ms() if gen is not None else (0.0, 0.0)
     per_rank = torch.zeros(2 * world, dtype=torch.float64, device="cuda")
-    per_rank[2 * rank], per_rank[2 * rank + 1] = km[0] / steps, km[1] / steps
+    per_rank[2 * rank], per_rank[2 * rank + 1] = (km[0] - km0[0]) / steps, (km[1] - km0[1]) / steps
     dist.all_reduce(per_rank)
     per_rank = [round(float(x), 4) for x in per_rank.tolist()]
     ncoll = getattr(vg, "collectives", None)
@@ -878,7 +883,6 @@ def leg_c3_sharded(args, dist, rank, local_rank, world, steps=20, warmup=3):
         for i in range(len(first)):
             more, pcm, n = g.run(FRAMES)
             mx = max(mx, int(np.abs(pcm.astype(np.int32) - first[i].astype(np.int32)).max()))
-        g.set_timing(True)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
