@@ -651,6 +651,8 @@ using ShapeC3FM    = Shape<FOsc<0, 0, 1, true, false, false, false>, FRange<true
  * oscillators counted that it feeds; then those two and the voice output */
 using ShapeC3FMq0  = Shape<FOsc<0, 0, 1, true, false, false, false>, FRange<true, true>, FSave<false>,
                            FCount<2, true>, FCount<1, false>>;
+using ShapeC3FMq0h = Shape<FOsc<0, 0, 0, true, false, false, false>, FRange<true, true>, FSave<false>,
+                           FCount<2, true>, FCount<1, false>>;                                       /* ... modulator ramp ended */
 using ShapeC3FMq1  = Shape<FLoad<true>, FOsc<2, 0, 0, false, false, false, true>,
                            FOsc<1, 2, 2, false, false, false, false>, FVout<true>>;
 constexpr uint32_t FUSED_NONE = 0;
@@ -682,6 +684,7 @@ __device__ __noinline__ uint32_t fused_match(uint32_t plan, uint32_t nrec, bool 
 	if (ShapeFM3h::match(codes, n)) return 9;
 	if (ShapeC3FMq0::match(codes, n)) return 10;
 	if (ShapeC3FMq1::match(codes, n)) return 11;
+	if (ShapeC3FMq0h::match(codes, n)) return 12;
 	return FUSED_NONE;
 }
 __device__ __forceinline__ void fused_run(uint32_t which, uint32_t sb, uint32_t plan, int lane, uint32_t oc0, uint32_t len) {
@@ -696,6 +699,7 @@ __device__ __forceinline__ void fused_run(uint32_t which, uint32_t sb, uint32_t 
 	case 8: ShapePM3::run(sb, plan, lane, oc0, len); break;
 	case 10: ShapeC3FMq0::run(sb, plan, lane, oc0, len); break;
 	case 11: ShapeC3FMq1::run(sb, plan, lane, oc0, len); break;
+	case 12: ShapeC3FMq0h::run(sb, plan, lane, oc0, len); break;
 	default: ShapeFM3h::run(sb, plan, lane, oc0, len); break;
 	}
 }
