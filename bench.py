@@ -562,7 +562,7 @@ def run_gpu_arm(args):
             line["cpu_baseline"] = {"value": None, "unit": "voice-samples/s", "cores": 0,
                                     "kind": "reference", "sample": f"unavailable: {e}"}
     if world == 1 and not args.no_extra:
-        for name, leg in (("c4", leg_c4), ("c5", leg_c5)):
+        for name, leg in (("c2", leg_c2), ("c4", leg_c4), ("c5", leg_c5)):
             try:
                 extra[name] = leg(args, local_rank, clocks)
             except Exception as e:
@@ -653,6 +653,73 @@ def leg_c4(args, device, clocks, steps=20, warmup=3):
         leg["cpu_baseline"] = {"value": vs / wall, "unit": "voice-samples/s", "cores": used, "kind": "reference",
                                "sample": f"unmodified reference generator, same script, calls 2..9, voices split "
                                          f"over {used} single-threaded processes; {wall:.2f} s wall"}
+    return leg
+
+
+def leg_c2(args, device, clocks):
+    """BASELINE config 2: the reference's examples/misc1-4fm_pm.sau -- ONE voice alive at a time, range-FM nested up
+    to three deep under a PM modulator (the few-voice case, where a GPU has nothing to spread over
+    voices).  The whole 60 s render through the public call with host PCM buffers, against the unmodified reference
+    on ONE host core (the reference is single-threaded and the script has one voice at a time)."""
+    import numpy as np
+    import torch
+    import saugns_b200
+    from saugns_b200 import workloads
+    prg = workloads.build_c2()
+    ncalls = (60 * SRATE + FRAMES - 1) // FRAMES
+    par = None if args.no_cpu else start_parity(workloads.C2_TEXT, ncalls)
+
+    def render_once():
+        t0 = time.perf_counter()
+        g = saugns_b200.Generator(prg, SRATE, device=device, max_call_len=FRAMES)
+        calls, more = [], True
+        while more:
+            more, pcm, n = g.run(FRAMES)
+            calls.append(pcm.copy())
+        g.close()
+        return time.perf_counter() - t0, calls
+
+    first_s, _ = render_once()
+    walls = []
+    for _ in range(3):
+        w, calls = render_once()
+        walls.append(w)
+    wall = sorted(walls)[1]
+    # the kernels alone, PCM left on the device
+    g = saugns_b200.Generator(prg, SRATE, device=device, max_call_len=FRAMES)
+    torch.cuda.synchronize()
+    g.set_timing(True)
+    t0 = time.perf_counter()
+    more, k = True, 0
+    while more:
+        more, _, n = g.run_device(FRAMES)
+        k += 1
+    torch.cuda.synchronize()
+    dev_s = time.perf_counter() - t0
+    rk, mk = g.kernel_ms()
+    g.close()
+    vs = 4 * 15 * SRATE                 # four voices of 15 s, one after the other
+    leg = {"metric": METRIC, "unit": "voice-samples/s", "value": vs / dev_s, "ms_per_step": 1e3 * dev_s / k,
+           "steps": k, "realtime_factor": 60.0 / dev_s,
+           "config": {"workload": "C2: examples/misc1-4fm_pm.sau, 60 s, one voice slot (four 15 s voices in turn), "
+                                  "7 / 4 / 5 / 5 operators with nested range-FM + PM; step = one 24576-frame call",
+                      "frames_per_step": FRAMES, "srate": SRATE},
+           "e2e": {"value": vs / wall, "unit": "voice-samples/s", "seconds_for_the_60_s_render": wall,
+                   "first_render_of_the_process_s": first_s, "h2d_bytes_per_step": program_bytes(prg) // k,
+                   "d2h_bytes_per_step": FRAMES * 2 * 2 + 8,
+                   "timed": "create + every call with a host PCM buffer + destroy, wall clock (median of 3)"},
+           "roofline": {"bound": "latency", "kernel": "render_kernel", "kernel_ms_per_launch": rk / k,
+                        "mix_kernel_ms_per_launch": mk / k,
+                        "note": "one voice alive: its team of warps spans several CTAs (DESIGN.md 3.1c); every member is "
+                                "a latency-bound chain, the HBM roofline does not apply"}}
+    if par is not None:
+        leg["parity"] = finish_parity(par, calls, "every call of the 60 s render against the reference")
+        secs = leg["parity"]["reference_seconds"]
+        leg["cpu_baseline"] = {"value": vs / secs, "unit": "voice-samples/s", "cores": 1, "kind": "reference",
+                               "seconds_for_the_60_s_render": secs,
+                               "sample": "unmodified reference generator (oracle/_ref), the whole script in one "
+                                         "process on one core (the reference is single-threaded)"}
+        leg["speedup_vs_one_core_e2e"] = secs / wall
     return leg
 
 

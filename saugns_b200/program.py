@@ -274,18 +274,25 @@ class ProgramBuilder:
         out.append(od)
         return op_id
 
-    def add_voice(self, carrier, wait_ms=0):
+    def add_voice(self, carrier, wait_ms=0, vo_id=None):
+        """wait_ms: time since the event before (a `|` in a script: the duration of what came before);
+        vo_id: the voice slot (the converter gives a voice that has ended its slot back: the voices of
+        `A | B | C` all live in slot 0, sau/parser/parseconv.h voice allocation); default: a slot of its own."""
         ops = []
         dur = carrier["time_ms"]
         carr_id = self._emit(carrier, "carr", 0, ops, dur)
-        self._events.append((wait_ms, ops, carr_id, dur))
+        self._events.append((wait_ms, ops, carr_id, dur, len(self._events) if vo_id is None else vo_id))
 
     def finish(self):
         """-> object with .ptr (address of the sauProgram) keeping memory alive."""
         nev = len(self._events)
         evs = (Event * max(nev, 1))()
         total_ms = 0
-        for vi, (wait_ms, ops, carr_id, dur) in enumerate(self._events):
+        start_ms = 0
+        vo_count = 0
+        for vi, (wait_ms, ops, carr_id, dur, vo_id) in enumerate(self._events):
+            start_ms += wait_ms
+            vo_count = max(vo_count, vo_id + 1)
             ods = (OpData * len(ops))()
             for k, od in enumerate(ops):
                 node = od["node"]
@@ -319,18 +326,18 @@ class ProgramBuilder:
             self._keep.append(ods)
             e = evs[vi]
             e.wait_ms = wait_ms
-            e.vo_id = vi
+            e.vo_id = vo_id
             e.carr_op_id = carr_id
             e.op_count = 0
             e.op_data_count = len(ops)
             e.op_list = None
             e.op_data = C.cast(ods, C.POINTER(OpData))
-            total_ms = max(total_ms, dur)
+            total_ms = max(total_ms, start_ms + dur)
         prg = Program()
         prg.events = C.cast(evs, C.POINTER(Event))
         prg.ev_count = nev
         prg.mode = PMODE_AMP_DIV_VOICES if self.amp_div_voices else 0
-        prg.vo_count = nev
+        prg.vo_count = vo_count
         prg.op_count = self._next_op
         prg.op_nest_depth = self._depth
         prg.duration_ms = total_ms

@@ -172,3 +172,55 @@ def synth_c5_script(index):
             lines.append(f"W{rnd.choice(WAVES)} f{f:.3f}[g{f * rnd.uniform(0.5, 2):.3f} "
                          f"l{rnd.choice(LINES)}] t{t:.3f} c{c:.3f} a1.r0[Wsin f{rnd.uniform(0.5, 9):.3f}]")
     return "\n".join(lines) + "\n"
+
+
+C2_TEXT = """Wsin t15 f500.r501[Wsin f1] p[
+	Wsin f400.r800[
+		Wsqr f1.r10[Wsin f5000]
+		Wtri f0.1.r10.0[Wsin f0.2]
+	]
+] |
+
+Wsin t15 f400.r500[Wsqr f10] p[
+	Wsin r1.22/2 a.5
+	Wsin f244 a.5
+] |
+
+Wsin t15 f600.r666[Wsin f2] p[
+	Wsin f400
+	Wsin f400.r500[Wsin f.1]
+] |
+
+Wsin t15 f222.r666[Wsin f0.1] p[
+	Wsin r2/1
+	Wsin r4/3
+	Wsin r3/7
+]
+"""
+
+
+def build_c2():
+    """BASELINE config 2 (the reference's examples/misc1-4fm_pm.sau, quoted above): four 15 s voices one after
+    the other in ONE voice slot, range-FM nested up to three deep under a PM modulator -- built without a script
+    front end (bench.py's product arm); the same program the reference's parser makes of the text."""
+    from saugns_b200 import program as P
+    B = P.ProgramBuilder
+    W = B.wave
+    r = lambda x: P.value(x, ratio=True)
+    pb = B(ampmult=1.0, amp_div_voices=True)
+    pb.add_voice(W("sin", time_ms=15000, freq=500.0, freq2=501.0, mods={
+        "rfmod": [W("sin", freq=1.0)],
+        "pmod": [W("sin", freq=400.0, freq2=800.0, mods={"rfmod": [
+            W("sqr", freq=1.0, freq2=10.0, mods={"rfmod": [W("sin", freq=5000.0)]}),
+            W("tri", freq=0.1, freq2=10.0, mods={"rfmod": [W("sin", freq=0.2)]})]})]}), vo_id=0)
+    pb.add_voice(W("sin", time_ms=15000, freq=400.0, freq2=500.0, mods={
+        "rfmod": [W("sqr", freq=10.0)],
+        "pmod": [W("sin", freq=r(1.22 / 2), amp=0.5), W("sin", freq=244.0, amp=0.5)]}), wait_ms=15000, vo_id=0)
+    pb.add_voice(W("sin", time_ms=15000, freq=600.0, freq2=666.0, mods={
+        "rfmod": [W("sin", freq=2.0)],
+        "pmod": [W("sin", freq=400.0),
+                 W("sin", freq=400.0, freq2=500.0, mods={"rfmod": [W("sin", freq=0.1)]})]}), wait_ms=15000, vo_id=0)
+    pb.add_voice(W("sin", time_ms=15000, freq=222.0, freq2=666.0, mods={
+        "rfmod": [W("sin", freq=0.1)],
+        "pmod": [W("sin", freq=r(2 / 1)), W("sin", freq=r(4 / 3)), W("sin", freq=r(3 / 7))]}), wait_ms=15000, vo_id=0)
+    return pb.finish()

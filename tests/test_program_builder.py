@@ -61,3 +61,17 @@ def test_builder_programs_render_identically_on_oracle_c4_c5(ref, port):
         a = port.render(prg, srate=48000, max_frames=48000)
         b = port.render(built, srate=48000, max_frames=48000)
         assert np.array_equal(a, b)
+
+
+def test_builder_c2_equals_the_parsed_script(ref, port):
+    """BASELINE config 2 (examples/misc1-4fm_pm.sau): four voices one after the other in ONE voice slot --
+    the builder's program is the parser's, field for field, and renders the same PCM."""
+    import json
+    import numpy as np
+    from saugns_b200 import workloads, program as P
+    import scripts
+    assert workloads.C2_TEXT.split() == scripts.C2_MISC1_4FM_PM.split()
+    built, parsed = workloads.build_c2(), ref.Program(workloads.C2_TEXT)
+    db, dp = P.dump(built.ptr), P.dump(parsed.ptr)
+    assert json.dumps(db, sort_keys=True, default=str) == json.dumps(dp, sort_keys=True, default=str)
+    assert np.array_equal(port.render(built, srate=96000), ref.render(parsed, srate=96000))
