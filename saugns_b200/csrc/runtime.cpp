@@ -683,6 +683,14 @@ static bool flatten_program(const sauabi_Program *prg, uint32_t srate, Flat &f) 
 	std::vector<uint32_t> &prog_ops = f.prog_ops, &vev_off = f.vev_off, &vev_idx = f.vev_idx;
 	events.assign(prg->ev_count, EventRec());
 	f.ev_handover.assign(prg->ev_count, 0u);
+	{
+		/* (one allocation each instead of a chain of doublings: a 4096-voice script has 12 288 op-data records) */
+		size_t nod = 0;
+		for (size_t i = 0; i < prg->ev_count; ++i) nod += prg->events[i].op_data_count;
+		opdata.reserve(nod);
+		code.reserve(4 * nod + 4 * prg->ev_count);
+		prog_ops.reserve(nod + prg->ev_count);
+	}
 	std::vector<uint32_t> op_voice(prg->op_count, 0xffffffffu);   /* voice an operator was last touched under */
 	std::vector<HostOp> hops(prg->op_count);
 	std::vector<std::vector<uint32_t>> vev(prg->vo_count);
