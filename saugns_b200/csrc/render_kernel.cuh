@@ -421,7 +421,15 @@ __device__ __forceinline__ void render_body(const CallDesc *calls, uint32_t ncal
 		/* one warp (or, with few voices, a team of warps: render_team.cuh) renders every unit
 		 * of one voice; task -> (call, voice) by binary search on task_base */
 		const uint32_t per_cta = warps_per_cta / team;
-		const uint32_t team_i = warp / team, rank = warp - team_i * team;
+		uint32_t team_i = warp / team;
+		const uint32_t rank = warp - team_i * team;
+		if (team == 1u) {
+			/* Voices of a script tend to alternate in kind (C3: PM chain / range-FM) while a warp's scheduler
+			 * is its number mod 4: every other PAIR of warps swaps its voices, so that the dearer kind does
+			 * not pile up on two of the SM's four schedulers. */
+			const uint32_t sw = team_i ^ (((team_i >> 1) ^ (team_i >> 2)) & 1u);
+			if (sw < per_cta) team_i = sw;
+		}
 		if (team_i >= per_cta) return;
 		const uint32_t task = (blockIdx.x / multi) * per_cta + team_i;
 		if (task >= ntasks) return;
