@@ -397,14 +397,18 @@ __device__ __forceinline__ void run_chunk_lowered(const HotCtx &c) {
 			} else {
 				fld<4>(c, bufa, sv);
 			}
-			const float pan = lds32f(p0.z + OS_LINE + 16 * LINE_PAN);
-			const uint4 h1 = lds128u(c.plan + 16);         /* wave mask, amp_scale, write_r, tile stride */
-			const uint4 h2 = lds128u(c.plan + PH_ROW_S);   /* the voice's rows */
-			const float amp_scale = __uint_as_float(h1.y);
-			const uint32_t write_r = h1.z, tstride = h1.w;
-			float *row_s = reinterpret_cast<float*>((uint64_t) h2.x | ((uint64_t) h2.y << 32));
-			float *row_r = reinterpret_cast<float*>((uint64_t) h2.z | ((uint64_t) h2.w << 32));
-			const uint32_t frame = lds32(c.plan + PH_FRAME0) + c.oc;
+			const uint4 h1 = lds128u(c.plan + PH_ROW_S);   /* the s row, tile stride, frame0 | write_r << 31 */
+			const float2 h2 = lds64f(c.plan + PH_AMP_SCALE);       /* amp_scale, the static pan */
+			const float amp_scale = h2.x, pan = h2.y;
+			const uint32_t write_r = h1.w >> 31, tstride = h1.z;
+			float *row_s = reinterpret_cast<float*>((uint64_t) h1.x | ((uint64_t) h1.y << 32));
+			float *row_r = nullptr;
+			if (write_r) {
+				uint2 rr;
+				asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(rr.x), "=r"(rr.y) : "r"(c.plan + PH_ROW_R));
+				row_r = reinterpret_cast<float*>((uint64_t) rr.x | ((uint64_t) rr.y << 32));
+			}
+			const uint32_t frame = (h1.w & 0x7fffffffu) + c.oc;
 			float s[4], rv[4];
 #pragma unroll
 			for (int k = 0; k < 4; ++k) { s[k] = sv[k] * amp_scale; rv[k] = s[k] * pan; }
@@ -524,29 +528,31 @@ struct FVout {
 	static constexpr uint32_t SLOTS = 1;
 	static constexpr uint16_t CODE = 0x3000u | (SRCVAL ? 0x200u : 0u);
 	static __device__ __forceinline__ void exec(const HotCtx &c, const uint32_t rec, float val[4]) {
-		const uint4 p0 = lds128u(rec);
-		const uint32_t bufa = (p0.x >> 16) & 0xffu;
 		float sv[4];
 		if (SRCVAL) {
 #pragma unroll
 			for (int k = 0; k < 4; ++k) sv[k] = val[k];
 		} else {
-			fld<4>(c, bufa, sv);
+			fld<4>(c, (lds32(rec) >> 16) & 0xffu, sv);
 		}
-		const float pan = lds32f(p0.z + OS_LINE + 16 * LINE_PAN);
-		const uint4 h1 = lds128u(c.plan + 16);
-		const uint4 h2 = lds128u(c.plan + PH_ROW_S);
-		const float amp_scale = __uint_as_float(h1.y);
-		const uint32_t write_r = h1.z, tstride = h1.w;
-		float *row_s = reinterpret_cast<float*>((uint64_t) h2.x | ((uint64_t) h2.y << 32));
-		float *row_r = reinterpret_cast<float*>((uint64_t) h2.z | ((uint64_t) h2.w << 32));
-		const uint32_t frame = lds32(c.plan + PH_FRAME0) + c.oc;
+		/* two loads from the plan header's output slot (render_plan.cuh:PH_ROW_S), not the record */
+		const uint4 h1 = lds128u(c.plan + PH_ROW_S);
+		const float2 h2 = lds64f(c.plan + PH_AMP_SCALE);
+		const float amp_scale = h2.x, pan = h2.y;
+		const uint32_t write_r = h1.w >> 31, tstride = h1.z;
+		float *row_s = reinterpret_cast<float*>((uint64_t) h1.x | ((uint64_t) h1.y << 32));
+		const uint32_t frame = (h1.w & 0x7fffffffu) + c.oc;
 		float s[4], rv[4];
 #pragma unroll
 		for (int k = 0; k < 4; ++k) { s[k] = sv[k] * amp_scale; rv[k] = s[k] * pan; }
 		const size_t at = row_index(frame + c.lane * 4, tstride);       /* (fused plans: aligned frames only) */
 		__stcs(reinterpret_cast<float4*>(row_s + at), make_float4(s[0], s[1], s[2], s[3]));
-		if (write_r) __stcs(reinterpret_cast<float4*>(row_r + at), make_float4(rv[0], rv[1], rv[2], rv[3]));
+		if (write_r) {
+			uint2 rr;
+			asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(rr.x), "=r"(rr.y) : "r"(c.plan + PH_ROW_R));
+			float *row_r = reinterpret_cast<float*>((uint64_t) rr.x | ((uint64_t) rr.y << 32));
+			__stcs(reinterpret_cast<float4*>(row_r + at), make_float4(rv[0], rv[1], rv[2], rv[3]));
+		}
 	}
 };
 

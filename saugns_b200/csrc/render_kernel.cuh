@@ -193,11 +193,12 @@ __device__ __noinline__ void render_units(Ctx &c, FastCtx &fc, const CallDesc *c
 					/* plan header: what the rare paths and VOUT need */
 					const uint64_t tp = reinterpret_cast<uint64_t>(fc.tab), wp = reinterpret_cast<uint64_t>(fc.wc);
 					plan_put(fc.plan, 0, (uint32_t) tp, (uint32_t) (tp >> 32), (uint32_t) wp, (uint32_t) (wp >> 32),
-							__uint_as_float(fc.wave_mask), fc.amp_scale, __uint_as_float(fc.write_r),
-							__uint_as_float(c.tstride));
+							__uint_as_float(fc.wave_mask), fc.coeff, 0.f, 0.f);
 					const uint64_t rs = reinterpret_cast<uint64_t>(row_s), rr = reinterpret_cast<uint64_t>(row_r);
-					plan_put(fc.plan, 1, (uint32_t) rs, (uint32_t) (rs >> 32), (uint32_t) rr, (uint32_t) (rr >> 32),
-							__uint_as_float(sd.start + off), fc.coeff, 0.f, 0.f);
+					plan_put(fc.plan, 1, (uint32_t) rs, (uint32_t) (rs >> 32), c.tstride,
+							(sd.start + off) | (fc.write_r ? 0x80000000u : 0u),
+							fc.amp_scale, op_ptr(c, vs.carr_slot)->line[LINE_PAN].v0,
+							__uint_as_float((uint32_t) rr), __uint_as_float((uint32_t) (rr >> 32)));
 					__syncwarp();
 				}
 				if (fc.wave_mask & CTAB_FLAG) {

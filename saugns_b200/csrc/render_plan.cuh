@@ -601,8 +601,11 @@ struct HotCtx {
 };
 /* plan header (PLAN_HDR bytes): the cold paths' context, VOUT's constants, the voice's rows and
  * the frame of the stretch's first sample */
-constexpr uint32_t PH_TAB = 0, PH_WC = 8, PH_WAVE_MASK = 16, PH_AMP_SCALE = 20, PH_WRITE_R = 24,
-	PH_TSTRIDE = 28, PH_ROW_S = 32, PH_ROW_R = 40, PH_FRAME0 = 48, PH_COEFF = 52;
+/* slot 1 is the voice output's: what every chunk needs in ONE 128-bit load (the s row, the tile stride, the frame
+ * of the stretch's first sample with "the r row is written" in bit 31) + one 64-bit load (amp_scale, the static
+ * pan), then the r row */
+constexpr uint32_t PH_TAB = 0, PH_WC = 8, PH_WAVE_MASK = 16, PH_COEFF = 20,
+	PH_ROW_S = 32, PH_TSTRIDE = 40, PH_FRAME0 = 44, PH_AMP_SCALE = 48, PH_PAN = 52, PH_ROW_R = 56;
 template <int NS>
 __device__ __forceinline__ void fld(const HotCtx &c, uint32_t buf, float v[NS]) {
 	const uint32_t a = c.sb + buf * FastCfg<NS>::FBUF_BYTES;
@@ -1091,7 +1094,7 @@ __device__ __forceinline__ bool plan_record_generic(const HotCtx &c, uint32_t &r
 		const float pan = lds32f(op + OS_LINE + 16 * LINE_PAN);
 		float s[NS], rv[NS];
 		const float amp_scale = lds32f(c.plan + PH_AMP_SCALE);
-		const uint32_t write_r = lds32(c.plan + PH_WRITE_R);
+		const uint32_t write_r = lds32(c.plan + PH_FRAME0) >> 31;
 		const uint32_t tstride = lds32(c.plan + PH_TSTRIDE);
 #pragma unroll
 		for (int k = 0; k < NS; ++k) { s[k] = sv[k] * amp_scale; rv[k] = s[k] * pan; }
